@@ -1,0 +1,669 @@
+/* cib_oracle.c - CPU ORACLE (test infrastructure, NOT product code). See cib_oracle.h.
+ *
+ * Literal restatement of the reference's uniform-grid hot path.  Every function cites the
+ * reference file:line it follows (paths relative to /root/reference/src).  Compile with
+ * -ffp-contract=off: the reference (Julia without @fastmath) never contracts a*b+c.
+ *
+ * Known places where bit-equality with Julia is not knowable from the source and the oracle
+ * makes a stated choice (all at the 1-ulp-of-a-term level, far below the 1e-12 budget):
+ *   - sum(slice)/n            Julia mapreduce is @simd-reassociated; here: sequential sum
+ *   - mul!(ghost, M, y)       OpenBLAS gemv order unspecified; here: sequential over columns
+ *   - x^n for n>=4, exp       Julia's own pow_body / exp; here: pow_body restated, libm exp
+ */
+#include "cib_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "oracle_tables.inc"
+
+#define N_PRE 101
+
+static int g_threads = 1;
+void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+int orc_get_threads(void) { return g_threads; }
+
+/* data_structures/degree_to_equations.jl:13-25 */
+int orc_eqs(int kernel) {
+  switch (kernel) {
+    case ORC_K_B5: return 5;
+    case ORC_K_B7: return 6;
+    case ORC_K_B9: return 7;
+    case ORC_K_B11: return 8;
+    case ORC_K_B13: return 9;
+    default: return -1;
+  }
+}
+
+int orc_max_table_derivative(int kernel) {
+  switch (kernel) {
+    case ORC_K_B5: return 3;
+    case ORC_K_B7: return 4;
+    case ORC_K_B9: return 5;
+    case ORC_K_B11: return 6;
+    case ORC_K_B13: return 6;
+    default: return -1;
+  }
+}
+
+/* precomputed_kernels/precomputed_kernel_tables.jl:18-249: kernel_pre = K^(d), kernel_d1_pre = K^(d+1) */
+const double *orc_table(int kernel, int d) {
+  static const double *const b5[] = {CIB_TAB_b5_d0, CIB_TAB_b5_d1, CIB_TAB_b5_d2, CIB_TAB_b5_d3};
+  static const double *const b7[] = {CIB_TAB_b7_d0, CIB_TAB_b7_d1, CIB_TAB_b7_d2, CIB_TAB_b7_d3,
+                                     CIB_TAB_b7_d4};
+  static const double *const b9[] = {CIB_TAB_b9_d0, CIB_TAB_b9_d1, CIB_TAB_b9_d2,
+                                     CIB_TAB_b9_d3, CIB_TAB_b9_d4, CIB_TAB_b9_d5};
+  static const double *const b11[] = {CIB_TAB_b11_d0, CIB_TAB_b11_d1, CIB_TAB_b11_d2, CIB_TAB_b11_d3,
+                                      CIB_TAB_b11_d4, CIB_TAB_b11_d5, CIB_TAB_b11_d6};
+  static const double *const b13[] = {CIB_TAB_b13_d0, CIB_TAB_b13_d1, CIB_TAB_b13_d2, CIB_TAB_b13_d3,
+                                      CIB_TAB_b13_d4, CIB_TAB_b13_d5, CIB_TAB_b13_d6};
+  if (d < 0 || d > orc_max_table_derivative(kernel)) return NULL;
+  switch (kernel) {
+    case ORC_K_B5: return b5[d];
+    case ORC_K_B7: return b7[d];
+    case ORC_K_B9: return b9[d];
+    case ORC_K_B11: return b11[d];
+    case ORC_K_B13: return b13[d];
+    default: return NULL;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Julia Base: ^(x::Float64, n::Integer) -> pow_body (base/math.jl, Julia >= 1.8), restated.
+ * n == 0 -> 1 ; n == 3 -> x*x*x ; otherwise compensated power by squaring.
+ * ------------------------------------------------------------------------------------------- */
+static double jl_pow_int(double x, int64_t n) {
+  if (n == 0) return 1.0;
+  double y = 1.0, xnlo = -0.0, ynlo = 0.0;
+  if (n == 3) return x * x * x;
+  if (n < 0) {
+    double rx = 1.0 / x;
+    if (n == -2) return rx * rx;
+    if (isfinite(x)) xnlo = -fma(x, rx, -1.0) * rx;
+    x = rx;
+    n = -n;
+  }
+  while (n > 1) {
+    if (n & 1) {
+      double err = fma(y, xnlo, x * ynlo);
+      double p = x * y;
+      ynlo = fma(x, y, -p);
+      y = p;
+      ynlo += err;
+    }
+    double err = x * 2 * xnlo;
+    double p = x * x;
+    xnlo = fma(x, x, -p);
+    x = p;
+    xnlo += err;
+    n >>= 1;
+  }
+  double err = fma(y, xnlo, x * ynlo);
+  if (isfinite(x) && isfinite(err)) return fma(x, y, err);
+  return x * y;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Ghost matrices: convolution_coefs/polynomial_boundary.jl:29-131 (POLYNOMIAL_GHOST_COEFFS),
+ * :157-179 (LINEAR/QUADRATIC).  Every row j is the Lagrange extrapolation to x = -j from the
+ * nodes 0..m-1 (m = 2 linear, 3 quadratic, 6 for b5, 8 for b7..b13); regenerated here in exact
+ * integer arithmetic and compared with the reference's literals in tests/test_oracle_kat.py.
+ * ------------------------------------------------------------------------------------------- */
+static void lagrange_row(int m, int j, double *row) {
+  for (int k = 0; k < m; ++k) {
+    int64_t num = 1, den = 1;
+    for (int i = 0; i < m; ++i) {
+      if (i == k) continue;
+      num *= (int64_t)(-j - i);
+      den *= (int64_t)(k - i);
+    }
+    row[k] = (double)(num / den); /* exact: the quotient is an integer */
+  }
+}
+
+static int poly_ncol(int kernel) { return kernel == ORC_K_B5 ? 6 : 8; }
+
+/* exported for the KAT test: fills rows x ncol (row-major), returns ncol */
+int orc_ghost_matrix(int which /*0 poly,1 linear,2 quadratic*/, int kernel, int rows, double *out) {
+  int m = which == 1 ? 2 : which == 2 ? 3 : poly_ncol(kernel);
+  for (int j = 1; j <= rows; ++j) lagrange_row(m, j, out + (size_t)(j - 1) * m);
+  return m;
+}
+
+/* One side of one boundary line.
+ * convolution_coefs/create_convolutional_coefs.jl:232-299 (left), :302-369 (right),
+ * fill_ghost_points_polynomial! :408-441, fill_ghost_points_gaussian! :443-494.
+ * s = mean-centred slice in natural (left-to-right) order, n points.  gv[j-1] = ghost j. */
+static void ghost_side(const double *s, int64_t n, double y_mean, double h, int eqs, int kernel,
+                       int bc, int gaussian, int right, double *gv) {
+  const int ng = eqs - 1;
+  if (gaussian) {
+    /* :443-494 ; n_fit = min(max(6, eqs ÷ 3), n) */
+    int64_t n_fit = eqs / 3 > 6 ? eqs / 3 : 6;
+    if (n_fit > n) n_fit = n;
+    double sx = 0, sy = 0, sxx = 0, sxy = 0;
+    for (int64_t k = 1; k <= n_fit; ++k) {
+      double xk = (double)k;
+      double yk = right ? s[n - k] : s[k - 1];
+      sx += xk;
+      sy += yk;
+      sxx += xk * xk;
+      sxy += xk * yk;
+    }
+    double nf = (double)n_fit;
+    double denom = nf * sxx - sx * sx;
+    double b = (nf * sxy - sx * sy) / denom;
+    double a = (sy - b * sx) / nf;
+    for (int k = 1; k <= ng; ++k) {
+      double y_temp = a + b * (double)(1 - k) - y_mean; /* :463 */
+      gv[k - 1] = y_mean + y_temp;                      /* :469 */
+    }
+    return;
+  }
+  const int n_interior = poly_ncol(kernel); /* size(ghost_matrix, 2), :225 */
+  const int few_points = n < n_interior;     /* :226 */
+  int use_poly;
+  if (few_points || !(bc == ORC_BC_DETECT || bc == ORC_BC_POLY)) {
+    use_poly = 0; /* :247-248 */
+  } else {
+    const int ns = n_interior;
+    const double *p = right ? s + (n - ns) : s; /* last / first ns points, natural order */
+    double d1[8], d2[8];
+    double mn1 = INFINITY, mx1 = -INFINITY;
+    for (int d = 1; d <= ns - 1; ++d) {
+      double v = p[d] - p[d - 1];
+      d1[d - 1] = v;
+      mn1 = fmin(mn1, v);
+      mx1 = fmax(mx1, v);
+    }
+    int periodic = (mn1 * mx1) / (h * h) < -1.0 / 10; /* :259 */
+    double mn2 = INFINITY, mx2 = -INFINITY;
+    for (int d = 1; d <= ns - 2; ++d) {
+      double v = d1[d] - d1[d - 1];
+      d2[d - 1] = v;
+      mn2 = fmin(mn2, v);
+      mx2 = fmax(mx2, v);
+    }
+    int high_curv = fabs(mx2 - mn2) / h > 1.0 / 2; /* :268 */
+    int high_d3 = 0;
+    if (ns > 4) {
+      double mn3 = INFINITY, mx3 = -INFINITY;
+      for (int d = 1; d <= ns - 3; ++d) {
+        double v = d2[d] - d2[d - 1];
+        mn3 = fmin(mn3, v);
+        mx3 = fmax(mx3, v);
+      }
+      high_d3 = fabs(mx3 - mn3) / h > 1.0 / 2; /* :277 */
+    }
+    use_poly = (bc == ORC_BC_POLY) || (bc == ORC_BC_DETECT && !periodic && !high_curv && !high_d3);
+  }
+  int m; /* matrix columns */
+  if (use_poly) m = n_interior;                        /* :286-287 */
+  else if (bc == ORC_BC_LINEAR) m = 2;                 /* :290-292 */
+  else if (bc == ORC_BC_QUADRATIC) m = 3;
+  else m = 2;                                          /* :293-295 fallback -> linear */
+  double y[8], row[8];
+  for (int k = 1; k <= m; ++k) y[k - 1] = right ? s[n - k] : s[k - 1]; /* :428-430 reversal */
+  for (int j = 1; j <= ng; ++j) {
+    lagrange_row(m, j, row);
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) acc += row[k] * y[k];
+    gv[j - 1] = y_mean + acc; /* :424 / :438 */
+  }
+}
+
+/* one full line: both sides.  line0 -> first interior element, stride in elements.
+ * ghost j is written at first_interior - (j + shift) / last_interior + (j + shift):
+ * shift = 0 for the interpolant and resample; shift = 1 reproduces convolution_smooth's
+ * buffer (padding E instead of E-1 => get_boundary_indices lands one slot outside the
+ * interior, create_convolutional_coefs.jl:77-81 with convolution_gaussian_smoothing.jl:83-105). */
+static void ghost_fill_line(double *line0, int64_t stride, int64_t n, double h, int eqs, int kernel,
+                            int bc_l, int bc_r, int gaussian, int shift, double *slice) {
+  double gv[32 + 64];
+  double *gvp = gv;
+  double *heap = NULL;
+  if (eqs - 1 > 96) { heap = (double *)malloc(sizeof(double) * (size_t)(eqs - 1)); gvp = heap; }
+  for (int side = 0; side < 2; ++side) {
+    for (int64_t j = 0; j < n; ++j) slice[j] = line0[j * stride]; /* :233-239 / :303-309 */
+    double sum = 0.0;
+    for (int64_t j = 0; j < n; ++j) sum += slice[j];
+    double y_mean = sum / (double)n; /* :242 */
+    for (int64_t j = 0; j < n; ++j) slice[j] -= y_mean;
+    ghost_side(slice, n, y_mean, h, eqs, kernel, side ? bc_r : bc_l, gaussian, side, gvp);
+    for (int j = 1; j <= eqs - 1; ++j) {
+      if (side == 0) line0[-(int64_t)(j + shift) * stride] = gvp[j - 1];
+      else line0[(n - 1 + j + shift) * stride] = gvp[j - 1];
+    }
+  }
+  free(heap);
+}
+
+/* create_convolutional_coefs.jl:141-160 */
+int orc_create_coefs(int ndim, const int64_t *n, const double *vs, const double *h,
+                     const int32_t *kernel, const int32_t *bc_left, const int32_t *bc_right,
+                     double *c) {
+  if (ndim < 1 || ndim > ORC_MAXDIM) return ORC_EARG;
+  int eqs[ORC_MAXDIM];
+  int64_t cs[ORC_MAXDIM], cstride[ORC_MAXDIM];
+  int64_t ctot = 1, vtot = 1, nmax = 0;
+  for (int d = 0; d < ndim; ++d) {
+    eqs[d] = orc_eqs(kernel[d]);
+    if (eqs[d] < 0) return ORC_EARG;
+    cs[d] = n[d] + 2 * (eqs[d] - 1);
+    cstride[d] = ctot;
+    ctot *= cs[d];
+    vtot *= n[d];
+    if (n[d] > nmax) nmax = n[d];
+  }
+  memset(c, 0, sizeof(double) * (size_t)ctot);
+  /* interior copy :143-145 */
+  for (int64_t lin = 0; lin < vtot; ++lin) {
+    int64_t rem = lin, off = 0;
+    for (int d = 0; d < ndim; ++d) {
+      int64_t id = rem % n[d];
+      rem /= n[d];
+      off += (id + eqs[d] - 1) * cstride[d];
+    }
+    c[off] = vs[lin];
+  }
+  /* axis by axis, over the FULL padded extent of the other axes (:77-81, :151-158) */
+  for (int fd = 0; fd < ndim; ++fd) {
+    int64_t nlines = ctot / cs[fd];
+#pragma omp parallel num_threads(g_threads)
+    {
+      double *slice = (double *)malloc(sizeof(double) * (size_t)nmax);
+#pragma omp for schedule(static)
+      for (int64_t ln = 0; ln < nlines; ++ln) {
+        int64_t rem = ln, off = 0;
+        for (int d = 0; d < ndim; ++d) {
+          if (d == fd) continue;
+          int64_t id = rem % cs[d];
+          rem /= cs[d];
+          off += id * cstride[d];
+        }
+        off += (int64_t)(eqs[fd] - 1) * cstride[fd];
+        ghost_fill_line(c + off, cstride[fd], n[fd], h[fd], eqs[fd], kernel[fd], bc_left[fd],
+                        bc_right[fd], 0, 0, slice);
+      }
+      free(slice);
+    }
+  }
+  return ORC_OK;
+}
+
+/* convolution_fast_interpolation/cubic_hermite_interpolation.jl:15-28 */
+static inline double cubic_hermite(double t, double f0, double f1, double d0, double d1, double h) {
+  double t2 = t * t;
+  double h00 = 1.0 + t2 * (-3.0 + 2.0 * t);
+  double h01 = t2 * (3.0 - 2.0 * t);
+  double h10 = t + t2 * (-2.0 + t);
+  double h11 = t2 * (t - 1.0);
+  return h00 * f0 + h01 * f1 + h * (h10 * d0 + h11 * d1);
+}
+
+typedef struct {
+  int64_t i;   /* 1-based cell index into the extended knots / padded coefs */
+  int64_t idx; /* 1-based lower table row */
+  double t;
+} axis_pos;
+
+/* eager_3d.jl:115-137 (same lines in eager_1d.jl:60-71, eager_2d.jl:138-156, perdim_2d.jl:17-49).
+ * returns 0 ok, 1 if floor(Int, .) would throw InexactError (NaN / Inf) */
+static inline int locate(double x, const double *knots, int64_t nk, double h, int eqs, axis_pos *p) {
+  double i_float = (x - knots[0]) / h + 1.0;
+  if (!(fabs(i_float) < 9.0e18)) return 1;
+  int64_t i = (int64_t)floor(i_float);
+  if (i < eqs) i = eqs;
+  if (i > nk - eqs) i = nk - eqs;
+  double x_diff_right = 1.0 - (x - knots[i - 1]) / h;
+  double cidx = x_diff_right * (double)(N_PRE - 1) + 1.0;
+  if (!(fabs(cidx) < 9.0e18)) return 1;
+  int64_t idx = (int64_t)floor(cidx);
+  if (idx < 1) idx = 1;
+  if (idx > N_PRE - 1) idx = N_PRE - 1;
+  p->i = i;
+  p->idx = idx;
+  p->t = cidx - (double)idx;
+  return 0;
+}
+
+typedef struct {
+  const double *kp[3];
+  const double *kd[3];
+  int eqs[3];
+} itp_tabs;
+
+#define TAB(T, row1, col1, eqs) ((T)[((row1)-1) * 2 * (eqs) + ((col1)-1)])
+
+/* the un-wrapped functor itp(x...) : eager_1d.jl:92-115, eager_2d.jl:136-212 / perdim_2d.jl:182-215,
+ * eager_3d.jl:181-305 / perdim_3d.jl:12-159 */
+static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, double *res) {
+  const double h_pre = 1.0 / (double)(N_PRE - 1);
+  axis_pos p[3];
+  for (int d = 0; d < it->ndim; ++d)
+    if (locate(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d])) return ORC_ENAN;
+
+  if (it->ndim == 1) {
+    const int e = tb->eqs[0];
+    double sum_f0 = 0, sum_f1 = 0, sum_di0 = 0, sum_di1 = 0;
+    for (int j = -(e - 1); j <= e; ++j) {
+      double coef = it->coefs[p[0].i + j - 1];
+      int col = j + e;
+      sum_f0 += coef * TAB(tb->kp[0], p[0].idx, col, e);
+      sum_f1 += coef * TAB(tb->kp[0], p[0].idx + 1, col, e);
+      sum_di0 += coef * TAB(tb->kd[0], p[0].idx, col, e);
+      sum_di1 += coef * TAB(tb->kd[0], p[0].idx + 1, col, e);
+    }
+    double result = cubic_hermite(p[0].t, sum_f0, sum_f1, sum_di0, sum_di1, h_pre);
+    double scale = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
+    *res = result * scale;
+    return ORC_OK;
+  }
+
+  if (it->ndim == 2) {
+    const int ex = tb->eqs[0], ey = tb->eqs[1];
+    const int64_t s1 = it->cshape[0];
+    double s[2][2][2][2]; /* [x-type][y-type][x-bracket][y-bracket], type 0=f 1=d */
+    memset(s, 0, sizeof s);
+    for (int m = -(ey - 1); m <= ey; ++m) {
+      int col_y = m + ey;
+      double ky[2][2] = {{TAB(tb->kp[1], p[1].idx, col_y, ey), TAB(tb->kp[1], p[1].idx + 1, col_y, ey)},
+                         {TAB(tb->kd[1], p[1].idx, col_y, ey), TAB(tb->kd[1], p[1].idx + 1, col_y, ey)}};
+      for (int l = -(ex - 1); l <= ex; ++l) {
+        double coef = it->coefs[(p[0].i + l - 1) + (p[1].i + m - 1) * s1];
+        int col_x = l + ex;
+        double kx[2][2] = {{TAB(tb->kp[0], p[0].idx, col_x, ex), TAB(tb->kp[0], p[0].idx + 1, col_x, ex)},
+                           {TAB(tb->kd[0], p[0].idx, col_x, ex), TAB(tb->kd[0], p[0].idx + 1, col_x, ex)}};
+        for (int tx = 0; tx < 2; ++tx)
+          for (int ty = 0; ty < 2; ++ty)
+            for (int bx = 0; bx < 2; ++bx)
+              for (int by = 0; by < 2; ++by) s[tx][ty][bx][by] += coef * kx[tx][bx] * ky[ty][by];
+      }
+    }
+    double val_y0 = cubic_hermite(p[0].t, s[0][0][0][0], s[0][0][1][0], s[1][0][0][0], s[1][0][1][0], h_pre);
+    double val_y1 = cubic_hermite(p[0].t, s[0][0][0][1], s[0][0][1][1], s[1][0][0][1], s[1][0][1][1], h_pre);
+    double dval_y0 = cubic_hermite(p[0].t, s[0][1][0][0], s[0][1][1][0], s[1][1][0][0], s[1][1][1][0], h_pre);
+    double dval_y1 = cubic_hermite(p[0].t, s[0][1][0][1], s[0][1][1][1], s[1][1][0][1], s[1][1][1][1], h_pre);
+    double result = cubic_hermite(p[1].t, val_y0, val_y1, dval_y0, dval_y1, h_pre);
+    double sc0 = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
+    double sc1 = jl_pow_int(-1.0 / it->h[1], it->deriv[1]);
+    if (it->perdim) { /* perdim_2d.jl:24-30,214: result * (1*sc0*sc1) */
+      double sc = 1.0;
+      sc *= sc0;
+      sc *= sc1;
+      *res = result * sc;
+    } else { /* eager_2d.jl:212 */
+      *res = result * sc0 * sc1;
+    }
+    return ORC_OK;
+  }
+
+  /* 3-D */
+  const int ex = tb->eqs[0], ey = tb->eqs[1], ez = tb->eqs[2];
+  const int64_t s1 = it->cshape[0], s2 = it->cshape[0] * it->cshape[1];
+  double s[2][2][2][2][2][2]; /* [xt][yt][zt][bx][by][bz] */
+  memset(s, 0, sizeof s);
+  for (int n = -(ez - 1); n <= ez; ++n) {
+    int col_z = n + ez;
+    double kz[2][2] = {{TAB(tb->kp[2], p[2].idx, col_z, ez), TAB(tb->kp[2], p[2].idx + 1, col_z, ez)},
+                       {TAB(tb->kd[2], p[2].idx, col_z, ez), TAB(tb->kd[2], p[2].idx + 1, col_z, ez)}};
+    for (int m = -(ey - 1); m <= ey; ++m) {
+      int col_y = m + ey;
+      double ky[2][2] = {{TAB(tb->kp[1], p[1].idx, col_y, ey), TAB(tb->kp[1], p[1].idx + 1, col_y, ey)},
+                         {TAB(tb->kd[1], p[1].idx, col_y, ey), TAB(tb->kd[1], p[1].idx + 1, col_y, ey)}};
+      for (int l = -(ex - 1); l <= ex; ++l) {
+        double coef = it->coefs[(p[0].i + l - 1) + (p[1].i + m - 1) * s1 + (p[2].i + n - 1) * s2];
+        int col_x = l + ex;
+        double kx[2][2] = {{TAB(tb->kp[0], p[0].idx, col_x, ex), TAB(tb->kp[0], p[0].idx + 1, col_x, ex)},
+                           {TAB(tb->kd[0], p[0].idx, col_x, ex), TAB(tb->kd[0], p[0].idx + 1, col_x, ex)}};
+        for (int tx = 0; tx < 2; ++tx)
+          for (int bx = 0; bx < 2; ++bx) {
+            double cx = coef * kx[tx][bx];
+            for (int ty = 0; ty < 2; ++ty)
+              for (int by = 0; by < 2; ++by) {
+                double cxy = cx * ky[ty][by];
+                for (int tz = 0; tz < 2; ++tz)
+                  for (int bz = 0; bz < 2; ++bz) s[tx][ty][tz][bx][by][bz] += cxy * kz[tz][bz];
+              }
+          }
+      }
+    }
+  }
+  double v[2][2][2][2]; /* [yt][zt][by][bz] */
+  for (int ty = 0; ty < 2; ++ty)
+    for (int tz = 0; tz < 2; ++tz)
+      for (int by = 0; by < 2; ++by)
+        for (int bz = 0; bz < 2; ++bz)
+          v[ty][tz][by][bz] = cubic_hermite(p[0].t, s[0][ty][tz][0][by][bz], s[0][ty][tz][1][by][bz],
+                                            s[1][ty][tz][0][by][bz], s[1][ty][tz][1][by][bz], h_pre);
+  double w[2][2]; /* [zt][bz] */
+  for (int tz = 0; tz < 2; ++tz)
+    for (int bz = 0; bz < 2; ++bz)
+      w[tz][bz] = cubic_hermite(p[1].t, v[0][tz][0][bz], v[0][tz][1][bz], v[1][tz][0][bz], v[1][tz][1][bz], h_pre);
+  double result = cubic_hermite(p[2].t, w[0][0], w[0][1], w[1][0], w[1][1], h_pre);
+  *res = result * jl_pow_int(-1.0 / it->h[0], it->deriv[0]) * jl_pow_int(-1.0 / it->h[1], it->deriv[1]) *
+         jl_pow_int(-1.0 / it->h[2], it->deriv[2]);
+  return ORC_OK;
+}
+
+/* extrapolation_operator.jl:31-63 + extrapolate_point.jl:41-94 (1-D), :98-160 (N-D) */
+static int etp_point(const orc_itp *it, const itp_tabs *tb, const double *x, double *res) {
+  const int N = it->ndim;
+  double lo[3], hi[3];
+  int within = 1;
+  for (int d = 0; d < N; ++d) { /* _domain_bounds, extrapolate_point.jl:172-176 */
+    lo[d] = it->knots[d][tb->eqs[d] - 1];
+    hi[d] = it->knots[d][it->cshape[d] - 1 - (tb->eqs[d] - 1)];
+  }
+  for (int d = 0; d < N; ++d)
+    if (x[d] > hi[d] || x[d] < lo[d]) { within = 0; break; }
+  if (within) return itp_core(it, tb, x, res);
+  double cl[3];
+  for (int d = 0; d < N; ++d) cl[d] = x[d] < lo[d] ? lo[d] : (x[d] > hi[d] ? hi[d] : x[d]);
+  if (it->extrap == ORC_EXTRAP_LINE) {
+    double dx[3], dist_sq = 0.0;
+    for (int d = 0; d < N; ++d) {
+      dx[d] = x[d] - cl[d];
+      dist_sq += dx[d] * dx[d];
+    }
+    if (dist_sq < 2.220446049250313e-16) return itp_core(it, tb, cl, res);
+    double h_min = it->h[0];
+    for (int d = 1; d < N; ++d) h_min = it->h[d] < h_min ? it->h[d] : h_min;
+    double eps = h_min / 100.0;
+    double dist = sqrt(dist_sq);
+    double xin[3];
+    for (int d = 0; d < N; ++d) xin[d] = cl[d] - eps * dx[d] / dist;
+    double f_b, f_in;
+    int rc = itp_core(it, tb, cl, &f_b);
+    if (rc) return rc;
+    rc = itp_core(it, tb, xin, &f_in);
+    if (rc) return rc;
+    double slope = (f_b - f_in) / eps;
+    *res = f_b + slope * dist;
+    return ORC_OK;
+  }
+  if (it->extrap == ORC_EXTRAP_FLAT) return itp_core(it, tb, cl, res);
+  return ORC_EOOB; /* Throw */
+}
+
+int orc_itp_eval(const orc_itp *it, int64_t nq, const double *const *x, double *out, int64_t *first_bad) {
+  if (it->ndim < 1 || it->ndim > 3) return ORC_EARG;
+  itp_tabs tb;
+  for (int d = 0; d < it->ndim; ++d) {
+    tb.eqs[d] = orc_eqs(it->kernel[d]);
+    tb.kp[d] = orc_table(it->kernel[d], it->deriv[d]);
+    tb.kd[d] = orc_table(it->kernel[d], it->deriv[d] + 1);
+    if (tb.eqs[d] < 0 || !tb.kp[d] || !tb.kd[d]) return ORC_EARG;
+  }
+  int64_t bad = -1;
+  int bad_rc = ORC_OK;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int64_t q = 0; q < nq; ++q) {
+    double xq[3] = {0, 0, 0};
+    for (int d = 0; d < it->ndim; ++d) xq[d] = x[d][q];
+    double r = NAN;
+    int rc = etp_point(it, &tb, xq, &r);
+    out[q] = r;
+    if (rc) {
+#pragma omp critical
+      {
+        if (bad < 0 || q < bad) { bad = q; bad_rc = rc; }
+      }
+    }
+  }
+  if (first_bad) *first_bad = bad;
+  return bad_rc;
+}
+
+/* convolution/convolution_resample.jl:240-386, cubic subgrid branch :350-361 */
+int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const double *values,
+                 double *out, const double *const *knots_in, const double *const *knots_out,
+                 const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                 const int32_t *bc_right) {
+  if (ndim < 1 || ndim > ORC_MAXDIM) return ORC_EARG;
+  int64_t cur_shape[ORC_MAXDIM];
+  int64_t tot = 1;
+  for (int d = 0; d < ndim; ++d) { cur_shape[d] = n_in[d]; tot *= n_in[d]; }
+  double *current = (double *)malloc(sizeof(double) * (size_t)tot);
+  memcpy(current, values, sizeof(double) * (size_t)tot);
+  const double h_pre = 1.0 / (double)(N_PRE - 1);
+  for (int d = 0; d < ndim; ++d) {
+    const int eqs_d = orc_eqs(kernel[d]);
+    const double *kernel_pre = orc_table(kernel[d], deriv[d]);
+    const double *kd1_pre = orc_table(kernel[d], deriv[d] + 1);
+    if (eqs_d < 0 || !kernel_pre || !kd1_pre) { free(current); return ORC_EARG; }
+    const int64_t nin = cur_shape[d], nout = n_out[d];
+    const double h_d = knots_in[d][1] - knots_in[d][0];
+    const int64_t n_coef = nin + 2 * (eqs_d - 1);
+    const double x_expanded_1 = knots_in[d][0] - (double)(eqs_d - 1) * h_d;
+    int64_t next_shape[ORC_MAXDIM], ntot = 1, stride_in = 1, stride_out = 1;
+    for (int j = 0; j < ndim; ++j) { next_shape[j] = j == d ? nout : cur_shape[j]; ntot *= next_shape[j]; }
+    for (int j = 0; j < d; ++j) { stride_in *= cur_shape[j]; stride_out *= next_shape[j]; }
+    double *next = (double *)calloc((size_t)ntot, sizeof(double));
+    const int64_t inner = stride_in; /* product of dims < d (equal in/out) */
+    int64_t outer = 1;
+    for (int j = d + 1; j < ndim; ++j) outer *= cur_shape[j];
+    const double scale = jl_pow_int(-1.0 / h_d, deriv[d]);
+#pragma omp parallel num_threads(g_threads)
+    {
+      double *coef_buf = (double *)malloc(sizeof(double) * (size_t)n_coef);
+      double *slice = (double *)malloc(sizeof(double) * (size_t)nin);
+#pragma omp for schedule(static) collapse(2)
+      for (int64_t o = 0; o < outer; ++o)
+        for (int64_t in = 0; in < inner; ++in) {
+          const int64_t offset_in = in + o * inner * nin;
+          const int64_t offset_out = in + o * inner * nout;
+          memset(coef_buf, 0, sizeof(double) * (size_t)n_coef);
+          for (int64_t k = 1; k <= nin; ++k) coef_buf[k + eqs_d - 1 - 1] = current[offset_in + (k - 1) * stride_in];
+          ghost_fill_line(coef_buf + (eqs_d - 1), 1, nin, h_d, eqs_d, kernel[d], bc_left[d], bc_right[d], 0, 0, slice);
+          for (int64_t k = 1; k <= nout; ++k) {
+            double xq = knots_out[d][k - 1];
+            double i_float = (xq - x_expanded_1) / h_d + 1.0;
+            int64_t i = (int64_t)floor(i_float);
+            if (i < eqs_d) i = eqs_d;
+            if (i > n_coef - eqs_d) i = n_coef - eqs_d;
+            double knot_i = x_expanded_1 + (double)(i - 1) * h_d;
+            double x_diff_left = (xq - knot_i) / h_d;
+            double x_diff_right = 1.0 - x_diff_left;
+            double continuous_idx = x_diff_right * (double)(N_PRE - 1) + 1.0;
+            int64_t idx = (int64_t)floor(continuous_idx);
+            if (idx < 1) idx = 1;
+            if (idx > N_PRE - 1) idx = N_PRE - 1;
+            double t = continuous_idx - (double)idx;
+            double sum_f0 = 0, sum_f1 = 0, sum_d0 = 0, sum_d1 = 0;
+            for (int l = -(eqs_d - 1); l <= eqs_d; ++l) {
+              double coef = coef_buf[i + l - 1];
+              int col = l + eqs_d;
+              sum_f0 += coef * TAB(kernel_pre, idx, col, eqs_d);
+              sum_f1 += coef * TAB(kernel_pre, idx + 1, col, eqs_d);
+              sum_d0 += coef * TAB(kd1_pre, idx, col, eqs_d);
+              sum_d1 += coef * TAB(kd1_pre, idx + 1, col, eqs_d);
+            }
+            double v = cubic_hermite(t, sum_f0, sum_f1, sum_d0, sum_d1, h_pre);
+            next[offset_out + (k - 1) * stride_out] = v * scale; /* :378-380 */
+          }
+        }
+      free(coef_buf);
+      free(slice);
+    }
+    free(current);
+    current = next;
+    cur_shape[d] = nout;
+  }
+  int64_t otot = 1;
+  for (int d = 0; d < ndim; ++d) otot *= n_out[d];
+  memcpy(out, current, sizeof(double) * (size_t)otot);
+  free(current);
+  return ORC_OK;
+}
+
+/* convolution_gaussian_smoothing.jl:46 */
+int orc_smooth_halfwidth(double B) { return (int)ceil(sqrt(-log(1e-12 / 2) / B)); }
+
+/* convolution_kernels/convolution_kernel_gaussian.jl:23-31 */
+static double theta(double B, int terms) {
+  double q = exp(-B);
+  double sum = 1.0;
+  for (int n = 1; n <= terms; ++n) {
+    double term = 2 * jl_pow_int(q, (int64_t)n * n);
+    sum += term;
+  }
+  return sum;
+}
+
+/* convolution/convolution_gaussian_smoothing.jl:45-126 */
+int orc_smooth(int ndim, const int64_t *n, const double *values, double *out, const double *h, double B) {
+  if (ndim < 1 || ndim > ORC_MAXDIM) return ORC_EARG;
+  const int E = orc_smooth_halfwidth(B);
+  int64_t tot = 1;
+  for (int d = 0; d < ndim; ++d) {
+    if (E >= n[d]) return ORC_EARG; /* :50-56 */
+    tot *= n[d];
+  }
+  const double norm = theta(B, E);
+  double *kw = (double *)malloc(sizeof(double) * (size_t)(2 * E + 1));
+  for (int l = -E; l <= E; ++l) kw[l + E] = exp(-B * ((double)l * (double)l)) / norm; /* :59-63 */
+  double *current = (double *)malloc(sizeof(double) * (size_t)tot);
+  memcpy(current, values, sizeof(double) * (size_t)tot);
+  for (int d = 0; d < ndim; ++d) {
+    const int64_t nd = n[d];
+    const int64_t n_coef = nd + 2 * E;
+    int64_t stride = 1, outer = 1;
+    for (int j = 0; j < d; ++j) stride *= n[j];
+    for (int j = d + 1; j < ndim; ++j) outer *= n[j];
+    double *next = (double *)calloc((size_t)tot, sizeof(double));
+#pragma omp parallel num_threads(g_threads)
+    {
+      double *coef_buf = (double *)malloc(sizeof(double) * (size_t)n_coef);
+      double *slice = (double *)malloc(sizeof(double) * (size_t)nd);
+#pragma omp for schedule(static) collapse(2)
+      for (int64_t o = 0; o < outer; ++o)
+        for (int64_t in = 0; in < stride; ++in) {
+          const int64_t off = in + o * stride * nd;
+          memset(coef_buf, 0, sizeof(double) * (size_t)n_coef);
+          for (int64_t k = 1; k <= nd; ++k) coef_buf[k + E - 1] = current[off + (k - 1) * stride]; /* :97-100 */
+          /* :103-105 -> Gaussian branch, ghosts shifted one slot outward (shift = 1), the two
+           * slots next to the interior stay 0 */
+          ghost_fill_line(coef_buf + E, 1, nd, h[d], E, ORC_K_GAUSS, ORC_BC_DETECT, ORC_BC_DETECT, 1, 1, slice);
+          for (int64_t k = 1; k <= nd; ++k) {
+            double result = 0.0;
+            int64_t i_base = k + E;
+            for (int l = -E; l <= E; ++l) result += coef_buf[i_base + l - 1] * kw[l + E];
+            next[off + (k - 1) * stride] = result;
+          }
+        }
+      free(coef_buf);
+      free(slice);
+    }
+    free(current);
+    current = next;
+  }
+  memcpy(out, current, sizeof(double) * (size_t)tot);
+  free(current);
+  free(kw);
+  return ORC_OK;
+}

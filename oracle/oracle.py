@@ -1,0 +1,307 @@
+"""ctypes front-end of the CPU ORACLE (oracle/cib_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+`--impl reference` legs of bench.py - never by the product package.
+
+The Python part restates the reference's *host* logic that sits in front of the hot loops
+(argument normalisation, mode resolution, knot extension); each helper cites the reference
+file:line it follows (paths relative to /root/reference/src).  Parity status: unpinned against
+real Julia output (Julia is not available); pinned against the shipped kernel tables, the
+integer ghost matrices and the analytic properties of the reference's test-suite.
+
+Array convention: `values[i1, i2, ...]` is indexed like the Julia array; memory order is free
+(converted to column-major before the call).
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4}
+KERNEL_EQS = {"b5": 5, "b7": 6, "b9": 7, "b11": 8, "b13": 9}        # degree_to_equations.jl:13-25
+MAX_SMOOTH_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6}  # constructor.jl:400-412
+MAX_SHIPPED_DERIVATIVE = {"b5": 2, "b7": 3, "b9": 4, "b11": 5, "b13": 5}  # get_precomputed...jl:33-40
+MIN_POLY_BC_POINTS = {"b5": 6, "b7": 8, "b9": 8, "b11": 8, "b13": 8}  # convolution_interpolation_function.jl:183-195
+BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
+EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libcib_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("cib_oracle.c", "cib_oracle.h", "oracle_tables.inc")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "libcib_oracle.so"], check=True, capture_output=True)
+    return so
+
+
+class _Itp(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("cshape", C.c_int64 * 3), ("coefs", C.c_void_p),
+                ("knots", C.c_void_p * 3), ("h", C.c_double * 3), ("kernel", C.c_int32 * 3),
+                ("deriv", C.c_int32 * 3), ("extrap", C.c_int32), ("perdim", C.c_int32)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_table.restype = C.POINTER(C.c_double)
+        L.orc_table.argtypes = [C.c_int, C.c_int]
+        L.orc_itp_eval.argtypes = [C.POINTER(_Itp), C.c_int64, C.POINTER(C.c_void_p), C.c_void_p,
+                                   C.POINTER(C.c_int64)]
+        L.orc_create_coefs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_resample.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 4
+        L.orc_smooth.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.orc_smooth_halfwidth.argtypes = [C.c_double]
+        L.orc_ghost_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+def table(kernel, d):
+    """K^(d) table of `kernel` as a (101, 2*eqs) array (copy)."""
+    p = lib().orc_table(KERNEL_IDS[kernel], int(d))
+    if not p:
+        raise OracleError(f"no table for {kernel} d={d}")
+    e = KERNEL_EQS[kernel]
+    return np.ctypeslib.as_array(p, shape=(101, 2 * e)).copy()
+
+
+def ghost_matrix(which, kernel, rows):
+    m = {"poly": 6 if kernel == "b5" else 8, "linear": 2, "quadratic": 3}[which]
+    out = np.zeros((rows, m))
+    lib().orc_ghost_matrix({"poly": 0, "linear": 1, "quadratic": 2}[which], KERNEL_IDS[kernel], rows,
+                           out.ctypes.data)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# argument normalisation: convolution_interpolation_function.jl:88-107
+# ---------------------------------------------------------------------------------------------
+def _ntuple(v, n, scalar_types):
+    if isinstance(v, scalar_types):
+        return (v,) * n
+    v = tuple(v)
+    if len(v) == 1:
+        return v * n
+    if len(v) != n:
+        raise OracleError(f"Invalid specification: {v}")
+    return v
+
+
+def _norm_bc(bc, n):
+    if isinstance(bc, str):
+        return tuple((bc, bc) for _ in range(n))
+    bc = tuple(bc)
+    if len(bc) == 2 and all(isinstance(b, str) for b in bc):
+        return tuple(tuple(bc) for _ in range(n))
+    if len(bc) == 1:
+        return tuple(tuple(bc[0]) for _ in range(n))
+    if len(bc) != n:
+        raise OracleError(f"Invalid bc specification: {bc}")
+    return tuple(tuple(b) for b in bc)
+
+
+def _knots_tuple(knots, ndim):
+    if ndim == 1 and not isinstance(knots, (tuple, list)):
+        knots = (knots,)
+    if isinstance(knots, np.ndarray) and knots.ndim == 1 and ndim == 1:
+        knots = (knots,)
+    return tuple(np.ascontiguousarray(k, dtype=np.float64) for k in knots)
+
+
+def build_subgrids(kernels, derivs, subgrids):
+    """fast_convolution_interpolation_constructor.jl:456-494 (no a0/a1, no integral dims)."""
+    n = len(kernels)
+    all_cubic = len(set(subgrids)) == 1 and subgrids[0] == "cubic"
+    out = []
+    for k, dv, sg in zip(kernels, derivs, subgrids):
+        if dv == 0:
+            out.append("linear" if (n == 3 and not all_cubic) or n >= 4 else sg)
+        else:
+            avail = MAX_SMOOTH_DERIVATIVE[k] - dv
+            out.append("linear" if avail <= 0 or (n == 3 and not all_cubic) or n >= 4 else sg)
+    return tuple(out)
+
+
+def extend_vector(x, n_extra):
+    """convolution/extend_vector.jl:10-18"""
+    step_start = x[1] - x[0]
+    step_end = x[-1] - x[-2]
+    start = np.array([x[0] - i * step_start for i in range(n_extra, 0, -1)])
+    end = np.array([x[-1] + i * step_end for i in range(1, n_extra + 1)])
+    return np.concatenate([start, x, end])
+
+
+def create_coefs(values, h, kernels, bcs):
+    """create_convolutional_coefs.jl:141-160 -> padded array (Julia index order)."""
+    v = np.asfortranarray(values, dtype=np.float64)
+    nd = v.ndim
+    n = (C.c_int64 * nd)(*v.shape)
+    hh = (C.c_double * nd)(*h)
+    kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in kernels])
+    bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
+    br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
+    cshape = tuple(s + 2 * (KERNEL_EQS[k] - 1) for s, k in zip(v.shape, kernels))
+    c = np.zeros(cshape, order="F")
+    rc = lib().orc_create_coefs(nd, n, v.ctypes.data, hh, kid, bl, br, c.ctypes.data)
+    if rc:
+        raise OracleError(f"orc_create_coefs rc={rc}")
+    return c
+
+
+class Interpolant:
+    """convolution_interpolation(knots, values; kernel, extrap, bc, derivative) - fast eager path,
+    cubic subgrid (convolution_interpolation_function.jl:79-170,
+    fast_convolution_interpolation_constructor.jl:99-174)."""
+
+    def __init__(self, knots, values, kernel="b5", extrap="throw", bc="detect", derivative=0,
+                 subgrid="cubic"):
+        values = np.asarray(values, dtype=np.float64)
+        nd = values.ndim
+        if nd < 1 or nd > 3:
+            raise OracleError("oracle covers 1-3 D")
+        self.ndim = nd
+        self.knots_in = _knots_tuple(knots, nd)
+        self.kernels = _ntuple(kernel, nd, str)
+        self.derivs = _ntuple(derivative, nd, int)
+        sg_req = _ntuple(subgrid, nd, str)
+        bcs = _norm_bc(bc, nd)
+        # :poly -> :linear downgrade, convolution_interpolation_function.jl:135-143
+        fixed = []
+        for d in range(nd):
+            b = bcs[d]
+            if "poly" in b and values.shape[d] < MIN_POLY_BC_POINTS[self.kernels[d]]:
+                if b == ("poly", "poly"):
+                    b = ("linear", "linear")
+                elif b[0] == "poly":
+                    b = ("linear", b[1])
+                else:
+                    b = (b[0], "linear")
+            fixed.append(b)
+        self.bc = tuple(fixed)
+        self.subgrid = build_subgrids(self.kernels, self.derivs, sg_req)
+        for d in range(nd):
+            if self.subgrid[d] != "cubic" or self.derivs[d] > MAX_SHIPPED_DERIVATIVE[self.kernels[d]] \
+                    or self.derivs[d] < 0:
+                raise OracleError(f"mode outside the oracle's scope: subgrid={self.subgrid} deriv={self.derivs}")
+        self.eqs = tuple(KERNEL_EQS[k] for k in self.kernels)
+        self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120
+        self.coefs = create_coefs(values, self.h, self.kernels, self.bc)
+        self.knots = tuple(extend_vector(k, e - 1) for k, e in zip(self.knots_in, self.eqs))
+        self.extrap = extrap
+        # _build_kernel_sym, constructor.jl:378-398
+        self.perdim = not (len(set(self.kernels)) == 1 and len(set(self.derivs)) == 1)
+        it = _Itp()
+        it.ndim = nd
+        for d in range(nd):
+            it.cshape[d] = self.coefs.shape[d]
+            it.knots[d] = self.knots[d].ctypes.data
+            it.h[d] = self.h[d]
+            it.kernel[d] = KERNEL_IDS[self.kernels[d]]
+            it.deriv[d] = self.derivs[d]
+        it.coefs = self.coefs.ctypes.data
+        it.extrap = EXTRAP_IDS[extrap]
+        it.perdim = int(self.perdim)
+        self._it = it
+
+    def eval_points(self, *xs):
+        """itp.(xs...) : element-wise over equally long coordinate vectors."""
+        xs = [np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), np.broadcast(*xs).shape)).ravel()
+              for x in xs]
+        assert len(xs) == self.ndim
+        nq = xs[0].size
+        out = np.empty(nq)
+        ptrs = (C.c_void_p * self.ndim)(*[x.ctypes.data for x in xs])
+        bad = C.c_int64(-1)
+        rc = lib().orc_itp_eval(C.byref(self._it), nq, ptrs, out.ctypes.data, C.byref(bad))
+        if rc == 1:
+            raise OracleError(f"query {bad.value} outside the domain with extrap=throw")
+        if rc == 2:
+            raise OracleError(f"query {bad.value}: InexactError (NaN/Inf coordinate)")
+        if rc:
+            raise OracleError(f"orc_itp_eval rc={rc}")
+        return out
+
+    def __call__(self, *xs):
+        if all(np.ndim(x) == 0 for x in xs):
+            return float(self.eval_points(*[np.array([x]) for x in xs])[0])
+        # extrapolation_operator.jl:66-99: Cartesian product of coordinate vectors
+        grids = np.meshgrid(*[np.asarray(x, dtype=np.float64) for x in xs], indexing="ij")
+        return self.eval_points(*[g.ravel() for g in grids]).reshape(grids[0].shape)
+
+
+def convolution_interpolation(knots, values, **kw):
+    return Interpolant(knots, values, **kw)
+
+
+def convolution_resample(knots_in, knots_out, values, kernel="b13", derivative=0, bc="detect",
+                         subgrid="cubic"):
+    """convolution_resample.jl:174-238 front-end + :240-386 internal."""
+    v = np.asfortranarray(values, dtype=np.float64)
+    nd = v.ndim
+    kin = _knots_tuple(knots_in, nd)
+    kout = _knots_tuple(knots_out, nd)
+    kernels = _ntuple(kernel, nd, str)
+    derivs = _ntuple(derivative, nd, int)
+    bcs = _norm_bc(bc, nd)
+    sgs = build_subgrids(kernels, derivs, _ntuple(subgrid, nd, str))
+    for d in range(nd):
+        if derivs[d] < 0:
+            raise OracleError("convolution_resample does not support antiderivatives")
+        if sgs[d] != "cubic" or derivs[d] > MAX_SHIPPED_DERIVATIVE[kernels[d]]:
+            raise OracleError(f"mode outside the oracle's scope: subgrid={sgs} deriv={derivs}")
+    n_in = (C.c_int64 * nd)(*v.shape)
+    n_out = (C.c_int64 * nd)(*[len(k) for k in kout])
+    out = np.zeros(tuple(len(k) for k in kout), order="F")
+    kinp = (C.c_void_p * nd)(*[k.ctypes.data for k in kin])
+    koutp = (C.c_void_p * nd)(*[k.ctypes.data for k in kout])
+    kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in kernels])
+    dv = (C.c_int32 * nd)(*derivs)
+    bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
+    br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
+    rc = lib().orc_resample(nd, n_in, n_out, v.ctypes.data, out.ctypes.data, kinp, koutp, kid, dv, bl, br)
+    if rc:
+        raise OracleError(f"orc_resample rc={rc}")
+    return out
+
+
+def smooth_halfwidth(B):
+    return lib().orc_smooth_halfwidth(float(B))
+
+
+def convolution_smooth(knots, values, B):
+    """convolution_gaussian_smoothing.jl:45-131"""
+    v = np.asfortranarray(values, dtype=np.float64)
+    nd = v.ndim
+    ks = _knots_tuple(knots, nd)
+    E = smooth_halfwidth(B)
+    for d in range(nd):
+        if E >= len(ks[d]):
+            raise OracleError(f"Gaussian stencil half-width ({E} points) exceeds grid size (n={len(ks[d])}) "
+                              f"in dimension {d + 1}.")
+    n = (C.c_int64 * nd)(*v.shape)
+    h = (C.c_double * nd)(*[float(k[1] - k[0]) for k in ks])
+    out = np.zeros(v.shape, order="F")
+    rc = lib().orc_smooth(nd, n, v.ctypes.data, out.ctypes.data, h, float(B))
+    if rc:
+        raise OracleError(f"orc_smooth rc={rc}")
+    return out
+
+
+def theta(B, terms):
+    q = math.exp(-B)
+    return 1.0 + sum(2 * q ** (n * n) for n in range(1, terms + 1))
