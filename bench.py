@@ -1,0 +1,333 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark: 3-D :b5 point evaluations per second (BASELINE.json config 5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nq Q] [--grid G]
+
+A "step" is one pass of the hot path over one batch of synthetic queries: Q uniformly random points on a
+G^3 Float64 grid (defaults: Q = 10^9 per GPU, G = 512; the coefficient grid is replicated on every rank and
+every rank evaluates its own batch - weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
+
+  value      whole-job evaluations/s with queries and results resident in HBM (CUDA events, max over ranks)
+  e2e        the same metric through the public API with pinned HOST buffers (H2D + D2H inside the timed region)
+  roofline   the evaluation kernel against the measured HBM peak with the gather model
+             (8 032 algorithmic bytes per evaluation: SURVEY.md 8d / DESIGN.md)
+  cpu_baseline  the reference's algorithm (literal C restatement, oracle/) on this box's host cores, bounded sample
+
+`--impl reference` times that CPU restatement instead (the reference is Julia-only and Julia is not in the
+image, so there is no oracle/_ref build), same metric / unit / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "3d_b5_point_evals_per_s"
+UNIT = "evals/s"
+BYTES_PER_EVAL = 3 * 8 + 8 + 10 ** 3 * 8  # coordinates + result + (2*eqs)^3 stencil gather = 8032 B (f64, :b5)
+SEED = 0xC1B200 + 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nq", type=float, default=1e9, help="queries per GPU per step")
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--e2e-nq", type=float, default=1e8, help="queries per step of the host-buffer (e2e) leg")
+    ap.add_argument("--mode", default=os.environ.get("CIB200_EVAL_MODE", "auto"), choices=["auto", "gather", "binned"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def make_grid(n):
+    """512^3 synthetic field: a few smooth modes + 1 % uniform noise."""
+    import numpy as np
+    rng = np.random.default_rng(SEED)
+    g = np.linspace(0.0, 1.0, n)
+    a = np.sin(2 * np.pi * g) + 0.5 * np.cos(6 * np.pi * g + 0.3)
+    b = np.cos(2 * np.pi * g) + 0.3 * np.sin(10 * np.pi * g)
+    c = np.sin(4 * np.pi * g + 1.0)
+    v = np.empty((n, n, n), order="F")
+    # built plane by plane to keep the peak host footprint near one copy
+    for k in range(n):
+        v[:, :, k] = a[:, None] * b[None, :] * c[k] + 0.01 * rng.uniform(-1, 1, (n, n))
+    return (g, g, g), v
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # "under load": the upper half of the samples (idle samples before/after the region pull the median down)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_eval():
+    """DRAM bytes per evaluation of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def cpu_baseline(seconds, grid_n=96, threads=None):
+    """The reference's algorithm on host cores: literal 64-accumulator evaluator (oracle/cib_oracle.c), all
+    host threads, on a bounded sample of the same workload (3-D :b5, uniformly random queries).  A smaller grid
+    is used for the sample (the per-query cost of the reference does not depend on the grid size beyond cache
+    effects; 96^3 doubles = 7 MB sits in L2/L3 like the reference's own 50^3 benchmark grid)."""
+    import numpy as np
+    from oracle import oracle as O
+    threads = threads or (os.cpu_count() or 1)
+    O.set_threads(threads)
+    rng = np.random.default_rng(SEED)
+    g = np.linspace(0, 1, grid_n)
+    v = rng.uniform(-1, 1, (grid_n,) * 3)
+    itp = O.convolution_interpolation((g, g, g), v, kernel="b5", bc="poly")
+    q = rng.uniform(0, 1, (3, 20_000 * threads))
+    t0 = time.perf_counter()
+    itp.eval(*q)
+    dt = time.perf_counter() - t0
+    rate = q.shape[1] / dt
+    n = int(max(q.shape[1], min(rate * seconds, 5e7)))
+    q = rng.uniform(0, 1, (3, n))
+    t0 = time.perf_counter()
+    itp.eval(*q)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} uniformly random queries, 3-D :b5 on a {grid_n}^3 Float64 grid, literal 64-accumulator "
+                      f"evaluator (eager_3d.jl:181-305) in C with OpenMP, {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    O.set_threads(threads)
+    rng = np.random.default_rng(SEED)
+    grid_n = 96
+    g = np.linspace(0, 1, grid_n)
+    v = rng.uniform(-1, 1, (grid_n,) * 3)
+    itp = O.convolution_interpolation((g, g, g), v, kernel="b5", bc="poly")
+    probe = rng.uniform(0, 1, (3, 10_000 * threads))
+    t0 = time.perf_counter()
+    itp.eval(*probe)
+    rate = probe.shape[1] / (time.perf_counter() - t0)
+    total_steps = args.steps + args.warmup
+    n = int(max(10_000, min(rate * 60.0 / max(total_steps, 1), 2e7)))  # whole run ~1 minute
+    q = rng.uniform(0, 1, (3, n))
+    for _ in range(args.warmup):
+        itp.eval(*q)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        itp.eval(*q)
+    dt = time.perf_counter() - t0
+    value = args.steps * n / dt
+    sample = (f"{n} uniformly random queries per step, 3-D :b5, {grid_n}^3 Float64 grid, literal restatement of the "
+              f"reference evaluator (oracle/cib_oracle.c, OpenMP); the reference itself is Julia-only and Julia is not "
+              f"in the image")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D :b5 point evaluation, uniformly random queries (BASELINE config 5)",
+                       "queries_per_step": n, "grid": f"{grid_n}^3 (bounded CPU sample)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for this path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import convitp_b200 as ci
+
+    nq = int(args.nq)
+    knots, vals = make_grid(args.grid)
+    t0 = time.perf_counter()
+    itp = ci.convolution_interpolation(knots, vals, kernel="b5", bc="poly", eval_mode=args.mode)
+    build_s = time.perf_counter() - t0
+    del vals
+
+    # queries generated on the device, per rank: 24 GB in + 8 GB out at 10^9
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + rank)
+    xs = [torch.rand(nq, dtype=torch.float64, device=dev, generator=gen) for _ in range(3)]
+    out = torch.empty(nq, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        itp.eval(*xs, out=out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ci.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for s in range(args.steps):
+        itp.eval(*xs, out=out)
+        ev[s + 1].record()
+    barrier()
+    launches = ci.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * nq * args.steps / (total_ms_max * 1e-3)
+
+    # sanity: a strided subsample must be finite and reproduce a second evaluation bit for bit
+    sub = slice(0, nq, max(1, nq // 1_000_000))
+    chk = itp.eval(*[x[sub].contiguous() for x in xs])
+    assert torch.isfinite(chk).all()
+    assert torch.equal(chk, out[sub]), "subsample re-evaluation differs from the timed result"
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region -----------------------
+    e2e = None
+    if not args.no_e2e:
+        nqe = int(min(args.e2e_nq, nq))
+        hx = [torch.empty(nqe, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+        for i in range(3):
+            hx[i].copy_(xs[i][:nqe])
+        hout = torch.empty(nqe, dtype=torch.float64, pin_memory=True)
+        hxn = [h.numpy() for h in hx]
+        houtn = hout.numpy()
+        for _ in range(max(1, min(args.warmup, 2))):
+            itp.eval(*hxn, out=houtn)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            itp.eval(*hxn, out=houtn)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        assert np.array_equal(houtn[:1000], out[:1000].cpu().numpy())
+        e2e = {"value": world * nqe * args.steps / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 3 * 8 * nqe, "d2h_bytes_per_step": 8 * nqe, "queries_per_step": nqe,
+               "note": "cib200_itp_eval with pinned host buffers: chunked, double-buffered H2D -> kernel -> D2H"}
+        del hx, hout
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernel_ms = sum(step_ms) / len(step_ms)  # one kernel launch per step: the step IS the kernel
+        achieved = BYTES_PER_EVAL * nq / (kernel_ms * 1e-3) / 1e9
+        traffic = ncu_traffic_per_eval()
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                    "kernel": "eval_warp3d_kernel<double,5>" if itp.itp.eval_mode != "binned" else "binned pipeline",
+                    "model": f"gather model, {BYTES_PER_EVAL} algorithmic B/eval x {nq} evals per launch",
+                    "peak_source": peak_src, "traffic_source": (traffic or {}).get("source")}
+        cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"3D :b5 point evaluation, {nq} uniformly random queries per GPU on a "
+                                       f"{args.grid}^3 Float64 grid (BASELINE config 5)",
+                           "queries_per_gpu_per_step": nq, "grid": args.grid, "kernel": "b5", "derivative": 0,
+                           "bc": "poly", "extrap": "throw", "eval_mode": itp.itp.eval_mode,
+                           "parallelism": f"query-sharded x{world}, coefficient grid replicated, no collective",
+                           "l2": "inputs (32 B/query x nq) and the 1.1 GB grid exceed the 126 MB L2; no flush needed",
+                           "grid_build_s": build_s},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "step_ms": step_ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

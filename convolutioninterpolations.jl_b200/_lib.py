@@ -1,0 +1,101 @@
+"""ctypes binding of libcib200.so (the C-ABI declared in include/cib200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded this module raises,
+and every compute entry point fails loudly when no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcib200.so")
+
+OK, EOOB, ENAN, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(7)
+F64, F32 = 0, 1
+HOST, DEVICE = 0, 1
+KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4}
+BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
+EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
+EVAL_MODES = {"auto": 0, "gather": 1, "binned": 2}
+
+# every symbol include/cib200.h declares (tests assert the library exports all of them)
+SYMBOLS = [
+    "cib200_version", "cib200_last_error", "cib200_launch_count", "cib200_kernel_table",
+    "cib200_build_coefs", "cib200_extend_knots", "cib200_itp_create", "cib200_itp_destroy",
+    "cib200_itp_set_eval_mode", "cib200_itp_eval", "cib200_itp_eval_grid", "cib200_itp_scratch_bytes",
+    "cib200_resample", "cib200_smooth", "cib200_smooth_halfwidth", "cib200_host_register",
+    "cib200_host_unregister",
+]
+
+
+class ItpDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("dtype", C.c_int32), ("coef_shape", C.c_int64 * 3),
+                ("coefs", C.c_void_p), ("knots", C.c_void_p * 3), ("h", C.c_double * 3),
+                ("kernel", C.c_int32 * 3), ("deriv", C.c_int32 * 3), ("extrap", C.c_int32),
+                ("perdim", C.c_int32)]
+
+
+class CIB200Error(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+class DomainError(CIB200Error):
+    """extrap=Throw and a query is outside the domain (ErrorException in the reference)."""
+
+
+class InexactError(CIB200Error):
+    """NaN / Inf coordinate (InexactError from floor(Int, x) in the reference)."""
+
+
+class UnsupportedModeError(CIB200Error):
+    """A mode that stays on the reference's own Julia path (never silently approximated here)."""
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for this path.")
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.cib200_version.restype = i32
+    L.cib200_last_error.restype = C.c_char_p
+    L.cib200_launch_count.restype = i64
+    L.cib200_kernel_table.restype = C.POINTER(dbl)
+    L.cib200_kernel_table.argtypes = [i32, i32, C.POINTER(i32)]
+    L.cib200_build_coefs.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.cib200_extend_knots.argtypes = [vp, i64, i32, vp]
+    L.cib200_itp_create.argtypes = [C.POINTER(ItpDesc), C.POINTER(vp)]
+    L.cib200_itp_destroy.argtypes = [vp]
+    L.cib200_itp_set_eval_mode.argtypes = [vp, i32]
+    L.cib200_itp_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itp_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itp_scratch_bytes.restype = i64
+    L.cib200_itp_scratch_bytes.argtypes = [vp, i64]
+    L.cib200_resample.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, i32, vp]
+    L.cib200_smooth.argtypes = [i32, i32, vp, vp, vp, vp, dbl, i32, vp]
+    L.cib200_smooth_halfwidth.restype = i32
+    L.cib200_smooth_halfwidth.argtypes = [dbl]
+    L.cib200_host_register.argtypes = [vp, C.c_size_t]
+    L.cib200_host_unregister.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def check(status):
+    if status == OK:
+        return
+    msg = lib().cib200_last_error().decode("utf-8", "replace")
+    cls = {EOOB: DomainError, ENAN: InexactError, EUNSUPPORTED: UnsupportedModeError}.get(status, CIB200Error)
+    raise cls(status, msg or f"cib200 status {status}")
+
+
+def launch_count():
+    return int(lib().cib200_launch_count())

@@ -1,0 +1,477 @@
+"""Host-side mirror of the reference's public API for the accelerated path.
+
+Same names, keyword arguments, defaults and error behaviour as
+  convolution_interpolation   src/convolution/convolution_interpolation_function.jl:79-157
+  convolution_resample        src/convolution/convolution_resample.jl:65-238
+  convolution_smooth          src/convolution/convolution_gaussian_smoothing.jl:45-131
+(Julia symbols become strings: :b5 -> "b5"; `itp.(xs...)` becomes `itp.eval(xs...)`,
+`itp(xs, ys)` with vectors is the Cartesian product exactly as extrapolation_operator.jl:66-99.)
+
+This file only normalises arguments and resolves modes; all numerical work happens behind the
+C-ABI (include/cib200.h) in libcib200.so.  Modes the CUDA path does not implement raise
+UnsupportedModeError - in the Julia glue those calls keep dispatching to the reference's own
+methods; nothing is silently approximated and nothing falls back to the CPU here.
+
+Inputs may be numpy arrays (host buffers, copied through the library's pipelined H2D/D2H path) or
+CUDA torch tensors (device-resident, zero-copy, asynchronous on torch's current stream).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BC_IDS, EXTRAP_IDS, KERNEL_IDS, CIB200Error, UnsupportedModeError, check, lib)
+
+# data_structures/degree_to_equations.jl:13-25
+DEGREE_TO_EQUATIONS = {"a0": 1, "a1": 1, "a3": 2, "a4": 3, "a5": 3, "a7": 4, "b5": 5, "b7": 6, "b9": 7,
+                       "b11": 8, "b13": 9}
+# fast_convolution_interpolation_constructor.jl:400-412
+MAX_SMOOTH_DERIVATIVE = {"a0": -1, "a1": 0, "a3": 1, "a4": 1, "a5": 1, "a7": 1, "b5": 3, "b7": 4, "b9": 5,
+                         "b11": 6, "b13": 6}
+# get_precomputed_kernel_and_range.jl:33-40
+MAX_SHIPPED_DERIVATIVE = {"a0": 0, "a1": 0, "a3": 0, "a4": 0, "a5": 0, "a7": 0, "b5": 2, "b7": 3, "b9": 4,
+                          "b11": 5, "b13": 5}
+# convolution_interpolation_function.jl:183-195
+MINIMUM_POLYNOMIAL_BC_POINTS = {"a0": 2, "a1": 2, "a3": 4, "a4": 4, "a5": 4, "a7": 4, "b5": 6, "b7": 8,
+                                "b9": 8, "b11": 8, "b13": 8}
+ACCELERATED_KERNELS = tuple(KERNEL_IDS)
+
+
+class AbstractExtrapolation:
+    name = None
+
+    def __eq__(self, other):
+        return type(self) is type(other)
+
+    def __hash__(self):
+        return hash(type(self))
+
+    def __repr__(self):
+        return f"{type(self).__name__}()"
+
+
+class Throw(AbstractExtrapolation):
+    name = "throw"
+
+
+class Flat(AbstractExtrapolation):
+    name = "flat"
+
+
+class Line(AbstractExtrapolation):
+    name = "line"
+
+
+class Natural(AbstractExtrapolation):
+    name = "natural"
+
+
+def _sym(s):
+    if isinstance(s, str):
+        return s[1:] if s.startswith(":") else s
+    return s
+
+
+def _extrap_type(s):
+    """convolution_interpolation_function.jl:197-211"""
+    if isinstance(s, AbstractExtrapolation):
+        return s
+    s = _sym(s)
+    if s == "throw":
+        return Throw()
+    if s == "line":
+        return Line()
+    if s == "flat":
+        return Flat()
+    raise ValueError(f"Unknown extrapolation type: {s}, must be :throw, :line, :flat or :natural.")
+
+
+def _ntuple(v, n, scalar, what):
+    if isinstance(v, scalar):
+        return tuple(_sym(v) for _ in range(n))
+    v = tuple(_sym(x) for x in v)
+    if len(v) == n:
+        return v
+    if len(v) == 1:
+        return v * n
+    raise ValueError(f"Invalid {what} specification: {v}.")
+
+
+def _norm_bc(bc, n):
+    if isinstance(bc, str):
+        return tuple((_sym(bc), _sym(bc)) for _ in range(n))
+    bc = tuple(bc)
+    if len(bc) == 2 and all(isinstance(b, str) for b in bc):
+        return tuple((_sym(bc[0]), _sym(bc[1])) for _ in range(n))
+    if len(bc) == n and all(len(tuple(b)) == 2 for b in bc):
+        return tuple((_sym(b[0]), _sym(b[1])) for b in bc)
+    if len(bc) == 1:
+        return tuple((_sym(bc[0][0]), _sym(bc[0][1])) for _ in range(n))
+    raise ValueError(f"Invalid bc specification: {bc}.")
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _np_dtype(dtype_id):
+    return np.float32 if dtype_id == _lib.F32 else np.float64
+
+
+def _knots_tuple(knots, ndim, what="knots"):
+    if ndim == 1 and not (isinstance(knots, (tuple, list)) and len(knots) == 1 and np.ndim(knots[0]) == 1):
+        knots = (knots,)
+    knots = tuple(knots)
+    if len(knots) != ndim:
+        raise ValueError(f"Invalid {what} specification: expected {ndim} knot vectors, got {len(knots)}.")
+    return knots
+
+
+def is_uniform_grid(k, rtol=1e-10):
+    """convolution_kernels/nonuniform.jl:13-25"""
+    h0 = k[1] - k[0]
+    if h0 == 0:
+        return False
+    d = np.diff(k)
+    return bool(np.all(np.abs(d - h0) <= rtol * abs(h0)))
+
+
+def _build_subgrids(kernels, derivs, subgrids):
+    """fast_convolution_interpolation_constructor.jl:456-494"""
+    n = len(kernels)
+    low = any(k in ("a0", "a1") for k in kernels)
+    all_cubic = len(set(subgrids)) == 1 and subgrids[0] == "cubic"
+    has_int = any(d == -1 for d in derivs)
+    out = []
+    for k, dv, sg in zip(kernels, derivs, subgrids):
+        if dv == -1:
+            if k in ("a0", "a1") or n >= 4:
+                out.append("linear")
+            elif k in ("a3", "a4", "a5", "a7"):
+                out.append("cubic")
+            else:
+                out.append(sg)
+        elif dv == 0:
+            out.append("linear" if (low or (n == 3 and not all_cubic) or n >= 4 or has_int) else sg)
+        else:
+            avail = MAX_SMOOTH_DERIVATIVE.get(k, 0) - dv
+            out.append("linear" if (avail <= 0 or (n == 3 and not all_cubic) or n >= 4 or low or has_int) else sg)
+    return tuple(out)
+
+
+def _require_accelerated(kernels, derivs, subgrids, ndim, what):
+    """Raise UnsupportedModeError for modes that stay on the reference's Julia path."""
+    if ndim > 3 and what == "convolution_interpolation":
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N={ndim} uses the linear-subgrid N-D evaluators "
+                                   "(eager_nd.jl / perdim_nd.jl); not on the accelerated path")
+    for d, (k, dv, sg) in enumerate(zip(kernels, derivs, subgrids)):
+        if k not in KERNEL_IDS:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: kernel :{k} (axis {d + 1}) is not on the "
+                                       f"accelerated path (b-series only: {ACCELERATED_KERNELS})")
+        if dv < 0:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivatives (derivative=-1) stay on the reference path")
+        if sg != "cubic":
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: resolved subgrid {subgrids} needs the "
+                                       f":{sg} evaluators / generated tables; only :cubic is accelerated")
+        if dv > MAX_SHIPPED_DERIVATIVE[k]:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative {dv} of :{k} is not a shipped table")
+
+
+def _stream_ptr(device_tensor):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device_tensor.device).cuda_stream)
+
+
+class FastConvolutionInterpolation:
+    """Numeric content of the reference struct (data_structures/fast_convolution_interpolation.jl:56-102)
+    for the eager cubic-subgrid case, plus the device handle."""
+
+    def __init__(self, knots, values, kernel="b5", precompute=101, bc="detect", derivative=0, subgrid="cubic",
+                 lazy=False, boundary_fallback=False, dtype=None, eval_mode="auto", _extrap="throw"):
+        values = np.asarray(values)
+        if values.dtype not in (np.float32, np.float64):
+            values = values.astype(np.float64)
+        if dtype is not None:
+            values = values.astype(np.dtype(dtype))
+        nd = values.ndim
+        self.ndim = nd
+        self.dtype = values.dtype
+        self.dtype_id = _lib.F32 if values.dtype == np.float32 else _lib.F64
+        knots = _knots_tuple(knots, nd)
+        # T.(knots): knots are converted to the element type (constructor.jl:60-62)
+        self.knots_in = tuple(np.asarray(k).astype(self.dtype).astype(np.float64) for k in knots)
+        for d in range(nd):
+            if len(self.knots_in[d]) != values.shape[d]:
+                raise ValueError(f"knots[{d}] has {len(self.knots_in[d])} points but values has {values.shape[d]}")
+        self.kernel = _ntuple(kernel, nd, str, "kernel")
+        self.derivative = _ntuple(derivative, nd, (int, np.integer), "derivative")
+        sg_req = _ntuple(subgrid, nd, str, "subgrid")
+        self.bc = _norm_bc(bc, nd)
+        if any(k == "n3" for k in self.kernel):
+            raise ValueError("The :n3 kernel is not supported by FastConvolutionInterpolation.")
+        if lazy:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, "lazy=true stays on the reference path (ghost-padded grids "
+                                       "are built once on the host and uploaded)")
+        for k in self.kernel:
+            if k not in DEGREE_TO_EQUATIONS:
+                raise ValueError(f"Unknown kernel :{k}")
+        self.subgrid = _build_subgrids(self.kernel, self.derivative, sg_req)
+        if precompute != 101:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, "precompute != 101 needs generated tables (reference path)")
+        _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation")
+        self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
+        self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120
+        # _build_kernel_sym (constructor.jl:378-398): HigherOrderKernel vs HigherOrderMixedKernel
+        self.perdim = not (len(set(self.kernel)) == 1 and len(set(self.derivative)) == 1)
+        L = lib()
+        # ---- subsystem 1: ghost-padded coefficients + extended knots, on the host ----
+        v = np.asfortranarray(values)
+        cshape = tuple(s + 2 * (e - 1) for s, e in zip(v.shape, self.eqs))
+        self.coefs = np.zeros(cshape, dtype=self.dtype, order="F")
+        n = (C.c_int64 * nd)(*v.shape)
+        hh = (C.c_double * nd)(*self.h)
+        kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in self.kernel])
+        bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in self.bc])
+        br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in self.bc])
+        check(L.cib200_build_coefs(nd, self.dtype_id, n, v.ctypes.data, hh, kid, bl, br, self.coefs.ctypes.data))
+        self.knots = []
+        for d in range(nd):
+            ext = np.zeros(cshape[d])
+            check(L.cib200_extend_knots(self.knots_in[d].ctypes.data, len(self.knots_in[d]), self.eqs[d] - 1,
+                                        ext.ctypes.data))
+            self.knots.append(ext)
+        self.knots = tuple(self.knots)
+        # ---- upload ----
+        desc = _lib.ItpDesc()
+        desc.ndim = nd
+        desc.dtype = self.dtype_id
+        for d in range(nd):
+            desc.coef_shape[d] = cshape[d]
+            desc.knots[d] = self.knots[d].ctypes.data
+            desc.h[d] = self.h[d]
+            desc.kernel[d] = KERNEL_IDS[self.kernel[d]]
+            desc.deriv[d] = int(self.derivative[d])
+        desc.coefs = self.coefs.ctypes.data
+        desc.extrap = EXTRAP_IDS[_extrap]
+        desc.perdim = int(self.perdim)
+        handle = C.c_void_p()
+        check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
+        self._handle = handle
+        self.set_eval_mode(eval_mode)
+
+    def set_eval_mode(self, mode):
+        check(lib().cib200_itp_set_eval_mode(self._handle, _lib.EVAL_MODES[mode]))
+        self.eval_mode = mode
+
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            lib().cib200_itp_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ConvolutionExtrapolation:
+    """data_structures/convolution_extrapolation.jl:28-31 + the call operators of
+    convolution_extrapolate/extrapolation_operator.jl."""
+
+    def __init__(self, itp, et):
+        self.itp = itp
+        self.et = et
+
+    # -- itp.(xs, ys, zs): element-wise over equally shaped coordinate arrays --------------------
+    def eval(self, *xs, out=None):
+        itp = self.itp
+        if len(xs) != itp.ndim:
+            raise ValueError(f"expected {itp.ndim} coordinate arrays, got {len(xs)}")
+        L = lib()
+        bad = C.c_int64(-1)
+        if _is_torch(xs[0]):
+            import torch
+            tdt = torch.float32 if itp.dtype_id == _lib.F32 else torch.float64
+            xs = [x.to(tdt).contiguous() for x in xs]
+            if not all(x.is_cuda for x in xs):
+                raise ValueError("torch inputs must be CUDA tensors (use numpy arrays for host buffers)")
+            shape = xs[0].shape
+            nq = xs[0].numel()
+            if any(x.numel() != nq for x in xs):
+                raise ValueError("coordinate tensors must have the same number of elements")
+            if out is None:
+                out = torch.empty(shape, dtype=tdt, device=xs[0].device)
+            ptrs = (C.c_void_p * itp.ndim)(*[x.data_ptr() for x in xs])
+            check(L.cib200_itp_eval(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE,
+                                    _stream_ptr(xs[0]), None))
+            return out
+        ndt = _np_dtype(itp.dtype_id)
+        xs = np.broadcast_arrays(*[np.asarray(x, dtype=ndt) for x in xs])
+        shape = xs[0].shape
+        xs = [np.ascontiguousarray(x).reshape(-1) for x in xs]
+        nq = xs[0].size
+        if out is None:
+            out = np.empty(nq, dtype=ndt)
+        ptrs = (C.c_void_p * itp.ndim)(*[x.ctypes.data for x in xs])
+        check(L.cib200_itp_eval(itp._handle, nq, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
+        return out.reshape(shape)
+
+    # -- itp(x, y, z): scalars, or vectors -> Cartesian product ---------------------------------
+    def __call__(self, *xs):
+        itp = self.itp
+        if len(xs) != itp.ndim:
+            raise ValueError(f"expected {itp.ndim} coordinates, got {len(xs)}")
+        if all(np.ndim(x) == 0 and not _is_torch(x) for x in xs):
+            return float(self.eval(*[np.array([x]) for x in xs])[0])
+        L = lib()
+        bad = C.c_int64(-1)
+        ndt = _np_dtype(itp.dtype_id)
+        vs = [np.ascontiguousarray(np.atleast_1d(np.asarray(x, dtype=ndt))) for x in xs]
+        if any(v.ndim != 1 for v in vs):
+            raise ValueError("itp(xs...) takes scalars or vectors; use itp.eval(...) for element-wise evaluation")
+        n = (C.c_int64 * itp.ndim)(*[v.size for v in vs])
+        out = np.zeros(tuple(v.size for v in vs), dtype=ndt, order="F")
+        ptrs = (C.c_void_p * itp.ndim)(*[v.ctypes.data for v in vs])
+        check(L.cib200_itp_eval_grid(itp._handle, n, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
+        return out
+
+
+def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=101, extrap=None, bc="detect",
+                              derivative=0, subgrid="cubic", lazy=False, boundary_fallback=False, dtype=None,
+                              eval_mode="auto"):
+    """convolution_interpolation(knots, values; kernel, fast, precompute, extrap, bc, derivative, subgrid,
+    lazy, boundary_fallback)  -  convolution_interpolation_function.jl:79-157"""
+    values = np.asarray(values)
+    nd = values.ndim
+    knots_t = _knots_tuple(knots, nd)
+    kernels = _ntuple(kernel, nd, str, "kernel")
+    derivs = _ntuple(derivative, nd, (int, np.integer), "derivative")
+    bcs = _norm_bc(bc, nd)
+    extrap = Throw() if extrap is None else extrap
+    is_integral = any(d == -1 for d in derivs)
+    is_nonuniform = any(not is_uniform_grid(np.asarray(k, dtype=np.float64)) for k in knots_t) or \
+        any(k == "n3" for k in kernels)
+    if is_nonuniform:
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, "non-uniform grids stay on the reference path (fast=false)")
+    if is_integral:
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, "antiderivatives (derivative=-1) stay on the reference path")
+    if not fast:
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, "fast=false (direct kernel evaluation) stays on the reference path")
+    # :poly -> :linear when a dimension has too few points (:135-143)
+    fixed = []
+    for d in range(nd):
+        b = bcs[d]
+        if "poly" in b and values.shape[d] < MINIMUM_POLYNOMIAL_BC_POINTS.get(kernels[d], 2):
+            b = ("linear", "linear") if b == ("poly", "poly") else (("linear", b[1]) if b[0] == "poly" else (b[0], "linear"))
+        fixed.append(b)
+    if isinstance(extrap, Natural) or _sym(extrap) == "natural":
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, "extrap=:natural is not on the accelerated path")
+    et = _extrap_type(extrap)
+    itp = FastConvolutionInterpolation(knots_t, values, kernel=kernels, precompute=precompute, bc=tuple(fixed),
+                                       derivative=derivs, subgrid=subgrid, lazy=lazy,
+                                       boundary_fallback=boundary_fallback, dtype=dtype, eval_mode=eval_mode,
+                                       _extrap=et.name)
+    return ConvolutionExtrapolation(itp, et)
+
+
+def _sweep_io(values, dtype):
+    """returns (dtype_id, memkind, in_ptr, make_out(shape), stream, keepalive)"""
+    if _is_torch(values):
+        import torch
+        if not values.is_cuda:
+            raise ValueError("torch inputs must be CUDA tensors (use numpy arrays for host buffers)")
+        tdt = values.dtype if values.dtype in (torch.float32, torch.float64) else torch.float64
+        if dtype is not None:
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+        # Julia order = column-major: a torch tensor indexed [i1, i2, ...] is laid out with axis 0 contiguous
+        v = values.to(tdt)
+        vt = v.permute(*reversed(range(v.dim()))).contiguous()  # memory == column-major of v
+        did = _lib.F32 if tdt == torch.float32 else _lib.F64
+
+        def make_out(shape):
+            o = torch.empty(tuple(reversed(shape)), dtype=tdt, device=values.device)
+            return o, C.c_void_p(o.data_ptr()), lambda: o.permute(*reversed(range(o.dim())))
+        return did, _lib.DEVICE, C.c_void_p(vt.data_ptr()), make_out, _stream_ptr(values), vt
+    v = np.asarray(values)
+    if v.dtype not in (np.float32, np.float64):
+        v = v.astype(np.float64)
+    if dtype is not None:
+        v = v.astype(np.dtype(dtype))
+    v = np.asfortranarray(v)
+    did = _lib.F32 if v.dtype == np.float32 else _lib.F64
+
+    def make_out(shape):
+        o = np.zeros(shape, dtype=v.dtype, order="F")
+        return o, C.c_void_p(o.ctypes.data), lambda: o
+    return did, _lib.HOST, C.c_void_p(v.ctypes.data), make_out, None, v
+
+
+def convolution_resample(knots_in, knots_out, values, precompute=101, kernel="b13", derivative=0, bc="detect",
+                         subgrid="cubic", dtype=None):
+    """convolution_resample(knots_in, knots_out, values; precompute, kernel, derivative, bc, subgrid)
+    convolution_resample.jl:65-238 (front-ends) -> :240-386 (internal, replaced by cib200_resample)."""
+    nd = values.dim() if _is_torch(values) else np.ndim(values)
+    shape_in = tuple(values.shape)
+    kin = _knots_tuple(knots_in, nd, "knots_in")
+    kout = _knots_tuple(knots_out, nd, "knots_out")
+    kernels = _ntuple(kernel, nd, str, "kernel")
+    derivs = _ntuple(derivative, nd, (int, np.integer), "derivative")
+    sgs = _ntuple(subgrid, nd, str, "subgrid")
+    bcs = _norm_bc(bc, nd)
+    for d in range(nd):  # :213-224
+        if sgs[d] != "linear" and kernels[d] in ("a0", "a1"):
+            raise ValueError(f"Cannot use {sgs[d]} subgrid with {kernels[d]} kernel. Use :linear instead.")
+    for d in range(nd):
+        if derivs[d] < 0:
+            raise ValueError("convolution_resample does not support antiderivatives (derivative=-1). "
+                             "Use convolution_interpolation with derivative=-1 instead.")
+    if precompute != 101:
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, "precompute != 101 needs generated tables (reference path)")
+    sgs_valid = _build_subgrids(kernels, derivs, sgs)  # :226
+    _require_accelerated(kernels, derivs, sgs_valid, nd, "convolution_resample")
+    did, memkind, in_ptr, make_out, stream, keep = _sweep_io(values, dtype)
+    ndt = _np_dtype(did)
+    # T.(knots): :183-188
+    kin = [np.ascontiguousarray(np.asarray(k).astype(ndt).astype(np.float64)) for k in kin]
+    kout = [np.ascontiguousarray(np.asarray(k).astype(ndt).astype(np.float64)) for k in kout]
+    for d in range(nd):
+        if len(kin[d]) != shape_in[d]:
+            raise ValueError(f"knots_in[{d}] has {len(kin[d])} points but values has {shape_in[d]}")
+    shape_out = tuple(len(k) for k in kout)
+    out, out_ptr, view = make_out(shape_out)
+    n_in = (C.c_int64 * nd)(*shape_in)
+    n_out = (C.c_int64 * nd)(*shape_out)
+    kinp = (C.c_void_p * nd)(*[k.ctypes.data for k in kin])
+    koutp = (C.c_void_p * nd)(*[k.ctypes.data for k in kout])
+    kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in kernels])
+    dv = (C.c_int32 * nd)(*[int(d) for d in derivs])
+    bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
+    br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
+    check(lib().cib200_resample(nd, did, n_in, n_out, in_ptr, out_ptr, kinp, koutp, kid, dv, bl, br, memkind, stream))
+    del keep
+    return view()
+
+
+def convolution_smooth(knots, values, B, dtype=None):
+    """convolution_smooth(knots, values, B) - convolution_gaussian_smoothing.jl:45-131"""
+    nd = values.dim() if _is_torch(values) else np.ndim(values)
+    shape = tuple(values.shape)
+    ks = _knots_tuple(knots, nd)
+    B = float(B)
+    did, memkind, in_ptr, make_out, stream, keep = _sweep_io(values, dtype)
+    ndt = _np_dtype(did)
+    E = lib().cib200_smooth_halfwidth(B)
+    for d in range(nd):  # :50-56
+        n = len(ks[d])
+        if E >= n:
+            raise ValueError(f"Gaussian stencil half-width ({E} points) exceeds grid size (n={n}) in dimension {d + 1}. "
+                             f"Use a larger B (currently B={B}) or more grid points (need n > {E}).")
+        if n != shape[d]:
+            raise ValueError(f"knots[{d}] has {n} points but values has {shape[d]}")
+    h = (C.c_double * nd)(*[float(ndt(k[1]) - ndt(k[0])) for k in ks])  # T(knots[d][2] - knots[d][1]), :72
+    out, out_ptr, view = make_out(shape)
+    n = (C.c_int64 * nd)(*shape)
+    check(lib().cib200_smooth(nd, did, n, in_ptr, out_ptr, h, B, memkind, stream))
+    del keep
+    return view()

@@ -1,0 +1,773 @@
+// cib200_api.cu - the C-ABI (include/cib200.h): handles, uploads, host-side coefficient builder,
+// host<->device pipelining of batched evaluation.  No CPU evaluation path exists in this library.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "cib200_internal.cuh"
+#include "cib200_tables.inc"
+
+namespace cib {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int kernel_eqs(int kernel) {
+  switch (kernel) {
+    case CIB200_B5: return 5;
+    case CIB200_B7: return 6;
+    case CIB200_B9: return 7;
+    case CIB200_B11: return 8;
+    case CIB200_B13: return 9;
+    default: return -1;
+  }
+}
+int kernel_max_deriv_table(int kernel) {
+  switch (kernel) {
+    case CIB200_B5: return 3;
+    case CIB200_B7: return 4;
+    case CIB200_B9: return 5;
+    case CIB200_B11: return 6;
+    case CIB200_B13: return 6;
+    default: return -1;
+  }
+}
+int kernel_max_eval_deriv(int kernel) {
+  switch (kernel) {
+    case CIB200_B5: return 2;
+    case CIB200_B7: return 3;
+    case CIB200_B9: return 4;
+    case CIB200_B11: return 5;
+    case CIB200_B13: return 5;
+    default: return -1;
+  }
+}
+const double *host_table(int kernel, int d) {
+  static const double *const b5[] = {CIB_TAB_b5_d0, CIB_TAB_b5_d1, CIB_TAB_b5_d2, CIB_TAB_b5_d3};
+  static const double *const b7[] = {CIB_TAB_b7_d0, CIB_TAB_b7_d1, CIB_TAB_b7_d2, CIB_TAB_b7_d3, CIB_TAB_b7_d4};
+  static const double *const b9[] = {CIB_TAB_b9_d0, CIB_TAB_b9_d1, CIB_TAB_b9_d2,
+                                     CIB_TAB_b9_d3, CIB_TAB_b9_d4, CIB_TAB_b9_d5};
+  static const double *const b11[] = {CIB_TAB_b11_d0, CIB_TAB_b11_d1, CIB_TAB_b11_d2, CIB_TAB_b11_d3,
+                                      CIB_TAB_b11_d4, CIB_TAB_b11_d5, CIB_TAB_b11_d6};
+  static const double *const b13[] = {CIB_TAB_b13_d0, CIB_TAB_b13_d1, CIB_TAB_b13_d2, CIB_TAB_b13_d3,
+                                      CIB_TAB_b13_d4, CIB_TAB_b13_d5, CIB_TAB_b13_d6};
+  if (d < 0 || d > kernel_max_deriv_table(kernel)) return nullptr;
+  switch (kernel) {
+    case CIB200_B5: return b5[d];
+    case CIB200_B7: return b7[d];
+    case CIB200_B9: return b9[d];
+    case CIB200_B11: return b11[d];
+    case CIB200_B13: return b13[d];
+    default: return nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side ghost fill (north_star subsystem 1).  Restates, independently of the oracle,
+// apply_boundary_conditions_for_dim! (convolution_coefs/create_convolutional_coefs.jl:200-370) with
+// fill_ghost_points_polynomial! (:408-441); matrices of polynomial_boundary.jl:29-179 are the
+// Lagrange extrapolation weights to x = -j from nodes 0..m-1 and are generated, not tabulated.
+// Compiled with -ffp-contract=off so the mean / matrix-vector sums are plain mul+add.
+// ---------------------------------------------------------------------------------------------
+static void extrap_row(int m, int j, double *row) {
+  for (int k = 0; k < m; ++k) {
+    long long num = 1, den = 1;
+    for (int i = 0; i < m; ++i)
+      if (i != k) {
+        num *= (long long)(-j - i);
+        den *= (long long)(k - i);
+      }
+    row[k] = (double)(num / den);
+  }
+}
+
+static inline int poly_nodes(int kernel) { return kernel == CIB200_B5 ? 6 : 8; }
+
+// decides the matrix width for one side of one line; p = first (left) / last (right) `ns` centred values
+static int choose_nodes(const double *s, long long n, double h, int kernel, int bc, bool right) {
+  const int ns = poly_nodes(kernel);
+  bool use_poly = false;
+  if (n >= ns && (bc == CIB200_BC_DETECT || bc == CIB200_BC_POLY)) {
+    if (bc == CIB200_BC_POLY) {
+      use_poly = true;
+    } else {
+      const double *p = right ? s + (n - ns) : s;
+      double d1[8], d2[8];
+      double mn = INFINITY, mx = -INFINITY;
+      for (int d = 0; d < ns - 1; ++d) {
+        d1[d] = p[d + 1] - p[d];
+        mn = std::fmin(mn, d1[d]);
+        mx = std::fmax(mx, d1[d]);
+      }
+      bool periodic = (mn * mx) / (h * h) < -1.0 / 10;
+      mn = INFINITY, mx = -INFINITY;
+      for (int d = 0; d < ns - 2; ++d) {
+        d2[d] = d1[d + 1] - d1[d];
+        mn = std::fmin(mn, d2[d]);
+        mx = std::fmax(mx, d2[d]);
+      }
+      bool high_curv = std::fabs(mx - mn) / h > 1.0 / 2;
+      bool high_d3 = false;
+      if (ns > 4) {
+        mn = INFINITY, mx = -INFINITY;
+        for (int d = 0; d < ns - 3; ++d) {
+          double v = d2[d + 1] - d2[d];
+          mn = std::fmin(mn, v);
+          mx = std::fmax(mx, v);
+        }
+        high_d3 = std::fabs(mx - mn) / h > 1.0 / 2;
+      }
+      use_poly = !periodic && !high_curv && !high_d3;
+    }
+  }
+  if (use_poly) return ns;
+  if (bc == CIB200_BC_QUADRATIC) return 3;
+  return 2;  // :linear, failed :detect, too few points
+}
+
+template <typename T>
+static void fill_line(T *line0, long long stride, long long n, double h, int eqs, int kernel, int bcl,
+                      int bcr, double *slice) {
+  double sum = 0.0;
+  for (long long j = 0; j < n; ++j) {
+    slice[j] = (double)line0[j * stride];
+    sum += slice[j];
+  }
+  const double mean = sum / (double)n;
+  for (long long j = 0; j < n; ++j) slice[j] -= mean;
+  for (int side = 0; side < 2; ++side) {
+    const int m = choose_nodes(slice, n, h, kernel, side ? bcr : bcl, side != 0);
+    double y[8], row[8];
+    for (int k = 0; k < m; ++k) y[k] = side ? slice[n - 1 - k] : slice[k];
+    for (int j = 1; j <= eqs - 1; ++j) {
+      extrap_row(m, j, row);
+      double acc = 0.0;
+      for (int k = 0; k < m; ++k) acc += row[k] * y[k];
+      const double gval = mean + acc;
+      if (side == 0) line0[-(long long)j * stride] = (T)gval;
+      else line0[(n - 1 + j) * stride] = (T)gval;
+    }
+  }
+}
+
+template <typename T>
+static int build_coefs_t(int ndim, const int64_t *n, const T *vs, const double *h, const int32_t *kernel,
+                         const int32_t *bcl, const int32_t *bcr, T *c) {
+  int eqs[CIB200_MAX_SWEEP_DIM];
+  long long cs[CIB200_MAX_SWEEP_DIM], cstr[CIB200_MAX_SWEEP_DIM];
+  long long ctot = 1, vtot = 1, nmax = 0;
+  for (int d = 0; d < ndim; ++d) {
+    eqs[d] = kernel_eqs(kernel[d]);
+    if (eqs[d] < 0) {
+      set_error("cib200_build_coefs: unknown kernel id %d on axis %d", kernel[d], d);
+      return CIB200_EINVAL;
+    }
+    if (n[d] < 3) {
+      set_error("cib200_build_coefs: axis %d has %lld points (< 3)", d, (long long)n[d]);
+      return CIB200_EINVAL;
+    }
+    cs[d] = n[d] + 2 * (eqs[d] - 1);
+    cstr[d] = ctot;
+    ctot *= cs[d];
+    vtot *= n[d];
+    nmax = std::max<long long>(nmax, n[d]);
+  }
+  std::fill(c, c + ctot, (T)0);
+  // interior copy, row of axis 0 at a time
+  const long long rows = vtot / n[0];
+  for (long long r = 0; r < rows; ++r) {
+    long long rem = r, off = (long long)(eqs[0] - 1);
+    for (int d = 1; d < ndim; ++d) {
+      long long id = rem % n[d];
+      rem /= n[d];
+      off += (id + eqs[d] - 1) * cstr[d];
+    }
+    memcpy(c + off, vs + r * n[0], sizeof(T) * (size_t)n[0]);
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nthreads = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+  for (int fd = 0; fd < ndim; ++fd) {
+    const long long nlines = ctot / cs[fd];
+    auto work = [&](int tid) {
+      std::vector<double> slice((size_t)nmax);
+      for (long long ln = tid; ln < nlines; ln += nthreads) {
+        long long rem = ln, off = 0;
+        for (int d = 0; d < ndim; ++d) {
+          if (d == fd) continue;
+          long long id = rem % cs[d];
+          rem /= cs[d];
+          off += id * cstr[d];
+        }
+        off += (long long)(eqs[fd] - 1) * cstr[fd];
+        fill_line(c + off, cstr[fd], n[fd], h[fd], eqs[fd], kernel[fd], bcl[fd], bcr[fd], slice.data());
+      }
+    };
+    if (nthreads == 1 || nlines < 64) {
+      for (int t = 0; t < nthreads; ++t) work(t);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
+      for (auto &th : pool) th.join();
+    }
+  }
+  return CIB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int current_device(int *dev) {
+  CIB_CUDA(cudaGetDevice(dev));
+  return CIB200_OK;
+}
+
+static size_t esize(int dtype) { return dtype == CIB200_F32 ? 4 : 8; }
+
+static int fetch_status(cib200_itp *h, cudaStream_t st, int64_t *first_bad, int *code) {
+  EvalStatus hs;
+  CIB_CUDA(cudaMemcpyAsync(&hs, h->d_status, sizeof hs, cudaMemcpyDeviceToHost, st));
+  CIB_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long none = std::numeric_limits<unsigned long long>::max();
+  *code = CIB200_OK;
+  long long idx = -1;
+  if (hs.first_oob != none || hs.first_nan != none) {
+    if (hs.first_nan < hs.first_oob) {
+      *code = CIB200_ENAN;
+      idx = (long long)hs.first_nan;
+    } else {
+      *code = CIB200_EOOB;
+      idx = (long long)hs.first_oob;
+    }
+  }
+  if (first_bad) *first_bad = idx;
+  return CIB200_OK;
+}
+
+static int reset_status(cib200_itp *h, cudaStream_t st) {
+  CIB_CUDA(cudaMemsetAsync(h->d_status, 0xff, sizeof(EvalStatus), st));
+  return CIB200_OK;
+}
+
+static int ensure_stage(cib200_itp *h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return CIB200_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+    h->d_stage[i] = nullptr;
+  }
+  h->stage_bytes = 0;
+  for (int i = 0; i < 2; ++i) CIB_CUDA(cudaMalloc(&h->d_stage[i], bytes));
+  h->stage_bytes = bytes;
+  if (!h->streams[0]) {
+    for (int i = 0; i < 2; ++i) {
+      CIB_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+      CIB_CUDA(cudaEventCreateWithFlags(&h->events[i], cudaEventDisableTiming));
+    }
+  }
+  return CIB200_OK;
+}
+
+static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st) {
+  int mode = h->eval_mode;
+  if (mode == CIB200_EVAL_AUTO) mode = CIB200_EVAL_GATHER;
+  if (mode == CIB200_EVAL_BINNED) {
+    if (!binned_supported(h) || c.grid) {
+      set_error("cib200_itp_eval: BINNED strategy needs a 3-D f64 b5 interpolant and a point list");
+      return CIB200_EUNSUPPORTED;
+    }
+    return launch_eval_binned(h, c, out, nq, st);
+  }
+  return launch_eval(h, c, out, nq, st);
+}
+
+}  // namespace cib
+
+using namespace cib;
+
+extern "C" {
+
+int32_t cib200_version(void) { return 100; }
+const char *cib200_last_error(void) { return g_err; }
+int64_t cib200_launch_count(void) { return g_launches.load(); }
+
+const double *cib200_kernel_table(int32_t kernel, int32_t deriv, int32_t *eqs_out) {
+  if (eqs_out) *eqs_out = kernel_eqs(kernel);
+  return host_table(kernel, deriv);
+}
+
+int32_t cib200_smooth_halfwidth(double B) {
+  // convolution_gaussian_smoothing.jl:46
+  return (int32_t)std::ceil(std::sqrt(-std::log(1e-12 / 2) / B));
+}
+
+int32_t cib200_extend_knots(const double *knots, int64_t n, int32_t n_extra, double *out) {
+  if (!knots || !out || n < 2 || n_extra < 0) {
+    set_error("cib200_extend_knots: bad arguments");
+    return CIB200_EINVAL;
+  }
+  const double step_start = knots[1] - knots[0];
+  const double step_end = knots[n - 1] - knots[n - 2];
+  for (int i = n_extra; i >= 1; --i) out[n_extra - i] = knots[0] - (double)i * step_start;
+  for (int64_t i = 0; i < n; ++i) out[n_extra + i] = knots[i];
+  for (int i = 1; i <= n_extra; ++i) out[n_extra + n - 1 + i] = knots[n - 1] + (double)i * step_end;
+  return CIB200_OK;
+}
+
+int32_t cib200_build_coefs(int32_t ndim, int32_t dtype, const int64_t *n, const void *values, const double *h,
+                           const int32_t *kernel, const int32_t *bc_left, const int32_t *bc_right,
+                           void *coefs_out) {
+  if (ndim < 1 || ndim > CIB200_MAX_SWEEP_DIM || !n || !values || !h || !kernel || !bc_left || !bc_right ||
+      !coefs_out) {
+    set_error("cib200_build_coefs: bad arguments");
+    return CIB200_EINVAL;
+  }
+  for (int d = 0; d < ndim; ++d)
+    if (bc_left[d] < 0 || bc_left[d] > 3 || bc_right[d] < 0 || bc_right[d] > 3) {
+      set_error("cib200_build_coefs: unknown boundary condition on axis %d", d);
+      return CIB200_EINVAL;
+    }
+  if (dtype == CIB200_F32)
+    return build_coefs_t<float>(ndim, n, (const float *)values, h, kernel, bc_left, bc_right, (float *)coefs_out);
+  if (dtype == CIB200_F64)
+    return build_coefs_t<double>(ndim, n, (const double *)values, h, kernel, bc_left, bc_right, (double *)coefs_out);
+  set_error("cib200_build_coefs: unknown dtype %d", dtype);
+  return CIB200_EINVAL;
+}
+
+int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
+  if (!desc || !handle) {
+    set_error("cib200_itp_create: null argument");
+    return CIB200_EINVAL;
+  }
+  *handle = nullptr;
+  if (desc->ndim < 1 || desc->ndim > CIB200_MAX_ITP_DIM) {
+    set_error("cib200_itp_create: ndim=%d outside 1..3 (N>=4 uses the reference's linear-subgrid path)", desc->ndim);
+    return CIB200_EUNSUPPORTED;
+  }
+  if (desc->dtype != CIB200_F64 && desc->dtype != CIB200_F32) {
+    set_error("cib200_itp_create: unknown dtype %d", desc->dtype);
+    return CIB200_EINVAL;
+  }
+  if (desc->extrap < CIB200_THROW || desc->extrap > CIB200_LINE) {
+    set_error("cib200_itp_create: unknown extrapolation %d", desc->extrap);
+    return CIB200_EINVAL;
+  }
+  if (!desc->coefs) {
+    set_error("cib200_itp_create: coefs is null");
+    return CIB200_EINVAL;
+  }
+  const int nd = desc->ndim;
+  int eqs[3] = {1, 1, 1};
+  for (int d = 0; d < nd; ++d) {
+    eqs[d] = kernel_eqs(desc->kernel[d]);
+    if (eqs[d] < 0) {
+      set_error("cib200_itp_create: unknown kernel id %d on axis %d", desc->kernel[d], d);
+      return CIB200_EUNSUPPORTED;
+    }
+    if (desc->deriv[d] < 0 || desc->deriv[d] > kernel_max_eval_deriv(desc->kernel[d])) {
+      set_error("cib200_itp_create: derivative %d on axis %d is outside the shipped cubic-subgrid tables", desc->deriv[d], d);
+      return CIB200_EUNSUPPORTED;
+    }
+    if (desc->coef_shape[d] < 2 * eqs[d] || desc->coef_shape[d] > 0x7fffffffLL || !desc->knots[d]) {
+      set_error("cib200_itp_create: bad coef_shape / knots on axis %d", d);
+      return CIB200_EINVAL;
+    }
+    if (!(desc->h[d] > 0)) {
+      set_error("cib200_itp_create: h[%d] must be positive", d);
+      return CIB200_EINVAL;
+    }
+  }
+  int dev = 0;
+  int rc = current_device(&dev);
+  if (rc) return rc;
+
+  cib200_itp *h = new cib200_itp();
+  memset(h, 0, sizeof *h);
+  h->device = dev;
+  h->dtype = desc->dtype;
+  h->eval_mode = CIB200_EVAL_AUTO;
+  h->perdim = desc->perdim;
+  ItpParams &p = h->p;
+  p.ndim = nd;
+  p.extrap = desc->extrap;
+  long long total = 1;
+  for (int d = 0; d < 3; ++d) {
+    h->cshape[d] = d < nd ? desc->coef_shape[d] : 1;
+    h->kernel[d] = d < nd ? desc->kernel[d] : 0;
+    h->deriv[d] = d < nd ? desc->deriv[d] : 0;
+    p.nk[d] = (int)h->cshape[d];
+    p.eqs[d] = eqs[d];
+    p.h[d] = d < nd ? desc->h[d] : 1.0;
+    total *= h->cshape[d];
+  }
+  p.s1 = h->cshape[0];
+  p.s2 = h->cshape[0] * h->cshape[1];
+  double hmin = p.h[0];
+  for (int d = 1; d < nd; ++d) hmin = std::min(hmin, p.h[d]);
+  p.eps_line = hmin / 100.0;
+  p.scale = 1.0;
+
+#define CIB_CREATE_CUDA(expr)                                                            \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                         \
+      cib200_itp_destroy(h);                                                             \
+      return _e == cudaErrorMemoryAllocation ? CIB200_ENOMEM : CIB200_ECUDA;             \
+    }                                                                                    \
+  } while (0)
+
+  const size_t es = esize(h->dtype);
+  CIB_CREATE_CUDA(cudaMalloc(&h->d_coefs, es * (size_t)total));
+  CIB_CREATE_CUDA(cudaMemcpy(h->d_coefs, desc->coefs, es * (size_t)total, cudaMemcpyHostToDevice));
+  p.coefs = h->d_coefs;
+  for (int d = 0; d < nd; ++d) {
+    CIB_CREATE_CUDA(cudaMalloc(&h->d_knots[d], sizeof(double) * (size_t)h->cshape[d]));
+    CIB_CREATE_CUDA(cudaMemcpy(h->d_knots[d], desc->knots[d], sizeof(double) * (size_t)h->cshape[d], cudaMemcpyHostToDevice));
+    p.knots[d] = h->d_knots[d];
+    p.lo[d] = desc->knots[d][eqs[d] - 1];
+    p.hi[d] = desc->knots[d][h->cshape[d] - 1 - (eqs[d] - 1)];
+  }
+  // distinct (kernel, derivative) tables -> one packed device image
+  struct Slot { int kernel, d; };
+  std::vector<Slot> slots;
+  auto slot_of = [&](int kernel, int d) {
+    for (size_t i = 0; i < slots.size(); ++i)
+      if (slots[i].kernel == kernel && slots[i].d == d) return (int)i;
+    slots.push_back({kernel, d});
+    return (int)slots.size() - 1;
+  };
+  for (int d = 0; d < nd; ++d) {
+    p.tab_slot_k[d] = slot_of(h->kernel[d], h->deriv[d]);
+    p.tab_slot_d[d] = slot_of(h->kernel[d], h->deriv[d] + 1);
+  }
+  p.n_tab_slots = (int)slots.size();
+  size_t tab_doubles = 0;
+  for (auto &s : slots) tab_doubles += (size_t)CIB_TAB_ROWS * 2 * kernel_eqs(s.kernel);
+  CIB_CREATE_CUDA(cudaMalloc(&h->d_tables, sizeof(double) * tab_doubles));
+  size_t off = 0;
+  for (size_t i = 0; i < slots.size(); ++i) {
+    const int e = kernel_eqs(slots[i].kernel);
+    const size_t nelem = (size_t)CIB_TAB_ROWS * 2 * e;
+    CIB_CREATE_CUDA(cudaMemcpy(h->d_tables + off, host_table(slots[i].kernel, slots[i].d), sizeof(double) * nelem, cudaMemcpyHostToDevice));
+    p.tab_slot_eqs[i] = e;
+    p.tab_slot_ptr[i] = h->d_tables + off;
+    off += nelem;
+  }
+  for (int d = 0; d < nd; ++d) {
+    p.tabk[d] = p.tab_slot_ptr[p.tab_slot_k[d]];
+    p.tabd[d] = p.tab_slot_ptr[p.tab_slot_d[d]];
+  }
+  CIB_CREATE_CUDA(cudaMalloc(&h->d_status, sizeof(EvalStatus)));
+  CIB_CREATE_CUDA(cudaMemset(h->d_status, 0xff, sizeof(EvalStatus)));
+#undef CIB_CREATE_CUDA
+  *handle = h;
+  return CIB200_OK;
+}
+
+int32_t cib200_itp_destroy(cib200_itp *h) {
+  if (!h) return CIB200_OK;
+  binned_destroy(h);
+  if (h->d_coefs) cudaFree(h->d_coefs);
+  for (int d = 0; d < 3; ++d)
+    if (h->d_knots[d]) cudaFree(h->d_knots[d]);
+  if (h->d_tables) cudaFree(h->d_tables);
+  if (h->d_status) cudaFree(h->d_status);
+  for (int i = 0; i < 2; ++i) {
+    if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+    if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    if (h->events[i]) cudaEventDestroy(h->events[i]);
+  }
+  if (h->d_bin_scratch) cudaFree(h->d_bin_scratch);
+  delete h;
+  return CIB200_OK;
+}
+
+int32_t cib200_itp_set_eval_mode(cib200_itp *h, int32_t mode) {
+  if (!h || mode < CIB200_EVAL_AUTO || mode > CIB200_EVAL_BINNED) {
+    set_error("cib200_itp_set_eval_mode: bad arguments");
+    return CIB200_EINVAL;
+  }
+  if (mode == CIB200_EVAL_BINNED && !binned_supported(h)) {
+    set_error("cib200_itp_set_eval_mode: BINNED needs a 3-D f64 interpolant with one kernel on all axes");
+    return CIB200_EUNSUPPORTED;
+  }
+  h->eval_mode = mode;
+  return CIB200_OK;
+}
+
+int64_t cib200_itp_scratch_bytes(cib200_itp *h, int64_t nq) {
+  if (!h) return 0;
+  return h->eval_mode == CIB200_EVAL_BINNED ? binned_scratch_bytes(h, nq) : 0;
+}
+
+static int32_t eval_common(cib200_itp *h, const Coords &c_in, long long nq, void *out, int32_t memkind,
+                           void *stream, int64_t *first_bad, const char *who) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nd = h->p.ndim;
+  const size_t es = esize(h->dtype);
+  if (first_bad) *first_bad = -1;
+  if (nq == 0) return CIB200_OK;
+  int rc;
+  if (memkind == CIB200_DEVICE) {
+    if ((rc = reset_status(h, st))) return rc;
+    if ((rc = eval_dispatch(h, c_in, out, nq, st))) return rc;
+    if (first_bad || h->p.extrap == CIB200_THROW) {
+      int code;
+      if ((rc = fetch_status(h, st, first_bad, &code))) return rc;
+      if (code == CIB200_EOOB) set_error("%s: query %lld is outside the interpolation domain (extrap=Throw)", who, first_bad ? (long long)*first_bad : -1LL);
+      if (code == CIB200_ENAN) set_error("%s: query %lld has a NaN/Inf coordinate (InexactError in the reference)", who, first_bad ? (long long)*first_bad : -1LL);
+      return code;
+    }
+    return CIB200_OK;
+  }
+  if (memkind != CIB200_HOST) {
+    set_error("%s: unknown memkind %d", who, memkind);
+    return CIB200_EINVAL;
+  }
+  // host buffers: chunked, double-buffered H2D -> kernel -> D2H on two private streams
+  if (c_in.grid) {
+    // coordinate vectors are tiny: upload them whole, keep the result pipeline chunk-free
+    size_t xbytes = 0;
+    for (int d = 0; d < nd; ++d) xbytes += es * (size_t)c_in.n[d];
+    if ((rc = ensure_stage(h, std::max(xbytes, es * (size_t)nq)))) return rc;
+    cudaStream_t s0 = h->streams[0];
+    Coords c = c_in;
+    char *dst = (char *)h->d_stage[0];
+    for (int d = 0; d < nd; ++d) {
+      CIB_CUDA(cudaMemcpyAsync(dst, c_in.x[d], es * (size_t)c_in.n[d], cudaMemcpyHostToDevice, s0));
+      c.x[d] = dst;
+      dst += es * (size_t)c_in.n[d];
+    }
+    if ((rc = reset_status(h, s0))) return rc;
+    if ((rc = eval_dispatch(h, c, h->d_stage[1], nq, s0))) return rc;
+    CIB_CUDA(cudaMemcpyAsync(out, h->d_stage[1], es * (size_t)nq, cudaMemcpyDeviceToHost, s0));
+    int code;
+    if ((rc = fetch_status(h, s0, first_bad, &code))) return rc;
+    if (code) set_error("%s: query %lld %s", who, first_bad ? (long long)*first_bad : -1LL, code == CIB200_EOOB ? "is outside the interpolation domain (extrap=Throw)" : "has a NaN/Inf coordinate");
+    return code;
+  }
+  const long long chunk = std::min<long long>(nq, 1LL << 23);
+  // per buffer: nd coordinate chunks + 1 result chunk
+  if ((rc = ensure_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
+  if ((rc = reset_status(h, h->streams[0]))) return rc;
+  CIB_CUDA(cudaStreamSynchronize(h->streams[0]));
+  int buf = 0;
+  for (long long q0 = 0; q0 < nq; q0 += chunk, buf ^= 1) {
+    const long long m = std::min(chunk, nq - q0);
+    cudaStream_t s = h->streams[buf];
+    char *base = (char *)h->d_stage[buf];
+    Coords c = c_in;
+    for (int d = 0; d < nd; ++d) {
+      char *dst = base + es * (size_t)chunk * d;
+      CIB_CUDA(cudaMemcpyAsync(dst, (const char *)c_in.x[d] + es * (size_t)q0, es * (size_t)m, cudaMemcpyHostToDevice, s));
+      c.x[d] = dst;
+    }
+    void *dout = base + es * (size_t)chunk * nd;
+    c.qoff = q0;  // failing queries are reported in absolute numbering
+    if ((rc = eval_dispatch(h, c, dout, m, s))) return rc;
+    CIB_CUDA(cudaMemcpyAsync((char *)out + es * (size_t)q0, dout, es * (size_t)m, cudaMemcpyDeviceToHost, s));
+  }
+  CIB_CUDA(cudaStreamSynchronize(h->streams[0]));
+  CIB_CUDA(cudaStreamSynchronize(h->streams[1]));
+  int code;
+  if ((rc = fetch_status(h, h->streams[0], first_bad, &code))) return rc;
+  if (code)
+    set_error("%s: query %lld %s", who, first_bad ? (long long)*first_bad : -1LL,
+              code == CIB200_EOOB ? "is outside the interpolation domain (extrap=Throw)" : "has a NaN/Inf coordinate");
+  return code;
+}
+
+int32_t cib200_itp_eval(cib200_itp *h, int64_t nq, const void *const *x, void *out, int32_t memkind,
+                        void *stream, int64_t *first_bad) {
+  if (!h || nq < 0 || (nq > 0 && (!x || !out))) {
+    set_error("cib200_itp_eval: bad arguments");
+    return CIB200_EINVAL;
+  }
+  Coords c;
+  memset(&c, 0, sizeof c);
+  for (int d = 0; d < h->p.ndim; ++d) {
+    if (nq > 0 && !x[d]) {
+      set_error("cib200_itp_eval: x[%d] is null", d);
+      return CIB200_EINVAL;
+    }
+    c.x[d] = nq > 0 ? x[d] : nullptr;
+  }
+  c.grid = 0;
+  return eval_common(h, c, nq, out, memkind, stream, first_bad, "cib200_itp_eval");
+}
+
+int32_t cib200_itp_eval_grid(cib200_itp *h, const int64_t *n, const void *const *x, void *out, int32_t memkind,
+                             void *stream, int64_t *first_bad) {
+  if (!h || !n || !x || !out) {
+    set_error("cib200_itp_eval_grid: bad arguments");
+    return CIB200_EINVAL;
+  }
+  Coords c;
+  memset(&c, 0, sizeof c);
+  long long nq = 1;
+  for (int d = 0; d < 3; ++d) c.n[d] = 1;
+  for (int d = 0; d < h->p.ndim; ++d) {
+    if (n[d] < 0 || (n[d] > 0 && !x[d])) {
+      set_error("cib200_itp_eval_grid: bad axis %d", d);
+      return CIB200_EINVAL;
+    }
+    c.x[d] = x[d];
+    c.n[d] = n[d];
+    nq *= n[d];
+  }
+  c.grid = 1;
+  return eval_common(h, c, nq, out, memkind, stream, first_bad, "cib200_itp_eval_grid");
+}
+
+// ---- sweeps -----------------------------------------------------------------------------------
+static int32_t sweep_io(int ndim, int dtype, long long tot_in, long long tot_out, const void *values, void *out,
+                        int memkind, cudaStream_t st, void **d_in, void **d_out, bool *owned) {
+  const size_t es = esize(dtype);
+  *owned = false;
+  if (memkind == CIB200_DEVICE) {
+    *d_in = const_cast<void *>(values);
+    *d_out = out;
+    return CIB200_OK;
+  }
+  if (memkind != CIB200_HOST) {
+    set_error("sweep: unknown memkind %d", memkind);
+    return CIB200_EINVAL;
+  }
+  CIB_CUDA(cudaMalloc(d_in, es * (size_t)tot_in));
+  cudaError_t e = cudaMalloc(d_out, es * (size_t)tot_out);
+  if (e != cudaSuccess) {
+    cudaFree(*d_in);
+    set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+    return CIB200_ENOMEM;
+  }
+  *owned = true;
+  CIB_CUDA(cudaMemcpyAsync(*d_in, values, es * (size_t)tot_in, cudaMemcpyHostToDevice, st));
+  (void)ndim;
+  return CIB200_OK;
+}
+
+int32_t cib200_resample(int32_t ndim, int32_t dtype, const int64_t *n_in, const int64_t *n_out, const void *values,
+                        void *out, const double *const *knots_in, const double *const *knots_out,
+                        const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                        const int32_t *bc_right, int32_t memkind, void *stream) {
+  if (ndim < 1 || ndim > CIB200_MAX_SWEEP_DIM || !n_in || !n_out || !values || !out || !knots_in || !knots_out ||
+      !kernel || !deriv || !bc_left || !bc_right) {
+    set_error("cib200_resample: bad arguments");
+    return CIB200_EINVAL;
+  }
+  if (dtype != CIB200_F64 && dtype != CIB200_F32) {
+    set_error("cib200_resample: unknown dtype %d", dtype);
+    return CIB200_EINVAL;
+  }
+  long long nin[CIB200_MAX_SWEEP_DIM], nout[CIB200_MAX_SWEEP_DIM], tin = 1, tout = 1;
+  int k[CIB200_MAX_SWEEP_DIM], dv[CIB200_MAX_SWEEP_DIM], bl[CIB200_MAX_SWEEP_DIM], br[CIB200_MAX_SWEEP_DIM];
+  for (int d = 0; d < ndim; ++d) {
+    if (kernel_eqs(kernel[d]) < 0) {
+      set_error("cib200_resample: unknown kernel id %d on axis %d", kernel[d], d);
+      return CIB200_EUNSUPPORTED;
+    }
+    if (deriv[d] < 0) {
+      set_error("convolution_resample does not support antiderivatives (derivative=-1)");
+      return CIB200_EINVAL;
+    }
+    if (deriv[d] > kernel_max_eval_deriv(kernel[d])) {
+      set_error("cib200_resample: derivative %d on axis %d needs the linear-subgrid path", deriv[d], d);
+      return CIB200_EUNSUPPORTED;
+    }
+    if (n_in[d] < 3 || n_out[d] < 1 || !knots_in[d] || !knots_out[d] || bc_left[d] < 0 || bc_left[d] > 3 ||
+        bc_right[d] < 0 || bc_right[d] > 3) {
+      set_error("cib200_resample: bad axis %d", d);
+      return CIB200_EINVAL;
+    }
+    nin[d] = n_in[d];
+    nout[d] = n_out[d];
+    tin *= nin[d];
+    tout *= nout[d];
+    k[d] = kernel[d];
+    dv[d] = deriv[d];
+    bl[d] = bc_left[d];
+    br[d] = bc_right[d];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  void *d_in, *d_out;
+  bool owned;
+  int rc = sweep_io(ndim, dtype, tin, tout, values, out, memkind, st, &d_in, &d_out, &owned);
+  if (rc) return rc;
+  rc = sweep_resample(ndim, dtype, nin, nout, d_in, d_out, knots_in, knots_out, k, dv, bl, br, st);
+  if (owned) {
+    if (!rc) {
+      cudaError_t e = cudaMemcpyAsync(out, d_out, esize(dtype) * (size_t)tout, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        set_error("cib200_resample: D2H failed: %s", cudaGetErrorString(e));
+        rc = CIB200_ECUDA;
+      }
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+  }
+  return rc;
+}
+
+int32_t cib200_smooth(int32_t ndim, int32_t dtype, const int64_t *n, const void *values, void *out, const double *h,
+                      double B, int32_t memkind, void *stream) {
+  if (ndim < 1 || ndim > CIB200_MAX_SWEEP_DIM || !n || !values || !out || !h || !(B > 0)) {
+    set_error("cib200_smooth: bad arguments");
+    return CIB200_EINVAL;
+  }
+  if (dtype != CIB200_F64 && dtype != CIB200_F32) {
+    set_error("cib200_smooth: unknown dtype %d", dtype);
+    return CIB200_EINVAL;
+  }
+  const int E = cib200_smooth_halfwidth(B);
+  long long nn[CIB200_MAX_SWEEP_DIM], tot = 1;
+  for (int d = 0; d < ndim; ++d) {
+    if (E >= n[d]) {
+      set_error("Gaussian stencil half-width (%d points) exceeds grid size (n=%lld) in dimension %d. Use a larger B (currently B=%g) or more grid points (need n > %d).", E, (long long)n[d], d + 1, B, E);
+      return CIB200_EINVAL;
+    }
+    nn[d] = n[d];
+    tot *= n[d];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  void *d_in, *d_out;
+  bool owned;
+  int rc = sweep_io(ndim, dtype, tot, tot, values, out, memkind, st, &d_in, &d_out, &owned);
+  if (rc) return rc;
+  rc = sweep_smooth(ndim, dtype, nn, d_in, d_out, h, B, st);
+  if (owned) {
+    if (!rc) {
+      cudaError_t e = cudaMemcpyAsync(out, d_out, esize(dtype) * (size_t)tot, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        set_error("cib200_smooth: D2H failed: %s", cudaGetErrorString(e));
+        rc = CIB200_ECUDA;
+      }
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+  }
+  return rc;
+}
+
+int32_t cib200_host_register(void *ptr, size_t bytes) {
+  CIB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return CIB200_OK;
+}
+int32_t cib200_host_unregister(void *ptr) {
+  CIB_CUDA(cudaHostUnregister(ptr));
+  return CIB200_OK;
+}
+
+}  // extern "C"

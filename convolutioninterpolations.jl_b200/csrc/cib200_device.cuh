@@ -1,0 +1,116 @@
+// cib200_device.cuh - device helpers shared by the point-evaluation and sweep kernels.
+#pragma once
+#include "cib200_internal.cuh"
+
+namespace cib {
+
+// Position of x on one axis.  The index arithmetic restates the reference exactly, operation by
+// operation and WITHOUT fma contraction (__d*_rn intrinsics are never contracted), so that cell
+// and table-row indices are the reference's own for every finite input
+// (convolution_fast_interpolation_eager_3d.jl:115-137; same lines in eager_1d/2d, perdim_2d.jl:17-49).
+struct AxisPos {
+  int base;  // 0-based index of the first stencil coefficient: (i - eqs) with Julia's 1-based i
+  int row;   // 0-based lower table row: idx - 1
+  double t;  // fractional position between table rows
+};
+
+__device__ __forceinline__ bool locate_from_knot(double x, double knot0, double h, int eqs, int nk,
+                                                 const double *__restrict__ knots, AxisPos &p) {
+  double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x, knot0), h), 1.0);
+  bool ok = fabs(i_float) < 9.0e18;  // floor(Int, .) throws InexactError otherwise (NaN / Inf)
+  long long i = ok ? (long long)floor(i_float) : (long long)eqs;
+  i = i < eqs ? eqs : i;
+  i = i > nk - eqs ? nk - eqs : i;
+  double knot_i = knots[i - 1];  // the STORED knot, not knot0 + (i-1) h
+  double x_diff_right = __dsub_rn(1.0, __ddiv_rn(__dsub_rn(x, knot_i), h));
+  double cidx = __dadd_rn(__dmul_rn(x_diff_right, (double)(CIB_N_PRE - 1)), 1.0);
+  ok = ok && (fabs(cidx) < 9.0e18);
+  int idx = ok ? (int)floor(cidx) : 1;
+  idx = idx < 1 ? 1 : idx;
+  idx = idx > CIB_N_PRE - 1 ? CIB_N_PRE - 1 : idx;
+  p.base = (int)(i - eqs);
+  p.row = idx - 1;
+  p.t = __dsub_rn(cidx, (double)idx);
+  return ok;
+}
+
+// resample variant: the cell's left knot is COMPUTED (convolution_resample.jl:322-326)
+__device__ __forceinline__ void locate_computed(double x, double x_expanded_1, double h, int eqs,
+                                                long long n_coef, AxisPos &p) {
+  double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x, x_expanded_1), h), 1.0);
+  bool ok = fabs(i_float) < 9.0e18;
+  long long i = ok ? (long long)floor(i_float) : (long long)eqs;
+  i = i < eqs ? eqs : i;
+  i = i > n_coef - eqs ? n_coef - eqs : i;
+  double knot_i = __dadd_rn(x_expanded_1, __dmul_rn((double)(i - 1), h));
+  double x_diff_left = __ddiv_rn(__dsub_rn(x, knot_i), h);
+  double x_diff_right = __dsub_rn(1.0, x_diff_left);
+  double cidx = __dadd_rn(__dmul_rn(x_diff_right, (double)(CIB_N_PRE - 1)), 1.0);
+  int idx = (fabs(cidx) < 9.0e18) ? (int)floor(cidx) : 1;
+  idx = idx < 1 ? 1 : idx;
+  idx = idx > CIB_N_PRE - 1 ? CIB_N_PRE - 1 : idx;
+  p.base = (int)(i - eqs);
+  p.row = idx - 1;
+  p.t = __dsub_rn(cidx, (double)idx);
+}
+
+// cubic Hermite basis (cubic_hermite_interpolation.jl:15-28), h_pre folded into the derivative terms
+struct Hermite {
+  double h00, h01, h10, h11;
+};
+__device__ __forceinline__ Hermite hermite_basis(double t) {
+  const double h_pre = 1.0 / (double)(CIB_N_PRE - 1);
+  double t2 = t * t;
+  Hermite b;
+  b.h00 = 1.0 + t2 * (-3.0 + 2.0 * t);
+  b.h01 = t2 * (3.0 - 2.0 * t);
+  b.h10 = h_pre * (t + t2 * (-2.0 + t));
+  b.h11 = h_pre * (t2 * (t - 1.0));
+  return b;
+}
+
+// One stencil weight.  By linearity of cubic_hermite in (f0, f1, d0, d1) the reference's
+// "4 / 16 / 64 convolved sums, then nested Hermite" equals "Hermite-blend the table rows per axis,
+// then one tensor contraction" (SURVEY.md 3.2); this is that per-axis blended weight.
+__device__ __forceinline__ double blended_weight(const Hermite &b, const double *__restrict__ tk,
+                                                 const double *__restrict__ td, int row, int col, int w) {
+  const double *k0 = tk + row * w + col;
+  const double *d0 = td + row * w + col;
+  return b.h00 * k0[0] + b.h01 * k0[w] + (b.h10 * d0[0] + b.h11 * d0[w]);
+}
+
+// copy the distinct tables of an interpolant into shared memory; returns nothing, fills ptr arrays
+__device__ __forceinline__ void stage_tables(const ItpParams &p, double *smem, const double *tk[3],
+                                             const double *td[3]) {
+  int off[6];
+  int o = 0;
+  for (int s = 0; s < p.n_tab_slots; ++s) {
+    off[s] = o;
+    int nelem = CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
+    const double *src = p.tab_slot_ptr[s];
+    for (int i = threadIdx.x; i < nelem; i += blockDim.x) smem[o + i] = src[i];
+    o += nelem;
+  }
+  for (int d = 0; d < p.ndim; ++d) {
+    tk[d] = smem + off[p.tab_slot_k[d]];
+    td[d] = smem + off[p.tab_slot_d[d]];
+  }
+}
+
+__host__ __device__ inline int tables_smem_doubles(const ItpParams &p) {
+  int o = 0;
+  for (int s = 0; s < p.n_tab_slots; ++s) o += CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
+  return o;
+}
+
+template <typename T>
+__device__ __forceinline__ double load_coord(const Coords &c, int d, long long q, long long qd) {
+  const T *x = (const T *)c.x[d];
+  return (double)x[c.grid ? qd : q];
+}
+
+__device__ __forceinline__ void atomic_min_u64(unsigned long long *addr, unsigned long long v) {
+  atomicMin(addr, v);
+}
+
+}  // namespace cib

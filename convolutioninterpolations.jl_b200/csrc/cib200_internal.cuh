@@ -1,0 +1,112 @@
+// cib200_internal.cuh - shared declarations of the sm_100a library (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "cib200.h"
+
+#define CIB_N_PRE 101
+#define CIB_TAB_ROWS 101
+
+namespace cib {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define CIB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      cib::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CIB200_ECUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define CIB_LAUNCHED() (cib::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---- kernel registry ------------------------------------------------------------------------
+int kernel_eqs(int kernel);              // degree_to_equations.jl:13-25
+int kernel_max_deriv_table(int kernel);  // highest d for which K^(d) is tabulated
+int kernel_max_eval_deriv(int kernel);   // _max_shipped_derivative, get_precomputed_kernel_and_range.jl:33-40
+const double *host_table(int kernel, int d);
+
+// ---- device-side view of one interpolant (passed by value to kernels) -------------------------
+struct ItpParams {
+  const void *coefs;       // T*, column-major with pitches below
+  long long s1, s2;        // element strides of axis 1 / axis 2
+  int ndim;
+  int nk[3];               // padded extents = knot vector lengths
+  int eqs[3];
+  const double *knots[3];  // device
+  const double *tabk[3];   // device, K^(d)    101 x 2 eqs
+  const double *tabd[3];   // device, K^(d+1)
+  int tab_slot_k[3];       // index of the distinct table in the packed smem image
+  int tab_slot_d[3];
+  int n_tab_slots;
+  int tab_slot_eqs[6];     // eqs of each distinct table
+  const double *tab_slot_ptr[6];
+  double h[3];
+  double lo[3], hi[3];     // _domain_bounds, extrapolate_point.jl:172-176
+  double scale;            // prod (-1/h_d)^DO_d, associated as the reference does
+  double eps_line;         // min(h)/100, extrapolate_point.jl:138-139
+  int extrap;
+};
+
+// coordinate source: SoA point list or Cartesian product of per-axis vectors
+struct Coords {
+  const void *x[3];
+  long long n[3];  // grid mode: per-axis lengths
+  int grid;        // 0: x[d][q], 1: x[d][q_d]
+  long long qoff;  // added to q when a failing query is reported (host-chunked calls)
+};
+
+struct EvalStatus {
+  unsigned long long first_oob;
+  unsigned long long first_nan;
+};
+
+}  // namespace cib
+
+// opaque handle behind cib200_itp*
+struct cib200_itp {
+  int device;
+  int dtype;
+  int eval_mode;
+  int perdim;
+  int kernel[3], deriv[3];
+  long long cshape[3];
+  void *d_coefs;
+  double *d_knots[3];
+  double *d_tables;  // packed distinct tables
+  cib::EvalStatus *d_status;
+  cib::ItpParams p;
+  // staging for host-memory calls (lazily allocated)
+  void *d_stage[2];
+  size_t stage_bytes;
+  cudaStream_t streams[2];
+  cudaEvent_t events[2];
+  // scratch for the binned strategy (lazily allocated, grows)
+  void *d_bin_scratch;
+  size_t bin_scratch_bytes;
+  void *bin_state;  // opaque, owned by cib200_binned.cu
+};
+
+namespace cib {
+// K1 launchers (cib200_eval.cu)
+int launch_eval(const cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st);
+// binned strategy (cib200_binned.cu)
+bool binned_supported(const cib200_itp *h);
+long long binned_scratch_bytes(const cib200_itp *h, long long nq);
+int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st);
+void binned_destroy(cib200_itp *h);
+// sweeps (cib200_sweep.cu)
+int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *n_out, const void *d_in,
+                   void *d_out, const double *const *knots_in, const double *const *knots_out,
+                   const int *kernel, const int *deriv, const int *bcl, const int *bcr, cudaStream_t st);
+int sweep_smooth(int ndim, int dtype, const long long *n, const void *d_in, void *d_out, const double *h,
+                 double B, cudaStream_t st);
+}  // namespace cib

@@ -1,0 +1,141 @@
+/* cib200.h - C-ABI of the B200 (sm_100a) uniform-grid evaluation library.
+ *
+ * This is the drop-in boundary for the hot path of ConvolutionInterpolations.jl v0.17.0.
+ * The reference is pure Julia and has no FFI today; every entry point below names the Julia
+ * method whose body a maintainer replaces by a `ccall` (see INTEGRATION.md for the glue).
+ * Paths are relative to the reference's src/.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns a cib200_status (0 = OK);
+ *     cib200_last_error() returns the thread-local message of the last failure.
+ *   - all arrays are column-major (axis 0 contiguous) = Julia memory order.
+ *   - dtype CIB200_F64 is the reference precision; CIB200_F32 is the opt-in mode (coefficients,
+ *     queries and results in float; cell / table-row arithmetic stays in double).
+ *   - host pointers are borrowed for the duration of the call; device memory behind a handle is
+ *     owned by the library.  `stream` is a cudaStream_t (NULL = legacy default stream).
+ *   - the library binds to the CUDA device that is current when a handle is created / a sweep
+ *     is called (one process per GPU); there is NO CPU fallback: without a usable device every
+ *     compute entry point fails with CIB200_ECUDA.
+ */
+#ifndef CIB200_H
+#define CIB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CIB200_MAX_ITP_DIM 3
+#define CIB200_MAX_SWEEP_DIM 8
+#define CIB200_N_PRE 101
+
+typedef enum {
+  CIB200_OK = 0,
+  CIB200_EOOB = 1,         /* query outside the domain with extrap = Throw (extrapolate_point.jl:156-159) */
+  CIB200_ENAN = 2,         /* NaN/Inf coordinate: Julia raises InexactError from floor(Int, x)          */
+  CIB200_EINVAL = 3,       /* malformed arguments                                                     */
+  CIB200_EUNSUPPORTED = 4, /* mode outside the accelerated path (glue must keep the Julia method)     */
+  CIB200_ECUDA = 5,        /* CUDA runtime error / no device                                          */
+  CIB200_ENOMEM = 6
+} cib200_status;
+
+typedef enum { CIB200_F64 = 0, CIB200_F32 = 1 } cib200_dtype;
+typedef enum { CIB200_HOST = 0, CIB200_DEVICE = 1 } cib200_memkind;
+typedef enum { CIB200_B5 = 0, CIB200_B7 = 1, CIB200_B9 = 2, CIB200_B11 = 3, CIB200_B13 = 4 } cib200_kernel;
+typedef enum { CIB200_BC_DETECT = 0, CIB200_BC_POLY = 1, CIB200_BC_LINEAR = 2, CIB200_BC_QUADRATIC = 3 } cib200_bc;
+typedef enum { CIB200_THROW = 0, CIB200_FLAT = 1, CIB200_LINE = 2 } cib200_extrap;
+
+/* evaluation strategies of cib200_itp_eval (3-D only; 1-D/2-D always use the direct kernel) */
+typedef enum {
+  CIB200_EVAL_AUTO = 0,
+  CIB200_EVAL_GATHER = 1, /* one warp resolves one query's stencil straight from global memory    */
+  CIB200_EVAL_BINNED = 2  /* queries binned by coefficient brick, bricks staged in smem by TMA     */
+} cib200_eval_mode;
+
+/* One uniform fast interpolant = the numeric fields of FastConvolutionInterpolation
+ * (data_structures/fast_convolution_interpolation.jl:56-102) that the eager cubic-subgrid
+ * evaluators read.  Built by fast_convolution_interpolation_constructor.jl:99-174. */
+typedef struct cib200_itp_desc {
+  int32_t ndim;                          /* 1..3                                                    */
+  int32_t dtype;                         /* cib200_dtype of coefs / queries / results               */
+  int64_t coef_shape[CIB200_MAX_ITP_DIM]; /* size(itp.coefs) = n_d + 2 (eqs_d - 1)                    */
+  const void *coefs;                     /* itp.coefs, ghost-padded, host memory                    */
+  const double *knots[CIB200_MAX_ITP_DIM]; /* itp.knots[d] (extended, length coef_shape[d]), host    */
+  double h[CIB200_MAX_ITP_DIM];           /* itp.h                                                   */
+  int32_t kernel[CIB200_MAX_ITP_DIM];     /* cib200_kernel per axis                                  */
+  int32_t deriv[CIB200_MAX_ITP_DIM];      /* derivative order per axis, 0..max shipped               */
+  int32_t extrap;                        /* cib200_extrap (etp.et)                                  */
+  int32_t perdim;                        /* 0: HigherOrderKernel evaluators, 1: HigherOrderMixedKernel
+                                            (only changes how the final scale is associated)        */
+} cib200_itp_desc;
+
+typedef struct cib200_itp cib200_itp; /* opaque */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int32_t cib200_version(void);
+const char *cib200_last_error(void);
+/* number of kernel launches issued by this library since process start (bench bookkeeping) */
+int64_t cib200_launch_count(void);
+/* 101 x 2*eqs row-major table K^(deriv) of `kernel` (host pointer into the library image); the same
+ * numbers as precomputed_kernels/kernel_<k>.jl (KERNEL_PRE_<k>_d<deriv>). NULL if not shipped. */
+const double *cib200_kernel_table(int32_t kernel, int32_t deriv, int32_t *eqs_out);
+
+/* ---- subsystem 1: ghost-padded coefficient grid, built on the HOST -------------------------- */
+/* replaces create_convolutional_coefs (convolution_coefs/create_convolutional_coefs.jl:141-160).
+ * values: n[0] x ... x n[ndim-1]; coefs_out: (n[d] + 2 (eqs_d - 1)) per axis, caller-allocated. */
+int32_t cib200_build_coefs(int32_t ndim, int32_t dtype, const int64_t *n, const void *values,
+                           const double *h, const int32_t *kernel, const int32_t *bc_left,
+                           const int32_t *bc_right, void *coefs_out);
+/* replaces extend_vector (convolution/extend_vector.jl:10-18); out has n + 2 n_extra entries */
+int32_t cib200_extend_knots(const double *knots, int64_t n, int32_t n_extra, double *out);
+
+/* ---- subsystem 2+3: batched point evaluation ------------------------------------------------ */
+/* uploads coefficient grid, knots and tables once (replaces nothing: called by the glue right after
+ * _build_fast_uniform_convolution, fast_convolution_interpolation_constructor.jl:99-174). */
+int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle);
+int32_t cib200_itp_destroy(cib200_itp *handle);
+int32_t cib200_itp_set_eval_mode(cib200_itp *handle, int32_t mode);
+
+/* itp.(xs...) : replaces the per-element loop over
+ * (etp::ConvolutionExtrapolation)(x::Vararg{Number,N}) (convolution_extrapolate/extrapolation_operator.jl:31-63)
+ * -> extrapolate_point (extrapolate_point.jl:41-160) -> eager evaluators
+ * (convolution_fast_interpolation_eager_{1d,2d,3d}.jl, ..._perdim_{2d,3d}.jl).
+ * x: ndim SoA coordinate arrays of nq elements, out: nq results, all of `memkind`.
+ * first_bad (may be NULL): lowest query index that raised CIB200_EOOB / CIB200_ENAN, else -1.
+ * With memkind = DEVICE the call is asynchronous on `stream` unless first_bad != NULL or
+ * extrap = Throw (the status needs the device's answer). */
+int32_t cib200_itp_eval(cib200_itp *handle, int64_t nq, const void *const *x, void *out,
+                        int32_t memkind, void *stream, int64_t *first_bad);
+
+/* itp(xs, ys, zs) with vectors: Cartesian product
+ * ((etp)(x::Vararg{AbstractArray,N}), extrapolation_operator.jl:66-99). out: n[0] x ... column-major */
+int32_t cib200_itp_eval_grid(cib200_itp *handle, const int64_t *n, const void *const *x, void *out,
+                             int32_t memkind, void *stream, int64_t *first_bad);
+
+/* bytes of device scratch the BINNED strategy needs for nq queries (0 for the other modes) */
+int64_t cib200_itp_scratch_bytes(cib200_itp *handle, int64_t nq);
+
+/* ---- subsystem 4: separable axis sweeps ------------------------------------------------------ */
+/* replaces convolution_resample_internal (convolution/convolution_resample.jl:240-386), cubic subgrid.
+ * values: n_in[0] x ...; out: n_out[0] x ...; knots_in[d] / knots_out[d]: HOST arrays (always). */
+int32_t cib200_resample(int32_t ndim, int32_t dtype, const int64_t *n_in, const int64_t *n_out,
+                        const void *values, void *out, const double *const *knots_in,
+                        const double *const *knots_out, const int32_t *kernel, const int32_t *deriv,
+                        const int32_t *bc_left, const int32_t *bc_right, int32_t memkind, void *stream);
+
+/* replaces convolution_smooth (convolution/convolution_gaussian_smoothing.jl:45-126).
+ * h[d] = knots[d][2] - knots[d][1]. Fails with CIB200_EINVAL when the half-width E >= n[d] (:50-56). */
+int32_t cib200_smooth(int32_t ndim, int32_t dtype, const int64_t *n, const void *values, void *out,
+                      const double *h, double B, int32_t memkind, void *stream);
+int32_t cib200_smooth_halfwidth(double B);
+
+/* ---- pinned host memory helpers for the glue (GC-rooted Julia arrays can be registered) ------- */
+int32_t cib200_host_register(void *ptr, size_t bytes);
+int32_t cib200_host_unregister(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIB200_H */

@@ -305,6 +305,8 @@ static inline double cubic_hermite(double t, double f0, double f1, double d0, do
   return h00 * f0 + h01 * f1 + h * (h10 * d0 + h11 * d1);
 }
 
+typedef double v4d __attribute__((vector_size(32), aligned(32)));
+
 typedef struct {
   int64_t i;   /* 1-based cell index into the extended knots / padded coefs */
   int64_t idx; /* 1-based lower table row */
@@ -402,44 +404,55 @@ static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, doub
     return ORC_OK;
   }
 
-  /* 3-D */
+  /* 3-D: eager_3d.jl:181-305 / perdim_3d.jl:12-159.  The 64 accumulators s_{x}{y}{z}_{bx}{by}{bz} are kept in a
+   * flat array s[iz*16 + iy*4 + ix] with i? = type*2 + bracket (0: f0, 1: f1, 2: d0, 3: d1); every accumulator
+   * receives ((coef*kx)*ky)*kz in the reference's n -> m -> l loop order, so each sum is bit-identical to the
+   * literal code while the compiler is free to vectorise ACROSS accumulators. */
   const int ex = tb->eqs[0], ey = tb->eqs[1], ez = tb->eqs[2];
   const int64_t s1 = it->cshape[0], s2 = it->cshape[0] * it->cshape[1];
-  double s[2][2][2][2][2][2]; /* [xt][yt][zt][bx][by][bz] */
-  memset(s, 0, sizeof s);
+  double s[64];
+  v4d sv[16];
+  memset(sv, 0, sizeof sv);
+  double kxs[18][4] __attribute__((aligned(32))); /* the four x-table entries per tap (loop-invariant loads of eager_3d.jl:224-229) */
+  for (int l = -(ex - 1); l <= ex; ++l) {
+    int col_x = l + ex;
+    kxs[col_x - 1][0] = TAB(tb->kp[0], p[0].idx, col_x, ex);
+    kxs[col_x - 1][1] = TAB(tb->kp[0], p[0].idx + 1, col_x, ex);
+    kxs[col_x - 1][2] = TAB(tb->kd[0], p[0].idx, col_x, ex);
+    kxs[col_x - 1][3] = TAB(tb->kd[0], p[0].idx + 1, col_x, ex);
+  }
   for (int n = -(ez - 1); n <= ez; ++n) {
     int col_z = n + ez;
-    double kz[2][2] = {{TAB(tb->kp[2], p[2].idx, col_z, ez), TAB(tb->kp[2], p[2].idx + 1, col_z, ez)},
-                       {TAB(tb->kd[2], p[2].idx, col_z, ez), TAB(tb->kd[2], p[2].idx + 1, col_z, ez)}};
+    const double kz4[4] = {TAB(tb->kp[2], p[2].idx, col_z, ez), TAB(tb->kp[2], p[2].idx + 1, col_z, ez),
+                           TAB(tb->kd[2], p[2].idx, col_z, ez), TAB(tb->kd[2], p[2].idx + 1, col_z, ez)};
     for (int m = -(ey - 1); m <= ey; ++m) {
       int col_y = m + ey;
-      double ky[2][2] = {{TAB(tb->kp[1], p[1].idx, col_y, ey), TAB(tb->kp[1], p[1].idx + 1, col_y, ey)},
-                         {TAB(tb->kd[1], p[1].idx, col_y, ey), TAB(tb->kd[1], p[1].idx + 1, col_y, ey)}};
-      for (int l = -(ex - 1); l <= ex; ++l) {
-        double coef = it->coefs[(p[0].i + l - 1) + (p[1].i + m - 1) * s1 + (p[2].i + n - 1) * s2];
-        int col_x = l + ex;
-        double kx[2][2] = {{TAB(tb->kp[0], p[0].idx, col_x, ex), TAB(tb->kp[0], p[0].idx + 1, col_x, ex)},
-                           {TAB(tb->kd[0], p[0].idx, col_x, ex), TAB(tb->kd[0], p[0].idx + 1, col_x, ex)}};
-        for (int tx = 0; tx < 2; ++tx)
-          for (int bx = 0; bx < 2; ++bx) {
-            double cx = coef * kx[tx][bx];
-            for (int ty = 0; ty < 2; ++ty)
-              for (int by = 0; by < 2; ++by) {
-                double cxy = cx * ky[ty][by];
-                for (int tz = 0; tz < 2; ++tz)
-                  for (int bz = 0; bz < 2; ++bz) s[tx][ty][tz][bx][by][bz] += cxy * kz[tz][bz];
-              }
-          }
+      const double ky4[4] = {TAB(tb->kp[1], p[1].idx, col_y, ey), TAB(tb->kp[1], p[1].idx + 1, col_y, ey),
+                             TAB(tb->kd[1], p[1].idx, col_y, ey), TAB(tb->kd[1], p[1].idx + 1, col_y, ey)};
+      const double *crow = it->coefs + (p[0].i - ex) + (p[1].i + m - 1) * s1 + (p[2].i + n - 1) * s2;
+      for (int c = 0; c < 2 * ex; ++c) {
+        const double coef = crow[c];
+        const double *kx4 = kxs[c];
+        /* cx = coef*kx (4 lanes), then per (iy, iz): s[iz][iy][0..3] += (cx*ky[iy])*kz[iz] - same products,
+         * same order of the two multiplications and the addition as the reference's scalar statements */
+        v4d cx = (v4d){coef, coef, coef, coef} * *(const v4d *)kx4;
+        for (int j = 0; j < 4; ++j) {
+          v4d cxy = cx * (v4d){ky4[j], ky4[j], ky4[j], ky4[j]};
+          for (int k = 0; k < 4; ++k) sv[k * 4 + j] += cxy * (v4d){kz4[k], kz4[k], kz4[k], kz4[k]};
+        }
       }
     }
   }
+  memcpy(s, sv, sizeof s);
+#define S3(tx, bx, ty, by, tz, bz) s[((tz)*2 + (bz)) * 16 + ((ty)*2 + (by)) * 4 + ((tx)*2 + (bx))]
   double v[2][2][2][2]; /* [yt][zt][by][bz] */
   for (int ty = 0; ty < 2; ++ty)
     for (int tz = 0; tz < 2; ++tz)
       for (int by = 0; by < 2; ++by)
         for (int bz = 0; bz < 2; ++bz)
-          v[ty][tz][by][bz] = cubic_hermite(p[0].t, s[0][ty][tz][0][by][bz], s[0][ty][tz][1][by][bz],
-                                            s[1][ty][tz][0][by][bz], s[1][ty][tz][1][by][bz], h_pre);
+          v[ty][tz][by][bz] = cubic_hermite(p[0].t, S3(0, 0, ty, by, tz, bz), S3(0, 1, ty, by, tz, bz),
+                                            S3(1, 0, ty, by, tz, bz), S3(1, 1, ty, by, tz, bz), h_pre);
+#undef S3
   double w[2][2]; /* [zt][bz] */
   for (int tz = 0; tz < 2; ++tz)
     for (int bz = 0; bz < 2; ++bz)

@@ -236,6 +236,8 @@ class Interpolant:
             raise OracleError(f"orc_itp_eval rc={rc}")
         return out
 
+    eval = eval_points
+
     def __call__(self, *xs):
         if all(np.ndim(x) == 0 for x in xs):
             return float(self.eval_points(*[np.array([x]) for x in xs])[0])

@@ -1,0 +1,229 @@
+"""Parity of the CUDA point-evaluation path (through the C-ABI) with the CPU oracle on the same seeded inputs.
+
+Tolerance (north_star): <= 1e-12 relative in Float64, <= 1e-5 in Float32.  "Relative" is measured against
+max(|ref|, S) with S = max|coefs| * prod_d (1/h_d)^DO_d - the magnitude of the terms being summed - because
+results of sin-product fixtures cross zero.  For Line-extrapolated queries the
+reference formula f_b + (f_b - f_in)/eps * dist amplifies ANY rounding difference by dist/eps, so S is scaled
+by (1 + 2 dist/eps) for those queries; the amplification is a property of the formula, not of either side.
+"""
+import numpy as np
+import pytest
+
+from .conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 1e-5
+
+
+def _field(shape, rng, noise=0.05):
+    grids = np.meshgrid(*[np.linspace(0, 2 * np.pi, n) for n in shape], indexing="ij")
+    f = np.ones(shape)
+    for i, g in enumerate(grids):
+        f = f * (np.sin(g + 0.3 * i) if i % 2 == 0 else np.cos(g))
+    return f + noise * rng.uniform(-1, 1, shape)
+
+
+def _scale(oitp):
+    s = np.abs(oitp.coefs).max()
+    for h, d in zip(oitp.h, oitp.derivs):
+        s *= (1.0 / h) ** d
+    return s
+
+
+def _line_amplification(oitp, xs):
+    lo = np.array([k[e - 1] for k, e in zip(oitp.knots, oitp.eqs)])
+    hi = np.array([k[-e] for k, e in zip(oitp.knots, oitp.eqs)])
+    X = np.stack(xs)
+    cl = np.clip(X, lo[:, None], hi[:, None])
+    dist = np.sqrt(((X - cl) ** 2).sum(axis=0))
+    return 1.0 + 2.0 * dist / (min(oitp.h) / 100.0)
+
+
+def _compare(ci, oracle, knots, vals, xs, tol=TOL64, dtype=None, **kw):
+    o = oracle.convolution_interpolation(knots, vals, **kw)
+    g = ci.convolution_interpolation(knots, vals, dtype=dtype, **kw)
+    ref = o.eval(*xs)
+    got = g.eval(*xs)
+    S = _scale(o)
+    amp = _line_amplification(o, xs) if kw.get("extrap") == "line" else 1.0
+    err = rel_err(got, ref, S * amp)
+    assert np.isfinite(got).all()
+    assert err.max() <= tol, (err.max(), int(err.argmax()))
+    return got, ref, g, o
+
+
+def test_c1_1d_b5_n1000_1e6_queries(ci, oracle):
+    """BASELINE config 1 at full size."""
+    rng = np.random.default_rng(0xC1B200 + 1)
+    x = np.linspace(0, 1, 1000)
+    v = np.sin(2 * np.pi * x) + 0.1 * rng.uniform(-1, 1, 1000)
+    q = rng.uniform(0, 1, 1_000_000)
+    for bc in ("detect", "poly"):
+        _compare(ci, oracle, x, v, (q,), kernel="b5", bc=bc)
+
+
+def test_c2_2d_b5_derivative_line_extrapolation(ci, oracle):
+    """BASELINE config 2 (200^2, derivative=(1,0) -> per-dim path, Line extrapolation), 10^6 of the 10^7 queries."""
+    rng = np.random.default_rng(0xC1B200 + 2)
+    x = np.linspace(0, 2 * np.pi, 200)
+    v = np.sin(x)[:, None] * np.cos(x)[None, :] + 0.05 * rng.uniform(-1, 1, (200, 200))
+    q = rng.uniform(-0.1 * 2 * np.pi, 1.1 * 2 * np.pi, (2, 1_000_000))
+    got, ref, g, o = _compare(ci, oracle, (x, x), v, (q[0], q[1]), kernel="b5", derivative=(1, 0), extrap="line")
+    assert o.perdim and g.itp.perdim
+    outside = (q < 0).any(axis=0) | (q > 2 * np.pi).any(axis=0)
+    assert 0.2 < outside.mean() < 0.4  # ~31 % of the queries exercise the Line branch
+    _compare(ci, oracle, (x, x), v, (q[0][:200_000], q[1][:200_000]), kernel="b5", derivative=(1, 0),
+             extrap="line", bc="linear")
+
+
+@pytest.mark.parametrize("extrap", ["throw", "flat", "line"])
+def test_c5_small_3d_b5(ci, oracle, extrap):
+    """BASELINE config 5 at oracle-sized dimensions: 3-D :b5, 64^3 grid, :detect ghosts, warp-cooperative kernel."""
+    rng = np.random.default_rng(0xC1B200 + 5)
+    shape = (64, 60, 56)
+    knots = tuple(np.linspace(0, 1, n) for n in shape)
+    v = _field(shape, rng, noise=0.01)
+    lo, hi = (0.0, 1.0) if extrap == "throw" else (-0.08, 1.08)
+    q = rng.uniform(lo, hi, (3, 100_003))  # ragged: not a multiple of the 32-query warp tile
+    _compare(ci, oracle, knots, v, tuple(q), kernel="b5", extrap=extrap)
+
+
+@pytest.mark.parametrize("kernel,deriv,bc", [("b13", (1, 0, 0), "detect"), ("b13", 0, "poly"), ("b7", (0, 2, 1), "linear"),
+                                             ("b9", 1, "quadratic"), ("b11", (0, 0, 3), "detect"), ("b5", (2, 2, 2), "poly")])
+def test_3d_kernels_and_derivatives(ci, oracle, kernel, deriv, bc):
+    rng = np.random.default_rng(11)
+    shape = (26, 24, 28)
+    knots = (np.linspace(0, 1, 26), np.linspace(-1, 1, 24), np.linspace(2, 5, 28))
+    v = _field(shape, rng)
+    q = np.stack([rng.uniform(k[0], k[-1], 8000) for k in knots])
+    _compare(ci, oracle, knots, v, tuple(q), kernel=kernel, derivative=deriv, bc=bc)
+
+
+def test_mixed_kernels_per_axis_use_the_generic_path(ci, oracle):
+    rng = np.random.default_rng(12)
+    shape = (22, 25, 21)
+    knots = tuple(np.linspace(0, 1, n) for n in shape)
+    v = _field(shape, rng)
+    q = rng.uniform(0, 1, (3, 5000))
+    _compare(ci, oracle, knots, v, tuple(q), kernel=("b5", "b13", "b7"), derivative=(0, 1, 0), extrap="line")
+    v2 = _field((30, 33), rng)
+    k2 = (np.linspace(0, 1, 30), np.linspace(0, 2, 33))
+    q2 = np.stack([rng.uniform(-0.1, 1.1, 20000), rng.uniform(-0.1, 2.1, 20000)])
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=("b13", "b5"), extrap="flat")
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=("b7", "b7"), derivative=(1, 1), extrap="line")
+
+
+@pytest.mark.parametrize("kernel", ["b5", "b7", "b9", "b11", "b13"])
+def test_1d_2d_all_b_kernels(ci, oracle, kernel):
+    rng = np.random.default_rng(13)
+    x = np.linspace(-2, 3, 77)
+    v = np.cos(1.7 * x) + 0.03 * rng.standard_normal(77)
+    q = rng.uniform(-2.3, 3.3, 50_000)
+    for d in (0, 1, 2):
+        _compare(ci, oracle, x, v, (q,), kernel=kernel, derivative=d, extrap="line")
+    v2 = _field((40, 35), rng)
+    k2 = (np.linspace(0, 1, 40), np.linspace(0, 1, 35))
+    q2 = rng.uniform(0, 1, (2, 30_000))
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=kernel)
+
+
+def test_boundary_and_edge_queries(ci, oracle):
+    """queries exactly on knots, on the domain bounds, within 1 ulp of cell boundaries, and far outside"""
+    rng = np.random.default_rng(14)
+    x = np.linspace(0, 1, 33)
+    v = rng.random(33)
+    edge = np.concatenate([x, np.nextafter(x, 2), np.nextafter(x, -2), [0.0, 1.0, -5.0, 7.5, 1e6, -1e6]])
+    for extrap in ("flat", "line"):
+        _compare(ci, oracle, x, v, (edge,), extrap=extrap)
+    inside = edge[(edge >= 0) & (edge <= 1)]
+    _compare(ci, oracle, x, v, (inside,), extrap="throw")
+    k3 = (x, x, x)
+    v3 = _field((33, 33, 33), rng)
+    e3 = np.stack([rng.choice(inside, 4000), rng.choice(inside, 4000), rng.choice(inside, 4000)])
+    _compare(ci, oracle, k3, v3, tuple(e3))
+
+
+def test_throw_reports_first_offending_query(ci, oracle):
+    x = np.linspace(0, 1, 50)
+    g = ci.convolution_interpolation(x, np.sin(x))
+    q = np.full(100_000, 0.5)
+    q[[70_001, 90_000]] = 1.5
+    with pytest.raises(ci.DomainError, match="query 70001 "):
+        g.eval(q)
+    q[123] = np.nan
+    with pytest.raises(ci.InexactError, match="query 123 "):
+        g.eval(q)
+    g3 = ci.convolution_interpolation((x, x, x), np.zeros((50, 50, 50)), extrap="flat")
+    q3 = np.full((3, 1000), 0.5)
+    q3[1, 777] = np.inf  # Flat clamps +Inf; Line would produce NaN -> InexactError in the reference
+    assert np.isfinite(g3.eval(*q3)).all()
+    g3l = ci.convolution_interpolation((x, x, x), np.zeros((50, 50, 50)), extrap="line")
+    with pytest.raises(ci.InexactError, match="query 777 "):
+        g3l.eval(*q3)
+    with pytest.raises(oracle.OracleError, match="query 777"):
+        oracle.convolution_interpolation((x, x, x), np.zeros((50, 50, 50)), extrap="line").eval(*q3)
+
+
+def test_empty_and_tiny_batches(ci, oracle):
+    x = np.linspace(0, 1, 20)
+    v3 = np.random.default_rng(3).random((20, 20, 20))
+    g = ci.convolution_interpolation((x, x, x), v3)
+    assert g.eval(np.empty(0), np.empty(0), np.empty(0)).shape == (0,)
+    o = oracle.convolution_interpolation((x, x, x), v3)
+    for n in (1, 2, 31, 32, 33):
+        q = np.random.default_rng(n).uniform(0, 1, (3, n))
+        assert rel_err(g.eval(*q), o.eval(*q), 1.0).max() <= TOL64
+
+
+def test_cartesian_product_call(ci, oracle):
+    rng = np.random.default_rng(15)
+    k = (np.linspace(0, 1, 20), np.linspace(0, 2, 24), np.linspace(-1, 0, 22))
+    v = rng.random((20, 24, 22))
+    g = ci.convolution_interpolation(k, v, extrap="line")
+    o = oracle.convolution_interpolation(k, v, extrap="line")
+    xs = (rng.uniform(-0.1, 1.1, 17), rng.uniform(0, 2, 9), rng.uniform(-1, 0, 13))
+    got, ref = g(*xs), o(*xs)
+    assert got.shape == (17, 9, 13)
+    amp = _line_amplification(o, [a.ravel() for a in np.meshgrid(*xs, indexing="ij")]).reshape(got.shape)
+    assert rel_err(got, ref, amp).max() <= TOL64
+    assert g(0.3, 1.1, -0.5) == pytest.approx(o(0.3, 1.1, -0.5), rel=1e-12)
+
+
+def test_device_resident_queries(ci, oracle):
+    import torch
+    rng = np.random.default_rng(16)
+    k = tuple(np.linspace(0, 1, 40) for _ in range(3))
+    v = _field((40, 40, 40), rng)
+    g = ci.convolution_interpolation(k, v, extrap="flat")
+    q = rng.uniform(-0.05, 1.05, (3, 50_000))
+    tq = [torch.from_numpy(a).cuda() for a in q]
+    out = g.eval(*tq)
+    assert out.is_cuda and out.dtype == torch.float64
+    host = g.eval(*q)
+    assert np.array_equal(out.cpu().numpy(), host)  # same kernel, same bits, whichever side the buffers live
+    o = oracle.convolution_interpolation(k, v, extrap="flat")
+    assert rel_err(host, o.eval(*q), _scale(o)).max() <= TOL64
+
+
+def test_float32_opt_in_mode(ci, oracle):
+    """Float32 mode has no same-precision reference (the reference's shipped tables are Float64 only,
+    SURVEY.md 4); its bound is <= 1e-5 against the Float64 result."""
+    rng = np.random.default_rng(17)
+    k = tuple(np.linspace(0, 1, 48) for _ in range(3))
+    v = _field((48, 48, 48), rng).astype(np.float32)
+    q = rng.uniform(0, 1, (3, 40_000)).astype(np.float32)
+    o = oracle.convolution_interpolation(k, v.astype(np.float64), bc="poly")
+    g = ci.convolution_interpolation(k, v, bc="poly")
+    assert g.itp.dtype == np.float32
+    got = g.eval(*q)
+    assert got.dtype == np.float32
+    ref = o.eval(*[a.astype(np.float64) for a in q])
+    assert rel_err(got, ref, _scale(o)).max() <= TOL32
+    x = np.linspace(0, 1, 300).astype(np.float32)
+    v1 = np.sin(6 * x).astype(np.float32)
+    q1 = rng.uniform(0, 1, 10_000).astype(np.float32)
+    g1 = ci.convolution_interpolation(x, v1, derivative=1, bc="poly")
+    o1 = oracle.convolution_interpolation(x.astype(np.float64), v1.astype(np.float64), derivative=1, bc="poly")
+    assert rel_err(g1.eval(q1), o1.eval(q1.astype(np.float64)), _scale(o1)).max() <= TOL32

@@ -22,6 +22,7 @@ What it does
   4. writes
        oracle/kernel_polys.json                  exact rationals (oracle input)
        tests/golden/shipped_tables.npz           the shipped literals (golden KAT)
+       tests/golden/ghost_matrices.json          the integer ghost matrices (golden KAT)
        convolutioninterpolations.jl_b200/csrc/cib200_tables.inc   C hex-float arrays
        oracle/oracle_tables.inc                  same data for the C oracle
 
@@ -133,6 +134,26 @@ def read_shipped(kernel):
     return out
 
 
+def read_ghost_matrices():
+    """integer ghost matrices: convolution_coefs/polynomial_boundary.jl:29-131,157-179"""
+    src = open(f"{REF}/convolution_coefs/polynomial_boundary.jl").read()
+    out = {}
+
+    def rows_of(body):
+        rows = []
+        for line in body.splitlines():
+            line = line.split("#")[0].strip().rstrip(";").strip()
+            if line:
+                rows.append([float(x) for x in line.split()])
+        return rows
+    for m in re.finditer(r":(\w+)\s*=>\s*\[(.*?)\]", src, re.S):
+        out["poly_" + m.group(1)] = rows_of(m.group(2))
+    for name, key in (("LINEAR_GHOST_MATRIX", "linear"), ("QUADRATIC_GHOST_MATRIX", "quadratic")):
+        m = re.search(rf"const {name} = \[(.*?)\n\]", src, re.S)
+        out[key] = rows_of(m.group(1))
+    return out
+
+
 def c_array(name, arr):
     flat = arr.reshape(-1)
     lines = [f"static const double {name}[{flat.size}] = {{"]
@@ -187,6 +208,7 @@ def main():
     json.dump(polys_json, open(os.path.join(ROOT, "oracle/kernel_polys.json"), "w"), indent=1)
     os.makedirs(os.path.join(ROOT, "tests/golden"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "tests/golden/shipped_tables.npz"), **golden)
+    json.dump(read_ghost_matrices(), open(os.path.join(ROOT, "tests/golden/ghost_matrices.json"), "w"), indent=1)
     print(f"bit-checked {n_checked} shipped doubles in {len(golden)} tables; "
           f"emitted {len(index_rows)} K^(d) tables")
 
