@@ -350,7 +350,10 @@ def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=
     bcs = _norm_bc(bc, nd)
     extrap = Throw() if extrap is None else extrap
     is_integral = any(d == -1 for d in derivs)
-    is_nonuniform = any(not is_uniform_grid(np.asarray(k, dtype=np.float64)) for k in knots_t) or \
+    # is_uniform_grid runs on T.(knots) with rtol 1e-5 for Float32, 1e-10 otherwise (nonuniform.jl:13-25)
+    vdt = np.dtype(dtype) if dtype is not None else (values.dtype if values.dtype == np.float32 else np.dtype(np.float64))
+    rtol = 1e-5 if vdt == np.float32 else 1e-10
+    is_nonuniform = any(not is_uniform_grid(np.asarray(k).astype(vdt).astype(np.float64), rtol) for k in knots_t) or \
         any(k == "n3" for k in kernels)
     if is_nonuniform:
         raise UnsupportedModeError(_lib.EUNSUPPORTED, "non-uniform grids stay on the reference path (fast=false)")
@@ -407,10 +410,23 @@ def _sweep_io(values, dtype):
     return did, _lib.HOST, C.c_void_p(v.ctypes.data), make_out, None, v
 
 
-def convolution_resample(knots_in, knots_out, values, precompute=101, kernel="b13", derivative=0, bc="detect",
-                         subgrid="cubic", dtype=None):
+_UNSET = object()
+
+
+def convolution_resample(knots_in, knots_out, values, precompute=_UNSET, kernel=_UNSET, derivative=_UNSET,
+                         bc=_UNSET, subgrid=_UNSET, dtype=None):
     """convolution_resample(knots_in, knots_out, values; precompute, kernel, derivative, bc, subgrid)
-    convolution_resample.jl:65-238 (front-ends) -> :240-386 (internal, replaced by cib200_resample)."""
+    convolution_resample.jl:65-238 (front-ends) -> :240-386 (internal, replaced by cib200_resample).
+
+    As in Julia, a call WITHOUT keyword arguments dispatches to the kw-less wrappers (:65-172), which pass
+    :b13 / :cubic / 101 / :detect straight to the internal routine for every N <= 10; a call WITH keyword
+    arguments goes through the kw method (:174-238), which runs _build_subgrids (N >= 4 -> :linear)."""
+    kwless = all(a is _UNSET for a in (precompute, kernel, derivative, bc, subgrid))
+    precompute = 101 if precompute is _UNSET else precompute
+    kernel = "b13" if kernel is _UNSET else kernel
+    derivative = 0 if derivative is _UNSET else derivative
+    bc = "detect" if bc is _UNSET else bc
+    subgrid = "cubic" if subgrid is _UNSET else subgrid
     nd = values.dim() if _is_torch(values) else np.ndim(values)
     shape_in = tuple(values.shape)
     kin = _knots_tuple(knots_in, nd, "knots_in")
@@ -428,7 +444,9 @@ def convolution_resample(knots_in, knots_out, values, precompute=101, kernel="b1
                              "Use convolution_interpolation with derivative=-1 instead.")
     if precompute != 101:
         raise UnsupportedModeError(_lib.EUNSUPPORTED, "precompute != 101 needs generated tables (reference path)")
-    sgs_valid = _build_subgrids(kernels, derivs, sgs)  # :226
+    sgs_valid = sgs if kwless else _build_subgrids(kernels, derivs, sgs)  # :226 (kw method only)
+    if kwless and nd > 10:
+        raise TypeError("no method matching convolution_resample for N > 10 without keyword arguments")
     _require_accelerated(kernels, derivs, sgs_valid, nd, "convolution_resample")
     did, memkind, in_ptr, make_out, stream, keep = _sweep_io(values, dtype)
     ndt = _np_dtype(did)

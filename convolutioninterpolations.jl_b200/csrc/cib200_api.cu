@@ -2,6 +2,7 @@
 // host<->device pipelining of batched evaluation.  No CPU evaluation path exists in this library.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -390,6 +391,12 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
   int dev = 0;
   int rc = current_device(&dev);
   if (rc) return rc;
+  // The stencil gather touches 80-byte rows at arbitrary offsets; a smaller L2->DRAM fetch granularity
+  // avoids dragging in the rest of a 64/128-byte block for every partially used sector (a hint).
+  if (const char *fg = getenv("CIB200_L2_FETCH")) {
+    size_t g = (size_t)atoi(fg);
+    if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+  }
 
   cib200_itp *h = new cib200_itp();
   memset(h, 0, sizeof *h);

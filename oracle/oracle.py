@@ -250,9 +250,17 @@ def convolution_interpolation(knots, values, **kw):
     return Interpolant(knots, values, **kw)
 
 
-def convolution_resample(knots_in, knots_out, values, kernel="b13", derivative=0, bc="detect",
-                         subgrid="cubic"):
-    """convolution_resample.jl:174-238 front-end + :240-386 internal."""
+_UNSET = object()
+
+
+def convolution_resample(knots_in, knots_out, values, kernel=_UNSET, derivative=_UNSET, bc=_UNSET,
+                         subgrid=_UNSET):
+    """convolution_resample.jl:65-172 (kw-less wrappers: no _build_subgrids) / :174-238 (kw method) + :240-386."""
+    kwless = all(a is _UNSET for a in (kernel, derivative, bc, subgrid))
+    kernel = "b13" if kernel is _UNSET else kernel
+    derivative = 0 if derivative is _UNSET else derivative
+    bc = "detect" if bc is _UNSET else bc
+    subgrid = "cubic" if subgrid is _UNSET else subgrid
     v = np.asfortranarray(values, dtype=np.float64)
     nd = v.ndim
     kin = _knots_tuple(knots_in, nd)
@@ -260,7 +268,7 @@ def convolution_resample(knots_in, knots_out, values, kernel="b13", derivative=0
     kernels = _ntuple(kernel, nd, str)
     derivs = _ntuple(derivative, nd, int)
     bcs = _norm_bc(bc, nd)
-    sgs = build_subgrids(kernels, derivs, _ntuple(subgrid, nd, str))
+    sgs = _ntuple(subgrid, nd, str) if kwless else build_subgrids(kernels, derivs, _ntuple(subgrid, nd, str))
     for d in range(nd):
         if derivs[d] < 0:
             raise OracleError("convolution_resample does not support antiderivatives")

@@ -221,7 +221,12 @@ def test_float32_opt_in_mode(ci, oracle):
     assert got.dtype == np.float32
     ref = o.eval(*[a.astype(np.float64) for a in q])
     assert rel_err(got, ref, _scale(o)).max() <= TOL32
-    x = np.linspace(0, 1, 300).astype(np.float32)
+    # Float32 knots must pass the reference's uniformity test at rtol 1e-5 (nonuniform.jl:13-25): a
+    # 300-point Float32 linspace does NOT (spacing jitter 3.6e-5) and is routed to the non-uniform path by the
+    # reference too; dyadic knots are exactly uniform in Float32
+    x = (np.arange(257) / 256).astype(np.float32)
+    with pytest.raises(ci.UnsupportedModeError, match="non-uniform"):
+        ci.convolution_interpolation(np.linspace(0, 1, 300).astype(np.float32), np.zeros(300, np.float32))
     v1 = np.sin(6 * x).astype(np.float32)
     q1 = rng.uniform(0, 1, 10_000).astype(np.float32)
     g1 = ci.convolution_interpolation(x, v1, derivative=1, bc="poly")

@@ -124,6 +124,8 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
     with pytest.raises(U):
         v3 = np.zeros((30, 30, 30))
         ci.convolution_interpolation((x, x, x), v3, subgrid=("cubic", "quintic", "cubic"))  # N==3 not all-cubic
+    with pytest.raises(U, match="subgrid"):  # kw method + N >= 4 -> :linear subgrid (reference path)
+        ci.convolution_resample((x,) * 4, (x,) * 4, np.zeros((30,) * 4), kernel="b5")
     with pytest.raises(ValueError, match="antiderivatives"):
         ci.convolution_resample(x, x, v, derivative=-1)
     with pytest.raises(ValueError, match="Cannot use cubic subgrid with a1"):
