@@ -280,7 +280,12 @@ static int ensure_stage(cib200_itp *h, size_t bytes) {
 
 static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st) {
   int mode = h->eval_mode;
-  if (mode == CIB200_EVAL_AUTO) mode = CIB200_EVAL_GATHER;
+  if (mode == CIB200_EVAL_AUTO) {
+    // large point lists: bin by coefficient brick (HBM traffic ~130 B/query instead of ~18 kB for random
+    // queries); small batches cannot amortise one brick load per tile and go straight to the gather kernel
+    const bool big = nq >= (1LL << 22) && nq < 0xffffffffLL;
+    mode = (big && !c.grid && binned_supported(h)) ? CIB200_EVAL_BINNED : CIB200_EVAL_GATHER;
+  }
   if (mode == CIB200_EVAL_BINNED) {
     if (!binned_supported(h) || c.grid) {
       set_error("cib200_itp_eval: BINNED strategy needs a 3-D f64 b5 interpolant and a point list");

@@ -17,199 +17,10 @@
 //
 // Arithmetic: positions exactly as the reference (see cib200_device.cuh); the stencil sum uses the
 // factorised form (per-axis blended weights, FMA) - same polynomial, different association; measured
-// deviation from the literal 64-accumulator form is a few ulp of sum|c w| (tests/test_parity_*.py).
-#include <math_constants.h>
-
-#include "cib200_device.cuh"
+// deviation from the literal 64-accumulator form is a few ulp of sum|c w| (tests/test_gpu_eval.py).
+#include "cib200_evalcore.cuh"
 
 namespace cib {
-
-struct Plan {
-  int ntask;  // 0: failed (err set) or out of range of the batch, 1: one evaluation, 2: Line (boundary, inward)
-  int err;    // 0 none, 1 OOB (Throw), 2 NaN/Inf
-  double dist;
-};
-
-// classification + positions of one query: extrapolation_operator.jl:39-61, extrapolate_point.jl:98-160
-template <int NDIM>
-__device__ __forceinline__ Plan make_plan(const ItpParams &p, const double *x, AxisPos *pa, AxisPos *pb) {
-  Plan pl;
-  pl.ntask = 0;
-  pl.err = 0;
-  pl.dist = 0.0;
-  bool inside = true;
-#pragma unroll
-  for (int d = 0; d < NDIM; ++d)
-    if (x[d] > p.hi[d] || x[d] < p.lo[d]) inside = false;
-  bool ok = true;
-  if (inside) {
-#pragma unroll
-    for (int d = 0; d < NDIM; ++d)
-      ok &= locate_from_knot(x[d], __ldg(p.knots[d]), p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
-    pl.ntask = 1;
-  } else if (p.extrap == CIB200_THROW) {
-    pl.err = 1;
-    return pl;
-  } else {
-    double cl[NDIM];
-#pragma unroll
-    for (int d = 0; d < NDIM; ++d) cl[d] = x[d] < p.lo[d] ? p.lo[d] : (x[d] > p.hi[d] ? p.hi[d] : x[d]);
-    double dist_sq = 0.0;
-    double dx[NDIM];
-#pragma unroll
-    for (int d = 0; d < NDIM; ++d) {
-      dx[d] = __dsub_rn(x[d], cl[d]);
-      dist_sq = __dadd_rn(dist_sq, __dmul_rn(dx[d], dx[d]));
-    }
-#pragma unroll
-    for (int d = 0; d < NDIM; ++d)
-      ok &= locate_from_knot(cl[d], __ldg(p.knots[d]), p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
-    pl.ntask = 1;
-    if (p.extrap == CIB200_LINE && !(dist_sq < 2.220446049250313e-16)) {
-      double dist = __dsqrt_rn(dist_sq);
-#pragma unroll
-      for (int d = 0; d < NDIM; ++d) {
-        double xin = __dsub_rn(cl[d], __ddiv_rn(__dmul_rn(p.eps_line, dx[d]), dist));
-        ok &= locate_from_knot(xin, __ldg(p.knots[d]), p.h[d], p.eqs[d], p.nk[d], p.knots[d], pb[d]);
-      }
-      pl.ntask = 2;
-      pl.dist = dist;
-    }
-  }
-  if (!ok) {
-    pl.ntask = 0;
-    pl.err = 2;
-  }
-  return pl;
-}
-
-// final scale, associated like the reference (eager_1d.jl:113-114, eager_2d.jl:212, eager_3d.jl:304,
-// perdim_2d.jl:24-30/214, perdim_3d.jl:159)
-struct Scale {
-  double s[3];
-  int perdim2d;
-};
-template <int NDIM>
-__device__ __forceinline__ double apply_scale(double r, const Scale &sc) {
-  if (NDIM == 1) return __dmul_rn(r, sc.s[0]);
-  if (NDIM == 2) {
-    if (sc.perdim2d) return __dmul_rn(r, __dmul_rn(__dmul_rn(1.0, sc.s[0]), sc.s[1]));
-    return __dmul_rn(__dmul_rn(r, sc.s[0]), sc.s[1]);
-  }
-  return __dmul_rn(__dmul_rn(__dmul_rn(r, sc.s[0]), sc.s[1]), sc.s[2]);
-}
-
-__device__ __forceinline__ double finish_line(double fb, double fin, double eps, double dist) {
-  double slope = __ddiv_rn(__dsub_rn(fb, fin), eps);  // extrapolate_point.jl:146-148
-  return __dadd_rn(fb, __dmul_rn(slope, dist));
-}
-
-__device__ __forceinline__ void report(EvalStatus *st, int err, long long q) {
-  if (err == 1) atomic_min_u64(&st->first_oob, (unsigned long long)q);
-  if (err == 2) atomic_min_u64(&st->first_nan, (unsigned long long)q);
-}
-
-template <int NDIM>
-__device__ __forceinline__ void decode_coords(const Coords &c, long long q, long long *qd) {
-  if (!c.grid) return;
-  long long r = q;
-#pragma unroll
-  for (int d = 0; d < NDIM; ++d) {
-    qd[d] = r % c.n[d];
-    r /= c.n[d];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// thread-per-query kernel
-// ---------------------------------------------------------------------------------------------
-template <typename T, int NDIM, int E>
-__device__ __forceinline__ double core_thread(const ItpParams &p, const double *const *tk, const double *const *td,
-                                              const AxisPos *pos) {
-  const T *__restrict__ coefs = (const T *)p.coefs;
-  if (E > 0) {
-    constexpr int W = 2 * (E > 0 ? E : 1);
-    double w[NDIM][W];
-#pragma unroll
-    for (int d = 0; d < NDIM; ++d) {
-      Hermite hb = hermite_basis(pos[d].t);
-#pragma unroll
-      for (int l = 0; l < W; ++l) w[d][l] = blended_weight(hb, tk[d], td[d], pos[d].row, l, W);
-    }
-    if (NDIM == 1) {
-      double acc = 0.0;
-#pragma unroll
-      for (int l = 0; l < W; ++l) acc = fma((double)coefs[pos[0].base + l], w[0][l], acc);
-      return acc;
-    }
-    if (NDIM == 2) {
-      double acc = 0.0;
-      const T *c0 = coefs + pos[0].base + (long long)pos[1].base * p.s1;
-#pragma unroll 2
-      for (int m = 0; m < W; ++m) {
-        double a = 0.0;
-#pragma unroll
-        for (int l = 0; l < W; ++l) a = fma((double)c0[l + (long long)m * p.s1], w[0][l], a);
-        acc = fma(a, w[NDIM > 1 ? 1 : 0][m], acc);
-      }
-      return acc;
-    }
-    double acc = 0.0;
-    const T *c0 = coefs + pos[0].base + (long long)pos[NDIM > 1 ? 1 : 0].base * p.s1 +
-                  (long long)pos[NDIM > 2 ? 2 : 0].base * p.s2;
-    for (int n = 0; n < W; ++n) {
-      double an = 0.0;
-      for (int m = 0; m < W; ++m) {
-        double a = 0.0;
-        const T *cr = c0 + (long long)m * p.s1 + (long long)n * p.s2;
-#pragma unroll
-        for (int l = 0; l < W; ++l) a = fma((double)cr[l], w[0][l], a);
-        an = fma(a, w[NDIM > 1 ? 1 : 0][m], an);
-      }
-      acc = fma(an, w[NDIM > 2 ? 2 : 0][n], acc);
-    }
-    return acc;
-  }
-  // generic: per-axis eqs at run time, weights recomputed from the shared-memory tables on the fly
-  Hermite hb[NDIM];
-#pragma unroll
-  for (int d = 0; d < NDIM; ++d) hb[d] = hermite_basis(pos[d].t);
-  const int w0 = 2 * p.eqs[0];
-  if (NDIM == 1) {
-    double acc = 0.0;
-    for (int l = 0; l < w0; ++l)
-      acc = fma((double)coefs[pos[0].base + l], blended_weight(hb[0], tk[0], td[0], pos[0].row, l, w0), acc);
-    return acc;
-  }
-  const int w1 = 2 * p.eqs[NDIM > 1 ? 1 : 0];
-  if (NDIM == 2) {
-    double acc = 0.0;
-    const T *c0 = coefs + pos[0].base + (long long)pos[NDIM > 1 ? 1 : 0].base * p.s1;
-    for (int m = 0; m < w1; ++m) {
-      double a = 0.0;
-      for (int l = 0; l < w0; ++l)
-        a = fma((double)c0[l + (long long)m * p.s1], blended_weight(hb[0], tk[0], td[0], pos[0].row, l, w0), a);
-      acc = fma(a, blended_weight(hb[NDIM > 1 ? 1 : 0], tk[1], td[1], pos[NDIM > 1 ? 1 : 0].row, m, w1), acc);
-    }
-    return acc;
-  }
-  const int w2 = 2 * p.eqs[NDIM > 2 ? 2 : 0];
-  double acc = 0.0;
-  const T *c0 = coefs + pos[0].base + (long long)pos[NDIM > 1 ? 1 : 0].base * p.s1 +
-                (long long)pos[NDIM > 2 ? 2 : 0].base * p.s2;
-  for (int n = 0; n < w2; ++n) {
-    double an = 0.0;
-    for (int m = 0; m < w1; ++m) {
-      double a = 0.0;
-      const T *cr = c0 + (long long)m * p.s1 + (long long)n * p.s2;
-      for (int l = 0; l < w0; ++l)
-        a = fma((double)cr[l], blended_weight(hb[0], tk[0], td[0], pos[0].row, l, w0), a);
-      an = fma(a, blended_weight(hb[NDIM > 1 ? 1 : 0], tk[1], td[1], pos[NDIM > 1 ? 1 : 0].row, m, w1), an);
-    }
-    acc = fma(an, blended_weight(hb[NDIM > 2 ? 2 : 0], tk[2], td[2], pos[NDIM > 2 ? 2 : 0].row, n, w2), acc);
-  }
-  return acc;
-}
 
 template <typename T, int NDIM, int E>
 __global__ void __launch_bounds__(256) eval_thread_kernel(ItpParams p, Coords c, Scale sc, T *__restrict__ out,
@@ -246,41 +57,23 @@ __global__ void __launch_bounds__(256) eval_thread_kernel(ItpParams p, Coords c,
 // ---------------------------------------------------------------------------------------------
 // 3-D warp-cooperative kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ double ldg_as_double(const T *p) {
-  return (double)__ldg(p);
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 template <typename T, int E>
 __global__ void __launch_bounds__(256, 2) eval_warp3d_kernel(ItpParams p, Coords c, Scale sc, T *__restrict__ out,
                                                              long long nq, EvalStatus *status) {
-  constexpr int W = 2 * E;           // taps per axis
-  constexpr int G = 32 / W;          // stencil rows fetched per load instruction
-  constexpr int ACTIVE = W * G;      // lanes that carry a tap
-  constexpr int ROWS = W * W;        // (m, n) rows of the brick
-  constexpr int ITERS = (ROWS + G - 1) / G;
-  constexpr int CHUNK = ITERS < 36 ? ITERS : 32;
-
+  using GM = WarpGeom<E>;
+  constexpr int W = GM::W;
   extern __shared__ double smem[];
   const double *tk[3];
   const double *td[3];
   stage_tables(p, smem, tk, td);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *wyz = smem + tables_smem_doubles(p) + warp * (ROWS + 3 * W);
-  double *wax = wyz + ROWS;  // [3][W] blended weights of the current evaluation point
+  double *wyz = smem + tables_smem_doubles(p) + warp * GM::SMEM_DOUBLES;
+  double *wax = wyz + GM::ROWS;  // [3][W] blended weights of the current evaluation point
   __syncthreads();
 
   const int l = lane % W, g = lane / W;
-  const bool active = lane < ACTIVE;
   const T *__restrict__ coefs = (const T *)p.coefs;
   const long long s1 = p.s1, s2 = p.s2;
-  const long long wrap_adj = s2 - (long long)W * s1;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const long long nbatch = (nq + 31) >> 5;
 
@@ -302,10 +95,9 @@ __global__ void __launch_bounds__(256, 2) eval_warp3d_kernel(ItpParams p, Coords
     }
     double res_a = 0.0, res_b = 0.0;
     // ---- phase 2: the warp resolves the stencils one evaluation point at a time ---------------
-    unsigned todo = __ballot_sync(0xffffffffu, pl.ntask > 0);
-    while (todo) {
-      const int j = __ffs(todo) - 1;
-      todo &= todo - 1;
+    // warp-uniform walk over the 32 lanes (a ballot-driven loop after the divergent planning phase produced
+    // lane-inconsistent trip counts in the binned kernel on sm_100a; the shuffle-broadcast count cannot)
+    for (int j = 0; j < 32; ++j) {
       const int nt = __shfl_sync(0xffffffffu, pl.ntask, j);
       for (int t = 0; t < nt; ++t) {
         int base[3], row[3];
@@ -316,40 +108,9 @@ __global__ void __launch_bounds__(256, 2) eval_warp3d_kernel(ItpParams p, Coords
           row[d] = __shfl_sync(0xffffffffu, t == 0 ? pa[d].row : pb[d].row, j);
           tt[d] = __shfl_sync(0xffffffffu, t == 0 ? pa[d].t : pb[d].t, j);
         }
-        for (int idx = lane; idx < 3 * W; idx += 32) {
-          const int a = idx / W, col = idx - a * W;
-          const double ta = a == 0 ? tt[0] : (a == 1 ? tt[1] : tt[2]);
-          const int ra = a == 0 ? row[0] : (a == 1 ? row[1] : row[2]);
-          Hermite hb = hermite_basis(ta);
-          wax[idx] = blended_weight(hb, a == 0 ? tk[0] : (a == 1 ? tk[1] : tk[2]),
-                                    a == 0 ? td[0] : (a == 1 ? td[1] : td[2]), ra, col, W);
-        }
-        __syncwarp();
-        for (int r = lane; r < ROWS; r += 32) wyz[r] = wax[W + r % W] * wax[2 * W + r / W];
-        const double wx = active ? wax[l] : 0.0;
-        __syncwarp();
+        const double wx = warp_weights<E>(wyz, wax, tk, td, row, tt, lane);
         const T *ptr = coefs + base[0] + l + ((long long)base[1] + g) * s1 + (long long)base[2] * s2;
-        double acc = 0.0;
-#pragma unroll 1
-        for (int it0 = 0; it0 < ITERS; it0 += CHUNK) {
-          double cv[CHUNK];
-#pragma unroll
-          for (int u = 0; u < CHUNK; ++u) {
-            const int r0 = (it0 + u) * G;  // row of lane group 0 in this step
-            const int m0 = r0 % W, n0 = r0 / W;
-            const bool wrap = m0 + g >= W;
-            const bool valid = active && (it0 + u) < ITERS && (r0 + g) < ROWS;
-            const long long off = (long long)m0 * s1 + (long long)n0 * s2 + (wrap ? wrap_adj : 0);
-            cv[u] = valid ? ldg_as_double(ptr + off) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < CHUNK; ++u) {
-            const int r = (it0 + u) * G + g;
-            const double wv = (active && (it0 + u) < ITERS && r < ROWS) ? wyz[r] : 0.0;
-            acc = fma(cv[u], wv, acc);
-          }
-        }
-        const double total = warp_sum(acc * wx);
+        const double total = warp_stencil<E>(ptr, s1, s2, wyz, wx, lane, [](const T *a) { return ldg_as_double(a); });
         if (lane == j) {
           if (t == 0) res_a = total;
           else res_b = total;
@@ -375,7 +136,7 @@ __global__ void __launch_bounds__(256, 2) eval_warp3d_kernel(ItpParams p, Coords
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-static double jl_pow_int(double x, long long n) {  // Julia Base pow_body (math.jl), restated
+double jl_pow_int(double x, long long n) {  // Julia Base pow_body (math.jl), restated
   if (n == 0) return 1.0;
   if (n == 1) return x;
   if (n == 2) return x * x;
@@ -406,7 +167,7 @@ static int set_smem(K kernel, size_t bytes) {
   return CIB200_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -437,8 +198,7 @@ static int launch_thread(const ItpParams &p, const Coords &c, const Scale &sc, v
 template <typename T, int E>
 static int launch_warp3d(const ItpParams &p, const Coords &c, const Scale &sc, void *out, long long nq,
                          EvalStatus *st, cudaStream_t stream) {
-  constexpr int W = 2 * E;
-  size_t smem = sizeof(double) * ((size_t)tables_smem_doubles(p) + 8 * (W * W + 3 * W));
+  size_t smem = sizeof(double) * ((size_t)tables_smem_doubles(p) + 8 * WarpGeom<E>::SMEM_DOUBLES);
   auto kern = eval_warp3d_kernel<T, E>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;

@@ -96,6 +96,8 @@ struct cib200_itp {
 };
 
 namespace cib {
+double jl_pow_int(double x, long long n);  // Julia Base pow_body restated (cib200_eval.cu)
+int sm_count();
 // K1 launchers (cib200_eval.cu)
 int launch_eval(const cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st);
 // binned strategy (cib200_binned.cu)

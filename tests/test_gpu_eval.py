@@ -232,3 +232,52 @@ def test_float32_opt_in_mode(ci, oracle):
     g1 = ci.convolution_interpolation(x, v1, derivative=1, bc="poly")
     o1 = oracle.convolution_interpolation(x.astype(np.float64), v1.astype(np.float64), derivative=1, bc="poly")
     assert rel_err(g1.eval(q1), o1.eval(q1.astype(np.float64)), _scale(o1)).max() <= TOL32
+
+
+@pytest.mark.parametrize("kernel,shape", [("b5", (64, 60, 56)), ("b13", (40, 44, 36)), ("b7", (50, 30, 34))])
+def test_binned_strategy_equals_gather_strategy(ci, oracle, kernel, shape):
+    """The binned strategy (tile binning + TMA-staged bricks) uses the same positions and the same per-axis
+    weights as the direct gather kernel; only the association of the (2E)^3-term sum differs (lanes own
+    different taps), so the two strategies agree to a few ulp of sum|c w| and both meet the parity bound against
+    the oracle.  Queries that need extrapolation go through the spill kernel."""
+    rng = np.random.default_rng(31)
+    knots = tuple(np.linspace(0, 1, n) for n in shape)
+    v = _field(shape, rng, noise=0.02)
+    q = rng.uniform(-0.03, 1.03, (3, 300_007))
+    for extrap in ("flat", "line"):
+        gg = ci.convolution_interpolation(knots, v, kernel=kernel, extrap=extrap, eval_mode="gather")
+        gb = ci.convolution_interpolation(knots, v, kernel=kernel, extrap=extrap, eval_mode="binned")
+        rg, rb = gg.eval(*q), gb.eval(*q)
+        inside = ((q >= 0) & (q <= 1)).all(axis=0)
+        assert inside.sum() > 200_000 and (~inside).sum() > 10_000
+        assert rel_err(rb[inside], rg[inside], np.abs(v).max()).max() <= 1e-14
+        o = oracle.convolution_interpolation(knots, v, kernel=kernel, extrap=extrap)
+        amp = _line_amplification(o, q) if extrap == "line" else 1.0
+        assert rel_err(rb, o.eval(*q), _scale(o) * amp).max() <= TOL64
+    # Throw: error reporting also works through the spill bin
+    gb = ci.convolution_interpolation(knots, v, kernel=kernel, eval_mode="binned")
+    qi = np.clip(q, 0, 1)
+    rg = ci.convolution_interpolation(knots, v, kernel=kernel, eval_mode="gather").eval(*qi)
+    assert rel_err(gb.eval(*qi), rg, np.abs(v).max()).max() <= 1e-14
+    qi[1, 12345] = 1.5
+    with pytest.raises(ci.DomainError, match="query 12345 "):
+        gb.eval(*qi)
+    qi[2, 777] = np.nan
+    with pytest.raises(ci.InexactError, match="query 777 "):
+        gb.eval(*qi)
+
+
+def test_binned_device_resident_and_auto_mode(ci):
+    import torch
+    rng = np.random.default_rng(32)
+    n = 128
+    k = tuple(np.linspace(0, 1, n) for _ in range(3))
+    v = _field((n, n, n), rng)
+    q = [torch.rand(5_000_000, dtype=torch.float64, device="cuda") for _ in range(3)]
+    ga = ci.convolution_interpolation(k, v, bc="poly")                       # auto -> binned for >= 2^22 queries
+    gg = ci.convolution_interpolation(k, v, bc="poly", eval_mode="gather")
+    ra, rg = ga.eval(*q), gg.eval(*q)
+    assert float((ra - rg).abs().max()) <= 1e-14 * float(np.abs(v).max())
+    assert ga.itp.eval_mode == "auto"
+    perm = torch.randperm(5_000_000, device="cuda")
+    assert torch.equal(ga.eval(*[x[perm] for x in q]), ra[perm])            # permutation invariance, bitwise
