@@ -288,15 +288,14 @@ __global__ void __launch_bounds__(512, 1)
   const double k0[3] = {__ldg(p.knots[0]), __ldg(p.knots[1]), __ldg(p.knots[2])};
   const int l = lane % W, gl = lane / W;
   const bool active = lane < ACTIVE;
-  // per-lane brick offsets of the axis-1 taps (an out-of-range tap re-reads tap 0 with weight 0)
-  int koff[KM];
+  // axis-1 taps of this lane; a tap beyond the stencil (only the last k, only when W % G != 0) is predicated off
+  // lanes without a tap (32 - W*G of them) alias the last active lane's addresses: a shared-memory broadcast,
+  // not a bank conflict; their partial sum is discarded
+  const int lane_off = active ? l + gl * PITCH : (W - 1) + (G - 1) * PITCH;
+  const int gle = active ? gl : G - 1;
   bool kval[KM];
 #pragma unroll
-  for (int k = 0; k < KM; ++k) {
-    kval[k] = active && (gl + k * G < W);
-    koff[k] = kval[k] ? k * G * PITCH : 0;
-  }
-  const int lane_off = active ? l + gl * PITCH : 0;
+  for (int k = 0; k < KM; ++k) kval[k] = gle + k * G < W;
   const unsigned total_items = n_items[0];
   unsigned parity = 0;
   for (unsigned iter = 0;; ++iter) {
@@ -383,14 +382,20 @@ __global__ void __launch_bounds__(512, 1)
             const double wx = wq[l];
             double wy[KM];
 #pragma unroll
-            for (int k = 0; k < KM; ++k) wy[k] = kval[k] ? wq[W + gl + k * G] : 0.0;
+            for (int k = 0; k < KM; ++k) wy[k] = ((G - 1) + k * G < W || kval[k]) ? wq[W + gle + k * G] : 0.0;
             const double *base = brick + m.x + lane_off;
             double acc = 0.0;
 #pragma unroll
             for (int n = 0; n < W; ++n) {
               double an = 0.0;
 #pragma unroll
-              for (int k = 0; k < KM; ++k) an = fma(base[koff[k] + n * PLANE], wy[k], an);
+              for (int k = 0; k < KM; ++k) {
+                if ((G - 1) + k * G < W) {  // compile-time: every lane group has this tap
+                  an = fma(base[k * G * PITCH + n * PLANE], wy[k], an);
+                } else if (kval[k]) {       // last, partially populated tap: only the lanes that own it load
+                  an = fma(base[k * G * PITCH + n * PLANE], wy[k], an);
+                }
+              }
               acc = fma(an, wq[2 * W + n], acc);
             }
             part[jj] = active ? acc * wx : 0.0;
