@@ -230,6 +230,7 @@ def main():
     t0 = time.perf_counter()
     itp = ci.convolution_interpolation(knots, vals, kernel="b5", bc="poly", eval_mode=args.mode)
     build_s = time.perf_counter() - t0
+    vmax = float(np.abs(vals).max())
     del vals
 
     # queries generated on the device, per rank: 24 GB in + 8 GB out at 10^9
@@ -268,11 +269,14 @@ def main():
     total_ms_max = float(t.item())
     value = world * nq * args.steps / (total_ms_max * 1e-3)
 
-    # sanity: a strided subsample must be finite and reproduce a second evaluation bit for bit
+    # sanity: a strided subsample re-evaluated on its own (small batch -> direct gather kernel) must agree with
+    # the timed result to a few ulp of the data magnitude (the binned and gather strategies associate the
+    # 1000-term sum differently; both are checked against the oracle to 1e-12 in tests/test_gpu_eval.py)
     sub = slice(0, nq, max(1, nq // 1_000_000))
     chk = itp.eval(*[x[sub].contiguous() for x in xs])
     assert torch.isfinite(chk).all()
-    assert torch.equal(chk, out[sub]), "subsample re-evaluation differs from the timed result"
+    dev_max = float((chk - out[sub]).abs().max())
+    assert dev_max <= 1e-13 * vmax, f"subsample re-evaluation differs from the timed result by {dev_max}"
 
     # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region -----------------------
     e2e = None
@@ -306,11 +310,17 @@ def main():
         kernel_ms = sum(step_ms) / len(step_ms)  # one kernel launch per step: the step IS the kernel
         achieved = BYTES_PER_EVAL * nq / (kernel_ms * 1e-3) / 1e9
         traffic = ncu_traffic_per_eval()
+        binned = itp.itp.eval_mode == "binned" or (itp.itp.eval_mode == "auto" and nq >= (1 << 22))
+        tr = (traffic or {}).get("binned" if binned else "gather", {})
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                    "kernel": "eval_warp3d_kernel<double,5>" if itp.itp.eval_mode != "binned" else "binned pipeline",
-                    "model": f"gather model, {BYTES_PER_EVAL} algorithmic B/eval x {nq} evals per launch",
-                    "peak_source": peak_src, "traffic_source": (traffic or {}).get("source")}
+                    "traffic": tr.get("dram_bytes_per_eval") and tr["dram_bytes_per_eval"] * nq,
+                    "kernel": ("eval_binned_kernel<5> (+ bin_count / bin_scatter passes, all inside the timed step)"
+                               if binned else "eval_warp3d_kernel<double,5>"),
+                    "model": f"gather model, {BYTES_PER_EVAL} algorithmic B/eval x {nq} evals per step; frac > 1 is "
+                             "possible because the binned strategy serves the stencil from shared memory "
+                             "(SURVEY.md 8d): see traffic for the measured DRAM bytes",
+                    "peak_source": peak_src, "traffic_source": tr.get("source"),
+                    "dram_bytes_per_eval_measured": tr.get("dram_bytes_per_eval")}
         cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,

@@ -1,0 +1,168 @@
+# CIB200Glue.jl - the thin `ccall` glue a maintainer adds to ConvolutionInterpolations.jl to route the
+# uniform-grid hot path to libcib200.so (C-ABI: include/cib200.h).  NOT executable in this repository's
+# build container (Julia is not installed there); kept in sync with the header by hand and exercised through
+# the identical ctypes binding in convolutioninterpolations.jl_b200/_lib.py.
+#
+# Nothing of the public API changes: the methods below are added on the reference's own types.
+#   include("CIB200Glue.jl") at the end of src/ConvolutionInterpolations.jl, `using .CIB200Glue`.
+module CIB200Glue
+
+using ..ConvolutionInterpolations: ConvolutionExtrapolation, FastConvolutionInterpolation,
+    HigherOrderKernel, HigherOrderMixedKernel, Throw, Flat, Line, DerivativeOrder
+
+const LIB = get(ENV, "CIB200_LIB", "libcib200.so")
+const KERNEL_ID = Dict(:b5 => 0, :b7 => 1, :b9 => 2, :b11 => 3, :b13 => 4)
+const BC_ID = Dict(:detect => 0, :poly => 1, :linear => 2, :quadratic => 3)
+const MAX_DERIV = Dict(:b5 => 2, :b7 => 3, :b9 => 4, :b11 => 5, :b13 => 5)   # _max_shipped_derivative
+
+# mirror of cib200_itp_desc (include/cib200.h) -------------------------------------------------------
+struct ItpDesc
+    ndim::Int32
+    dtype::Int32
+    coef_shape::NTuple{3,Int64}
+    coefs::Ptr{Cvoid}
+    knots::NTuple{3,Ptr{Float64}}
+    h::NTuple{3,Float64}
+    kernel::NTuple{3,Int32}
+    deriv::NTuple{3,Int32}
+    extrap::Int32
+    perdim::Int32
+end
+
+last_error() = unsafe_string(ccall((:cib200_last_error, LIB), Cstring, ()))
+
+function check(status::Int32)
+    status == 0 && return
+    msg = last_error()
+    status == 1 && error(msg)                    # ErrorException, as extrapolate_point.jl:156-159
+    status == 2 && throw(InexactError(:floor, Int, NaN))  # what floor(Int, NaN) raises in the reference
+    error("cib200 status $status: $msg")
+end
+
+pad3(t::NTuple{N,T}, fill) where {N,T} = ntuple(d -> d <= N ? t[d] : fill, 3)
+
+# ---- which interpolants take the accelerated path (everything else keeps the Julia methods) ----------
+kernel_symbols(::HigherOrderKernel{KS}) where {KS} = KS
+kernel_symbols(::HigherOrderMixedKernel{KS}) where {KS} = KS
+kernel_symbols(_) = nothing
+
+function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
+    (T === Float64 || T === Float32) || return false
+    1 <= N <= 3 || return false
+    ks = kernel_symbols(itp.kernel_sym)
+    ks === nothing && return false
+    all(k -> haskey(KERNEL_ID, k), ks) || return false
+    itp.lazy === Val{false}() || return false
+    itp.subgrid === Val(ntuple(_ -> :cubic, N)) || return false
+    itp.derivative isa DerivativeOrder || return false
+    dv = derivative_tuple(itp)
+    all(d -> 0 <= dv[d] <= MAX_DERIV[ks[d]], 1:N) || return false
+    return true
+end
+derivative_tuple(itp) = typeof(itp.derivative).parameters[1]   # DerivativeOrder{DO}
+
+# ---- handle cache: one upload per interpolant, freed by a finalizer --------------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+end
+const HANDLES = WeakKeyDict{Any,Handle}()
+const HANDLES_LOCK = ReentrantLock()
+
+extrap_id(::Throw) = Int32(0)
+extrap_id(::Flat) = Int32(1)
+extrap_id(::Line) = Int32(2)
+
+function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
+    lock(HANDLES_LOCK) do
+        get!(HANDLES, etp) do
+            itp = etp.itp
+            ks = kernel_symbols(itp.kernel_sym)
+            dv = derivative_tuple(itp)
+            knots64 = ntuple(d -> Vector{Float64}(itp.knots[d]), N)
+            desc = Ref(ItpDesc(Int32(N), T === Float32 ? Int32(1) : Int32(0),
+                               pad3(Int64.(size(itp.coefs)), Int64(1)), pointer(itp.coefs),
+                               pad3(ntuple(d -> pointer(knots64[d]), N), Ptr{Float64}(0)),
+                               pad3(Float64.(itp.h), 1.0), pad3(ntuple(d -> Int32(KERNEL_ID[ks[d]]), N), Int32(0)),
+                               pad3(ntuple(d -> Int32(dv[d]), N), Int32(0)), extrap_id(etp.et),
+                               Int32(itp.kernel_sym isa HigherOrderMixedKernel)))
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            GC.@preserve itp knots64 check(ccall((:cib200_itp_create, LIB), Int32,
+                                                 (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
+            h = Handle(out[])
+            finalizer(x -> ccall((:cib200_itp_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+            h
+        end
+    end
+end
+
+# ---- itp.(xs...) : replaces the per-element loop over extrapolation_operator.jl:31-63 ---------------
+function Base.Broadcast.broadcasted(etp::ConvolutionExtrapolation{T,N}, xs::Vararg{AbstractVector{<:Real},N}) where {T,N}
+    accelerated(etp.itp) || return Base.Broadcast.broadcasted(Base.Broadcast.DefaultArrayStyle{1}(), etp, xs...)
+    nq = length(xs[1])
+    all(x -> length(x) == nq, xs) || throw(DimensionMismatch("coordinate vectors must have equal length"))
+    xq = ntuple(d -> Vector{T}(xs[d]), N)
+    out = Vector{T}(undef, nq)
+    ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
+    bad = Ref{Int64}(-1)
+    GC.@preserve xq out ptrs check(ccall((:cib200_itp_eval, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+        handle(etp).ptr, nq, ptrs, out, 0, C_NULL, bad))
+    return out
+end
+
+# ---- itp(xs, ys, zs) with vectors: Cartesian product, extrapolation_operator.jl:66-99 ----------------
+function (etp::ConvolutionExtrapolation{T,N})(xs::Vararg{AbstractVector{<:Real},N}) where {T,N}
+    accelerated(etp.itp) || return invoke(etp, Tuple{Vararg{AbstractArray,N}}, xs...)
+    xq = ntuple(d -> Vector{T}(xs[d]), N)
+    n = Int64[length(x) for x in xq]
+    out = zeros(T, n...)
+    ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
+    bad = Ref{Int64}(-1)
+    GC.@preserve xq out ptrs check(ccall((:cib200_itp_eval_grid, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+        handle(etp).ptr, n, ptrs, out, 0, C_NULL, bad))
+    return out
+end
+
+# ---- convolution_resample_internal (convolution_resample.jl:240-386) ---------------------------------
+function resample_accelerated(values::AbstractArray{T,N}, kernels, derivatives, subgrids, precompute) where {T,N}
+    (T === Float64 || T === Float32) && N <= 8 && all(k -> haskey(KERNEL_ID, k), kernels) &&
+        all(==(:cubic), subgrids) && all(==(101), precompute) &&
+        all(d -> 0 <= derivatives[d] <= MAX_DERIV[kernels[d]], 1:N)
+end
+
+function cib200_resample(knots_in::NTuple{N}, knots_out::NTuple{N}, values::Array{T,N},
+                         kernels, derivatives, bcs) where {T,N}
+    kin = ntuple(d -> Vector{Float64}(knots_in[d]), N)
+    kout = ntuple(d -> Vector{Float64}(knots_out[d]), N)
+    out = Array{T,N}(undef, ntuple(d -> length(kout[d]), N))
+    n_in = Int64[size(values)...]; n_out = Int64[size(out)...]
+    pin = [pointer(k) for k in kin]; pout = [pointer(k) for k in kout]
+    kid = Int32[KERNEL_ID[k] for k in kernels]; dv = Int32[derivatives...]
+    bl = Int32[BC_ID[b[1]] for b in bcs]; br = Int32[BC_ID[b[2]] for b in bcs]
+    GC.@preserve kin kout values out check(ccall((:cib200_resample, LIB), Int32,
+        (Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}},
+         Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Cvoid}),
+        N, T === Float32 ? 1 : 0, n_in, n_out, values, out, pin, pout, kid, dv, bl, br, 0, C_NULL))
+    return out
+end
+# in convolution_resample_internal, first line:
+#   resample_accelerated(values, kernels, derivatives, subgrids, precompute) &&
+#       return CIB200Glue.cib200_resample(knots_in, knots_out, values, kernels, derivatives, bcs)
+
+# ---- convolution_smooth (convolution_gaussian_smoothing.jl:45-126) -----------------------------------
+function cib200_smooth(knots::NTuple{N,AbstractVector}, values::Array{T,N}, B::Float64) where {T,N}
+    out = similar(values)
+    n = Int64[size(values)...]
+    h = Float64[T(knots[d][2] - knots[d][1]) for d in 1:N]
+    st = GC.@preserve values out ccall((:cib200_smooth, LIB), Int32,
+        (Int32, Int32, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Int32, Ptr{Cvoid}),
+        N, T === Float32 ? 1 : 0, n, values, out, h, B, 0, C_NULL)
+    st == 3 && error(last_error())   # "Gaussian stencil half-width (E points) exceeds grid size ..." (:50-56)
+    check(st)
+    return out
+end
+# in convolution_smooth(knots::NTuple{N}, values::AbstractArray{T,N}, B), first line:
+#   (T === Float64 || T === Float32) && N <= 8 && return CIB200Glue.cib200_smooth(knots, Array(values), B)
+
+end # module
