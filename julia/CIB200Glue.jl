@@ -42,7 +42,7 @@ end
 pad3(t::NTuple{N,T}, fill) where {N,T} = ntuple(d -> d <= N ? t[d] : fill, 3)
 
 # ---- which interpolants take the accelerated path (everything else keeps the Julia methods) ----------
-kernel_symbols(::HigherOrderKernel{KS}) where {KS} = KS
+kernel_symbols(::HigherOrderKernel{KS}) where {KS} = KS        # struct_constructors.jl:76-80
 kernel_symbols(::HigherOrderMixedKernel{KS}) where {KS} = KS
 kernel_symbols(_) = nothing
 
@@ -54,12 +54,12 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     all(k -> haskey(KERNEL_ID, k), ks) || return false
     itp.lazy === Val{false}() || return false
     itp.subgrid === Val(ntuple(_ -> :cubic, N)) || return false
-    itp.derivative isa DerivativeOrder || return false
+    itp.derivative_order isa DerivativeOrder || return false
     dv = derivative_tuple(itp)
     all(d -> 0 <= dv[d] <= MAX_DERIV[ks[d]], 1:N) || return false
     return true
 end
-derivative_tuple(itp) = typeof(itp.derivative).parameters[1]   # DerivativeOrder{DO}
+derivative_tuple(itp) = typeof(itp.derivative_order).parameters[1]   # DerivativeOrder{DO} (struct_constructors.jl:182)
 
 # ---- handle cache: one upload per interpolant, freed by a finalizer --------------------------------
 mutable struct Handle
