@@ -263,10 +263,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = ci.sharding.max_over_ranks_ms(total_ms, world, dev)
     value = world * nq * args.steps / (total_ms_max * 1e-3)
 
     # sanity: a strided subsample re-evaluated on its own (small batch -> direct gather kernel) must agree with

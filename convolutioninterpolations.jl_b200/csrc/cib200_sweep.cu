@@ -157,15 +157,19 @@ __device__ void ghost_gauss_side(double *buf, int pad, int pitch, int ti, long l
   }
 }
 
-template <typename T, bool SMOOTH, bool AXIS0>
+static constexpr int SMOOTH_R = 8;  // consecutive outputs per thread in the Gaussian FIR (sliding register window)
+
+// TAPS = 2 eqs (compile time) for resample, 0 for smooth (run-time 2E+1 taps)
+// CPITCH = compile-time buffer pitch (shared-memory loads get immediate offsets), 0 = run-time pitch
+template <typename T, bool SMOOTH, bool AXIS0, int TAPS, int CPITCH>
 __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm, const T *__restrict__ in,
                                                     T *__restrict__ out) {
   extern __shared__ double sm[];
-  const int pad = sp.pad, pitch = sp.pitch, TI = sp.ti;
+  const int pad = sp.pad, pitch = CPITCH > 0 ? CPITCH : sp.pitch, TI = sp.ti;
   const long long n = sp.n_in, nout = sp.n_out;
   const long long nrow = n + 2 * pad;
   double *buf = sm;
-  double *kw = sm + nrow * pitch;  // smooth only
+  double *kw = sm + (nrow + (SMOOTH ? 2 * SMOOTH_R : 0)) * pitch;  // smooth only
   const int tid = threadIdx.x, nth = blockDim.x;
 
   // tile coordinates
@@ -187,29 +191,28 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm
   }
   (void)tiles_inner;
 
+  // (all tile loops are warp-per-row / lane-per-column: no integer division in the hot path)
+  const int warp_ = tid >> 5, lane_ = tid & 31, nwarp_ = nth >> 5;
+  const int n_i = (int)n;
   // 0. clear ghost slots (the reference zero-fills the line buffer: resample :309, smooth :96)
-  for (long long e = tid; e < (long long)2 * pad * TI; e += nth) {
-    int ti = (int)(e % TI);
-    long long r = e / TI;
-    long long slot = r < pad ? r : (n + r);
-    buf[slot * pitch + ti] = 0.0;
+  for (int r = warp_; r < 2 * pad; r += nwarp_) {
+    const int slot = r < pad ? r : (n_i + r);
+    for (int ti = lane_; ti < TI; ti += 32) buf[slot * pitch + ti] = 0.0;
   }
   if (SMOOTH)
     for (int e = tid; e < sp.taps; e += nth) kw[e] = sp.W[e];
   // 1. stage the lines
   if (AXIS0) {
     const T *src = in + line0 * n;
-    for (long long e = tid; e < (long long)valid * n; e += nth) {
-      long long j = e % n;
-      int ti = (int)(e / n);
-      buf[(pad + j) * pitch + ti] = (double)src[e];
+    for (int ti = warp_; ti < valid; ti += nwarp_) {
+      const T *ln = src + (long long)ti * n;
+      for (int j = lane_; j < n_i; j += 32) buf[(pad + j) * pitch + ti] = (double)ln[j];
     }
   } else {
     const T *src = in + tile_i * TI + o * sp.inner * n;
-    for (long long e = tid; e < (long long)TI * n; e += nth) {
-      int ti = (int)(e % TI);
-      long long j = e / TI;
-      if (ti < valid) buf[(pad + j) * pitch + ti] = (double)src[ti + j * sp.inner];
+    for (int j = warp_; j < n_i; j += nwarp_) {
+      const T *row = src + (long long)j * sp.inner;
+      for (int ti = lane_; ti < valid; ti += 32) buf[(pad + j) * pitch + ti] = (double)row[ti];
     }
   }
   __syncthreads();
@@ -226,30 +229,89 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm
   }
   __syncthreads();
   // 3. outputs
-  const long long total = (long long)valid * nout;
-  const int taps = sp.taps;
-  for (long long e = tid; e < total; e += nth) {
-    int ti;
-    long long k;
-    if (AXIS0) {
-      k = e % nout;
-      ti = (int)(e / nout);
-    } else {
-      ti = (int)(e % valid);
-      k = e / valid;
+  if (SMOOTH) {
+    // thread = (line, block of R consecutive outputs): the R outputs share a sliding window of inputs kept in
+    // registers, so one LDS feeds R DFMAs; taps are accumulated in the reference's order l = -E..E
+    constexpr int R = SMOOTH_R;
+    const int taps = sp.taps;
+    const int nblk = (int)((nout + R - 1) / R);
+    for (int kb = warp_; kb < nblk; kb += nwarp_)
+    for (int ti = lane_; ti < valid; ti += 32) {
+      const long long k0 = (long long)kb * R;
+      double acc[R], win[R];
+      int off = (int)k0 * pitch + ti;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r] = 0.0;
+        win[r] = buf[off + r * pitch];
+      }
+      off += R * pitch;
+      for (int l = 0; l < taps; l += R) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          if (l + u < taps) {  // uniform
+            const double wv = kw[l + u];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
+            win[u] = buf[off];  // element k0 + (l+u) + R replaces k0 + (l+u), which no output needs any more
+            off += pitch;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const long long k = k0 + r;
+        if (k < nout) {
+          if (AXIS0) out[(line0 + ti) * nout + k] = (T)acc[r];
+          else out[tile_i * TI + ti + k * sp.inner + o * sp.inner * nout] = (T)acc[r];
+        }
+      }
     }
-    double acc = 0.0;
-    if (SMOOTH) {
-      const double *b = buf + k * pitch + ti;  // taps k+E+l, l=-E..E  -> rows k .. k+2E
-      for (int l = 0; l < taps; ++l) acc = fma(b[(long long)l * pitch], kw[l], acc);
-    } else {
-      const double *b = buf + (long long)__ldg(sp.base + k) * pitch + ti;
-      const double *w = sp.W + k;
-      for (int l = 0; l < taps; ++l) acc = fma(b[(long long)l * pitch], __ldg(w + (long long)l * nout), acc);
-      acc = __dmul_rn(acc, sp.scale);
+  } else if (AXIS0) {
+    // lane = output knot k (stores coalesced along the line); its 2 eqs blended weights stay in registers while
+    // the thread walks the lines of the tile
+    const int kthreads = nout >= nth ? nth : (int)((nout + 31) / 32 * 32);
+    const int lgroups = nth / kthreads;
+    const int kk = tid % kthreads, lg = tid / kthreads;
+    if (lg < lgroups) {
+      for (long long k = kk; k < nout; k += kthreads) {
+        const int base = __ldg(sp.base + k);
+        double w[TAPS > 0 ? TAPS : 1];
+#pragma unroll
+        for (int l = 0; l < TAPS; ++l) w[l] = __ldg(sp.W + (long long)l * nout + k);
+        for (int ti = lg; ti < valid; ti += lgroups) {
+          int off = base * pitch + ti;
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < TAPS; ++l) {
+            acc = fma(buf[off], w[l], acc);
+            off += pitch;
+          }
+          out[(line0 + ti) * nout + k] = (T)__dmul_rn(acc, sp.scale);
+        }
+      }
     }
-    if (AXIS0) out[(line0 + ti) * nout + k] = (T)acc;
-    else out[tile_i * TI + ti + k * sp.inner + o * sp.inner * nout] = (T)acc;
+  } else {
+    // lane = line (loads from the tile and global stores coalesced along `inner`); a warp owns one output knot at
+    // a time: its weights are warp-uniform registers reused for every line of the tile
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
+    for (long long k = warp; k < nout; k += nwarp) {
+      const int base = __ldg(sp.base + k);
+      double w[TAPS > 0 ? TAPS : 1];
+#pragma unroll
+      for (int l = 0; l < TAPS; ++l) w[l] = __ldg(sp.W + (long long)l * nout + k);
+      T *orow = out + tile_i * TI + k * sp.inner + o * sp.inner * nout;
+      for (int ti = lane; ti < valid; ti += 32) {
+        int off = base * pitch + ti;
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < TAPS; ++l) {
+          acc = fma(buf[off], w[l], acc);
+          off += pitch;
+        }
+        orow[ti] = (T)__dmul_rn(acc, sp.scale);
+      }
+    }
   }
 }
 
@@ -303,12 +365,39 @@ static int max_dyn_smem() {
   return v;
 }
 
+template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
+static int launch_kernel(const SweepParams &sp, const GhostMats &gm, const T *in, T *out, long long blocks, size_t smem,
+                         cudaStream_t st) {
+  auto k = sweep_kernel<T, SMOOTH, AXIS0, TAPS, 0>;
+  if (sp.pitch == (AXIS0 ? 33 : 32)) k = sweep_kernel<T, SMOOTH, AXIS0, TAPS, AXIS0 ? 33 : 32>;
+  if (smem > 48 * 1024) CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)blocks, 256, smem, st>>>(sp, gm, in, out);
+  CIB_LAUNCHED();
+  CIB_CUDA(cudaGetLastError());
+  return CIB200_OK;
+}
+
+template <typename T, bool SMOOTH, bool AXIS0>
+static int launch_taps(const SweepParams &sp, const GhostMats &gm, const T *in, T *out, long long blocks, size_t smem,
+                       cudaStream_t st) {
+  if (SMOOTH) return launch_kernel<T, SMOOTH, AXIS0, 0>(sp, gm, in, out, blocks, smem, st);
+  switch (sp.taps) {
+    case 10: return launch_kernel<T, false, AXIS0, 10>(sp, gm, in, out, blocks, smem, st);
+    case 12: return launch_kernel<T, false, AXIS0, 12>(sp, gm, in, out, blocks, smem, st);
+    case 14: return launch_kernel<T, false, AXIS0, 14>(sp, gm, in, out, blocks, smem, st);
+    case 16: return launch_kernel<T, false, AXIS0, 16>(sp, gm, in, out, blocks, smem, st);
+    case 18: return launch_kernel<T, false, AXIS0, 18>(sp, gm, in, out, blocks, smem, st);
+  }
+  set_error("sweep: unsupported tap count %d", sp.taps);
+  return CIB200_EUNSUPPORTED;
+}
+
 template <typename T, bool SMOOTH>
 static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out, bool axis0, cudaStream_t st) {
-  // choose the tile width: as many lines as fit, <= 32, a power of two
+  // tile width: as many lines as fit, a power of two, at most 32 (the common full tile gets a compile-time pitch)
   const long long lines = axis0 ? sp.outer : sp.inner;
-  const long long nrow = sp.n_in + 2 * sp.pad;
-  const size_t budget = (size_t)std::min(max_dyn_smem(), 160 * 1024);
+  const long long nrow = sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_R : 0);
+  const size_t budget = (size_t)std::min(max_dyn_smem(), 100 * 1024);
   int ti = 32;
   while (ti > 1 && (long long)ti / 2 >= lines) ti /= 2;
   auto bytes_for = [&](int t) {
@@ -329,18 +418,8 @@ static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out,
     set_error("sweep: grid too large");
     return CIB200_EUNSUPPORTED;
   }
-  if (axis0) {
-    auto k = sweep_kernel<T, SMOOTH, true>;
-    if (smem > 48 * 1024) CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)blocks, 256, smem, st>>>(sp, gm, in, out);
-  } else {
-    auto k = sweep_kernel<T, SMOOTH, false>;
-    if (smem > 48 * 1024) CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)blocks, 256, smem, st>>>(sp, gm, in, out);
-  }
-  CIB_LAUNCHED();
-  CIB_CUDA(cudaGetLastError());
-  return CIB200_OK;
+  if (axis0) return launch_taps<T, SMOOTH, true>(sp, gm, in, out, blocks, smem, st);
+  return launch_taps<T, SMOOTH, false>(sp, gm, in, out, blocks, smem, st);
 }
 
 struct TempBufs {
