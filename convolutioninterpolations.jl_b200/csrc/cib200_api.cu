@@ -261,20 +261,22 @@ static int reset_status(cib200_itp *h, cudaStream_t st) {
 }
 
 static int ensure_stage(cib200_itp *h, size_t bytes) {
+  if (!h->streams[0]) {
+    for (int i = 0; i < 3; ++i) CIB_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < cib200_itp::NSTAGE; ++i) {
+      CIB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CIB_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+      CIB_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+  }
   if (h->stage_bytes >= bytes) return CIB200_OK;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cib200_itp::NSTAGE; ++i) {
     if (h->d_stage[i]) cudaFree(h->d_stage[i]);
     h->d_stage[i] = nullptr;
   }
   h->stage_bytes = 0;
-  for (int i = 0; i < 2; ++i) CIB_CUDA(cudaMalloc(&h->d_stage[i], bytes));
+  for (int i = 0; i < cib200_itp::NSTAGE; ++i) CIB_CUDA(cudaMalloc(&h->d_stage[i], bytes));
   h->stage_bytes = bytes;
-  if (!h->streams[0]) {
-    for (int i = 0; i < 2; ++i) {
-      CIB_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
-      CIB_CUDA(cudaEventCreateWithFlags(&h->events[i], cudaEventDisableTiming));
-    }
-  }
   return CIB200_OK;
 }
 
@@ -495,11 +497,14 @@ int32_t cib200_itp_destroy(cib200_itp *h) {
     if (h->d_knots[d]) cudaFree(h->d_knots[d]);
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_status) cudaFree(h->d_status);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cib200_itp::NSTAGE; ++i) {
     if (h->d_stage[i]) cudaFree(h->d_stage[i]);
-    if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
-    if (h->events[i]) cudaEventDestroy(h->events[i]);
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
   }
+  for (int i = 0; i < 3; ++i)
+    if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
   if (h->d_bin_scratch) cudaFree(h->d_bin_scratch);
   delete h;
   return CIB200_OK;
@@ -547,53 +552,62 @@ static int32_t eval_common(cib200_itp *h, const Coords &c_in, long long nq, void
     set_error("%s: unknown memkind %d", who, memkind);
     return CIB200_EINVAL;
   }
-  // host buffers: chunked, double-buffered H2D -> kernel -> D2H on two private streams
+  // host buffers: chunked pipeline H2D (stream 0) -> kernels (stream 1) -> D2H (stream 2) over a ring of device buffers
+  cudaStream_t s_in, s_comp, s_out;
   if (c_in.grid) {
     // coordinate vectors are tiny: upload them whole, keep the result pipeline chunk-free
     size_t xbytes = 0;
     for (int d = 0; d < nd; ++d) xbytes += es * (size_t)c_in.n[d];
     if ((rc = ensure_stage(h, std::max(xbytes, es * (size_t)nq)))) return rc;
-    cudaStream_t s0 = h->streams[0];
+    s_comp = h->streams[1];
     Coords c = c_in;
     char *dst = (char *)h->d_stage[0];
     for (int d = 0; d < nd; ++d) {
-      CIB_CUDA(cudaMemcpyAsync(dst, c_in.x[d], es * (size_t)c_in.n[d], cudaMemcpyHostToDevice, s0));
+      CIB_CUDA(cudaMemcpyAsync(dst, c_in.x[d], es * (size_t)c_in.n[d], cudaMemcpyHostToDevice, s_comp));
       c.x[d] = dst;
       dst += es * (size_t)c_in.n[d];
     }
-    if ((rc = reset_status(h, s0))) return rc;
-    if ((rc = eval_dispatch(h, c, h->d_stage[1], nq, s0))) return rc;
-    CIB_CUDA(cudaMemcpyAsync(out, h->d_stage[1], es * (size_t)nq, cudaMemcpyDeviceToHost, s0));
+    if ((rc = reset_status(h, s_comp))) return rc;
+    if ((rc = eval_dispatch(h, c, h->d_stage[1], nq, s_comp))) return rc;
+    CIB_CUDA(cudaMemcpyAsync(out, h->d_stage[1], es * (size_t)nq, cudaMemcpyDeviceToHost, s_comp));
     int code;
-    if ((rc = fetch_status(h, s0, first_bad, &code))) return rc;
+    if ((rc = fetch_status(h, s_comp, first_bad, &code))) return rc;
     if (code) set_error("%s: query %lld %s", who, first_bad ? (long long)*first_bad : -1LL, code == CIB200_EOOB ? "is outside the interpolation domain (extrap=Throw)" : "has a NaN/Inf coordinate");
     return code;
   }
-  const long long chunk = std::min<long long>(nq, 1LL << 23);
+  const long long chunk = std::min<long long>(nq, 1LL << 24);
   // per buffer: nd coordinate chunks + 1 result chunk
   if ((rc = ensure_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
-  if ((rc = reset_status(h, h->streams[0]))) return rc;
-  CIB_CUDA(cudaStreamSynchronize(h->streams[0]));
-  int buf = 0;
-  for (long long q0 = 0; q0 < nq; q0 += chunk, buf ^= 1) {
+  s_in = h->streams[0];
+  s_comp = h->streams[1];
+  s_out = h->streams[2];
+  if ((rc = reset_status(h, s_comp))) return rc;
+  constexpr int NS = cib200_itp::NSTAGE;
+  long long ichunk = 0;
+  for (long long q0 = 0; q0 < nq; q0 += chunk, ++ichunk) {
+    const int b = (int)(ichunk % NS);
     const long long m = std::min(chunk, nq - q0);
-    cudaStream_t s = h->streams[buf];
-    char *base = (char *)h->d_stage[buf];
+    char *base = (char *)h->d_stage[b];
     Coords c = c_in;
+    if (ichunk >= NS) CIB_CUDA(cudaStreamWaitEvent(s_in, h->ev_out[b], 0));  // buffer b drained by its last D2H
     for (int d = 0; d < nd; ++d) {
       char *dst = base + es * (size_t)chunk * d;
-      CIB_CUDA(cudaMemcpyAsync(dst, (const char *)c_in.x[d] + es * (size_t)q0, es * (size_t)m, cudaMemcpyHostToDevice, s));
+      CIB_CUDA(cudaMemcpyAsync(dst, (const char *)c_in.x[d] + es * (size_t)q0, es * (size_t)m, cudaMemcpyHostToDevice, s_in));
       c.x[d] = dst;
     }
+    CIB_CUDA(cudaEventRecord(h->ev_in[b], s_in));
     void *dout = base + es * (size_t)chunk * nd;
     c.qoff = q0;  // failing queries are reported in absolute numbering
-    if ((rc = eval_dispatch(h, c, dout, m, s))) return rc;
-    CIB_CUDA(cudaMemcpyAsync((char *)out + es * (size_t)q0, dout, es * (size_t)m, cudaMemcpyDeviceToHost, s));
+    CIB_CUDA(cudaStreamWaitEvent(s_comp, h->ev_in[b], 0));
+    if ((rc = eval_dispatch(h, c, dout, m, s_comp))) return rc;
+    CIB_CUDA(cudaEventRecord(h->ev_comp[b], s_comp));
+    CIB_CUDA(cudaStreamWaitEvent(s_out, h->ev_comp[b], 0));
+    CIB_CUDA(cudaMemcpyAsync((char *)out + es * (size_t)q0, dout, es * (size_t)m, cudaMemcpyDeviceToHost, s_out));
+    CIB_CUDA(cudaEventRecord(h->ev_out[b], s_out));
   }
-  CIB_CUDA(cudaStreamSynchronize(h->streams[0]));
-  CIB_CUDA(cudaStreamSynchronize(h->streams[1]));
+  CIB_CUDA(cudaStreamSynchronize(s_out));
   int code;
-  if ((rc = fetch_status(h, h->streams[0], first_bad, &code))) return rc;
+  if ((rc = fetch_status(h, s_comp, first_bad, &code))) return rc;
   if (code)
     set_error("%s: query %lld %s", who, first_bad ? (long long)*first_bad : -1LL,
               code == CIB200_EOOB ? "is outside the interpolation domain (extrap=Throw)" : "has a NaN/Inf coordinate");

@@ -84,11 +84,14 @@ struct cib200_itp {
   double *d_tables;  // packed distinct tables
   cib::EvalStatus *d_status;
   cib::ItpParams p;
-  // staging for host-memory calls (lazily allocated)
-  void *d_stage[2];
+  // staging for host-memory calls (lazily allocated): ring of NSTAGE device buffers, three role streams
+  // (copy-in, compute, copy-out) chained by events; all kernels of a call run on ONE stream, so the binned
+  // strategy's scratch is never shared between chunks in flight
+  static constexpr int NSTAGE = 3;
+  void *d_stage[NSTAGE];
   size_t stage_bytes;
-  cudaStream_t streams[2];
-  cudaEvent_t events[2];
+  cudaStream_t streams[3];          // 0: H2D, 1: compute, 2: D2H
+  cudaEvent_t ev_in[NSTAGE], ev_comp[NSTAGE], ev_out[NSTAGE];
   // scratch for the binned strategy (lazily allocated, grows)
   void *d_bin_scratch;
   size_t bin_scratch_bytes;
