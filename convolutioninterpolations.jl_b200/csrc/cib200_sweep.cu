@@ -42,16 +42,19 @@ struct SweepParams {
   int ti;         // lines per tile
   int pitch;      // buffer pitch (doubles)
   int bcl, bcr;
+  int w_smem;     // resample, axis >= 1: blended weights + first-tap indices are staged in shared memory
   double h;
   double scale;   // (-1/h)^derivative (resample) ; 1 (smooth)
   const double *W;     // resample: [taps][n_out] blended weights ; smooth: kw[taps]
+  const double *Wk;    // resample: the same weights as [n_out][taps] (16-byte aligned rows: taps is even)
   const int *base;     // resample: first tap index into the padded line (0-based) per output
 };
 
 // ---- per-output-knot weights: convolution_resample.jl:320-361 minus the data ------------------
 __global__ void resample_weights_kernel(const double *__restrict__ knots_out, long long n_out, double x_expanded_1,
                                         double h, int eqs, long long n_coef, const double *__restrict__ tk,
-                                        const double *__restrict__ td, double *__restrict__ W, int *__restrict__ base) {
+                                        const double *__restrict__ td, double *__restrict__ W, double *__restrict__ Wk,
+                                        int *__restrict__ base) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_out) return;
   AxisPos p;
@@ -59,54 +62,81 @@ __global__ void resample_weights_kernel(const double *__restrict__ knots_out, lo
   base[k] = p.base;
   Hermite hb = hermite_basis(p.t);
   const int w = 2 * eqs;
-  for (int l = 0; l < w; ++l) W[(long long)l * n_out + k] = blended_weight(hb, tk, td, p.row, l, w);
+  for (int l = 0; l < w; ++l) {
+    const double v = blended_weight(hb, tk, td, p.row, l, w);
+    W[(long long)l * n_out + k] = v;
+    Wk[k * w + l] = v;
+  }
 }
 
 // ---- ghost fill of one line held in shared memory ----------------------------------------------
-// line(j) = buf[(pad + j) * pitch + ti], j = 0..n-1
-__device__ __forceinline__ double line_mean(const double *buf, int pad, int pitch, int ti, long long n) {
-  double sum = 0.0;
-  for (long long j = 0; j < n; ++j) sum = __dadd_rn(sum, buf[(pad + j) * pitch + ti]);
+// bl = buf + ti; line(j) = bl[(pad + j) * pitch], j = 0..n-1.  Everything below is lane-private (lane = line),
+// fully unrolled with compile-time node counts so that no array is indexed dynamically (no local memory), and
+// plain mul/add via __d*_rn so that the :detect branch decisions and the ghost values do not depend on fma
+// contraction.
+// The reference computes sum(slice)/n with Julia's `sum` (create_convolutional_coefs.jl:242,312): a @simd loop whose
+// lanes are partial sums in an unspecified (vector-width dependent) association.  Here: 8 interleaved partial sums
+// combined pairwise - the dependent chain is n/8 additions instead of n, and the result is within a few ulp of any
+// other association (the oracle's sequential loop included).
+__device__ __forceinline__ double line_mean(const double *bl, int pad, int pitch, int n) {
+  double s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.0;
+  const double *p = bl + pad * pitch;
+  int j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = __dadd_rn(s[i], p[(j + i) * pitch]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (j + i < n) s[i] = __dadd_rn(s[i], p[(j + i) * pitch]);
+  const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
+                               __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
   return __ddiv_rn(sum, (double)n);
 }
 
-__device__ void ghost_poly_side(double *buf, int pad, int pitch, int ti, long long n, double mean, double h, int eqs,
-                                int bc, bool right, const GhostMats &gm) {
-  const int ns = gm.poly_nodes;
+// NS = polynomial node count of the kernel (6 for b5, 8 otherwise), EQS-1 ghosts per side
+template <int NS, int EQS>
+__device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, int n, double mean, double h, int bc,
+                                                bool right, const GhostMats &gm) {
   double y[8];  // centred boundary values, y[0] = the boundary point itself, then inward
-  const int navail = n < 8 ? (int)n : 8;
-  for (int k = 0; k < navail; ++k) {
-    long long j = right ? (n - 1 - k) : k;
-    y[k] = __dsub_rn(buf[(pad + j) * pitch + ti], mean);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = right ? (n - 1 - k) : k;
+    y[k] = k < n ? __dsub_rn(bl[(pad + j) * pitch], mean) : 0.0;
   }
   bool use_poly = false;
-  if (n >= ns && (bc == CIB200_BC_DETECT || bc == CIB200_BC_POLY)) {
+  if (n >= NS && (bc == CIB200_BC_DETECT || bc == CIB200_BC_POLY)) {
     if (bc == CIB200_BC_POLY) {
       use_poly = true;
     } else {
-      // natural-order window p[0..ns-1]: left p[i] = y[i]; right p[i] = y[ns-1-i]
-      double d1[8], d2[8];
+      // natural-order window p[0..NS-1]: left p[i] = y[i]; right p[i] = y[NS-1-i]
+      double d1[NS - 1], d2[NS - 2];
       double mn = INFINITY, mx = -INFINITY;
-      for (int d = 0; d < ns - 1; ++d) {
-        double a = right ? y[ns - 2 - d] : y[d + 1];
-        double b = right ? y[ns - 1 - d] : y[d];
+#pragma unroll
+      for (int d = 0; d < NS - 1; ++d) {
+        const double a = right ? y[NS - 2 - d] : y[d + 1];
+        const double b = right ? y[NS - 1 - d] : y[d];
         d1[d] = __dsub_rn(a, b);
         mn = fmin(mn, d1[d]);
         mx = fmax(mx, d1[d]);
       }
-      bool periodic = __ddiv_rn(__dmul_rn(mn, mx), __dmul_rn(h, h)) < -1.0 / 10;
+      const bool periodic = __ddiv_rn(__dmul_rn(mn, mx), __dmul_rn(h, h)) < -1.0 / 10;
       mn = INFINITY, mx = -INFINITY;
-      for (int d = 0; d < ns - 2; ++d) {
+#pragma unroll
+      for (int d = 0; d < NS - 2; ++d) {
         d2[d] = __dsub_rn(d1[d + 1], d1[d]);
         mn = fmin(mn, d2[d]);
         mx = fmax(mx, d2[d]);
       }
-      bool high_curv = __ddiv_rn(fabs(__dsub_rn(mx, mn)), h) > 1.0 / 2;
+      const bool high_curv = __ddiv_rn(fabs(__dsub_rn(mx, mn)), h) > 1.0 / 2;
       bool high_d3 = false;
-      if (ns > 4) {
+      if (NS > 4) {
         mn = INFINITY, mx = -INFINITY;
-        for (int d = 0; d < ns - 3; ++d) {
-          double v = __dsub_rn(d2[d + 1], d2[d]);
+#pragma unroll
+        for (int d = 0; d < NS - 3; ++d) {
+          const double v = __dsub_rn(d2[d + 1], d2[d]);
           mn = fmin(mn, v);
           mx = fmax(mx, v);
         }
@@ -115,16 +145,33 @@ __device__ void ghost_poly_side(double *buf, int pad, int pitch, int ti, long lo
       use_poly = !periodic && !high_curv && !high_d3;
     }
   }
-  const int m = use_poly ? ns : (bc == CIB200_BC_QUADRATIC ? 3 : 2);
-  for (int j = 1; j <= eqs - 1; ++j) {
-    double acc = 0.0;
-    for (int k = 0; k < m; ++k) {
-      double mv = use_poly ? gm.poly[j - 1][k] : (m == 3 ? gm.quad[j - 1][k] : gm.lin[j - 1][k]);
-      acc = __dadd_rn(acc, __dmul_rn(mv, y[k]));
+  const int row0 = right ? (pad + n) : (pad - 1);  // slot of ghost j = 1
+  const int step = right ? pitch : -pitch;
+  double *g = bl + row0 * pitch;
+  if (use_poly) {
+#pragma unroll
+    for (int j = 1; j <= EQS - 1; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.poly[j - 1][k], y[k]));
+      g[(j - 1) * step] = __dadd_rn(mean, acc);
     }
-    double gv = __dadd_rn(mean, acc);
-    long long slot = right ? (pad + n - 1 + j) : (pad - j);
-    buf[slot * pitch + ti] = gv;
+  } else if (bc == CIB200_BC_QUADRATIC) {
+#pragma unroll
+    for (int j = 1; j <= EQS - 1; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.quad[j - 1][k], y[k]));
+      g[(j - 1) * step] = __dadd_rn(mean, acc);
+    }
+  } else {
+#pragma unroll
+    for (int j = 1; j <= EQS - 1; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.lin[j - 1][k], y[k]));
+      g[(j - 1) * step] = __dadd_rn(mean, acc);
+    }
   }
 }
 
@@ -132,32 +179,133 @@ __device__ void ghost_poly_side(double *buf, int pad, int pitch, int ti, long lo
 // get_boundary_indices(size = n + 2E, eqs = E) -> ghosts land one slot further out, slot next to the
 // interior stays 0.  Values are the centred least-squares line (mean NOT added back in
 // exact arithmetic: y_mean + (a + b(1-k) - y_mean)).
-__device__ void ghost_gauss_side(double *buf, int pad, int pitch, int ti, long long n, double mean, int E, bool right) {
-  long long n_fit = E / 3 > 6 ? E / 3 : 6;
+__device__ __forceinline__ void ghost_gauss_side(double *bl, int pad, int pitch, int n, double mean, int E, bool right) {
+  int n_fit = E / 3 > 6 ? E / 3 : 6;
   if (n_fit > n) n_fit = n;
-  double sx = 0, sy = 0, sxx = 0, sxy = 0;
-  for (long long k = 1; k <= n_fit; ++k) {
-    double xk = (double)k;
-    long long j = right ? (n - k) : (k - 1);
-    double yk = __dsub_rn(buf[(pad + j) * pitch + ti], mean);
-    sx = __dadd_rn(sx, xk);
+  // sx = sum k and sxx = sum k^2 are sums of small integers: exact in any order, so closed forms give the same bits
+  const double nfd = (double)n_fit;
+  const double sx = nfd * (nfd + 1.0) * 0.5, sxx = nfd * (nfd + 1.0) * (2.0 * nfd + 1.0) / 6.0;
+  double sy = 0, sxy = 0, xk = 1.0;
+  const double *q = bl + (pad + (right ? n - 1 : 0)) * pitch;
+  const int qs = right ? -pitch : pitch;
+#pragma unroll 2
+  for (int k = 0; k < n_fit; ++k) {
+    const double yk = __dsub_rn(q[k * qs], mean);
     sy = __dadd_rn(sy, yk);
-    sxx = __dadd_rn(sxx, __dmul_rn(xk, xk));
     sxy = __dadd_rn(sxy, __dmul_rn(xk, yk));
+    xk += 1.0;
   }
-  double nf = (double)n_fit;
-  double denom = __dsub_rn(__dmul_rn(nf, sxx), __dmul_rn(sx, sx));
-  double b = __ddiv_rn(__dsub_rn(__dmul_rn(nf, sxy), __dmul_rn(sx, sy)), denom);
-  double a = __ddiv_rn(__dsub_rn(sy, __dmul_rn(b, sx)), nf);
+  const double nf = (double)n_fit;
+  const double denom = __dsub_rn(__dmul_rn(nf, sxx), __dmul_rn(sx, sx));
+  const double b = __ddiv_rn(__dsub_rn(__dmul_rn(nf, sxy), __dmul_rn(sx, sy)), denom);
+  const double a = __ddiv_rn(__dsub_rn(sy, __dmul_rn(b, sx)), nf);
+  double *g = bl + (right ? (pad + n + 1) : (pad - 2)) * pitch;  // slot of ghost k = 1
+  const int step = right ? pitch : -pitch;
+  double c = 0.0;  // 1 - k
+#pragma unroll 4
   for (int k = 1; k <= E - 1; ++k) {
-    double y_temp = __dsub_rn(__dadd_rn(a, __dmul_rn(b, (double)(1 - k))), mean);
-    double gv = __dadd_rn(mean, y_temp);
-    long long slot = right ? (pad + n + k) : (pad - 1 - k);
-    buf[slot * pitch + ti] = gv;
+    const double y_temp = __dsub_rn(__dadd_rn(a, __dmul_rn(b, c)), mean);
+    g[(k - 1) * step] = __dadd_rn(mean, y_temp);
+    c -= 1.0;
   }
 }
 
-static constexpr int SMOOTH_R = 8;  // consecutive outputs per thread in the Gaussian FIR (sliding register window)
+static constexpr int SMOOTH_R = 8;    // consecutive outputs per thread in the Gaussian FIR (sliding register window)
+static constexpr int RESAMPLE_R = 8;  // anchor offsets a register window of the resample pass can serve
+
+// sum_l win[O + l] * w[l] with static register indices; three partial sums keep the FP64 pipe busy from one warp
+template <int TAPS, int WIN, int O>
+__device__ __forceinline__ double window_dot(const double (&win)[WIN], const double (&w)[TAPS]) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int l = 0; l < TAPS; l += 3) {
+    a0 = fma(win[O + l], w[l], a0);
+    if (l + 1 < TAPS) a1 = fma(win[O + l + 1], w[l + 1], a1);
+    if (l + 2 < TAPS) a2 = fma(win[O + l + 2], w[l + 2], a2);
+  }
+  return (a0 + a1) + a2;
+}
+
+// Phase 3 of a resample pass along an axis >= 1, one lane = one line.  A warp walks a contiguous range of output
+// knots.  Its inputs sit in a register window of TAPS + R - 1 consecutive rows anchored at row a: an output whose
+// first tap is row a + o, 0 <= o < R, is served from registers (one shared-memory load feeds ~TAPS/ratio DFMAs when
+// upsampling); the window is re-anchored when o leaves that range.  The weights of an output knot are warp-uniform:
+// they are fetched with uniform 16-byte loads one knot ahead (from shared memory when they fit next to the tile).
+template <bool WS>
+__device__ __forceinline__ double2 load_w2(const double2 *p) {
+  if (WS) {  // explicit ld.shared: a pointer that may be shared or global would compile to generic loads
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+  }
+  return __ldg(p);
+}
+template <bool WS>
+__device__ __forceinline__ int load_b(const int *p) {
+  if (WS) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+  }
+  return __ldg(p);
+}
+
+template <typename T, int TP, bool WS>
+__device__ __forceinline__ void resample_lines(const double *bl, const int pitch, const double2 *__restrict__ wsrc,
+                                               const int *__restrict__ bsrc, int kbeg, int kend, T *optr,
+                                               long long ostride, double scale) {
+  constexpr int R = RESAMPLE_R, WIN = TP + R - 1;
+  double win[WIN];
+  int a = load_b<WS>(bsrc + kbeg);
+#pragma unroll
+  for (int j = 0; j < WIN; ++j) win[j] = bl[(a + j) * pitch];
+  double wA[TP], wB[TP];
+  auto fetch = [&](int k, double(&w)[TP]) {
+    const double2 *src = wsrc + k * (TP / 2);
+#pragma unroll
+    for (int l = 0; l < TP; l += 2) {
+      const double2 v = load_w2<WS>(src + (l >> 1));
+      w[l] = v.x;
+      w[l + 1] = v.y;
+    }
+  };
+  auto emit = [&](int b, const double(&w)[TP]) {
+    int oo = b - a;
+    if ((unsigned)oo >= (unsigned)R) {  // warp-uniform
+      a = b;
+      oo = 0;
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) win[j] = bl[(a + j) * pitch];
+    }
+    double acc;
+    switch (oo) {
+      case 0: acc = window_dot<TP, WIN, 0>(win, w); break;
+      case 1: acc = window_dot<TP, WIN, 1>(win, w); break;
+      case 2: acc = window_dot<TP, WIN, 2>(win, w); break;
+      case 3: acc = window_dot<TP, WIN, 3>(win, w); break;
+      case 4: acc = window_dot<TP, WIN, 4>(win, w); break;
+      case 5: acc = window_dot<TP, WIN, 5>(win, w); break;
+      case 6: acc = window_dot<TP, WIN, 6>(win, w); break;
+      default: acc = window_dot<TP, WIN, 7>(win, w); break;
+    }
+    *optr = (T)__dmul_rn(acc, scale);
+    optr += ostride;
+  };
+  fetch(kbeg, wA);
+  int b0 = a;
+  for (int k = kbeg; k < kend; k += 2) {
+    const int k1 = k + 1 < kend ? k + 1 : k;
+    const int b1 = load_b<WS>(bsrc + k1);
+    fetch(k1, wB);
+    emit(b0, wA);
+    if (k + 1 < kend) {
+      const int k2 = k + 2 < kend ? k + 2 : k1;
+      b0 = load_b<WS>(bsrc + k2);
+      fetch(k2, wA);
+      emit(b1, wB);
+    }
+  }
+}
 
 // TAPS = 2 eqs (compile time) for resample, 0 for smooth (run-time 2E+1 taps)
 // CPITCH = compile-time buffer pitch (shared-memory loads get immediate offsets), 0 = run-time pitch
@@ -166,65 +314,105 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm
                                                     T *__restrict__ out) {
   extern __shared__ double sm[];
   const int pad = sp.pad, pitch = CPITCH > 0 ? CPITCH : sp.pitch, TI = sp.ti;
-  const long long n = sp.n_in, nout = sp.n_out;
-  const long long nrow = n + 2 * pad;
+  const int n = (int)sp.n_in, nout = (int)sp.n_out;
+  const int nrow = n + 2 * pad;
   double *buf = sm;
-  double *kw = sm + (nrow + (SMOOTH ? 2 * SMOOTH_R : 0)) * pitch;  // smooth only
+  // rows past the line: the register windows of phase 3 may read (never use) up to R-1 rows beyond it
+  double *kw = sm + (nrow + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R)) * pitch;  // smooth only
   const int tid = threadIdx.x, nth = blockDim.x;
+  const int warp_ = tid >> 5, lane_ = tid & 31, nwarp_ = nth >> 5;
 
   // tile coordinates
-  long long tiles_inner, tile_i, o;
-  long long line0;  // AXIS0: first line of the tile
-  int valid;        // lines of this tile that exist
+  long long tile_i = 0, o = 0;
+  long long line0 = 0;  // AXIS0: first line of the tile
+  int valid;            // lines of this tile that exist
   if (AXIS0) {
     line0 = (long long)blockIdx.x * TI;
-    long long rem = sp.outer - line0;
+    const long long rem = sp.outer - line0;
     valid = rem < TI ? (int)rem : TI;
-    tiles_inner = 1; tile_i = 0; o = 0;
   } else {
-    tiles_inner = (sp.inner + TI - 1) / TI;
+    const long long tiles_inner = (sp.inner + TI - 1) / TI;
     tile_i = blockIdx.x % tiles_inner;
     o = blockIdx.x / tiles_inner;
-    long long rem = sp.inner - tile_i * TI;
+    const long long rem = sp.inner - tile_i * TI;
     valid = rem < TI ? (int)rem : TI;
-    line0 = 0;
   }
-  (void)tiles_inner;
 
   // (all tile loops are warp-per-row / lane-per-column: no integer division in the hot path)
-  const int warp_ = tid >> 5, lane_ = tid & 31, nwarp_ = nth >> 5;
-  const int n_i = (int)n;
   // 0. clear ghost slots (the reference zero-fills the line buffer: resample :309, smooth :96)
   for (int r = warp_; r < 2 * pad; r += nwarp_) {
-    const int slot = r < pad ? r : (n_i + r);
+    const int slot = r < pad ? r : (n + r);
     for (int ti = lane_; ti < TI; ti += 32) buf[slot * pitch + ti] = 0.0;
   }
   if (SMOOTH)
     for (int e = tid; e < sp.taps; e += nth) kw[e] = sp.W[e];
-  // 1. stage the lines
+  // resample, axis >= 1: the per-output-knot weights (warp-uniform in phase 3) next to the tile
+  double *wsm = kw;
+  int *bsm = (int *)(wsm + (TAPS > 0 ? TAPS : 2) * nout);
+  if (!SMOOTH && !AXIS0 && sp.w_smem) {
+    const double2 *src = (const double2 *)sp.Wk;
+    double2 *dst = (double2 *)wsm;
+    const int nv = (TAPS > 0 ? TAPS : 2) * nout / 2;
+    for (int e = tid; e < nv; e += nth) dst[e] = __ldg(src + e);
+    for (int e = tid; e < nout; e += nth) bsm[e] = __ldg(sp.base + e);
+  }
+  // 1. stage the lines: explicit batches of independent loads (a whole batch is in flight before its first use)
   if (AXIS0) {
     const T *src = in + line0 * n;
-    for (int ti = warp_; ti < valid; ti += nwarp_) {
-      const T *ln = src + (long long)ti * n;
-      for (int j = lane_; j < n_i; j += 32) buf[(pad + j) * pitch + ti] = (double)ln[j];
-    }
+    constexpr int LB = 4, JB = 2;
+    for (int t0 = warp_; t0 < valid; t0 += nwarp_ * LB)
+      for (int j0 = lane_; j0 < n; j0 += 32 * JB) {
+        double v[LB][JB];
+#pragma unroll
+        for (int u = 0; u < LB; ++u)
+#pragma unroll
+          for (int w = 0; w < JB; ++w) {
+            const int ti = t0 + u * nwarp_, j = j0 + 32 * w;
+            v[u][w] = (ti < valid && j < n) ? (double)src[(long long)ti * n + j] : 0.0;
+          }
+#pragma unroll
+        for (int u = 0; u < LB; ++u)
+#pragma unroll
+          for (int w = 0; w < JB; ++w) {
+            const int ti = t0 + u * nwarp_, j = j0 + 32 * w;
+            if (ti < valid && j < n) buf[(pad + j) * pitch + ti] = v[u][w];
+          }
+      }
   } else {
     const T *src = in + tile_i * TI + o * sp.inner * n;
-    for (int j = warp_; j < n_i; j += nwarp_) {
-      const T *row = src + (long long)j * sp.inner;
-      for (int ti = lane_; ti < valid; ti += 32) buf[(pad + j) * pitch + ti] = (double)row[ti];
+    if (lane_ < valid) {
+      const T *col = src + lane_;
+      double *dst = buf + pad * pitch + lane_;
+      constexpr int RB = 16;
+      for (int j0 = warp_; j0 < n; j0 += nwarp_ * RB) {
+        double v[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int j = j0 + u * nwarp_;
+          v[u] = j < n ? (double)col[(long long)j * sp.inner] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int j = j0 + u * nwarp_;
+          if (j < n) dst[j * pitch] = v[u];
+        }
+      }
     }
   }
   __syncthreads();
-  // 2. ghosts: one thread per line
-  if (tid < valid) {
-    double mean = line_mean(buf, pad, pitch, tid, n);
-    if (SMOOTH) {
-      ghost_gauss_side(buf, pad, pitch, tid, n, mean, sp.eqs, false);
-      ghost_gauss_side(buf, pad, pitch, tid, n, mean, sp.eqs, true);
-    } else {
-      ghost_poly_side(buf, pad, pitch, tid, n, mean, sp.h, sp.eqs, sp.bcl, false, gm);
-      ghost_poly_side(buf, pad, pitch, tid, n, mean, sp.h, sp.eqs, sp.bcr, true, gm);
+  // 2. ghosts: lane = line, warp 0 fills the left side and warp 1 the right side (each sums the line itself, in
+  //    the same order, so both use the same mean)
+  for (int side = warp_; side < 2; side += nwarp_) {
+    if (lane_ < valid) {
+      double *bl = buf + lane_;
+      const double mean = line_mean(bl, pad, pitch, n);
+      if (SMOOTH) {
+        ghost_gauss_side(bl, pad, pitch, n, mean, sp.eqs, side == 1);
+      } else {
+        constexpr int EQS = TAPS > 0 ? TAPS / 2 : 5;
+        constexpr int NS = EQS == 5 ? 6 : 8;
+        ghost_poly_side<NS, EQS>(bl, pad, pitch, n, mean, sp.h, side ? sp.bcr : sp.bcl, side == 1, gm);
+      }
     }
   }
   __syncthreads();
@@ -234,83 +422,84 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm
     // registers, so one LDS feeds R DFMAs; taps are accumulated in the reference's order l = -E..E
     constexpr int R = SMOOTH_R;
     const int taps = sp.taps;
-    const int nblk = (int)((nout + R - 1) / R);
+    const int nblk = (nout + R - 1) / R;
     for (int kb = warp_; kb < nblk; kb += nwarp_)
-    for (int ti = lane_; ti < valid; ti += 32) {
-      const long long k0 = (long long)kb * R;
-      double acc[R], win[R];
-      int off = (int)k0 * pitch + ti;
+      for (int ti = lane_; ti < valid; ti += 32) {
+        const int k0 = kb * R;
+        double acc[R], win[R];
+        const double *p = buf + k0 * pitch + ti;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        acc[r] = 0.0;
-        win[r] = buf[off + r * pitch];
-      }
-      off += R * pitch;
-      for (int l = 0; l < taps; l += R) {
+        for (int r = 0; r < R; ++r) {
+          acc[r] = 0.0;
+          win[r] = p[r * pitch];
+        }
+        p += R * pitch;
+        int l = 0;
+        for (; l + R <= taps; l += R) {  // full groups: no predicates
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            const double wv = kw[l + u];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
+            win[u] = p[u * pitch];  // element k0 + (l+u) + R replaces k0 + (l+u), which no output needs any more
+          }
+          p += R * pitch;
+        }
 #pragma unroll
         for (int u = 0; u < R; ++u) {
           if (l + u < taps) {  // uniform
             const double wv = kw[l + u];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
-            win[u] = buf[off];  // element k0 + (l+u) + R replaces k0 + (l+u), which no output needs any more
-            off += pitch;
+            win[u] = p[u * pitch];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int k = k0 + r;
+          if (k < nout) {
+            if (AXIS0) out[(line0 + ti) * nout + k] = (T)acc[r];
+            else out[tile_i * TI + ti + (long long)k * sp.inner + o * sp.inner * nout] = (T)acc[r];
           }
         }
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const long long k = k0 + r;
-        if (k < nout) {
-          if (AXIS0) out[(line0 + ti) * nout + k] = (T)acc[r];
-          else out[tile_i * TI + ti + k * sp.inner + o * sp.inner * nout] = (T)acc[r];
-        }
-      }
-    }
   } else if (AXIS0) {
     // lane = output knot k (stores coalesced along the line); its 2 eqs blended weights stay in registers while
     // the thread walks the lines of the tile
-    const int kthreads = nout >= nth ? nth : (int)((nout + 31) / 32 * 32);
+    const int kthreads = nout >= nth ? nth : ((nout + 31) / 32 * 32);
     const int lgroups = nth / kthreads;
     const int kk = tid % kthreads, lg = tid / kthreads;
     if (lg < lgroups) {
-      for (long long k = kk; k < nout; k += kthreads) {
+      for (int k = kk; k < nout; k += kthreads) {
         const int base = __ldg(sp.base + k);
         double w[TAPS > 0 ? TAPS : 1];
 #pragma unroll
         for (int l = 0; l < TAPS; ++l) w[l] = __ldg(sp.W + (long long)l * nout + k);
+        T *orow = out + line0 * nout + k;
+#pragma unroll 2
         for (int ti = lg; ti < valid; ti += lgroups) {
-          int off = base * pitch + ti;
-          double acc = 0.0;
+          const double *p = buf + base * pitch + ti;
+          double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-          for (int l = 0; l < TAPS; ++l) {
-            acc = fma(buf[off], w[l], acc);
-            off += pitch;
+          for (int l = 0; l < TAPS; l += 2) {
+            a0 = fma(p[l * pitch], w[l], a0);
+            a1 = fma(p[(l + 1) * pitch], w[l + 1], a1);
           }
-          out[(line0 + ti) * nout + k] = (T)__dmul_rn(acc, sp.scale);
+          orow[(long long)ti * nout] = (T)__dmul_rn(a0 + a1, sp.scale);
         }
       }
     }
   } else {
-    // lane = line (loads from the tile and global stores coalesced along `inner`); a warp owns one output knot at
-    // a time: its weights are warp-uniform registers reused for every line of the tile
-    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
-    for (long long k = warp; k < nout; k += nwarp) {
-      const int base = __ldg(sp.base + k);
-      double w[TAPS > 0 ? TAPS : 1];
-#pragma unroll
-      for (int l = 0; l < TAPS; ++l) w[l] = __ldg(sp.W + (long long)l * nout + k);
-      T *orow = out + tile_i * TI + k * sp.inner + o * sp.inner * nout;
-      for (int ti = lane; ti < valid; ti += 32) {
-        int off = base * pitch + ti;
-        double acc = 0.0;
-#pragma unroll
-        for (int l = 0; l < TAPS; ++l) {
-          acc = fma(buf[off], w[l], acc);
-          off += pitch;
-        }
-        orow[ti] = (T)__dmul_rn(acc, sp.scale);
-      }
+    // lane = line (loads from the tile and global stores coalesced along `inner`): resample_lines
+    constexpr int TPX = (TAPS > 0) ? TAPS : 2;
+    const int kper = (nout + nwarp_ - 1) / nwarp_;
+    const int kbeg = warp_ * kper, kend = min(nout, kbeg + kper);
+    if (kbeg < kend && lane_ < valid) {
+      T *optr = out + tile_i * TI + lane_ + o * sp.inner * nout + (long long)kbeg * sp.inner;
+      if (sp.w_smem)
+        resample_lines<T, TPX, true>(buf + lane_, pitch, (const double2 *)wsm, bsm, kbeg, kend, optr, sp.inner, sp.scale);
+      else
+        resample_lines<T, TPX, false>(buf + lane_, pitch, (const double2 *)sp.Wk, sp.base, kbeg, kend, optr, sp.inner, sp.scale);
     }
   }
 }
@@ -371,7 +560,10 @@ static int launch_kernel(const SweepParams &sp, const GhostMats &gm, const T *in
   auto k = sweep_kernel<T, SMOOTH, AXIS0, TAPS, 0>;
   if (sp.pitch == (AXIS0 ? 33 : 32)) k = sweep_kernel<T, SMOOTH, AXIS0, TAPS, AXIS0 ? 33 : 32>;
   if (smem > 48 * 1024) CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)blocks, 256, smem, st>>>(sp, gm, in, out);
+  int threads = 256;
+  if (SMOOTH) threads = 32 * (int)std::max<long long>(2, std::min<long long>(8, (sp.n_out + SMOOTH_R - 1) / SMOOTH_R));
+  else if (!AXIS0) threads = 128;
+  k<<<(unsigned)blocks, threads, smem, st>>>(sp, gm, in, out);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   return CIB200_OK;
@@ -396,7 +588,7 @@ template <typename T, bool SMOOTH>
 static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out, bool axis0, cudaStream_t st) {
   // tile width: as many lines as fit, a power of two, at most 32 (the common full tile gets a compile-time pitch)
   const long long lines = axis0 ? sp.outer : sp.inner;
-  const long long nrow = sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_R : 0);
+  const long long nrow = sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R);
   const size_t budget = (size_t)std::min(max_dyn_smem(), 100 * 1024);
   int ti = 32;
   while (ti > 1 && (long long)ti / 2 >= lines) ti /= 2;
@@ -404,6 +596,8 @@ static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out,
     int pitch = axis0 ? (t > 1 ? t + 1 : 1) : t;
     return sizeof(double) * ((size_t)nrow * pitch + (SMOOTH ? sp.taps : 0));
   };
+  // resample along axis >= 1: weights [n_out][taps] + first-tap indices next to the tile when three CTAs still fit
+  const size_t w_bytes = (!SMOOTH && !axis0) ? sizeof(double) * (size_t)sp.taps * sp.n_out + sizeof(int) * (size_t)sp.n_out : 0;
   while (ti > 1 && bytes_for(ti) > budget) ti /= 2;
   if (bytes_for(ti) > (size_t)max_dyn_smem()) {
     set_error("sweep: a line of %lld points (+%d ghosts per side) does not fit in shared memory; lines up to ~%d points are supported",
@@ -412,7 +606,12 @@ static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out,
   }
   sp.ti = ti;
   sp.pitch = axis0 ? (ti > 1 ? ti + 1 : 1) : ti;
-  const size_t smem = bytes_for(ti);
+  size_t smem = bytes_for(ti);
+  sp.w_smem = 0;
+  if (w_bytes && sp.pitch == 32 && smem + w_bytes <= 75 * 1024) {
+    sp.w_smem = 1;
+    smem += w_bytes;
+  }
   long long blocks = axis0 ? (sp.outer + ti - 1) / ti : ((sp.inner + ti - 1) / ti) * sp.outer;
   if (blocks > 0x7fffffffLL) {
     set_error("sweep: grid too large");
@@ -453,19 +652,20 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     const double x_expanded_1 = knots_in[d][0] - (double)(eqs - 1) * h;  // :285
     const long long n_coef = nin + 2 * (eqs - 1);
     // tables + output knots + weights on the device
-    double *d_tk, *d_td, *d_ko, *d_W;
+    double *d_tk, *d_td, *d_ko, *d_W, *d_Wk;
     int *d_base;
     const size_t tab_bytes = sizeof(double) * CIB_TAB_ROWS * taps;
     if ((rc = tmp.alloc((void **)&d_tk, tab_bytes))) return rc;
     if ((rc = tmp.alloc((void **)&d_td, tab_bytes))) return rc;
     if ((rc = tmp.alloc((void **)&d_ko, sizeof(double) * (size_t)nout))) return rc;
     if ((rc = tmp.alloc((void **)&d_W, sizeof(double) * (size_t)nout * taps))) return rc;
+    if ((rc = tmp.alloc((void **)&d_Wk, sizeof(double) * (size_t)nout * taps))) return rc;
     if ((rc = tmp.alloc((void **)&d_base, sizeof(int) * (size_t)nout))) return rc;
     CIB_CUDA(cudaMemcpyAsync(d_tk, host_table(kernel[d], deriv[d]), tab_bytes, cudaMemcpyHostToDevice, st));
     CIB_CUDA(cudaMemcpyAsync(d_td, host_table(kernel[d], deriv[d] + 1), tab_bytes, cudaMemcpyHostToDevice, st));
     CIB_CUDA(cudaMemcpyAsync(d_ko, knots_out[d], sizeof(double) * (size_t)nout, cudaMemcpyHostToDevice, st));
     resample_weights_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(d_ko, nout, x_expanded_1, h, eqs, n_coef,
-                                                                           d_tk, d_td, d_W, d_base);
+                                                                           d_tk, d_td, d_W, d_Wk, d_base);
     CIB_LAUNCHED();
     CIB_CUDA(cudaGetLastError());
 
@@ -485,6 +685,7 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     sp.h = h;
     sp.scale = pow_int(-1.0 / h, deriv[d]);  // :379
     sp.W = d_W;
+    sp.Wk = d_Wk;
     sp.base = d_base;
     GhostMats gm;
     memset(&gm, 0, sizeof gm);
