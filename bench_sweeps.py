@@ -36,11 +36,12 @@ def timeit(fn, warmup=3, iters=10):
 def main():
     rng = np.random.default_rng(3)
     out = []
+    only = sys.argv[1] if len(sys.argv) > 1 else 'all'
     # C3: 3-D resample b13 128^3 -> 256^3 (+ derivative pass)
     kin = tuple(np.linspace(0, 2 * np.pi, 128) for _ in range(3))
     kout = tuple(np.linspace(0, 2 * np.pi, 256) for _ in range(3))
     v = torch.from_numpy(rng.random((128, 128, 128))).cuda()
-    for der in (0, (1, 0, 0)):
+    for der in ((0, (1, 0, 0)) if only in ('all', 'resample') else ()):
         best, med = timeit(lambda: ci.convolution_resample(kin, kout, v, kernel="b13", derivative=der))
         mb = (128 ** 3 + 256 * 128 ** 2) + (256 * 128 ** 2 + 256 ** 2 * 128) + (256 ** 2 * 128 + 256 ** 3)
         bytes_ = 8 * mb
@@ -49,7 +50,7 @@ def main():
                     "roofline": {"bound": "hbm", "achieved": bytes_ / (best * 1e-3) / 1e9, "peak": PEAK, "unit": "GB/s",
                                  "frac": bytes_ / (best * 1e-3) / 1e9 / PEAK, "model": "sum over passes (read+write) = 352.3 MB"}})
     # C4: 4-D smooth 40^4 and 64^4, B = 0.05
-    for n in (40, 64):
+    for n in ((40, 64) if only in ('all', 'smooth') else ()):
         ks = tuple(np.linspace(0, 2 * np.pi, n) for _ in range(4))
         v4 = torch.from_numpy(rng.random((n,) * 4)).cuda()
         best, med = timeit(lambda: ci.convolution_smooth(ks, v4, 0.05))
@@ -59,6 +60,10 @@ def main():
                     "roofline": {"bound": "hbm", "achieved": bytes_ / (best * 1e-3) / 1e9, "peak": PEAK, "unit": "GB/s",
                                  "frac": bytes_ / (best * 1e-3) / 1e9 / PEAK, "model": "4 passes x 16 B per grid point",
                                  "note": "40^4 (20 MB) is L2-resident: frac may exceed 1"}})
+    if only != 'all':
+        for o in out:
+            print(json.dumps(o), flush=True)
+        return
     # C1 / C2 point evaluation (latency / cache bound: reported, not graded against HBM)
     x = np.linspace(0, 1, 1000)
     it1 = ci.convolution_interpolation(x, np.sin(2 * np.pi * x))

@@ -468,7 +468,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_fn() {
+void *tma_encode_tiled_fn();
+static EncodeTiledFn encode_fn() { return (EncodeTiledFn)tma_encode_tiled_fn(); }
+void *tma_encode_tiled_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *ptr = nullptr;
@@ -477,7 +479,7 @@ static EncodeTiledFn encode_fn() {
         qres == cudaDriverEntryPointSuccess)
       fn = (EncodeTiledFn)ptr;
   }
-  return fn;
+  return (void *)fn;
 }
 
 bool binned_supported(const cib200_itp *h) {

@@ -101,6 +101,7 @@ struct cib200_itp {
 namespace cib {
 double jl_pow_int(double x, long long n);  // Julia Base pow_body restated (cib200_eval.cu)
 int sm_count();
+void *tma_encode_tiled_fn();  // cuTensorMapEncodeTiled through the runtime's driver entry point, or nullptr
 // K1 launchers (cib200_eval.cu)
 int launch_eval(const cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st);
 // binned strategy (cib200_binned.cu)

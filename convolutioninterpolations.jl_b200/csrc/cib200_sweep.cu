@@ -19,8 +19,10 @@
 //      W[l][k] + first-tap index (computed once per pass by resample_weights_kernel: they depend on
 //      (axis, k) only, the reference recomputes them for every line); smooth uses the (2E+1)-tap
 //      normalised Gaussian held in shared memory.
+#include <cuda.h>
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "cib200_device.cuh"
@@ -505,6 +507,379 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised variant of the same pass (Float64; used whenever a ring of tiles fits in shared
+// memory).  The phases of one tile are a dependent chain - global loads (~2 us under load), line mean, ghost fill,
+// only then the outputs - and in sweep_kernel every warp of the CTA waits at a barrier for each link of it.  Here a
+// CTA (one per SM) is a pipeline over the tiles it owns (tile = blockIdx.x + i gridDim.x) through a ring of NB tile
+// buffers, with three kinds of warps:
+//   loader (warp 0)        copies tile i global -> shared with per-thread 8-byte cp.async (LDGSTS: no register
+//                          staging, several tiles in flight; for axis 0 the copy also transposes) and lets the copies
+//                          themselves signal LOADED[b] (cp.async.mbarrier.arrive)
+//   ghost teams (2 warps)  wait LOADED[b], compute the line means and fill the ghosts (left / right warp), signal FULL[b]
+//   consumer groups        wait FULL[b], turn the tile into outputs, signal EMPTY[b] back to the loader
+// All hand-offs are mbarriers in shared memory; a tile's buffer index and barrier phase follow from its sequence
+// number, teams / groups take tiles round-robin, so nobody needs a scheduler.
+struct PipeCfg {
+  int tma;  // axis >= 1 with 16-byte aligned rows: one 3-D TMA per tile instead of per-element cp.async
+  int l;    // loader warps
+  int nb;   // ring depth
+  int g;    // ghost teams
+  int c;    // consumer groups
+  int cwg;  // warps per consumer group
+};
+static constexpr int PIPE_MAX_NB = 8;
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_copies(unsigned long long *bar) {
+  // arrives once every cp.async this thread issued so far has landed; does not change the expected count
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  // try_wait with a suspend-time hint parks the warp in hardware instead of spinning: a spinning consumer would take
+  // issue slots from the loader / ghost warps whose dependent chains are the critical path of the pipeline
+  unsigned done, spins = 0;
+  do {
+    if (++spins > (1u << 22)) __trap();  // a broken pipeline must not hang the device
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (!done) __nanosleep(128);
+  } while (!done);
+}
+__device__ __forceinline__ void stage_elem(double *dst, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+
+// two consecutive output knots from one register window (first taps o and o + D rows past the anchor): six
+// independent DFMA chains per lane
+template <int TP, int WIN, int O, int D>
+__device__ __forceinline__ void window_dot2(const double (&win)[WIN], const double (&w0)[TP], const double (&w1)[TP],
+                                            double &r0, double &r1) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int l = 0; l < TP; l += 3) {
+    a0 = fma(win[O + l], w0[l], a0);
+    b0 = fma(win[O + D + l], w1[l], b0);
+    if (l + 1 < TP) {
+      a1 = fma(win[O + l + 1], w0[l + 1], a1);
+      b1 = fma(win[O + D + l + 1], w1[l + 1], b1);
+    }
+    if (l + 2 < TP) {
+      a2 = fma(win[O + l + 2], w0[l + 2], a2);
+      b2 = fma(win[O + D + l + 2], w1[l + 2], b2);
+    }
+  }
+  r0 = (a0 + a1) + a2;
+  r1 = (b0 + b1) + b2;
+}
+
+// resample_lines with the output knots taken two at a time whenever the second one starts 0 or 1 rows after the first
+// (always, when upsampling): same per-knot arithmetic (three partial sums, combined the same way)
+template <typename T, int TP, bool WS>
+__device__ __forceinline__ void resample_lines2(const double *bl, const int pitch, const double2 *__restrict__ wsrc,
+                                                const int *__restrict__ bsrc, int kbeg, int kend, T *optr,
+                                                long long ostride, double scale) {
+  constexpr int R = RESAMPLE_R, WIN = TP + R - 1;
+  double win[WIN];
+  int a = load_b<WS>(bsrc + kbeg);
+#pragma unroll
+  for (int j = 0; j < WIN; ++j) win[j] = bl[(a + j) * pitch];
+  auto fetch = [&](int k, double(&w)[TP]) {
+    const double2 *src = wsrc + k * (TP / 2);
+#pragma unroll
+    for (int l = 0; l < TP; l += 2) {
+      const double2 v = load_w2<WS>(src + (l >> 1));
+      w[l] = v.x;
+      w[l + 1] = v.y;
+    }
+  };
+  int k = kbeg;
+  int b0 = a;
+  while (k < kend) {
+    if ((unsigned)(b0 - a) >= (unsigned)(R - 1)) {  // warp-uniform: keep o <= R-2 so that a pair always fits
+      a = b0;
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) win[j] = bl[(a + j) * pitch];
+    }
+    const int o = b0 - a;
+    int b1 = b0, d = -1;
+    if (k + 1 < kend) {
+      b1 = load_b<WS>(bsrc + k + 1);
+      d = b1 - b0;
+    }
+    double w0[TP];
+    fetch(k, w0);
+    if ((unsigned)d <= 1u) {
+      double w1[TP];
+      fetch(k + 1, w1);
+      double r0, r1;
+      switch (o * 2 + d) {
+        case 0: window_dot2<TP, WIN, 0, 0>(win, w0, w1, r0, r1); break;
+        case 1: window_dot2<TP, WIN, 0, 1>(win, w0, w1, r0, r1); break;
+        case 2: window_dot2<TP, WIN, 1, 0>(win, w0, w1, r0, r1); break;
+        case 3: window_dot2<TP, WIN, 1, 1>(win, w0, w1, r0, r1); break;
+        case 4: window_dot2<TP, WIN, 2, 0>(win, w0, w1, r0, r1); break;
+        case 5: window_dot2<TP, WIN, 2, 1>(win, w0, w1, r0, r1); break;
+        case 6: window_dot2<TP, WIN, 3, 0>(win, w0, w1, r0, r1); break;
+        case 7: window_dot2<TP, WIN, 3, 1>(win, w0, w1, r0, r1); break;
+        case 8: window_dot2<TP, WIN, 4, 0>(win, w0, w1, r0, r1); break;
+        case 9: window_dot2<TP, WIN, 4, 1>(win, w0, w1, r0, r1); break;
+        case 10: window_dot2<TP, WIN, 5, 0>(win, w0, w1, r0, r1); break;
+        case 11: window_dot2<TP, WIN, 5, 1>(win, w0, w1, r0, r1); break;
+        case 12: window_dot2<TP, WIN, 6, 0>(win, w0, w1, r0, r1); break;
+        default: window_dot2<TP, WIN, 6, 1>(win, w0, w1, r0, r1); break;
+      }
+      optr[0] = (T)__dmul_rn(r0, scale);
+      optr[ostride] = (T)__dmul_rn(r1, scale);
+      optr += 2 * ostride;
+      k += 2;
+      b0 = k < kend ? load_b<WS>(bsrc + k) : b1;
+    } else {
+      double acc;
+      switch (o) {
+        case 0: acc = window_dot<TP, WIN, 0>(win, w0); break;
+        case 1: acc = window_dot<TP, WIN, 1>(win, w0); break;
+        case 2: acc = window_dot<TP, WIN, 2>(win, w0); break;
+        case 3: acc = window_dot<TP, WIN, 3>(win, w0); break;
+        case 4: acc = window_dot<TP, WIN, 4>(win, w0); break;
+        case 5: acc = window_dot<TP, WIN, 5>(win, w0); break;
+        default: acc = window_dot<TP, WIN, 6>(win, w0); break;
+      }
+      *optr = (T)__dmul_rn(acc, scale);
+      optr += ostride;
+      k += 1;
+      b0 = b1;
+    }
+  }
+}
+
+template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
+__global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
+    sweep_pipe_kernel(const __grid_constant__ CUtensorMap tmap, SweepParams sp, GhostMats gm, PipeCfg cfg,
+                      const T *__restrict__ in, T *__restrict__ out, long long ntiles) {
+  extern __shared__ __align__(128) double sm[];
+  constexpr int PITCH = AXIS0 ? 33 : 32;
+  constexpr int TP = (TAPS > 0) ? TAPS : 2;
+  const int pad = sp.pad;
+  const int n = (int)sp.n_in, nout = (int)sp.n_out;
+  const int nrow = n + 2 * pad;
+  const int bufsz = ((nrow + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R)) * PITCH + 1) & ~1;  // doubles, even
+  const int NB = cfg.nb;
+  double *extra = sm + NB * bufsz;  // smooth: kw[taps] ; resample (axis >= 1): W[nout][TP] + base[nout]
+  int *bsm = (int *)(extra + TP * nout);
+  const int extra_doubles = SMOOTH ? ((sp.taps + 1) & ~1) : ((!AXIS0 && sp.w_smem) ? TP * nout + ((nout + 1) >> 1) : 0);
+  unsigned long long *bars = (unsigned long long *)(extra + extra_doubles);
+  unsigned long long *loaded = bars, *full = bars + PIPE_MAX_NB, *empty = bars + 2 * PIPE_MAX_NB;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  // one-time: clear the ring (ghost slots the fill never writes stay 0 like the reference's zero-filled line buffer:
+  // resample :309, smooth :96), stage the pass constants, initialise the barriers
+  for (int e = tid; e < NB * bufsz; e += nth) sm[e] = 0.0;
+  if (SMOOTH) {
+    for (int e = tid; e < sp.taps; e += nth) extra[e] = sp.W[e];
+  } else if (!AXIS0 && sp.w_smem) {
+    const double2 *src = (const double2 *)sp.Wk;
+    double2 *dst = (double2 *)extra;
+    for (int e = tid; e < TP * nout / 2; e += nth) dst[e] = __ldg(src + e);
+    for (int e = tid; e < nout; e += nth) bsm[e] = __ldg(sp.base + e);
+  }
+  if (tid == 0) {
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(loaded + b, cfg.tma ? 1 : 32 * cfg.l);
+      mbar_init(full + b, 64);
+      mbar_init(empty + b, 32 * cfg.cwg);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long tiles_inner = AXIS0 ? 1 : (sp.inner + 31) / 32;
+  const long long tstep = gridDim.x;
+  auto tile_valid = [&](long long t) {
+    const long long rem = AXIS0 ? sp.outer - t * 32 : sp.inner - (t % tiles_inner) * 32;
+    return rem < 32 ? (int)rem : 32;
+  };
+
+  if (warp < cfg.l) {
+    // ------------------------------- loader(s) --------------------------------------------------
+    int i = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += tstep, ++i) {
+      const int b = i % NB, rev = i / NB;
+      double *buf = sm + b * bufsz;
+      if (rev > 0) mbar_wait(empty + b, (unsigned)(rev - 1) & 1u);
+      if (!AXIS0 && cfg.tma) {
+        if (lane == 0) {
+          const long long tile_i = t % tiles_inner, o = t / tiles_inner;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(loaded + b)),
+                       "r"((unsigned)(32 * n * 8))
+                       : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                  smem_addr(buf + pad * PITCH)),
+              "l"(&tmap), "r"((int)(tile_i * 32)), "r"(0), "r"((int)o), "r"(smem_addr(loaded + b))
+              : "memory");
+        }
+        continue;
+      }
+      const int valid = tile_valid(t);
+      if (AXIS0) {
+        // lanes along the line (coalesced 256-byte reads), destination transposed: element (ti, j) -> row pad + j
+        const double *src = (const double *)in + t * 32 * n + (long long)warp * n + lane;
+        double *dst = buf + (pad + lane) * PITCH + warp;
+        for (int ti = warp; ti < valid; ti += cfg.l) {
+          for (int j = lane, q = 0; j < n; j += 32, q += 32) stage_elem(dst + q * PITCH, src + q);
+          src += (long long)cfg.l * n;
+          dst += cfg.l;
+        }
+      } else if (lane < valid) {
+        const long long tile_i = t % tiles_inner, o = t / tiles_inner;
+        const double *col = (const double *)in + tile_i * 32 + o * sp.inner * n + lane + (long long)warp * sp.inner;
+        double *dst = buf + (pad + warp) * PITCH + lane;
+        const long long cs = (long long)cfg.l * sp.inner;
+        const int ds = cfg.l * PITCH;
+#pragma unroll 4
+        for (int j = warp; j < n; j += cfg.l) {
+          stage_elem(dst, col);
+          col += cs;
+          dst += ds;
+        }
+      }
+      mbar_arrive_on_copies(loaded + b);
+    }
+  } else if (warp < cfg.l + 2 * cfg.g) {
+    // ------------------------------- ghost teams ------------------------------------------------
+    const int team = (warp - cfg.l) >> 1, side = (warp - cfg.l) & 1;
+    int i = team;
+    for (long long t = blockIdx.x + team * tstep; t < ntiles; t += cfg.g * tstep, i += cfg.g) {
+      const int b = i % NB, rev = i / NB;
+      double *buf = sm + b * bufsz;
+      mbar_wait(loaded + b, (unsigned)rev & 1u);
+      if (lane < tile_valid(t)) {
+        double *bl = buf + lane;
+        const double mean = line_mean(bl, pad, PITCH, n);
+        if (SMOOTH) {
+          ghost_gauss_side(bl, pad, PITCH, n, mean, sp.eqs, side == 1);
+        } else {
+          constexpr int EQS = TAPS > 0 ? TAPS / 2 : 5;
+          constexpr int NS = EQS == 5 ? 6 : 8;
+          ghost_poly_side<NS, EQS>(bl, pad, PITCH, n, mean, sp.h, side ? sp.bcr : sp.bcl, side == 1, gm);
+        }
+      }
+      mbar_arrive(full + b);
+    }
+  } else {
+    // ------------------------------- consumer groups --------------------------------------------
+    const int cidx = warp - cfg.l - 2 * cfg.g;
+    const int grp = cidx / cfg.cwg, cw = cidx - grp * cfg.cwg, CW = cfg.cwg;
+    if (grp < cfg.c) {
+      int i = grp;
+      for (long long t = blockIdx.x + grp * tstep; t < ntiles; t += cfg.c * tstep, i += cfg.c) {
+        const int b = i % NB, rev = i / NB;
+        const double *buf = sm + b * bufsz;
+        const int valid = tile_valid(t);
+        long long tile_i = 0, o = 0, line0 = 0;
+        if (AXIS0) {
+          line0 = t * 32;
+        } else {
+          tile_i = t % tiles_inner;
+          o = t / tiles_inner;
+        }
+        mbar_wait(full + b, (unsigned)rev & 1u);
+        if (SMOOTH) {
+          constexpr int R = SMOOTH_R;
+          const double *kw = extra;
+          const int taps = sp.taps;
+          const int nblk = (nout + R - 1) / R;
+          if (lane < valid)
+            for (int kb = cw; kb < nblk; kb += CW) {
+              const int k0 = kb * R;
+              double acc[R], win[R];
+              const double *p = buf + k0 * PITCH + lane;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                acc[r] = 0.0;
+                win[r] = p[r * PITCH];
+              }
+              p += R * PITCH;
+              int l = 0;
+              for (; l + R <= taps; l += R) {  // full groups: no predicates
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                  const double wv = kw[l + u];
+#pragma unroll
+                  for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
+                  win[u] = p[u * PITCH];
+                }
+                p += R * PITCH;
+              }
+#pragma unroll
+              for (int u = 0; u < R; ++u) {
+                if (l + u < taps) {  // uniform
+                  const double wv = kw[l + u];
+#pragma unroll
+                  for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
+                  win[u] = p[u * PITCH];
+                }
+              }
+              T *op = AXIS0 ? out + (line0 + lane) * nout + k0
+                            : out + tile_i * 32 + lane + (long long)k0 * sp.inner + o * sp.inner * nout;
+              const long long os = AXIS0 ? 1 : sp.inner;
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                if (k0 + r < nout) op[r * os] = (T)acc[r];
+            }
+        } else if (AXIS0) {
+          // lane = output knot k (stores coalesced along the line); weights in registers across the lines of the tile
+          const int cn = 32 * CW, ctid = cw * 32 + lane;
+          const int kthreads = nout >= cn ? cn : ((nout + 31) / 32 * 32);
+          const int lgroups = cn / kthreads;
+          const int kk = ctid % kthreads, lg = ctid / kthreads;
+          if (lg < lgroups) {
+            for (int k = kk; k < nout; k += kthreads) {
+              const int base = __ldg(sp.base + k);
+              double w[TP];
+#pragma unroll
+              for (int l = 0; l < TP; ++l) w[l] = __ldg(sp.W + (long long)l * nout + k);
+              T *orow = out + line0 * nout + k;
+#pragma unroll 2
+              for (int ti = lg; ti < valid; ti += lgroups) {
+                const double *p = buf + base * PITCH + ti;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int l = 0; l < TP; l += 2) {
+                  a0 = fma(p[l * PITCH], w[l], a0);
+                  a1 = fma(p[(l + 1) * PITCH], w[l + 1], a1);
+                }
+                orow[(long long)ti * nout] = (T)__dmul_rn(a0 + a1, sp.scale);
+              }
+            }
+          }
+        } else {
+          const int kper = (((nout + CW - 1) / CW) + 1) & ~1;  // even: pairs never straddle two warps' ranges
+          const int kbeg = cw * kper, kend = min(nout, kbeg + kper);
+          if (kbeg < kend && lane < valid) {
+            T *optr = out + tile_i * 32 + lane + o * sp.inner * nout + (long long)kbeg * sp.inner;
+            if (sp.w_smem)
+              resample_lines2<T, TP, true>(buf + lane, PITCH, (const double2 *)extra, bsm, kbeg, kend, optr, sp.inner, sp.scale);
+            else
+              resample_lines2<T, TP, false>(buf + lane, PITCH, (const double2 *)sp.Wk, sp.base, kbeg, kend, optr, sp.inner, sp.scale);
+          }
+        }
+        mbar_arrive(empty + b);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 static void lagrange_rows(int m, int rows, double *out, int ld) {
   for (int j = 1; j <= rows; ++j)
     for (int k = 0; k < m; ++k) {
@@ -584,8 +959,123 @@ static int launch_taps(const SweepParams &sp, const GhostMats &gm, const T *in, 
   return CIB200_EUNSUPPORTED;
 }
 
+template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
+static int launch_pipe_kernel(const SweepParams &sp, const GhostMats &gm, const PipeCfg &cfg, const T *in, T *out,
+                              long long ntiles, int threads, size_t smem, cudaStream_t st) {
+  auto k = sweep_pipe_kernel<T, SMOOTH, AXIS0, TAPS>;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  if (cfg.tma) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    cuuint64_t gdim[3] = {(cuuint64_t)sp.inner, (cuuint64_t)sp.n_in, (cuuint64_t)sp.outer};
+    cuuint64_t gstr[2] = {(cuuint64_t)sp.inner * 8, (cuuint64_t)sp.inner * (cuuint64_t)sp.n_in * 8};
+    cuuint32_t box[3] = {32, (cuuint32_t)sp.n_in, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)tma_encode_tiled_fn())(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<T *>(in), gdim,
+                                                        gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("sweep: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      return CIB200_ECUDA;
+    }
+  }
+  CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long grid = std::min<long long>(ntiles, (long long)sm_count());
+  k<<<(unsigned)grid, threads, smem, st>>>(tmap, sp, gm, cfg, in, out, ntiles);
+  CIB_LAUNCHED();
+  CIB_CUDA(cudaGetLastError());
+  return CIB200_OK;
+}
+
+template <typename T, bool SMOOTH, bool AXIS0>
+static int launch_pipe_taps(const SweepParams &sp, const GhostMats &gm, const PipeCfg &cfg, const T *in, T *out,
+                            long long ntiles, int threads, size_t smem, cudaStream_t st) {
+  if (SMOOTH) return launch_pipe_kernel<T, true, AXIS0, 0>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+  switch (sp.taps) {
+    case 10: return launch_pipe_kernel<T, false, AXIS0, 10>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    case 12: return launch_pipe_kernel<T, false, AXIS0, 12>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    case 14: return launch_pipe_kernel<T, false, AXIS0, 14>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    case 16: return launch_pipe_kernel<T, false, AXIS0, 16>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    case 18: return launch_pipe_kernel<T, false, AXIS0, 18>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+  }
+  set_error("sweep: unsupported tap count %d", sp.taps);
+  return CIB200_EUNSUPPORTED;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
+// returns -1 when the pass does not qualify for the pipelined kernel (Float32, or a ring of >= 3 tiles does not fit)
+template <typename T, bool SMOOTH>
+static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *out, bool axis0, cudaStream_t st) {
+  if (env_int("CIB200_SWEEP_NO_PIPE", 0) == 1) return -1;
+  if (sizeof(T) != sizeof(double)) return -1;  // the asynchronous staging copies 8-byte elements
+  const int pitch = axis0 ? 33 : 32;
+  const size_t bufsz = (((size_t)(sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R)) * pitch + 1) & ~(size_t)1);
+  const size_t tile_bytes = sizeof(double) * bufsz;
+  const size_t bar_bytes = 8 * 3 * PIPE_MAX_NB;
+  const size_t budget = (size_t)max_dyn_smem();
+  size_t fixed = bar_bytes;
+  sp.w_smem = 0;
+  if (SMOOTH) {
+    fixed += sizeof(double) * (size_t)((sp.taps + 1) & ~1);
+  } else if (!axis0) {
+    const size_t w_bytes = sizeof(double) * ((size_t)sp.taps * sp.n_out + (size_t)((sp.n_out + 1) >> 1));
+    if (fixed + w_bytes + 4 * tile_bytes <= budget) {
+      sp.w_smem = 1;
+      fixed += w_bytes;
+    }
+  }
+  if (fixed + 3 * tile_bytes > budget) return -1;
+  PipeCfg cfg;
+  cfg.nb = (int)std::min<size_t>(PIPE_MAX_NB, (budget - fixed) / tile_bytes);
+  // consumers: a group of cwg warps works on one tile
+  int regs_per_thread;  // what ptxas needs for the consumer code (bounds the thread count: 64k registers per SM)
+  if (SMOOTH) {
+    cfg.cwg = (int)std::max<long long>(1, std::min<long long>(8, (sp.n_out + SMOOTH_R - 1) / SMOOTH_R));
+    regs_per_thread = 80;
+  } else if (axis0) {
+    cfg.cwg = 8;
+    regs_per_thread = 80;
+  } else {
+    cfg.cwg = 8;
+    regs_per_thread = 168;
+  }
+  const int max_warps = SMOOTH ? 32 : (axis0 ? 20 : 12);  // the kernels' __launch_bounds__
+  (void)regs_per_thread;
+  cfg.g = SMOOTH ? 2 : 1;
+  // one 3-D TMA per tile when the rows are 16-byte aligned (box 32 x n_in x 1, n_in <= 256); otherwise four loader
+  // warps issue per-element cp.async
+  cfg.tma = (!axis0 && (sp.inner % 2 == 0) && sp.n_in <= 256 && sp.inner * 8 < (1LL << 40) && tma_encode_tiled_fn() != nullptr &&
+             ((uintptr_t)in % 16 == 0) && env_int("CIB200_PIPE_NO_TMA", 0) != 1) ? 1 : 0;
+  cfg.l = cfg.tma ? 1 : (SMOOTH ? 4 : 2);
+  cfg.c = std::max(1, (max_warps - cfg.l - 2 * cfg.g) / cfg.cwg);
+  cfg.c = std::min(cfg.c, std::max(1, cfg.nb - cfg.g - 1));
+  cfg.g = env_int("CIB200_PIPE_G", cfg.g);
+  cfg.c = env_int("CIB200_PIPE_C", cfg.c);
+  cfg.cwg = env_int("CIB200_PIPE_CWG", cfg.cwg);
+  cfg.nb = std::min(cfg.nb, env_int("CIB200_PIPE_NB", cfg.nb));
+  const int threads = 32 * (cfg.l + 2 * cfg.g + cfg.c * cfg.cwg);
+  if (threads > 32 * max_warps || cfg.nb < 3) return -1;
+  sp.ti = 32;
+  sp.pitch = pitch;
+  const size_t smem = fixed + (size_t)cfg.nb * tile_bytes;
+  const long long ntiles = axis0 ? (sp.outer + 31) / 32 : ((sp.inner + 31) / 32) * sp.outer;
+  if (axis0) return launch_pipe_taps<T, SMOOTH, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+  return launch_pipe_taps<T, SMOOTH, false>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+}
+
 template <typename T, bool SMOOTH>
 static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out, bool axis0, cudaStream_t st) {
+  {
+    const int rc = try_launch_pipe<T, SMOOTH>(sp, gm, in, out, axis0, st);
+    if (rc >= 0) return rc;
+  }
   // tile width: as many lines as fit, a power of two, at most 32 (the common full tile gets a compile-time pitch)
   const long long lines = axis0 ? sp.outer : sp.inner;
   const long long nrow = sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R);
