@@ -37,6 +37,7 @@ static constexpr int BRICK_SIDE = 25;        // T + 2E - 1
 static constexpr int BRICK_PITCH = 26;       // inner TMA box extent: 26 * 8 B is a multiple of 16 B
 static constexpr int BRICK_DOUBLES = BRICK_PITCH * BRICK_SIDE * BRICK_SIDE;
 static constexpr int CHUNK_QUERIES = 4096;   // queries per work item
+static constexpr int BIN_U = 4;              // queries per thread and iteration in the binning passes
 static constexpr int MAX_BINS = 49152;       // u32 histogram must fit one CTA's shared memory (192 KB)
 
 struct BinGeom {
@@ -63,6 +64,7 @@ struct BinState {
   size_t cap_q;       // queries the scratch can hold
   // scratch layout (device)
   Record *rec;
+  Record *rec2;       // records sorted by (tile, cell) - cell-sorted variant only
   unsigned *hist;     // [nblk][nbin] counts -> write cursors
   unsigned *tile_start;  // [nbin + 1]
   WorkItem *items;
@@ -80,17 +82,25 @@ __device__ __forceinline__ int first_coef(double x, double knot0, double h, int 
   return (int)(i - eqs);
 }
 
-__device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, const double *x, const double *k0) {
+// bin of a query; lcell = its cell inside the tile, (cz T + cy) T + cx (0 for the spill bin)
+__device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, const double *x, const double *k0,
+                                        unsigned &lcell) {
+  lcell = 0;
   bool inside = true;
 #pragma unroll
   for (int d = 0; d < 3; ++d)
     if (x[d] > p.hi[d] || x[d] < p.lo[d]) inside = false;
   if (!inside) return g.ntiles;
   bool ok = true;
-  int t[3];
+  int t[3], c[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) t[d] = first_coef(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], ok) / g.T;
+  for (int d = 0; d < 3; ++d) {
+    const int fc = first_coef(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], ok);
+    t[d] = fc / g.T;
+    c[d] = fc - t[d] * g.T;
+  }
   if (!ok) return g.ntiles;
+  lcell = (unsigned)((c[2] * g.T + c[1]) * g.T + c[0]);
   return (t[2] * g.nt[1] + t[1]) * g.nt[0] + t[0];
 }
 
@@ -104,11 +114,21 @@ __global__ void __launch_bounds__(1024, 1) bin_count_kernel(ItpParams p, BinGeom
   per = (per + 31) & ~31LL;
   const long long q0 = (long long)blockIdx.x * per;
   const long long q1 = q0 + per < nq ? q0 + per : nq;
-  for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-    double x[3];
+  // BIN_U queries per thread and iteration: all their coordinate loads are in flight before the first is used
+  for (long long qb = q0 + threadIdx.x; qb < q1; qb += (long long)BIN_U * blockDim.x) {
+    double x[BIN_U][3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) x[d] = ((const double *)c.x[d])[q];
-    atomicAdd(&sh[classify(p, g, x, k0)], 1u);
+    for (int u = 0; u < BIN_U; ++u) {
+      const long long q = qb + (long long)u * blockDim.x;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? ((const double *)c.x[d])[q] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < BIN_U; ++u) {
+      const long long q = qb + (long long)u * blockDim.x;
+      unsigned lc;
+      if (q < q1) atomicAdd(&sh[classify(p, g, x[u], k0, lc)], 1u);
+    }
   }
   __syncthreads();
   unsigned *dst = hist + (size_t)blockIdx.x * g.nbin;
@@ -167,7 +187,8 @@ __global__ void __launch_bounds__(1024, 1) bin_scan_kernel(BinGeom g, unsigned *
   if (tid == 1023) {
     tile_start[g.nbin] = part[1023];
     n_items[0] = part2[1023];
-    n_items[1] = 0;  // work counter
+    n_items[1] = 0;  // work counter of the evaluation kernel
+    n_items[2] = 0;  // tile counter of the cell sort
   }
 }
 
@@ -194,18 +215,124 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
   per = (per + 31) & ~31LL;
   const long long q0 = (long long)blockIdx.x * per;
   const long long q1 = q0 + per < nq ? q0 + per : nq;
-  for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-    double x[3];
+  for (long long qb = q0 + threadIdx.x; qb < q1; qb += (long long)BIN_U * blockDim.x) {
+    double x[BIN_U][3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) x[d] = ((const double *)c.x[d])[q];
-    const unsigned slot = atomicAdd(&sh[classify(p, g, x, k0)], 1u);
-    // one 32-byte sector per query, written with two 16-byte stores
-    double2 a = make_double2(x[0], x[1]);
-    double2 b = make_double2(x[2], __hiloint2double(0, (int)(unsigned)q));
-    double2 *dst = (double2 *)(rec + slot);
-    dst[0] = a;
-    dst[1] = b;
+    for (int u = 0; u < BIN_U; ++u) {
+      const long long q = qb + (long long)u * blockDim.x;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? ((const double *)c.x[d])[q] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < BIN_U; ++u) {
+      const long long q = qb + (long long)u * blockDim.x;
+      if (q < q1) {
+        unsigned lc;
+        const unsigned slot = atomicAdd(&sh[classify(p, g, x[u], k0, lc)], 1u);
+        // one 32-byte sector per query, written with two 16-byte stores; the spare word carries the cell inside the tile
+        double2 a = make_double2(x[u][0], x[u][1]);
+        double2 b = make_double2(x[u][2], __hiloint2double((int)lc, (int)(unsigned)q));
+        double2 *dst = (double2 *)(rec + slot);
+        dst[0] = a;
+        dst[1] = b;
+      }
+    }
   }
+}
+
+// ---- pass B2: counting sort of every tile's records by cell ---------------------------------------
+// One CTA per tile at a time (persistent CTAs pull tiles from a counter): histogram of the 12-bit cell ids carried
+// by the records in shared memory, exclusive scan, then the records are re-read (L2) and written to their slot in
+// the second record array.  Afterwards the queries of a cell are consecutive, so the evaluation kernel can keep the
+// cell's (2E)^3 coefficients in registers for the whole run.
+static constexpr int CELLS_MAX = 4096;  // T^3 with T = 16 (E = 5); smaller for wider kernels
+
+__global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const Record *__restrict__ rec,
+                                                               Record *__restrict__ rec2,
+                                                               const unsigned *__restrict__ tile_start,
+                                                               unsigned *__restrict__ counter) {
+  __shared__ unsigned hist[CELLS_MAX];
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncell = g.T * g.T * g.T;
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= (unsigned)g.ntiles) break;
+    const unsigned r0 = tile_start[tile], r1 = tile_start[tile + 1];
+    for (int i = tid; i < CELLS_MAX; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (unsigned rb = r0 + tid; rb < r1; rb += 4 * 1024) {
+      int cell[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned r = rb + u * 1024;
+        cell[u] = r < r1 ? __ldg((const int2 *)(rec + r) + 3).y : -1;  // {idx, cell}
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cell[u] >= 0) atomicAdd(&hist[cell[u]], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of hist[0..4095]: 4 consecutive bins per thread, warp scan, scan of the 32 warp totals
+    unsigned v[4], tsum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = hist[tid * 4 + i];
+      tsum += v[i];
+    }
+    unsigned inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = wsum[lane], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += y;
+      }
+      wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    unsigned run = r0 + wsum[warp] + inc - tsum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hist[tid * 4 + i] = run;
+      run += v[i];
+    }
+    __syncthreads();
+    for (unsigned rb = r0 + tid; rb < r1; rb += 4 * 1024) {
+      double2 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned r = rb + u * 1024;
+        if (r < r1) {
+          const double2 *src = (const double2 *)(rec + r);
+          a[u] = __ldg(src);
+          b[u] = __ldg(src + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned r = rb + u * 1024;
+        if (r < r1) {
+          const unsigned slot = atomicAdd(&hist[__double2hiint(b[u].y)], 1u);
+          double2 *dst = (double2 *)(rec2 + slot);
+          dst[0] = a[u];
+          dst[1] = b[u];
+        }
+      }
+    }
+    __syncthreads();  // hist / s_tile are reused by the next tile
+  }
+  (void)ncell;
 }
 
 // ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG, SYNCS) -----------------------------------
@@ -435,6 +562,215 @@ __global__ void __launch_bounds__(512, 1)
   }
 }
 
+// ---- pass C, cell-sorted variant ---------------------------------------------------------------
+// Same lane layout and the same arithmetic as eval_binned_kernel, but the records of a work item arrive sorted by
+// cell (pass B2) and every warp owns a CONTIGUOUS range of them: the KM x W coefficients a lane needs from the
+// cell's stencil stay in registers for the whole run of queries that share the cell (10^9 queries on 512^3 cells:
+// 7.5 per cell), so a query costs its weights and 50 DFMAs instead of 40 + 15 shared-memory loads feeding them.
+// The blended weights of 8 queries are produced together (lane = one (axis, tap) pair, fixed for the whole kernel)
+// into a per-warp [8][32] scratch, one __syncwarp per 8 queries.
+template <int E>
+struct CellrunWarpSmem {
+  static constexpr int HB = 32 * 3 * 4;  // Hermite basis per (query, axis): h00 h01 h10' h11'
+  static constexpr int MISC = 32 * 2;    // int4 per query: brick offset + 3 table rows
+  static constexpr int WQ = 8 * 32;      // blended weights of 8 queries, 32 doubles per query ([3][W] used)
+  static constexpr int DOUBLES = HB + MISC + WQ;
+};
+
+template <int E>
+__global__ void __launch_bounds__(384, 1)
+    eval_cellrun_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
+                        const Record *__restrict__ rec, const WorkItem *__restrict__ items,
+                        unsigned *__restrict__ n_items, double *__restrict__ out, int use_tma) {
+  using WS = CellrunWarpSmem<E>;
+  constexpr int W = 2 * E, G = 32 / W, ACTIVE = W * G, KM = (W + G - 1) / G;
+  static_assert(3 * W <= 32, "one lane per (axis, tap) pair");
+  constexpr int PITCH = BRICK_PITCH, PLANE = BRICK_PITCH * BRICK_SIDE;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *brick = (double *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][BRICK_PITCH], axis 0 contiguous
+  double *tab = brick + BRICK_DOUBLES;
+  const double *tk[3];
+  const double *td[3];
+  stage_tables(p, tab, tk, td);
+  const int nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wbase = BRICK_DOUBLES + ((tables_smem_doubles(p) + 1) & ~1);  // doubles from the start of shared memory
+  double *wsm = brick + wbase + warp * WS::DOUBLES;
+  double *hbs = wsm;                        // [32][3][4]
+  int *misc = (int *)(wsm + WS::HB);        // [32][4]
+  double *wq = wsm + WS::HB + WS::MISC;     // [8][32]
+  unsigned long long *bar = (unsigned long long *)(brick + wbase + nwarps * WS::DOUBLES);
+  unsigned *slot = (unsigned *)(bar + 1);  // [2]
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double k0[3] = {__ldg(p.knots[0]), __ldg(p.knots[1]), __ldg(p.knots[2])};
+  const int l = lane % W, gl = lane / W;
+  const bool active = lane < ACTIVE;
+  const int lane_off = active ? l + gl * PITCH : (W - 1) + (G - 1) * PITCH;
+  const int gle = active ? gl : G - 1;
+  bool kval[KM];
+#pragma unroll
+  for (int k = 0; k < KM; ++k) kval[k] = gle + k * G < W;
+  // weight role of this lane: axis wa, tap wcol; table offsets relative to `brick` keep the loads in the shared window
+  const bool wrole = lane < 3 * W;
+  const int wa = wrole ? lane / W : 2, wcol = wrole ? lane - wa * W : 0;
+  const int tko = (int)((wa == 0 ? tk[0] : (wa == 1 ? tk[1] : tk[2])) - brick) + wcol;
+  const int tdo = (int)((wa == 0 ? td[0] : (wa == 1 ? td[1] : td[2])) - brick) + wcol;
+  const unsigned total_items = n_items[0];
+  unsigned parity = 0;
+  double creg[KM][W];  // this lane's share of the current cell's stencil: c[l, gle + k G, n]
+#pragma unroll
+  for (int k = 0; k < KM; ++k)
+#pragma unroll
+    for (int n = 0; n < W; ++n) creg[k][n] = 0.0;
+  for (unsigned iter = 0;; ++iter) {
+    if (threadIdx.x == 0) slot[iter & 1] = atomicAdd(&n_items[1], 1u);
+    __syncthreads();  // also: every warp is done with the previous brick
+    const unsigned item = slot[iter & 1];
+    if (item >= total_items) break;
+    const WorkItem it = items[item];
+    const int tx = it.bin % g.nt[0], ty = (it.bin / g.nt[0]) % g.nt[1], tz = it.bin / (g.nt[0] * g.nt[1]);
+    const int org[3] = {tx * g.T, ty * g.T, tz * g.T};
+    if (use_tma) {
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, BRICK_DOUBLES * 8);
+        tma_load_3d(brick, &tmap, org[0], org[1], org[2], bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1;
+    } else {
+      const double *__restrict__ cg = (const double *)p.coefs;
+      for (int e = threadIdx.x; e < BRICK_DOUBLES; e += blockDim.x) {
+        const int bx = e % BRICK_PITCH, by = (e / BRICK_PITCH) % BRICK_SIDE, bz = e / (BRICK_PITCH * BRICK_SIDE);
+        const int gx = org[0] + bx, gy = org[1] + by, gz = org[2] + bz;
+        brick[e] = (gx < p.nk[0] && gy < p.nk[1] && gz < p.nk[2]) ? __ldg(cg + gx + (long long)gy * p.s1 + (long long)gz * p.s2) : 0.0;
+      }
+      __syncthreads();
+    }
+    int cur = -1;  // brick offset of the cell held in creg (a new brick invalidates it)
+    // contiguous range of this warp, in whole batches of 32 records
+    const unsigned per = ((it.count + nwarps - 1) / nwarps + 31u) & ~31u;
+    const unsigned w0 = warp * per, w1 = min(it.count, w0 + per);
+    for (unsigned b0 = w0; b0 < w1; b0 += 32) {
+      // ---- phase 1: one query per lane: positions + Hermite bases into the warp's scratch ----------
+      const int nvalid = (int)min(32u, w1 - b0);
+      const bool have = lane < nvalid;
+      unsigned idx = 0;
+      __syncwarp();  // the previous batch is done with hbs / misc
+      if (have) {
+        const double2 *src = (const double2 *)(rec + it.start + b0 + lane);
+        const double2 ra = __ldg(src), rb = __ldg(src + 1);
+        const double x[3] = {ra.x, ra.y, rb.x};
+        idx = (unsigned)__double2loint(rb.y);
+        AxisPos pa[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+          const Hermite hb = hermite_basis(pa[d].t);
+          double2 *dst = (double2 *)(hbs + (lane * 3 + d) * 4);
+          dst[0] = make_double2(hb.h00, hb.h01);
+          dst[1] = make_double2(hb.h10, hb.h11);
+        }
+        int4 m;
+        m.x = (pa[0].base - org[0]) + (pa[1].base - org[1]) * PITCH + (pa[2].base - org[2]) * PLANE;
+        m.y = pa[0].row * W;
+        m.z = pa[1].row * W;
+        m.w = pa[2].row * W;
+        ((int4 *)misc)[lane] = m;
+      }
+      __syncwarp();
+      // ---- phase 2: 8 queries per group: weights, then the contractions, then one reduce-scatter -----
+      double res = 0.0;
+      for (int j0 = 0; j0 < nvalid; j0 += 8) {
+        if (wrole) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j = min(j0 + jj, nvalid - 1);  // past the end: recompute the last query, result unused
+            const int rw = misc[j * 4 + 1 + wa];
+            const double2 *hp = (const double2 *)(hbs + (j * 3 + wa) * 4);
+            const double2 h0 = hp[0], h1 = hp[1];
+            const double *kp = brick + tko + rw, *dp = brick + tdo + rw;
+            wq[jj * 32 + lane] = h0.x * kp[0] + h0.y * kp[W] + (h1.x * dp[0] + h1.y * dp[W]);
+          }
+        }
+        __syncwarp();
+        double part[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = j0 + jj;
+          part[jj] = 0.0;
+          if (j < nvalid) {  // warp-uniform
+            const int mx = misc[j * 4];
+            if (mx != cur) {  // warp-uniform: first query of a run - fetch the cell's stencil into registers
+              cur = mx;
+              const double *base = brick + mx + lane_off;
+#pragma unroll
+              for (int n = 0; n < W; ++n)
+#pragma unroll
+                for (int k = 0; k < KM; ++k) {
+                  if ((G - 1) + k * G < W) creg[k][n] = base[k * G * PITCH + n * PLANE];
+                  else creg[k][n] = kval[k] ? base[k * G * PITCH + n * PLANE] : 0.0;
+                }
+            }
+            const double *wj = wq + jj * 32;
+            double wy[KM];
+#pragma unroll
+            for (int k = 0; k < KM; ++k) wy[k] = ((G - 1) + k * G < W || kval[k]) ? wj[W + gle + k * G] : 0.0;
+            double wz[W];
+#pragma unroll
+            for (int n = 0; n < W; n += 2) {
+              const double2 v = *(const double2 *)(wj + 2 * W + n);
+              wz[n] = v.x;
+              wz[n + 1] = v.y;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int n = 0; n < W; ++n) {
+              double an = 0.0;
+#pragma unroll
+              for (int k = 0; k < KM; ++k) an = fma(creg[k][n], wy[k], an);
+              acc = fma(an, wz[n], acc);
+            }
+            part[jj] = active ? acc * wj[l] : 0.0;
+          }
+        }
+        __syncwarp();  // wq is rewritten by the next group
+        // reduce-scatter butterfly (see eval_binned_kernel)
+        double q4[4], q2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool hi = lane & 1;
+          const double send = hi ? part[2 * i] : part[2 * i + 1];
+          const double keep = hi ? part[2 * i + 1] : part[2 * i];
+          q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bool hi = lane & 2;
+          const double send = hi ? q4[2 * i] : q4[2 * i + 1];
+          const double keep = hi ? q4[2 * i + 1] : q4[2 * i];
+          q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        double s1;
+        {
+          const bool hi = lane & 4;
+          const double send = hi ? q2[0] : q2[1];
+          const double keep = hi ? q2[1] : q2[0];
+          s1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        if ((lane >> 3) == (j0 >> 3)) res = s1;
+      }
+      if (have) out[idx] = apply_scale<3>(res, sc);
+    }
+  }
+}
+
 // spill bin: queries outside the domain (Flat / Line / Throw) or with NaN / Inf coordinates
 template <int E>
 __global__ void __launch_bounds__(256) eval_spill_kernel(ItpParams p, BinGeom g, Scale sc, const Record *__restrict__ rec,
@@ -503,7 +839,7 @@ long long binned_scratch_bytes(const cib200_itp *h, long long nq) {
   long long nt = 1;
   for (int d = 0; d < 3; ++d) nt *= (p.nk[d] - 2 * p.eqs[d] + 1 + T - 1) / T;
   const size_t nbin = (size_t)nt + 1, nblk = (size_t)sm_count();
-  size_t b = align_up(sizeof(Record) * (size_t)nq, 256);
+  size_t b = 2 * align_up(sizeof(Record) * (size_t)nq, 256);
   b += align_up(4 * nblk * nbin, 256) + align_up(4 * (nbin + 1), 256);
   b += align_up(sizeof(WorkItem) * ((size_t)nt + (size_t)nq / CHUNK_QUERIES + 1), 256) + 256;
   return (long long)b;
@@ -515,26 +851,41 @@ void binned_destroy(cib200_itp *h) {
 }
 
 template <int E>
-static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *out, long long qoff, cudaStream_t st) {
+static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *out, long long qoff, bool cellsort,
+                          cudaStream_t st) {
   const ItpParams &p = h->p;
   using WS = BinnedWarpSmem<E>;
-  int nwarps = 16;
+  int nwarps = cellsort ? 12 : 16;
+  const size_t per_warp = cellsort ? (size_t)CellrunWarpSmem<5>::DOUBLES : (size_t)WS::DOUBLES;
   auto smem_for = [&](int nw) {
-    return (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nw * WS::DOUBLES) + 32;
+    return (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nw * per_warp) + 32;
   };
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  while (nwarps > 4 && smem_for(nwarps) > (size_t)max_smem) nwarps /= 2;
+  while (nwarps > 4 && smem_for(nwarps) > (size_t)max_smem) nwarps -= 4;
   if (smem_for(nwarps) > (size_t)max_smem) {
     set_error("binned strategy: shared memory budget exceeded");
     return CIB200_EUNSUPPORTED;
   }
-  auto kern = eval_binned_kernel<E>;
-  CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
   const char *no_tma = getenv("CIB200_BINNED_NO_TMA");
-  kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec, bs->items, bs->n_items, out,
-                                                        (no_tma && no_tma[0] == '1') ? 0 : 1);
+  const int use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
+  if constexpr (E == 5) {
+   if (cellsort) {
+    bin_cellsort_kernel<<<bs->nblk, 1024, 0, st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2);
+    CIB_LAUNCHED();
+    auto kern = eval_cellrun_kernel<E>;
+    CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
+    kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec2, bs->items, bs->n_items, out,
+                                                          use_tma);
+   }
+  }
+  if (!(E == 5 && cellsort)) {
+    auto kern = eval_binned_kernel<E>;
+    CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
+    kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec, bs->items, bs->n_items, out,
+                                                          use_tma);
+  }
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   auto spill = eval_spill_kernel<E>;
@@ -598,6 +949,8 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     char *base = (char *)h->d_bin_scratch;
     bs->rec = (Record *)base;
     base += align_up(sizeof(Record) * (size_t)nq, 256);
+    bs->rec2 = (Record *)base;
+    base += align_up(sizeof(Record) * (size_t)nq, 256);
     bs->hist = (unsigned *)base;
     base += align_up(4 * (size_t)bs->nblk * g.nbin, 256);
     bs->tile_start = (unsigned *)base;
@@ -624,12 +977,19 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
+  // cell-sorted variant: pays one more streaming pass over the records (64 B/query) to keep each cell's stencil in
+  // registers across the queries that share it - worth it from about one query per cell upwards
+  double ncell = 1.0;
+  for (int d = 0; d < 3; ++d) ncell *= (double)(p.nk[d] - 2 * p.eqs[d] + 1);
+  // (b5 only: a lane's share of a wider stencil, KM x W coefficients, does not fit in registers)
+  bool cellsort = p.eqs[0] == 5 && (double)nq >= ncell && g.T * g.T * g.T <= CELLS_MAX;
+  if (const char *e = getenv("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   switch (p.eqs[0]) {
-    case 5: return launch_pass_cd<5>(h, bs, sc, (double *)out, c.qoff, st);
-    case 6: return launch_pass_cd<6>(h, bs, sc, (double *)out, c.qoff, st);
-    case 7: return launch_pass_cd<7>(h, bs, sc, (double *)out, c.qoff, st);
-    case 8: return launch_pass_cd<8>(h, bs, sc, (double *)out, c.qoff, st);
-    case 9: return launch_pass_cd<9>(h, bs, sc, (double *)out, c.qoff, st);
+    case 5: return launch_pass_cd<5>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 6: return launch_pass_cd<6>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 7: return launch_pass_cd<7>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 8: return launch_pass_cd<8>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 9: return launch_pass_cd<9>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
   }
   set_error("binned strategy: unsupported kernel");
   return CIB200_EUNSUPPORTED;
