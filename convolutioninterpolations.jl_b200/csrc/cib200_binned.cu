@@ -511,20 +511,33 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll
             for (int k = 0; k < KM; ++k) wy[k] = ((G - 1) + k * G < W || kval[k]) ? wq[W + gle + k * G] : 0.0;
             const double *base = brick + m.x + lane_off;
-            double acc = 0.0;
-#pragma unroll
-            for (int n = 0; n < W; ++n) {
-              double an = 0.0;
+            // sum_k wy[k] sum_n c[k][n] wz[n], even / odd n in separate chains - the association of
+            // eval_cellrun_kernel, so that both kernels return the same bits for the same query
+            auto coef = [&](int k, int n) {
+              if ((G - 1) + k * G < W) return base[k * G * PITCH + n * PLANE];  // compile-time: every lane group has this tap
+              return kval[k] ? base[k * G * PITCH + n * PLANE] : 0.0;          // last, partially populated tap
+            };
+            double be[KM], bo[KM];
+            {
+              const double z0 = wq[2 * W], z1 = wq[2 * W + 1];
 #pragma unroll
               for (int k = 0; k < KM; ++k) {
-                if ((G - 1) + k * G < W) {  // compile-time: every lane group has this tap
-                  an = fma(base[k * G * PITCH + n * PLANE], wy[k], an);
-                } else if (kval[k]) {       // last, partially populated tap: only the lanes that own it load
-                  an = fma(base[k * G * PITCH + n * PLANE], wy[k], an);
-                }
+                be[k] = coef(k, 0) * z0;
+                bo[k] = coef(k, 1) * z1;
               }
-              acc = fma(an, wq[2 * W + n], acc);
             }
+#pragma unroll
+            for (int n = 2; n < W; n += 2) {
+              const double z0 = wq[2 * W + n], z1 = wq[2 * W + n + 1];
+#pragma unroll
+              for (int k = 0; k < KM; ++k) {
+                be[k] = fma(coef(k, n), z0, be[k]);
+                bo[k] = fma(coef(k, n + 1), z1, bo[k]);
+              }
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < KM; ++k) acc = fma(be[k] + bo[k], wy[k], acc);
             part[jj] = active ? acc * wx : 0.0;
             buf ^= 1;
           }
@@ -655,15 +668,26 @@ __global__ void __launch_bounds__(384, 1)
     // contiguous range of this warp, in whole batches of 32 records
     const unsigned per = ((it.count + nwarps - 1) / nwarps + 31u) & ~31u;
     const unsigned w0 = warp * per, w1 = min(it.count, w0 + per);
+    // the record of the NEXT batch is fetched while the current one is being evaluated
+    double2 ra_n = make_double2(0.0, 0.0), rb_n = ra_n;
+    if (w0 + lane < w1) {
+      const double2 *src = (const double2 *)(rec + it.start + w0 + lane);
+      ra_n = __ldg(src);
+      rb_n = __ldg(src + 1);
+    }
     for (unsigned b0 = w0; b0 < w1; b0 += 32) {
       // ---- phase 1: one query per lane: positions + Hermite bases into the warp's scratch ----------
       const int nvalid = (int)min(32u, w1 - b0);
       const bool have = lane < nvalid;
       unsigned idx = 0;
+      const double2 ra = ra_n, rb = rb_n;
+      if (b0 + 32 + lane < w1) {
+        const double2 *src = (const double2 *)(rec + it.start + b0 + 32 + lane);
+        ra_n = __ldg(src);
+        rb_n = __ldg(src + 1);
+      }
       __syncwarp();  // the previous batch is done with hbs / misc
       if (have) {
-        const double2 *src = (const double2 *)(rec + it.start + b0 + lane);
-        const double2 ra = __ldg(src), rb = __ldg(src + 1);
         const double x[3] = {ra.x, ra.y, rb.x};
         idx = (unsigned)__double2loint(rb.y);
         AxisPos pa[3];
@@ -687,14 +711,28 @@ __global__ void __launch_bounds__(384, 1)
       double res = 0.0;
       for (int j0 = 0; j0 < nvalid; j0 += 8) {
         if (wrole) {
+          // two rounds of 4 queries: all shared-memory loads of a round are issued before its first store (the
+          // compiler cannot prove that the wq stores do not alias the scratch it reads, and would serialise them)
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int j = min(j0 + jj, nvalid - 1);  // past the end: recompute the last query, result unused
-            const int rw = misc[j * 4 + 1 + wa];
-            const double2 *hp = (const double2 *)(hbs + (j * 3 + wa) * 4);
-            const double2 h0 = hp[0], h1 = hp[1];
-            const double *kp = brick + tko + rw, *dp = brick + tdo + rw;
-            wq[jj * 32 + lane] = h0.x * kp[0] + h0.y * kp[W] + (h1.x * dp[0] + h1.y * dp[W]);
+          for (int r4 = 0; r4 < 8; r4 += 4) {
+            double2 h0[4], h1[4];
+            double ka[4], kb[4], da[4], db[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = min(j0 + r4 + u, nvalid - 1);  // past the end: recompute the last query, result unused
+              const int rw = misc[j * 4 + 1 + wa];
+              const double2 *hp = (const double2 *)(hbs + (j * 3 + wa) * 4);
+              h0[u] = hp[0];
+              h1[u] = hp[1];
+              const double *kp = brick + tko + rw, *dp = brick + tdo + rw;
+              ka[u] = kp[0];
+              kb[u] = kp[W];
+              da[u] = dp[0];
+              db[u] = dp[W];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              wq[(r4 + u) * 32 + lane] = h0[u].x * ka[u] + h0[u].y * kb[u] + (h1[u].x * da[u] + h1[u].y * db[u]);
           }
         }
         __syncwarp();
@@ -727,14 +765,23 @@ __global__ void __launch_bounds__(384, 1)
               wz[n] = v.x;
               wz[n + 1] = v.y;
             }
+            // sum_k wy[k] sum_n c[k][n] wz[n]: 2 KM independent chains (even / odd n) of W/2 DFMAs, then KM more
+            double be[KM], bo[KM];
+#pragma unroll
+            for (int k = 0; k < KM; ++k) {
+              be[k] = creg[k][0] * wz[0];
+              bo[k] = creg[k][1] * wz[1];
+            }
+#pragma unroll
+            for (int n = 2; n < W; n += 2)
+#pragma unroll
+              for (int k = 0; k < KM; ++k) {
+                be[k] = fma(creg[k][n], wz[n], be[k]);
+                bo[k] = fma(creg[k][n + 1], wz[n + 1], bo[k]);
+              }
             double acc = 0.0;
 #pragma unroll
-            for (int n = 0; n < W; ++n) {
-              double an = 0.0;
-#pragma unroll
-              for (int k = 0; k < KM; ++k) an = fma(creg[k][n], wy[k], an);
-              acc = fma(an, wz[n], acc);
-            }
+            for (int k = 0; k < KM; ++k) acc = fma(be[k] + bo[k], wy[k], acc);
             part[jj] = active ? acc * wj[l] : 0.0;
           }
         }
@@ -978,11 +1025,11 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   // cell-sorted variant: pays one more streaming pass over the records (64 B/query) to keep each cell's stencil in
-  // registers across the queries that share it - worth it from about one query per cell upwards
+  // registers across the queries that share it - worth it from about one query per two cells upwards (measured)
   double ncell = 1.0;
   for (int d = 0; d < 3; ++d) ncell *= (double)(p.nk[d] - 2 * p.eqs[d] + 1);
   // (b5 only: a lane's share of a wider stencil, KM x W coefficients, does not fit in registers)
-  bool cellsort = p.eqs[0] == 5 && (double)nq >= ncell && g.T * g.T * g.T <= CELLS_MAX;
+  bool cellsort = p.eqs[0] == 5 && (double)nq >= 0.5 * ncell && g.T * g.T * g.T <= CELLS_MAX;
   if (const char *e = getenv("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   switch (p.eqs[0]) {
     case 5: return launch_pass_cd<5>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
