@@ -36,7 +36,7 @@ namespace cib {
 static constexpr int BRICK_SIDE = 25;        // T + 2E - 1
 static constexpr int BRICK_PITCH = 26;       // inner TMA box extent: 26 * 8 B is a multiple of 16 B
 static constexpr int BRICK_DOUBLES = BRICK_PITCH * BRICK_SIDE * BRICK_SIDE;
-static constexpr int CHUNK_QUERIES = 4096;   // queries per work item
+static constexpr int CHUNK_QUERIES = 16384;  // queries per work item
 static constexpr int BIN_U = 4;              // queries per thread and iteration in the binning passes
 static constexpr int MAX_BINS = 49152;       // u32 histogram must fit one CTA's shared memory (192 KB)
 
@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(384, 1)
   double *wq = wsm + WS::HB + WS::MISC;     // [8][32]
   unsigned long long *bar = (unsigned long long *)(brick + wbase + nwarps * WS::DOUBLES);
   unsigned *slot = (unsigned *)(bar + 1);  // [2]
+  double *kt = (double *)(bar + 2);         // [3][32]: the stored knots the tile's queries can select
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -647,6 +648,11 @@ __global__ void __launch_bounds__(384, 1)
     const WorkItem it = items[item];
     const int tx = it.bin % g.nt[0], ty = (it.bin / g.nt[0]) % g.nt[1], tz = it.bin / (g.nt[0] * g.nt[1]);
     const int org[3] = {tx * g.T, ty * g.T, tz * g.T};
+    if (threadIdx.x < 96) {
+      const int d = threadIdx.x >> 5, r = threadIdx.x & 31;
+      const int o = d == 0 ? org[0] : (d == 1 ? org[1] : org[2]);
+      kt[threadIdx.x] = __ldg(p.knots[d] + min(o + r, p.nk[d] - 1));
+    }
     if (use_tma) {
       if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -655,6 +661,7 @@ __global__ void __launch_bounds__(384, 1)
       }
       mbar_wait(bar, parity);
       parity ^= 1;
+      __syncthreads();  // kt
     } else {
       const double *__restrict__ cg = (const double *)p.coefs;
       for (int e = threadIdx.x; e < BRICK_DOUBLES; e += blockDim.x) {
@@ -693,7 +700,7 @@ __global__ void __launch_bounds__(384, 1)
         AxisPos pa[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+          locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], kt + 32 * d - org[d], pa[d]);
           const Hermite hb = hermite_basis(pa[d].t);
           double2 *dst = (double2 *)(hbs + (lane * 3 + d) * 4);
           dst[0] = make_double2(hb.h00, hb.h01);
@@ -905,7 +912,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
   int nwarps = cellsort ? 12 : 16;
   const size_t per_warp = cellsort ? (size_t)CellrunWarpSmem<5>::DOUBLES : (size_t)WS::DOUBLES;
   auto smem_for = [&](int nw) {
-    return (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nw * per_warp) + 32;
+    return (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nw * per_warp) + 32 + 8 * 96;
   };
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
