@@ -23,7 +23,7 @@ SYMBOLS = [
     "cib200_build_coefs", "cib200_extend_knots", "cib200_itp_create", "cib200_itp_destroy",
     "cib200_itp_set_eval_mode", "cib200_itp_eval", "cib200_itp_eval_grid", "cib200_itp_scratch_bytes",
     "cib200_resample", "cib200_smooth", "cib200_smooth_halfwidth", "cib200_host_register",
-    "cib200_host_unregister",
+    "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
 ]
 
 
@@ -77,6 +77,8 @@ def lib():
     L.cib200_itp_set_eval_mode.argtypes = [vp, i32]
     L.cib200_itp_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
     L.cib200_itp_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itp_set_profiling.argtypes = [vp, i32]
+    L.cib200_itp_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.cib200_itp_scratch_bytes.restype = i64
     L.cib200_itp_scratch_bytes.argtypes = [vp, i64]
     L.cib200_resample.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, i32, vp]

@@ -263,6 +263,16 @@ class FastConvolutionInterpolation:
         check(lib().cib200_itp_set_eval_mode(self._handle, _lib.EVAL_MODES[mode]))
         self.eval_mode = mode
 
+    def set_profiling(self, enable=True):
+        """Measurement hook: bracket the passes of every evaluation with CUDA events (cib200_itp_set_profiling)."""
+        check(lib().cib200_itp_set_profiling(self._handle, 1 if enable else 0))
+
+    def last_pass_ms(self):
+        """Device time of the most recent profiled evaluation: {binning, cell sort, evaluation kernel, spill} in ms."""
+        ms = (C.c_float * 4)()
+        check(lib().cib200_itp_last_pass_ms(self._handle, ms))
+        return dict(zip(("binning", "cellsort", "eval_kernel", "spill"), (float(v) for v in ms)))
+
     def close(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h:

@@ -280,6 +280,15 @@ static int ensure_stage(cib200_itp *h, size_t bytes) {
   return CIB200_OK;
 }
 
+int prof_mark(cib200_itp *h, int i, cudaStream_t st) {
+  if (!h->profiling) return CIB200_OK;
+  if (!h->prof_ev[0])
+    for (int k = 0; k < 5; ++k) CIB_CUDA(cudaEventCreate(&h->prof_ev[k]));
+  CIB_CUDA(cudaEventRecord(h->prof_ev[i], st));
+  if (i == 4) h->prof_valid = 1;
+  return CIB200_OK;
+}
+
 static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st) {
   int mode = h->eval_mode;
   if (mode == CIB200_EVAL_AUTO) {
@@ -295,7 +304,11 @@ static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq
     }
     return launch_eval_binned(h, c, out, nq, st);
   }
-  return launch_eval(h, c, out, nq, st);
+  for (int i = 0; i < 3; ++i) prof_mark(h, i, st);
+  const int rc = launch_eval(h, c, out, nq, st);
+  prof_mark(h, 3, st);
+  prof_mark(h, 4, st);
+  return rc;
 }
 
 }  // namespace cib
@@ -506,6 +519,8 @@ int32_t cib200_itp_destroy(cib200_itp *h) {
   for (int i = 0; i < 3; ++i)
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
   if (h->d_bin_scratch) cudaFree(h->d_bin_scratch);
+  for (int k = 0; k < 5; ++k)
+    if (h->prof_ev[k]) cudaEventDestroy(h->prof_ev[k]);
   delete h;
   return CIB200_OK;
 }
@@ -520,6 +535,26 @@ int32_t cib200_itp_set_eval_mode(cib200_itp *h, int32_t mode) {
     return CIB200_EUNSUPPORTED;
   }
   h->eval_mode = mode;
+  return CIB200_OK;
+}
+
+int32_t cib200_itp_set_profiling(cib200_itp *h, int32_t enable) {
+  if (!h) {
+    set_error("cib200_itp_set_profiling: null handle");
+    return CIB200_EINVAL;
+  }
+  h->profiling = enable ? 1 : 0;
+  h->prof_valid = 0;
+  return CIB200_OK;
+}
+
+int32_t cib200_itp_last_pass_ms(cib200_itp *h, float *ms) {
+  if (!h || !ms || !h->prof_valid) {
+    set_error("cib200_itp_last_pass_ms: no profiled evaluation (enable cib200_itp_set_profiling first)");
+    return CIB200_EINVAL;
+  }
+  CIB_CUDA(cudaEventSynchronize(h->prof_ev[4]));
+  for (int i = 0; i < 4; ++i) CIB_CUDA(cudaEventElapsedTime(&ms[i], h->prof_ev[i], h->prof_ev[i + 1]));
   return CIB200_OK;
 }
 
@@ -575,7 +610,9 @@ static int32_t eval_common(cib200_itp *h, const Coords &c_in, long long nq, void
     if (code) set_error("%s: query %lld %s", who, first_bad ? (long long)*first_bad : -1LL, code == CIB200_EOOB ? "is outside the interpolation domain (extrap=Throw)" : "has a NaN/Inf coordinate");
     return code;
   }
-  const long long chunk = std::min<long long>(nq, 1LL << 24);
+  int chunk_log2 = 24;
+  if (const char *e = getenv("CIB200_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(30, atoi(e)));
+  const long long chunk = std::min<long long>(nq, 1LL << chunk_log2);
   // per buffer: nd coordinate chunks + 1 result chunk
   if ((rc = ensure_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
   s_in = h->streams[0];

@@ -928,6 +928,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
    if (cellsort) {
     bin_cellsort_kernel<<<bs->nblk, 1024, 0, st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2);
     CIB_LAUNCHED();
+    prof_mark(h, 2, st);
     auto kern = eval_cellrun_kernel<E>;
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec2, bs->items, bs->n_items, out,
@@ -935,6 +936,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
    }
   }
   if (!(E == 5 && cellsort)) {
+    prof_mark(h, 2, st);
     auto kern = eval_binned_kernel<E>;
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec, bs->items, bs->n_items, out,
@@ -942,12 +944,14 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
   }
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
+  prof_mark(h, 3, st);
   auto spill = eval_spill_kernel<E>;
   const size_t tsm = 8 * (size_t)tables_smem_doubles(p);
   if (tsm > 48 * 1024) CIB_CUDA(cudaFuncSetAttribute(spill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
   spill<<<bs->nblk, 256, tsm, st>>>(p, bs->g, sc, bs->rec, bs->tile_start, out, h->d_status, qoff);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
+  prof_mark(h, 4, st);
   return CIB200_OK;
 }
 
@@ -1020,6 +1024,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   const size_t hsm = 4 * (size_t)g.nbin;
   CIB_CUDA(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   CIB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+  prof_mark(h, 0, st);
   bin_count_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist);
   CIB_LAUNCHED();
   bin_totals_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
@@ -1031,6 +1036,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
+  prof_mark(h, 1, st);
   // cell-sorted variant: pays one more streaming pass over the records (64 B/query) to keep each cell's stencil in
   // registers across the queries that share it - worth it from about one query per two cells upwards (measured)
   double ncell = 1.0;

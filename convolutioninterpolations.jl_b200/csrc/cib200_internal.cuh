@@ -96,11 +96,16 @@ struct cib200_itp {
   void *d_bin_scratch;
   size_t bin_scratch_bytes;
   void *bin_state;  // opaque, owned by cib200_binned.cu
+  // optional pass timing (cib200_itp_set_profiling): events on the launching stream around the passes of a call
+  int profiling;
+  cudaEvent_t prof_ev[5];  // before binning | after scatter | after cell sort | after evaluation | after spill
+  int prof_valid;
 };
 
 namespace cib {
 double jl_pow_int(double x, long long n);  // Julia Base pow_body restated (cib200_eval.cu)
 int sm_count();
+int prof_mark(cib200_itp *h, int i, cudaStream_t st);  // records prof_ev[i] when profiling is enabled
 void *tma_encode_tiled_fn();  // cuTensorMapEncodeTiled through the runtime's driver entry point, or nullptr
 // K1 launchers (cib200_eval.cu)
 int launch_eval(const cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st);

@@ -114,6 +114,13 @@ int32_t cib200_itp_eval(cib200_itp *handle, int64_t nq, const void *const *x, vo
 int32_t cib200_itp_eval_grid(cib200_itp *handle, const int64_t *n, const void *const *x, void *out,
                              int32_t memkind, void *stream, int64_t *first_bad);
 
+/* Measurement hook (bench.py's roofline): with profiling enabled the library brackets the passes of every evaluation
+ * with CUDA events on the launching stream; cib200_itp_last_pass_ms then returns, for the most recent call, the
+ * device time in ms of {binning passes, cell sort, evaluation kernel, spill kernel} (gather strategy: {0, 0, kernel, 0}).
+ * No counterpart in the reference. */
+int32_t cib200_itp_set_profiling(cib200_itp *handle, int32_t enable);
+int32_t cib200_itp_last_pass_ms(cib200_itp *handle, float *ms4);
+
 /* bytes of device scratch the BINNED strategy needs for nq queries (0 for the other modes) */
 int64_t cib200_itp_scratch_bytes(cib200_itp *handle, int64_t nq);
 
