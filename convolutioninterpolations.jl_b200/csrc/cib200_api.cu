@@ -462,6 +462,7 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
     CIB_CREATE_CUDA(cudaMalloc(&h->d_knots[d], sizeof(double) * (size_t)h->cshape[d]));
     CIB_CREATE_CUDA(cudaMemcpy(h->d_knots[d], desc->knots[d], sizeof(double) * (size_t)h->cshape[d], cudaMemcpyHostToDevice));
     p.knots[d] = h->d_knots[d];
+    p.knot0[d] = desc->knots[d][0];
     p.lo[d] = desc->knots[d][eqs[d] - 1];
     p.hi[d] = desc->knots[d][h->cshape[d] - 1 - (eqs[d] - 1)];
   }

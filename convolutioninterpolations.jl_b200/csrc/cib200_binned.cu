@@ -57,6 +57,15 @@ struct WorkItem {
   unsigned bin, start, count;
 };
 
+// A record is one 32-byte sector: moved with ONE 256-bit access (sm_100: LDG/STG.E.ENL2.256).  Two 16-byte stores
+// to a scattered sector reach L2 as two partial-sector writes, which is what limited the scatter pass.
+__device__ __forceinline__ void st_record(Record *dst, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_record(const Record *src, double2 &a, double2 &b) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(src));
+}
+
 struct BinState {
   BinGeom g;
   CUtensorMap tmap;
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(1024, 1) bin_count_kernel(ItpParams p, BinGeom
   extern __shared__ unsigned sh[];
   for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  const double k0[3] = {__ldg(p.knots[0]), __ldg(p.knots[1]), __ldg(p.knots[2])};
+  const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   long long per = (nq + gridDim.x - 1) / gridDim.x;
   per = (per + 31) & ~31LL;
   const long long q0 = (long long)blockIdx.x * per;
@@ -205,12 +214,12 @@ __global__ void bin_offsets_kernel(BinGeom g, int nblk, unsigned *__restrict__ h
 }
 
 __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGeom g, Coords c, long long nq,
-                                                              const unsigned *__restrict__ hist, Record *__restrict__ rec) {
+                                                              const unsigned *__restrict__ hist, Record *__restrict__ rec, int dbg) {
   extern __shared__ unsigned sh[];
   const unsigned *src = hist + (size_t)blockIdx.x * g.nbin;
   for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = src[i];
   __syncthreads();
-  const double k0[3] = {__ldg(p.knots[0]), __ldg(p.knots[1]), __ldg(p.knots[2])};
+  const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   long long per = (nq + gridDim.x - 1) / gridDim.x;
   per = (per + 31) & ~31LL;
   const long long q0 = (long long)blockIdx.x * per;
@@ -228,13 +237,11 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
       const long long q = qb + (long long)u * blockDim.x;
       if (q < q1) {
         unsigned lc;
-        const unsigned slot = atomicAdd(&sh[classify(p, g, x[u], k0, lc)], 1u);
+        const int bin_ = classify(p, g, x[u], k0, lc);
+        const unsigned slot = dbg == 2 ? (unsigned)q : atomicAdd(&sh[bin_], 1u);
+        if (dbg == 1 && slot != 0xffffffffu) continue;
         // one 32-byte sector per query, written with two 16-byte stores; the spare word carries the cell inside the tile
-        double2 a = make_double2(x[u][0], x[u][1]);
-        double2 b = make_double2(x[u][2], __hiloint2double((int)lc, (int)(unsigned)q));
-        double2 *dst = (double2 *)(rec + slot);
-        dst[0] = a;
-        dst[1] = b;
+        st_record(rec + slot, x[u][0], x[u][1], x[u][2], __hiloint2double((int)lc, (int)(unsigned)q));
       }
     }
   }
@@ -313,20 +320,14 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
-        if (r < r1) {
-          const double2 *src = (const double2 *)(rec + r);
-          a[u] = __ldg(src);
-          b[u] = __ldg(src + 1);
-        }
+        if (r < r1) ld_record(rec + r, a[u], b[u]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
         if (r < r1) {
           const unsigned slot = atomicAdd(&hist[__double2hiint(b[u].y)], 1u);
-          double2 *dst = (double2 *)(rec2 + slot);
-          dst[0] = a[u];
-          dst[1] = b[u];
+          st_record(rec2 + slot, a[u].x, a[u].y, b[u].x, b[u].y);
         }
       }
     }
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(512, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const double k0[3] = {__ldg(p.knots[0]), __ldg(p.knots[1]), __ldg(p.knots[2])};
+  const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   const int l = lane % W, gl = lane / W;
   const bool active = lane < ACTIVE;
   // axis-1 taps of this lane; a tap beyond the stencil (only the last k, only when W % G != 0) is predicated off
@@ -459,8 +460,8 @@ __global__ void __launch_bounds__(512, 1)
       unsigned idx = 0;
       __syncwarp();  // the previous batch is done with hbs / misc
       if (have) {
-        const double2 *src = (const double2 *)(rec + it.start + qi);
-        const double2 ra = __ldg(src), rb = __ldg(src + 1);
+        double2 ra, rb;
+        ld_record(rec + it.start + qi, ra, rb);
         const double x[3] = {ra.x, ra.y, rb.x};
         idx = (unsigned)__double2loint(rb.y);
         AxisPos pa[3];
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(384, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const double k0[3] = {__ldg(p.knots[0]), __ldg(p.knots[1]), __ldg(p.knots[2])};
+  const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   const int l = lane % W, gl = lane / W;
   const bool active = lane < ACTIVE;
   const int lane_off = active ? l + gl * PITCH : (W - 1) + (G - 1) * PITCH;
@@ -677,22 +678,14 @@ __global__ void __launch_bounds__(384, 1)
     const unsigned w0 = warp * per, w1 = min(it.count, w0 + per);
     // the record of the NEXT batch is fetched while the current one is being evaluated
     double2 ra_n = make_double2(0.0, 0.0), rb_n = ra_n;
-    if (w0 + lane < w1) {
-      const double2 *src = (const double2 *)(rec + it.start + w0 + lane);
-      ra_n = __ldg(src);
-      rb_n = __ldg(src + 1);
-    }
+    if (w0 + lane < w1) ld_record(rec + it.start + w0 + lane, ra_n, rb_n);
     for (unsigned b0 = w0; b0 < w1; b0 += 32) {
       // ---- phase 1: one query per lane: positions + Hermite bases into the warp's scratch ----------
       const int nvalid = (int)min(32u, w1 - b0);
       const bool have = lane < nvalid;
       unsigned idx = 0;
       const double2 ra = ra_n, rb = rb_n;
-      if (b0 + 32 + lane < w1) {
-        const double2 *src = (const double2 *)(rec + it.start + b0 + 32 + lane);
-        ra_n = __ldg(src);
-        rb_n = __ldg(src + 1);
-      }
+      if (b0 + 32 + lane < w1) ld_record(rec + it.start + b0 + 32 + lane, ra_n, rb_n);
       __syncwarp();  // the previous batch is done with hbs / misc
       if (have) {
         const double x[3] = {ra.x, ra.y, rb.x};
@@ -1033,10 +1026,14 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   CIB_LAUNCHED();
   bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
-  bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec);
+  bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, getenv("CIB200_DBG_SCATTER") ? atoi(getenv("CIB200_DBG_SCATTER")) : 0);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 1, st);
+  if (getenv("CIB200_DBG_SCATTER") && atoi(getenv("CIB200_DBG_SCATTER")) != 0) {  // timing experiments only: no evaluation
+    for (int i = 2; i < 5; ++i) prof_mark(h, i, st);
+    return CIB200_OK;
+  }
   // cell-sorted variant: pays one more streaming pass over the records (64 B/query) to keep each cell's stencil in
   // registers across the queries that share it - worth it from about one query per two cells upwards (measured)
   double ncell = 1.0;

@@ -29,7 +29,7 @@ __device__ __forceinline__ Plan make_plan(const ItpParams &p, const double *x, A
   if (inside) {
 #pragma unroll
     for (int d = 0; d < NDIM; ++d)
-      ok &= locate_from_knot(x[d], __ldg(p.knots[d]), p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+      ok &= locate_from_knot(x[d], p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
     pl.ntask = 1;
   } else if (p.extrap == CIB200_THROW) {
     pl.err = 1;
@@ -47,14 +47,14 @@ __device__ __forceinline__ Plan make_plan(const ItpParams &p, const double *x, A
     }
 #pragma unroll
     for (int d = 0; d < NDIM; ++d)
-      ok &= locate_from_knot(cl[d], __ldg(p.knots[d]), p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+      ok &= locate_from_knot(cl[d], p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
     pl.ntask = 1;
     if (p.extrap == CIB200_LINE && !(dist_sq < 2.220446049250313e-16)) {
       double dist = __dsqrt_rn(dist_sq);
 #pragma unroll
       for (int d = 0; d < NDIM; ++d) {
         double xin = __dsub_rn(cl[d], __ddiv_rn(__dmul_rn(p.eps_line, dx[d]), dist));
-        ok &= locate_from_knot(xin, __ldg(p.knots[d]), p.h[d], p.eqs[d], p.nk[d], p.knots[d], pb[d]);
+        ok &= locate_from_knot(xin, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pb[d]);
       }
       pl.ntask = 2;
       pl.dist = dist;

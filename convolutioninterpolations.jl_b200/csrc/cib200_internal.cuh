@@ -51,6 +51,7 @@ struct ItpParams {
   const double *tab_slot_ptr[6];
   double h[3];
   double lo[3], hi[3];     // _domain_bounds, extrapolate_point.jl:172-176
+  double knot0[3];         // knots[d][0] (kernel-parameter constant: never re-loaded inside a loop)
   double scale;            // prod (-1/h_d)^DO_d, associated as the reference does
   double eps_line;         // min(h)/100, extrapolate_point.jl:138-139
   int extrap;
