@@ -12,7 +12,7 @@ SO_PATH = os.path.join(_HERE, "libcib200.so")
 OK, EOOB, ENAN, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(7)
 F64, F32 = 0, 1
 HOST, DEVICE = 0, 1
-KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4}
+KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4, "a3": 5, "a4": 6, "a5": 7, "a7": 8}
 BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
 EVAL_MODES = {"auto": 0, "gather": 1, "binned": 2}

@@ -167,7 +167,7 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what):
     for d, (k, dv, sg) in enumerate(zip(kernels, derivs, subgrids)):
         if k not in KERNEL_IDS:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: kernel :{k} (axis {d + 1}) is not on the "
-                                       f"accelerated path (b-series only: {ACCELERATED_KERNELS})")
+                                       f"accelerated path ({ACCELERATED_KERNELS})")
         if dv < 0:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivatives (derivative=-1) stay on the reference path")
         if sg != "cubic":

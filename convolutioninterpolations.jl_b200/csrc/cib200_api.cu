@@ -33,6 +33,10 @@ int kernel_eqs(int kernel) {
     case CIB200_B9: return 7;
     case CIB200_B11: return 8;
     case CIB200_B13: return 9;
+    case CIB200_A3: return 2;
+    case CIB200_A4: return 3;
+    case CIB200_A5: return 3;
+    case CIB200_A7: return 4;
     default: return -1;
   }
 }
@@ -43,6 +47,7 @@ int kernel_max_deriv_table(int kernel) {
     case CIB200_B9: return 5;
     case CIB200_B11: return 6;
     case CIB200_B13: return 6;
+    case CIB200_A3: case CIB200_A4: case CIB200_A5: case CIB200_A7: return 1;
     default: return -1;
   }
 }
@@ -53,6 +58,7 @@ int kernel_max_eval_deriv(int kernel) {
     case CIB200_B9: return 4;
     case CIB200_B11: return 5;
     case CIB200_B13: return 5;
+    case CIB200_A3: case CIB200_A4: case CIB200_A5: case CIB200_A7: return 0;
     default: return -1;
   }
 }
@@ -65,8 +71,16 @@ const double *host_table(int kernel, int d) {
                                       CIB_TAB_b11_d4, CIB_TAB_b11_d5, CIB_TAB_b11_d6};
   static const double *const b13[] = {CIB_TAB_b13_d0, CIB_TAB_b13_d1, CIB_TAB_b13_d2, CIB_TAB_b13_d3,
                                       CIB_TAB_b13_d4, CIB_TAB_b13_d5, CIB_TAB_b13_d6};
+  static const double *const a3[] = {CIB_TAB_a3_d0, CIB_TAB_a3_d1};
+  static const double *const a4[] = {CIB_TAB_a4_d0, CIB_TAB_a4_d1};
+  static const double *const a5[] = {CIB_TAB_a5_d0, CIB_TAB_a5_d1};
+  static const double *const a7[] = {CIB_TAB_a7_d0, CIB_TAB_a7_d1};
   if (d < 0 || d > kernel_max_deriv_table(kernel)) return nullptr;
   switch (kernel) {
+    case CIB200_A3: return a3[d];
+    case CIB200_A4: return a4[d];
+    case CIB200_A5: return a5[d];
+    case CIB200_A7: return a7[d];
     case CIB200_B5: return b5[d];
     case CIB200_B7: return b7[d];
     case CIB200_B9: return b9[d];
@@ -95,7 +109,9 @@ static void extrap_row(int m, int j, double *row) {
   }
 }
 
-static inline int poly_nodes(int kernel) { return kernel == CIB200_B5 ? 6 : 8; }
+// minimum_polynomial_bc_points, convolution_interpolation_function.jl:183-195 = columns of the kernel's ghost matrix
+int kernel_poly_nodes(int kernel) { return kernel >= CIB200_A3 ? 4 : (kernel == CIB200_B5 ? 6 : 8); }
+static inline int poly_nodes(int kernel) { return kernel_poly_nodes(kernel); }
 
 // decides the matrix width for one side of one line; p = first (left) / last (right) `ns` centred values
 static int choose_nodes(const double *s, long long n, double h, int kernel, int bc, bool right) {

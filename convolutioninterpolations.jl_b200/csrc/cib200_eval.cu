@@ -234,6 +234,9 @@ static int launch_eval_t(const cib200_itp *h, const Coords &c, void *out, long l
     return launch_thread<T, 2, 0>(p, c, sc, out, nq, h->d_status, st);
   }
   switch (e) {
+    case 2: return launch_warp3d<T, 2>(p, c, sc, out, nq, h->d_status, st);
+    case 3: return launch_warp3d<T, 3>(p, c, sc, out, nq, h->d_status, st);
+    case 4: return launch_warp3d<T, 4>(p, c, sc, out, nq, h->d_status, st);
     case 5: return launch_warp3d<T, 5>(p, c, sc, out, nq, h->d_status, st);
     case 6: return launch_warp3d<T, 6>(p, c, sc, out, nq, h->d_status, st);
     case 7: return launch_warp3d<T, 7>(p, c, sc, out, nq, h->d_status, st);

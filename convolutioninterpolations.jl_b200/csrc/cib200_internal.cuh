@@ -30,6 +30,7 @@ extern std::atomic<long long> g_launches;
 
 // ---- kernel registry ------------------------------------------------------------------------
 int kernel_eqs(int kernel);              // degree_to_equations.jl:13-25
+int kernel_poly_nodes(int kernel);       // interior points of the polynomial ghost extrapolation (4 / 6 / 8)
 int kernel_max_deriv_table(int kernel);  // highest d for which K^(d) is tabulated
 int kernel_max_eval_deriv(int kernel);   // _max_shipped_derivative, get_precomputed_kernel_and_range.jl:33-40
 const double *host_table(int kernel, int d);

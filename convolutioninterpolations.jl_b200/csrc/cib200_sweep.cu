@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepParams sp, GhostMats gm
         ghost_gauss_side(bl, pad, pitch, n, mean, sp.eqs, side == 1);
       } else {
         constexpr int EQS = TAPS > 0 ? TAPS / 2 : 5;
-        constexpr int NS = EQS == 5 ? 6 : 8;
+        constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
         ghost_poly_side<NS, EQS>(bl, pad, pitch, n, mean, sp.h, side ? sp.bcr : sp.bcl, side == 1, gm);
       }
     }
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
           ghost_gauss_side(bl, pad, PITCH, n, mean, sp.eqs, side == 1);
         } else {
           constexpr int EQS = TAPS > 0 ? TAPS / 2 : 5;
-          constexpr int NS = EQS == 5 ? 6 : 8;
+          constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
           ghost_poly_side<NS, EQS>(bl, pad, PITCH, n, mean, sp.h, side ? sp.bcr : sp.bcl, side == 1, gm);
         }
       }
@@ -949,6 +949,9 @@ static int launch_taps(const SweepParams &sp, const GhostMats &gm, const T *in, 
                        cudaStream_t st) {
   if (SMOOTH) return launch_kernel<T, SMOOTH, AXIS0, 0>(sp, gm, in, out, blocks, smem, st);
   switch (sp.taps) {
+    case 4: return launch_kernel<T, false, AXIS0, 4>(sp, gm, in, out, blocks, smem, st);
+    case 6: return launch_kernel<T, false, AXIS0, 6>(sp, gm, in, out, blocks, smem, st);
+    case 8: return launch_kernel<T, false, AXIS0, 8>(sp, gm, in, out, blocks, smem, st);
     case 10: return launch_kernel<T, false, AXIS0, 10>(sp, gm, in, out, blocks, smem, st);
     case 12: return launch_kernel<T, false, AXIS0, 12>(sp, gm, in, out, blocks, smem, st);
     case 14: return launch_kernel<T, false, AXIS0, 14>(sp, gm, in, out, blocks, smem, st);
@@ -995,6 +998,9 @@ static int launch_pipe_taps(const SweepParams &sp, const GhostMats &gm, const Pi
                             long long ntiles, int threads, size_t smem, cudaStream_t st) {
   if (SMOOTH) return launch_pipe_kernel<T, true, AXIS0, 0>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
   switch (sp.taps) {
+    case 4: return launch_pipe_kernel<T, false, AXIS0, 4>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    case 6: return launch_pipe_kernel<T, false, AXIS0, 6>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    case 8: return launch_pipe_kernel<T, false, AXIS0, 8>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
     case 10: return launch_pipe_kernel<T, false, AXIS0, 10>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
     case 12: return launch_pipe_kernel<T, false, AXIS0, 12>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
     case 14: return launch_pipe_kernel<T, false, AXIS0, 14>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
@@ -1179,7 +1185,7 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     sp.base = d_base;
     GhostMats gm;
     memset(&gm, 0, sizeof gm);
-    gm.poly_nodes = kernel[d] == CIB200_B5 ? 6 : 8;
+    gm.poly_nodes = kernel_poly_nodes(kernel[d]);
     lagrange_rows(gm.poly_nodes, eqs - 1, &gm.poly[0][0], 8);
     lagrange_rows(2, eqs - 1, &gm.lin[0][0], 2);
     lagrange_rows(3, eqs - 1, &gm.quad[0][0], 3);

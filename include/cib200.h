@@ -43,7 +43,12 @@ typedef enum {
 
 typedef enum { CIB200_F64 = 0, CIB200_F32 = 1 } cib200_dtype;
 typedef enum { CIB200_HOST = 0, CIB200_DEVICE = 1 } cib200_memkind;
-typedef enum { CIB200_B5 = 0, CIB200_B7 = 1, CIB200_B9 = 2, CIB200_B11 = 3, CIB200_B13 = 4 } cib200_kernel;
+/* b-series: derivatives up to the shipped tables; a-series (Keys-type, a4 is the reference's default kernel):
+ * derivative 0 only (their K'' tables are not shipped: derivatives take the reference's :linear-subgrid path) */
+typedef enum {
+  CIB200_B5 = 0, CIB200_B7 = 1, CIB200_B9 = 2, CIB200_B11 = 3, CIB200_B13 = 4,
+  CIB200_A3 = 5, CIB200_A4 = 6, CIB200_A5 = 7, CIB200_A7 = 8
+} cib200_kernel;
 typedef enum { CIB200_BC_DETECT = 0, CIB200_BC_POLY = 1, CIB200_BC_LINEAR = 2, CIB200_BC_QUADRATIC = 3 } cib200_bc;
 typedef enum { CIB200_THROW = 0, CIB200_FLAT = 1, CIB200_LINE = 2 } cib200_extrap;
 

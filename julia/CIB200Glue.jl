@@ -11,9 +11,9 @@ using ..ConvolutionInterpolations: ConvolutionExtrapolation, FastConvolutionInte
     HigherOrderKernel, HigherOrderMixedKernel, Throw, Flat, Line, DerivativeOrder
 
 const LIB = get(ENV, "CIB200_LIB", "libcib200.so")
-const KERNEL_ID = Dict(:b5 => 0, :b7 => 1, :b9 => 2, :b11 => 3, :b13 => 4)
+const KERNEL_ID = Dict(:b5 => 0, :b7 => 1, :b9 => 2, :b11 => 3, :b13 => 4, :a3 => 5, :a4 => 6, :a5 => 7, :a7 => 8)
 const BC_ID = Dict(:detect => 0, :poly => 1, :linear => 2, :quadratic => 3)
-const MAX_DERIV = Dict(:b5 => 2, :b7 => 3, :b9 => 4, :b11 => 5, :b13 => 5)   # _max_shipped_derivative
+const MAX_DERIV = Dict(:b5 => 2, :b7 => 3, :b9 => 4, :b11 => 5, :b13 => 5, :a3 => 0, :a4 => 0, :a5 => 0, :a7 => 0)   # _max_shipped_derivative
 
 # mirror of cib200_itp_desc (include/cib200.h) -------------------------------------------------------
 struct ItpDesc

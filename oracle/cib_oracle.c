@@ -35,6 +35,10 @@ int orc_eqs(int kernel) {
     case ORC_K_B9: return 7;
     case ORC_K_B11: return 8;
     case ORC_K_B13: return 9;
+    case ORC_K_A3: return 2;
+    case ORC_K_A4: return 3;
+    case ORC_K_A5: return 3;
+    case ORC_K_A7: return 4;
     default: return -1;
   }
 }
@@ -46,6 +50,7 @@ int orc_max_table_derivative(int kernel) {
     case ORC_K_B9: return 5;
     case ORC_K_B11: return 6;
     case ORC_K_B13: return 6;
+    case ORC_K_A3: case ORC_K_A4: case ORC_K_A5: case ORC_K_A7: return 1;
     default: return -1;
   }
 }
@@ -61,8 +66,16 @@ const double *orc_table(int kernel, int d) {
                                       CIB_TAB_b11_d4, CIB_TAB_b11_d5, CIB_TAB_b11_d6};
   static const double *const b13[] = {CIB_TAB_b13_d0, CIB_TAB_b13_d1, CIB_TAB_b13_d2, CIB_TAB_b13_d3,
                                       CIB_TAB_b13_d4, CIB_TAB_b13_d5, CIB_TAB_b13_d6};
+  static const double *const a3[] = {CIB_TAB_a3_d0, CIB_TAB_a3_d1};
+  static const double *const a4[] = {CIB_TAB_a4_d0, CIB_TAB_a4_d1};
+  static const double *const a5[] = {CIB_TAB_a5_d0, CIB_TAB_a5_d1};
+  static const double *const a7[] = {CIB_TAB_a7_d0, CIB_TAB_a7_d1};
   if (d < 0 || d > orc_max_table_derivative(kernel)) return NULL;
   switch (kernel) {
+    case ORC_K_A3: return a3[d];
+    case ORC_K_A4: return a4[d];
+    case ORC_K_A5: return a5[d];
+    case ORC_K_A7: return a7[d];
     case ORC_K_B5: return b5[d];
     case ORC_K_B7: return b7[d];
     case ORC_K_B9: return b9[d];
@@ -110,7 +123,7 @@ static double jl_pow_int(double x, int64_t n) {
 /* ---------------------------------------------------------------------------------------------
  * Ghost matrices: convolution_coefs/polynomial_boundary.jl:29-131 (POLYNOMIAL_GHOST_COEFFS),
  * :157-179 (LINEAR/QUADRATIC).  Every row j is the Lagrange extrapolation to x = -j from the
- * nodes 0..m-1 (m = 2 linear, 3 quadratic, 6 for b5, 8 for b7..b13); regenerated here in exact
+ * nodes 0..m-1 (m = 2 linear, 3 quadratic, 4 for the a-series, 6 for b5, 8 for b7..b13); regenerated here in exact
  * integer arithmetic and compared with the reference's literals in tests/test_oracle_kat.py.
  * ------------------------------------------------------------------------------------------- */
 static void lagrange_row(int m, int j, double *row) {
@@ -125,7 +138,8 @@ static void lagrange_row(int m, int j, double *row) {
   }
 }
 
-static int poly_ncol(int kernel) { return kernel == ORC_K_B5 ? 6 : 8; }
+/* minimum_polynomial_bc_points, convolution_interpolation_function.jl:183-195 */
+static int poly_ncol(int kernel) { return (kernel >= ORC_K_A3 && kernel <= ORC_K_A7) ? 4 : (kernel == ORC_K_B5 ? 6 : 8); }
 
 /* exported for the KAT test: fills rows x ncol (row-major), returns ncol */
 int orc_ghost_matrix(int which /*0 poly,1 linear,2 quadratic*/, int kernel, int rows, double *out) {

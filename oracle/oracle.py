@@ -22,11 +22,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4}
-KERNEL_EQS = {"b5": 5, "b7": 6, "b9": 7, "b11": 8, "b13": 9}        # degree_to_equations.jl:13-25
-MAX_SMOOTH_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6}  # constructor.jl:400-412
-MAX_SHIPPED_DERIVATIVE = {"b5": 2, "b7": 3, "b9": 4, "b11": 5, "b13": 5}  # get_precomputed...jl:33-40
-MIN_POLY_BC_POINTS = {"b5": 6, "b7": 8, "b9": 8, "b11": 8, "b13": 8}  # convolution_interpolation_function.jl:183-195
+KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4, "a3": 5, "a4": 6, "a5": 7, "a7": 8}
+KERNEL_EQS = {"b5": 5, "b7": 6, "b9": 7, "b11": 8, "b13": 9, "a3": 2, "a4": 3, "a5": 3, "a7": 4}        # degree_to_equations.jl:13-25
+MAX_SMOOTH_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6, "a3": 1, "a4": 1, "a5": 1, "a7": 1}  # constructor.jl:400-412
+MAX_SHIPPED_DERIVATIVE = {"b5": 2, "b7": 3, "b9": 4, "b11": 5, "b13": 5, "a3": 0, "a4": 0, "a5": 0, "a7": 0}  # get_precomputed...jl:33-40
+MIN_POLY_BC_POINTS = {"b5": 6, "b7": 8, "b9": 8, "b11": 8, "b13": 8, "a3": 4, "a4": 4, "a5": 4, "a7": 4}  # convolution_interpolation_function.jl:183-195
 BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
 
@@ -81,7 +81,7 @@ def table(kernel, d):
 
 
 def ghost_matrix(which, kernel, rows):
-    m = {"poly": 6 if kernel == "b5" else 8, "linear": 2, "quadratic": 3}[which]
+    m = {"poly": MIN_POLY_BC_POINTS[kernel], "linear": 2, "quadratic": 3}[which]
     out = np.zeros((rows, m))
     lib().orc_ghost_matrix({"poly": 0, "linear": 1, "quadratic": 2}[which], KERNEL_IDS[kernel], rows,
                            out.ctypes.data)

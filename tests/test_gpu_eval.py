@@ -115,6 +115,31 @@ def test_mixed_kernels_per_axis_use_the_generic_path(ci, oracle):
     _compare(ci, oracle, k2, v2, tuple(q2), kernel=("b7", "b7"), derivative=(1, 1), extrap="line")
 
 
+@pytest.mark.parametrize("kernel", ["a3", "a4", "a5", "a7"])
+@pytest.mark.parametrize("bc", ["detect", "poly", "linear", "quadratic"])
+def test_a_series_kernels_1d_2d_3d(ci, oracle, kernel, bc):
+    """a-series kernels (a4 is the reference's default): derivative 0, cubic subgrid, 4-node polynomial ghosts."""
+    rng = np.random.default_rng(41)
+    x = np.linspace(-2, 3, 61)
+    v = np.cos(1.7 * x) + 0.03 * rng.standard_normal(61)
+    q = rng.uniform(-2.3, 3.3, 40_000)
+    _compare(ci, oracle, x, v, (q,), kernel=kernel, bc=bc, extrap="line")
+    v2 = _field((40, 35), rng, noise=0.02)
+    k2 = (np.linspace(0, 1, 40), np.linspace(0, 1, 35))
+    q2 = rng.uniform(-0.05, 1.05, (2, 30_000))
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=kernel, bc=bc, extrap="flat")
+    shape = (26, 24, 28)
+    k3 = tuple(np.linspace(0, 1, n) for n in shape)
+    v3 = _field(shape, rng, noise=0.02)
+    q3 = rng.uniform(0, 1, (3, 20_011))
+    _compare(ci, oracle, k3, v3, tuple(q3), kernel=kernel, bc=bc)
+    if bc == "detect":
+        # mixed a / b kernels per axis take the generic per-axis path; derivatives of a-kernels are not shipped
+        _compare(ci, oracle, k3, v3, tuple(q3), kernel=(kernel, "b5", "a4"), derivative=(0, 1, 0), extrap="line")
+        with pytest.raises(ci.UnsupportedModeError):
+            ci.convolution_interpolation(x, v, kernel=kernel, derivative=1)
+
+
 @pytest.mark.parametrize("kernel", ["b5", "b7", "b9", "b11", "b13"])
 def test_1d_2d_all_b_kernels(ci, oracle, kernel):
     rng = np.random.default_rng(13)

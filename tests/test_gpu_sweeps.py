@@ -66,7 +66,7 @@ def test_c3_resample_b13_128_to_256_with_derivative_pass(ci, oracle):
     _check_resample(ci, oracle, kin, kout, vn, kernel="b13", derivative=(1, 0, 0))
 
 
-@pytest.mark.parametrize("kernel", ["b5", "b7", "b9", "b11", "b13"])
+@pytest.mark.parametrize("kernel", ["b5", "b7", "b9", "b11", "b13", "a3", "a4", "a5", "a7"])
 @pytest.mark.parametrize("bc", ["detect", "poly", "linear", "quadratic"])
 def test_resample_1d_2d_kernels_and_bcs(ci, oracle, kernel, bc):
     rng = np.random.default_rng(21)
@@ -74,7 +74,12 @@ def test_resample_1d_2d_kernels_and_bcs(ci, oracle, kernel, bc):
     _check_resample(ci, oracle, xi, xo, np.sin(xi) + 0.01 * rng.standard_normal(50), kernel=kernel, bc=bc)
     k2i = (np.linspace(0, 1, 37), np.linspace(-1, 1, 29))
     k2o = (np.linspace(0, 1, 64), np.linspace(-1, 1, 45))
-    _check_resample(ci, oracle, k2i, k2o, rng.random((37, 29)), kernel=kernel, bc=bc, derivative=(0, 1))
+    _check_resample(ci, oracle, k2i, k2o, rng.random((37, 29)), kernel=kernel, bc=bc,
+                    derivative=(0, 1) if kernel.startswith("b") else 0)
+    if kernel.startswith("a") and bc == "detect":  # 3-D, through the pipelined passes
+        k3i = tuple(np.linspace(0, 1, n) for n in (40, 33, 36))
+        k3o = tuple(np.linspace(0, 1, n) for n in (64, 70, 41))
+        _check_resample(ci, oracle, k3i, k3o, rng.random((40, 33, 36)), kernel=kernel)
 
 
 def test_resample_shapes_downsampling_extrapolating_knots_and_4d(ci, oracle):

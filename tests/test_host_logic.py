@@ -23,11 +23,11 @@ def test_library_exports_every_declared_symbol(ci):
 
 def test_embedded_tables_are_the_shipped_ones(ci, golden_dir):
     g = np.load(os.path.join(golden_dir, "shipped_tables.npz"))
-    ids = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4}
+    ids = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4, "a3": 5, "a4": 6, "a5": 7, "a7": 8}
     L = ci.lib()
     n = 0
     for name in g.files:
-        m = re.match(r"KERNEL_(D1_|D2_|)PRE_(b\d+)_d(\d+)$", name)
+        m = re.match(r"KERNEL_(D1_|D2_|)PRE_([ab]\d+)_d(\d+)$", name)
         kernel, d = m.group(2), int(m.group(3)) + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
         eqs = C.c_int32()
         p = L.cib200_kernel_table(ids[kernel], d, C.byref(eqs))
@@ -35,7 +35,7 @@ def test_embedded_tables_are_the_shipped_ones(ci, golden_dir):
         lit = g[name]
         assert ((t.view(np.uint64) == lit.view(np.uint64)) | ((t == 0) & (lit == 0))).all(), name
         n += 1
-    assert n == 67
+    assert n == 75
     assert not L.cib200_kernel_table(0, 4, None)  # b5 has no 4th derivative table
 
 
@@ -43,7 +43,7 @@ def _build(ci, values, h, kernels, bcs, dtype=np.float64):
     from convitp_b200 import _lib
     v = np.asfortranarray(values, dtype=dtype)
     nd = v.ndim
-    eqs = [{"b5": 5, "b7": 6, "b9": 7, "b11": 8, "b13": 9}[k] for k in kernels]
+    eqs = [{"b5": 5, "b7": 6, "b9": 7, "b11": 8, "b13": 9, "a3": 2, "a4": 3, "a5": 3, "a7": 4}[k] for k in kernels]
     out = np.zeros(tuple(s + 2 * (e - 1) for s, e in zip(v.shape, eqs)), dtype=dtype, order="F")
     st = ci.lib().cib200_build_coefs(
         nd, 0 if dtype == np.float64 else 1, (C.c_int64 * nd)(*v.shape), v.ctypes.data, (C.c_double * nd)(*h),
@@ -56,7 +56,8 @@ def _build(ci, values, h, kernels, bcs, dtype=np.float64):
 
 @pytest.mark.parametrize("shape,kernels", [((40,), ("b5",)), ((7,), ("b13",)), ((17, 23), ("b5", "b5")),
                                           ((12, 9), ("b13", "b5")), ((14, 11, 13), ("b5", "b5", "b5")),
-                                          ((10, 12, 9), ("b13", "b7", "b9"))])
+                                          ((10, 12, 9), ("b13", "b7", "b9")),
+                                          ((9,), ("a3",)), ((15, 12), ("a4", "a7")), ((8, 9, 10), ("a5", "b5", "a4"))])
 @pytest.mark.parametrize("bc", ["detect", "poly", "linear", "quadratic", ("detect", "linear")])
 def test_host_coefficient_builder_bit_equals_oracle(ci, oracle, shape, kernels, bc):
     rng = np.random.default_rng(hash((shape, kernels, str(bc))) % 2 ** 32)
@@ -106,7 +107,9 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
     v = np.sin(x)
     U = ci.UnsupportedModeError
     with pytest.raises(U):
-        ci.convolution_interpolation(x, v, kernel="a3")
+        ci.convolution_interpolation(x, v, kernel="a1")           # a0 / a1: :linear subgrid only
+    with pytest.raises(U):
+        ci.convolution_interpolation(x, v, kernel="a4", derivative=1)  # K'' of the a-series is not shipped
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, derivative=-1)
     with pytest.raises(U):

@@ -1,6 +1,6 @@
 """Pins the oracle against the reference's own known answers (no GPU needed).
 
-  - the 67 shipped b-series Float64 tables (src/precomputed_kernels/kernel_b*.jl) - bit equality
+  - the 75 shipped Float64 tables of the b-series and of a3 / a4 / a5 / a7 (src/precomputed_kernels/kernel_*.jl) - bit equality
   - the integer ghost matrices (src/convolution_coefs/polynomial_boundary.jl:29-179) - exact
   - the exact-rational kernel polynomials regenerate the tables (independent Fraction path)
 """
@@ -21,7 +21,7 @@ def test_oracle_tables_bit_equal_shipped_literals(oracle, golden_dir):
     g = _golden_tables(golden_dir)
     n = 0
     for name in g.files:
-        m = re.match(r"KERNEL_(D1_|D2_|)PRE_(b\d+)_d(\d+)$", name)
+        m = re.match(r"KERNEL_(D1_|D2_|)PRE_([ab]\d+)_d(\d+)$", name)
         kernel, d = m.group(2), int(m.group(3)) + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
         t = oracle.table(kernel, d)
         lit = g[name]
@@ -29,7 +29,7 @@ def test_oracle_tables_bit_equal_shipped_literals(oracle, golden_dir):
         same = (t.view(np.uint64) == lit.view(np.uint64)) | ((t == 0) & (lit == 0))
         assert same.all(), name
         n += 1
-    assert n == 67
+    assert n == 75
 
 
 def test_d1_companion_is_next_derivative_table(golden_dir):
@@ -41,7 +41,9 @@ def test_d1_companion_is_next_derivative_table(golden_dir):
 
 
 @pytest.mark.parametrize("kernel,d,rows", [("b5", 0, range(0, 101, 7)), ("b5", 2, range(0, 101, 9)),
-                                           ("b13", 0, (0, 37, 100)), ("b13", 5, (1, 50, 99))])
+                                           ("b13", 0, (0, 37, 100)), ("b13", 5, (1, 50, 99)),
+                                           ("a3", 0, range(0, 101, 11)), ("a4", 0, range(0, 101, 13)),
+                                           ("a5", 0, (0, 33, 100)), ("a7", 0, (2, 51, 99))])
 def test_rational_polynomials_regenerate_tables(kernel, d, rows, golden_dir):
     root = os.path.dirname(os.path.dirname(golden_dir))
     polys = json.load(open(os.path.join(root, "oracle", "kernel_polys.json")))[kernel]
@@ -72,7 +74,7 @@ def test_rational_polynomials_regenerate_tables(kernel, d, rows, golden_dir):
 
 def test_ghost_matrices_match_reference_literals(oracle, golden_dir):
     g = json.load(open(os.path.join(golden_dir, "ghost_matrices.json")))
-    for kernel in ("b5", "b7", "b9", "b11", "b13"):
+    for kernel in ("b5", "b7", "b9", "b11", "b13", "a3", "a4", "a5", "a7"):
         lit = np.array(g[f"poly_{kernel}"])
         assert np.array_equal(oracle.ghost_matrix("poly", kernel, lit.shape[0]), lit)
     assert np.array_equal(oracle.ghost_matrix("linear", "b13", 9), np.array(g["linear"]))
@@ -84,7 +86,7 @@ def test_ghost_matrices_match_reference_literals(oracle, golden_dir):
 
 def test_table_properties(oracle):
     # partition of unity of the interpolating kernel: each table row of K sums to 1, of K' to 0
-    for k in ("b5", "b13"):
+    for k in ("b5", "b13", "a3", "a4", "a5", "a7"):
         t0, t1 = oracle.table(k, 0), oracle.table(k, 1)
         assert np.abs(t0.sum(axis=1) - 1).max() < 1e-14
         assert np.abs(t1.sum(axis=1)).max() < 1e-12

@@ -7,7 +7,7 @@ Run in the authoring container only (needs /root/reference, read-only):
 
 What it does
   1. reads the exact rational piecewise-polynomial coefficients of the b-series
-     kernels (reference: src/convolution_kernels/convolution_kernel_b*.jl, the
+     and a-series (a3, a4, a5, a7) kernels (reference: src/convolution_kernels/convolution_kernel_b*.jl, the
      `<k>_coefs = Dict(:eq1 => [...], ...)` literal; derivative dictionaries are
      NOT read, they are re-derived as k*(k-1)*... * c_k),
   2. regenerates every 101 x 2*eqs table with `fractions.Fraction` following the
@@ -40,7 +40,9 @@ REF = "/root/reference/src"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # kernel -> (eqs, highest analytic derivative that has a coefficient dict)
-KERNELS = {"b5": (5, 3), "b7": (6, 4), "b9": (7, 5), "b11": (8, 6), "b13": (9, 6)}
+KERNELS = {"b5": (5, 3), "b7": (6, 4), "b9": (7, 5), "b11": (8, 6), "b13": (9, 6),
+           # a-series (Keys-type cubic pieces): only K and K' are shipped / needed (derivative 0, cubic subgrid)
+           "a3": (2, 1), "a4": (3, 1), "a5": (3, 1), "a7": (4, 1)}
 N_PRE = 101
 
 
@@ -49,7 +51,8 @@ def _parse_rational_expr(expr):
     expr = expr.strip().replace("big(", "(")
     expr = re.sub(r"(?<![\w.])(-?\d+)", r"Fraction(\1)", expr)
     expr = expr.replace("//", "/")
-    return eval(expr, {"Fraction": Fraction})  # noqa: S307 - trusted local literal
+    # `a` is the free parameter of the :a5 kernel (convolution_kernel_a5.jl:8: const a = 3//64)
+    return eval(expr, {"Fraction": Fraction, "a": Fraction(3, 64)})  # noqa: S307 - trusted local literal
 
 
 def read_base_coefs(kernel):
