@@ -21,6 +21,7 @@
 //      normalised Gaussian held in shared memory.
 #include <cuda.h>
 #include <math.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <vector>
@@ -526,6 +527,7 @@ struct PipeCfg {
   int g;    // ghost teams
   int c;    // consumer groups
   int cwg;  // warps per consumer group
+  unsigned long long *stats;  // debug (CIB200_PIPE_STATS=1): cycles [loader wait, loader busy, ghost wait, ghost busy, consumer wait, consumer busy]
 };
 static constexpr int PIPE_MAX_NB = 8;
 
@@ -662,7 +664,7 @@ __device__ __forceinline__ void resample_lines2(const double *bl, const int pitc
 }
 
 template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
-__global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
+__global__ void __launch_bounds__(SMOOTH ? 768 : (AXIS0 ? 640 : 384), 1)
     sweep_pipe_kernel(const __grid_constant__ CUtensorMap tmap, SweepParams sp, GhostMats gm, PipeCfg cfg,
                       const T *__restrict__ in, T *__restrict__ out, long long ntiles) {
   extern __shared__ __align__(128) double sm[];
@@ -700,10 +702,12 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const long long tiles_inner = AXIS0 ? 1 : (sp.inner + 31) / 32;
+  // tile index -> (tile_i, o) with 32-bit arithmetic (a 64-bit division per tile and thread costs as many
+  // instructions as the tile's FIR); the host guarantees ntiles < 2^31
+  const unsigned tiles_inner = AXIS0 ? 1u : (unsigned)((sp.inner + 31) / 32);
   const long long tstep = gridDim.x;
   auto tile_valid = [&](long long t) {
-    const long long rem = AXIS0 ? sp.outer - t * 32 : sp.inner - (t % tiles_inner) * 32;
+    const long long rem = AXIS0 ? sp.outer - t * 32 : sp.inner - (long long)((unsigned)t % tiles_inner) * 32;
     return rem < 32 ? (int)rem : 32;
   };
 
@@ -713,10 +717,12 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
     for (long long t = blockIdx.x; t < ntiles; t += tstep, ++i) {
       const int b = i % NB, rev = i / NB;
       double *buf = sm + b * bufsz;
+      const long long tw0 = cfg.stats ? clock64() : 0;
       if (rev > 0) mbar_wait(empty + b, (unsigned)(rev - 1) & 1u);
+      if (cfg.stats && lane == 0 && warp == 0) atomicAdd(cfg.stats + 0, (unsigned long long)(clock64() - tw0));
       if (!AXIS0 && cfg.tma) {
         if (lane == 0) {
-          const long long tile_i = t % tiles_inner, o = t / tiles_inner;
+          const long long tile_i = (unsigned)t % tiles_inner, o = (unsigned)t / tiles_inner;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(loaded + b)),
                        "r"((unsigned)(32 * n * 8))
@@ -740,7 +746,7 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
           dst += cfg.l;
         }
       } else if (lane < valid) {
-        const long long tile_i = t % tiles_inner, o = t / tiles_inner;
+        const long long tile_i = (unsigned)t % tiles_inner, o = (unsigned)t / tiles_inner;
         const double *col = (const double *)in + tile_i * 32 + o * sp.inner * n + lane + (long long)warp * sp.inner;
         double *dst = buf + (pad + warp) * PITCH + lane;
         const long long cs = (long long)cfg.l * sp.inner;
@@ -761,7 +767,9 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
     for (long long t = blockIdx.x + team * tstep; t < ntiles; t += cfg.g * tstep, i += cfg.g) {
       const int b = i % NB, rev = i / NB;
       double *buf = sm + b * bufsz;
+      const long long tw0 = cfg.stats ? clock64() : 0;
       mbar_wait(loaded + b, (unsigned)rev & 1u);
+      const long long tw1 = cfg.stats ? clock64() : 0;
       if (lane < tile_valid(t)) {
         double *bl = buf + lane;
         const double mean = line_mean(bl, pad, PITCH, n);
@@ -772,6 +780,10 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
           constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
           ghost_poly_side<NS, EQS>(bl, pad, PITCH, n, mean, sp.h, side ? sp.bcr : sp.bcl, side == 1, gm);
         }
+      }
+      if (cfg.stats && lane == 0) {
+        atomicAdd(cfg.stats + 2, (unsigned long long)(tw1 - tw0));
+        atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - tw1));
       }
       mbar_arrive(full + b);
     }
@@ -789,11 +801,16 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
         if (AXIS0) {
           line0 = t * 32;
         } else {
-          tile_i = t % tiles_inner;
-          o = t / tiles_inner;
+          tile_i = (unsigned)t % tiles_inner;
+          o = (unsigned)t / tiles_inner;
         }
+        const long long tw0 = cfg.stats ? clock64() : 0;
         mbar_wait(full + b, (unsigned)rev & 1u);
+        const long long tw1 = cfg.stats ? clock64() : 0;
         if (SMOOTH) {
+          // FIR with a sliding register window, software-pipelined: the R inputs the NEXT group of R taps slides in
+          // are loaded (R independent LDS) before the current group's R*R DFMAs are issued, so the shared-memory
+          // latency never sits between dependent DFMAs (a consumer group runs with ~2 warps per scheduler)
           constexpr int R = SMOOTH_R;
           const double *kw = extra;
           const int taps = sp.taps;
@@ -801,32 +818,40 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
           if (lane < valid)
             for (int kb = cw; kb < nblk; kb += CW) {
               const int k0 = kb * R;
-              double acc[R], win[R];
+              double acc[R], cur[R], nxt[R];
               const double *p = buf + k0 * PITCH + lane;
 #pragma unroll
               for (int r = 0; r < R; ++r) {
                 acc[r] = 0.0;
-                win[r] = p[r * PITCH];
+                cur[r] = p[r * PITCH];
               }
               p += R * PITCH;
               int l = 0;
               for (; l + R <= taps; l += R) {  // full groups: no predicates
 #pragma unroll
-                for (int u = 0; u < R; ++u) {
-                  const double wv = kw[l + u];
-#pragma unroll
-                  for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
-                  win[u] = p[u * PITCH];
-                }
+                for (int u = 0; u < R; ++u) nxt[u] = p[u * PITCH];  // rows k0 + l + R + u (the buffer has 2R spare rows)
                 p += R * PITCH;
+#pragma unroll
+                for (int u = 0; u < R; u += 2) {
+                  const double2 wv = *(const double2 *)(kw + l + u);
+#pragma unroll
+                  for (int r = 0; r < R; ++r) acc[r] = fma(u + r < R ? cur[u + r] : nxt[u + r - R], wv.x, acc[r]);
+#pragma unroll
+                  for (int r = 0; r < R; ++r) acc[r] = fma(u + 1 + r < R ? cur[u + 1 + r] : nxt[u + 1 + r - R], wv.y, acc[r]);
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u) cur[u] = nxt[u];
               }
 #pragma unroll
               for (int u = 0; u < R; ++u) {
-                if (l + u < taps) {  // uniform
+                if (l + u < taps) {  // uniform tail (taps = 2E + 1 is odd)
+                  if (u == 0) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) nxt[q] = p[q * PITCH];
+                  }
                   const double wv = kw[l + u];
 #pragma unroll
-                  for (int r = 0; r < R; ++r) acc[r] = fma(win[(u + r) % R], wv, acc[r]);
-                  win[u] = p[u * PITCH];
+                  for (int r = 0; r < R; ++r) acc[r] = fma(u + r < R ? cur[u + r] : nxt[u + r - R], wv, acc[r]);
                 }
               }
               T *op = AXIS0 ? out + (line0 + lane) * nout + k0
@@ -872,6 +897,10 @@ __global__ void __launch_bounds__(SMOOTH ? 1024 : (AXIS0 ? 640 : 384), 1)
             else
               resample_lines2<T, TP, false>(buf + lane, PITCH, (const double2 *)sp.Wk, sp.base, kbeg, kend, optr, sp.inner, sp.scale);
           }
+        }
+        if (cfg.stats && lane == 0) {
+          atomicAdd(cfg.stats + 4, (unsigned long long)(tw1 - tw0));
+          atomicAdd(cfg.stats + 5, (unsigned long long)(clock64() - tw1));
         }
         mbar_arrive(empty + b);
       }
@@ -962,6 +991,11 @@ static int launch_taps(const SweepParams &sp, const GhostMats &gm, const T *in, 
   return CIB200_EUNSUPPORTED;
 }
 
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
 template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
 static int launch_pipe_kernel(const SweepParams &sp, const GhostMats &gm, const PipeCfg &cfg, const T *in, T *out,
                               long long ntiles, int threads, size_t smem, cudaStream_t st) {
@@ -987,9 +1021,26 @@ static int launch_pipe_kernel(const SweepParams &sp, const GhostMats &gm, const 
   }
   CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long grid = std::min<long long>(ntiles, (long long)sm_count());
-  k<<<(unsigned)grid, threads, smem, st>>>(tmap, sp, gm, cfg, in, out, ntiles);
+  PipeCfg cfg2 = cfg;
+  cfg2.stats = nullptr;
+  const bool want_stats = env_int("CIB200_PIPE_STATS", 0) == 1;
+  if (want_stats) {
+    CIB_CUDA(cudaMalloc(&cfg2.stats, 6 * sizeof(unsigned long long)));
+    CIB_CUDA(cudaMemsetAsync(cfg2.stats, 0, 6 * sizeof(unsigned long long), st));
+  }
+  k<<<(unsigned)grid, threads, smem, st>>>(tmap, sp, gm, cfg2, in, out, ntiles);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
+  if (want_stats) {
+    unsigned long long hs[6];
+    CIB_CUDA(cudaMemcpyAsync(hs, cfg2.stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CIB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(cfg2.stats);
+    const double per_tile = 1.0 / (double)ntiles;
+    fprintf(stderr, "[pipe %s axis0=%d taps=%d] tiles=%lld grid=%lld nb=%d l=%d g=%d c=%d cwg=%d | cycles/tile: loader wait %.0f | ghost wait %.0f busy %.0f (per warp) | consumer wait %.0f busy %.0f (per warp)\n",
+            SMOOTH ? "smooth" : "resample", (int)AXIS0, TAPS, ntiles, grid, cfg.nb, cfg.l, cfg.g, cfg.c, cfg.cwg,
+            hs[0] * per_tile, hs[2] * per_tile / 2, hs[3] * per_tile / 2, hs[4] * per_tile / cfg.cwg, hs[5] * per_tile / cfg.cwg);
+  }
   return CIB200_OK;
 }
 
@@ -1009,11 +1060,6 @@ static int launch_pipe_taps(const SweepParams &sp, const GhostMats &gm, const Pi
   }
   set_error("sweep: unsupported tap count %d", sp.taps);
   return CIB200_EUNSUPPORTED;
-}
-
-static int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return (e && e[0]) ? atoi(e) : dflt;
 }
 
 // returns -1 when the pass does not qualify for the pipelined kernel (Float32, or a ring of >= 3 tiles does not fit)
@@ -1039,6 +1085,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
   }
   if (fixed + 3 * tile_bytes > budget) return -1;
   PipeCfg cfg;
+  cfg.stats = nullptr;
   cfg.nb = (int)std::min<size_t>(PIPE_MAX_NB, (budget - fixed) / tile_bytes);
   // consumers: a group of cwg warps works on one tile
   int regs_per_thread;  // what ptxas needs for the consumer code (bounds the thread count: 64k registers per SM)
@@ -1052,7 +1099,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
     cfg.cwg = 8;
     regs_per_thread = 168;
   }
-  const int max_warps = SMOOTH ? 32 : (axis0 ? 20 : 12);  // the kernels' __launch_bounds__
+  const int max_warps = SMOOTH ? 24 : (axis0 ? 20 : 12);  // the kernels' __launch_bounds__
   (void)regs_per_thread;
   cfg.g = SMOOTH ? 2 : 1;
   // one 3-D TMA per tile when the rows are 16-byte aligned (box 32 x n_in x 1, n_in <= 256); otherwise four loader
@@ -1072,6 +1119,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
   sp.pitch = pitch;
   const size_t smem = fixed + (size_t)cfg.nb * tile_bytes;
   const long long ntiles = axis0 ? (sp.outer + 31) / 32 : ((sp.inner + 31) / 32) * sp.outer;
+  if (ntiles >= (1LL << 31) || (sp.inner + 31) / 32 >= (1LL << 31)) return -1;
   if (axis0) return launch_pipe_taps<T, SMOOTH, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
   return launch_pipe_taps<T, SMOOTH, false>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
 }
