@@ -308,6 +308,28 @@ def test_binned_device_resident_and_auto_mode(ci):
     assert torch.equal(ga.eval(*[x[perm] for x in q]), ra[perm])            # permutation invariance, bitwise
 
 
+def test_binned_clustered_query_distributions(ci):
+    """Adversarial batches for the binning passes (everything in one cell / one tile / one plane of cells / a narrow
+    blob): the binned strategies must return what the gather strategy returns."""
+    import torch
+    rng = np.random.default_rng(34)
+    n = 96
+    k = tuple(np.linspace(0, 1, n) for _ in range(3))
+    v = _field((n, n, n), rng)
+    gb = ci.convolution_interpolation(k, v, bc="poly", eval_mode="binned")
+    gg = ci.convolution_interpolation(k, v, bc="poly", eval_mode="gather")
+    nq, h = 3_000_000, 1.0 / (n - 1)
+    u = lambda: torch.rand(nq, dtype=torch.float64, device="cuda")
+    blob = lambda: (0.5 + 0.01 * torch.randn(nq, dtype=torch.float64, device="cuda")).clamp_(0, 1)
+    cases = {"one cell": [0.5 + h * u(), 0.25 + h * u(), 0.75 + h * u()],
+             "one tile": [0.5 + 16 * h * u(), 0.25 + 16 * h * u(), 0.75 + 16 * h * u()],
+             "one plane": [u(), u(), 0.5 + h * u()],
+             "blob": [blob(), blob(), blob()]}
+    for name, q in cases.items():
+        rb, rg = gb.eval(*q), gg.eval(*q)
+        assert float((rb - rg).abs().max()) <= 1e-13 * float(np.abs(v).max()), name
+
+
 def test_host_buffer_pipeline_equals_device_resident(ci):
     """cib200_itp_eval with HOST buffers runs a chunked H2D -> kernels -> D2H pipeline (2^24-query chunks, ring of 3
     device buffers, one compute stream).  Several chunks in flight must give the same bits as one device-resident
