@@ -15,6 +15,7 @@ HOST, DEVICE = 0, 1
 KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4, "a3": 5, "a4": 6, "a5": 7, "a7": 8}
 BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
+SUBGRID_IDS = {"cubic": 0, "quintic": 1}
 EVAL_MODES = {"auto": 0, "gather": 1, "binned": 2}
 
 # every symbol include/cib200.h declares (tests assert the library exports all of them)
@@ -22,7 +23,7 @@ SYMBOLS = [
     "cib200_version", "cib200_last_error", "cib200_launch_count", "cib200_kernel_table",
     "cib200_build_coefs", "cib200_extend_knots", "cib200_itp_create", "cib200_itp_destroy",
     "cib200_itp_set_eval_mode", "cib200_itp_eval", "cib200_itp_eval_grid", "cib200_itp_scratch_bytes",
-    "cib200_resample", "cib200_smooth", "cib200_smooth_halfwidth", "cib200_host_register",
+    "cib200_resample", "cib200_resample_sg", "cib200_smooth", "cib200_smooth_halfwidth", "cib200_host_register",
     "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
 ]
 
@@ -31,7 +32,7 @@ class ItpDesc(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("dtype", C.c_int32), ("coef_shape", C.c_int64 * 3),
                 ("coefs", C.c_void_p), ("knots", C.c_void_p * 3), ("h", C.c_double * 3),
                 ("kernel", C.c_int32 * 3), ("deriv", C.c_int32 * 3), ("extrap", C.c_int32),
-                ("perdim", C.c_int32)]
+                ("perdim", C.c_int32), ("subgrid", C.c_int32 * 3)]
 
 
 class CIB200Error(RuntimeError):
@@ -82,6 +83,7 @@ def lib():
     L.cib200_itp_scratch_bytes.restype = i64
     L.cib200_itp_scratch_bytes.argtypes = [vp, i64]
     L.cib200_resample.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, i32, vp]
+    L.cib200_resample_sg.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, i32, vp]
     L.cib200_smooth.argtypes = [i32, i32, vp, vp, vp, vp, dbl, i32, vp]
     L.cib200_smooth_halfwidth.restype = i32
     L.cib200_smooth_halfwidth.argtypes = [dbl]

@@ -20,7 +20,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (BC_IDS, EXTRAP_IDS, KERNEL_IDS, CIB200Error, UnsupportedModeError, check, lib)
+from ._lib import (BC_IDS, EXTRAP_IDS, KERNEL_IDS, SUBGRID_IDS, CIB200Error, UnsupportedModeError, check, lib)
 
 # data_structures/degree_to_equations.jl:13-25
 DEGREE_TO_EQUATIONS = {"a0": 1, "a1": 1, "a3": 2, "a4": 3, "a5": 3, "a7": 4, "b5": 5, "b7": 6, "b9": 7,
@@ -34,6 +34,8 @@ MAX_SHIPPED_DERIVATIVE = {"a0": 0, "a1": 0, "a3": 0, "a4": 0, "a5": 0, "a7": 0, 
 # convolution_interpolation_function.jl:183-195
 MINIMUM_POLYNOMIAL_BC_POINTS = {"a0": 2, "a1": 2, "a3": 4, "a4": 4, "a5": 4, "a7": 4, "b5": 6, "b7": 8,
                                 "b9": 8, "b11": 8, "b13": 8}
+# highest K^(d) table shipped per kernel (precomputed_kernels/kernel_<k>.jl): the quintic subgrid needs K^(d+2)
+MAX_TABLE_DERIVATIVE = {"a3": 1, "a4": 1, "a5": 1, "a7": 1, "b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6}
 ACCELERATED_KERNELS = tuple(KERNEL_IDS)
 
 
@@ -159,7 +161,7 @@ def _build_subgrids(kernels, derivs, subgrids):
     return tuple(out)
 
 
-def _require_accelerated(kernels, derivs, subgrids, ndim, what):
+def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
     """Raise UnsupportedModeError for modes that stay on the reference's Julia path."""
     if ndim > 3 and what == "convolution_interpolation":
         raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N={ndim} uses the linear-subgrid N-D evaluators "
@@ -170,11 +172,20 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what):
                                        f"accelerated path ({ACCELERATED_KERNELS})")
         if dv < 0:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivatives (derivative=-1) stay on the reference path")
-        if sg != "cubic":
+        if sg not in ("cubic", "quintic"):
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: resolved subgrid {subgrids} needs the "
-                                       f":{sg} evaluators / generated tables; only :cubic is accelerated")
+                                       f":{sg} evaluators / generated tables; :cubic and :quintic are accelerated")
         if dv > MAX_SHIPPED_DERIVATIVE[k]:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative {dv} of :{k} is not a shipped table")
+        if sg == "quintic" and dv + 2 > MAX_TABLE_DERIVATIVE[k]:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: the quintic subgrid needs K^({dv + 2}) of :{k}, "
+                                       "which is not a shipped table")
+    if what == "convolution_interpolation" and "quintic" in subgrids:
+        # eager_2d.jl handles (quintic, quintic) only; the mixed pairs exist on the per-dim path (perdim_2d.jl);
+        # N = 3 never resolves to quintic (_build_subgrids)
+        if ndim > 2 or (ndim == 2 and not perdim and tuple(subgrids) != ("quintic", "quintic")):
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: subgrid {tuple(subgrids)} has no evaluator for "
+                                       "one kernel and one derivative order on all axes (eager_2d.jl:91-311)")
 
 
 def _stream_ptr(device_tensor):
@@ -218,11 +229,11 @@ class FastConvolutionInterpolation:
         self.subgrid = _build_subgrids(self.kernel, self.derivative, sg_req)
         if precompute != 101:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, "precompute != 101 needs generated tables (reference path)")
-        _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation")
-        self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
-        self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120
         # _build_kernel_sym (constructor.jl:378-398): HigherOrderKernel vs HigherOrderMixedKernel
         self.perdim = not (len(set(self.kernel)) == 1 and len(set(self.derivative)) == 1)
+        _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation", self.perdim)
+        self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
+        self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120
         L = lib()
         # ---- subsystem 1: ghost-padded coefficients + extended knots, on the host ----
         v = np.asfortranarray(values)
@@ -251,6 +262,7 @@ class FastConvolutionInterpolation:
             desc.h[d] = self.h[d]
             desc.kernel[d] = KERNEL_IDS[self.kernel[d]]
             desc.deriv[d] = int(self.derivative[d])
+            desc.subgrid[d] = SUBGRID_IDS[self.subgrid[d]]
         desc.coefs = self.coefs.ctypes.data
         desc.extrap = EXTRAP_IDS[_extrap]
         desc.perdim = int(self.perdim)
@@ -476,7 +488,9 @@ def convolution_resample(knots_in, knots_out, values, precompute=_UNSET, kernel=
     dv = (C.c_int32 * nd)(*[int(d) for d in derivs])
     bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
     br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
-    check(lib().cib200_resample(nd, did, n_in, n_out, in_ptr, out_ptr, kinp, koutp, kid, dv, bl, br, memkind, stream))
+    sg = (C.c_int32 * nd)(*[SUBGRID_IDS[x] for x in sgs_valid])
+    check(lib().cib200_resample_sg(nd, did, n_in, n_out, in_ptr, out_ptr, kinp, koutp, kid, dv, bl, br, sg, memkind,
+                                   stream))
     del keep
     return view()
 

@@ -415,6 +415,20 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
       set_error("cib200_itp_create: derivative %d on axis %d is outside the shipped cubic-subgrid tables", desc->deriv[d], d);
       return CIB200_EUNSUPPORTED;
     }
+    if (desc->subgrid[d] != CIB200_SG_CUBIC && desc->subgrid[d] != CIB200_SG_QUINTIC) {
+      set_error("cib200_itp_create: unknown subgrid %d on axis %d", desc->subgrid[d], d);
+      return CIB200_EINVAL;
+    }
+    if (desc->subgrid[d] == CIB200_SG_QUINTIC) {
+      if (nd > 2) {
+        set_error("cib200_itp_create: the quintic subgrid exists for 1-D and 2-D interpolants only (3-D resolves to :linear)");
+        return CIB200_EUNSUPPORTED;
+      }
+      if (desc->deriv[d] + 2 > kernel_max_deriv_table(desc->kernel[d])) {
+        set_error("cib200_itp_create: quintic subgrid on axis %d needs K^(%d), which is not a shipped table", d, desc->deriv[d] + 2);
+        return CIB200_EUNSUPPORTED;
+      }
+    }
     if (desc->coef_shape[d] < 2 * eqs[d] || desc->coef_shape[d] > 0x7fffffffLL || !desc->knots[d]) {
       set_error("cib200_itp_create: bad coef_shape / knots on axis %d", d);
       return CIB200_EINVAL;
@@ -494,6 +508,10 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
   for (int d = 0; d < nd; ++d) {
     p.tab_slot_k[d] = slot_of(h->kernel[d], h->deriv[d]);
     p.tab_slot_d[d] = slot_of(h->kernel[d], h->deriv[d] + 1);
+  }
+  for (int d = 0; d < 3; ++d) {
+    p.subgrid[d] = d < nd ? desc->subgrid[d] : 0;
+    p.tab_slot_e[d] = (d < nd && desc->subgrid[d] == CIB200_SG_QUINTIC) ? slot_of(h->kernel[d], h->deriv[d] + 2) : -1;
   }
   p.n_tab_slots = (int)slots.size();
   size_t tab_doubles = 0;
@@ -741,6 +759,14 @@ int32_t cib200_resample(int32_t ndim, int32_t dtype, const int64_t *n_in, const 
                         void *out, const double *const *knots_in, const double *const *knots_out,
                         const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
                         const int32_t *bc_right, int32_t memkind, void *stream) {
+  return cib200_resample_sg(ndim, dtype, n_in, n_out, values, out, knots_in, knots_out, kernel, deriv, bc_left, bc_right,
+                            nullptr, memkind, stream);
+}
+
+int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, const int64_t *n_out, const void *values,
+                           void *out, const double *const *knots_in, const double *const *knots_out,
+                           const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                           const int32_t *bc_right, const int32_t *subgrid, int32_t memkind, void *stream) {
   if (ndim < 1 || ndim > CIB200_MAX_SWEEP_DIM || !n_in || !n_out || !values || !out || !knots_in || !knots_out ||
       !kernel || !deriv || !bc_left || !bc_right) {
     set_error("cib200_resample: bad arguments");
@@ -752,7 +778,18 @@ int32_t cib200_resample(int32_t ndim, int32_t dtype, const int64_t *n_in, const 
   }
   long long nin[CIB200_MAX_SWEEP_DIM], nout[CIB200_MAX_SWEEP_DIM], tin = 1, tout = 1;
   int k[CIB200_MAX_SWEEP_DIM], dv[CIB200_MAX_SWEEP_DIM], bl[CIB200_MAX_SWEEP_DIM], br[CIB200_MAX_SWEEP_DIM];
+  int sgv[CIB200_MAX_SWEEP_DIM];
   for (int d = 0; d < ndim; ++d) {
+    sgv[d] = subgrid ? subgrid[d] : CIB200_SG_CUBIC;
+    if (sgv[d] != CIB200_SG_CUBIC && sgv[d] != CIB200_SG_QUINTIC) {
+      set_error("cib200_resample: unknown subgrid %d on axis %d", sgv[d], d);
+      return CIB200_EINVAL;
+    }
+    if (kernel_eqs(kernel[d]) >= 0 && sgv[d] == CIB200_SG_QUINTIC && deriv[d] >= 0 &&
+        deriv[d] + 2 > kernel_max_deriv_table(kernel[d])) {
+      set_error("cib200_resample: quintic subgrid on axis %d needs K^(%d), which is not a shipped table", d, deriv[d] + 2);
+      return CIB200_EUNSUPPORTED;
+    }
     if (kernel_eqs(kernel[d]) < 0) {
       set_error("cib200_resample: unknown kernel id %d on axis %d", kernel[d], d);
       return CIB200_EUNSUPPORTED;
@@ -784,7 +821,7 @@ int32_t cib200_resample(int32_t ndim, int32_t dtype, const int64_t *n_in, const 
   bool owned;
   int rc = sweep_io(ndim, dtype, tin, tout, values, out, memkind, st, &d_in, &d_out, &owned);
   if (rc) return rc;
-  rc = sweep_resample(ndim, dtype, nin, nout, d_in, d_out, knots_in, knots_out, k, dv, bl, br, st);
+  rc = sweep_resample(ndim, dtype, nin, nout, d_in, d_out, knots_in, knots_out, k, dv, bl, br, sgv, st);
   if (owned) {
     if (!rc) {
       cudaError_t e = cudaMemcpyAsync(out, d_out, esize(dtype) * (size_t)tout, cudaMemcpyDeviceToHost, st);

@@ -57,6 +57,7 @@ __device__ __forceinline__ void locate_computed(double x, double x_expanded_1, d
 // cubic Hermite basis (cubic_hermite_interpolation.jl:15-28), h_pre folded into the derivative terms
 struct Hermite {
   double h00, h01, h10, h11;
+  double h20, h21;  // quintic only: second-derivative basis, (h_pre^2 / 2) folded in
 };
 __device__ __forceinline__ Hermite hermite_basis(double t) {
   const double h_pre = 1.0 / (double)(CIB_N_PRE - 1);
@@ -66,6 +67,22 @@ __device__ __forceinline__ Hermite hermite_basis(double t) {
   b.h01 = t2 * (3.0 - 2.0 * t);
   b.h10 = h_pre * (t + t2 * (-2.0 + t));
   b.h11 = h_pre * (t2 * (t - 1.0));
+  b.h20 = 0.0;
+  b.h21 = 0.0;
+  return b;
+}
+
+// quintic Hermite basis (quintic_hermite_interpolation.jl:16-37), h_pre and h_pre^2/2 folded into the derivative terms
+__device__ __forceinline__ Hermite hermite_basis_quintic(double t) {
+  const double h_pre = 1.0 / (double)(CIB_N_PRE - 1);
+  const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+  Hermite b;
+  b.h00 = 1.0 - 10 * t3 + 15 * t4 - 6 * t5;
+  b.h01 = 10 * t3 - 15 * t4 + 6 * t5;
+  b.h10 = h_pre * (t - 6 * t3 + 8 * t4 - 3 * t5);
+  b.h11 = h_pre * (-4 * t3 + 7 * t4 - 3 * t5);
+  b.h20 = (h_pre * h_pre / 2) * (t2 - 3 * t3 + 3 * t4 - t5);
+  b.h21 = (h_pre * h_pre / 2) * (t3 - 2 * t4 + t5);
   return b;
 }
 
@@ -79,10 +96,18 @@ __device__ __forceinline__ double blended_weight(const Hermite &b, const double 
   return b.h00 * k0[0] + b.h01 * k0[w] + (b.h10 * d0[0] + b.h11 * d0[w]);
 }
 
+// quintic subgrid: the same plus the second-derivative rows (te = K^(d+2))
+__device__ __forceinline__ double blended_weight_quintic(const Hermite &b, const double *__restrict__ tk,
+                                                         const double *__restrict__ td, const double *__restrict__ te,
+                                                         int row, int col, int w) {
+  const double *e0 = te + row * w + col;
+  return blended_weight(b, tk, td, row, col, w) + (b.h20 * e0[0] + b.h21 * e0[w]);
+}
+
 // copy the distinct tables of an interpolant into shared memory; returns nothing, fills ptr arrays
 __device__ __forceinline__ void stage_tables(const ItpParams &p, double *smem, const double *tk[3],
                                              const double *td[3]) {
-  int off[6];
+  int off[9];
   int o = 0;
   for (int s = 0; s < p.n_tab_slots; ++s) {
     off[s] = o;
@@ -95,6 +120,14 @@ __device__ __forceinline__ void stage_tables(const ItpParams &p, double *smem, c
     tk[d] = smem + off[p.tab_slot_k[d]];
     td[d] = smem + off[p.tab_slot_d[d]];
   }
+}
+
+// shared-memory address of the staged K^(d+2) table of axis d (quintic subgrid), nullptr for a cubic axis
+__device__ __forceinline__ const double *staged_e_table(const ItpParams &p, const double *smem, int d) {
+  if (p.tab_slot_e[d] < 0) return nullptr;
+  int o = 0;
+  for (int s = 0; s < p.tab_slot_e[d]; ++s) o += CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
+  return smem + o;
 }
 
 __host__ __device__ inline int tables_smem_doubles(const ItpParams &p) {

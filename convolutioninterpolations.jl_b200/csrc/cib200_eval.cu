@@ -29,6 +29,9 @@ __global__ void __launch_bounds__(256) eval_thread_kernel(ItpParams p, Coords c,
   const double *tk[3];
   const double *td[3];
   stage_tables(p, smem, tk, td);
+  const double *te[3] = {nullptr, nullptr, nullptr};
+  if (NDIM <= 2)
+    for (int d = 0; d < NDIM; ++d) te[d] = staged_e_table(p, smem, d);
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
@@ -41,10 +44,10 @@ __global__ void __launch_bounds__(256) eval_thread_kernel(ItpParams p, Coords c,
     Plan pl = make_plan<NDIM>(p, x, pa, pb);
     double r = CUDART_NAN;
     if (pl.ntask >= 1) {
-      double fb = apply_scale<NDIM>(core_thread<T, NDIM, E>(p, tk, td, pa), sc);
+      double fb = apply_scale<NDIM>(core_thread<T, NDIM, E>(p, tk, td, pa, te), sc);
       r = fb;
       if (pl.ntask == 2) {
-        double fin = apply_scale<NDIM>(core_thread<T, NDIM, E>(p, tk, td, pb), sc);
+        double fin = apply_scale<NDIM>(core_thread<T, NDIM, E>(p, tk, td, pb, te), sc);
         r = finish_line(fb, fin, p.eps_line, pl.dist);
       }
     } else {

@@ -107,18 +107,32 @@ __device__ __forceinline__ void decode_coords(const Coords &c, long long q, long
 // ---------------------------------------------------------------------------------------------
 // thread-per-query kernel
 // ---------------------------------------------------------------------------------------------
+// per-axis Hermite basis / blended weight honouring the axis' subgrid (quintic exists for NDIM <= 2 only)
+template <int NDIM>
+__device__ __forceinline__ Hermite axis_basis(const ItpParams &p, int d, double t) {
+  if (NDIM <= 2 && p.subgrid[d]) return hermite_basis_quintic(t);
+  return hermite_basis(t);
+}
+template <int NDIM>
+__device__ __forceinline__ double axis_weight(const ItpParams &p, int d, const Hermite &hb, const double *tk,
+                                              const double *td, const double *te, int row, int col, int w) {
+  if (NDIM <= 2 && p.subgrid[d]) return blended_weight_quintic(hb, tk, td, te, row, col, w);
+  return blended_weight(hb, tk, td, row, col, w);
+}
+
 template <typename T, int NDIM, int E>
 __device__ __forceinline__ double core_thread(const ItpParams &p, const double *const *tk, const double *const *td,
-                                              const AxisPos *pos) {
+                                              const AxisPos *pos, const double *const *te = nullptr) {
   const T *__restrict__ coefs = (const T *)p.coefs;
+  const double *tq[3] = {te ? te[0] : nullptr, te ? te[1] : nullptr, te ? te[2] : nullptr};
   if (E > 0) {
     constexpr int W = 2 * (E > 0 ? E : 1);
     double w[NDIM][W];
 #pragma unroll
     for (int d = 0; d < NDIM; ++d) {
-      Hermite hb = hermite_basis(pos[d].t);
+      Hermite hb = axis_basis<NDIM>(p, d, pos[d].t);
 #pragma unroll
-      for (int l = 0; l < W; ++l) w[d][l] = blended_weight(hb, tk[d], td[d], pos[d].row, l, W);
+      for (int l = 0; l < W; ++l) w[d][l] = axis_weight<NDIM>(p, d, hb, tk[d], td[d], tq[d], pos[d].row, l, W);
     }
     if (NDIM == 1) {
       double acc = 0.0;
@@ -157,12 +171,12 @@ __device__ __forceinline__ double core_thread(const ItpParams &p, const double *
   // generic: per-axis eqs at run time, weights recomputed from the shared-memory tables on the fly
   Hermite hb[NDIM];
 #pragma unroll
-  for (int d = 0; d < NDIM; ++d) hb[d] = hermite_basis(pos[d].t);
+  for (int d = 0; d < NDIM; ++d) hb[d] = axis_basis<NDIM>(p, d, pos[d].t);
   const int w0 = 2 * p.eqs[0];
   if (NDIM == 1) {
     double acc = 0.0;
     for (int l = 0; l < w0; ++l)
-      acc = fma((double)coefs[pos[0].base + l], blended_weight(hb[0], tk[0], td[0], pos[0].row, l, w0), acc);
+      acc = fma((double)coefs[pos[0].base + l], axis_weight<NDIM>(p, 0, hb[0], tk[0], td[0], tq[0], pos[0].row, l, w0), acc);
     return acc;
   }
   const int w1 = 2 * p.eqs[NDIM > 1 ? 1 : 0];
@@ -172,8 +186,8 @@ __device__ __forceinline__ double core_thread(const ItpParams &p, const double *
     for (int m = 0; m < w1; ++m) {
       double a = 0.0;
       for (int l = 0; l < w0; ++l)
-        a = fma((double)c0[l + (long long)m * p.s1], blended_weight(hb[0], tk[0], td[0], pos[0].row, l, w0), a);
-      acc = fma(a, blended_weight(hb[NDIM > 1 ? 1 : 0], tk[1], td[1], pos[NDIM > 1 ? 1 : 0].row, m, w1), acc);
+        a = fma((double)c0[l + (long long)m * p.s1], axis_weight<NDIM>(p, 0, hb[0], tk[0], td[0], tq[0], pos[0].row, l, w0), a);
+      acc = fma(a, axis_weight<NDIM>(p, 1, hb[NDIM > 1 ? 1 : 0], tk[1], td[1], tq[1], pos[NDIM > 1 ? 1 : 0].row, m, w1), acc);
     }
     return acc;
   }

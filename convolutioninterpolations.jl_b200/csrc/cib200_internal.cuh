@@ -47,9 +47,11 @@ struct ItpParams {
   const double *tabd[3];   // device, K^(d+1)
   int tab_slot_k[3];       // index of the distinct table in the packed smem image
   int tab_slot_d[3];
+  int tab_slot_e[3];       // K^(d+2), quintic subgrid only (-1 otherwise)
+  int subgrid[3];          // 0 cubic, 1 quintic (1-D / 2-D interpolants only)
   int n_tab_slots;
-  int tab_slot_eqs[6];     // eqs of each distinct table
-  const double *tab_slot_ptr[6];
+  int tab_slot_eqs[9];     // eqs of each distinct table
+  const double *tab_slot_ptr[9];
   double h[3];
   double lo[3], hi[3];     // _domain_bounds, extrapolate_point.jl:172-176
   double knot0[3];         // knots[d][0] (kernel-parameter constant: never re-loaded inside a loop)
@@ -119,7 +121,8 @@ void binned_destroy(cib200_itp *h);
 // sweeps (cib200_sweep.cu)
 int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *n_out, const void *d_in,
                    void *d_out, const double *const *knots_in, const double *const *knots_out,
-                   const int *kernel, const int *deriv, const int *bcl, const int *bcr, cudaStream_t st);
+                   const int *kernel, const int *deriv, const int *bcl, const int *bcr, const int *subgrid,
+                   cudaStream_t st);
 int sweep_smooth(int ndim, int dtype, const long long *n, const void *d_in, void *d_out, const double *h,
                  double B, cudaStream_t st);
 }  // namespace cib

@@ -56,17 +56,17 @@ struct SweepParams {
 // ---- per-output-knot weights: convolution_resample.jl:320-361 minus the data ------------------
 __global__ void resample_weights_kernel(const double *__restrict__ knots_out, long long n_out, double x_expanded_1,
                                         double h, int eqs, long long n_coef, const double *__restrict__ tk,
-                                        const double *__restrict__ td, double *__restrict__ W, double *__restrict__ Wk,
-                                        int *__restrict__ base) {
+                                        const double *__restrict__ td, const double *__restrict__ te,
+                                        double *__restrict__ W, double *__restrict__ Wk, int *__restrict__ base) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_out) return;
   AxisPos p;
   locate_computed(knots_out[k], x_expanded_1, h, eqs, n_coef, p);
   base[k] = p.base;
-  Hermite hb = hermite_basis(p.t);
+  const Hermite hb = te ? hermite_basis_quintic(p.t) : hermite_basis(p.t);  // te != nullptr: quintic subgrid (:333-349)
   const int w = 2 * eqs;
   for (int l = 0; l < w; ++l) {
-    const double v = blended_weight(hb, tk, td, p.row, l, w);
+    const double v = te ? blended_weight_quintic(hb, tk, td, te, p.row, l, w) : blended_weight(hb, tk, td, p.row, l, w);
     W[(long long)l * n_out + k] = v;
     Wk[k * w + l] = v;
   }
@@ -1181,7 +1181,7 @@ struct TempBufs {
 template <typename T>
 static int resample_t(int ndim, const long long *n_in, const long long *n_out, const T *d_in, T *d_out,
                       const double *const *knots_in, const double *const *knots_out, const int *kernel,
-                      const int *deriv, const int *bcl, const int *bcr, cudaStream_t st) {
+                      const int *deriv, const int *bcl, const int *bcr, const int *subgrid, cudaStream_t st) {
   TempBufs tmp;
   tmp.st = st;
   long long shape[CIB200_MAX_SWEEP_DIM];
@@ -1196,7 +1196,7 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     const double x_expanded_1 = knots_in[d][0] - (double)(eqs - 1) * h;  // :285
     const long long n_coef = nin + 2 * (eqs - 1);
     // tables + output knots + weights on the device
-    double *d_tk, *d_td, *d_ko, *d_W, *d_Wk;
+    double *d_tk, *d_td, *d_te = nullptr, *d_ko, *d_W, *d_Wk;
     int *d_base;
     const size_t tab_bytes = sizeof(double) * CIB_TAB_ROWS * taps;
     if ((rc = tmp.alloc((void **)&d_tk, tab_bytes))) return rc;
@@ -1207,9 +1207,13 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     if ((rc = tmp.alloc((void **)&d_base, sizeof(int) * (size_t)nout))) return rc;
     CIB_CUDA(cudaMemcpyAsync(d_tk, host_table(kernel[d], deriv[d]), tab_bytes, cudaMemcpyHostToDevice, st));
     CIB_CUDA(cudaMemcpyAsync(d_td, host_table(kernel[d], deriv[d] + 1), tab_bytes, cudaMemcpyHostToDevice, st));
+    if (subgrid[d] == CIB200_SG_QUINTIC) {
+      if ((rc = tmp.alloc((void **)&d_te, tab_bytes))) return rc;
+      CIB_CUDA(cudaMemcpyAsync(d_te, host_table(kernel[d], deriv[d] + 2), tab_bytes, cudaMemcpyHostToDevice, st));
+    }
     CIB_CUDA(cudaMemcpyAsync(d_ko, knots_out[d], sizeof(double) * (size_t)nout, cudaMemcpyHostToDevice, st));
     resample_weights_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(d_ko, nout, x_expanded_1, h, eqs, n_coef,
-                                                                           d_tk, d_td, d_W, d_Wk, d_base);
+                                                                           d_tk, d_td, d_te, d_W, d_Wk, d_base);
     CIB_LAUNCHED();
     CIB_CUDA(cudaGetLastError());
 
@@ -1261,10 +1265,10 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
 
 int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *n_out, const void *d_in, void *d_out,
                    const double *const *knots_in, const double *const *knots_out, const int *kernel, const int *deriv,
-                   const int *bcl, const int *bcr, cudaStream_t st) {
+                   const int *bcl, const int *bcr, const int *subgrid, cudaStream_t st) {
   if (dtype == CIB200_F32)
-    return resample_t<float>(ndim, n_in, n_out, (const float *)d_in, (float *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, st);
-  return resample_t<double>(ndim, n_in, n_out, (const double *)d_in, (double *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, st);
+    return resample_t<float>(ndim, n_in, n_out, (const float *)d_in, (float *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, subgrid, st);
+  return resample_t<double>(ndim, n_in, n_out, (const double *)d_in, (double *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, subgrid, st);
 }
 
 // convolution_kernels/convolution_kernel_gaussian.jl:23-31

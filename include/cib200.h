@@ -51,6 +51,9 @@ typedef enum {
 } cib200_kernel;
 typedef enum { CIB200_BC_DETECT = 0, CIB200_BC_POLY = 1, CIB200_BC_LINEAR = 2, CIB200_BC_QUADRATIC = 3 } cib200_bc;
 typedef enum { CIB200_THROW = 0, CIB200_FLAT = 1, CIB200_LINE = 2 } cib200_extrap;
+/* subgrid = how the 101-row tables are interpolated between rows: cubic Hermite (K, K') or quintic Hermite (K, K', K'')
+ * - cubic_hermite_interpolation.jl:15-28, quintic_hermite_interpolation.jl:16-37 */
+typedef enum { CIB200_SG_CUBIC = 0, CIB200_SG_QUINTIC = 1 } cib200_subgrid;
 
 /* evaluation strategies of cib200_itp_eval (3-D only; 1-D/2-D always use the direct kernel) */
 typedef enum {
@@ -74,6 +77,8 @@ typedef struct cib200_itp_desc {
   int32_t extrap;                        /* cib200_extrap (etp.et)                                  */
   int32_t perdim;                        /* 0: HigherOrderKernel evaluators, 1: HigherOrderMixedKernel
                                             (only changes how the final scale is associated)        */
+  int32_t subgrid[CIB200_MAX_ITP_DIM];    /* cib200_subgrid per axis (itp.subgrid, resolved by _build_subgrids);
+                                            quintic: ndim <= 2 and K^(deriv+2) shipped              */
 } cib200_itp_desc;
 
 typedef struct cib200_itp cib200_itp; /* opaque */
@@ -136,6 +141,14 @@ int32_t cib200_resample(int32_t ndim, int32_t dtype, const int64_t *n_in, const 
                         const void *values, void *out, const double *const *knots_in,
                         const double *const *knots_out, const int32_t *kernel, const int32_t *deriv,
                         const int32_t *bc_left, const int32_t *bc_right, int32_t memkind, void *stream);
+
+/* the same with a per-axis subgrid (cib200_subgrid; quintic branch convolution_resample.jl:333-349); subgrid == NULL
+ * means cubic on every axis */
+int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, const int64_t *n_out,
+                           const void *values, void *out, const double *const *knots_in,
+                           const double *const *knots_out, const int32_t *kernel, const int32_t *deriv,
+                           const int32_t *bc_left, const int32_t *bc_right, const int32_t *subgrid,
+                           int32_t memkind, void *stream);
 
 /* replaces convolution_smooth (convolution/convolution_gaussian_smoothing.jl:45-126).
  * h[d] = knots[d][2] - knots[d][1]. Fails with CIB200_EINVAL when the half-width E >= n[d] (:50-56). */

@@ -13,6 +13,8 @@ using ..ConvolutionInterpolations: ConvolutionExtrapolation, FastConvolutionInte
 const LIB = get(ENV, "CIB200_LIB", "libcib200.so")
 const KERNEL_ID = Dict(:b5 => 0, :b7 => 1, :b9 => 2, :b11 => 3, :b13 => 4, :a3 => 5, :a4 => 6, :a5 => 7, :a7 => 8)
 const BC_ID = Dict(:detect => 0, :poly => 1, :linear => 2, :quadratic => 3)
+const SUBGRID_ID = Dict(:cubic => 0, :quintic => 1)
+const MAX_TABLE = Dict(:b5 => 3, :b7 => 4, :b9 => 5, :b11 => 6, :b13 => 6, :a3 => 1, :a4 => 1, :a5 => 1, :a7 => 1)  # shipped K^(d)
 const MAX_DERIV = Dict(:b5 => 2, :b7 => 3, :b9 => 4, :b11 => 5, :b13 => 5, :a3 => 0, :a4 => 0, :a5 => 0, :a7 => 0)   # _max_shipped_derivative
 
 # mirror of cib200_itp_desc (include/cib200.h) -------------------------------------------------------
@@ -27,6 +29,7 @@ struct ItpDesc
     deriv::NTuple{3,Int32}
     extrap::Int32
     perdim::Int32
+    subgrid::NTuple{3,Int32}
 end
 
 last_error() = unsafe_string(ccall((:cib200_last_error, LIB), Cstring, ()))
@@ -53,12 +56,21 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     ks === nothing && return false
     all(k -> haskey(KERNEL_ID, k), ks) || return false
     itp.lazy === Val{false}() || return false
-    itp.subgrid === Val(ntuple(_ -> :cubic, N)) || return false
     itp.derivative_order isa DerivativeOrder || return false
     dv = derivative_tuple(itp)
     all(d -> 0 <= dv[d] <= MAX_DERIV[ks[d]], 1:N) || return false
+    sg = subgrid_tuple(itp)
+    all(s -> s === :cubic || s === :quintic, sg) || return false
+    # :quintic needs K^(d+2) among the shipped tables; evaluators: eager_1d.jl:117-145, eager_2d.jl:214-311
+    # ((quintic, quintic) only), perdim_2d.jl (mixed pairs); never in 3-D (_build_subgrids)
+    all(d -> sg[d] === :cubic || dv[d] + 2 <= MAX_TABLE[ks[d]], 1:N) || return false
+    if any(==(:quintic), sg)
+        N <= 2 || return false
+        (N == 1 || itp.kernel_sym isa HigherOrderMixedKernel || all(==(:quintic), sg)) || return false
+    end
     return true
 end
+subgrid_tuple(itp) = typeof(itp.subgrid).parameters[1]               # Val{SG}
 derivative_tuple(itp) = typeof(itp.derivative_order).parameters[1]   # DerivativeOrder{DO} (struct_constructors.jl:182)
 
 # ---- handle cache: one upload per interpolant, freed by a finalizer --------------------------------
@@ -84,7 +96,8 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
                                pad3(ntuple(d -> pointer(knots64[d]), N), Ptr{Float64}(0)),
                                pad3(Float64.(itp.h), 1.0), pad3(ntuple(d -> Int32(KERNEL_ID[ks[d]]), N), Int32(0)),
                                pad3(ntuple(d -> Int32(dv[d]), N), Int32(0)), extrap_id(etp.et),
-                               Int32(itp.kernel_sym isa HigherOrderMixedKernel)))
+                               Int32(itp.kernel_sym isa HigherOrderMixedKernel),
+                               pad3(ntuple(d -> Int32(SUBGRID_ID[subgrid_tuple(itp)[d]]), N), Int32(0))))
             out = Ref{Ptr{Cvoid}}(C_NULL)
             GC.@preserve itp knots64 check(ccall((:cib200_itp_create, LIB), Int32,
                                                  (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
@@ -127,12 +140,13 @@ end
 # ---- convolution_resample_internal (convolution_resample.jl:240-386) ---------------------------------
 function resample_accelerated(values::AbstractArray{T,N}, kernels, derivatives, subgrids, precompute) where {T,N}
     (T === Float64 || T === Float32) && N <= 8 && all(k -> haskey(KERNEL_ID, k), kernels) &&
-        all(==(:cubic), subgrids) && all(==(101), precompute) &&
-        all(d -> 0 <= derivatives[d] <= MAX_DERIV[kernels[d]], 1:N)
+        all(s -> s === :cubic || s === :quintic, subgrids) && all(==(101), precompute) &&
+        all(d -> 0 <= derivatives[d] <= MAX_DERIV[kernels[d]], 1:N) &&
+        all(d -> subgrids[d] === :cubic || derivatives[d] + 2 <= MAX_TABLE[kernels[d]], 1:N)
 end
 
 function cib200_resample(knots_in::NTuple{N}, knots_out::NTuple{N}, values::Array{T,N},
-                         kernels, derivatives, bcs) where {T,N}
+                         kernels, derivatives, bcs, subgrids) where {T,N}
     kin = ntuple(d -> Vector{Float64}(knots_in[d]), N)
     kout = ntuple(d -> Vector{Float64}(knots_out[d]), N)
     out = Array{T,N}(undef, ntuple(d -> length(kout[d]), N))
@@ -140,15 +154,16 @@ function cib200_resample(knots_in::NTuple{N}, knots_out::NTuple{N}, values::Arra
     pin = [pointer(k) for k in kin]; pout = [pointer(k) for k in kout]
     kid = Int32[KERNEL_ID[k] for k in kernels]; dv = Int32[derivatives...]
     bl = Int32[BC_ID[b[1]] for b in bcs]; br = Int32[BC_ID[b[2]] for b in bcs]
-    GC.@preserve kin kout values out check(ccall((:cib200_resample, LIB), Int32,
+    sg = Int32[SUBGRID_ID[s] for s in subgrids]
+    GC.@preserve kin kout values out check(ccall((:cib200_resample_sg, LIB), Int32,
         (Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}},
-         Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Cvoid}),
-        N, T === Float32 ? 1 : 0, n_in, n_out, values, out, pin, pout, kid, dv, bl, br, 0, C_NULL))
+         Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Cvoid}),
+        N, T === Float32 ? 1 : 0, n_in, n_out, values, out, pin, pout, kid, dv, bl, br, sg, 0, C_NULL))
     return out
 end
 # in convolution_resample_internal, first line:
 #   resample_accelerated(values, kernels, derivatives, subgrids, precompute) &&
-#       return CIB200Glue.cib200_resample(knots_in, knots_out, values, kernels, derivatives, bcs)
+#       return CIB200Glue.cib200_resample(knots_in, knots_out, values, kernels, derivatives, bcs, subgrids)
 
 # ---- convolution_smooth (convolution_gaussian_smoothing.jl:45-126) -----------------------------------
 function cib200_smooth(knots::NTuple{N,AbstractVector}, values::Array{T,N}, B::Float64) where {T,N}

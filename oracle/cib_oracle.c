@@ -319,6 +319,24 @@ static inline double cubic_hermite(double t, double f0, double f1, double d0, do
   return h00 * f0 + h01 * f1 + h * (h10 * d0 + h11 * d1);
 }
 
+/* convolution_fast_interpolation/quintic_hermite_interpolation.jl:16-37 (Julia's 10t3 etc. are plain products;
+ * a - b + c chains associate left to right) */
+static inline double quintic_hermite(double t, double f0, double f1, double d0, double d1, double dd0, double dd1,
+                                     double h) {
+  double t2 = t * t;
+  double t3 = t2 * t;
+  double t4 = t3 * t;
+  double t5 = t4 * t;
+  double h00 = 1.0 - 10 * t3 + 15 * t4 - 6 * t5;
+  double h01 = 10 * t3 - 15 * t4 + 6 * t5;
+  double h10 = t - 6 * t3 + 8 * t4 - 3 * t5;
+  double h11 = -4 * t3 + 7 * t4 - 3 * t5;
+  double h20 = t2 - 3 * t3 + 3 * t4 - t5;
+  double h21 = t3 - 2 * t4 + t5;
+  double h2 = h * h;
+  return h00 * f0 + h01 * f1 + h * (h10 * d0 + h11 * d1) + (h2 / 2) * (h20 * dd0 + h21 * dd1);
+}
+
 typedef double v4d __attribute__((vector_size(32), aligned(32)));
 
 typedef struct {
@@ -350,6 +368,7 @@ static inline int locate(double x, const double *knots, int64_t nk, double h, in
 typedef struct {
   const double *kp[3];
   const double *kd[3];
+  const double *ke[3]; /* K^(d+2): quintic subgrid only */
   int eqs[3];
 } itp_tabs;
 
@@ -362,6 +381,78 @@ static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, doub
   axis_pos p[3];
   for (int d = 0; d < it->ndim; ++d)
     if (locate(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d])) return ORC_ENAN;
+
+  if (it->ndim == 1 && it->subgrid[0] == ORC_SG_QUINTIC) { /* eager_1d.jl:117-145 */
+    const int e = tb->eqs[0];
+    double sum_f0 = 0, sum_f1 = 0, sum_d0 = 0, sum_d1 = 0, sum_dd0 = 0, sum_dd1 = 0;
+    for (int j = -(e - 1); j <= e; ++j) {
+      double coef = it->coefs[p[0].i + j - 1];
+      int col = j + e;
+      sum_f0 += coef * TAB(tb->kp[0], p[0].idx, col, e);
+      sum_f1 += coef * TAB(tb->kp[0], p[0].idx + 1, col, e);
+      sum_d0 += coef * TAB(tb->kd[0], p[0].idx, col, e);
+      sum_d1 += coef * TAB(tb->kd[0], p[0].idx + 1, col, e);
+      sum_dd0 += coef * TAB(tb->ke[0], p[0].idx, col, e);
+      sum_dd1 += coef * TAB(tb->ke[0], p[0].idx + 1, col, e);
+    }
+    double result = quintic_hermite(p[0].t, sum_f0, sum_f1, sum_d0, sum_d1, sum_dd0, sum_dd1, h_pre);
+    double scale = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
+    *res = result * scale;
+    return ORC_OK;
+  }
+
+  if (it->ndim == 2 && (it->subgrid[0] == ORC_SG_QUINTIC || it->subgrid[1] == ORC_SG_QUINTIC)) {
+    /* eager_2d.jl:214-311 (quintic, quintic); perdim_2d.jl (quintic, cubic) :218-258, (cubic, quintic), (quintic,
+     * quintic): accumulators s[x-type][y-type][x-bracket][y-bracket], type 0 = f, 1 = d, 2 = e, each receiving
+     * (coef * kx) * ky in the reference's m -> l loop order; Hermite along x first, then along y */
+    const int ex = tb->eqs[0], ey = tb->eqs[1];
+    const int64_t s1 = it->cshape[0];
+    const int nx = it->subgrid[0] == ORC_SG_QUINTIC ? 3 : 2, ny = it->subgrid[1] == ORC_SG_QUINTIC ? 3 : 2;
+    const double *tx_tab[3] = {tb->kp[0], tb->kd[0], tb->ke[0]};
+    const double *ty_tab[3] = {tb->kp[1], tb->kd[1], tb->ke[1]};
+    double s[3][3][2][2];
+    memset(s, 0, sizeof s);
+    for (int m = -(ey - 1); m <= ey; ++m) {
+      int col_y = m + ey;
+      double ky[3][2];
+      for (int ty = 0; ty < ny; ++ty) {
+        ky[ty][0] = TAB(ty_tab[ty], p[1].idx, col_y, ey);
+        ky[ty][1] = TAB(ty_tab[ty], p[1].idx + 1, col_y, ey);
+      }
+      for (int l = -(ex - 1); l <= ex; ++l) {
+        double coef = it->coefs[(p[0].i + l - 1) + (p[1].i + m - 1) * s1];
+        int col_x = l + ex;
+        for (int tx = 0; tx < nx; ++tx) {
+          double kx0 = TAB(tx_tab[tx], p[0].idx, col_x, ex), kx1 = TAB(tx_tab[tx], p[0].idx + 1, col_x, ex);
+          for (int ty = 0; ty < ny; ++ty) {
+            s[tx][ty][0][0] += coef * kx0 * ky[ty][0];
+            s[tx][ty][1][0] += coef * kx1 * ky[ty][0];
+            s[tx][ty][0][1] += coef * kx0 * ky[ty][1];
+            s[tx][ty][1][1] += coef * kx1 * ky[ty][1];
+          }
+        }
+      }
+    }
+    double vy[3][2]; /* [y-type][y-bracket] after the Hermite along x */
+    for (int ty = 0; ty < ny; ++ty)
+      for (int by = 0; by < 2; ++by)
+        vy[ty][by] = nx == 3 ? quintic_hermite(p[0].t, s[0][ty][0][by], s[0][ty][1][by], s[1][ty][0][by], s[1][ty][1][by],
+                                               s[2][ty][0][by], s[2][ty][1][by], h_pre)
+                             : cubic_hermite(p[0].t, s[0][ty][0][by], s[0][ty][1][by], s[1][ty][0][by], s[1][ty][1][by], h_pre);
+    double result = ny == 3 ? quintic_hermite(p[1].t, vy[0][0], vy[0][1], vy[1][0], vy[1][1], vy[2][0], vy[2][1], h_pre)
+                            : cubic_hermite(p[1].t, vy[0][0], vy[0][1], vy[1][0], vy[1][1], h_pre);
+    double sc0 = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
+    double sc1 = jl_pow_int(-1.0 / it->h[1], it->deriv[1]);
+    if (it->perdim) {
+      double sc = 1.0;
+      sc *= sc0;
+      sc *= sc1;
+      *res = result * sc;
+    } else {
+      *res = result * sc0 * sc1;
+    }
+    return ORC_OK;
+  }
 
   if (it->ndim == 1) {
     const int e = tb->eqs[0];
@@ -524,7 +615,9 @@ int orc_itp_eval(const orc_itp *it, int64_t nq, const double *const *x, double *
     tb.eqs[d] = orc_eqs(it->kernel[d]);
     tb.kp[d] = orc_table(it->kernel[d], it->deriv[d]);
     tb.kd[d] = orc_table(it->kernel[d], it->deriv[d] + 1);
+    tb.ke[d] = it->subgrid[d] == ORC_SG_QUINTIC ? orc_table(it->kernel[d], it->deriv[d] + 2) : NULL;
     if (tb.eqs[d] < 0 || !tb.kp[d] || !tb.kd[d]) return ORC_EARG;
+    if (it->subgrid[d] == ORC_SG_QUINTIC && (!tb.ke[d] || it->ndim > 2)) return ORC_EARG;
   }
   int64_t bad = -1;
   int bad_rc = ORC_OK;
@@ -551,6 +644,14 @@ int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const doub
                  double *out, const double *const *knots_in, const double *const *knots_out,
                  const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
                  const int32_t *bc_right) {
+  int32_t sg[ORC_MAXDIM] = {0, 0, 0, 0};
+  return orc_resample_sg(ndim, n_in, n_out, values, out, knots_in, knots_out, kernel, deriv, bc_left, bc_right, sg);
+}
+
+int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const double *values,
+                    double *out, const double *const *knots_in, const double *const *knots_out,
+                    const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                    const int32_t *bc_right, const int32_t *subgrid) {
   if (ndim < 1 || ndim > ORC_MAXDIM) return ORC_EARG;
   int64_t cur_shape[ORC_MAXDIM];
   int64_t tot = 1;
@@ -562,7 +663,9 @@ int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const doub
     const int eqs_d = orc_eqs(kernel[d]);
     const double *kernel_pre = orc_table(kernel[d], deriv[d]);
     const double *kd1_pre = orc_table(kernel[d], deriv[d] + 1);
-    if (eqs_d < 0 || !kernel_pre || !kd1_pre) { free(current); return ORC_EARG; }
+    const int quintic = subgrid[d] == ORC_SG_QUINTIC;
+    const double *kd2_pre = quintic ? orc_table(kernel[d], deriv[d] + 2) : NULL;
+    if (eqs_d < 0 || !kernel_pre || !kd1_pre || (quintic && !kd2_pre)) { free(current); return ORC_EARG; }
     const int64_t nin = cur_shape[d], nout = n_out[d];
     const double h_d = knots_in[d][1] - knots_in[d][0];
     const int64_t n_coef = nin + 2 * (eqs_d - 1);
@@ -601,7 +704,7 @@ int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const doub
             if (idx < 1) idx = 1;
             if (idx > N_PRE - 1) idx = N_PRE - 1;
             double t = continuous_idx - (double)idx;
-            double sum_f0 = 0, sum_f1 = 0, sum_d0 = 0, sum_d1 = 0;
+            double sum_f0 = 0, sum_f1 = 0, sum_d0 = 0, sum_d1 = 0, sum_dd0 = 0, sum_dd1 = 0;
             for (int l = -(eqs_d - 1); l <= eqs_d; ++l) {
               double coef = coef_buf[i + l - 1];
               int col = l + eqs_d;
@@ -609,8 +712,13 @@ int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const doub
               sum_f1 += coef * TAB(kernel_pre, idx + 1, col, eqs_d);
               sum_d0 += coef * TAB(kd1_pre, idx, col, eqs_d);
               sum_d1 += coef * TAB(kd1_pre, idx + 1, col, eqs_d);
+              if (quintic) { /* :333-349 */
+                sum_dd0 += coef * TAB(kd2_pre, idx, col, eqs_d);
+                sum_dd1 += coef * TAB(kd2_pre, idx + 1, col, eqs_d);
+              }
             }
-            double v = cubic_hermite(t, sum_f0, sum_f1, sum_d0, sum_d1, h_pre);
+            double v = quintic ? quintic_hermite(t, sum_f0, sum_f1, sum_d0, sum_d1, sum_dd0, sum_dd1, h_pre)
+                               : cubic_hermite(t, sum_f0, sum_f1, sum_d0, sum_d1, h_pre);
             next[offset_out + (k - 1) * stride_out] = v * scale; /* :378-380 */
           }
         }

@@ -27,6 +27,8 @@ KERNEL_EQS = {"b5": 5, "b7": 6, "b9": 7, "b11": 8, "b13": 9, "a3": 2, "a4": 3, "
 MAX_SMOOTH_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6, "a3": 1, "a4": 1, "a5": 1, "a7": 1}  # constructor.jl:400-412
 MAX_SHIPPED_DERIVATIVE = {"b5": 2, "b7": 3, "b9": 4, "b11": 5, "b13": 5, "a3": 0, "a4": 0, "a5": 0, "a7": 0}  # get_precomputed...jl:33-40
 MIN_POLY_BC_POINTS = {"b5": 6, "b7": 8, "b9": 8, "b11": 8, "b13": 8, "a3": 4, "a4": 4, "a5": 4, "a7": 4}  # convolution_interpolation_function.jl:183-195
+MAX_TABLE_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6, "a3": 1, "a4": 1, "a5": 1, "a7": 1}  # shipped K^(d)
+SUBGRID_IDS = {"cubic": 0, "quintic": 1}
 BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
 
@@ -46,7 +48,8 @@ def build(force=False):
 class _Itp(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("cshape", C.c_int64 * 3), ("coefs", C.c_void_p),
                 ("knots", C.c_void_p * 3), ("h", C.c_double * 3), ("kernel", C.c_int32 * 3),
-                ("deriv", C.c_int32 * 3), ("extrap", C.c_int32), ("perdim", C.c_int32)]
+                ("deriv", C.c_int32 * 3), ("extrap", C.c_int32), ("perdim", C.c_int32),
+                ("subgrid", C.c_int32 * 3)]
 
 
 def lib():
@@ -60,6 +63,7 @@ def lib():
         L.orc_create_coefs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_resample.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 4
+        L.orc_resample_sg.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 5
         L.orc_smooth.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.orc_smooth_halfwidth.argtypes = [C.c_double]
         L.orc_ghost_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -137,6 +141,21 @@ def build_subgrids(kernels, derivs, subgrids):
     return tuple(out)
 
 
+def check_subgrids(kernels, derivs, subgrids, ndim, perdim, what):
+    """Which resolved (kernel, derivative, subgrid) combinations the shipped 101-row tables can serve:
+    :cubic needs K^(d), K^(d+1); :quintic also K^(d+2) and exists in 1-D / 2-D only (eager_1d.jl:117-145,
+    eager_2d.jl:214-311 for (quintic, quintic), perdim_2d.jl for the mixed pairs)."""
+    for d in range(ndim):
+        k, dv, sg = kernels[d], derivs[d], subgrids[d]
+        if dv < 0 or sg not in ("cubic", "quintic") or dv > MAX_SHIPPED_DERIVATIVE[k]:
+            raise OracleError(f"{what}: mode outside the oracle's scope: subgrid={subgrids} deriv={derivs}")
+        if sg == "quintic" and dv + 2 > MAX_TABLE_DERIVATIVE[k]:
+            raise OracleError(f"{what}: K^({dv + 2}) of :{k} is not shipped (quintic subgrid)")
+    if what == "interpolation" and "quintic" in subgrids:
+        if ndim > 2 or (ndim == 2 and not perdim and subgrids != ("quintic", "quintic")):
+            raise OracleError(f"{what}: subgrid {subgrids} has no evaluator on this path")
+
+
 def extend_vector(x, n_extra):
     """convolution/extend_vector.jl:10-18"""
     step_start = x[1] - x[0]
@@ -194,10 +213,8 @@ class Interpolant:
             fixed.append(b)
         self.bc = tuple(fixed)
         self.subgrid = build_subgrids(self.kernels, self.derivs, sg_req)
-        for d in range(nd):
-            if self.subgrid[d] != "cubic" or self.derivs[d] > MAX_SHIPPED_DERIVATIVE[self.kernels[d]] \
-                    or self.derivs[d] < 0:
-                raise OracleError(f"mode outside the oracle's scope: subgrid={self.subgrid} deriv={self.derivs}")
+        self.perdim = not (len(set(self.kernels)) == 1 and len(set(self.derivs)) == 1)
+        check_subgrids(self.kernels, self.derivs, self.subgrid, nd, self.perdim, "interpolation")
         self.eqs = tuple(KERNEL_EQS[k] for k in self.kernels)
         self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120
         self.coefs = create_coefs(values, self.h, self.kernels, self.bc)
@@ -213,6 +230,7 @@ class Interpolant:
             it.h[d] = self.h[d]
             it.kernel[d] = KERNEL_IDS[self.kernels[d]]
             it.deriv[d] = self.derivs[d]
+            it.subgrid[d] = SUBGRID_IDS[self.subgrid[d]]
         it.coefs = self.coefs.ctypes.data
         it.extrap = EXTRAP_IDS[extrap]
         it.perdim = int(self.perdim)
@@ -272,8 +290,7 @@ def convolution_resample(knots_in, knots_out, values, kernel=_UNSET, derivative=
     for d in range(nd):
         if derivs[d] < 0:
             raise OracleError("convolution_resample does not support antiderivatives")
-        if sgs[d] != "cubic" or derivs[d] > MAX_SHIPPED_DERIVATIVE[kernels[d]]:
-            raise OracleError(f"mode outside the oracle's scope: subgrid={sgs} deriv={derivs}")
+    check_subgrids(kernels, derivs, sgs, nd, True, "resample")
     n_in = (C.c_int64 * nd)(*v.shape)
     n_out = (C.c_int64 * nd)(*[len(k) for k in kout])
     out = np.zeros(tuple(len(k) for k in kout), order="F")
@@ -283,7 +300,8 @@ def convolution_resample(knots_in, knots_out, values, kernel=_UNSET, derivative=
     dv = (C.c_int32 * nd)(*derivs)
     bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
     br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
-    rc = lib().orc_resample(nd, n_in, n_out, v.ctypes.data, out.ctypes.data, kinp, koutp, kid, dv, bl, br)
+    sg = (C.c_int32 * nd)(*[SUBGRID_IDS[x] for x in sgs])
+    rc = lib().orc_resample_sg(nd, n_in, n_out, v.ctypes.data, out.ctypes.data, kinp, koutp, kid, dv, bl, br, sg)
     if rc:
         raise OracleError(f"orc_resample rc={rc}")
     return out

@@ -140,6 +140,30 @@ def test_a_series_kernels_1d_2d_3d(ci, oracle, kernel, bc):
             ci.convolution_interpolation(x, v, kernel=kernel, derivative=1)
 
 
+@pytest.mark.parametrize("kernel", ["b5", "b7", "b13"])
+def test_quintic_subgrid_1d_2d(ci, oracle, kernel):
+    """:quintic subgrid (K, K', K'' rows, quintic_hermite): 1-D, 2-D (quintic, quintic) on the eager path, the mixed
+    (quintic, cubic) / (cubic, quintic) pairs on the per-dim path, derivatives while K^(d+2) is shipped."""
+    rng = np.random.default_rng(42)
+    x = np.linspace(-2, 3, 77)
+    v = np.cos(1.7 * x) + 0.03 * rng.standard_normal(77)
+    q = rng.uniform(-2.3, 3.3, 40_000)
+    for d in (0, 1):
+        g = _compare(ci, oracle, x, v, (q,), kernel=kernel, derivative=d, subgrid="quintic", extrap="line")[2]
+        assert g.itp.subgrid == ("quintic",)
+    v2 = _field((40, 35), rng, noise=0.02)
+    k2 = (np.linspace(0, 1, 40), np.linspace(0, 1, 35))
+    q2 = rng.uniform(-0.05, 1.05, (2, 30_000))
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=kernel, subgrid="quintic", extrap="flat")
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=kernel, derivative=(1, 1), subgrid="quintic", extrap="line")
+    for sg in (("quintic", "cubic"), ("cubic", "quintic"), ("quintic", "quintic")):
+        _compare(ci, oracle, k2, v2, tuple(q2), kernel=(kernel, "b9"), derivative=(1, 0), subgrid=sg, extrap="line")
+    # quintic and cubic subgrids agree to the accuracy of the table interpolation, not to rounding
+    gq = ci.convolution_interpolation(x, v, kernel=kernel, subgrid="quintic").eval(np.clip(q, -2, 3))
+    gc = ci.convolution_interpolation(x, v, kernel=kernel).eval(np.clip(q, -2, 3))
+    assert 0 < np.abs(gq - gc).max() < 1e-8
+
+
 @pytest.mark.parametrize("kernel", ["b5", "b7", "b9", "b11", "b13"])
 def test_1d_2d_all_b_kernels(ci, oracle, kernel):
     rng = np.random.default_rng(13)

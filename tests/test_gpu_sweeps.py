@@ -82,6 +82,20 @@ def test_resample_1d_2d_kernels_and_bcs(ci, oracle, kernel, bc):
         _check_resample(ci, oracle, k3i, k3o, rng.random((40, 33, 36)), kernel=kernel)
 
 
+def test_resample_quintic_subgrid(ci, oracle):
+    rng = np.random.default_rng(26)
+    xi, xo = np.linspace(0, TWO_PI, 60), np.linspace(0, TWO_PI, 131)
+    v = np.sin(xi) + 0.01 * rng.standard_normal(60)
+    _check_resample(ci, oracle, xi, xo, v, kernel="b5", subgrid="quintic")
+    _check_resample(ci, oracle, xi, xo, v, kernel="b13", subgrid="quintic", derivative=2)
+    k2i = (np.linspace(0, 1, 37), np.linspace(-1, 1, 29))
+    k2o = (np.linspace(0, 1, 64), np.linspace(-1, 1, 45))
+    _check_resample(ci, oracle, k2i, k2o, rng.random((37, 29)), kernel=("b7", "b5"), subgrid=("quintic", "cubic"),
+                    derivative=(1, 0))
+    with pytest.raises(ci.UnsupportedModeError):
+        ci.convolution_resample(xi, xo, v, kernel="b5", subgrid="quintic", derivative=2)  # K^(4) of b5 not shipped
+
+
 def test_resample_shapes_downsampling_extrapolating_knots_and_4d(ci, oracle):
     rng = np.random.default_rng(22)
     # output knots outside the input range are silently clamped to the edge cell (convolution_resample.jl:322)

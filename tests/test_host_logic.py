@@ -115,7 +115,10 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, derivative=3)          # top derivative -> :linear subgrid
     with pytest.raises(U):
-        ci.convolution_interpolation(x, v, subgrid="quintic")
+        ci.convolution_interpolation(x, v, derivative=2, subgrid="quintic")   # K^(4) of :b5 is not shipped
+    with pytest.raises(U):
+        v2 = np.zeros((30, 30))
+        ci.convolution_interpolation((x, x), v2, subgrid=("quintic", "cubic"))  # eager 2-D: (quintic, quintic) only
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, lazy=True)
     with pytest.raises(U):
