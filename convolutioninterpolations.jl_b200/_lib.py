@@ -15,7 +15,7 @@ HOST, DEVICE = 0, 1
 KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4, "a3": 5, "a4": 6, "a5": 7, "a7": 8}
 BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
-SUBGRID_IDS = {"cubic": 0, "quintic": 1}
+SUBGRID_IDS = {"cubic": 0, "quintic": 1, "linear": 2}
 EVAL_MODES = {"auto": 0, "gather": 1, "binned": 2}
 
 # every symbol include/cib200.h declares (tests assert the library exports all of them)

@@ -161,10 +161,20 @@ def _build_subgrids(kernels, derivs, subgrids):
     return tuple(out)
 
 
+def _effective_subgrids(subgrids, ndim):
+    """What the evaluators do with a resolved subgrid tuple: in 3-D anything but all-cubic is evaluated with linear
+    blending on every axis (eager_3d.jl:139-176; perdim_3d.jl:161 "fallback to all linear")."""
+    if ndim == 3 and tuple(subgrids) != ("cubic",) * 3:
+        return ("linear",) * 3
+    return tuple(subgrids)
+
+
 def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
-    """Raise UnsupportedModeError for modes that stay on the reference's Julia path."""
+    """Raise UnsupportedModeError for modes that stay on the reference's Julia path.  With precompute = 101 the tables
+    of every subgrid are the shipped K^(d) (the generated ones of the :linear path are the same exact rationals rounded
+    once): :linear needs K^(d), :cubic also K^(d+1), :quintic also K^(d+2)."""
     if ndim > 3 and what == "convolution_interpolation":
-        raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N={ndim} uses the linear-subgrid N-D evaluators "
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N={ndim} uses the N-D evaluators "
                                    "(eager_nd.jl / perdim_nd.jl); not on the accelerated path")
     for d, (k, dv, sg) in enumerate(zip(kernels, derivs, subgrids)):
         if k not in KERNEL_IDS:
@@ -172,18 +182,18 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
                                        f"accelerated path ({ACCELERATED_KERNELS})")
         if dv < 0:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivatives (derivative=-1) stay on the reference path")
-        if sg not in ("cubic", "quintic"):
-            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: resolved subgrid {subgrids} needs the "
-                                       f":{sg} evaluators / generated tables; :cubic and :quintic are accelerated")
-        if dv > MAX_SHIPPED_DERIVATIVE[k]:
-            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative {dv} of :{k} is not a shipped table")
-        if sg == "quintic" and dv + 2 > MAX_TABLE_DERIVATIVE[k]:
-            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: the quintic subgrid needs K^({dv + 2}) of :{k}, "
-                                       "which is not a shipped table")
-    if what == "convolution_interpolation" and "quintic" in subgrids:
-        # eager_2d.jl handles (quintic, quintic) only; the mixed pairs exist on the per-dim path (perdim_2d.jl);
-        # N = 3 never resolves to quintic (_build_subgrids)
-        if ndim > 2 or (ndim == 2 and not perdim and tuple(subgrids) != ("quintic", "quintic")):
+        if sg not in ("cubic", "quintic", "linear"):
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: unknown subgrid {subgrids}")
+        need = dv + {"linear": 0, "cubic": 1, "quintic": 2}[sg]
+        if need > MAX_TABLE_DERIVATIVE[k]:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative {dv} of :{k} with the :{sg} subgrid needs "
+                                       f"K^({need}), which is not a shipped table")
+    if what == "convolution_interpolation":
+        # eager_2d.jl handles (linear, linear), (cubic, cubic), (quintic, quintic) only; the mixed pairs exist on the
+        # per-dim path (perdim_2d.jl); N = 3 never resolves to quintic (_build_subgrids)
+        if "quintic" in subgrids and ndim > 2:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: subgrid {tuple(subgrids)} has no 3-D evaluator")
+        if ndim == 2 and not perdim and len(set(subgrids)) != 1:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: subgrid {tuple(subgrids)} has no evaluator for "
                                        "one kernel and one derivative order on all axes (eager_2d.jl:91-311)")
 
@@ -231,6 +241,7 @@ class FastConvolutionInterpolation:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, "precompute != 101 needs generated tables (reference path)")
         # _build_kernel_sym (constructor.jl:378-398): HigherOrderKernel vs HigherOrderMixedKernel
         self.perdim = not (len(set(self.kernel)) == 1 and len(set(self.derivative)) == 1)
+        self.subgrid = _effective_subgrids(self.subgrid, nd)
         _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation", self.perdim)
         self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
         self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120

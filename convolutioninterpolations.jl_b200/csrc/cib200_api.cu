@@ -411,13 +411,22 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
       set_error("cib200_itp_create: unknown kernel id %d on axis %d", desc->kernel[d], d);
       return CIB200_EUNSUPPORTED;
     }
-    if (desc->deriv[d] < 0 || desc->deriv[d] > kernel_max_eval_deriv(desc->kernel[d])) {
-      set_error("cib200_itp_create: derivative %d on axis %d is outside the shipped cubic-subgrid tables", desc->deriv[d], d);
-      return CIB200_EUNSUPPORTED;
+    {
+      // tables the subgrid needs: K^(d) (linear), + K^(d+1) (cubic), + K^(d+2) (quintic)
+      const int sgd = desc->subgrid[d];
+      const int need = desc->deriv[d] + (sgd == CIB200_SG_LINEAR ? 0 : (sgd == CIB200_SG_QUINTIC ? 2 : 1));
+      if (desc->deriv[d] < 0 || need > kernel_max_deriv_table(desc->kernel[d])) {
+        set_error("cib200_itp_create: derivative %d on axis %d needs K^(%d), which is not a shipped table", desc->deriv[d], d, need);
+        return CIB200_EUNSUPPORTED;
+      }
     }
-    if (desc->subgrid[d] != CIB200_SG_CUBIC && desc->subgrid[d] != CIB200_SG_QUINTIC) {
+    if (desc->subgrid[d] < CIB200_SG_CUBIC || desc->subgrid[d] > CIB200_SG_LINEAR) {
       set_error("cib200_itp_create: unknown subgrid %d on axis %d", desc->subgrid[d], d);
       return CIB200_EINVAL;
+    }
+    if (nd == 3 && (desc->subgrid[d] == CIB200_SG_LINEAR) != (desc->subgrid[0] == CIB200_SG_LINEAR)) {
+      set_error("cib200_itp_create: a 3-D interpolant is all-cubic or all-linear (eager_3d.jl / perdim_3d.jl)");
+      return CIB200_EUNSUPPORTED;
     }
     if (desc->subgrid[d] == CIB200_SG_QUINTIC) {
       if (nd > 2) {
@@ -507,8 +516,10 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
   };
   for (int d = 0; d < nd; ++d) {
     p.tab_slot_k[d] = slot_of(h->kernel[d], h->deriv[d]);
-    p.tab_slot_d[d] = slot_of(h->kernel[d], h->deriv[d] + 1);
+    // linear axes read K only: their "derivative" table aliases K (its terms carry zero factors)
+    p.tab_slot_d[d] = desc->subgrid[d] == CIB200_SG_LINEAR ? p.tab_slot_k[d] : slot_of(h->kernel[d], h->deriv[d] + 1);
   }
+  p.prerange_pos = (nd == 2 && !desc->perdim && desc->subgrid[0] == CIB200_SG_LINEAR && desc->subgrid[1] == CIB200_SG_LINEAR) ? 1 : 0;
   for (int d = 0; d < 3; ++d) {
     p.subgrid[d] = d < nd ? desc->subgrid[d] : 0;
     p.tab_slot_e[d] = (d < nd && desc->subgrid[d] == CIB200_SG_QUINTIC) ? slot_of(h->kernel[d], h->deriv[d] + 2) : -1;
@@ -781,14 +792,9 @@ int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, con
   int sgv[CIB200_MAX_SWEEP_DIM];
   for (int d = 0; d < ndim; ++d) {
     sgv[d] = subgrid ? subgrid[d] : CIB200_SG_CUBIC;
-    if (sgv[d] != CIB200_SG_CUBIC && sgv[d] != CIB200_SG_QUINTIC) {
+    if (sgv[d] < CIB200_SG_CUBIC || sgv[d] > CIB200_SG_LINEAR) {
       set_error("cib200_resample: unknown subgrid %d on axis %d", sgv[d], d);
       return CIB200_EINVAL;
-    }
-    if (kernel_eqs(kernel[d]) >= 0 && sgv[d] == CIB200_SG_QUINTIC && deriv[d] >= 0 &&
-        deriv[d] + 2 > kernel_max_deriv_table(kernel[d])) {
-      set_error("cib200_resample: quintic subgrid on axis %d needs K^(%d), which is not a shipped table", d, deriv[d] + 2);
-      return CIB200_EUNSUPPORTED;
     }
     if (kernel_eqs(kernel[d]) < 0) {
       set_error("cib200_resample: unknown kernel id %d on axis %d", kernel[d], d);
@@ -798,9 +804,12 @@ int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, con
       set_error("convolution_resample does not support antiderivatives (derivative=-1)");
       return CIB200_EINVAL;
     }
-    if (deriv[d] > kernel_max_eval_deriv(kernel[d])) {
-      set_error("cib200_resample: derivative %d on axis %d needs the linear-subgrid path", deriv[d], d);
-      return CIB200_EUNSUPPORTED;
+    {
+      const int need = deriv[d] + (sgv[d] == CIB200_SG_LINEAR ? 0 : (sgv[d] == CIB200_SG_QUINTIC ? 2 : 1));
+      if (need > kernel_max_deriv_table(kernel[d])) {
+        set_error("cib200_resample: derivative %d on axis %d needs K^(%d), which is not a shipped table", deriv[d], d, need);
+        return CIB200_EUNSUPPORTED;
+      }
     }
     if (n_in[d] < 3 || n_out[d] < 1 || !knots_in[d] || !knots_out[d] || bc_left[d] < 0 || bc_left[d] > 3 ||
         bc_right[d] < 0 || bc_right[d] > 3) {

@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
-          const Hermite hb = hermite_basis(pa[d].t);
+          const Hermite hb = p.subgrid[d] == CIB200_SG_LINEAR ? linear_basis(pa[d].t) : hermite_basis(pa[d].t);
           double2 *dst = (double2 *)(hbs + (lane * 3 + d) * 4);
           dst[0] = make_double2(hb.h00, hb.h01);
           dst[1] = make_double2(hb.h10, hb.h11);
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(384, 1)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], kt + 32 * d - org[d], pa[d]);
-          const Hermite hb = hermite_basis(pa[d].t);
+          const Hermite hb = p.subgrid[d] == CIB200_SG_LINEAR ? linear_basis(pa[d].t) : hermite_basis(pa[d].t);
           double2 *dst = (double2 *)(hbs + (lane * 3 + d) * 4);
           dst[0] = make_double2(hb.h00, hb.h01);
           dst[1] = make_double2(hb.h10, hb.h11);

@@ -34,6 +34,35 @@ __device__ __forceinline__ bool locate_from_knot(double x, double knot0, double 
   return ok;
 }
 
+// (linear, linear) on the single-kernel 2-D path (eager_2d.jl:93-107): the table row comes from
+// floor(diff_right (n_pre - 1)) + 1 and t from the stored pre_range values, pre_range[r] = Float64((r-1)//(n_pre-1))
+__device__ __forceinline__ bool locate_prerange(double x, double knot0, double h, int eqs, int nk,
+                                                const double *__restrict__ knots, AxisPos &p) {
+  double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x, knot0), h), 1.0);
+  bool ok = fabs(i_float) < 9.0e18;
+  long long i = ok ? (long long)floor(i_float) : (long long)eqs;
+  i = i < eqs ? eqs : i;
+  i = i > nk - eqs ? nk - eqs : i;
+  const double knot_i = knots[i - 1];
+  const double diff_right = __dsub_rn(1.0, __ddiv_rn(__dsub_rn(x, knot_i), h));
+  const double f = __dmul_rn(diff_right, (double)(CIB_N_PRE - 1));
+  ok = ok && (fabs(f) < 9.0e18);
+  int idx = ok ? (int)floor(f) + 1 : 1;
+  idx = idx < 1 ? 1 : idx;
+  idx = idx > CIB_N_PRE - 1 ? CIB_N_PRE - 1 : idx;
+  const double r0 = __ddiv_rn((double)(idx - 1), (double)(CIB_N_PRE - 1)), r1 = __ddiv_rn((double)idx, (double)(CIB_N_PRE - 1));
+  p.base = (int)(i - eqs);
+  p.row = idx - 1;
+  p.t = __ddiv_rn(__dsub_rn(diff_right, r0), __dsub_rn(r1, r0));
+  return ok;
+}
+
+// position of x on axis d in the variant the interpolant's evaluator uses
+__device__ __forceinline__ bool locate_axis(const ItpParams &p, int d, double x, AxisPos &pos) {
+  if (p.prerange_pos) return locate_prerange(x, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pos);
+  return locate_from_knot(x, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pos);
+}
+
 // resample variant: the cell's left knot is COMPUTED (convolution_resample.jl:322-326)
 __device__ __forceinline__ void locate_computed(double x, double x_expanded_1, double h, int eqs,
                                                 long long n_coef, AxisPos &p) {
@@ -69,6 +98,16 @@ __device__ __forceinline__ Hermite hermite_basis(double t) {
   b.h11 = h_pre * (t2 * (t - 1.0));
   b.h20 = 0.0;
   b.h21 = 0.0;
+  return b;
+}
+
+// linear subgrid: (1 - t) K[row] + t K[row+1] (eager_1d.jl:88, eager_3d.jl:167-171, perdim_*.jl) expressed with the same
+// four-term weight formula: the derivative-table terms get zero factors (the kernels then read K instead of K')
+__device__ __forceinline__ Hermite linear_basis(double t) {
+  Hermite b;
+  b.h00 = 1.0 - t;
+  b.h01 = t;
+  b.h10 = b.h11 = b.h20 = b.h21 = 0.0;
   return b;
 }
 

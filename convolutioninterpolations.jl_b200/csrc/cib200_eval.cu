@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256, 2) eval_warp3d_kernel(ItpParams p, Coords
           row[d] = __shfl_sync(0xffffffffu, t == 0 ? pa[d].row : pb[d].row, j);
           tt[d] = __shfl_sync(0xffffffffu, t == 0 ? pa[d].t : pb[d].t, j);
         }
-        const double wx = warp_weights<E>(wyz, wax, tk, td, row, tt, lane);
+        const double wx = warp_weights<E>(wyz, wax, tk, td, row, tt, lane, p.subgrid[0] == CIB200_SG_LINEAR);
         const T *ptr = coefs + base[0] + l + ((long long)base[1] + g) * s1 + (long long)base[2] * s2;
         const double total = warp_stencil<E>(ptr, s1, s2, wyz, wx, lane, [](const T *a) { return ldg_as_double(a); });
         if (lane == j) {

@@ -29,7 +29,7 @@ __device__ __forceinline__ Plan make_plan(const ItpParams &p, const double *x, A
   if (inside) {
 #pragma unroll
     for (int d = 0; d < NDIM; ++d)
-      ok &= locate_from_knot(x[d], p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+      ok &= locate_axis(p, d, x[d], pa[d]);
     pl.ntask = 1;
   } else if (p.extrap == CIB200_THROW) {
     pl.err = 1;
@@ -47,14 +47,14 @@ __device__ __forceinline__ Plan make_plan(const ItpParams &p, const double *x, A
     }
 #pragma unroll
     for (int d = 0; d < NDIM; ++d)
-      ok &= locate_from_knot(cl[d], p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+      ok &= locate_axis(p, d, cl[d], pa[d]);
     pl.ntask = 1;
     if (p.extrap == CIB200_LINE && !(dist_sq < 2.220446049250313e-16)) {
       double dist = __dsqrt_rn(dist_sq);
 #pragma unroll
       for (int d = 0; d < NDIM; ++d) {
         double xin = __dsub_rn(cl[d], __ddiv_rn(__dmul_rn(p.eps_line, dx[d]), dist));
-        ok &= locate_from_knot(xin, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pb[d]);
+        ok &= locate_axis(p, d, xin, pb[d]);
       }
       pl.ntask = 2;
       pl.dist = dist;
@@ -110,15 +110,17 @@ __device__ __forceinline__ void decode_coords(const Coords &c, long long q, long
 // per-axis Hermite basis / blended weight honouring the axis' subgrid (quintic exists for NDIM <= 2 only)
 template <int NDIM>
 __device__ __forceinline__ Hermite axis_basis(const ItpParams &p, int d, double t) {
-  if (NDIM <= 2 && p.subgrid[d]) return hermite_basis_quintic(t);
+  if (p.subgrid[d] == CIB200_SG_LINEAR) return linear_basis(t);
+  if (NDIM <= 2 && p.subgrid[d] == CIB200_SG_QUINTIC) return hermite_basis_quintic(t);
   return hermite_basis(t);
 }
 template <int NDIM>
 __device__ __forceinline__ double axis_weight(const ItpParams &p, int d, const Hermite &hb, const double *tk,
                                               const double *td, const double *te, int row, int col, int w) {
-  if (NDIM <= 2 && p.subgrid[d]) return blended_weight_quintic(hb, tk, td, te, row, col, w);
-  return blended_weight(hb, tk, td, row, col, w);
+  if (NDIM <= 2 && p.subgrid[d] == CIB200_SG_QUINTIC) return blended_weight_quintic(hb, tk, td, te, row, col, w);
+  return blended_weight(hb, tk, td, row, col, w);  // linear axes: td aliases tk, its terms carry zero factors
 }
+
 
 template <typename T, int NDIM, int E>
 __device__ __forceinline__ double core_thread(const ItpParams &p, const double *const *tk, const double *const *td,
@@ -239,14 +241,14 @@ struct WarpGeom {
 // fills wax[3][W] (Hermite-blended per-axis weights) and wyz[m + W n] = wy[m] wz[n]; returns wx of this lane
 template <int E>
 __device__ __forceinline__ double warp_weights(double *wyz, double *wax, const double *const *tk, const double *const *td,
-                                               const int *row, const double *tt, int lane) {
+                                               const int *row, const double *tt, int lane, bool linear = false) {
   using GM = WarpGeom<E>;
   constexpr int W = GM::W;
   for (int idx = lane; idx < 3 * W; idx += 32) {
     const int a = idx / W, col = idx - a * W;
     const double ta = a == 0 ? tt[0] : (a == 1 ? tt[1] : tt[2]);
     const int ra = a == 0 ? row[0] : (a == 1 ? row[1] : row[2]);
-    Hermite hb = hermite_basis(ta);
+    Hermite hb = linear ? linear_basis(ta) : hermite_basis(ta);
     wax[idx] = blended_weight(hb, a == 0 ? tk[0] : (a == 1 ? tk[1] : tk[2]), a == 0 ? td[0] : (a == 1 ? td[1] : td[2]),
                               ra, col, W);
   }

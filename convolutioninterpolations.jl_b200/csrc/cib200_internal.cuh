@@ -48,7 +48,8 @@ struct ItpParams {
   int tab_slot_k[3];       // index of the distinct table in the packed smem image
   int tab_slot_d[3];
   int tab_slot_e[3];       // K^(d+2), quintic subgrid only (-1 otherwise)
-  int subgrid[3];          // 0 cubic, 1 quintic (1-D / 2-D interpolants only)
+  int subgrid[3];          // cib200_subgrid: 0 cubic, 1 quintic (1-D / 2-D only), 2 linear
+  int prerange_pos;        // 1: eager_2d.jl (linear, linear) position arithmetic (row / t from the stored pre_range)
   int n_tab_slots;
   int tab_slot_eqs[9];     // eqs of each distinct table
   const double *tab_slot_ptr[9];

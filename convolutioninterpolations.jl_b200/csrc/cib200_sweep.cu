@@ -56,14 +56,15 @@ struct SweepParams {
 // ---- per-output-knot weights: convolution_resample.jl:320-361 minus the data ------------------
 __global__ void resample_weights_kernel(const double *__restrict__ knots_out, long long n_out, double x_expanded_1,
                                         double h, int eqs, long long n_coef, const double *__restrict__ tk,
-                                        const double *__restrict__ td, const double *__restrict__ te,
+                                        const double *__restrict__ td, const double *__restrict__ te, int linear,
                                         double *__restrict__ W, double *__restrict__ Wk, int *__restrict__ base) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_out) return;
   AxisPos p;
   locate_computed(knots_out[k], x_expanded_1, h, eqs, n_coef, p);
   base[k] = p.base;
-  const Hermite hb = te ? hermite_basis_quintic(p.t) : hermite_basis(p.t);  // te != nullptr: quintic subgrid (:333-349)
+  // te != nullptr: quintic subgrid (:333-349); linear (:363-373): td aliases tk, its terms carry zero factors
+  const Hermite hb = te ? hermite_basis_quintic(p.t) : (linear ? linear_basis(p.t) : hermite_basis(p.t));
   const int w = 2 * eqs;
   for (int l = 0; l < w; ++l) {
     const double v = te ? blended_weight_quintic(hb, tk, td, te, p.row, l, w) : blended_weight(hb, tk, td, p.row, l, w);
@@ -1206,14 +1207,15 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     if ((rc = tmp.alloc((void **)&d_Wk, sizeof(double) * (size_t)nout * taps))) return rc;
     if ((rc = tmp.alloc((void **)&d_base, sizeof(int) * (size_t)nout))) return rc;
     CIB_CUDA(cudaMemcpyAsync(d_tk, host_table(kernel[d], deriv[d]), tab_bytes, cudaMemcpyHostToDevice, st));
-    CIB_CUDA(cudaMemcpyAsync(d_td, host_table(kernel[d], deriv[d] + 1), tab_bytes, cudaMemcpyHostToDevice, st));
+    const int linear = subgrid[d] == CIB200_SG_LINEAR;
+    CIB_CUDA(cudaMemcpyAsync(d_td, host_table(kernel[d], deriv[d] + (linear ? 0 : 1)), tab_bytes, cudaMemcpyHostToDevice, st));
     if (subgrid[d] == CIB200_SG_QUINTIC) {
       if ((rc = tmp.alloc((void **)&d_te, tab_bytes))) return rc;
       CIB_CUDA(cudaMemcpyAsync(d_te, host_table(kernel[d], deriv[d] + 2), tab_bytes, cudaMemcpyHostToDevice, st));
     }
     CIB_CUDA(cudaMemcpyAsync(d_ko, knots_out[d], sizeof(double) * (size_t)nout, cudaMemcpyHostToDevice, st));
     resample_weights_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(d_ko, nout, x_expanded_1, h, eqs, n_coef,
-                                                                           d_tk, d_td, d_te, d_W, d_Wk, d_base);
+                                                                           d_tk, d_td, d_te, linear, d_W, d_Wk, d_base);
     CIB_LAUNCHED();
     CIB_CUDA(cudaGetLastError());
 

@@ -51,9 +51,10 @@ typedef enum {
 } cib200_kernel;
 typedef enum { CIB200_BC_DETECT = 0, CIB200_BC_POLY = 1, CIB200_BC_LINEAR = 2, CIB200_BC_QUADRATIC = 3 } cib200_bc;
 typedef enum { CIB200_THROW = 0, CIB200_FLAT = 1, CIB200_LINE = 2 } cib200_extrap;
-/* subgrid = how the 101-row tables are interpolated between rows: cubic Hermite (K, K') or quintic Hermite (K, K', K'')
- * - cubic_hermite_interpolation.jl:15-28, quintic_hermite_interpolation.jl:16-37 */
-typedef enum { CIB200_SG_CUBIC = 0, CIB200_SG_QUINTIC = 1 } cib200_subgrid;
+/* subgrid = how the 101-row tables are interpolated between rows: cubic Hermite (K, K'), quintic Hermite (K, K', K'')
+ * - cubic_hermite_interpolation.jl:15-28, quintic_hermite_interpolation.jl:16-37 - or linearly (K only: the path of
+ * top derivatives and of every non-all-cubic 3-D interpolant; precompute = 101 only, i.e. the shipped tables) */
+typedef enum { CIB200_SG_CUBIC = 0, CIB200_SG_QUINTIC = 1, CIB200_SG_LINEAR = 2 } cib200_subgrid;
 
 /* evaluation strategies of cib200_itp_eval (3-D only; 1-D/2-D always use the direct kernel) */
 typedef enum {
@@ -78,7 +79,8 @@ typedef struct cib200_itp_desc {
   int32_t perdim;                        /* 0: HigherOrderKernel evaluators, 1: HigherOrderMixedKernel
                                             (only changes how the final scale is associated)        */
   int32_t subgrid[CIB200_MAX_ITP_DIM];    /* cib200_subgrid per axis (itp.subgrid, resolved by _build_subgrids);
-                                            quintic: ndim <= 2 and K^(deriv+2) shipped              */
+                                            quintic: ndim <= 2 and K^(deriv+2) shipped; linear: K^(deriv)
+                                            shipped; ndim == 3: all cubic or all linear                */
 } cib200_itp_desc;
 
 typedef struct cib200_itp cib200_itp; /* opaque */

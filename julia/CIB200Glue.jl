@@ -13,7 +13,7 @@ using ..ConvolutionInterpolations: ConvolutionExtrapolation, FastConvolutionInte
 const LIB = get(ENV, "CIB200_LIB", "libcib200.so")
 const KERNEL_ID = Dict(:b5 => 0, :b7 => 1, :b9 => 2, :b11 => 3, :b13 => 4, :a3 => 5, :a4 => 6, :a5 => 7, :a7 => 8)
 const BC_ID = Dict(:detect => 0, :poly => 1, :linear => 2, :quadratic => 3)
-const SUBGRID_ID = Dict(:cubic => 0, :quintic => 1)
+const SUBGRID_ID = Dict(:cubic => 0, :quintic => 1, :linear => 2)
 const MAX_TABLE = Dict(:b5 => 3, :b7 => 4, :b9 => 5, :b11 => 6, :b13 => 6, :a3 => 1, :a4 => 1, :a5 => 1, :a7 => 1)  # shipped K^(d)
 const MAX_DERIV = Dict(:b5 => 2, :b7 => 3, :b9 => 4, :b11 => 5, :b13 => 5, :a3 => 0, :a4 => 0, :a5 => 0, :a7 => 0)   # _max_shipped_derivative
 
@@ -58,18 +58,20 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     itp.lazy === Val{false}() || return false
     itp.derivative_order isa DerivativeOrder || return false
     dv = derivative_tuple(itp)
-    all(d -> 0 <= dv[d] <= MAX_DERIV[ks[d]], 1:N) || return false
-    sg = subgrid_tuple(itp)
-    all(s -> s === :cubic || s === :quintic, sg) || return false
-    # :quintic needs K^(d+2) among the shipped tables; evaluators: eager_1d.jl:117-145, eager_2d.jl:214-311
-    # ((quintic, quintic) only), perdim_2d.jl (mixed pairs); never in 3-D (_build_subgrids)
-    all(d -> sg[d] === :cubic || dv[d] + 2 <= MAX_TABLE[ks[d]], 1:N) || return false
-    if any(==(:quintic), sg)
-        N <= 2 || return false
-        (N == 1 || itp.kernel_sym isa HigherOrderMixedKernel || all(==(:quintic), sg)) || return false
-    end
+    all(d -> length(itp.pre_range[d]) == 101, 1:N) || return false   # precompute = 101: the shipped tables
+    sg = effective_subgrids(subgrid_tuple(itp), N)
+    all(s -> haskey(SUBGRID_ID, s), sg) || return false
+    # tables a subgrid needs: K^(d) (:linear), + K^(d+1) (:cubic), + K^(d+2) (:quintic)
+    need(d) = dv[d] + (sg[d] === :linear ? 0 : sg[d] === :cubic ? 1 : 2)
+    all(d -> dv[d] >= 0 && need(d) <= MAX_TABLE[ks[d]], 1:N) || return false
+    # evaluators: eager_2d.jl has (linear, linear), (cubic, cubic), (quintic, quintic); the mixed pairs exist on the
+    # per-dim path (perdim_2d.jl); :quintic never in 3-D (_build_subgrids)
+    any(==(:quintic), sg) && N > 2 && return false
+    N == 2 && !(itp.kernel_sym isa HigherOrderMixedKernel) && !allequal(sg) && return false
     return true
 end
+# in 3-D anything but all-cubic is evaluated with linear blending on every axis (eager_3d.jl:139-176, perdim_3d.jl:161)
+effective_subgrids(sg, N) = (N == 3 && any(!=(:cubic), sg)) ? ntuple(_ -> :linear, 3) : sg
 subgrid_tuple(itp) = typeof(itp.subgrid).parameters[1]               # Val{SG}
 derivative_tuple(itp) = typeof(itp.derivative_order).parameters[1]   # DerivativeOrder{DO} (struct_constructors.jl:182)
 
@@ -97,7 +99,7 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
                                pad3(Float64.(itp.h), 1.0), pad3(ntuple(d -> Int32(KERNEL_ID[ks[d]]), N), Int32(0)),
                                pad3(ntuple(d -> Int32(dv[d]), N), Int32(0)), extrap_id(etp.et),
                                Int32(itp.kernel_sym isa HigherOrderMixedKernel),
-                               pad3(ntuple(d -> Int32(SUBGRID_ID[subgrid_tuple(itp)[d]]), N), Int32(0))))
+                               pad3(ntuple(d -> Int32(SUBGRID_ID[effective_subgrids(subgrid_tuple(itp), N)[d]]), N), Int32(0))))
             out = Ref{Ptr{Cvoid}}(C_NULL)
             GC.@preserve itp knots64 check(ccall((:cib200_itp_create, LIB), Int32,
                                                  (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
@@ -140,9 +142,9 @@ end
 # ---- convolution_resample_internal (convolution_resample.jl:240-386) ---------------------------------
 function resample_accelerated(values::AbstractArray{T,N}, kernels, derivatives, subgrids, precompute) where {T,N}
     (T === Float64 || T === Float32) && N <= 8 && all(k -> haskey(KERNEL_ID, k), kernels) &&
-        all(s -> s === :cubic || s === :quintic, subgrids) && all(==(101), precompute) &&
-        all(d -> 0 <= derivatives[d] <= MAX_DERIV[kernels[d]], 1:N) &&
-        all(d -> subgrids[d] === :cubic || derivatives[d] + 2 <= MAX_TABLE[kernels[d]], 1:N)
+        all(s -> haskey(SUBGRID_ID, s), subgrids) && all(==(101), precompute) &&
+        all(d -> derivatives[d] >= 0 && derivatives[d] + (subgrids[d] === :linear ? 0 : subgrids[d] === :cubic ? 1 : 2) <=
+                 MAX_TABLE[kernels[d]], 1:N)
 end
 
 function cib200_resample(knots_in::NTuple{N}, knots_out::NTuple{N}, values::Array{T,N},

@@ -365,6 +365,29 @@ static inline int locate(double x, const double *knots, int64_t nk, double h, in
   return 0;
 }
 
+/* the position variant of eager_2d.jl:93-107 ((linear, linear) on the single-kernel path; eager_nd.jl:97-115 uses the
+ * same): table row from floor(diff_right * (n_pre - 1)) + 1 and t from the stored pre_range values,
+ * pre_range[r] = Float64((r-1)//(n_pre-1)) (pre_range.jl) */
+static inline int locate_prerange(double x, const double *knots, int64_t nk, double h, int eqs, axis_pos *p) {
+  double i_float = (x - knots[0]) / h + 1.0;
+  if (!(fabs(i_float) < 9.0e18)) return 1;
+  int64_t i = (int64_t)floor(i_float);
+  if (i < eqs) i = eqs;
+  if (i > nk - eqs) i = nk - eqs;
+  double diff_left = (x - knots[i - 1]) / h;
+  double diff_right = 1.0 - diff_left;
+  double f = diff_right * (double)(N_PRE - 1);
+  if (!(fabs(f) < 9.0e18)) return 1;
+  int64_t idx = (int64_t)floor(f) + 1;
+  if (idx < 1) idx = 1;
+  if (idx > N_PRE - 1) idx = N_PRE - 1;
+  double r0 = (double)(idx - 1) / (double)(N_PRE - 1), r1 = (double)idx / (double)(N_PRE - 1);
+  p->i = i;
+  p->idx = idx;
+  p->t = (diff_right - r0) / (r1 - r0);
+  return 0;
+}
+
 typedef struct {
   const double *kp[3];
   const double *kd[3];
@@ -379,8 +402,61 @@ typedef struct {
 static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, double *res) {
   const double h_pre = 1.0 / (double)(N_PRE - 1);
   axis_pos p[3];
+  const int prerange = it->ndim == 2 && !it->perdim && it->subgrid[0] == ORC_SG_LINEAR && it->subgrid[1] == ORC_SG_LINEAR;
   for (int d = 0; d < it->ndim; ++d)
-    if (locate(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d])) return ORC_ENAN;
+    if (prerange ? locate_prerange(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d])
+                 : locate(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d]))
+      return ORC_ENAN;
+
+  if (it->ndim == 1 && it->subgrid[0] == ORC_SG_LINEAR) { /* eager_1d.jl:73-90 */
+    const int e = tb->eqs[0];
+    double result_lower = 0, result_upper = 0;
+    for (int j = -(e - 1); j <= e; ++j) {
+      double coef = it->coefs[p[0].i + j - 1];
+      result_lower += coef * TAB(tb->kp[0], p[0].idx, j + e, e);
+      result_upper += coef * TAB(tb->kp[0], p[0].idx + 1, j + e, e);
+    }
+    double result = (1.0 - p[0].t) * result_lower + p[0].t * result_upper;
+    double scale = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
+    *res = result * scale;
+    return ORC_OK;
+  }
+
+  if (it->ndim == 3 && it->subgrid[0] == ORC_SG_LINEAR) {
+    /* eager_3d.jl:139-176 (linear, linear, linear) / perdim_3d.jl:161-194 ("fallback to all linear"): 8 accumulators
+     * r[bx][by][bz] += ((coef * kx) * ky) * kz in the n -> m -> l loop order, trilinear blend (@fastmath there) */
+    const int ex = tb->eqs[0], ey = tb->eqs[1], ez = tb->eqs[2];
+    const int64_t s1 = it->cshape[0], s2 = it->cshape[0] * it->cshape[1];
+    double r[2][2][2];
+    memset(r, 0, sizeof r);
+    for (int n = -(ez - 1); n <= ez; ++n) {
+      double kz[2] = {TAB(tb->kp[2], p[2].idx, n + ez, ez), TAB(tb->kp[2], p[2].idx + 1, n + ez, ez)};
+      for (int m = -(ey - 1); m <= ey; ++m) {
+        double ky[2] = {TAB(tb->kp[1], p[1].idx, m + ey, ey), TAB(tb->kp[1], p[1].idx + 1, m + ey, ey)};
+        for (int l = -(ex - 1); l <= ex; ++l) {
+          double coef = it->coefs[(p[0].i + l - 1) + (p[1].i + m - 1) * s1 + (p[2].i + n - 1) * s2];
+          double kx[2] = {TAB(tb->kp[0], p[0].idx, l + ex, ex), TAB(tb->kp[0], p[0].idx + 1, l + ex, ex)};
+          for (int bz = 0; bz < 2; ++bz)
+            for (int by = 0; by < 2; ++by)
+              for (int bx = 0; bx < 2; ++bx) r[bx][by][bz] += coef * kx[bx] * ky[by] * kz[bz];
+        }
+      }
+    }
+    double tx = p[0].t, ty = p[1].t, tz = p[2].t, ox = 1.0 - tx, oy = 1.0 - ty, oz = 1.0 - tz;
+    double result = ox * oy * oz * r[0][0][0] + tx * oy * oz * r[1][0][0] + ox * ty * oz * r[0][1][0] +
+                    tx * ty * oz * r[1][1][0] + ox * oy * tz * r[0][0][1] + tx * oy * tz * r[1][0][1] +
+                    ox * ty * tz * r[0][1][1] + tx * ty * tz * r[1][1][1];
+    double sc[3];
+    for (int d = 0; d < 3; ++d) sc[d] = jl_pow_int(-1.0 / it->h[d], it->deriv[d]);
+    if (it->perdim) {
+      double s = 1.0;
+      for (int d = 0; d < 3; ++d) s *= sc[d];
+      *res = result * s;
+    } else {
+      *res = result * (sc[0] * sc[1] * sc[2]); /* result * prod(...) */
+    }
+    return ORC_OK;
+  }
 
   if (it->ndim == 1 && it->subgrid[0] == ORC_SG_QUINTIC) { /* eager_1d.jl:117-145 */
     const int e = tb->eqs[0];
@@ -401,13 +477,15 @@ static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, doub
     return ORC_OK;
   }
 
-  if (it->ndim == 2 && (it->subgrid[0] == ORC_SG_QUINTIC || it->subgrid[1] == ORC_SG_QUINTIC)) {
+  if (it->ndim == 2 && (it->subgrid[0] != ORC_SG_CUBIC || it->subgrid[1] != ORC_SG_CUBIC)) {
     /* eager_2d.jl:214-311 (quintic, quintic); perdim_2d.jl (quintic, cubic) :218-258, (cubic, quintic), (quintic,
      * quintic): accumulators s[x-type][y-type][x-bracket][y-bracket], type 0 = f, 1 = d, 2 = e, each receiving
      * (coef * kx) * ky in the reference's m -> l loop order; Hermite along x first, then along y */
     const int ex = tb->eqs[0], ey = tb->eqs[1];
     const int64_t s1 = it->cshape[0];
-    const int nx = it->subgrid[0] == ORC_SG_QUINTIC ? 3 : 2, ny = it->subgrid[1] == ORC_SG_QUINTIC ? 3 : 2;
+    /* linear axes (perdim_2d.jl:57-76, :78-113, :115-147 ..., eager_2d.jl:91-134): one type (f), linear blend */
+    const int nx = it->subgrid[0] == ORC_SG_QUINTIC ? 3 : (it->subgrid[0] == ORC_SG_LINEAR ? 1 : 2);
+    const int ny = it->subgrid[1] == ORC_SG_QUINTIC ? 3 : (it->subgrid[1] == ORC_SG_LINEAR ? 1 : 2);
     const double *tx_tab[3] = {tb->kp[0], tb->kd[0], tb->ke[0]};
     const double *ty_tab[3] = {tb->kp[1], tb->kd[1], tb->ke[1]};
     double s[3][3][2][2];
@@ -438,9 +516,11 @@ static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, doub
       for (int by = 0; by < 2; ++by)
         vy[ty][by] = nx == 3 ? quintic_hermite(p[0].t, s[0][ty][0][by], s[0][ty][1][by], s[1][ty][0][by], s[1][ty][1][by],
                                                s[2][ty][0][by], s[2][ty][1][by], h_pre)
-                             : cubic_hermite(p[0].t, s[0][ty][0][by], s[0][ty][1][by], s[1][ty][0][by], s[1][ty][1][by], h_pre);
+                   : nx == 2 ? cubic_hermite(p[0].t, s[0][ty][0][by], s[0][ty][1][by], s[1][ty][0][by], s[1][ty][1][by], h_pre)
+                             : (1.0 - p[0].t) * s[0][ty][0][by] + p[0].t * s[0][ty][1][by];
     double result = ny == 3 ? quintic_hermite(p[1].t, vy[0][0], vy[0][1], vy[1][0], vy[1][1], vy[2][0], vy[2][1], h_pre)
-                            : cubic_hermite(p[1].t, vy[0][0], vy[0][1], vy[1][0], vy[1][1], h_pre);
+                  : ny == 2 ? cubic_hermite(p[1].t, vy[0][0], vy[0][1], vy[1][0], vy[1][1], h_pre)
+                            : (1.0 - p[1].t) * vy[0][0] + p[1].t * vy[0][1];
     double sc0 = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
     double sc1 = jl_pow_int(-1.0 / it->h[1], it->deriv[1]);
     if (it->perdim) {
@@ -616,8 +696,9 @@ int orc_itp_eval(const orc_itp *it, int64_t nq, const double *const *x, double *
     tb.kp[d] = orc_table(it->kernel[d], it->deriv[d]);
     tb.kd[d] = orc_table(it->kernel[d], it->deriv[d] + 1);
     tb.ke[d] = it->subgrid[d] == ORC_SG_QUINTIC ? orc_table(it->kernel[d], it->deriv[d] + 2) : NULL;
-    if (tb.eqs[d] < 0 || !tb.kp[d] || !tb.kd[d]) return ORC_EARG;
+    if (tb.eqs[d] < 0 || !tb.kp[d] || (!tb.kd[d] && it->subgrid[d] != ORC_SG_LINEAR)) return ORC_EARG;
     if (it->subgrid[d] == ORC_SG_QUINTIC && (!tb.ke[d] || it->ndim > 2)) return ORC_EARG;
+    if (it->ndim == 3 && (it->subgrid[d] == ORC_SG_LINEAR) != (it->subgrid[0] == ORC_SG_LINEAR)) return ORC_EARG;
   }
   int64_t bad = -1;
   int bad_rc = ORC_OK;
@@ -665,7 +746,8 @@ int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const d
     const double *kd1_pre = orc_table(kernel[d], deriv[d] + 1);
     const int quintic = subgrid[d] == ORC_SG_QUINTIC;
     const double *kd2_pre = quintic ? orc_table(kernel[d], deriv[d] + 2) : NULL;
-    if (eqs_d < 0 || !kernel_pre || !kd1_pre || (quintic && !kd2_pre)) { free(current); return ORC_EARG; }
+    const int linear = subgrid[d] == ORC_SG_LINEAR;
+    if (eqs_d < 0 || !kernel_pre || (!kd1_pre && !linear) || (quintic && !kd2_pre)) { free(current); return ORC_EARG; }
     const int64_t nin = cur_shape[d], nout = n_out[d];
     const double h_d = knots_in[d][1] - knots_in[d][0];
     const int64_t n_coef = nin + 2 * (eqs_d - 1);
@@ -710,6 +792,7 @@ int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const d
               int col = l + eqs_d;
               sum_f0 += coef * TAB(kernel_pre, idx, col, eqs_d);
               sum_f1 += coef * TAB(kernel_pre, idx + 1, col, eqs_d);
+              if (linear) continue; /* :363-373 */
               sum_d0 += coef * TAB(kd1_pre, idx, col, eqs_d);
               sum_d1 += coef * TAB(kd1_pre, idx + 1, col, eqs_d);
               if (quintic) { /* :333-349 */
@@ -718,6 +801,7 @@ int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const d
               }
             }
             double v = quintic ? quintic_hermite(t, sum_f0, sum_f1, sum_d0, sum_d1, sum_dd0, sum_dd1, h_pre)
+                     : linear  ? (1.0 - t) * sum_f0 + t * sum_f1
                                : cubic_hermite(t, sum_f0, sum_f1, sum_d0, sum_d1, h_pre);
             next[offset_out + (k - 1) * stride_out] = v * scale; /* :378-380 */
           }

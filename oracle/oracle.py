@@ -28,7 +28,7 @@ MAX_SMOOTH_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6, "a3": 1,
 MAX_SHIPPED_DERIVATIVE = {"b5": 2, "b7": 3, "b9": 4, "b11": 5, "b13": 5, "a3": 0, "a4": 0, "a5": 0, "a7": 0}  # get_precomputed...jl:33-40
 MIN_POLY_BC_POINTS = {"b5": 6, "b7": 8, "b9": 8, "b11": 8, "b13": 8, "a3": 4, "a4": 4, "a5": 4, "a7": 4}  # convolution_interpolation_function.jl:183-195
 MAX_TABLE_DERIVATIVE = {"b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6, "a3": 1, "a4": 1, "a5": 1, "a7": 1}  # shipped K^(d)
-SUBGRID_IDS = {"cubic": 0, "quintic": 1}
+SUBGRID_IDS = {"cubic": 0, "quintic": 1, "linear": 2}
 BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
 
@@ -141,19 +141,30 @@ def build_subgrids(kernels, derivs, subgrids):
     return tuple(out)
 
 
+def effective_subgrids(subgrids, ndim):
+    """What the evaluators actually do with a resolved subgrid tuple: in 3-D anything but all-cubic is evaluated with
+    linear blending on every axis (eager_3d.jl:139-176; perdim_3d.jl:161 "fallback to all linear")."""
+    if ndim == 3 and tuple(subgrids) != ("cubic",) * 3:
+        return ("linear",) * 3
+    return tuple(subgrids)
+
+
 def check_subgrids(kernels, derivs, subgrids, ndim, perdim, what):
-    """Which resolved (kernel, derivative, subgrid) combinations the shipped 101-row tables can serve:
-    :cubic needs K^(d), K^(d+1); :quintic also K^(d+2) and exists in 1-D / 2-D only (eager_1d.jl:117-145,
-    eager_2d.jl:214-311 for (quintic, quintic), perdim_2d.jl for the mixed pairs)."""
+    """Which resolved (kernel, derivative, subgrid) combinations the shipped 101-row tables can serve (precompute = 101:
+    the generated tables of the :linear path are then the shipped K^(d), both are exact rationals rounded once):
+    :linear needs K^(d); :cubic also K^(d+1); :quintic also K^(d+2) and exists in 1-D / 2-D only."""
     for d in range(ndim):
         k, dv, sg = kernels[d], derivs[d], subgrids[d]
-        if dv < 0 or sg not in ("cubic", "quintic") or dv > MAX_SHIPPED_DERIVATIVE[k]:
+        if dv < 0 or sg not in ("cubic", "quintic", "linear"):
             raise OracleError(f"{what}: mode outside the oracle's scope: subgrid={subgrids} deriv={derivs}")
-        if sg == "quintic" and dv + 2 > MAX_TABLE_DERIVATIVE[k]:
-            raise OracleError(f"{what}: K^({dv + 2}) of :{k} is not shipped (quintic subgrid)")
-    if what == "interpolation" and "quintic" in subgrids:
-        if ndim > 2 or (ndim == 2 and not perdim and subgrids != ("quintic", "quintic")):
+        need = dv + {"linear": 0, "cubic": 1, "quintic": 2}[sg]
+        if need > MAX_TABLE_DERIVATIVE[k]:
+            raise OracleError(f"{what}: K^({need}) of :{k} is not shipped ({sg} subgrid, derivative {dv})")
+    if what == "interpolation":
+        if "quintic" in subgrids and (ndim > 2 or (ndim == 2 and not perdim and subgrids != ("quintic", "quintic"))):
             raise OracleError(f"{what}: subgrid {subgrids} has no evaluator on this path")
+        if ndim == 2 and not perdim and len(set(subgrids)) != 1:
+            raise OracleError(f"{what}: subgrid {subgrids} has no evaluator on the single-kernel 2-D path")
 
 
 def extend_vector(x, n_extra):
@@ -214,6 +225,7 @@ class Interpolant:
         self.bc = tuple(fixed)
         self.subgrid = build_subgrids(self.kernels, self.derivs, sg_req)
         self.perdim = not (len(set(self.kernels)) == 1 and len(set(self.derivs)) == 1)
+        self.subgrid = effective_subgrids(self.subgrid, nd)
         check_subgrids(self.kernels, self.derivs, self.subgrid, nd, self.perdim, "interpolation")
         self.eqs = tuple(KERNEL_EQS[k] for k in self.kernels)
         self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120

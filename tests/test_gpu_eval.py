@@ -136,8 +136,49 @@ def test_a_series_kernels_1d_2d_3d(ci, oracle, kernel, bc):
     if bc == "detect":
         # mixed a / b kernels per axis take the generic per-axis path; derivatives of a-kernels are not shipped
         _compare(ci, oracle, k3, v3, tuple(q3), kernel=(kernel, "b5", "a4"), derivative=(0, 1, 0), extrap="line")
+        # derivative 1 of an a-kernel resolves to the :linear subgrid (K' rows, linear blend)
+        g = _compare(ci, oracle, x, v, (q,), kernel=kernel, derivative=1, extrap="line")[2]
+        assert g.itp.subgrid == ("linear",)
         with pytest.raises(ci.UnsupportedModeError):
-            ci.convolution_interpolation(x, v, kernel=kernel, derivative=1)
+            ci.convolution_interpolation(x, v, kernel=kernel, derivative=2)
+
+
+@pytest.mark.parametrize("kernel", ["b5", "b9", "b13"])
+def test_linear_subgrid_and_top_derivatives(ci, oracle, kernel):
+    """:linear subgrid (K rows only, linear blend; precompute = 101): requested explicitly, reached through a top
+    derivative (b5: 3, b9: 5, b13: 6), mixed with cubic / quintic axes on the per-dim 2-D path, the all-linear 3-D
+    evaluators (any non-all-cubic 3-D interpolant), and the (linear, linear) position arithmetic of eager_2d.jl."""
+    rng = np.random.default_rng(43)
+    top = {"b5": 3, "b9": 5, "b13": 6}[kernel]
+    x = np.linspace(-2, 3, 77)
+    v = np.cos(1.7 * x) + 0.03 * rng.standard_normal(77)
+    q = rng.uniform(-2.3, 3.3, 40_000)
+    _compare(ci, oracle, x, v, (q,), kernel=kernel, subgrid="linear", extrap="line")
+    g = _compare(ci, oracle, x, v, (q,), kernel=kernel, derivative=top, extrap="flat")[2]
+    assert g.itp.subgrid == ("linear",)
+    v2 = _field((40, 35), rng, noise=0.02)
+    k2 = (np.linspace(0, 1, 40), np.linspace(0, 1, 35))
+    q2 = rng.uniform(-0.05, 1.05, (2, 30_000))
+    g = _compare(ci, oracle, k2, v2, tuple(q2), kernel=kernel, subgrid="linear", extrap="line")[2]   # eager (linear, linear)
+    assert g.itp.subgrid == ("linear", "linear") and not g.itp.perdim
+    g = _compare(ci, oracle, k2, v2, tuple(q2), kernel=kernel, derivative=(top, 0), extrap="flat")[2]  # per-dim (linear, cubic)
+    assert g.itp.subgrid == ("linear", "cubic") and g.itp.perdim
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=(kernel, "b7"), derivative=(0, 1), subgrid=("quintic", "linear"),
+             extrap="flat")
+    _compare(ci, oracle, k2, v2, tuple(q2), kernel=(kernel, "b7"), subgrid=("linear", "linear"), extrap="line")
+    shape = (26, 24, 28)
+    k3 = tuple(np.linspace(0, 1, n) for n in shape)
+    v3 = _field(shape, rng, noise=0.02)
+    q3 = rng.uniform(-0.03, 1.03, (3, 20_011))
+    g = _compare(ci, oracle, k3, v3, tuple(q3), kernel=kernel, derivative=(top, 0, 0), extrap="flat")[2]
+    assert g.itp.subgrid == ("linear",) * 3 and g.itp.perdim
+    _compare(ci, oracle, k3, v3, tuple(q3), kernel=kernel, subgrid="linear", extrap="line")
+    _compare(ci, oracle, k3, v3, tuple(q3), kernel=kernel, subgrid=("cubic", "quintic", "cubic"), extrap="flat")
+    if kernel == "b5":  # the binned strategies on an all-linear 3-D interpolant
+        qb = rng.uniform(0, 1, (3, 300_007))
+        gg = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="gather")
+        gb = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned")
+        assert rel_err(gb.eval(*qb), gg.eval(*qb), np.abs(v3).max()).max() <= 1e-14
 
 
 @pytest.mark.parametrize("kernel", ["b5", "b7", "b13"])

@@ -94,6 +94,12 @@ def test_resample_quintic_subgrid(ci, oracle):
                     derivative=(1, 0))
     with pytest.raises(ci.UnsupportedModeError):
         ci.convolution_resample(xi, xo, v, kernel="b5", subgrid="quintic", derivative=2)  # K^(4) of b5 not shipped
+    # :linear subgrid: explicit, through a top derivative, and the 3-D kw method (resolves to all-linear)
+    _check_resample(ci, oracle, xi, xo, v, kernel="b5", subgrid="linear")
+    _check_resample(ci, oracle, xi, xo, v, kernel="b5", derivative=3)
+    k3i = tuple(np.linspace(0, 1, n) for n in (30, 28, 33))
+    k3o = tuple(np.linspace(0, 1, n) for n in (40, 50, 61))
+    _check_resample(ci, oracle, k3i, k3o, rng.random((30, 28, 33)), kernel="b7", derivative=(4, 0, 1))
 
 
 def test_resample_shapes_downsampling_extrapolating_knots_and_4d(ci, oracle):
@@ -110,11 +116,11 @@ def test_resample_shapes_downsampling_extrapolating_knots_and_4d(ci, oracle):
     k4i = tuple(np.linspace(0, 1, n) for n in (12, 11, 13, 10))
     k4o = tuple(np.linspace(0, 1, n) for n in (20, 9, 15, 17))
     # N = 4: only the kw-less call keeps the cubic subgrid (convolution_resample.jl:65-172); with keyword
-    # arguments _build_subgrids turns N >= 4 into :linear, which stays on the reference path
+    # arguments _build_subgrids turns N >= 4 into :linear (K rows only, linear blend)
     v4 = rng.random((12, 11, 13, 10))
-    _check_resample(ci, oracle, k4i, k4o, v4)
-    with pytest.raises(ci.UnsupportedModeError, match="subgrid"):
-        ci.convolution_resample(k4i, k4o, v4, kernel="b7")
+    got_c, _ = _check_resample(ci, oracle, k4i, k4o, v4)
+    got_l, _ = _check_resample(ci, oracle, k4i, k4o, v4, kernel="b13")
+    assert 0 < np.abs(got_c - got_l).max() < 1e-3  # a 101-row table blended linearly is ~1e-4 accurate
     # a long 1-D line (single line -> tile width 1)
     xl = np.linspace(0, 50, 9001)
     _check_resample(ci, oracle, xl, np.linspace(0, 50, 12345), np.sin(xl) + 0.001 * rng.standard_normal(9001), kernel="b13")

@@ -109,11 +109,13 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, kernel="a1")           # a0 / a1: :linear subgrid only
     with pytest.raises(U):
-        ci.convolution_interpolation(x, v, kernel="a4", derivative=1)  # K'' of the a-series is not shipped
+        ci.convolution_interpolation(x, v, kernel="a4", derivative=2)  # K'' of the a-series does not exist
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, derivative=-1)
     with pytest.raises(U):
-        ci.convolution_interpolation(x, v, derivative=3)          # top derivative -> :linear subgrid
+        ci.convolution_interpolation(x, v, derivative=4)          # K^(4) of :b5 does not exist in the tables
+    with pytest.raises(U):
+        ci.convolution_interpolation(x, v, derivative=3, precompute=1000)  # generated tables: reference path
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, derivative=2, subgrid="quintic")   # K^(4) of :b5 is not shipped
     with pytest.raises(U):
@@ -127,11 +129,8 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
         ci.convolution_interpolation(np.sort(np.random.default_rng(0).random(30)), v)  # non-uniform grid
     with pytest.raises(U):
         ci.convolution_interpolation((x,) * 4, np.zeros((30,) * 4))
-    with pytest.raises(U):
-        v3 = np.zeros((30, 30, 30))
-        ci.convolution_interpolation((x, x, x), v3, subgrid=("cubic", "quintic", "cubic"))  # N==3 not all-cubic
-    with pytest.raises(U, match="subgrid"):  # kw method + N >= 4 -> :linear subgrid (reference path)
-        ci.convolution_resample((x,) * 4, (x,) * 4, np.zeros((30,) * 4), kernel="b5")
+    with pytest.raises(U):  # generated tables
+        ci.convolution_resample(x, x, v, kernel="b5", precompute=1000)
     with pytest.raises(ValueError, match="antiderivatives"):
         ci.convolution_resample(x, x, v, derivative=-1)
     with pytest.raises(ValueError, match="Cannot use cubic subgrid with a1"):
@@ -145,6 +144,8 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
 def test_mode_resolution_mirrors_reference(ci):
     from convitp_b200 import api
     assert api._build_subgrids(("b5", "b5"), (3, 0), ("cubic", "cubic")) == ("linear", "cubic")
+    assert api._effective_subgrids(("linear", "cubic", "cubic"), 3) == ("linear",) * 3  # perdim_3d.jl:161
+    assert api._effective_subgrids(("linear", "cubic"), 2) == ("linear", "cubic")
     assert api._build_subgrids(("b5", "b5"), (3, 3), ("cubic", "cubic")) == ("linear", "linear")
     assert api._build_subgrids(("b13",) * 3, (1, 0, 0), ("cubic",) * 3) == ("cubic",) * 3
     assert api._build_subgrids(("b5",) * 4, (0,) * 4, ("cubic",) * 4) == ("linear",) * 4
