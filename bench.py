@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nq", type=float, default=1e9, help="queries per GPU per step")
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--e2e-nq", type=float, default=1e8, help="queries per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-nq", type=float, default=0, help="queries per step of the host-buffer (e2e) leg; default: as many as --nq, capped by 40 %% of the free host memory per rank (32 B of pinned memory per query)")
     ap.add_argument("--mode", default=os.environ.get("CIB200_EVAL_MODE", "auto"), choices=["auto", "gather", "binned"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -322,7 +322,11 @@ def main():
     # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region -----------------------
     e2e = None
     if not args.no_e2e:
-        nqe = int(min(args.e2e_nq, nq))
+        if args.e2e_nq > 0:
+            nqe = int(min(args.e2e_nq, nq))
+        else:
+            import psutil
+            nqe = int(min(nq, 0.4 * psutil.virtual_memory().available / max(world, 1) / 32))
         hx = [torch.empty(nqe, dtype=torch.float64, pin_memory=True) for _ in range(3)]
         for i in range(3):
             hx[i].copy_(xs[i][:nqe])
@@ -345,7 +349,7 @@ def main():
         assert hdiff <= 1e-13 * vmax, f"host-buffer result differs from the device-resident one by {hdiff}"
         e2e = {"value": world * nqe * args.steps / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": 3 * 8 * nqe, "d2h_bytes_per_step": 8 * nqe, "queries_per_step": nqe,
-               "note": "cib200_itp_eval with pinned host buffers: 2^24-query chunks, H2D / kernels / D2H on three streams over a 3-buffer ring"}
+               "note": "cib200_itp_eval with pinned host buffers: 2^26-query chunks, H2D / kernels / D2H on three streams over a 3-buffer ring"}
         del hx, hout
 
     if rank == 0:
