@@ -37,6 +37,7 @@ MINIMUM_POLYNOMIAL_BC_POINTS = {"a0": 2, "a1": 2, "a3": 4, "a4": 4, "a5": 4, "a7
 # highest K^(d) table shipped per kernel (precomputed_kernels/kernel_<k>.jl): the quintic subgrid needs K^(d+2)
 MAX_TABLE_DERIVATIVE = {"a3": 1, "a4": 1, "a5": 1, "a7": 1, "b5": 3, "b7": 4, "b9": 5, "b11": 6, "b13": 6}
 ACCELERATED_KERNELS = tuple(KERNEL_IDS)
+MAX_ND = 8  # CIB200_MAX_ND: point evaluation in 4..8 dimensions goes through cib200_itpnd_*
 
 
 class AbstractExtrapolation:
@@ -173,9 +174,8 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
     """Raise UnsupportedModeError for modes that stay on the reference's Julia path.  With precompute = 101 the tables
     of every subgrid are the shipped K^(d) (the generated ones of the :linear path are the same exact rationals rounded
     once): :linear needs K^(d), :cubic also K^(d+1), :quintic also K^(d+2)."""
-    if ndim > 3 and what == "convolution_interpolation":
-        raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N={ndim} uses the N-D evaluators "
-                                   "(eager_nd.jl / perdim_nd.jl); not on the accelerated path")
+    if ndim > MAX_ND and what == "convolution_interpolation":
+        raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N={ndim} > {MAX_ND} is not on the accelerated path")
     for d, (k, dv, sg) in enumerate(zip(kernels, derivs, subgrids)):
         if k not in KERNEL_IDS:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: kernel :{k} (axis {d + 1}) is not on the "
@@ -264,6 +264,19 @@ class FastConvolutionInterpolation:
             self.knots.append(ext)
         self.knots = tuple(self.knots)
         # ---- upload ----
+        if nd >= 4:
+            # HigherDimension evaluators (eager_nd.jl:97-140 / perdim_nd.jl:4-36): every axis on the :linear subgrid
+            self._nd = True
+            cs = (C.c_int64 * nd)(*cshape)
+            kp = (C.c_void_p * nd)(*[k.ctypes.data for k in self.knots])
+            dv = (C.c_int32 * nd)(*[int(d) for d in self.derivative])
+            handle = C.c_void_p()
+            check(L.cib200_itpnd_create(nd, self.dtype_id, cs, self.coefs.ctypes.data, kp, hh, kid, dv,
+                                        EXTRAP_IDS[_extrap], int(self.perdim), C.byref(handle)))
+            self._handle = handle
+            self.eval_mode = "nd"
+            return
+        self._nd = False
         desc = _lib.ItpDesc()
         desc.ndim = nd
         desc.dtype = self.dtype_id
@@ -283,11 +296,15 @@ class FastConvolutionInterpolation:
         self.set_eval_mode(eval_mode)
 
     def set_eval_mode(self, mode):
+        if self._nd:
+            return  # one strategy in N >= 4 dimensions
         check(lib().cib200_itp_set_eval_mode(self._handle, _lib.EVAL_MODES[mode]))
         self.eval_mode = mode
 
     def set_profiling(self, enable=True):
         """Measurement hook: bracket the passes of every evaluation with CUDA events (cib200_itp_set_profiling)."""
+        if self._nd:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, "pass timing exists for 1-3 dimensions only")
         check(lib().cib200_itp_set_profiling(self._handle, 1 if enable else 0))
 
     def last_pass_ms(self):
@@ -299,7 +316,7 @@ class FastConvolutionInterpolation:
     def close(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h:
-            lib().cib200_itp_destroy(h)
+            (lib().cib200_itpnd_destroy if getattr(self, "_nd", False) else lib().cib200_itp_destroy)(h)
 
     def __del__(self):
         try:
@@ -336,8 +353,8 @@ class ConvolutionExtrapolation:
             if out is None:
                 out = torch.empty(shape, dtype=tdt, device=xs[0].device)
             ptrs = (C.c_void_p * itp.ndim)(*[x.data_ptr() for x in xs])
-            check(L.cib200_itp_eval(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE,
-                                    _stream_ptr(xs[0]), None))
+            fn = L.cib200_itpnd_eval if itp._nd else L.cib200_itp_eval
+            check(fn(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE, _stream_ptr(xs[0]), None))
             return out
         ndt = _np_dtype(itp.dtype_id)
         xs = np.broadcast_arrays(*[np.asarray(x, dtype=ndt) for x in xs])
@@ -347,7 +364,8 @@ class ConvolutionExtrapolation:
         if out is None:
             out = np.empty(nq, dtype=ndt)
         ptrs = (C.c_void_p * itp.ndim)(*[x.ctypes.data for x in xs])
-        check(L.cib200_itp_eval(itp._handle, nq, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
+        fn = L.cib200_itpnd_eval if itp._nd else L.cib200_itp_eval
+        check(fn(itp._handle, nq, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
         return out.reshape(shape)
 
     # -- itp(x, y, z): scalars, or vectors -> Cartesian product ---------------------------------
@@ -366,7 +384,8 @@ class ConvolutionExtrapolation:
         n = (C.c_int64 * itp.ndim)(*[v.size for v in vs])
         out = np.zeros(tuple(v.size for v in vs), dtype=ndt, order="F")
         ptrs = (C.c_void_p * itp.ndim)(*[v.ctypes.data for v in vs])
-        check(L.cib200_itp_eval_grid(itp._handle, n, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
+        fn = L.cib200_itpnd_eval_grid if itp._nd else L.cib200_itp_eval_grid
+        check(fn(itp._handle, n, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
         return out
 
 

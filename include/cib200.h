@@ -29,6 +29,7 @@ extern "C" {
 
 #define CIB200_MAX_ITP_DIM 3
 #define CIB200_MAX_SWEEP_DIM 8
+#define CIB200_MAX_ND 8 /* N-D point evaluation (cib200_itpnd_*): 4..8 dimensions */
 #define CIB200_N_PRE 101
 
 typedef enum {
@@ -125,6 +126,25 @@ int32_t cib200_itp_eval(cib200_itp *handle, int64_t nq, const void *const *x, vo
  * ((etp)(x::Vararg{AbstractArray,N}), extrapolation_operator.jl:66-99). out: n[0] x ... column-major */
 int32_t cib200_itp_eval_grid(cib200_itp *handle, const int64_t *n, const void *const *x, void *out,
                              int32_t memkind, void *stream, int64_t *first_bad);
+
+/* ---- N >= 4 dimensions: the reference's HigherDimension evaluators ------------------------------
+ * itp.(xs...) for 4..CIB200_MAX_ND axes: replaces the per-element loop over the N-D functors
+ *   convolution_fast_interpolation_eager_nd.jl:97-140   (perdim = 0: one kernel, one derivative order)
+ *   convolution_fast_interpolation_perdim_nd.jl:4-36    (perdim = 1: per-axis kernels / derivative orders)
+ * behind extrapolation_operator.jl:31-99 / extrapolate_point.jl:98-160.  For N >= 4 _build_subgrids
+ * (fast_convolution_interpolation_constructor.jl:456-494) resolves every axis to the :linear subgrid; with
+ * precompute = 101 the tables are the shipped K^(deriv).  coefs: ghost-padded grid (cib200_build_coefs takes up to
+ * CIB200_MAX_SWEEP_DIM axes), knots[d]: extended knot vector of length coef_shape[d], all host memory, copied. */
+typedef struct cib200_itpnd cib200_itpnd; /* opaque */
+int32_t cib200_itpnd_create(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
+                            const double *const *knots, const double *h, const int32_t *kernel,
+                            const int32_t *deriv, int32_t extrap, int32_t perdim, cib200_itpnd **handle);
+int32_t cib200_itpnd_destroy(cib200_itpnd *handle);
+/* same contracts as cib200_itp_eval / cib200_itp_eval_grid */
+int32_t cib200_itpnd_eval(cib200_itpnd *handle, int64_t nq, const void *const *x, void *out,
+                          int32_t memkind, void *stream, int64_t *first_bad);
+int32_t cib200_itpnd_eval_grid(cib200_itpnd *handle, const int64_t *n, const void *const *x, void *out,
+                               int32_t memkind, void *stream, int64_t *first_bad);
 
 /* Measurement hook (bench.py's roofline): with profiling enabled the library brackets the passes of every evaluation
  * with CUDA events on the launching stream; cib200_itp_last_pass_ms then returns, for the most recent call, the

@@ -51,7 +51,7 @@ kernel_symbols(_) = nothing
 
 function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     (T === Float64 || T === Float32) || return false
-    1 <= N <= 3 || return false
+    1 <= N <= 8 || return false                                          # CIB200_MAX_ND
     ks = kernel_symbols(itp.kernel_sym)
     ks === nothing && return false
     all(k -> haskey(KERNEL_ID, k), ks) || return false
@@ -67,6 +67,7 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     # evaluators: eager_2d.jl has (linear, linear), (cubic, cubic), (quintic, quintic); the mixed pairs exist on the
     # per-dim path (perdim_2d.jl); :quintic never in 3-D (_build_subgrids)
     any(==(:quintic), sg) && N > 2 && return false
+    N >= 4 && !all(==(:linear), sg) && return false                      # HigherDimension: :linear only (_build_subgrids)
     N == 2 && !(itp.kernel_sym isa HigherOrderMixedKernel) && !allequal(sg) && return false
     return true
 end
@@ -93,6 +94,23 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
             ks = kernel_symbols(itp.kernel_sym)
             dv = derivative_tuple(itp)
             knots64 = ntuple(d -> Vector{Float64}(itp.knots[d]), N)
+            if N >= 4
+                # HigherDimension evaluators (eager_nd.jl:97-140 / perdim_nd.jl:4-36): cib200_itpnd_*
+                out = Ref{Ptr{Cvoid}}(C_NULL)
+                cshape = Int64[size(itp.coefs)...]
+                kptr = [pointer(knots64[d]) for d in 1:N]
+                hh = Float64[itp.h...]
+                kid = Int32[KERNEL_ID[ks[d]] for d in 1:N]
+                dvv = Int32[dv[d] for d in 1:N]
+                GC.@preserve itp knots64 cshape kptr hh kid dvv check(ccall((:cib200_itpnd_create, LIB), Int32,
+                    (Int32, Int32, Ptr{Int64}, Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32},
+                     Int32, Int32, Ref{Ptr{Cvoid}}),
+                    N, T === Float32 ? 1 : 0, cshape, pointer(itp.coefs), kptr, hh, kid, dvv, extrap_id(etp.et),
+                    Int32(itp.kernel_sym isa HigherOrderMixedKernel), out))
+                h = Handle(out[])
+                finalizer(x -> ccall((:cib200_itpnd_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+                return h
+            end
             desc = Ref(ItpDesc(Int32(N), T === Float32 ? Int32(1) : Int32(0),
                                pad3(Int64.(size(itp.coefs)), Int64(1)), pointer(itp.coefs),
                                pad3(ntuple(d -> pointer(knots64[d]), N), Ptr{Float64}(0)),
@@ -119,9 +137,14 @@ function Base.Broadcast.broadcasted(etp::ConvolutionExtrapolation{T,N}, xs::Vara
     out = Vector{T}(undef, nq)
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
     bad = Ref{Int64}(-1)
-    GC.@preserve xq out ptrs check(ccall((:cib200_itp_eval, LIB), Int32,
-        (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
-        handle(etp).ptr, nq, ptrs, out, 0, C_NULL, bad))
+    hp = handle(etp).ptr
+    GC.@preserve xq out ptrs check(N >= 4 ?   # ccall needs a literal symbol: one call site per entry point
+        ccall((:cib200_itpnd_eval, LIB), Int32,
+              (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+              hp, nq, ptrs, out, 0, C_NULL, bad) :
+        ccall((:cib200_itp_eval, LIB), Int32,
+              (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+              hp, nq, ptrs, out, 0, C_NULL, bad))
     return out
 end
 
@@ -133,9 +156,14 @@ function (etp::ConvolutionExtrapolation{T,N})(xs::Vararg{AbstractVector{<:Real},
     out = zeros(T, n...)
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
     bad = Ref{Int64}(-1)
-    GC.@preserve xq out ptrs check(ccall((:cib200_itp_eval_grid, LIB), Int32,
-        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
-        handle(etp).ptr, n, ptrs, out, 0, C_NULL, bad))
+    hp = handle(etp).ptr
+    GC.@preserve xq out ptrs check(N >= 4 ?
+        ccall((:cib200_itpnd_eval_grid, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+              hp, n, ptrs, out, 0, C_NULL, bad) :
+        ccall((:cib200_itp_eval_grid, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+              hp, n, ptrs, out, 0, C_NULL, bad))
     return out
 end
 

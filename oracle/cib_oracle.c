@@ -720,6 +720,135 @@ int orc_itp_eval(const orc_itp *it, int64_t nq, const double *const *x, double *
   return bad_rc;
 }
 
+/* ---- N >= 4 dimensions ------------------------------------------------------------------------ */
+typedef struct {
+  const double *kp[ORC_MAXND];
+  int eqs[ORC_MAXND];
+} nd_tabs;
+
+/* the un-wrapped N-D functor: eager_nd.jl:97-140 (HigherOrderKernel: pre_range positions, itp.eqs[1] and
+ * itp.kernel_pre[1] on every axis) / perdim_nd.jl:4-36 (cidx positions, per-axis tables) */
+static int itp_core_nd(const orc_itp_nd *it, const nd_tabs *tb, const double *x, double *res) {
+  const int N = it->ndim;
+  axis_pos p[ORC_MAXND];
+  for (int d = 0; d < N; ++d) {
+    const int eqs = it->perdim ? tb->eqs[d] : tb->eqs[0];
+    int bad = it->perdim ? locate(x[d], it->knots[d], it->cshape[d], it->h[d], eqs, &p[d])
+                         : locate_prerange(x[d], it->knots[d], it->cshape[d], it->h[d], eqs, &p[d]);
+    if (bad) return ORC_ENAN;
+  }
+  int64_t stride[ORC_MAXND];
+  stride[0] = 1;
+  for (int d = 1; d < N; ++d) stride[d] = stride[d - 1] * it->cshape[d - 1];
+  int off[ORC_MAXND]; /* offsets[d] + eqs - 1 = 0 .. 2 eqs - 1, first axis fastest (Iterators.product) */
+  for (int d = 0; d < N; ++d) off[d] = 0;
+  double result = 0.0;
+  for (;;) {
+    int64_t lin = 0;
+    for (int d = 0; d < N; ++d) {
+      const int eqs = it->perdim ? tb->eqs[d] : tb->eqs[0];
+      lin += (p[d].i - 1 + (off[d] - (eqs - 1))) * stride[d];
+    }
+    const double coef = it->coefs[lin];
+    double kernel_val = 1.0;
+    for (int d = 0; d < N; ++d) {
+      const int eqs = it->perdim ? tb->eqs[d] : tb->eqs[0];
+      const double *kp = it->perdim ? tb->kp[d] : tb->kp[0];
+      const int col = off[d] + 1; /* offsets[d] + eqs, 1-based */
+      const double k_lower = TAB(kp, p[d].idx, col, eqs);
+      const double k_upper = TAB(kp, p[d].idx + 1, col, eqs);
+      kernel_val *= (1.0 - p[d].t) * k_lower + p[d].t * k_upper;
+    }
+    result += coef * kernel_val;
+    int d = 0;
+    for (; d < N; ++d) {
+      const int eqs = it->perdim ? tb->eqs[d] : tb->eqs[0];
+      if (++off[d] < 2 * eqs) break;
+      off[d] = 0;
+    }
+    if (d == N) break;
+  }
+  double s;
+  if (it->perdim) { /* _perdim_scale, perdim_2d.jl:24-30 */
+    s = 1.0;
+    for (int d = 0; d < N; ++d) s *= jl_pow_int(-1.0 / it->h[d], it->deriv[d]);
+  } else { /* prod(generator), eager_nd.jl:139 */
+    s = jl_pow_int(-1.0 / it->h[0], it->deriv[0]);
+    for (int d = 1; d < N; ++d) s *= jl_pow_int(-1.0 / it->h[d], it->deriv[d]);
+  }
+  *res = result * s;
+  return ORC_OK;
+}
+
+/* extrapolation_operator.jl:31-63 + extrapolate_point.jl:98-160 */
+static int etp_point_nd(const orc_itp_nd *it, const nd_tabs *tb, const double *x, double *res) {
+  const int N = it->ndim;
+  double lo[ORC_MAXND], hi[ORC_MAXND];
+  int within = 1;
+  for (int d = 0; d < N; ++d) {
+    lo[d] = it->knots[d][tb->eqs[d] - 1];
+    hi[d] = it->knots[d][it->cshape[d] - 1 - (tb->eqs[d] - 1)];
+  }
+  for (int d = 0; d < N; ++d)
+    if (x[d] > hi[d] || x[d] < lo[d]) { within = 0; break; }
+  if (within) return itp_core_nd(it, tb, x, res);
+  double cl[ORC_MAXND];
+  for (int d = 0; d < N; ++d) cl[d] = x[d] < lo[d] ? lo[d] : (x[d] > hi[d] ? hi[d] : x[d]);
+  if (it->extrap == ORC_EXTRAP_LINE) {
+    double dx[ORC_MAXND], dist_sq = 0.0;
+    for (int d = 0; d < N; ++d) {
+      dx[d] = x[d] - cl[d];
+      dist_sq += dx[d] * dx[d];
+    }
+    if (dist_sq < 2.220446049250313e-16) return itp_core_nd(it, tb, cl, res);
+    double h_min = it->h[0];
+    for (int d = 1; d < N; ++d) h_min = it->h[d] < h_min ? it->h[d] : h_min;
+    double eps = h_min / 100.0;
+    double dist = sqrt(dist_sq);
+    double xin[ORC_MAXND];
+    for (int d = 0; d < N; ++d) xin[d] = cl[d] - eps * dx[d] / dist;
+    double f_b, f_in;
+    int rc = itp_core_nd(it, tb, cl, &f_b);
+    if (rc) return rc;
+    rc = itp_core_nd(it, tb, xin, &f_in);
+    if (rc) return rc;
+    double slope = (f_b - f_in) / eps;
+    *res = f_b + slope * dist;
+    return ORC_OK;
+  }
+  if (it->extrap == ORC_EXTRAP_FLAT) return itp_core_nd(it, tb, cl, res);
+  return ORC_EOOB;
+}
+
+int orc_itp_eval_nd(const orc_itp_nd *it, int64_t nq, const double *const *x, double *out, int64_t *first_bad) {
+  if (it->ndim < 4 || it->ndim > ORC_MAXND) return ORC_EARG;
+  nd_tabs tb;
+  for (int d = 0; d < it->ndim; ++d) {
+    tb.eqs[d] = orc_eqs(it->kernel[d]);
+    tb.kp[d] = orc_table(it->kernel[d], it->deriv[d]);
+    if (tb.eqs[d] < 0 || !tb.kp[d]) return ORC_EARG;
+    if (!it->perdim && (it->kernel[d] != it->kernel[0] || it->deriv[d] != it->deriv[0])) return ORC_EARG;
+  }
+  int64_t bad = -1;
+  int bad_rc = ORC_OK;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int64_t q = 0; q < nq; ++q) {
+    double xq[ORC_MAXND];
+    for (int d = 0; d < it->ndim; ++d) xq[d] = x[d][q];
+    double r = NAN;
+    int rc = etp_point_nd(it, &tb, xq, &r);
+    out[q] = r;
+    if (rc) {
+#pragma omp critical
+      {
+        if (bad < 0 || q < bad) { bad = q; bad_rc = rc; }
+      }
+    }
+  }
+  if (first_bad) *first_bad = bad;
+  return bad_rc;
+}
+
 /* convolution/convolution_resample.jl:240-386, cubic subgrid branch :350-361 */
 int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const double *values,
                  double *out, const double *const *knots_in, const double *const *knots_out,

@@ -52,6 +52,12 @@ class _Itp(C.Structure):
                 ("subgrid", C.c_int32 * 3)]
 
 
+class _ItpNd(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("cshape", C.c_int64 * 8), ("coefs", C.c_void_p),
+                ("knots", C.c_void_p * 8), ("h", C.c_double * 8), ("kernel", C.c_int32 * 8),
+                ("deriv", C.c_int32 * 8), ("extrap", C.c_int32), ("perdim", C.c_int32)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -60,6 +66,8 @@ def lib():
         L.orc_table.argtypes = [C.c_int, C.c_int]
         L.orc_itp_eval.argtypes = [C.POINTER(_Itp), C.c_int64, C.POINTER(C.c_void_p), C.c_void_p,
                                    C.POINTER(C.c_int64)]
+        L.orc_itp_eval_nd.argtypes = [C.POINTER(_ItpNd), C.c_int64, C.POINTER(C.c_void_p), C.c_void_p,
+                                      C.POINTER(C.c_int64)]
         L.orc_create_coefs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_resample.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 4
@@ -202,8 +210,8 @@ class Interpolant:
                  subgrid="cubic"):
         values = np.asarray(values, dtype=np.float64)
         nd = values.ndim
-        if nd < 1 or nd > 3:
-            raise OracleError("oracle covers 1-3 D")
+        if nd < 1 or nd > 8:
+            raise OracleError("oracle covers 1-8 D")
         self.ndim = nd
         self.knots_in = _knots_tuple(knots, nd)
         self.kernels = _ntuple(kernel, nd, str)
@@ -234,7 +242,7 @@ class Interpolant:
         self.extrap = extrap
         # _build_kernel_sym, constructor.jl:378-398
         self.perdim = not (len(set(self.kernels)) == 1 and len(set(self.derivs)) == 1)
-        it = _Itp()
+        it = _Itp() if nd <= 3 else _ItpNd()  # N >= 4: HigherDimension evaluators (eager_nd.jl / perdim_nd.jl)
         it.ndim = nd
         for d in range(nd):
             it.cshape[d] = self.coefs.shape[d]
@@ -242,7 +250,8 @@ class Interpolant:
             it.h[d] = self.h[d]
             it.kernel[d] = KERNEL_IDS[self.kernels[d]]
             it.deriv[d] = self.derivs[d]
-            it.subgrid[d] = SUBGRID_IDS[self.subgrid[d]]
+            if nd <= 3:
+                it.subgrid[d] = SUBGRID_IDS[self.subgrid[d]]
         it.coefs = self.coefs.ctypes.data
         it.extrap = EXTRAP_IDS[extrap]
         it.perdim = int(self.perdim)
@@ -257,7 +266,8 @@ class Interpolant:
         out = np.empty(nq)
         ptrs = (C.c_void_p * self.ndim)(*[x.ctypes.data for x in xs])
         bad = C.c_int64(-1)
-        rc = lib().orc_itp_eval(C.byref(self._it), nq, ptrs, out.ctypes.data, C.byref(bad))
+        fn = lib().orc_itp_eval if self.ndim <= 3 else lib().orc_itp_eval_nd
+        rc = fn(C.byref(self._it), nq, ptrs, out.ctypes.data, C.byref(bad))
         if rc == 1:
             raise OracleError(f"query {bad.value} outside the domain with extrap=throw")
         if rc == 2:

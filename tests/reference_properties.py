@@ -121,6 +121,31 @@ def check_extrapolation(impl):
     assert np.abs(np.array([etp(float(i), float(i), float(i)) for i in pts]) - np.array([0, 0, 3.0, 3.0])).max() < 1e-6
 
 
+def check_extrapolation_4d(impl):
+    """test_extrapolation.jl:124-140 (4D fast kernels, N=5, bc=:linear): the HigherDimension evaluators (eager_nd.jl)
+    behind :line / :flat; plus an analytic derivative through the per-dim N-D evaluator (perdim_nd.jl)"""
+    N = 5
+    r = np.linspace(0.0, 1.0, N)
+    pts = np.array([-0.2, -0.1, 1.1, 1.2])
+    v4 = r[:, None, None, None] + r[None, :, None, None] + r[None, None, :, None] + r[None, None, None, :]
+    for kernel in ("a3", "b5"):
+        etp = impl.interp((r, r, r, r), v4, kernel=kernel, bc="linear", extrap="line")
+        assert np.abs(etp.eval(pts, pts, pts, pts) - 4 * pts).max() < 1e-3
+        etp = impl.interp((r, r, r, r), v4, kernel=kernel, bc="linear", extrap="flat")
+        assert np.abs(etp.eval(pts, pts, pts, pts) - np.array([0, 0, 4.0, 4.0])).max() < 1e-6
+    n = 20
+    x = np.linspace(0, TWO_PI, n)
+    g = np.meshgrid(x, x, x, x, indexing="ij")
+    v = np.sin(g[0]) * np.cos(g[1]) * np.sin(g[2]) * np.cos(g[3])
+    q = np.random.default_rng(7).uniform(0.5, TWO_PI - 0.5, (4, 300))
+    itp = impl.interp((x, x, x, x), v, kernel="b5", derivative=(1, 0, 0, 0))
+    ref = np.cos(q[0]) * np.cos(q[1]) * np.sin(q[2]) * np.cos(q[3])
+    assert np.abs(itp.eval(*q) - ref).max() < 1e-3
+    itp = impl.interp((x, x, x, x), v, kernel="b5")
+    ref = np.sin(q[0]) * np.cos(q[1]) * np.sin(q[2]) * np.cos(q[3])
+    assert np.abs(itp.eval(*q) - ref).max() < 1e-4
+
+
 def check_resample(impl):
     """test_resample.jl:4-80 - resample of sin products vs analytic (1e-5 / 1e-4 / 1e-4), sizes, derivative"""
     xi, xo = np.linspace(0, TWO_PI, 50), np.linspace(0, TWO_PI, 100)
@@ -169,5 +194,5 @@ def check_smooth(impl):
 
 
 ALL_CHECKS = [check_grid_point_reproduction, check_multilinear_midpoints, check_convergence_order,
-              check_uniform_derivatives, check_perdim_derivatives, check_extrapolation, check_resample,
-              check_smooth]
+              check_uniform_derivatives, check_perdim_derivatives, check_extrapolation, check_extrapolation_4d,
+              check_resample, check_smooth]

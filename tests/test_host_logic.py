@@ -128,7 +128,9 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
     with pytest.raises(U):
         ci.convolution_interpolation(np.sort(np.random.default_rng(0).random(30)), v)  # non-uniform grid
     with pytest.raises(U):
-        ci.convolution_interpolation((x,) * 4, np.zeros((30,) * 4))
+        ci.convolution_interpolation((x[:4],) * 9, np.zeros((4,) * 9), kernel="a3")  # N > CIB200_MAX_ND = 8
+    with pytest.raises(U):
+        ci.convolution_interpolation((x[:8],) * 4, np.zeros((8,) * 4), kernel="a4", derivative=2)  # 4-D: K'' of a4
     with pytest.raises(U):  # generated tables
         ci.convolution_resample(x, x, v, kernel="b5", precompute=1000)
     with pytest.raises(ValueError, match="antiderivatives"):
