@@ -7,7 +7,7 @@ The directory name contains a dot, so import it through the `convitp_b200` shim 
     itp = ci.convolution_interpolation((x, y, z), vals, kernel="b5")
     ys = itp.eval(xq, yq, zq)
 """
-from ._lib import (CIB200Error, DomainError, InexactError, UnsupportedModeError, SO_PATH, SYMBOLS, launch_count,
+from ._lib import (CIB200Error, DomainError, InexactError, UnsupportedModeError, SO_PATH, SYMBOLS, check, launch_count,
                    lib)
 from . import sharding
 from .api import (ConvolutionExtrapolation, FastConvolutionInterpolation, Flat, Line, Natural, Throw,

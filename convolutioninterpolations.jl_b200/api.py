@@ -208,7 +208,7 @@ class FastConvolutionInterpolation:
     for the eager cubic-subgrid case, plus the device handle."""
 
     def __init__(self, knots, values, kernel="b5", precompute=101, bc="detect", derivative=0, subgrid="cubic",
-                 lazy=False, boundary_fallback=False, dtype=None, eval_mode="auto", _extrap="throw"):
+                 lazy=False, boundary_fallback=False, dtype=None, eval_mode="auto", _extrap="throw", coefs_on="host"):
         values = np.asarray(values)
         if values.dtype not in (np.float32, np.float64):
             values = values.astype(np.float64)
@@ -249,13 +249,33 @@ class FastConvolutionInterpolation:
         # ---- subsystem 1: ghost-padded coefficients + extended knots, on the host ----
         v = np.asfortranarray(values)
         cshape = tuple(s + 2 * (e - 1) for s, e in zip(v.shape, self.eqs))
-        self.coefs = np.zeros(cshape, dtype=self.dtype, order="F")
         n = (C.c_int64 * nd)(*v.shape)
         hh = (C.c_double * nd)(*self.h)
         kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in self.kernel])
         bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in self.bc])
         br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in self.bc])
-        check(L.cib200_build_coefs(nd, self.dtype_id, n, v.ctypes.data, hh, kid, bl, br, self.coefs.ctypes.data))
+        if coefs_on not in ("host", "device"):
+            raise ValueError("coefs_on must be 'host' or 'device'")
+        self.coefs_on = coefs_on
+        self._d_coefs = None
+        if coefs_on == "device":
+            # values go up once, the ghost fill runs on the GPU (cib200_build_coefs_device) and the
+            # padded grid never visits the host unless .coefs is read
+            import torch
+            tdt = torch.float32 if self.dtype_id == _lib.F32 else torch.float64
+            d_vals = torch.from_numpy(v.reshape(-1, order="F").copy()).cuda()  # column-major image of the values
+            self._d_coefs = torch.empty(int(np.prod(cshape)), dtype=tdt, device=d_vals.device)
+            check(L.cib200_build_coefs_device(nd, self.dtype_id, n, C.c_void_p(d_vals.data_ptr()), hh, kid, bl, br,
+                                              C.c_void_p(self._d_coefs.data_ptr()), _lib.DEVICE, _stream_ptr(d_vals)))
+            torch.cuda.current_stream(d_vals.device).synchronize()
+            del d_vals
+            self._coefs = None
+            self._cshape = cshape
+            coefs_ptr = self._d_coefs.data_ptr()
+        else:
+            self._coefs = np.zeros(cshape, dtype=self.dtype, order="F")
+            check(L.cib200_build_coefs(nd, self.dtype_id, n, v.ctypes.data, hh, kid, bl, br, self._coefs.ctypes.data))
+            coefs_ptr = self._coefs.ctypes.data
         self.knots = []
         for d in range(nd):
             ext = np.zeros(cshape[d])
@@ -271,7 +291,9 @@ class FastConvolutionInterpolation:
             kp = (C.c_void_p * nd)(*[k.ctypes.data for k in self.knots])
             dv = (C.c_int32 * nd)(*[int(d) for d in self.derivative])
             handle = C.c_void_p()
-            check(L.cib200_itpnd_create(nd, self.dtype_id, cs, self.coefs.ctypes.data, kp, hh, kid, dv,
+            if coefs_on == "device":
+                coefs_ptr = self.coefs.ctypes.data  # the N-D constructor copies from host memory
+            check(L.cib200_itpnd_create(nd, self.dtype_id, cs, coefs_ptr, kp, hh, kid, dv,
                                         EXTRAP_IDS[_extrap], int(self.perdim), C.byref(handle)))
             self._handle = handle
             self.eval_mode = "nd"
@@ -287,13 +309,26 @@ class FastConvolutionInterpolation:
             desc.kernel[d] = KERNEL_IDS[self.kernel[d]]
             desc.deriv[d] = int(self.derivative[d])
             desc.subgrid[d] = SUBGRID_IDS[self.subgrid[d]]
-        desc.coefs = self.coefs.ctypes.data
+        desc.coefs = coefs_ptr
         desc.extrap = EXTRAP_IDS[_extrap]
         desc.perdim = int(self.perdim)
         handle = C.c_void_p()
         check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
         self._handle = handle
+        self._d_coefs = None  # the handle holds its own copy
         self.set_eval_mode(eval_mode)
+
+    @property
+    def coefs(self):
+        """itp.coefs (ghost-padded grid); with coefs_on="device" it is downloaded on first access"""
+        if self._coefs is None:
+            import torch
+            if self._d_coefs is not None:
+                self._coefs = self._d_coefs.cpu().numpy().reshape(self._cshape, order="F")
+            else:
+                self._coefs = np.zeros(self._cshape, dtype=self.dtype, order="F")
+                check(lib().cib200_itp_get_coefs(self._handle, self._coefs.ctypes.data))
+        return self._coefs
 
     def set_eval_mode(self, mode):
         if self._nd:
@@ -391,7 +426,7 @@ class ConvolutionExtrapolation:
 
 def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=101, extrap=None, bc="detect",
                               derivative=0, subgrid="cubic", lazy=False, boundary_fallback=False, dtype=None,
-                              eval_mode="auto"):
+                              eval_mode="auto", coefs_on="host"):
     """convolution_interpolation(knots, values; kernel, fast, precompute, extrap, bc, derivative, subgrid,
     lazy, boundary_fallback)  -  convolution_interpolation_function.jl:79-157"""
     values = np.asarray(values)
@@ -426,7 +461,7 @@ def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=
     itp = FastConvolutionInterpolation(knots_t, values, kernel=kernels, precompute=precompute, bc=tuple(fixed),
                                        derivative=derivs, subgrid=subgrid, lazy=lazy,
                                        boundary_fallback=boundary_fallback, dtype=dtype, eval_mode=eval_mode,
-                                       _extrap=et.name)
+                                       _extrap=et.name, coefs_on=coefs_on)
     return ConvolutionExtrapolation(itp, et)
 
 

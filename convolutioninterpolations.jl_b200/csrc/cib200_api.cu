@@ -381,6 +381,65 @@ int32_t cib200_build_coefs(int32_t ndim, int32_t dtype, const int64_t *n, const 
   return CIB200_EINVAL;
 }
 
+static int32_t sweep_io(int ndim, int dtype, long long tot_in, long long tot_out, const void *values, void *out,
+                        int memkind, cudaStream_t st, void **d_in, void **d_out, bool *owned);
+
+int32_t cib200_build_coefs_device(int32_t ndim, int32_t dtype, const int64_t *n, const void *values, const double *h,
+                                  const int32_t *kernel, const int32_t *bc_left, const int32_t *bc_right,
+                                  void *coefs_out, int32_t memkind, void *stream) {
+  if (ndim < 1 || ndim > CIB200_MAX_SWEEP_DIM || !n || !values || !h || !kernel || !bc_left || !bc_right ||
+      !coefs_out) {
+    set_error("cib200_build_coefs_device: bad arguments");
+    return CIB200_EINVAL;
+  }
+  if (dtype != CIB200_F64 && dtype != CIB200_F32) {
+    set_error("cib200_build_coefs_device: unknown dtype %d", dtype);
+    return CIB200_EINVAL;
+  }
+  long long nn[CIB200_MAX_SWEEP_DIM], tin = 1, tout = 1;
+  int k[CIB200_MAX_SWEEP_DIM], bl[CIB200_MAX_SWEEP_DIM], br[CIB200_MAX_SWEEP_DIM];
+  for (int d = 0; d < ndim; ++d) {
+    const int eqs = kernel_eqs(kernel[d]);
+    if (eqs < 0) {
+      set_error("cib200_build_coefs_device: unknown kernel id %d on axis %d", kernel[d], d);
+      return CIB200_EUNSUPPORTED;
+    }
+    if (n[d] < 3) {
+      set_error("cib200_build_coefs_device: axis %d has %lld points (< 3)", d, (long long)n[d]);
+      return CIB200_EINVAL;
+    }
+    if (bc_left[d] < 0 || bc_left[d] > 3 || bc_right[d] < 0 || bc_right[d] > 3) {
+      set_error("cib200_build_coefs_device: unknown boundary condition on axis %d", d);
+      return CIB200_EINVAL;
+    }
+    nn[d] = n[d];
+    k[d] = kernel[d];
+    bl[d] = bc_left[d];
+    br[d] = bc_right[d];
+    tin *= n[d];
+    tout *= n[d] + 2 * (eqs - 1);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  void *d_in, *d_out;
+  bool owned;
+  int rc = sweep_io(ndim, dtype, tin, tout, values, coefs_out, memkind, st, &d_in, &d_out, &owned);
+  if (rc) return rc;
+  rc = sweep_build_coefs(ndim, dtype, nn, d_in, h, k, bl, br, d_out, st);
+  if (owned) {
+    if (!rc) {
+      cudaError_t e = cudaMemcpyAsync(coefs_out, d_out, esize(dtype) * (size_t)tout, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        set_error("cib200_build_coefs_device: D2H failed: %s", cudaGetErrorString(e));
+        rc = CIB200_ECUDA;
+      }
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+  }
+  return rc;
+}
+
 int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
   if (!desc || !handle) {
     set_error("cib200_itp_create: null argument");
@@ -495,7 +554,8 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
 
   const size_t es = esize(h->dtype);
   CIB_CREATE_CUDA(cudaMalloc(&h->d_coefs, es * (size_t)total));
-  CIB_CREATE_CUDA(cudaMemcpy(h->d_coefs, desc->coefs, es * (size_t)total, cudaMemcpyHostToDevice));
+  // cudaMemcpyDefault: desc->coefs may also be device memory (a grid built by cib200_build_coefs_device)
+  CIB_CREATE_CUDA(cudaMemcpy(h->d_coefs, desc->coefs, es * (size_t)total, cudaMemcpyDefault));
   p.coefs = h->d_coefs;
   for (int d = 0; d < nd; ++d) {
     CIB_CREATE_CUDA(cudaMalloc(&h->d_knots[d], sizeof(double) * (size_t)h->cshape[d]));
@@ -707,6 +767,17 @@ static int32_t eval_common(cib200_itp *h, const Coords &c_in, long long nq, void
     set_error("%s: query %lld %s", who, first_bad ? (long long)*first_bad : -1LL,
               code == CIB200_EOOB ? "is outside the interpolation domain (extrap=Throw)" : "has a NaN/Inf coordinate");
   return code;
+}
+
+int32_t cib200_itp_get_coefs(cib200_itp *h, void *coefs_out) {
+  if (!h || !coefs_out) {
+    set_error("cib200_itp_get_coefs: bad arguments");
+    return CIB200_EINVAL;
+  }
+  size_t total = 1;
+  for (int d = 0; d < h->p.ndim; ++d) total *= (size_t)h->cshape[d];
+  CIB_CUDA(cudaMemcpy(coefs_out, h->d_coefs, esize(h->dtype) * total, cudaMemcpyDeviceToHost));
+  return CIB200_OK;
 }
 
 int32_t cib200_itp_eval(cib200_itp *h, int64_t nq, const void *const *x, void *out, int32_t memkind,

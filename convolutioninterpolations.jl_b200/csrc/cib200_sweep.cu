@@ -101,15 +101,11 @@ __device__ __forceinline__ double line_mean(const double *bl, int pad, int pitch
 }
 
 // NS = polynomial node count of the kernel (6 for b5, 8 otherwise), EQS-1 ghosts per side
+// core on registers: y[0..7] = centred boundary values (y[0] = the boundary point itself, then inward; 0 past the line),
+// gh[j-1] = ghost j = 1..EQS-1 counted outward
 template <int NS, int EQS>
-__device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, int n, double mean, double h, int bc,
-                                                bool right, const GhostMats &gm) {
-  double y[8];  // centred boundary values, y[0] = the boundary point itself, then inward
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int j = right ? (n - 1 - k) : k;
-    y[k] = k < n ? __dsub_rn(bl[(pad + j) * pitch], mean) : 0.0;
-  }
+__device__ __forceinline__ void ghost_poly_core(const double (&y)[8], int n, double mean, double h, int bc, bool right,
+                                                const GhostMats &gm, double (&gh)[EQS > 1 ? EQS - 1 : 1]) {
   bool use_poly = false;
   if (n >= NS && (bc == CIB200_BC_DETECT || bc == CIB200_BC_POLY)) {
     if (bc == CIB200_BC_POLY) {
@@ -149,16 +145,13 @@ __device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, 
       use_poly = !periodic && !high_curv && !high_d3;
     }
   }
-  const int row0 = right ? (pad + n) : (pad - 1);  // slot of ghost j = 1
-  const int step = right ? pitch : -pitch;
-  double *g = bl + row0 * pitch;
   if (use_poly) {
 #pragma unroll
     for (int j = 1; j <= EQS - 1; ++j) {
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < NS; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.poly[j - 1][k], y[k]));
-      g[(j - 1) * step] = __dadd_rn(mean, acc);
+      gh[j - 1] = __dadd_rn(mean, acc);
     }
   } else if (bc == CIB200_BC_QUADRATIC) {
 #pragma unroll
@@ -166,7 +159,7 @@ __device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, 
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.quad[j - 1][k], y[k]));
-      g[(j - 1) * step] = __dadd_rn(mean, acc);
+      gh[j - 1] = __dadd_rn(mean, acc);
     }
   } else {
 #pragma unroll
@@ -174,8 +167,118 @@ __device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, 
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < 2; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.lin[j - 1][k], y[k]));
-      g[(j - 1) * step] = __dadd_rn(mean, acc);
+      gh[j - 1] = __dadd_rn(mean, acc);
     }
+  }
+}
+
+// the same on a line held in shared memory: bl = buf + ti, line(j) = bl[(pad + j) * pitch]
+template <int NS, int EQS>
+__device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, int n, double mean, double h, int bc,
+                                                bool right, const GhostMats &gm) {
+  double y[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = right ? (n - 1 - k) : k;
+    y[k] = k < n ? __dsub_rn(bl[(pad + j) * pitch], mean) : 0.0;
+  }
+  double gh[EQS > 1 ? EQS - 1 : 1];
+  ghost_poly_core<NS, EQS>(y, n, mean, h, bc, right, gm, gh);
+  const int row0 = right ? (pad + n) : (pad - 1);  // slot of ghost j = 1
+  const int step = right ? pitch : -pitch;
+  double *g = bl + row0 * pitch;
+#pragma unroll
+  for (int j = 1; j <= EQS - 1; ++j) g[(j - 1) * step] = gh[j - 1];
+}
+
+// ---- device-side constructor ghost fill: one axis pass of create_convolutional_coefs ------------------------------
+// (create_convolutional_coefs.jl:141-160, apply_boundary_conditions_for_dim! :200-370).  The array is viewed as
+// [inner][n][outer]; the pass copies every line into its place in [inner][n + 2 pad][outer] and appends the pad =
+// eqs - 1 ghost values per side.  A line's ghosts need its mean (all of it) and its first / last 8 values only, so the
+// pass is a streaming copy: nothing is staged, loads and stores are coalesced along `inner` (axis >= 1: one thread per
+// line) or along the line (axis 0: one warp per line).
+template <typename T, int EQS>
+__global__ void __launch_bounds__(256) pad_lines_kernel(const T *__restrict__ in, T *__restrict__ out, long long inner,
+                                                        int n, long long outer, int bcl, int bcr, double h,
+                                                        const GhostMats gm) {
+  constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
+  constexpr int PAD = EQS - 1;
+  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= inner * outer) return;
+  const long long i = line % inner, o = line / inner;
+  const T *__restrict__ src = in + i + o * inner * n;
+  T *__restrict__ dst = out + i + o * inner * (n + 2 * PAD) + (long long)PAD * inner;
+  double s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.0;
+  int j = 0;
+  for (; j + 8 <= n; j += 8) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = src[(long long)(j + k) * inner];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dst[(long long)(j + k) * inner] = v[k];
+      s[k] = __dadd_rn(s[k], (double)v[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (j + k < n) {
+      const T v = src[(long long)(j + k) * inner];
+      dst[(long long)(j + k) * inner] = v;
+      s[k] = __dadd_rn(s[k], (double)v);
+    }
+  const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
+                               __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
+  const double mean = __ddiv_rn(sum, (double)n);
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    double y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int jj = side ? (n - 1 - k) : k;
+      y[k] = k < n ? __dsub_rn((double)src[(long long)jj * inner], mean) : 0.0;
+    }
+    double gh[EQS > 1 ? EQS - 1 : 1];
+    ghost_poly_core<NS, EQS>(y, n, mean, h, side ? bcr : bcl, side == 1, gm, gh);
+#pragma unroll
+    for (int g = 1; g <= PAD; ++g) dst[(long long)(side ? (n - 1 + g) : -g) * inner] = (T)gh[g - 1];
+  }
+}
+
+template <typename T, int EQS>
+__global__ void __launch_bounds__(256) pad_lines_axis0_kernel(const T *__restrict__ in, T *__restrict__ out, int n,
+                                                              long long outer, int bcl, int bcr, double h,
+                                                              const GhostMats gm) {
+  constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
+  constexpr int PAD = EQS - 1;
+  const int lane = threadIdx.x & 31;
+  const long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (o >= outer) return;  // warp-uniform
+  const T *__restrict__ src = in + o * n;
+  T *__restrict__ dst = out + o * (n + 2 * PAD) + PAD;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    const T v = src[j];
+    dst[j] = v;
+    s = __dadd_rn(s, (double)v);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, d));
+  const double mean = __ddiv_rn(s, (double)n);
+  if (lane < 2) {  // lane 0: left side, lane 1: right side
+    const int side = lane;
+    double y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int jj = side ? (n - 1 - k) : k;
+      y[k] = k < n ? __dsub_rn((double)src[jj], mean) : 0.0;
+    }
+    double gh[EQS > 1 ? EQS - 1 : 1];
+    ghost_poly_core<NS, EQS>(y, n, mean, h, side ? bcr : bcl, side == 1, gm, gh);
+#pragma unroll
+    for (int g = 1; g <= PAD; ++g) dst[side ? (n - 1 + g) : -g] = (T)gh[g - 1];
   }
 }
 
@@ -1263,6 +1366,83 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     shape[d] = nout;
   }
   return CIB200_OK;
+}
+
+template <typename T, int EQS>
+static int launch_pad(const T *in, T *out, long long inner, long long n, long long outer, int bcl, int bcr, double h,
+                      const GhostMats &gm, cudaStream_t st) {
+  if (inner == 1) {
+    const long long blocks = (outer * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return -1;
+    pad_lines_axis0_kernel<T, EQS><<<(unsigned)blocks, 256, 0, st>>>(in, out, (int)n, outer, bcl, bcr, h, gm);
+  } else {
+    const long long blocks = (inner * outer + 255) / 256;
+    if (blocks > 0x7fffffffLL) return -1;
+    pad_lines_kernel<T, EQS><<<(unsigned)blocks, 256, 0, st>>>(in, out, inner, (int)n, outer, bcl, bcr, h, gm);
+  }
+  CIB_LAUNCHED();
+  CIB_CUDA(cudaGetLastError());
+  return CIB200_OK;
+}
+
+// create_convolutional_coefs on the device: axis passes in order, each growing its axis by 2 (eqs - 1)
+template <typename T>
+static int build_coefs_t(int ndim, const long long *n, const T *d_values, const double *h, const int *kernel,
+                         const int *bcl, const int *bcr, T *d_coefs, cudaStream_t st) {
+  TempBufs tmp;
+  tmp.st = st;
+  long long shape[CIB200_MAX_SWEEP_DIM];
+  for (int d = 0; d < ndim; ++d) shape[d] = n[d];
+  const T *cur = d_values;
+  int rc;
+  for (int d = 0; d < ndim; ++d) {
+    const int eqs = kernel_eqs(kernel[d]);
+    if (eqs < 2 || n[d] >= (1LL << 31)) {
+      set_error("cib200_build_coefs_device: bad axis %d", d);
+      return CIB200_EINVAL;
+    }
+    long long inner = 1, outer = 1;
+    for (int j = 0; j < d; ++j) inner *= shape[j];
+    for (int j = d + 1; j < ndim; ++j) outer *= shape[j];
+    GhostMats gm;
+    memset(&gm, 0, sizeof gm);
+    gm.poly_nodes = kernel_poly_nodes(kernel[d]);
+    lagrange_rows(gm.poly_nodes, eqs - 1, &gm.poly[0][0], 8);
+    lagrange_rows(2, eqs - 1, &gm.lin[0][0], 2);
+    lagrange_rows(3, eqs - 1, &gm.quad[0][0], 3);
+    T *next;
+    if (d == ndim - 1) {
+      next = d_coefs;
+    } else {
+      if ((rc = tmp.alloc((void **)&next, sizeof(T) * (size_t)(inner * (n[d] + 2 * (eqs - 1)) * outer)))) return rc;
+    }
+    switch (eqs) {
+      case 2: rc = launch_pad<T, 2>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 3: rc = launch_pad<T, 3>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 4: rc = launch_pad<T, 4>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 5: rc = launch_pad<T, 5>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 6: rc = launch_pad<T, 6>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 7: rc = launch_pad<T, 7>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 8: rc = launch_pad<T, 8>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 9: rc = launch_pad<T, 9>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      default: rc = -1;
+    }
+    if (rc < 0) {
+      set_error("cib200_build_coefs_device: axis %d: unsupported eqs %d or grid too large", d, eqs);
+      return CIB200_EUNSUPPORTED;
+    }
+    if (rc) return rc;
+    cur = next;
+    shape[d] = n[d] + 2 * (eqs - 1);
+  }
+  return CIB200_OK;
+}
+
+int sweep_build_coefs(int ndim, int dtype, const long long *n, const void *d_values, const double *h, const int *kernel,
+                      const int *bcl, const int *bcr, void *d_coefs, cudaStream_t st) {
+  if (dtype == CIB200_F32)
+    return build_coefs_t<float>(ndim, n, (const float *)d_values, h, kernel, bcl, bcr, (float *)d_coefs, st);
+  return build_coefs_t<double>(ndim, n, (const double *)d_values, h, kernel, bcl, bcr, (double *)d_coefs, st);
 }
 
 int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *n_out, const void *d_in, void *d_out,

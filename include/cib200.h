@@ -71,7 +71,7 @@ typedef struct cib200_itp_desc {
   int32_t ndim;                          /* 1..3                                                    */
   int32_t dtype;                         /* cib200_dtype of coefs / queries / results               */
   int64_t coef_shape[CIB200_MAX_ITP_DIM]; /* size(itp.coefs) = n_d + 2 (eqs_d - 1)                    */
-  const void *coefs;                     /* itp.coefs, ghost-padded, host memory                    */
+  const void *coefs;                     /* itp.coefs, ghost-padded, host (or device) memory        */
   const double *knots[CIB200_MAX_ITP_DIM]; /* itp.knots[d] (extended, length coef_shape[d]), host    */
   double h[CIB200_MAX_ITP_DIM];           /* itp.h                                                   */
   int32_t kernel[CIB200_MAX_ITP_DIM];     /* cib200_kernel per axis                                  */
@@ -101,6 +101,14 @@ const double *cib200_kernel_table(int32_t kernel, int32_t deriv, int32_t *eqs_ou
 int32_t cib200_build_coefs(int32_t ndim, int32_t dtype, const int64_t *n, const void *values,
                            const double *h, const int32_t *kernel, const int32_t *bc_left,
                            const int32_t *bc_right, void *coefs_out);
+/* The same on the DEVICE: one streaming pass per axis (copy the lines into the padded array, append
+ * the eqs - 1 ghosts per side from the line mean and its first / last 8 values).  values / coefs_out are both of
+ * `memkind` (HOST: staged through device memory; DEVICE: asynchronous on `stream`).  A device-resident coefs_out can
+ * be passed as cib200_itp_desc.coefs (cib200_itp_create copies from host or device memory).  Ghost values equal the
+ * host build's up to the association of the line mean (<= 1e-15 relative). */
+int32_t cib200_build_coefs_device(int32_t ndim, int32_t dtype, const int64_t *n, const void *values,
+                                  const double *h, const int32_t *kernel, const int32_t *bc_left,
+                                  const int32_t *bc_right, void *coefs_out, int32_t memkind, void *stream);
 /* replaces extend_vector (convolution/extend_vector.jl:10-18); out has n + 2 n_extra entries */
 int32_t cib200_extend_knots(const double *knots, int64_t n, int32_t n_extra, double *out);
 
@@ -109,6 +117,8 @@ int32_t cib200_extend_knots(const double *knots, int64_t n, int32_t n_extra, dou
  * _build_fast_uniform_convolution, fast_convolution_interpolation_constructor.jl:99-174). */
 int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle);
 int32_t cib200_itp_destroy(cib200_itp *handle);
+/* copies the handle's ghost-padded grid to host memory (fills itp.coefs when the grid was built on the device) */
+int32_t cib200_itp_get_coefs(cib200_itp *handle, void *coefs_out);
 int32_t cib200_itp_set_eval_mode(cib200_itp *handle, int32_t mode);
 
 /* itp.(xs...) : replaces the per-element loop over

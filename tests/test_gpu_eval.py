@@ -413,3 +413,48 @@ def test_host_buffer_pipeline_equals_device_resident(ci):
         host = g.eval(*q)
         assert np.array_equal(host, dev), mode
         g.itp.close()
+
+
+@pytest.mark.parametrize("kernel,bc", [("b5", "detect"), ("b13", "poly"), ("a4", "detect"), ("b7", "linear"),
+                                       ("b9", ("quadratic", "detect"))])
+def test_device_side_coefficient_build_equals_host_build(ci, oracle, kernel, bc):
+    """cib200_build_coefs_device against the host build and the oracle's create_coefs: same ghost
+    branches (:detect decisions included), values equal up to the association of the line mean"""
+    rng = np.random.default_rng(77)
+    for shape in ((41,), (23, 37), (19, 33, 26), (9, 12, 10, 11)):
+        k = tuple(np.linspace(0, 1 + 0.2 * i, s) for i, s in enumerate(shape))
+        v = _field(shape, rng, noise=0.3 if bc == "detect" else 0.05)  # noisy lines exercise both :detect outcomes
+        kk = k[0] if len(shape) == 1 else k
+        gh = ci.convolution_interpolation(kk, v, kernel=kernel, bc=bc, extrap="flat")
+        gd = ci.convolution_interpolation(kk, v, kernel=kernel, bc=bc, extrap="flat", coefs_on="device")
+        o = oracle.convolution_interpolation(kk, v, kernel=kernel, bc=bc, extrap="flat")
+        ch, cd = gh.itp.coefs, gd.itp.coefs
+        assert ch.shape == cd.shape == o.coefs.shape
+        scale = np.abs(o.coefs).max()
+        assert np.abs(cd - o.coefs).max() <= 1e-13 * scale
+        assert np.abs(cd - ch).max() <= 1e-13 * scale
+        q = np.stack([rng.uniform(-0.05, kk_[-1] + 0.05, 2000) for kk_ in k])
+        assert rel_err(gd.eval(*q), o.eval(*q), _scale(o)).max() <= TOL64
+
+
+def test_device_side_coefficient_build_float32_and_c_abi_host_buffers(ci, oracle):
+    import ctypes as C
+    rng = np.random.default_rng(78)
+    shape = (30, 28, 31)
+    v = _field(shape, rng).astype(np.float32)
+    k = tuple(np.linspace(0, 1, s) for s in shape)
+    gh = ci.convolution_interpolation(k, v, kernel="b5", bc="poly")
+    gd = ci.convolution_interpolation(k, v, kernel="b5", bc="poly", coefs_on="device")
+    assert gd.itp.coefs.dtype == np.float32
+    assert np.abs(gd.itp.coefs.astype(np.float64) - gh.itp.coefs).max() <= 2e-6 * np.abs(gh.itp.coefs).max()
+    # the C entry point with HOST buffers (staged through the device)
+    L = ci.lib()
+    v64 = np.asfortranarray(_field(shape, rng))
+    out = np.zeros(tuple(s + 8 for s in shape), order="F")
+    n = (C.c_int64 * 3)(*shape)
+    hh = (C.c_double * 3)(*[kk[1] - kk[0] for kk in k])
+    kid = (C.c_int32 * 3)(0, 0, 0)
+    bc = (C.c_int32 * 3)(0, 0, 0)
+    ci.check(L.cib200_build_coefs_device(3, 0, n, v64.ctypes.data, hh, kid, bc, bc, out.ctypes.data, 0, None))
+    o = oracle.convolution_interpolation(k, v64, kernel="b5", bc="detect")
+    assert np.abs(out - o.coefs).max() <= 1e-13 * np.abs(o.coefs).max()
