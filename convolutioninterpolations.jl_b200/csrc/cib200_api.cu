@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -518,6 +519,7 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
 
   cib200_itp *h = new cib200_itp();
   memset(h, 0, sizeof *h);
+  h->mu = new std::mutex();
   h->device = dev;
   h->dtype = desc->dtype;
   h->eval_mode = CIB200_EVAL_AUTO;
@@ -603,6 +605,7 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
   }
   CIB_CREATE_CUDA(cudaMalloc(&h->d_status, sizeof(EvalStatus)));
   CIB_CREATE_CUDA(cudaMemset(h->d_status, 0xff, sizeof(EvalStatus)));
+  CIB_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_busy, cudaEventDisableTiming));
 #undef CIB_CREATE_CUDA
   *handle = h;
   return CIB200_OK;
@@ -627,6 +630,8 @@ int32_t cib200_itp_destroy(cib200_itp *h) {
   if (h->d_bin_scratch) cudaFree(h->d_bin_scratch);
   for (int k = 0; k < 5; ++k)
     if (h->prof_ev[k]) cudaEventDestroy(h->prof_ev[k]);
+  if (h->ev_busy) cudaEventDestroy(h->ev_busy);
+  delete h->mu;
   delete h;
   return CIB200_OK;
 }
@@ -669,8 +674,28 @@ int64_t cib200_itp_scratch_bytes(cib200_itp *h, int64_t nq) {
   return h->eval_mode == CIB200_EVAL_BINNED ? binned_scratch_bytes(h, nq) : 0;
 }
 
+static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long nq, void *out, int32_t memkind,
+                                  void *stream, int64_t *first_bad, const char *who);
+
+// Calls on ONE handle share its scratch (binning records, staging ring, status words): they are serialised here - the
+// host side by a mutex, the device side by an event recorded after a call's last kernel and awaited by the next call's
+// stream - so that `Threads.@threads` over chunks of a query vector (the reference's threading pattern) is safe.
 static int32_t eval_common(cib200_itp *h, const Coords &c_in, long long nq, void *out, int32_t memkind,
                            void *stream, int64_t *first_bad, const char *who) {
+  std::lock_guard<std::mutex> guard(*h->mu);
+  int dev = -1;
+  CIB_CUDA(cudaGetDevice(&dev));
+  if (dev != h->device) CIB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (memkind == CIB200_DEVICE && h->busy_valid) CIB_CUDA(cudaStreamWaitEvent(st, h->ev_busy, 0));
+  const int32_t rc = eval_common_locked(h, c_in, nq, out, memkind, stream, first_bad, who);
+  if (memkind == CIB200_DEVICE && nq > 0 && cudaEventRecord(h->ev_busy, st) == cudaSuccess) h->busy_valid = 1;
+  if (dev != h->device) cudaSetDevice(dev);
+  return rc;
+}
+
+static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long nq, void *out, int32_t memkind,
+                                  void *stream, int64_t *first_bad, const char *who) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nd = h->p.ndim;
   const size_t es = esize(h->dtype);

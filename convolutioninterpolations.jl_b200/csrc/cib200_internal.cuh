@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "cib200.h"
@@ -102,6 +103,10 @@ struct cib200_itp {
   size_t bin_scratch_bytes;
   void *bin_state;  // opaque, owned by cib200_binned.cu
   // optional pass timing (cib200_itp_set_profiling): events on the launching stream around the passes of a call
+  // serialisation of concurrent calls on one handle (cib200_api.cu eval_common)
+  std::mutex *mu;
+  cudaEvent_t ev_busy;
+  int busy_valid;
   int profiling;
   cudaEvent_t prof_ev[5];  // before binning | after scatter | after cell sort | after evaluation | after spill
   int prof_valid;

@@ -458,3 +458,38 @@ def test_device_side_coefficient_build_float32_and_c_abi_host_buffers(ci, oracle
     ci.check(L.cib200_build_coefs_device(3, 0, n, v64.ctypes.data, hh, kid, bc, bc, out.ctypes.data, 0, None))
     o = oracle.convolution_interpolation(k, v64, kernel="b5", bc="detect")
     assert np.abs(out - o.coefs).max() <= 1e-13 * np.abs(o.coefs).max()
+
+
+def test_concurrent_calls_on_one_handle_are_serialised(ci):
+    """Threads.@threads over chunks of a query vector is the reference's threading pattern: concurrent calls on one
+    handle (shared binning scratch / staging ring) must give the same bits as sequential calls"""
+    import threading
+    import torch
+    rng = np.random.default_rng(91)
+    k = tuple(np.linspace(0, 1, 48) for _ in range(3))
+    g = ci.convolution_interpolation(k, _field((48, 48, 48), rng), extrap="flat", eval_mode="binned")
+    chunks = [rng.uniform(-0.02, 1.02, (3, 300_000)) for _ in range(6)]
+    seq = [g.eval(*c) for c in chunks]
+    res = [None] * len(chunks)
+
+    def work(i):
+        res[i] = g.eval(*chunks[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(chunks))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for a, b in zip(seq, res):
+        assert np.array_equal(a, b)
+    # device-resident calls on different streams
+    dq = [[torch.from_numpy(a).cuda() for a in c] for c in chunks]
+    streams = [torch.cuda.Stream() for _ in chunks]
+    outs = []
+    torch.cuda.synchronize()
+    for s_, q in zip(streams, dq):
+        with torch.cuda.stream(s_):
+            outs.append(g.eval(*q))
+    torch.cuda.synchronize()
+    for a, o in zip(seq, outs):
+        assert np.array_equal(a, o.cpu().numpy())
