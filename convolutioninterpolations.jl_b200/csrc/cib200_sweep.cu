@@ -191,23 +191,40 @@ __device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, 
   for (int j = 1; j <= EQS - 1; ++j) g[(j - 1) * step] = gh[j - 1];
 }
 
-// ---- device-side constructor ghost fill: one axis pass of create_convolutional_coefs ------------------------------
-// (create_convolutional_coefs.jl:141-160, apply_boundary_conditions_for_dim! :200-370).  The array is viewed as
-// [inner][n][outer]; the pass copies every line into its place in [inner][n + 2 pad][outer] and appends the pad =
-// eqs - 1 ghost values per side.  A line's ghosts need its mean (all of it) and its first / last 8 values only, so the
-// pass is a streaming copy: nothing is staged, loads and stores are coalesced along `inner` (axis >= 1: one thread per
-// line) or along the line (axis 0: one warp per line).
+// ---- device-side constructor ghost fill: create_convolutional_coefs on the GPU ------------------------------------
+// (create_convolutional_coefs.jl:141-160, apply_boundary_conditions_for_dim! :200-370).  The axis passes run IN PLACE
+// on the final padded array: pass 0 copies every line of the dense values into its place and appends its ghosts, pass
+// d >= 1 reads the lines along axis d (over the padded extent of the axes < d, which form one contiguous block, and the
+// interior extent of the axes > d) and writes only their 2 (eqs_d - 1) ghosts.  A line's ghosts need its mean (all of
+// it) and its first / last 8 values, so every pass is a streaming read; nothing is staged, accesses are coalesced along
+// the line (axis 0: one warp per line) or along the contiguous block (axis >= 1: one thread per line).
+struct PadGeom {
+  int nouter;                                  // axes after the swept one
+  long long n[CIB200_MAX_SWEEP_DIM];           // their interior extents
+  long long off[CIB200_MAX_SWEEP_DIM];         // pad_j * stride_j: start of the interior along axis j
+  long long stride[CIB200_MAX_SWEEP_DIM];      // their element strides in the padded array
+};
+__device__ __forceinline__ long long pad_outer_offset(const PadGeom &g, long long o) {
+  long long r = o, a = 0;
+  for (int j = 0; j < g.nouter; ++j) {
+    const long long i = r % g.n[j];
+    r /= g.n[j];
+    a += g.off[j] + i * g.stride[j];
+  }
+  return a;
+}
+
+// axis >= 1, in place: arr viewed as [inner][n + 2 PAD][...]; thread = (i, o)
 template <typename T, int EQS>
-__global__ void __launch_bounds__(256) pad_lines_kernel(const T *__restrict__ in, T *__restrict__ out, long long inner,
-                                                        int n, long long outer, int bcl, int bcr, double h,
-                                                        const GhostMats gm) {
+__global__ void __launch_bounds__(256) ghost_lines_kernel(T *__restrict__ arr, long long inner, int n, long long outer,
+                                                          const PadGeom geom, int bcl, int bcr, double h,
+                                                          const GhostMats gm) {
   constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
   constexpr int PAD = EQS - 1;
   const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (line >= inner * outer) return;
   const long long i = line % inner, o = line / inner;
-  const T *__restrict__ src = in + i + o * inner * n;
-  T *__restrict__ dst = out + i + o * inner * (n + 2 * PAD) + (long long)PAD * inner;
+  T *__restrict__ src = arr + i + (long long)PAD * inner + pad_outer_offset(geom, o);  // first interior point
   double s[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = 0.0;
@@ -217,18 +234,11 @@ __global__ void __launch_bounds__(256) pad_lines_kernel(const T *__restrict__ in
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = src[(long long)(j + k) * inner];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      dst[(long long)(j + k) * inner] = v[k];
-      s[k] = __dadd_rn(s[k], (double)v[k]);
-    }
+    for (int k = 0; k < 8; ++k) s[k] = __dadd_rn(s[k], (double)v[k]);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    if (j + k < n) {
-      const T v = src[(long long)(j + k) * inner];
-      dst[(long long)(j + k) * inner] = v;
-      s[k] = __dadd_rn(s[k], (double)v);
-    }
+    if (j + k < n) s[k] = __dadd_rn(s[k], (double)src[(long long)(j + k) * inner]);
   const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
                                __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
   const double mean = __ddiv_rn(sum, (double)n);
@@ -243,21 +253,22 @@ __global__ void __launch_bounds__(256) pad_lines_kernel(const T *__restrict__ in
     double gh[EQS > 1 ? EQS - 1 : 1];
     ghost_poly_core<NS, EQS>(y, n, mean, h, side ? bcr : bcl, side == 1, gm, gh);
 #pragma unroll
-    for (int g = 1; g <= PAD; ++g) dst[(long long)(side ? (n - 1 + g) : -g) * inner] = (T)gh[g - 1];
+    for (int g = 1; g <= PAD; ++g) src[(long long)(side ? (n - 1 + g) : -g) * inner] = (T)gh[g - 1];
   }
 }
 
+// axis 0: copies line o of the dense values into the padded array and appends its ghosts; one warp per line
 template <typename T, int EQS>
 __global__ void __launch_bounds__(256) pad_lines_axis0_kernel(const T *__restrict__ in, T *__restrict__ out, int n,
-                                                              long long outer, int bcl, int bcr, double h,
-                                                              const GhostMats gm) {
+                                                              long long outer, const PadGeom geom, int bcl, int bcr,
+                                                              double h, const GhostMats gm) {
   constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
   constexpr int PAD = EQS - 1;
   const int lane = threadIdx.x & 31;
   const long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (o >= outer) return;  // warp-uniform
   const T *__restrict__ src = in + o * n;
-  T *__restrict__ dst = out + o * (n + 2 * PAD) + PAD;
+  T *__restrict__ dst = out + PAD + pad_outer_offset(geom, o);
   double s = 0.0;
   for (int j = lane; j < n; j += 32) {
     const T v = src[j];
@@ -1369,62 +1380,69 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
 }
 
 template <typename T, int EQS>
-static int launch_pad(const T *in, T *out, long long inner, long long n, long long outer, int bcl, int bcr, double h,
-                      const GhostMats &gm, cudaStream_t st) {
-  if (inner == 1) {
+static int launch_pad(const T *in, T *arr, int axis, long long inner, long long n, long long outer, const PadGeom &geom,
+                      int bcl, int bcr, double h, const GhostMats &gm, cudaStream_t st) {
+  if (axis == 0) {
     const long long blocks = (outer * 32 + 255) / 256;
     if (blocks > 0x7fffffffLL) return -1;
-    pad_lines_axis0_kernel<T, EQS><<<(unsigned)blocks, 256, 0, st>>>(in, out, (int)n, outer, bcl, bcr, h, gm);
+    pad_lines_axis0_kernel<T, EQS><<<(unsigned)blocks, 256, 0, st>>>(in, arr, (int)n, outer, geom, bcl, bcr, h, gm);
   } else {
     const long long blocks = (inner * outer + 255) / 256;
     if (blocks > 0x7fffffffLL) return -1;
-    pad_lines_kernel<T, EQS><<<(unsigned)blocks, 256, 0, st>>>(in, out, inner, (int)n, outer, bcl, bcr, h, gm);
+    ghost_lines_kernel<T, EQS><<<(unsigned)blocks, 256, 0, st>>>(arr, inner, (int)n, outer, geom, bcl, bcr, h, gm);
   }
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   return CIB200_OK;
 }
 
-// create_convolutional_coefs on the device: axis passes in order, each growing its axis by 2 (eqs - 1)
+// create_convolutional_coefs on the device: axis passes in order, in place on the padded array
 template <typename T>
 static int build_coefs_t(int ndim, const long long *n, const T *d_values, const double *h, const int *kernel,
                          const int *bcl, const int *bcr, T *d_coefs, cudaStream_t st) {
-  TempBufs tmp;
-  tmp.st = st;
-  long long shape[CIB200_MAX_SWEEP_DIM];
-  for (int d = 0; d < ndim; ++d) shape[d] = n[d];
-  const T *cur = d_values;
-  int rc;
+  long long np[CIB200_MAX_SWEEP_DIM], stride[CIB200_MAX_SWEEP_DIM];
+  int pad[CIB200_MAX_SWEEP_DIM];
+  long long tot = 1;
   for (int d = 0; d < ndim; ++d) {
     const int eqs = kernel_eqs(kernel[d]);
     if (eqs < 2 || n[d] >= (1LL << 31)) {
       set_error("cib200_build_coefs_device: bad axis %d", d);
       return CIB200_EINVAL;
     }
-    long long inner = 1, outer = 1;
-    for (int j = 0; j < d; ++j) inner *= shape[j];
-    for (int j = d + 1; j < ndim; ++j) outer *= shape[j];
+    pad[d] = eqs - 1;
+    np[d] = n[d] + 2 * pad[d];
+    stride[d] = tot;
+    tot *= np[d];
+  }
+  for (int d = 0; d < ndim; ++d) {
+    const int eqs = pad[d] + 1;
+    PadGeom geom;
+    memset(&geom, 0, sizeof geom);
+    long long outer = 1;
+    for (int j = d + 1; j < ndim; ++j) {
+      geom.n[geom.nouter] = n[j];
+      geom.off[geom.nouter] = (long long)pad[j] * stride[j];
+      geom.stride[geom.nouter] = stride[j];
+      ++geom.nouter;
+      outer *= n[j];
+    }
+    const long long inner = stride[d];  // the axes < d are complete: one contiguous block of prod np[j] elements
     GhostMats gm;
     memset(&gm, 0, sizeof gm);
     gm.poly_nodes = kernel_poly_nodes(kernel[d]);
     lagrange_rows(gm.poly_nodes, eqs - 1, &gm.poly[0][0], 8);
     lagrange_rows(2, eqs - 1, &gm.lin[0][0], 2);
     lagrange_rows(3, eqs - 1, &gm.quad[0][0], 3);
-    T *next;
-    if (d == ndim - 1) {
-      next = d_coefs;
-    } else {
-      if ((rc = tmp.alloc((void **)&next, sizeof(T) * (size_t)(inner * (n[d] + 2 * (eqs - 1)) * outer)))) return rc;
-    }
+    int rc;
     switch (eqs) {
-      case 2: rc = launch_pad<T, 2>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 3: rc = launch_pad<T, 3>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 4: rc = launch_pad<T, 4>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 5: rc = launch_pad<T, 5>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 6: rc = launch_pad<T, 6>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 7: rc = launch_pad<T, 7>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 8: rc = launch_pad<T, 8>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
-      case 9: rc = launch_pad<T, 9>(cur, next, inner, n[d], outer, bcl[d], bcr[d], h[d], gm, st); break;
+      case 2: rc = launch_pad<T, 2>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 3: rc = launch_pad<T, 3>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 4: rc = launch_pad<T, 4>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 5: rc = launch_pad<T, 5>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 6: rc = launch_pad<T, 6>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 7: rc = launch_pad<T, 7>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 8: rc = launch_pad<T, 8>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
+      case 9: rc = launch_pad<T, 9>(d_values, d_coefs, d, inner, n[d], outer, geom, bcl[d], bcr[d], h[d], gm, st); break;
       default: rc = -1;
     }
     if (rc < 0) {
@@ -1432,8 +1450,6 @@ static int build_coefs_t(int ndim, const long long *n, const T *d_values, const 
       return CIB200_EUNSUPPORTED;
     }
     if (rc) return rc;
-    cur = next;
-    shape[d] = n[d] + 2 * (eqs - 1);
   }
   return CIB200_OK;
 }
