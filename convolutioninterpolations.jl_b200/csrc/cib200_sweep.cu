@@ -51,6 +51,8 @@ struct SweepParams {
   const double *W;     // resample: [taps][n_out] blended weights ; smooth: kw[taps]
   const double *Wk;    // resample: the same weights as [n_out][taps] (16-byte aligned rows: taps is even)
   const int *base;     // resample: first tap index into the padded line (0-based) per output
+  double kwc[64];      // smooth: the normalised Gaussian taps again, BY VALUE: a kernel instantiated for a compile-time
+                       // tap count reads them as constant-bank operands (DFMA R, R, c[0][imm], R: no load at all)
 };
 
 // ---- per-output-knot weights: convolution_resample.jl:320-361 minus the data ------------------
@@ -329,6 +331,10 @@ __device__ __forceinline__ void ghost_gauss_side(double *bl, int pad, int pitch,
 }
 
 static constexpr int SMOOTH_R = 8;    // consecutive outputs per thread in the Gaussian FIR (sliding register window)
+#ifndef CIB_SMOOTH_RP
+#define CIB_SMOOTH_RP 16
+#endif
+static constexpr int SMOOTH_RP = CIB_SMOOTH_RP;  // the same in the pipelined kernel
 static constexpr int RESAMPLE_R = 8;  // anchor offsets a register window of the resample pass can serve
 
 // sum_l win[O + l] * w[l] with static register indices; three partial sums keep the FP64 pipe busy from one warp
@@ -779,16 +785,16 @@ __device__ __forceinline__ void resample_lines2(const double *bl, const int pitc
 }
 
 template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
-__global__ void __launch_bounds__(SMOOTH ? 768 : (AXIS0 ? 640 : 384), 1)
+__global__ void __launch_bounds__(SMOOTH ? (SMOOTH_RP > 8 ? 512 : 768) : (AXIS0 ? 640 : 384), 1)
     sweep_pipe_kernel(const __grid_constant__ CUtensorMap tmap, SweepParams sp, GhostMats gm, PipeCfg cfg,
                       const T *__restrict__ in, T *__restrict__ out, long long ntiles) {
   extern __shared__ __align__(128) double sm[];
   constexpr int PITCH = AXIS0 ? 33 : 32;
-  constexpr int TP = (TAPS > 0) ? TAPS : 2;
+  constexpr int TP = (!SMOOTH && TAPS > 0) ? TAPS : 2;
   const int pad = sp.pad;
   const int n = (int)sp.n_in, nout = (int)sp.n_out;
   const int nrow = n + 2 * pad;
-  const int bufsz = ((nrow + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R)) * PITCH + 1) & ~1;  // doubles, even
+  const int bufsz = ((nrow + (SMOOTH ? 2 * SMOOTH_RP : RESAMPLE_R)) * PITCH + 1) & ~1;  // doubles, even
   const int NB = cfg.nb;
   double *extra = sm + NB * bufsz;  // smooth: kw[taps] ; resample (axis >= 1): W[nout][TP] + base[nout]
   int *bsm = (int *)(extra + TP * nout);
@@ -891,7 +897,7 @@ __global__ void __launch_bounds__(SMOOTH ? 768 : (AXIS0 ? 640 : 384), 1)
         if (SMOOTH) {
           ghost_gauss_side(bl, pad, PITCH, n, mean, sp.eqs, side == 1);
         } else {
-          constexpr int EQS = TAPS > 0 ? TAPS / 2 : 5;
+          constexpr int EQS = (!SMOOTH && TAPS > 0) ? TAPS / 2 : 5;
           constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
           ghost_poly_side<NS, EQS>(bl, pad, PITCH, n, mean, sp.h, side ? sp.bcr : sp.bcl, side == 1, gm);
         }
@@ -922,11 +928,38 @@ __global__ void __launch_bounds__(SMOOTH ? 768 : (AXIS0 ? 640 : 384), 1)
         const long long tw0 = cfg.stats ? clock64() : 0;
         mbar_wait(full + b, (unsigned)rev & 1u);
         const long long tw1 = cfg.stats ? clock64() : 0;
-        if (SMOOTH) {
+        if (SMOOTH && TAPS > 0) {
+          // compile-time tap count: fully unrolled, every input row is loaded ONCE per block of R outputs and feeds the
+          // (up to) R accumulators it contributes to; the taps are literal offsets into the kernel-parameter bank, so
+          // the only shared-memory traffic is the R + TAPS - 1 input rows per R x TAPS DFMAs
+          constexpr int R = SMOOTH_RP;
+          const int nblk = (nout + R - 1) / R;
+          if (lane < valid)
+            for (int kb = cw; kb < nblk; kb += CW) {
+              const int k0 = kb * R;
+              double acc[R];
+#pragma unroll
+              for (int r = 0; r < R; ++r) acc[r] = 0.0;
+              const double *p = buf + k0 * PITCH + lane;
+#pragma unroll
+              for (int j = 0; j < R + TAPS - 1; ++j) {
+                const double x = p[j * PITCH];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                  if (j - r >= 0 && j - r < TAPS) acc[r] = fma(x, sp.kwc[(j - r >= 0 && j - r < TAPS) ? j - r : 0], acc[r]);
+              }
+              T *op = AXIS0 ? out + (line0 + lane) * nout + k0
+                            : out + tile_i * 32 + lane + (long long)k0 * sp.inner + o * sp.inner * nout;
+              const long long os = AXIS0 ? 1 : sp.inner;
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                if (k0 + r < nout) op[r * os] = (T)acc[r];
+            }
+        } else if (SMOOTH) {
           // FIR with a sliding register window, software-pipelined: the R inputs the NEXT group of R taps slides in
           // are loaded (R independent LDS) before the current group's R*R DFMAs are issued, so the shared-memory
           // latency never sits between dependent DFMAs (a consumer group runs with ~2 warps per scheduler)
-          constexpr int R = SMOOTH_R;
+          constexpr int R = SMOOTH_RP;
           const double *kw = extra;
           const int taps = sp.taps;
           const int nblk = (nout + R - 1) / R;
@@ -1162,7 +1195,18 @@ static int launch_pipe_kernel(const SweepParams &sp, const GhostMats &gm, const 
 template <typename T, bool SMOOTH, bool AXIS0>
 static int launch_pipe_taps(const SweepParams &sp, const GhostMats &gm, const PipeCfg &cfg, const T *in, T *out,
                             long long ntiles, int threads, size_t smem, cudaStream_t st) {
-  if (SMOOTH) return launch_pipe_kernel<T, true, AXIS0, 0>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+  if (SMOOTH) {
+    // tap counts of common B values get the fully unrolled constant-operand FIR (B = 0.05 -> E = 24 -> 49 taps is the
+    // reference's README benchmark shape); any other falls back to the run-time loop
+    if (env_int("CIB200_SMOOTH_NO_CONST", 0) != 1) switch (sp.taps) {
+      case 13: return launch_pipe_kernel<T, true, AXIS0, 13>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 17: return launch_pipe_kernel<T, true, AXIS0, 17>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 25: return launch_pipe_kernel<T, true, AXIS0, 25>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 35: return launch_pipe_kernel<T, true, AXIS0, 35>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 49: return launch_pipe_kernel<T, true, AXIS0, 49>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    }
+    return launch_pipe_kernel<T, true, AXIS0, 0>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+  }
   switch (sp.taps) {
     case 4: return launch_pipe_kernel<T, false, AXIS0, 4>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
     case 6: return launch_pipe_kernel<T, false, AXIS0, 6>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
@@ -1183,7 +1227,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
   if (env_int("CIB200_SWEEP_NO_PIPE", 0) == 1) return -1;
   if (sizeof(T) != sizeof(double)) return -1;  // the asynchronous staging copies 8-byte elements
   const int pitch = axis0 ? 33 : 32;
-  const size_t bufsz = (((size_t)(sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_R : RESAMPLE_R)) * pitch + 1) & ~(size_t)1);
+  const size_t bufsz = (((size_t)(sp.n_in + 2 * sp.pad + (SMOOTH ? 2 * SMOOTH_RP : RESAMPLE_R)) * pitch + 1) & ~(size_t)1);
   const size_t tile_bytes = sizeof(double) * bufsz;
   const size_t bar_bytes = 8 * 3 * PIPE_MAX_NB;
   const size_t budget = (size_t)max_dyn_smem();
@@ -1205,7 +1249,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
   // consumers: a group of cwg warps works on one tile
   int regs_per_thread;  // what ptxas needs for the consumer code (bounds the thread count: 64k registers per SM)
   if (SMOOTH) {
-    cfg.cwg = (int)std::max<long long>(1, std::min<long long>(8, (sp.n_out + SMOOTH_R - 1) / SMOOTH_R));
+    cfg.cwg = (int)std::max<long long>(1, std::min<long long>(8, (sp.n_out + SMOOTH_RP - 1) / SMOOTH_RP));
     regs_per_thread = 80;
   } else if (axis0) {
     cfg.cwg = 8;
@@ -1214,7 +1258,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
     cfg.cwg = 8;
     regs_per_thread = 168;
   }
-  const int max_warps = SMOOTH ? 24 : (axis0 ? 20 : 12);  // the kernels' __launch_bounds__
+  const int max_warps = SMOOTH ? (SMOOTH_RP > 8 ? 16 : 24) : (axis0 ? 20 : 12);  // the kernels' __launch_bounds__
   (void)regs_per_thread;
   cfg.g = SMOOTH ? 2 : 1;
   // one 3-D TMA per tile when the rows are 16-byte aligned (box 32 x n_in x 1, n_in <= 256); otherwise four loader
@@ -1513,6 +1557,8 @@ static int smooth_t(int ndim, const long long *n, const T *d_in, T *d_out, const
     sp.h = h[d];
     sp.scale = 1.0;
     sp.W = d_kw;
+    if (taps <= 64)
+      for (int l = 0; l < taps; ++l) sp.kwc[l] = kw[(size_t)l];
     T *next = (d == ndim - 1) ? d_out : scratch[d & 1];
     if ((rc = launch_pass<T, true>(sp, gm, cur, next, sp.inner == 1, st))) return rc;
     cur = next;
