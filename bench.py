@@ -197,9 +197,13 @@ def secondary_sweeps(peak):
         ks = tuple(np.linspace(0, 2 * np.pi, n) for _ in range(4))
         v4 = torch.from_numpy(rng.random((n,) * 4)).cuda()
         ms = best_ms(lambda: ci.convolution_smooth(ks, v4, 0.05))
+        # the smooth passes are FP64-bound before they are HBM-bound: 49 DFMA per point and pass against 64 FP64
+        # lanes per clock and SM (tools/micro) = 148 x 64 x 1.965e9 DFMA/s
+        fp64_floor_ms = 4 * 49 * n ** 4 / (148 * 64 * 1.965e9) * 1e3
         out[f"smooth_{n}^4_B0.05"] = {"value": n ** 4 / (ms * 1e-3), "unit": "grid pts/s", "ms": ms,
                                       "roofline_frac": 4 * 16 * n ** 4 / (ms * 1e-3) / 1e9 / peak,
-                                      "model": "4 passes x 16 B per grid point (40^4 is L2-resident)"}
+                                      "model": "4 passes x 16 B per grid point (40^4 is L2-resident)",
+                                      "fp64_floor_ms": fp64_floor_ms, "fp64_frac": fp64_floor_ms / ms}
     return out
 
 

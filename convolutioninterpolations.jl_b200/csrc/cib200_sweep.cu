@@ -1268,6 +1268,7 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
   cfg.l = cfg.tma ? 1 : (SMOOTH ? 4 : 2);
   cfg.c = std::max(1, (max_warps - cfg.l - 2 * cfg.g) / cfg.cwg);
   cfg.c = std::min(cfg.c, std::max(1, cfg.nb - cfg.g - 1));
+  if (!cfg.tma) cfg.l = env_int("CIB200_PIPE_L", cfg.l);
   cfg.g = env_int("CIB200_PIPE_G", cfg.g);
   cfg.c = env_int("CIB200_PIPE_C", cfg.c);
   cfg.cwg = env_int("CIB200_PIPE_CWG", cfg.cwg);
