@@ -60,19 +60,21 @@ __global__ void resample_weights_kernel(const double *__restrict__ knots_out, lo
                                         double h, int eqs, long long n_coef, const double *__restrict__ tk,
                                         const double *__restrict__ td, const double *__restrict__ te, int linear,
                                         double *__restrict__ W, double *__restrict__ Wk, int *__restrict__ base) {
-  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_out) return;
+  // one thread per (output knot, tap): the position arithmetic is recomputed by the 2 eqs threads of a knot (a
+  // thread per knot made this launch a 7 us dependent chain in front of every pass)
+  const int w = 2 * eqs;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out * w) return;
+  const long long k = idx / w;
+  const int l = (int)(idx - k * w);
   AxisPos p;
   locate_computed(knots_out[k], x_expanded_1, h, eqs, n_coef, p);
-  base[k] = p.base;
+  if (l == 0) base[k] = p.base;
   // te != nullptr: quintic subgrid (:333-349); linear (:363-373): td aliases tk, its terms carry zero factors
   const Hermite hb = te ? hermite_basis_quintic(p.t) : (linear ? linear_basis(p.t) : hermite_basis(p.t));
-  const int w = 2 * eqs;
-  for (int l = 0; l < w; ++l) {
-    const double v = te ? blended_weight_quintic(hb, tk, td, te, p.row, l, w) : blended_weight(hb, tk, td, p.row, l, w);
-    W[(long long)l * n_out + k] = v;
-    Wk[k * w + l] = v;
-  }
+  const double v = te ? blended_weight_quintic(hb, tk, td, te, p.row, l, w) : blended_weight(hb, tk, td, p.row, l, w);
+  W[(long long)l * n_out + k] = v;
+  Wk[k * w + l] = v;
 }
 
 // ---- ghost fill of one line held in shared memory ----------------------------------------------
@@ -1325,6 +1327,30 @@ static int launch_pass(SweepParams sp, const GhostMats &gm, const T *in, T *out,
   return launch_taps<T, SMOOTH, false>(sp, gm, in, out, blocks, smem, st);
 }
 
+// K^(d) tables in device memory: immutable, uploaded once per (device, kernel, derivative) and kept for the life of
+// the process (67 tables x <= 14.5 kB), so that a resample call issues no table copies
+static std::mutex g_tab_mu;
+static const double *g_tab_dev[16][16][8];
+static int device_table(int kernel, int d, const double **out) {
+  int dev = 0;
+  CIB_CUDA(cudaGetDevice(&dev));
+  const double *host = host_table(kernel, d);
+  if (!host || dev < 0 || dev >= 16 || kernel < 0 || kernel >= 16 || d < 0 || d >= 8) {
+    set_error("sweep: no table K^(%d) for kernel id %d", d, kernel);
+    return CIB200_EUNSUPPORTED;
+  }
+  std::lock_guard<std::mutex> guard(g_tab_mu);
+  if (!g_tab_dev[dev][kernel][d]) {
+    const size_t bytes = sizeof(double) * CIB_TAB_ROWS * 2 * (size_t)kernel_eqs(kernel);
+    double *p = nullptr;
+    CIB_CUDA(cudaMalloc((void **)&p, bytes));
+    CIB_CUDA(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+    g_tab_dev[dev][kernel][d] = p;
+  }
+  *out = g_tab_dev[dev][kernel][d];
+  return CIB200_OK;
+}
+
 struct TempBufs {
   std::vector<void *> ptrs;
   cudaStream_t st;
@@ -1355,25 +1381,20 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     const double h = knots_in[d][1] - knots_in[d][0];                 // convolution_resample.jl:270
     const double x_expanded_1 = knots_in[d][0] - (double)(eqs - 1) * h;  // :285
     const long long n_coef = nin + 2 * (eqs - 1);
-    // tables + output knots + weights on the device
-    double *d_tk, *d_td, *d_te = nullptr, *d_ko, *d_W, *d_Wk;
+    // tables (cached on the device) + output knots + weights
+    const double *d_tk, *d_td, *d_te = nullptr;
+    double *d_ko, *d_W, *d_Wk;
     int *d_base;
-    const size_t tab_bytes = sizeof(double) * CIB_TAB_ROWS * taps;
-    if ((rc = tmp.alloc((void **)&d_tk, tab_bytes))) return rc;
-    if ((rc = tmp.alloc((void **)&d_td, tab_bytes))) return rc;
+    const int linear = subgrid[d] == CIB200_SG_LINEAR;
+    if ((rc = device_table(kernel[d], deriv[d], &d_tk))) return rc;
+    if ((rc = device_table(kernel[d], deriv[d] + (linear ? 0 : 1), &d_td))) return rc;
+    if (subgrid[d] == CIB200_SG_QUINTIC && (rc = device_table(kernel[d], deriv[d] + 2, &d_te))) return rc;
     if ((rc = tmp.alloc((void **)&d_ko, sizeof(double) * (size_t)nout))) return rc;
     if ((rc = tmp.alloc((void **)&d_W, sizeof(double) * (size_t)nout * taps))) return rc;
     if ((rc = tmp.alloc((void **)&d_Wk, sizeof(double) * (size_t)nout * taps))) return rc;
     if ((rc = tmp.alloc((void **)&d_base, sizeof(int) * (size_t)nout))) return rc;
-    CIB_CUDA(cudaMemcpyAsync(d_tk, host_table(kernel[d], deriv[d]), tab_bytes, cudaMemcpyHostToDevice, st));
-    const int linear = subgrid[d] == CIB200_SG_LINEAR;
-    CIB_CUDA(cudaMemcpyAsync(d_td, host_table(kernel[d], deriv[d] + (linear ? 0 : 1)), tab_bytes, cudaMemcpyHostToDevice, st));
-    if (subgrid[d] == CIB200_SG_QUINTIC) {
-      if ((rc = tmp.alloc((void **)&d_te, tab_bytes))) return rc;
-      CIB_CUDA(cudaMemcpyAsync(d_te, host_table(kernel[d], deriv[d] + 2), tab_bytes, cudaMemcpyHostToDevice, st));
-    }
     CIB_CUDA(cudaMemcpyAsync(d_ko, knots_out[d], sizeof(double) * (size_t)nout, cudaMemcpyHostToDevice, st));
-    resample_weights_kernel<<<(unsigned)((nout + 127) / 128), 128, 0, st>>>(d_ko, nout, x_expanded_1, h, eqs, n_coef,
+    resample_weights_kernel<<<(unsigned)((nout * taps + 127) / 128), 128, 0, st>>>(d_ko, nout, x_expanded_1, h, eqs, n_coef,
                                                                            d_tk, d_td, d_te, linear, d_W, d_Wk, d_base);
     CIB_LAUNCHED();
     CIB_CUDA(cudaGetLastError());
