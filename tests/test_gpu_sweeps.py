@@ -146,7 +146,7 @@ def test_c4_smooth_4d_40_and_64(ci, oracle):
     _check_smooth(ci, oracle, tuple(np.linspace(0, TWO_PI, 40) for _ in range(4)), v5, 0.05)
 
 
-@pytest.mark.parametrize("B", [0.02, 0.05, 0.1, 1.0])
+@pytest.mark.parametrize("B", [0.02, 0.05, 0.1, 0.2, 0.3, 0.5, 1.0])  # 77 (run-time loop), 49, 35, 25, 21 (loop), 17, 13 taps
 def test_smooth_1d_2d_3d(ci, oracle, B):
     rng = np.random.default_rng(23)
     x = np.linspace(0, TWO_PI, 200)
