@@ -25,7 +25,8 @@ SYMBOLS = [
     "cib200_itp_set_eval_mode", "cib200_itp_eval", "cib200_itp_eval_grid", "cib200_itp_scratch_bytes",
     "cib200_resample", "cib200_resample_sg", "cib200_smooth", "cib200_smooth_halfwidth", "cib200_host_register",
     "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
-    "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
+    "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itp_eval_multi", "cib200_device_count",
+    "cib200_set_device", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
 ]
 
 
@@ -81,6 +82,9 @@ def lib():
     L.cib200_itp_set_eval_mode.argtypes = [vp, i32]
     L.cib200_itp_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
     L.cib200_itp_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_device_count.restype = i32
+    L.cib200_set_device.argtypes = [i32]
+    L.cib200_itp_eval_multi.argtypes = [C.POINTER(vp), i32, i64, C.POINTER(vp), vp, C.POINTER(i64)]
     L.cib200_itpnd_create.argtypes = [i32, i32, vp, vp, C.POINTER(vp), vp, vp, vp, i32, i32, C.POINTER(vp)]
     L.cib200_itpnd_destroy.argtypes = [vp]
     L.cib200_itpnd_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]

@@ -208,7 +208,8 @@ class FastConvolutionInterpolation:
     for the eager cubic-subgrid case, plus the device handle."""
 
     def __init__(self, knots, values, kernel="b5", precompute=101, bc="detect", derivative=0, subgrid="cubic",
-                 lazy=False, boundary_fallback=False, dtype=None, eval_mode="auto", _extrap="throw", coefs_on="host"):
+                 lazy=False, boundary_fallback=False, dtype=None, eval_mode="auto", _extrap="throw", coefs_on="host",
+                 devices=None):
         values = np.asarray(values)
         if values.dtype not in (np.float32, np.float64):
             values = values.astype(np.float64)
@@ -295,7 +296,11 @@ class FastConvolutionInterpolation:
                 coefs_ptr = self.coefs.ctypes.data  # the N-D constructor copies from host memory
             check(L.cib200_itpnd_create(nd, self.dtype_id, cs, coefs_ptr, kp, hh, kid, dv,
                                         EXTRAP_IDS[_extrap], int(self.perdim), C.byref(handle)))
+            if devices is not None and len(devices) > 1:
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, "devices=[...] (single-process multi-GPU) covers 1-3 dimensions")
             self._handle = handle
+            self._handles = [handle]
+            self.devices = None
             self.eval_mode = "nd"
             return
         self._nd = False
@@ -312,10 +317,25 @@ class FastConvolutionInterpolation:
         desc.coefs = coefs_ptr
         desc.extrap = EXTRAP_IDS[_extrap]
         desc.perdim = int(self.perdim)
-        handle = C.c_void_p()
-        check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
-        self._handle = handle
-        self._d_coefs = None  # the handle holds its own copy
+        # one handle per device (the grid is replicated, query batches are split by cib200_itp_eval_multi);
+        # devices=None: the current device only
+        self._handles = []
+        if devices is None:
+            handle = C.c_void_p()
+            check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
+            self._handles.append(handle)
+        else:
+            import torch
+            if not devices:
+                raise ValueError("devices must name at least one CUDA device")
+            for dev in devices:
+                with torch.cuda.device(int(dev)):
+                    handle = C.c_void_p()
+                    check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
+                    self._handles.append(handle)
+        self.devices = None if devices is None else tuple(int(d) for d in devices)
+        self._handle = self._handles[0]
+        self._d_coefs = None  # the handles hold their own copies
         self.set_eval_mode(eval_mode)
 
     @property
@@ -333,7 +353,8 @@ class FastConvolutionInterpolation:
     def set_eval_mode(self, mode):
         if self._nd:
             return  # one strategy in N >= 4 dimensions
-        check(lib().cib200_itp_set_eval_mode(self._handle, _lib.EVAL_MODES[mode]))
+        for h in self._handles:
+            check(lib().cib200_itp_set_eval_mode(h, _lib.EVAL_MODES[mode]))
         self.eval_mode = mode
 
     def set_profiling(self, enable=True):
@@ -349,8 +370,9 @@ class FastConvolutionInterpolation:
         return dict(zip(("binning", "cellsort", "eval_kernel", "spill"), (float(v) for v in ms)))
 
     def close(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h:
+        hs = getattr(self, "_handles", None) or ([self._handle] if getattr(self, "_handle", None) else [])
+        self._handle, self._handles = None, []
+        for h in hs:
             (lib().cib200_itpnd_destroy if getattr(self, "_nd", False) else lib().cib200_itp_destroy)(h)
 
     def __del__(self):
@@ -399,6 +421,10 @@ class ConvolutionExtrapolation:
         if out is None:
             out = np.empty(nq, dtype=ndt)
         ptrs = (C.c_void_p * itp.ndim)(*[x.ctypes.data for x in xs])
+        if len(itp._handles) > 1:
+            hs = (C.c_void_p * len(itp._handles))(*[h.value for h in itp._handles])
+            check(L.cib200_itp_eval_multi(hs, len(itp._handles), nq, ptrs, out.ctypes.data, C.byref(bad)))
+            return out.reshape(shape)
         fn = L.cib200_itpnd_eval if itp._nd else L.cib200_itp_eval
         check(fn(itp._handle, nq, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
         return out.reshape(shape)
@@ -426,7 +452,7 @@ class ConvolutionExtrapolation:
 
 def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=101, extrap=None, bc="detect",
                               derivative=0, subgrid="cubic", lazy=False, boundary_fallback=False, dtype=None,
-                              eval_mode="auto", coefs_on="host"):
+                              eval_mode="auto", coefs_on="host", devices=None):
     """convolution_interpolation(knots, values; kernel, fast, precompute, extrap, bc, derivative, subgrid,
     lazy, boundary_fallback)  -  convolution_interpolation_function.jl:79-157"""
     values = np.asarray(values)
@@ -461,7 +487,7 @@ def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=
     itp = FastConvolutionInterpolation(knots_t, values, kernel=kernels, precompute=precompute, bc=tuple(fixed),
                                        derivative=derivs, subgrid=subgrid, lazy=lazy,
                                        boundary_fallback=boundary_fallback, dtype=dtype, eval_mode=eval_mode,
-                                       _extrap=et.name, coefs_on=coefs_on)
+                                       _extrap=et.name, coefs_on=coefs_on, devices=devices)
     return ConvolutionExtrapolation(itp, et)
 
 

@@ -824,6 +824,61 @@ int32_t cib200_itp_eval(cib200_itp *h, int64_t nq, const void *const *x, void *o
   return eval_common(h, c, nq, out, memkind, stream, first_bad, "cib200_itp_eval");
 }
 
+// Single-process multi-GPU evaluation (replicated grid, split queries, no collective): one handle per
+// device, one host thread per handle, each slice through its handle's own H2D / kernel / D2H pipeline.
+int32_t cib200_itp_eval_multi(cib200_itp *const *handles, int32_t n_handles, int64_t nq, const void *const *x, void *out,
+                              int64_t *first_bad) {
+  if (!handles || n_handles < 1 || nq < 0 || (nq > 0 && (!x || !out))) {
+    set_error("cib200_itp_eval_multi: bad arguments");
+    return CIB200_EINVAL;
+  }
+  for (int i = 0; i < n_handles; ++i)
+    if (!handles[i] || handles[i]->p.ndim != handles[0]->p.ndim || handles[i]->dtype != handles[0]->dtype) {
+      set_error("cib200_itp_eval_multi: handle %d is null or describes a different interpolant", i);
+      return CIB200_EINVAL;
+    }
+  if (first_bad) *first_bad = -1;
+  if (n_handles == 1 || nq < 2 * (int64_t)n_handles)
+    return cib200_itp_eval(handles[0], nq, x, out, CIB200_HOST, nullptr, first_bad);
+  const int nd = handles[0]->p.ndim;
+  const size_t es = esize(handles[0]->dtype);
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  std::vector<int32_t> rcs((size_t)n_handles, CIB200_OK);
+  std::vector<int64_t> bads((size_t)n_handles, -1);
+  std::vector<std::string> msgs((size_t)n_handles);
+  std::vector<std::thread> pool;
+  const int64_t per = (nq + n_handles - 1) / n_handles;
+  for (int i = 0; i < n_handles; ++i) {
+    pool.emplace_back([&, i]() {
+      const int64_t q0 = std::min<int64_t>(nq, per * i), q1 = std::min<int64_t>(nq, q0 + per);
+      if (q1 <= q0) return;
+      const void *xs[3] = {nullptr, nullptr, nullptr};
+      for (int d = 0; d < nd; ++d) xs[d] = (const char *)x[d] + es * (size_t)q0;
+      int64_t bad = -1;
+      rcs[(size_t)i] = cib200_itp_eval(handles[i], q1 - q0, xs, (char *)out + es * (size_t)q0, CIB200_HOST, nullptr, &bad);
+      if (bad >= 0) bads[(size_t)i] = q0 + bad;
+      if (rcs[(size_t)i]) msgs[(size_t)i] = cib200_last_error();
+    });
+  }
+  for (auto &t : pool) t.join();
+  cudaSetDevice(prev_dev);
+  // the lowest offending query decides, as in a sequential pass over the batch
+  int32_t rc = CIB200_OK;
+  int64_t bad = -1;
+  for (int i = 0; i < n_handles; ++i) {
+    if (rcs[(size_t)i] == CIB200_OK) continue;
+    if (rc == CIB200_OK || (bads[(size_t)i] >= 0 && (bad < 0 || bads[(size_t)i] < bad))) {
+      rc = rcs[(size_t)i];
+      bad = bads[(size_t)i];
+      // slice-relative index in the message -> absolute
+      set_error("cib200_itp_eval_multi (device slice %d): %s [absolute query index %lld]", i, msgs[(size_t)i].c_str(), (long long)bad);
+    }
+  }
+  if (first_bad) *first_bad = bad;
+  return rc;
+}
+
 int32_t cib200_itp_eval_grid(cib200_itp *h, const int64_t *n, const void *const *x, void *out, int32_t memkind,
                              void *stream, int64_t *first_bad) {
   if (!h || !n || !x || !out) {
@@ -995,8 +1050,17 @@ int32_t cib200_smooth(int32_t ndim, int32_t dtype, const int64_t *n, const void 
   return rc;
 }
 
+int32_t cib200_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+int32_t cib200_set_device(int32_t device) {
+  CIB_CUDA(cudaSetDevice(device));
+  return CIB200_OK;
+}
+
 int32_t cib200_host_register(void *ptr, size_t bytes) {
-  CIB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  CIB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));  // pinned for every device of the process
   return CIB200_OK;
 }
 int32_t cib200_host_unregister(void *ptr) {

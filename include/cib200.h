@@ -89,6 +89,10 @@ typedef struct cib200_itp cib200_itp; /* opaque */
 /* ---- library ------------------------------------------------------------------------------ */
 int32_t cib200_version(void);
 const char *cib200_last_error(void);
+/* devices visible to the process / select the device the next cib200_itp_create binds to (callers without a CUDA
+ * binding of their own - the Julia glue - use these to build one handle per GPU for cib200_itp_eval_multi) */
+int32_t cib200_device_count(void);
+int32_t cib200_set_device(int32_t device);
 /* number of kernel launches issued by this library since process start (bench bookkeeping) */
 int64_t cib200_launch_count(void);
 /* 101 x 2*eqs row-major table K^(deriv) of `kernel` (host pointer into the library image); the same
@@ -131,6 +135,13 @@ int32_t cib200_itp_set_eval_mode(cib200_itp *handle, int32_t mode);
  * extrap = Throw (the status needs the device's answer). */
 int32_t cib200_itp_eval(cib200_itp *handle, int64_t nq, const void *const *x, void *out,
                         int32_t memkind, void *stream, int64_t *first_bad);
+
+/* The same over several GPUs of ONE process (host buffers): handles[i] was created with device i current and holds a
+ * replica of the grid; the batch is split into n_handles contiguous slices evaluated concurrently, one host thread and
+ * one H2D / kernel / D2H pipeline per device, no collective.  first_bad / status: the lowest offending
+ * query of the whole batch, as in a sequential pass. */
+int32_t cib200_itp_eval_multi(cib200_itp *const *handles, int32_t n_handles, int64_t nq,
+                              const void *const *x, void *out, int64_t *first_bad);
 
 /* itp(xs, ys, zs) with vectors: Cartesian product
  * ((etp)(x::Vararg{AbstractArray,N}), extrapolation_operator.jl:66-99). out: n[0] x ... column-major */

@@ -79,7 +79,11 @@ derivative_tuple(itp) = typeof(itp.derivative_order).parameters[1]   # Derivativ
 # ---- handle cache: one upload per interpolant, freed by a finalizer --------------------------------
 mutable struct Handle
     ptr::Ptr{Cvoid}
+    replicas::Vector{Ptr{Cvoid}}   # one handle per GPU (1-3 D): cib200_itp_eval_multi splits host batches over them
 end
+Handle(p::Ptr{Cvoid}) = Handle(p, Ptr{Cvoid}[p])
+# GPUs to use from this process: ENV["CIB200_DEVICES"] = "0,1,2,3" (default: the current device only)
+devices() = haskey(ENV, "CIB200_DEVICES") ? parse.(Int32, split(ENV["CIB200_DEVICES"], ",")) : Int32[]
 const HANDLES = WeakKeyDict{Any,Handle}()
 const HANDLES_LOCK = ReentrantLock()
 
@@ -118,11 +122,17 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
                                pad3(ntuple(d -> Int32(dv[d]), N), Int32(0)), extrap_id(etp.et),
                                Int32(itp.kernel_sym isa HigherOrderMixedKernel),
                                pad3(ntuple(d -> Int32(SUBGRID_ID[effective_subgrids(subgrid_tuple(itp), N)[d]]), N), Int32(0))))
-            out = Ref{Ptr{Cvoid}}(C_NULL)
-            GC.@preserve itp knots64 check(ccall((:cib200_itp_create, LIB), Int32,
-                                                 (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
-            h = Handle(out[])
-            finalizer(x -> ccall((:cib200_itp_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+            devs = devices()
+            ptrs = Ptr{Cvoid}[]
+            for dev in (isempty(devs) ? Int32[-1] : devs)
+                dev >= 0 && check(ccall((:cib200_set_device, LIB), Int32, (Int32,), dev))
+                out = Ref{Ptr{Cvoid}}(C_NULL)
+                GC.@preserve itp knots64 check(ccall((:cib200_itp_create, LIB), Int32,
+                                                     (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
+                push!(ptrs, out[])
+            end
+            h = Handle(ptrs[1], ptrs)
+            finalizer(x -> foreach(p -> ccall((:cib200_itp_destroy, LIB), Int32, (Ptr{Cvoid},), p), x.replicas), h)
             h
         end
     end
@@ -137,7 +147,14 @@ function Base.Broadcast.broadcasted(etp::ConvolutionExtrapolation{T,N}, xs::Vara
     out = Vector{T}(undef, nq)
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
     bad = Ref{Int64}(-1)
-    hp = handle(etp).ptr
+    hd = handle(etp)
+    if length(hd.replicas) > 1     # several GPUs: contiguous slices, one pipeline per device
+        GC.@preserve xq out ptrs check(ccall((:cib200_itp_eval_multi, LIB), Int32,
+            (Ptr{Ptr{Cvoid}}, Int32, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ref{Int64}),
+            hd.replicas, length(hd.replicas), nq, ptrs, out, bad))
+        return out
+    end
+    hp = hd.ptr
     GC.@preserve xq out ptrs check(N >= 4 ?   # ccall needs a literal symbol: one call site per entry point
         ccall((:cib200_itpnd_eval, LIB), Int32,
               (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),

@@ -493,3 +493,40 @@ def test_concurrent_calls_on_one_handle_are_serialised(ci):
     torch.cuda.synchronize()
     for a, o in zip(seq, outs):
         assert np.array_equal(a, o.cpu().numpy())
+
+
+def test_single_process_multi_gpu_evaluation(ci, oracle):
+    """cib200_itp_eval_multi: one handle per device, contiguous query slices, lowest offending index of the whole batch.
+    With one GPU the two handles share device 0 (the split / merge logic is the same)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    rng = np.random.default_rng(92)
+    k = tuple(np.linspace(0, 1, 40) for _ in range(3))
+    v = _field((40, 40, 40), rng)
+    one = ci.convolution_interpolation(k, v, extrap="line")
+    multi = ci.convolution_interpolation(k, v, extrap="line", devices=devices)
+    q = rng.uniform(-0.03, 1.03, (3, 1_000_003))
+    a, b = one.eval(*q), multi.eval(*q)
+    assert np.array_equal(a, b)
+    o = oracle.convolution_interpolation(k, v, extrap="line")
+    sub = slice(0, 200_000)
+    qs = tuple(x[sub] for x in q)
+    assert rel_err(b[sub], o.eval(*qs), _scale(o) * _line_amplification(o, qs)).max() <= TOL64
+    thr = ci.convolution_interpolation(k, v, devices=devices)
+    qq = np.full((3, 400_000), 0.5)
+    qq[1, 350_000] = 1.5   # second slice
+    qq[0, 399_999] = np.nan
+    with pytest.raises(ci.DomainError, match="absolute query index 350000"):
+        thr.eval(*qq)
+    qq[2, 10] = -0.5       # first slice: the lowest index wins
+    with pytest.raises(ci.DomainError, match="absolute query index 10"):
+        thr.eval(*qq)
+    # 2-D and tiny batches
+    k2 = (np.linspace(0, 1, 30), np.linspace(0, 2, 35))
+    v2 = rng.random((30, 35))
+    m2 = ci.convolution_interpolation(k2, v2, derivative=(1, 0), extrap="flat", devices=devices)
+    s2 = ci.convolution_interpolation(k2, v2, derivative=(1, 0), extrap="flat")
+    for n in (1, 3, 1000):
+        q2 = (rng.uniform(0, 1, n), rng.uniform(0, 2, n))
+        assert np.array_equal(m2.eval(*q2), s2.eval(*q2))
