@@ -334,7 +334,7 @@ __device__ __forceinline__ void ghost_gauss_side(double *bl, int pad, int pitch,
 
 static constexpr int SMOOTH_R = 8;    // consecutive outputs per thread in the Gaussian FIR (sliding register window)
 #ifndef CIB_SMOOTH_RP
-#define CIB_SMOOTH_RP 16
+#define CIB_SMOOTH_RP 8
 #endif
 static constexpr int SMOOTH_RP = CIB_SMOOTH_RP;  // the same in the pipelined kernel
 static constexpr int RESAMPLE_R = 8;  // anchor offsets a register window of the resample pass can serve
