@@ -650,6 +650,7 @@ struct PipeCfg {
   int g;    // ghost teams
   int c;    // consumer groups
   int cwg;  // warps per consumer group
+  int light;  // resample, axis >= 1, weights in shared memory: the low-register pair consumer with twice the warps
   unsigned long long *stats;  // debug (CIB200_PIPE_STATS=1): cycles [loader wait, loader busy, ghost wait, ghost busy, consumer wait, consumer busy]
 };
 static constexpr int PIPE_MAX_NB = 8;
@@ -786,8 +787,70 @@ __device__ __forceinline__ void resample_lines2(const double *bl, const int pitc
   }
 }
 
-template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
-__global__ void __launch_bounds__(SMOOTH ? (SMOOTH_RP > 8 ? 512 : 768) : (AXIS0 ? 640 : 384), 1)
+// "Light" resample consumer: no long-lived register window and no offset switch.  Every pair of consecutive output
+// knots re-loads the TP + 1 rows it touches and streams its weights from shared memory next to the DFMAs that use
+// them; the code is two straight-line cases (second knot starts 0 or 1 rows after the first) and needs ~90 registers,
+// so twice as many consumer warps fit.  It trades shared-memory traffic (~28 wavefronts per knot instead of ~13) for
+// latency hiding: the register-window consumer runs its 8 warps at 10 % of the FP64 issue rate (profiles/r01_sweeps_v10).
+template <int TP, int D>
+__device__ __forceinline__ void pair_dot(const double (&win)[TP + 1], const double2 *__restrict__ w0, const double2 *__restrict__ w1,
+                                         double &r0, double &r1) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int l = 0; l < TP; l += 6) {
+    // chains cycle with period 3 over the taps, as in window_dot2 (same association per knot)
+#pragma unroll
+    for (int u = 0; u < 6; u += 2) {
+      if (l + u < TP) {
+        const double2 va = load_w2<true>(w0 + ((l + u) >> 1)), vb = load_w2<true>(w1 + ((l + u) >> 1));
+        const int c0 = (l + u) % 3, c1 = (l + u + 1) % 3;
+        if (c0 == 0) { a0 = fma(win[l + u], va.x, a0); b0 = fma(win[l + u + D], vb.x, b0); }
+        if (c0 == 1) { a1 = fma(win[l + u], va.x, a1); b1 = fma(win[l + u + D], vb.x, b1); }
+        if (c0 == 2) { a2 = fma(win[l + u], va.x, a2); b2 = fma(win[l + u + D], vb.x, b2); }
+        if (c1 == 0) { a0 = fma(win[l + u + 1], va.y, a0); b0 = fma(win[l + u + 1 + D], vb.y, b0); }
+        if (c1 == 1) { a1 = fma(win[l + u + 1], va.y, a1); b1 = fma(win[l + u + 1 + D], vb.y, b1); }
+        if (c1 == 2) { a2 = fma(win[l + u + 1], va.y, a2); b2 = fma(win[l + u + 1 + D], vb.y, b2); }
+      }
+    }
+  }
+  r0 = (a0 + a1) + a2;
+  r1 = (b0 + b1) + b2;
+}
+
+template <typename T, int TP>
+__device__ __forceinline__ void resample_pairs_light(const double *bl, const int pitch, const double2 *__restrict__ wsm,
+                                                     const int *__restrict__ bsm, int kbeg, int kend, T *optr,
+                                                     long long ostride, double scale) {
+  int k = kbeg;
+  while (k < kend) {
+    const int b0 = load_b<true>(bsm + k);
+    const int b1 = k + 1 < kend ? load_b<true>(bsm + k + 1) : b0 + 2;
+    const int d = b1 - b0;
+    double win[TP + 1];
+#pragma unroll
+    for (int j = 0; j < TP + 1; ++j) win[j] = bl[(b0 + j) * pitch];  // row b0 + TP exists: the buffer has RESAMPLE_R spare rows
+    const double2 *w0 = wsm + k * (TP / 2);
+    if ((unsigned)d <= 1u) {
+      double r0, r1;
+      if (d == 0) pair_dot<TP, 0>(win, w0, w0 + TP / 2, r0, r1);
+      else pair_dot<TP, 1>(win, w0, w0 + TP / 2, r0, r1);
+      optr[0] = (T)__dmul_rn(r0, scale);
+      optr[ostride] = (T)__dmul_rn(r1, scale);
+      optr += 2 * ostride;
+      k += 2;
+    } else {
+      double r0, r1;
+      pair_dot<TP, 0>(win, w0, w0, r0, r1);
+      (void)r1;
+      *optr = (T)__dmul_rn(r0, scale);
+      optr += ostride;
+      k += 1;
+    }
+  }
+}
+
+template <typename T, bool SMOOTH, bool AXIS0, int TAPS, bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? 640 : SMOOTH ? (SMOOTH_RP > 8 ? 512 : 768) : (AXIS0 ? 640 : 384), 1)
     sweep_pipe_kernel(const __grid_constant__ CUtensorMap tmap, SweepParams sp, GhostMats gm, PipeCfg cfg,
                       const T *__restrict__ in, T *__restrict__ out, long long ntiles) {
   extern __shared__ __align__(128) double sm[];
@@ -1042,7 +1105,9 @@ __global__ void __launch_bounds__(SMOOTH ? (SMOOTH_RP > 8 ? 512 : 768) : (AXIS0 
           const int kbeg = cw * kper, kend = min(nout, kbeg + kper);
           if (kbeg < kend && lane < valid) {
             T *optr = out + tile_i * 32 + lane + o * sp.inner * nout + (long long)kbeg * sp.inner;
-            if (sp.w_smem)
+            if (LIGHT)
+              resample_pairs_light<T, TP>(buf + lane, PITCH, (const double2 *)extra, bsm, kbeg, kend, optr, sp.inner, sp.scale);
+            else if (sp.w_smem)
               resample_lines2<T, TP, true>(buf + lane, PITCH, (const double2 *)extra, bsm, kbeg, kend, optr, sp.inner, sp.scale);
             else
               resample_lines2<T, TP, false>(buf + lane, PITCH, (const double2 *)sp.Wk, sp.base, kbeg, kend, optr, sp.inner, sp.scale);
@@ -1146,10 +1211,10 @@ static int env_int(const char *name, int dflt) {
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
-template <typename T, bool SMOOTH, bool AXIS0, int TAPS>
+template <typename T, bool SMOOTH, bool AXIS0, int TAPS, bool LIGHT = false>
 static int launch_pipe_kernel(const SweepParams &sp, const GhostMats &gm, const PipeCfg &cfg, const T *in, T *out,
                               long long ntiles, int threads, size_t smem, cudaStream_t st) {
-  auto k = sweep_pipe_kernel<T, SMOOTH, AXIS0, TAPS>;
+  auto k = sweep_pipe_kernel<T, SMOOTH, AXIS0, TAPS, LIGHT>;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof tmap);
   if (cfg.tma) {
@@ -1209,6 +1274,18 @@ static int launch_pipe_taps(const SweepParams &sp, const GhostMats &gm, const Pi
     }
     return launch_pipe_kernel<T, true, AXIS0, 0>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
   }
+  if (!AXIS0 && cfg.light) {
+    switch (sp.taps) {
+      case 4: return launch_pipe_kernel<T, false, false, 4, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 6: return launch_pipe_kernel<T, false, false, 6, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 8: return launch_pipe_kernel<T, false, false, 8, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 10: return launch_pipe_kernel<T, false, false, 10, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 12: return launch_pipe_kernel<T, false, false, 12, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 14: return launch_pipe_kernel<T, false, false, 14, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 16: return launch_pipe_kernel<T, false, false, 16, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+      case 18: return launch_pipe_kernel<T, false, false, 18, true>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
+    }
+  }
   switch (sp.taps) {
     case 4: return launch_pipe_kernel<T, false, AXIS0, 4>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
     case 6: return launch_pipe_kernel<T, false, AXIS0, 6>(sp, gm, cfg, in, out, ntiles, threads, smem, st);
@@ -1260,7 +1337,8 @@ static int try_launch_pipe(SweepParams sp, const GhostMats &gm, const T *in, T *
     cfg.cwg = 8;
     regs_per_thread = 168;
   }
-  const int max_warps = SMOOTH ? (SMOOTH_RP > 8 ? 16 : 24) : (axis0 ? 20 : 12);  // the kernels' __launch_bounds__
+  cfg.light = (!SMOOTH && !axis0 && sp.w_smem && env_int("CIB200_RESAMPLE_LIGHT", 1) == 1) ? 1 : 0;
+  const int max_warps = SMOOTH ? (SMOOTH_RP > 8 ? 16 : 24) : (axis0 ? 20 : (cfg.light ? 20 : 12));  // the kernels' __launch_bounds__
   (void)regs_per_thread;
   cfg.g = SMOOTH ? 2 : 1;
   // one 3-D TMA per tile when the rows are 16-byte aligned (box 32 x n_in x 1, n_in <= 256); otherwise four loader
