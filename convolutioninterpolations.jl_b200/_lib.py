@@ -27,6 +27,7 @@ SYMBOLS = [
     "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
     "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itp_eval_multi", "cib200_device_count",
     "cib200_set_device", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
+    "cib200_itg_create", "cib200_itg_destroy", "cib200_itg_eval", "cib200_itg_eval_grid", "cib200_itg_get",
 ]
 
 
@@ -89,6 +90,11 @@ def lib():
     L.cib200_itpnd_destroy.argtypes = [vp]
     L.cib200_itpnd_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
     L.cib200_itpnd_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itg_create.argtypes = [C.POINTER(ItpDesc), C.POINTER(vp)]
+    L.cib200_itg_destroy.argtypes = [vp]
+    L.cib200_itg_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itg_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itg_get.argtypes = [vp, i32, i32, vp]
     L.cib200_itp_set_profiling.argtypes = [vp, i32]
     L.cib200_itp_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.cib200_itp_scratch_bytes.restype = i64

@@ -181,7 +181,18 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: kernel :{k} (axis {d + 1}) is not on the "
                                        f"accelerated path ({ACCELERATED_KERNELS})")
         if dv < 0:
-            raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivatives (derivative=-1) stay on the reference path")
+            # FastIntegralOrder (convolution_fast_integration_{1d,2d,3d}.jl): every axis an integral direction, shipped
+            # K~ / K / K' tables.  Mixed integral / interpolation axes and N >= 4 resolve to the :linear subgrid on
+            # generated 10 000-row tables (_build_subgrids + constructor.jl:117-118): reference path.
+            if what != "convolution_interpolation":
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what} does not support antiderivatives")
+            if dv != -1 or any(x != -1 for x in derivs) or ndim > 3:
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative={tuple(derivs)}: only the antiderivative "
+                                           "on every axis (1-3 dimensions) is on the accelerated path")
+            if sg not in ("cubic", "quintic"):
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivative with the :{sg} subgrid needs "
+                                           "generated tables")
+            continue
         if sg not in ("cubic", "quintic", "linear"):
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: unknown subgrid {subgrids}")
         need = dv + {"linear": 0, "cubic": 1, "quintic": 2}[sg]
@@ -242,8 +253,12 @@ class FastConvolutionInterpolation:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, "precompute != 101 needs generated tables (reference path)")
         # _build_kernel_sym (constructor.jl:378-398): HigherOrderKernel vs HigherOrderMixedKernel
         self.perdim = not (len(set(self.kernel)) == 1 and len(set(self.derivative)) == 1)
-        self.subgrid = _effective_subgrids(self.subgrid, nd)
+        self._itg = any(d == -1 for d in self.derivative)
+        if not self._itg:
+            self.subgrid = _effective_subgrids(self.subgrid, nd)
         _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation", self.perdim)
+        if self._itg and self.dtype_id != _lib.F64:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, "the antiderivative path is Float64 only")
         self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
         self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)  # constructor.jl:120
         L = lib()
@@ -317,6 +332,19 @@ class FastConvolutionInterpolation:
         desc.coefs = coefs_ptr
         desc.extrap = EXTRAP_IDS[_extrap]
         desc.perdim = int(self.perdim)
+        if self._itg:
+            # antiderivative on every axis: prefix-sum tails built on the device (constructor.jl:176-364)
+            if devices is not None and len(devices) > 1:
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, "devices=[...] is not available for antiderivatives")
+            handle = C.c_void_p()
+            check(L.cib200_itg_create(C.byref(desc), C.byref(handle)))
+            self._handle = handle
+            self._handles = [handle]
+            self.devices = None
+            self.eval_mode = "integral"
+            # itp.anchor (constructor.jl:139): the result is zero at the first interior knot of each axis
+            self.anchor = tuple(float(k[e - 1]) for k, e in zip(self.knots, self.eqs))
+            return
         # one handle per device (the grid is replicated, query batches are split by cib200_itp_eval_multi);
         # devices=None: the current device only
         self._handles = []
@@ -350,17 +378,34 @@ class FastConvolutionInterpolation:
                 check(lib().cib200_itp_get_coefs(self._handle, self._coefs.ctypes.data))
         return self._coefs
 
+    def left_values(self, d):
+        """itp.left_values[d + 1] of an antiderivative interpolant (constructor.jl:414-448)"""
+        out = np.empty(self.knots[d].size)
+        check(lib().cib200_itg_get(self._handle, 0, d, out.ctypes.data))
+        return out
+
+    def tail(self, mask):
+        """prefix-sum array saturated on the axes of the bit mask (see cib200_itg_get): tail1_left / tail2_ll / ..."""
+        out = np.empty(tuple(k.size for k in self.knots), order="F")
+        check(lib().cib200_itg_get(self._handle, 1, int(mask), out.ctypes.data))
+        return out
+
+    def _entry(self, name):
+        """the C-ABI entry point of this interpolant's family: cib200_itp_* / cib200_itpnd_* / cib200_itg_*"""
+        fam = "itg" if getattr(self, "_itg", False) else ("itpnd" if self._nd else "itp")
+        return getattr(lib(), f"cib200_{fam}_{name}")
+
     def set_eval_mode(self, mode):
-        if self._nd:
-            return  # one strategy in N >= 4 dimensions
+        if self._nd or self._itg:
+            return  # one strategy in N >= 4 dimensions and for antiderivatives
         for h in self._handles:
             check(lib().cib200_itp_set_eval_mode(h, _lib.EVAL_MODES[mode]))
         self.eval_mode = mode
 
     def set_profiling(self, enable=True):
         """Measurement hook: bracket the passes of every evaluation with CUDA events (cib200_itp_set_profiling)."""
-        if self._nd:
-            raise UnsupportedModeError(_lib.EUNSUPPORTED, "pass timing exists for 1-3 dimensions only")
+        if self._nd or self._itg:
+            raise UnsupportedModeError(_lib.EUNSUPPORTED, "pass timing exists for 1-3 dimensional interpolation only")
         check(lib().cib200_itp_set_profiling(self._handle, 1 if enable else 0))
 
     def last_pass_ms(self):
@@ -373,7 +418,7 @@ class FastConvolutionInterpolation:
         hs = getattr(self, "_handles", None) or ([self._handle] if getattr(self, "_handle", None) else [])
         self._handle, self._handles = None, []
         for h in hs:
-            (lib().cib200_itpnd_destroy if getattr(self, "_nd", False) else lib().cib200_itp_destroy)(h)
+            self._entry("destroy")(h)
 
     def __del__(self):
         try:
@@ -410,8 +455,7 @@ class ConvolutionExtrapolation:
             if out is None:
                 out = torch.empty(shape, dtype=tdt, device=xs[0].device)
             ptrs = (C.c_void_p * itp.ndim)(*[x.data_ptr() for x in xs])
-            fn = L.cib200_itpnd_eval if itp._nd else L.cib200_itp_eval
-            check(fn(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE, _stream_ptr(xs[0]), None))
+            check(itp._entry("eval")(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE, _stream_ptr(xs[0]), None))
             return out
         ndt = _np_dtype(itp.dtype_id)
         xs = np.broadcast_arrays(*[np.asarray(x, dtype=ndt) for x in xs])
@@ -425,8 +469,7 @@ class ConvolutionExtrapolation:
             hs = (C.c_void_p * len(itp._handles))(*[h.value for h in itp._handles])
             check(L.cib200_itp_eval_multi(hs, len(itp._handles), nq, ptrs, out.ctypes.data, C.byref(bad)))
             return out.reshape(shape)
-        fn = L.cib200_itpnd_eval if itp._nd else L.cib200_itp_eval
-        check(fn(itp._handle, nq, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
+        check(itp._entry("eval")(itp._handle, nq, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
         return out.reshape(shape)
 
     # -- itp(x, y, z): scalars, or vectors -> Cartesian product ---------------------------------
@@ -445,8 +488,7 @@ class ConvolutionExtrapolation:
         n = (C.c_int64 * itp.ndim)(*[v.size for v in vs])
         out = np.zeros(tuple(v.size for v in vs), dtype=ndt, order="F")
         ptrs = (C.c_void_p * itp.ndim)(*[v.ctypes.data for v in vs])
-        fn = L.cib200_itpnd_eval_grid if itp._nd else L.cib200_itp_eval_grid
-        check(fn(itp._handle, n, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
+        check(itp._entry("eval_grid")(itp._handle, n, ptrs, out.ctypes.data, _lib.HOST, None, C.byref(bad)))
         return out
 
 
@@ -470,8 +512,8 @@ def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=
         any(k == "n3" for k in kernels)
     if is_nonuniform:
         raise UnsupportedModeError(_lib.EUNSUPPORTED, "non-uniform grids stay on the reference path (fast=false)")
-    if is_integral:
-        raise UnsupportedModeError(_lib.EUNSUPPORTED, "antiderivatives (derivative=-1) stay on the reference path")
+    if is_integral and lazy and fast:
+        raise ValueError("Lazy mode not supported in fast mode for antiderivatives.")  # :114-117
     if not fast:
         raise UnsupportedModeError(_lib.EUNSUPPORTED, "fast=false (direct kernel evaluation) stays on the reference path")
     # :poly -> :linear when a dimension has too few points (:135-143)

@@ -63,6 +63,21 @@ int kernel_max_eval_deriv(int kernel) {
     default: return -1;
   }
 }
+// antiderivative tables K~ (KERNEL_PRE_<k>_i1, precomputed_kernel_tables.jl:93-96); companions are K^(0), K^(1)
+const double *host_table_i1(int kernel) {
+  switch (kernel) {
+    case CIB200_A3: return CIB_TAB_a3_i1;
+    case CIB200_A4: return CIB_TAB_a4_i1;
+    case CIB200_A5: return CIB_TAB_a5_i1;
+    case CIB200_A7: return CIB_TAB_a7_i1;
+    case CIB200_B5: return CIB_TAB_b5_i1;
+    case CIB200_B7: return CIB_TAB_b7_i1;
+    case CIB200_B9: return CIB_TAB_b9_i1;
+    case CIB200_B11: return CIB_TAB_b11_i1;
+    case CIB200_B13: return CIB_TAB_b13_i1;
+    default: return nullptr;
+  }
+}
 const double *host_table(int kernel, int d) {
   static const double *const b5[] = {CIB_TAB_b5_d0, CIB_TAB_b5_d1, CIB_TAB_b5_d2, CIB_TAB_b5_d3};
   static const double *const b7[] = {CIB_TAB_b7_d0, CIB_TAB_b7_d1, CIB_TAB_b7_d2, CIB_TAB_b7_d3, CIB_TAB_b7_d4};
@@ -340,6 +355,7 @@ int64_t cib200_launch_count(void) { return g_launches.load(); }
 
 const double *cib200_kernel_table(int32_t kernel, int32_t deriv, int32_t *eqs_out) {
   if (eqs_out) *eqs_out = kernel_eqs(kernel);
+  if (deriv == -1) return host_table_i1(kernel);
   return host_table(kernel, deriv);
 }
 

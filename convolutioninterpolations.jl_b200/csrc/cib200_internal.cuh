@@ -35,6 +35,7 @@ int kernel_poly_nodes(int kernel);       // interior points of the polynomial gh
 int kernel_max_deriv_table(int kernel);  // highest d for which K^(d) is tabulated
 int kernel_max_eval_deriv(int kernel);   // _max_shipped_derivative, get_precomputed_kernel_and_range.jl:33-40
 const double *host_table(int kernel, int d);
+const double *host_table_i1(int kernel);  // antiderivative table K~
 
 // ---- device-side view of one interpolant (passed by value to kernels) -------------------------
 struct ItpParams {

@@ -96,7 +96,8 @@ int32_t cib200_set_device(int32_t device);
 /* number of kernel launches issued by this library since process start (bench bookkeeping) */
 int64_t cib200_launch_count(void);
 /* 101 x 2*eqs row-major table K^(deriv) of `kernel` (host pointer into the library image); the same
- * numbers as precomputed_kernels/kernel_<k>.jl (KERNEL_PRE_<k>_d<deriv>). NULL if not shipped. */
+ * numbers as precomputed_kernels/kernel_<k>.jl (KERNEL_PRE_<k>_d<deriv>; deriv = -1: the antiderivative table
+ * KERNEL_PRE_<k>_i1). NULL if not shipped. */
 const double *cib200_kernel_table(int32_t kernel, int32_t deriv, int32_t *eqs_out);
 
 /* ---- subsystem 1: ghost-padded coefficient grid, built on the HOST -------------------------- */
@@ -166,6 +167,30 @@ int32_t cib200_itpnd_eval(cib200_itpnd *handle, int64_t nq, const void *const *x
                           int32_t memkind, void *stream, int64_t *first_bad);
 int32_t cib200_itpnd_eval_grid(cib200_itpnd *handle, const int64_t *n, const void *const *x, void *out,
                                int32_t memkind, void *stream, int64_t *first_bad);
+
+/* ---- antiderivatives: derivative = -1 on EVERY axis, 1..3 dimensions --------------
+ * itp.(xs...) / itp(xs, ys, zs) for the FastIntegralOrder functors
+ *   convolution_fast_interpolation/convolution_fast_integration_1d.jl:17-38, _2d.jl:18-80, _3d.jl:4-100
+ *   (+ eval_sg_kt, eval_subgrid_helpers.jl:22-32) behind extrapolation_operator.jl:31-99 / extrapolate_point.jl:41-160.
+ * cib200_itg_create replaces _build_tails (convolution/fast_convolution_interpolation_constructor.jl:176-364) and
+ * _compute_left_values (:414-448): desc is the same cib200_itp_desc with deriv[d] = -1 on every axis, dtype = F64,
+ * subgrid cubic or quintic (tables K~ = KERNEL_PRE_<k>_i1, K, K'); coefs may be host or device memory.  The prefix-sum
+ * arrays are built on the device; the reference's suffix-sum arrays are identically zero wherever its evaluators read
+ * them and are not materialised (cib200_integral.cu).  Results are anchored to zero at the first interior knot of each
+ * axis (itp.anchor).  Mixed integral / non-integral axes and N >= 4 need generated tables: CIB200_EUNSUPPORTED. */
+typedef struct cib200_itg cib200_itg; /* opaque */
+int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle);
+int32_t cib200_itg_destroy(cib200_itg *handle);
+/* same contracts as cib200_itp_eval / cib200_itp_eval_grid */
+int32_t cib200_itg_eval(cib200_itg *handle, int64_t nq, const void *const *x, void *out, int32_t memkind,
+                        void *stream, int64_t *first_bad);
+int32_t cib200_itg_eval_grid(cib200_itg *handle, const int64_t *n, const void *const *x, void *out,
+                             int32_t memkind, void *stream, int64_t *first_bad);
+/* copies to host memory: what = 0: itp.left_values[index + 1] (coef_shape[index] doubles); what = 1: the prefix array
+ * saturated on the axes of the bit mask `index` (padded grid size): 1-D mask 1 = tail1_left[1]; 2-D 1, 2 =
+ * tail1_left[1], tail1_left[2], 3 = tail2_ll; 3-D 1, 2, 4 = tail1_left[1..3] (= tail3_face_l), 6, 5, 3 =
+ * tail3_edge_ll[1..3], 7 = tail3_corner_lll */
+int32_t cib200_itg_get(cib200_itg *handle, int32_t what, int32_t index, void *out);
 
 /* Measurement hook (bench.py's roofline): with profiling enabled the library brackets the passes of every evaluation
  * with CUDA events on the launching stream; cib200_itp_last_pass_ms then returns, for the most recent call, the

@@ -1015,3 +1015,429 @@ int orc_smooth(int ndim, const int64_t *n, const double *values, double *out, co
   free(kw);
   return ORC_OK;
 }
+
+/* =============================================================================================
+ * Antiderivative fast path (derivative = -1 on EVERY axis, 1-D / 2-D / 3-D): FastIntegralOrder functors
+ *   convolution_fast_interpolation/convolution_fast_integration_{1d,2d,3d}.jl, eval_subgrid_helpers.jl:22-32,
+ *   tails built by convolution/fast_convolution_interpolation_constructor.jl:176-364 (_build_tails_dispatch),
+ *   _compute_left_values :414-448, _suffix_sum :452-454.
+ * Tables: kernel_pre = K~ (KERNEL_PRE_<k>_i1), kernel_d1_pre = K, kernel_d2_pre = K'
+ * (precomputed_kernel_tables.jl:93-96).  Everything below is a literal restatement, including the right-hand tails
+ * (which are identically zero: the clamped cell index keeps every right-tail index >= 2 eqs + 1, where
+ * -1/2 - left_values[j] == 0) and the scan order of tail3_corner_rlr (:351, suffix along int_dims[2] and cumsum along
+ * int_dims[1] although the weights are (r, l, r) - harmless for the same reason).
+ * ============================================================================================= */
+const double *orc_table_i1(int kernel) {
+  switch (kernel) {
+    case ORC_K_A3: return CIB_TAB_a3_i1;
+    case ORC_K_A4: return CIB_TAB_a4_i1;
+    case ORC_K_A5: return CIB_TAB_a5_i1;
+    case ORC_K_A7: return CIB_TAB_a7_i1;
+    case ORC_K_B5: return CIB_TAB_b5_i1;
+    case ORC_K_B7: return CIB_TAB_b7_i1;
+    case ORC_K_B9: return CIB_TAB_b9_i1;
+    case ORC_K_B11: return CIB_TAB_b11_i1;
+    case ORC_K_B13: return CIB_TAB_b13_i1;
+    default: return NULL;
+  }
+}
+
+struct orc_itg {
+  int ndim, extrap;
+  int64_t cshape[3], cstride[3], ntot;
+  double *coefs;
+  double *knots[3];
+  double h[3];
+  int eqs[3], subgrid[3];
+  const double *kp[3], *kd[3], *ke[3];
+  double *lv[3];
+  /* tails, indexed by a base-3 code over the axes: digit 0 = free (local stencil), 1 = left (prefix), 2 = right
+   * (suffix); code = s0 + 3 s1 + 9 s2.  1-D: tail1_left = [1], tail1_right = [2].  2-D: tail1_left[1] = [1],
+   * tail1_right[1] = [2], tail1_left[2] = [3], tail1_right[2] = [6], tail2_ll = [4], tail2_rl = [5], tail2_lr = [7],
+   * tail2_rr = [8].  3-D likewise (faces one non-zero digit, edges two, corners three). */
+  double *tail[27];
+};
+
+static double sg_blend(const orc_itg *g, int d, double t, int64_t idx, int64_t col) {
+  const int e = g->eqs[d];
+  const double h_pre = 1.0 / (double)(N_PRE - 1);
+  if (g->subgrid[d] == ORC_SG_QUINTIC)
+    return quintic_hermite(t, TAB(g->kp[d], idx, col, e), TAB(g->kp[d], idx + 1, col, e), TAB(g->kd[d], idx, col, e),
+                           TAB(g->kd[d], idx + 1, col, e), TAB(g->ke[d], idx, col, e), TAB(g->ke[d], idx + 1, col, e),
+                           h_pre);
+  if (g->subgrid[d] == ORC_SG_CUBIC)
+    return cubic_hermite(t, TAB(g->kp[d], idx, col, e), TAB(g->kp[d], idx + 1, col, e), TAB(g->kd[d], idx, col, e),
+                         TAB(g->kd[d], idx + 1, col, e), h_pre);
+  return (1.0 - t) * TAB(g->kp[d], idx, col, e) + t * TAB(g->kp[d], idx + 1, col, e);
+}
+
+/* eval_sg_kt, eval_subgrid_helpers.jl:22-32 (jd 1-based) */
+static double eval_sg_kt(const orc_itg *g, int d, int64_t jd, double xd) {
+  const int e = g->eqs[d];
+  double xjd = g->knots[d][e - 1] + (double)(jd - e) * g->h[d];
+  double sj = (xd - xjd) / g->h[d];
+  if (fabs(sj) >= (double)e) return 0.5 * (double)((sj > 0) - (sj < 0));
+  double col_float = (double)e + sj;
+  int64_t col = (int64_t)floor(col_float) + 1;
+  if (col < 1) col = 1;
+  if (col > 2 * e) col = 2 * e;
+  double t = (col_float - (double)(col - 1)) * (double)(N_PRE - 1) + 1.0;
+  int64_t idx = (int64_t)floor(t);
+  if (idx < 1) idx = 1;
+  if (idx > N_PRE - 1) idx = N_PRE - 1;
+  t -= (double)idx;
+  return sg_blend(g, d, t, idx, col);
+}
+
+/* _compute_left_values, fast_convolution_interpolation_constructor.jl:414-448 */
+static void compute_left_values(const orc_itg *g, int d, double *lv) {
+  const int e = g->eqs[d];
+  for (int64_t j = 1; j <= g->cshape[d]; ++j) {
+    double sj = (double)(e - j);
+    if (fabs(sj) >= (double)e) {
+      lv[j - 1] = 0.5 * (double)((sj > 0) - (sj < 0));
+      continue;
+    }
+    double col_float = (double)e + sj;
+    int64_t col = (int64_t)floor(col_float) + 1;
+    if (col < 1) col = 1;
+    if (col > 2 * e) col = 2 * e;
+    double x_diff_right = col_float - (double)(col - 1);
+    double cidx = x_diff_right * (double)(N_PRE - 1) + 1.0;
+    int64_t idx = (int64_t)floor(cidx);
+    if (idx < 1) idx = 1;
+    if (idx > N_PRE - 1) idx = N_PRE - 1;
+    lv[j - 1] = sg_blend(g, d, cidx - (double)idx, idx, col);
+  }
+}
+
+/* Julia Base accumulate_pairwise! (base/accumulate.jl): what cumsum(v::Vector; dims=1) runs for floats */
+static double jl_accumulate_pairwise(double *c, const double *v, double s, int64_t i1, int64_t n, int64_t stride) {
+  if (n < 128) {
+    double s_ = v[i1 * stride];
+    c[i1 * stride] = s + s_;
+    for (int64_t i = i1 + 1; i < i1 + n; ++i) {
+      s_ = s_ + v[i * stride];
+      c[i * stride] = s + s_;
+    }
+    return s_;
+  }
+  int64_t n2 = n >> 1;
+  double s_ = jl_accumulate_pairwise(c, v, s, i1, n2, stride);
+  s_ = s_ + jl_accumulate_pairwise(c, v, s + s_, i1 + n2, n - n2, stride);
+  return s_;
+}
+
+/* cumsum(A, dims = ax) (reverse = 0) or _suffix_sum(A, ax) = reverse(cumsum(reverse(A))) (reverse = 1), in place.
+ * N-D arrays: Base._accumulate! walks the axis sequentially; a Vector takes the pairwise route. */
+static void scan_axis(const orc_itg *g, double *a, int ax, int reverse) {
+  const int64_t n = g->cshape[ax], st = g->cstride[ax];
+  if (g->ndim == 1) {
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)n), *res = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) tmp[i] = reverse ? a[n - 1 - i] : a[i];
+    res[0] = tmp[0];
+    if (n > 1) jl_accumulate_pairwise(res, tmp, tmp[0], 1, n - 1, 1);
+    for (int64_t i = 0; i < n; ++i) a[i] = reverse ? res[n - 1 - i] : res[i];
+    free(tmp);
+    free(res);
+    return;
+  }
+  for (int64_t o = 0; o < g->ntot; ++o) {
+    if ((o / st) % n != 0) continue; /* first element of a line along ax */
+    double *line = a + o;
+    if (!reverse)
+      for (int64_t i = 1; i < n; ++i) line[i * st] = line[(i - 1) * st] + line[i * st];
+    else
+      for (int64_t i = n - 2; i >= 0; --i) line[i * st] = line[(i + 1) * st] + line[i * st];
+  }
+}
+
+/* coefs .* w_{d1} .* w_{d2} ... (ascending axes), side[d]: 0 none, 1 -> (1/2 - lv), 2 -> (-1/2 - lv) */
+static double *weighted(const orc_itg *g, const int *side) {
+  double *a = (double *)malloc(sizeof(double) * (size_t)g->ntot);
+  for (int64_t o = 0; o < g->ntot; ++o) {
+    double v = g->coefs[o];
+    for (int d = 0; d < g->ndim; ++d) {
+      if (!side[d]) continue;
+      int64_t j = (o / g->cstride[d]) % g->cshape[d];
+      v = v * ((side[d] == 1 ? 0.5 : -0.5) - g->lv[d][j]);
+    }
+    a[o] = v;
+  }
+  return a;
+}
+
+void orc_itg_destroy(orc_itg *g) {
+  if (!g) return;
+  free(g->coefs);
+  for (int d = 0; d < 3; ++d) { free(g->knots[d]); free(g->lv[d]); }
+  for (int c = 0; c < 27; ++c) free(g->tail[c]);
+  free(g);
+}
+
+int orc_itg_create(int ndim, const int64_t *cshape, const double *coefs, const double *const *knots, const double *h,
+                   const int32_t *kernel, const int32_t *subgrid, int extrap, orc_itg **out) {
+  if (ndim < 1 || ndim > 3) return ORC_EARG;
+  orc_itg *g = (orc_itg *)calloc(1, sizeof(orc_itg));
+  g->ndim = ndim;
+  g->extrap = extrap;
+  g->ntot = 1;
+  for (int d = 0; d < ndim; ++d) {
+    g->cshape[d] = cshape[d];
+    g->cstride[d] = g->ntot;
+    g->ntot *= cshape[d];
+    g->h[d] = h[d];
+    g->eqs[d] = orc_eqs(kernel[d]);
+    g->subgrid[d] = subgrid[d];
+    g->kp[d] = orc_table_i1(kernel[d]);
+    g->kd[d] = orc_table(kernel[d], 0);
+    g->ke[d] = orc_table(kernel[d], 1);
+    if (g->eqs[d] < 0 || !g->kp[d] || !g->kd[d] || (subgrid[d] == ORC_SG_QUINTIC && !g->ke[d]) ||
+        subgrid[d] == ORC_SG_LINEAR /* needs the generated 10 000-row tables */) {
+      orc_itg_destroy(g);
+      return ORC_EARG;
+    }
+    g->knots[d] = (double *)malloc(sizeof(double) * (size_t)cshape[d]);
+    memcpy(g->knots[d], knots[d], sizeof(double) * (size_t)cshape[d]);
+    g->lv[d] = (double *)malloc(sizeof(double) * (size_t)cshape[d]);
+  }
+  g->coefs = (double *)malloc(sizeof(double) * (size_t)g->ntot);
+  memcpy(g->coefs, coefs, sizeof(double) * (size_t)g->ntot);
+  for (int d = 0; d < ndim; ++d) compute_left_values(g, d, g->lv[d]);
+
+  /* scan recipes: {axis (0-based), reverse} in the order the reference applies them */
+  typedef struct { int n; int ax[3]; int rev[3]; } recipe;
+  int ncode = ndim == 1 ? 3 : (ndim == 2 ? 9 : 27);
+  for (int code = 1; code < ncode; ++code) {
+    int side[3] = {code % 3, (code / 3) % 3, (code / 9) % 3};
+    int nz = (side[0] != 0) + (side[1] != 0) + (side[2] != 0);
+    recipe r = {0, {0, 0, 0}, {0, 0, 0}};
+    if (nz == 1) { /* tail1_left / tail1_right (:207-222), tail3_face_* (:330-331) */
+      for (int d = 0; d < 3; ++d)
+        if (side[d]) { r.n = 1; r.ax[0] = d; r.rev[0] = side[d] == 2; }
+    } else if (nz == 2) { /* tail2_* (:265-268), tail3_edge_* (:332-335) */
+      int a = -1, b = -1; /* a < b: the two saturated axes */
+      for (int d = 0; d < 3; ++d)
+        if (side[d]) { if (a < 0) a = d; else b = d; }
+      r.n = 2;
+      if (side[a] == 1 && side[b] == 1) { /* ll: cumsum(cumsum(w, dims=a), dims=b) */
+        r.ax[0] = a; r.rev[0] = 0; r.ax[1] = b; r.rev[1] = 0;
+      } else { /* rl: suffix(cumsum(w, b), a); lr: cumsum(suffix(w, b), a); rr: suffix(suffix(w, b), a) */
+        r.ax[0] = b; r.rev[0] = side[b] == 2; r.ax[1] = a; r.rev[1] = side[a] == 2;
+      }
+    } else { /* corners (:336-343), digits (s0, s1, s2) */
+      r.n = 3;
+      const int key = side[0] * 100 + side[1] * 10 + side[2];
+      switch (key) {
+        case 111: r.ax[0] = 0; r.rev[0] = 0; r.ax[1] = 1; r.rev[1] = 0; r.ax[2] = 2; r.rev[2] = 0; break; /* lll */
+        case 211: r.ax[0] = 1; r.rev[0] = 0; r.ax[1] = 2; r.rev[1] = 0; r.ax[2] = 0; r.rev[2] = 1; break; /* rll */
+        case 121: r.ax[0] = 2; r.rev[0] = 0; r.ax[1] = 1; r.rev[1] = 1; r.ax[2] = 0; r.rev[2] = 0; break; /* lrl */
+        case 112: r.ax[0] = 2; r.rev[0] = 1; r.ax[1] = 0; r.rev[1] = 0; r.ax[2] = 1; r.rev[2] = 0; break; /* llr */
+        case 221: r.ax[0] = 2; r.rev[0] = 0; r.ax[1] = 1; r.rev[1] = 1; r.ax[2] = 0; r.rev[2] = 1; break; /* rrl */
+        case 212: r.ax[0] = 1; r.rev[0] = 1; r.ax[1] = 0; r.rev[1] = 0; r.ax[2] = 2; r.rev[2] = 1; break; /* rlr (sic) */
+        case 122: r.ax[0] = 2; r.rev[0] = 1; r.ax[1] = 1; r.rev[1] = 1; r.ax[2] = 0; r.rev[2] = 0; break; /* lrr */
+        default:  r.ax[0] = 2; r.rev[0] = 1; r.ax[1] = 1; r.rev[1] = 1; r.ax[2] = 0; r.rev[2] = 1; break; /* rrr */
+      }
+    }
+    double *a = weighted(g, side);
+    for (int s = 0; s < r.n; ++s) scan_axis(g, a, r.ax[s], r.rev[s]);
+    g->tail[code] = a;
+  }
+  *out = g;
+  return ORC_OK;
+}
+
+/* the un-wrapped functors: convolution_fast_integration_1d.jl:17-38, _2d.jl:18-80, _3d.jl:4-100 */
+static int itg_core(const orc_itg *g, const double *x, double *res) {
+  const int N = g->ndim;
+  int64_t i[3] = {1, 1, 1}, l[3], r[3];
+  int l_ok[3], r_ok[3];
+  for (int d = 0; d < N; ++d) {
+    double i_float = (x[d] - g->knots[d][0]) / g->h[d] + 1.0;
+    if (!(fabs(i_float) < 9.0e18)) return ORC_ENAN;
+    int64_t id = (int64_t)floor(i_float);
+    if (id < g->eqs[d]) id = g->eqs[d];
+    if (id > g->cshape[d] - g->eqs[d]) id = g->cshape[d] - g->eqs[d];
+    i[d] = id;
+    l[d] = id - g->eqs[d];
+    l_ok[d] = l[d] >= 1;
+    r[d] = id + g->eqs[d] + 1;
+    r_ok[d] = r[d] <= g->cshape[d];
+  }
+#define LVW(d, j) (eval_sg_kt(g, d, j, x[d]) - g->lv[d][(j)-1])
+#define A1(code, a) (g->tail[code][(a)-1])
+#define A2(code, a, b) (g->tail[code][((a)-1) + ((b)-1) * g->cstride[1]])
+#define A3(code, a, b, c) (g->tail[code][((a)-1) + ((b)-1) * g->cstride[1] + ((c)-1) * g->cstride[2]])
+  double result = 0.0;
+  if (N == 1) {
+    for (int64_t j = i[0] - g->eqs[0] + 1; j <= i[0] + g->eqs[0]; ++j)
+      result += g->coefs[j - 1] * LVW(0, j);
+    double left_tail = l_ok[0] ? A1(1, l[0]) : 0.0;
+    double right_tail = r_ok[0] ? A1(2, r[0]) : 0.0;
+    *res = (result + left_tail + right_tail) * g->h[0];
+    return ORC_OK;
+  }
+  if (N == 2) {
+    const int e1 = g->eqs[0], e2 = g->eqs[1];
+    for (int64_t j2 = i[1] - e2 + 1; j2 <= i[1] + e2; ++j2) {
+      double lv2 = LVW(1, j2);
+      for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1)
+        result += g->coefs[(j1 - 1) + (j2 - 1) * g->cstride[1]] * LVW(0, j1) * lv2;
+      double tl1 = l_ok[0] ? A2(1, l[0], j2) : 0.0;
+      double tr1 = r_ok[0] ? A2(2, r[0], j2) : 0.0;
+      result += (tl1 + tr1) * lv2;
+    }
+    if (l_ok[1]) {
+      for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1) result += A2(3, j1, l[1]) * LVW(0, j1);
+      result += l_ok[0] ? A2(4, l[0], l[1]) : 0.0;
+      result += r_ok[0] ? A2(5, r[0], l[1]) : 0.0;
+    }
+    if (r_ok[1]) {
+      for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1) result += A2(6, j1, r[1]) * LVW(0, j1);
+      result += l_ok[0] ? A2(7, l[0], r[1]) : 0.0;
+      result += r_ok[0] ? A2(8, r[0], r[1]) : 0.0;
+    }
+    *res = result * g->h[0] * g->h[1];
+    return ORC_OK;
+  }
+  const int e1 = g->eqs[0], e2 = g->eqs[1], e3 = g->eqs[2];
+  const int64_t l1 = l[0], l2 = l[1], l3 = l[2], r1 = r[0], r2 = r[1], r3 = r[2];
+  const int l1_ok = l_ok[0], l2_ok = l_ok[1], l3_ok = l_ok[2], r1_ok = r_ok[0], r2_ok = r_ok[1], r3_ok = r_ok[2];
+  for (int64_t j3 = i[2] - e3 + 1; j3 <= i[2] + e3; ++j3) {
+    double lv3 = LVW(2, j3);
+    for (int64_t j2 = i[1] - e2 + 1; j2 <= i[1] + e2; ++j2) {
+      double lv2 = LVW(1, j2);
+      double lv23 = lv2 * lv3;
+      for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1)
+        result += g->coefs[(j1 - 1) + (j2 - 1) * g->cstride[1] + (j3 - 1) * g->cstride[2]] * LVW(0, j1) * lv23;
+      result += (l1_ok ? A3(1, l1, j2, j3) : 0.0) * lv23;
+      result += (r1_ok ? A3(2, r1, j2, j3) : 0.0) * lv23;
+    }
+    for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1) {
+      double lv1 = LVW(0, j1);
+      result += (l2_ok ? A3(3, j1, l2, j3) : 0.0) * lv1 * lv3;
+      result += (r2_ok ? A3(6, j1, r2, j3) : 0.0) * lv1 * lv3;
+    }
+    result += (l1_ok && l2_ok ? A3(4, l1, l2, j3) : 0.0) * lv3;
+    result += (r1_ok && l2_ok ? A3(5, r1, l2, j3) : 0.0) * lv3;
+    result += (l1_ok && r2_ok ? A3(7, l1, r2, j3) : 0.0) * lv3;
+    result += (r1_ok && r2_ok ? A3(8, r1, r2, j3) : 0.0) * lv3;
+  }
+  for (int64_t j2 = i[1] - e2 + 1; j2 <= i[1] + e2; ++j2) {
+    double lv2 = LVW(1, j2);
+    for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1) {
+      double lv1 = LVW(0, j1);
+      result += (l3_ok ? A3(9, j1, j2, l3) : 0.0) * lv1 * lv2;
+      result += (r3_ok ? A3(18, j1, j2, r3) : 0.0) * lv1 * lv2;
+    }
+  }
+  for (int64_t j2 = i[1] - e2 + 1; j2 <= i[1] + e2; ++j2) {
+    double lv2 = LVW(1, j2);
+    result += (l1_ok && l3_ok ? A3(1 + 9, l1, j2, l3) : 0.0) * lv2;
+    result += (r1_ok && l3_ok ? A3(2 + 9, r1, j2, l3) : 0.0) * lv2;
+    result += (l1_ok && r3_ok ? A3(1 + 18, l1, j2, r3) : 0.0) * lv2;
+    result += (r1_ok && r3_ok ? A3(2 + 18, r1, j2, r3) : 0.0) * lv2;
+  }
+  for (int64_t j1 = i[0] - e1 + 1; j1 <= i[0] + e1; ++j1) {
+    double lv1 = LVW(0, j1);
+    result += (l2_ok && l3_ok ? A3(3 + 9, j1, l2, l3) : 0.0) * lv1;
+    result += (r2_ok && l3_ok ? A3(6 + 9, j1, r2, l3) : 0.0) * lv1;
+    result += (l2_ok && r3_ok ? A3(3 + 18, j1, l2, r3) : 0.0) * lv1;
+    result += (r2_ok && r3_ok ? A3(6 + 18, j1, r2, r3) : 0.0) * lv1;
+  }
+  result += (l1_ok && l2_ok && l3_ok ? A3(1 + 3 + 9, l1, l2, l3) : 0.0);
+  result += (r1_ok && l2_ok && l3_ok ? A3(2 + 3 + 9, r1, l2, l3) : 0.0);
+  result += (l1_ok && r2_ok && l3_ok ? A3(1 + 6 + 9, l1, r2, l3) : 0.0);
+  result += (l1_ok && l2_ok && r3_ok ? A3(1 + 3 + 18, l1, l2, r3) : 0.0);
+  result += (r1_ok && r2_ok && l3_ok ? A3(2 + 6 + 9, r1, r2, l3) : 0.0);
+  result += (r1_ok && l2_ok && r3_ok ? A3(2 + 3 + 18, r1, l2, r3) : 0.0);
+  result += (l1_ok && r2_ok && r3_ok ? A3(1 + 6 + 18, l1, r2, r3) : 0.0);
+  result += (r1_ok && r2_ok && r3_ok ? A3(2 + 6 + 18, r1, r2, r3) : 0.0);
+  *res = result * g->h[0] * g->h[1] * g->h[2];
+  return ORC_OK;
+#undef LVW
+#undef A1
+#undef A2
+#undef A3
+}
+
+/* extrapolation_operator.jl:31-63 + extrapolate_point.jl:41-160 around the integral functor */
+static int itg_etp_point(const orc_itg *g, const double *x, double *res) {
+  const int N = g->ndim;
+  double lo[3], hi[3], cl[3];
+  int within = 1;
+  for (int d = 0; d < N; ++d) {
+    lo[d] = g->knots[d][g->eqs[d] - 1];
+    hi[d] = g->knots[d][g->cshape[d] - 1 - (g->eqs[d] - 1)];
+  }
+  for (int d = 0; d < N; ++d)
+    if (x[d] > hi[d] || x[d] < lo[d]) { within = 0; break; }
+  if (within) return itg_core(g, x, res);
+  for (int d = 0; d < N; ++d) cl[d] = x[d] < lo[d] ? lo[d] : (x[d] > hi[d] ? hi[d] : x[d]);
+  if (g->extrap == ORC_EXTRAP_LINE) {
+    double dx[3], dist_sq = 0.0;
+    for (int d = 0; d < N; ++d) {
+      dx[d] = x[d] - cl[d];
+      dist_sq += dx[d] * dx[d];
+    }
+    if (dist_sq < 2.220446049250313e-16) return itg_core(g, cl, res);
+    double h_min = g->h[0];
+    for (int d = 1; d < N; ++d) h_min = g->h[d] < h_min ? g->h[d] : h_min;
+    double eps = h_min / 100.0, dist = sqrt(dist_sq), xin[3], f_b, f_in;
+    for (int d = 0; d < N; ++d) xin[d] = cl[d] - eps * dx[d] / dist;
+    int rc = itg_core(g, cl, &f_b);
+    if (rc) return rc;
+    rc = itg_core(g, xin, &f_in);
+    if (rc) return rc;
+    *res = f_b + (f_b - f_in) / eps * dist;
+    return ORC_OK;
+  }
+  if (g->extrap == ORC_EXTRAP_FLAT) return itg_core(g, cl, res);
+  return ORC_EOOB;
+}
+
+int orc_itg_eval(const orc_itg *g, int64_t nq, const double *const *x, double *out, int64_t *first_bad) {
+  int64_t bad = -1;
+  int bad_rc = ORC_OK;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int64_t q = 0; q < nq; ++q) {
+    double xq[3] = {0, 0, 0}, r = NAN;
+    for (int d = 0; d < g->ndim; ++d) xq[d] = x[d][q];
+    int rc = itg_etp_point(g, xq, &r);
+    out[q] = r;
+    if (rc) {
+#pragma omp critical
+      {
+        if (bad < 0 || q < bad) { bad = q; bad_rc = rc; }
+      }
+    }
+  }
+  if (first_bad) *first_bad = bad;
+  return bad_rc;
+}
+
+/* largest |value| the evaluators can ever read from a right-hand tail (indices r >= 2 eqs + 1 on the saturated axes):
+ * identically zero - the property the CUDA path relies on when it keeps the left-hand tails only */
+double orc_itg_right_tail_maxabs(const orc_itg *g) {
+  double m = 0.0;
+  int ncode = g->ndim == 1 ? 3 : (g->ndim == 2 ? 9 : 27);
+  for (int code = 1; code < ncode; ++code) {
+    int side[3] = {code % 3, (code / 3) % 3, (code / 9) % 3};
+    if (side[0] != 2 && side[1] != 2 && side[2] != 2) continue;
+    for (int64_t o = 0; o < g->ntot; ++o) {
+      int ok = 1;
+      for (int d = 0; d < g->ndim; ++d) {
+        int64_t j = (o / g->cstride[d]) % g->cshape[d] + 1;
+        if (side[d] == 2 && j < 2 * g->eqs[d] + 1) ok = 0;
+      }
+      if (ok && fabs(g->tail[code][o]) > m) m = fabs(g->tail[code][o]);
+    }
+  }
+  return m;
+}
+/* copies left_values[d] / one tail array (code as in struct orc_itg) for tests */
+int orc_itg_get(const orc_itg *g, int what, int idx, double *out) {
+  if (what == 0) { memcpy(out, g->lv[idx], sizeof(double) * (size_t)g->cshape[idx]); return ORC_OK; }
+  if (what == 1 && idx > 0 && idx < 27 && g->tail[idx]) { memcpy(out, g->tail[idx], sizeof(double) * (size_t)g->ntot); return ORC_OK; }
+  return ORC_EARG;
+}

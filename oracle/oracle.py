@@ -75,6 +75,15 @@ def lib():
         L.orc_smooth.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.orc_smooth_halfwidth.argtypes = [C.c_double]
         L.orc_ghost_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_table_i1.restype = C.POINTER(C.c_double)
+        L.orc_table_i1.argtypes = [C.c_int]
+        L.orc_itg_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.orc_itg_eval.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_int64)]
+        L.orc_itg_destroy.argtypes = [C.c_void_p]
+        L.orc_itg_right_tail_maxabs.restype = C.c_double
+        L.orc_itg_right_tail_maxabs.argtypes = [C.c_void_p]
+        L.orc_itg_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -88,6 +97,13 @@ def table(kernel, d):
     p = lib().orc_table(KERNEL_IDS[kernel], int(d))
     if not p:
         raise OracleError(f"no table for {kernel} d={d}")
+    e = KERNEL_EQS[kernel]
+    return np.ctypeslib.as_array(p, shape=(101, 2 * e)).copy()
+
+
+def table_i1(kernel):
+    """antiderivative table K~ of `kernel` (KERNEL_PRE_<k>_i1) as a (101, 2*eqs) array (copy)."""
+    p = lib().orc_table_i1(KERNEL_IDS[kernel])
     e = KERNEL_EQS[kernel]
     return np.ctypeslib.as_array(p, shape=(101, 2 * e)).copy()
 
@@ -286,7 +302,114 @@ class Interpolant:
         return self.eval_points(*[g.ravel() for g in grids]).reshape(grids[0].shape)
 
 
+def build_subgrids_integral(kernels, subgrids, ndim):
+    """_build_subgrids for integral directions, fast_convolution_interpolation_constructor.jl:464-472"""
+    out = []
+    for k, sg in zip(kernels, subgrids):
+        out.append("linear" if ndim >= 4 else ("cubic" if k in ("a3", "a4", "a5", "a7") else sg))
+    return tuple(out)
+
+
+class IntegralInterpolant:
+    """convolution_interpolation(knots, values; kernel, derivative=-1, ...) with EVERY axis an integral direction, 1-D to
+    3-D, fast path: FastConvolutionInterpolation with FastIntegralOrder (fast_convolution_interpolation_constructor.jl:
+    99-174, tails :176-364; evaluators convolution_fast_integration_{1d,2d,3d}.jl).  Result anchored to zero at the first
+    interior knot of each axis (`anchor`, constructor.jl:139)."""
+
+    def __init__(self, knots, values, kernel="b5", extrap="throw", bc="detect", subgrid="cubic"):
+        values = np.asarray(values, dtype=np.float64)
+        nd = values.ndim
+        if nd < 1 or nd > 3:
+            raise OracleError("antiderivative oracle covers 1-3 D")
+        self.ndim = nd
+        self.knots_in = _knots_tuple(knots, nd)
+        self.kernels = _ntuple(kernel, nd, str)
+        self.derivs = (-1,) * nd
+        bcs = _norm_bc(bc, nd)
+        fixed = []
+        for d in range(nd):  # :poly -> :linear downgrade, convolution_interpolation_function.jl:135-143
+            b = bcs[d]
+            if "poly" in b and values.shape[d] < MIN_POLY_BC_POINTS[self.kernels[d]]:
+                b = ("linear", "linear") if b == ("poly", "poly") else (("linear", b[1]) if b[0] == "poly" else (b[0], "linear"))
+            fixed.append(b)
+        self.bc = tuple(fixed)
+        self.subgrid = build_subgrids_integral(self.kernels, _ntuple(subgrid, nd, str), nd)
+        for k, sg in zip(self.kernels, self.subgrid):
+            if sg == "linear" or (sg == "quintic" and MAX_TABLE_DERIVATIVE[k] < 1):
+                raise OracleError(f"antiderivative: subgrid {self.subgrid} needs generated tables")
+        self.eqs = tuple(KERNEL_EQS[k] for k in self.kernels)
+        self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)
+        self.coefs = create_coefs(values, self.h, self.kernels, self.bc)
+        self.knots = tuple(extend_vector(k, e - 1) for k, e in zip(self.knots_in, self.eqs))
+        self.anchor = tuple(float(k[e - 1]) for k, e in zip(self.knots, self.eqs))
+        self.extrap = extrap
+        cs = (C.c_int64 * nd)(*self.coefs.shape)
+        kp = (C.c_void_p * nd)(*[k.ctypes.data for k in self.knots])
+        hh = (C.c_double * nd)(*self.h)
+        kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in self.kernels])
+        sg = (C.c_int32 * nd)(*[SUBGRID_IDS[x] for x in self.subgrid])
+        h = C.c_void_p()
+        rc = lib().orc_itg_create(nd, cs, self.coefs.ctypes.data, kp, hh, kid, sg, EXTRAP_IDS[extrap], C.byref(h))
+        if rc:
+            raise OracleError(f"orc_itg_create rc={rc}")
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_itg_destroy(self._h)
+            self._h = None
+
+    def right_tail_maxabs(self):
+        return float(lib().orc_itg_right_tail_maxabs(self._h))
+
+    def left_values(self, d):
+        out = np.empty(self.coefs.shape[d])
+        lib().orc_itg_get(self._h, 0, d, out.ctypes.data)
+        return out
+
+    def tail(self, code):
+        out = np.empty(self.coefs.shape, order="F")
+        if lib().orc_itg_get(self._h, 1, code, out.ctypes.data):
+            raise OracleError(f"no tail {code}")
+        return out
+
+    def eval_points(self, *xs):
+        xs = [np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), np.broadcast(*xs).shape)).ravel()
+              for x in xs]
+        assert len(xs) == self.ndim
+        nq = xs[0].size
+        out = np.empty(nq)
+        ptrs = (C.c_void_p * self.ndim)(*[x.ctypes.data for x in xs])
+        bad = C.c_int64(-1)
+        rc = lib().orc_itg_eval(self._h, nq, ptrs, out.ctypes.data, C.byref(bad))
+        if rc == 1:
+            raise OracleError(f"query {bad.value} outside the domain with extrap=throw")
+        if rc == 2:
+            raise OracleError(f"query {bad.value}: InexactError (NaN/Inf coordinate)")
+        if rc:
+            raise OracleError(f"orc_itg_eval rc={rc}")
+        return out
+
+    eval = eval_points
+
+    def __call__(self, *xs):
+        if all(np.ndim(x) == 0 for x in xs):
+            return float(self.eval_points(*[np.array([x]) for x in xs])[0])
+        grids = np.meshgrid(*[np.asarray(x, dtype=np.float64) for x in xs], indexing="ij")
+        return self.eval_points(*[g.ravel() for g in grids]).reshape(grids[0].shape)
+
+
 def convolution_interpolation(knots, values, **kw):
+    dv = kw.get("derivative", 0)
+    nd = np.ndim(values)
+    dvs = (dv,) * nd if isinstance(dv, int) else tuple(dv) * (nd if len(tuple(dv)) == 1 else 1)
+    if any(d == -1 for d in dvs):
+        if not all(d == -1 for d in dvs):
+            # mixed integral / interpolation axes resolve every non-integral axis to the :linear subgrid on generated
+            # 10 000-row tables (_build_subgrids, constructor.jl:474-491): outside the shipped-table path
+            raise OracleError("mixed antiderivative / interpolation axes need generated tables")
+        kw = {k: v for k, v in kw.items() if k != "derivative"}
+        return IntegralInterpolant(knots, values, **kw)
     return Interpolant(knots, values, **kw)
 
 

@@ -27,15 +27,16 @@ def test_embedded_tables_are_the_shipped_ones(ci, golden_dir):
     L = ci.lib()
     n = 0
     for name in g.files:
-        m = re.match(r"KERNEL_(D1_|D2_|)PRE_([ab]\d+)_d(\d+)$", name)
-        kernel, d = m.group(2), int(m.group(3)) + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
+        m = re.match(r"KERNEL_(D1_|D2_|)PRE_([ab]\d+)_(d|i)(\d+)$", name)
+        base = int(m.group(4)) if m.group(3) == "d" else -int(m.group(4))  # _i1: antiderivative tables (deriv = -1)
+        kernel, d = m.group(2), base + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
         eqs = C.c_int32()
         p = L.cib200_kernel_table(ids[kernel], d, C.byref(eqs))
         t = np.ctypeslib.as_array(p, shape=(101, 2 * eqs.value))
         lit = g[name]
         assert ((t.view(np.uint64) == lit.view(np.uint64)) | ((t == 0) & (lit == 0))).all(), name
         n += 1
-    assert n == 75
+    assert n == 102
     assert not L.cib200_kernel_table(0, 4, None)  # b5 has no 4th derivative table
 
 
@@ -110,8 +111,12 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
         ci.convolution_interpolation(x, v, kernel="a1")           # a0 / a1: :linear subgrid only
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, kernel="a4", derivative=2)  # K'' of the a-series does not exist
-    with pytest.raises(U):
-        ci.convolution_interpolation(x, v, derivative=-1)
+    with pytest.raises(U):  # mixed integral / interpolation axes resolve to :linear on generated tables
+        ci.convolution_interpolation((x, x), np.zeros((30, 30)), derivative=(-1, 0))
+    with pytest.raises(U):  # the antiderivative path is Float64 only
+        ci.convolution_interpolation(x, v, derivative=-1, dtype=np.float32)
+    with pytest.raises(U):  # N >= 4 integral directions: :linear subgrid
+        ci.convolution_interpolation((x[:12],) * 4, np.zeros((12,) * 4), derivative=-1)
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, derivative=4)          # K^(4) of :b5 does not exist in the tables
     with pytest.raises(U):
@@ -165,6 +170,9 @@ def test_no_cpu_fallback_without_a_device(ci):
     with pytest.raises(ci.CIB200Error) as e:
         ci.convolution_interpolation(x, np.sin(x))
     assert e.value.status == 5  # CIB200_ECUDA
+    with pytest.raises(ci.CIB200Error) as e:
+        ci.convolution_interpolation(x, np.sin(x), derivative=-1)  # antiderivative handle (cib200_itg_create)
+    assert e.value.status == 5
     with pytest.raises(ci.CIB200Error):
         ci.convolution_smooth(np.linspace(0, 1, 100), np.zeros(100), 0.05)
     with pytest.raises(ci.CIB200Error):

@@ -1,6 +1,7 @@
 """Pins the oracle against the reference's own known answers (no GPU needed).
 
-  - the 75 shipped Float64 tables of the b-series and of a3 / a4 / a5 / a7 (src/precomputed_kernels/kernel_*.jl) - bit equality
+  - the 102 shipped Float64 tables of the b-series and of a3 / a4 / a5 / a7 (src/precomputed_kernels/kernel_*.jl),
+    antiderivative tables (_i1) and their D1 / D2 companions included - bit equality
   - the integer ghost matrices (src/convolution_coefs/polynomial_boundary.jl:29-179) - exact
   - the exact-rational kernel polynomials regenerate the tables (independent Fraction path)
 """
@@ -21,15 +22,16 @@ def test_oracle_tables_bit_equal_shipped_literals(oracle, golden_dir):
     g = _golden_tables(golden_dir)
     n = 0
     for name in g.files:
-        m = re.match(r"KERNEL_(D1_|D2_|)PRE_([ab]\d+)_d(\d+)$", name)
-        kernel, d = m.group(2), int(m.group(3)) + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
-        t = oracle.table(kernel, d)
+        m = re.match(r"KERNEL_(D1_|D2_|)PRE_([ab]\d+)_(d|i)(\d+)$", name)
+        base = int(m.group(4)) if m.group(3) == "d" else -int(m.group(4))  # _i1: the antiderivative family
+        kernel, d = m.group(2), base + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
+        t = oracle.table_i1(kernel) if d == -1 else oracle.table(kernel, d)
         lit = g[name]
         assert t.shape == lit.shape
         same = (t.view(np.uint64) == lit.view(np.uint64)) | ((t == 0) & (lit == 0))
         assert same.all(), name
         n += 1
-    assert n == 75
+    assert n == 102
 
 
 def test_d1_companion_is_next_derivative_table(golden_dir):
@@ -92,3 +94,14 @@ def test_table_properties(oracle):
         assert np.abs(t1.sum(axis=1)).max() < 1e-12
         e = t0.shape[1] // 2
         assert t0[0, e] == 1.0 and t0[100, e - 1] == 1.0  # K(0) = 1 at both ends of the table
+
+
+def test_antiderivative_tables(oracle):
+    # K~ is odd, saturates at -+1/2 at the ends of the support, and its table rows telescope: K~(s + 1 cell) - K~(s)
+    # summed over the columns = K~(eqs) - K~(-eqs) = 1 (precomputed_kernel_tables.jl:93-96, KERNEL_PRE_<k>_i1)
+    for k in ("b5", "b7", "b9", "b11", "b13", "a3", "a4", "a5", "a7"):
+        t = oracle.table_i1(k)
+        assert t[0, 0] == -0.5 and t[100, -1] == 0.5
+        assert np.array_equal(t[100, :-1], t[0, 1:])          # row 100 of column c is row 0 of column c + 1
+        assert np.abs(t + t[::-1, ::-1]).max() < 1e-16         # odd
+        assert np.abs((t[100] - t[0]).sum() - 1.0) < 1e-15

@@ -115,6 +115,28 @@ def kernel_value(polys, eqs, d, s):
     return acc
 
 
+def kernel_antiderivative(polys, eqs, s):
+    """K~(s) = int_0^s K(u) du (odd, saturating at +-1/2 for |s| >= eqs): the `_i1` tables
+    (precomputed_kernels/kernel_<k>.jl KERNEL_PRE_<k>_i1; selector precomputed_kernel_tables.jl:93-96)."""
+    sa = min(abs(s), Fraction(eqs))
+    acc = Fraction(0)
+    for piece in range(eqs):
+        lo, hi = Fraction(piece), min(sa, Fraction(piece + 1))
+        if hi <= lo:
+            break
+        acc += sum(ck * (hi ** (k + 1) - lo ** (k + 1)) / (k + 1) for k, ck in enumerate(polys[piece]))
+    return acc * ((s > 0) - (s < 0))
+
+
+def make_antiderivative_table(polys, eqs):
+    t = np.zeros((N_PRE, 2 * eqs))
+    for r in range(N_PRE):
+        for c in range(2 * eqs):
+            v = kernel_antiderivative(polys, eqs, Fraction(r, N_PRE - 1) - eqs + c)
+            t[r, c] = v.numerator / v.denominator
+    return t
+
+
 def make_table(polys, eqs, d):
     t = np.zeros((N_PRE, 2 * eqs))
     for r in range(N_PRE):
@@ -170,7 +192,7 @@ def main():
     polys_json = {}
     golden = {}
     inc = ["/* GENERATED by tools/gen_tables.py - do not edit.",
-           " * K^(d) tables, 101 rows x 2*eqs columns, row-major:",
+           " * K^(d) tables, 101 rows x 2*eqs columns, row-major (and the antiderivative tables K~ = _i1):",
            " *   T[r][c] = K^(d)(r/100 - eqs + c), exact rational arithmetic rounded once.",
            " * Bit-identical to the Float64 literals shipped by the reference",
            " * (src/precomputed_kernels/kernel_<k>.jl), asserted at generation time. */"]
@@ -183,11 +205,16 @@ def main():
             "pieces": [[f"{c.numerator}/{c.denominator}" for c in p] for p in polys]}
         shipped = read_shipped(kernel)
         tabs = {d: make_table(polys, eqs, d) for d in range(dmax + 1)}
+        tabs[-1] = make_antiderivative_table(polys, eqs)
         for name, lit in shipped.items():
-            m = re.match(rf"KERNEL_(D1_|D2_|)PRE_{kernel}_d(\d+)$", name)
+            m = re.match(rf"KERNEL_(D1_|D2_|)PRE_{kernel}_(d|i)(\d+)$", name)
             if not m:
-                continue  # antiderivative (_i1) tables: out of scope
-            d = int(m.group(2)) + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
+                continue
+            # antiderivative family: K~ = _i1, its D1 / D2 companions are K and K'
+            base = int(m.group(3)) if m.group(2) == "d" else -int(m.group(3))
+            d = base + {"": 0, "D1_": 1, "D2_": 2}[m.group(1)]
+            if d not in tabs:
+                continue  # a-series K'' companions are not needed (integral directions use the cubic subgrid)
             assert lit.shape == tabs[d].shape, (name, lit.shape)
             same = lit.view(np.uint64) == tabs[d].view(np.uint64)
             # +0.0 vs -0.0 both legal for exact zeros of odd derivatives
@@ -196,6 +223,7 @@ def main():
             assert not bad.any(), (name, int(bad.sum()))
             golden[name] = lit
             n_checked += lit.size
+        inc.append(c_array(f"CIB_TAB_{kernel}_i1", tabs[-1]))
         for d in range(dmax + 1):
             cname = f"CIB_TAB_{kernel}_d{d}"
             inc.append(c_array(cname, tabs[d]))
