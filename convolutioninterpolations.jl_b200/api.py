@@ -199,7 +199,8 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
         if need > MAX_TABLE_DERIVATIVE[k]:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative {dv} of :{k} with the :{sg} subgrid needs "
                                        f"K^({need}), which is not a shipped table")
-    if what == "convolution_interpolation":
+    if what == "convolution_interpolation" and not any(dv == -1 for dv in derivs):
+        # (the antiderivative evaluators take any per-axis mix of cubic / quintic: eval_sg_k, eval_subgrid_helpers.jl:2-19)
         # eager_2d.jl handles (linear, linear), (cubic, cubic), (quintic, quintic) only; the mixed pairs exist on the
         # per-dim path (perdim_2d.jl); N = 3 never resolves to quintic (_build_subgrids)
         if "quintic" in subgrids and ndim > 2:
