@@ -14,6 +14,8 @@
 // axes, on the device: one fused weight-and-scan pass for the first axis of the mask, in-place scans for the others,
 // one thread per line, walking the axis in the reference's order (Base._accumulate! for N-D arrays, the pairwise
 // accumulate_pairwise! for a Vector) so that the prefix sums carry the reference's own rounding.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -113,10 +115,62 @@ __global__ void itg_scan_kernel(ItgParams p, const double *__restrict__ in, doub
     return;
   }
   double s = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const double v = value(i);
-    s = i == 0 ? v : __dadd_rn(s, v);
-    out[off + (long long)i * st] = s;
+  constexpr int B = 8;  // loads of a batch are independent of the running sum: issue them together
+  for (int i0 = 0; i0 < n; i0 += B) {
+    double v[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) v[u] = i0 + u < n ? value(i0 + u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      if (i0 + u < n) {
+        s = (i0 + u) == 0 ? v[u] : __dadd_rn(s, v[u]);
+        out[off + (long long)(i0 + u) * st] = s;
+      }
+    }
+  }
+}
+
+// the same along the CONTIGUOUS axis of an N-D array (N >= 2): a warp owns 32 lines and walks them in 32-element chunks
+// through a shared-memory tile - coalesced loads with lane = position along the line, then lane = line for the
+// sequential sums (the order of Base._accumulate!), coalesced stores of the result.
+__global__ void __launch_bounds__(128) itg_scan_axis0_kernel(ItgParams p, const double *__restrict__ in, double *out,
+                                                             int mask, int first, long long nlines) {
+  __shared__ double tile[4][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long line0 = ((long long)blockIdx.x * 4 + w) * 32;
+  if (line0 >= nlines) return;
+  const int n = p.nk[0];
+  const int nl = (int)min(32LL, nlines - line0);
+  double carry = 0.0;
+  double w12[2] = {1.0, 1.0};  // (1/2 - lv) of axes 1 and 2 for lane's OWN line
+  if (first && lane < nl) {
+    const long long off = (line0 + lane) * n;
+#pragma unroll
+    for (int d = 1; d < 3; ++d)
+      if (d < p.ndim && (mask >> d & 1)) w12[d - 1] = __dsub_rn(0.5, p.lv[d][(off / p.stride[d]) % p.nk[d]]);
+  }
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int ni = min(32, n - i0);
+    // load: lane = element along the line
+    for (int r = 0; r < nl; ++r)
+      if (lane < ni) tile[w][r][lane] = first ? in[(line0 + r) * n + i0 + lane] : out[(line0 + r) * n + i0 + lane];
+    __syncwarp();
+    if (lane < nl) {
+      for (int i = 0; i < ni; ++i) {
+        double v = tile[w][lane][i];
+        if (first) {  // coefs .* (1/2 - lv_0) .* (1/2 - lv_1) .* (1/2 - lv_2), ascending axes
+          if (mask & 1) v = __dmul_rn(v, __dsub_rn(0.5, p.lv[0][i0 + i]));
+          if (mask & 2) v = __dmul_rn(v, w12[0]);
+          if (mask & 4) v = __dmul_rn(v, w12[1]);
+        }
+        carry = (i0 + i) == 0 ? v : __dadd_rn(carry, v);
+        tile[w][lane][i] = carry;
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < nl; ++r)
+      if (lane < ni) out[(line0 + r) * n + i0 + lane] = tile[w][r][lane];
+    __syncwarp();
   }
 }
 
@@ -235,6 +289,169 @@ __global__ void __launch_bounds__(128) itg_eval_kernel(ItgParams p, Coords c, do
   out[q] = res;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3-D: one warp resolves one evaluation point.  The thread-per-query kernel above issues 1 331 scattered loads per
+// lane (center 10^3 + faces 3 x 10^2 + edges 3 x 10 + corner for :b5); here lanes classify 32 queries in parallel, then
+// the warp walks them one by one: lanes = (axis, tap) for the window weights, then every term of every mask is a
+// flattened (c0, c1, c2) index space strided over the lanes, c0 fastest so that a row of 2 eqs coefficients is one
+// contiguous segment of a load instruction.
+// ---------------------------------------------------------------------------------------------
+// per-block decode tables of the flattened index spaces (query independent): for every mask the lane's first element
+// (c0, c1, c2) and the mixed-radix image of the lane stride 32, so that the hot loop has no division
+struct ItgDecode {
+  int start[8][32];  // c0 | c1 << 8 | c2 << 16
+  int step[8];       // a0 | a1 << 8 | a2 << 16
+  int cnt[8];        // c0n | c1n << 8 | c2n << 16
+};
+
+__device__ __forceinline__ double itg_warp_point(const ItgParams &p, const ItgDecode &dc, const double x0, const double x1,
+                                                 const double x2, double *W /*per-warp smem: 3 * wmax weights + a 1.0*/,
+                                                 int lane, bool &ok) {
+  const double x[3] = {x0, x1, x2};
+  int base[3];
+  bool lok[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int e = p.eqs[d];
+    const double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x[d], p.knot0[d]), p.h[d]), 1.0);
+    const bool fin = fabs(i_float) < 9.0e18;
+    ok = ok && fin;
+    long long i = fin ? (long long)floor(i_float) : (long long)e;
+    i = i < e ? e : i;
+    i = i > p.nk[d] - e ? p.nk[d] - e : i;
+    base[d] = (int)i - e;  // 0-based first window coefficient; Julia's l = i - eqs is the same number (valid if >= 1)
+    lok[d] = base[d] >= 1;
+  }
+  __syncwarp();
+  const int ONE = 3 * p.wmax;
+  for (int idx = lane; idx < ONE; idx += 32) {
+    const int d = idx / p.wmax, jj = idx - d * p.wmax;
+    if (jj < 2 * p.eqs[d]) {
+      const int j = (d == 0 ? base[0] : (d == 1 ? base[1] : base[2])) + 1 + jj;
+      W[idx] = __dsub_rn(itg_kt(p, d, j, d == 0 ? x0 : (d == 1 ? x1 : x2)), __ldg(p.lv[d] + (j - 1)));
+    }
+  }
+  __syncwarp();
+  const int s1 = (int)p.stride[1], s2 = (int)p.stride[2];  // the warp kernel is used below 2^31 coefficients only
+  double acc = 0.0;
+#pragma unroll 1
+  for (int mask = 0; mask < 8; ++mask) {
+    const bool f0 = !(mask & 1), f1 = !(mask & 2), f2 = !(mask & 4);
+    if ((!f0 && !lok[0]) || (!f1 && !lok[1]) || (!f2 && !lok[2])) continue;
+    const int off = (f0 ? base[0] : base[0] - 1) + (f1 ? base[1] : base[1] - 1) * s1 + (f2 ? base[2] : base[2] - 1) * s2;
+    const double *__restrict__ A = p.A[mask] + off;
+    const int cn = dc.cnt[mask], st = dc.step[mask], pk = dc.start[mask][lane];
+    const int c0n = cn & 255, c1n = (cn >> 8) & 255, total = c0n * c1n * (cn >> 16);
+    const int a0 = st & 255, a1 = (st >> 8) & 255, a2 = st >> 16;
+    int c0 = pk & 255, c1 = (pk >> 8) & 255, c2 = pk >> 16;
+    const int o0 = f0 ? 0 : ONE, o1 = f1 ? p.wmax : ONE, o2 = f2 ? 2 * p.wmax : ONE;  // saturated axes: c = 0, weight 1.0
+    constexpr int U = 8;  // independent loads in flight per lane
+    for (int e0 = lane; e0 < total; e0 += U * 32) {
+      double v[U], wt[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool in = e0 + 32 * u < total;
+        v[u] = in ? __ldg(A + (c0 + c1 * s1 + c2 * s2)) : 0.0;
+        wt[u] = in ? W[o0 + c0] * W[o1 + c1] * W[o2 + c2] : 0.0;
+        c0 += a0;
+        int carry = c0 >= c0n;
+        c0 -= carry ? c0n : 0;
+        c1 += a1 + carry;
+        carry = c1 >= c1n;
+        c1 -= carry ? c1n : 0;
+        c2 += a2 + carry;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc = fma(v[u], wt[u], acc);
+    }
+  }
+  const double total = warp_sum(acc);
+  return __dmul_rn(__dmul_rn(__dmul_rn(total, p.h[0]), p.h[1]), p.h[2]);
+}
+
+__global__ void __launch_bounds__(256) itg_eval_warp3d_kernel(ItgParams p, Coords c, double *__restrict__ out, long long nq,
+                                                              EvalStatus *st) {
+  extern __shared__ double smem[];
+  __shared__ ItgDecode dc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *W = smem + warp * (3 * p.wmax + 1);
+  {  // blockDim.x == 256 == 8 masks x 32 lanes
+    const int mask = warp, c0n = (mask & 1) ? 1 : 2 * p.eqs[0], c1n = (mask & 2) ? 1 : 2 * p.eqs[1],
+              c2n = (mask & 4) ? 1 : 2 * p.eqs[2], c01 = c0n * c1n;
+    const int c2 = lane / c01, r = lane - c2 * c01, c1 = r / c0n, c0 = r - c1 * c0n;
+    dc.start[mask][lane] = c0 | c1 << 8 | c2 << 16;
+    if (lane == 0) {
+      const int a2 = 32 / c01, r32 = 32 - a2 * c01, a1 = r32 / c0n, a0 = r32 - a1 * c0n;
+      dc.step[mask] = a0 | a1 << 8 | a2 << 16;
+      dc.cnt[mask] = c0n | c1n << 8 | c2n << 16;
+      W[3 * p.wmax] = 1.0;
+    }
+  }
+  __syncthreads();
+  const long long q0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+  if (q0 >= nq) return;
+  const long long q = q0 + lane;
+  // lane-parallel classification: extrapolation_operator.jl:39-61, extrapolate_point.jl:98-160
+  double xa[3] = {0, 0, 0}, xb[3] = {0, 0, 0}, dist = 0.0;
+  int ntask = 0;
+  if (q < nq) {
+    long long qd[3] = {q, q, q};
+    decode_coords<3>(c, q, qd);
+    double x[3];
+    bool inside = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      x[d] = ((const double *)c.x[d])[qd[d]];
+      if (x[d] > p.hi[d] || x[d] < p.lo[d]) inside = false;
+    }
+    if (inside) {
+      ntask = 1;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xa[d] = x[d];
+    } else if (p.extrap == CIB200_THROW) {
+      report(st, 1, q + c.qoff);
+    } else {
+      double dx[3], dist_sq = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        xa[d] = x[d] < p.lo[d] ? p.lo[d] : (x[d] > p.hi[d] ? p.hi[d] : x[d]);
+        dx[d] = __dsub_rn(x[d], xa[d]);
+        dist_sq = __dadd_rn(dist_sq, __dmul_rn(dx[d], dx[d]));
+      }
+      ntask = 1;
+      if (p.extrap == CIB200_LINE && !(dist_sq < 2.220446049250313e-16)) {
+        dist = __dsqrt_rn(dist_sq);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) xb[d] = __dsub_rn(xa[d], __ddiv_rn(__dmul_rn(p.eps_line, dx[d]), dist));
+        ntask = 2;
+      }
+    }
+  }
+  double res = CUDART_NAN;
+  const int nvalid = (int)min(32LL, nq - q0);
+  for (int t = 0; t < nvalid; ++t) {  // warp-uniform trip count
+    const int nt = __shfl_sync(0xffffffffu, ntask, t);
+    if (nt == 0) continue;
+    bool ok = true;
+    const double fb = itg_warp_point(p, dc, __shfl_sync(0xffffffffu, xa[0], t), __shfl_sync(0xffffffffu, xa[1], t),
+                                     __shfl_sync(0xffffffffu, xa[2], t), W, lane, ok);
+    double r = fb;
+    if (nt == 2) {
+      const double fin = itg_warp_point(p, dc, __shfl_sync(0xffffffffu, xb[0], t), __shfl_sync(0xffffffffu, xb[1], t),
+                                        __shfl_sync(0xffffffffu, xb[2], t), W, lane, ok);
+      r = finish_line(fb, fin, p.eps_line, __shfl_sync(0xffffffffu, dist, t));
+    }
+    if (lane == t) {
+      if (!ok) {
+        report(st, 2, q + c.qoff);
+        r = CUDART_NAN;
+      }
+      res = r;
+    }
+  }
+  if (q < nq) out[q] = res;
+}
+
 }  // namespace cib
 
 using namespace cib;
@@ -264,10 +481,19 @@ static int itg_launch(cib200_itg *h, const Coords &c, void *out, long long nq, c
     case 2:
       itg_eval_kernel<2><<<grid, bs, smem, st>>>(h->p, c, (double *)out, nq, h->d_status);
       break;
-    default:
-      if (smem > 48 * 1024) e = cudaFuncSetAttribute(itg_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) itg_eval_kernel<3><<<grid, bs, smem, st>>>(h->p, c, (double *)out, nq, h->d_status);
+    default: {
+      static const bool thread_kernel = getenv("CIB200_ITG_THREAD3D") != nullptr;  // the v0 kernel, kept for comparison
+      if (thread_kernel || h->ntot >= (1LL << 31)) {  // the warp kernel indexes with 32-bit offsets
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(itg_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) itg_eval_kernel<3><<<grid, bs, smem, st>>>(h->p, c, (double *)out, nq, h->d_status);
+      } else {
+        const int wpb = 8;  // warps per block, 32 queries per warp
+        const unsigned g3 = (unsigned)((nq + 32 * wpb - 1) / (32 * wpb));
+        itg_eval_warp3d_kernel<<<g3, 32 * wpb, sizeof(double) * (3 * h->p.wmax + 1) * wpb, st>>>(h->p, c, (double *)out, nq,
+                                                                                         h->d_status);
+      }
       break;
+    }
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -476,6 +702,13 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) return fail(e);
   // left_values, then the prefix arrays: scans over the axes of the mask in ascending order (constructor.jl:207-343)
+  const bool stats = getenv("CIB200_ITG_STATS") != nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (stats) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, h->stream);
+  }
   for (int d = 0; d < nd; ++d) {
     itg_left_values_kernel<<<(p.nk[d] + 127) / 128, 128, 0, h->stream>>>(p, d, h->d_lv[d]);
     CIB_LAUNCHED();
@@ -494,15 +727,28 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
     for (int ax = 0; ax < nd; ++ax) {
       if (!(mask >> ax & 1)) continue;
       const long long nlines = tot / p.nk[ax];
-      itg_scan_kernel<<<(unsigned)((nlines + 127) / 128), 128, 0, h->stream>>>(p, h->d_coefs, h->d_tail[mask], mask, ax,
-                                                                               first, nlines);
+      if (ax == 0 && nd > 1)
+        itg_scan_axis0_kernel<<<(unsigned)((nlines + 127) / 128), 128, 0, h->stream>>>(p, h->d_coefs, h->d_tail[mask], mask,
+                                                                                       first, nlines);
+      else
+        itg_scan_kernel<<<(unsigned)((nlines + 127) / 128), 128, 0, h->stream>>>(p, h->d_coefs, h->d_tail[mask], mask, ax,
+                                                                                 first, nlines);
       CIB_LAUNCHED();
       first = 0;
     }
     p.A[mask] = h->d_tail[mask];
   }
+  if (stats) cudaEventRecord(ev1, h->stream);
   e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    fprintf(stderr, "[cib200_itg_create] left values + %d prefix arrays of %.1f MB: %.3f ms on the device (allocation included)\n",
+            (1 << nd) - 1, tot * 8 / 1e6, ms);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
   if (e != cudaSuccess) return fail(e);
   *handle = h;
   return CIB200_OK;
