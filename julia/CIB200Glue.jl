@@ -49,6 +49,9 @@ kernel_symbols(::HigherOrderKernel{KS}) where {KS} = KS        # struct_construc
 kernel_symbols(::HigherOrderMixedKernel{KS}) where {KS} = KS
 kernel_symbols(_) = nothing
 
+# antiderivative on EVERY axis (FastIntegralOrder, convolution_fast_integration_{1d,2d,3d}.jl): cib200_itg_*
+is_integral(itp::FastConvolutionInterpolation) = itp.derivative_order isa FastIntegralOrder
+
 function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     (T === Float64 || T === Float32) || return false
     1 <= N <= 8 || return false                                          # CIB200_MAX_ND
@@ -56,6 +59,12 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     ks === nothing && return false
     all(k -> haskey(KERNEL_ID, k), ks) || return false
     itp.lazy === Val{false}() || return false
+    if is_integral(itp)
+        # shipped K~ / K / K' tables only: Float64, N <= 3, cubic or quintic subgrid on every axis (mixed integral /
+        # interpolation axes and N >= 4 resolve to :linear on generated tables, _build_subgrids)
+        return T === Float64 && N <= 3 && all(d -> length(itp.pre_range[d]) == 101, 1:N) &&
+               all(s -> s === :cubic || s === :quintic, subgrid_tuple(itp))
+    end
     itp.derivative_order isa DerivativeOrder || return false
     dv = derivative_tuple(itp)
     all(d -> length(itp.pre_range[d]) == 101, 1:N) || return false   # precompute = 101: the shipped tables
@@ -115,6 +124,21 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
                 finalizer(x -> ccall((:cib200_itpnd_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
                 return h
             end
+            if is_integral(itp)
+                # the library builds left_values and the prefix-sum tails itself (constructor.jl:176-364, :414-448) from
+                # itp.coefs; itp.tail* of the Julia struct are not read
+                desc = Ref(ItpDesc(Int32(N), Int32(0), pad3(Int64.(size(itp.coefs)), Int64(1)), pointer(itp.coefs),
+                                   pad3(ntuple(d -> pointer(knots64[d]), N), Ptr{Float64}(0)),
+                                   pad3(Float64.(itp.h), 1.0), pad3(ntuple(d -> Int32(KERNEL_ID[ks[d]]), N), Int32(0)),
+                                   pad3(ntuple(_ -> Int32(-1), N), Int32(0)), extrap_id(etp.et), Int32(0),
+                                   pad3(ntuple(d -> Int32(SUBGRID_ID[subgrid_tuple(itp)[d]]), N), Int32(0))))
+                out = Ref{Ptr{Cvoid}}(C_NULL)
+                GC.@preserve itp knots64 check(ccall((:cib200_itg_create, LIB), Int32,
+                                                     (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
+                h = Handle(out[])
+                finalizer(x -> ccall((:cib200_itg_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+                return h
+            end
             desc = Ref(ItpDesc(Int32(N), T === Float32 ? Int32(1) : Int32(0),
                                pad3(Int64.(size(itp.coefs)), Int64(1)), pointer(itp.coefs),
                                pad3(ntuple(d -> pointer(knots64[d]), N), Ptr{Float64}(0)),
@@ -155,6 +179,12 @@ function Base.Broadcast.broadcasted(etp::ConvolutionExtrapolation{T,N}, xs::Vara
         return out
     end
     hp = hd.ptr
+    if is_integral(etp.itp)
+        GC.@preserve xq out ptrs check(ccall((:cib200_itg_eval, LIB), Int32,
+            (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+            hp, nq, ptrs, out, 0, C_NULL, bad))
+        return out
+    end
     GC.@preserve xq out ptrs check(N >= 4 ?   # ccall needs a literal symbol: one call site per entry point
         ccall((:cib200_itpnd_eval, LIB), Int32,
               (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
@@ -174,6 +204,12 @@ function (etp::ConvolutionExtrapolation{T,N})(xs::Vararg{AbstractVector{<:Real},
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
     bad = Ref{Int64}(-1)
     hp = handle(etp).ptr
+    if is_integral(etp.itp)
+        GC.@preserve xq out ptrs check(ccall((:cib200_itg_eval_grid, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+            hp, n, ptrs, out, 0, C_NULL, bad))
+        return out
+    end
     GC.@preserve xq out ptrs check(N >= 4 ?
         ccall((:cib200_itpnd_eval_grid, LIB), Int32,
               (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
