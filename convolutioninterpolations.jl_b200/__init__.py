@@ -10,9 +10,9 @@ The directory name contains a dot, so import it through the `convitp_b200` shim 
 from ._lib import (CIB200Error, DomainError, InexactError, UnsupportedModeError, SO_PATH, SYMBOLS, check, launch_count,
                    lib)
 from . import sharding
-from .api import (ConvolutionExtrapolation, FastConvolutionInterpolation, Flat, Line, Natural, Throw,
+from .api import (ConvolutionExtrapolation, FastConvolutionInterpolation, Flat, Line, LinearSubgridTableWarning, Natural, Throw,
                   convolution_interpolation, convolution_resample, convolution_smooth)
 
 __all__ = ["convolution_interpolation", "convolution_resample", "convolution_smooth", "ConvolutionExtrapolation",
            "FastConvolutionInterpolation", "Throw", "Flat", "Line", "Natural", "CIB200Error", "DomainError",
-           "InexactError", "UnsupportedModeError", "lib", "launch_count", "SO_PATH", "SYMBOLS", "sharding"]
+           "InexactError", "UnsupportedModeError", "LinearSubgridTableWarning", "lib", "launch_count", "SO_PATH", "SYMBOLS", "sharding"]

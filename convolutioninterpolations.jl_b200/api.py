@@ -162,6 +162,21 @@ def _build_subgrids(kernels, derivs, subgrids):
     return tuple(out)
 
 
+class LinearSubgridTableWarning(UserWarning):
+    """A :linear-subgrid axis is evaluated on the 101-row shipped table; the reference generates >= 10 000 rows for such
+    axes (precompute_actual = max(precompute, 10_000): fast_convolution_interpolation_constructor.jl:117-118,
+    convolution_resample.jl:228-229), so results agree with it only up to the table-resolution term
+    h_pre^2 / 8 * max|K''| ~ 1e-5 relative (DESIGN.md 1, row f)."""
+
+
+def _warn_linear_rows(subgrids, kernels, what):
+    if any(sg == "linear" and k not in ("a0", "a1") for sg, k in zip(subgrids, kernels)):
+        import warnings
+        warnings.warn(f"{what}: :linear subgrid axes {tuple(subgrids)} are evaluated on 101-row tables, the reference "
+                      "uses >= 10 000 rows for them (agreement ~1e-5 relative, not 1e-12)", LinearSubgridTableWarning,
+                      stacklevel=3)
+
+
 def _effective_subgrids(subgrids, ndim):
     """What the evaluators do with a resolved subgrid tuple: in 3-D anything but all-cubic is evaluated with linear
     blending on every axis (eager_3d.jl:139-176; perdim_3d.jl:161 "fallback to all linear")."""
@@ -258,6 +273,7 @@ class FastConvolutionInterpolation:
         if not self._itg:
             self.subgrid = _effective_subgrids(self.subgrid, nd)
         _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation", self.perdim)
+        _warn_linear_rows(self.subgrid, self.kernel, "convolution_interpolation")
         if self._itg and self.dtype_id != _lib.F64:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, "the antiderivative path is Float64 only")
         self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
@@ -604,6 +620,8 @@ def convolution_resample(knots_in, knots_out, values, precompute=_UNSET, kernel=
     if kwless and nd > 10:
         raise TypeError("no method matching convolution_resample for N > 10 without keyword arguments")
     _require_accelerated(kernels, derivs, sgs_valid, nd, "convolution_resample")
+    if not kwless:
+        _warn_linear_rows(sgs_valid, kernels, "convolution_resample")  # :228-229 precompute_actual >= 10 000
     did, memkind, in_ptr, make_out, stream, keep = _sweep_io(values, dtype)
     ndt = _np_dtype(did)
     # T.(knots): :183-188

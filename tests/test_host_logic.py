@@ -177,3 +177,16 @@ def test_no_cpu_fallback_without_a_device(ci):
         ci.convolution_smooth(np.linspace(0, 1, 100), np.zeros(100), 0.05)
     with pytest.raises(ci.CIB200Error):
         ci.convolution_resample(x, x, np.sin(x))
+
+
+def test_linear_subgrid_axes_warn_about_the_table_length(ci):
+    """The reference raises :linear axes to >= 10 000 table rows (constructor.jl:117-118); this library evaluates them on
+    the 101-row shipped tables and must say so (DESIGN.md 1, row f) - checked on the mode resolution, no device needed."""
+    from convitp_b200 import api
+    with pytest.warns(ci.LinearSubgridTableWarning):
+        api._warn_linear_rows(("linear", "cubic"), ("b5", "b5"), "test")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        api._warn_linear_rows(("cubic", "quintic"), ("b5", "b5"), "test")
+        api._warn_linear_rows(("linear",), ("a1",), "test")  # a0 / a1 keep their two-row tables
