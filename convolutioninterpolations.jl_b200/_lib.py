@@ -27,6 +27,7 @@ SYMBOLS = [
     "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
     "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itp_eval_multi", "cib200_device_count",
     "cib200_set_device", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
+    "cib200_itp_create_tables", "cib200_itpnd_create_tables",
     "cib200_itg_create", "cib200_itg_destroy", "cib200_itg_eval", "cib200_itg_eval_grid", "cib200_itg_get",
 ]
 
@@ -78,6 +79,7 @@ def lib():
     L.cib200_build_coefs_device.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     L.cib200_extend_knots.argtypes = [vp, i64, i32, vp]
     L.cib200_itp_create.argtypes = [C.POINTER(ItpDesc), C.POINTER(vp)]
+    L.cib200_itp_create_tables.argtypes = [C.POINTER(ItpDesc), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
     L.cib200_itp_destroy.argtypes = [vp]
     L.cib200_itp_get_coefs.argtypes = [vp, vp]
     L.cib200_itp_set_eval_mode.argtypes = [vp, i32]
@@ -87,6 +89,8 @@ def lib():
     L.cib200_set_device.argtypes = [i32]
     L.cib200_itp_eval_multi.argtypes = [C.POINTER(vp), i32, i64, C.POINTER(vp), vp, C.POINTER(i64)]
     L.cib200_itpnd_create.argtypes = [i32, i32, vp, vp, C.POINTER(vp), vp, vp, vp, i32, i32, C.POINTER(vp)]
+    L.cib200_itpnd_create_tables.argtypes = [i32, i32, vp, vp, C.POINTER(vp), vp, vp, vp, i32, i32, C.POINTER(vp),
+                                             C.POINTER(i32), C.POINTER(vp)]
     L.cib200_itpnd_destroy.argtypes = [vp]
     L.cib200_itpnd_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
     L.cib200_itpnd_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]

@@ -236,7 +236,7 @@ class FastConvolutionInterpolation:
 
     def __init__(self, knots, values, kernel="b5", precompute=101, bc="detect", derivative=0, subgrid="cubic",
                  lazy=False, boundary_fallback=False, dtype=None, eval_mode="auto", _extrap="throw", coefs_on="host",
-                 devices=None):
+                 devices=None, linear_rows=None):
         values = np.asarray(values)
         if values.dtype not in (np.float32, np.float64):
             values = values.astype(np.float64)
@@ -273,7 +273,19 @@ class FastConvolutionInterpolation:
         if not self._itg:
             self.subgrid = _effective_subgrids(self.subgrid, nd)
         _require_accelerated(self.kernel, self.derivative, self.subgrid, nd, "convolution_interpolation", self.perdim)
-        _warn_linear_rows(self.subgrid, self.kernel, "convolution_interpolation")
+        # :linear axes: precompute_actual = max(precompute, 10_000) rows, generated from exact rationals
+        # (constructor.jl:117-118); linear_rows=101 evaluates them on the shipped tables instead (NOT the reference's
+        # result: ~1e-4 relative away; kept for the kernels' own tests and for comparisons)
+        from . import tables as _tables
+        self.linear_rows = _tables.LINEAR_ROWS if linear_rows is None else int(linear_rows)
+        self._gen_tables = [None] * nd
+        if not self._itg and self.linear_rows != 101:
+            for d in range(nd):
+                if self.subgrid[d] == "linear":
+                    self._gen_tables[d] = np.asfortranarray(
+                        _tables.generated_table(self.kernel[d], int(self.derivative[d]), self.linear_rows))
+        elif not self._itg:
+            _warn_linear_rows(self.subgrid, self.kernel, "convolution_interpolation")
         if self._itg and self.dtype_id != _lib.F64:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, "the antiderivative path is Float64 only")
         self.eqs = tuple(DEGREE_TO_EQUATIONS[k] for k in self.kernel)
@@ -326,8 +338,10 @@ class FastConvolutionInterpolation:
             handle = C.c_void_p()
             if coefs_on == "device":
                 coefs_ptr = self.coefs.ctypes.data  # the N-D constructor copies from host memory
-            check(L.cib200_itpnd_create(nd, self.dtype_id, cs, coefs_ptr, kp, hh, kid, dv,
-                                        EXTRAP_IDS[_extrap], int(self.perdim), C.byref(handle)))
+            tp = (C.c_void_p * nd)(*[None if t is None else t.ctypes.data for t in self._gen_tables])
+            npre = (C.c_int32 * nd)(*[0 if t is None else t.shape[0] for t in self._gen_tables])
+            check(L.cib200_itpnd_create_tables(nd, self.dtype_id, cs, coefs_ptr, kp, hh, kid, dv,
+                                               EXTRAP_IDS[_extrap], int(self.perdim), tp, npre, C.byref(handle)))
             if devices is not None and len(devices) > 1:
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, "devices=[...] (single-process multi-GPU) covers 1-3 dimensions")
             self._handle = handle
@@ -365,9 +379,11 @@ class FastConvolutionInterpolation:
         # one handle per device (the grid is replicated, query batches are split by cib200_itp_eval_multi);
         # devices=None: the current device only
         self._handles = []
+        tp = (C.c_void_p * 3)(*[None if t is None else t.ctypes.data for t in self._gen_tables] + [None] * (3 - nd))
+        npre = (C.c_int32 * 3)(*[0 if t is None else t.shape[0] for t in self._gen_tables] + [0] * (3 - nd))
         if devices is None:
             handle = C.c_void_p()
-            check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
+            check(L.cib200_itp_create_tables(C.byref(desc), tp, npre, C.byref(handle)))
             self._handles.append(handle)
         else:
             import torch
@@ -376,7 +392,7 @@ class FastConvolutionInterpolation:
             for dev in devices:
                 with torch.cuda.device(int(dev)):
                     handle = C.c_void_p()
-                    check(L.cib200_itp_create(C.byref(desc), C.byref(handle)))
+                    check(L.cib200_itp_create_tables(C.byref(desc), tp, npre, C.byref(handle)))
                     self._handles.append(handle)
         self.devices = None if devices is None else tuple(int(d) for d in devices)
         self._handle = self._handles[0]
@@ -511,7 +527,7 @@ class ConvolutionExtrapolation:
 
 def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=101, extrap=None, bc="detect",
                               derivative=0, subgrid="cubic", lazy=False, boundary_fallback=False, dtype=None,
-                              eval_mode="auto", coefs_on="host", devices=None):
+                              eval_mode="auto", coefs_on="host", devices=None, linear_rows=None):
     """convolution_interpolation(knots, values; kernel, fast, precompute, extrap, bc, derivative, subgrid,
     lazy, boundary_fallback)  -  convolution_interpolation_function.jl:79-157"""
     values = np.asarray(values)
@@ -546,7 +562,7 @@ def convolution_interpolation(knots, values, kernel="b5", fast=True, precompute=
     itp = FastConvolutionInterpolation(knots_t, values, kernel=kernels, precompute=precompute, bc=tuple(fixed),
                                        derivative=derivs, subgrid=subgrid, lazy=lazy,
                                        boundary_fallback=boundary_fallback, dtype=dtype, eval_mode=eval_mode,
-                                       _extrap=et.name, coefs_on=coefs_on, devices=devices)
+                                       _extrap=et.name, coefs_on=coefs_on, devices=devices, linear_rows=linear_rows)
     return ConvolutionExtrapolation(itp, et)
 
 

@@ -457,7 +457,17 @@ int32_t cib200_build_coefs_device(int32_t ndim, int32_t dtype, const int64_t *n,
   return rc;
 }
 
+static int32_t itp_create_impl(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                               cib200_itp **handle);
 int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
+  return itp_create_impl(desc, nullptr, nullptr, handle);
+}
+int32_t cib200_itp_create_tables(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                                 cib200_itp **handle) {
+  return itp_create_impl(desc, tables, n_pre, handle);
+}
+static int32_t itp_create_impl(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                               cib200_itp **handle) {
   if (!desc || !handle) {
     set_error("cib200_itp_create: null argument");
     return CIB200_EINVAL;
@@ -583,35 +593,54 @@ int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle) {
     p.lo[d] = desc->knots[d][eqs[d] - 1];
     p.hi[d] = desc->knots[d][h->cshape[d] - 1 - (eqs[d] - 1)];
   }
-  // distinct (kernel, derivative) tables -> one packed device image
-  struct Slot { int kernel, d; };
+  // distinct (kernel, derivative, rows) tables -> one packed device image.  rows = 101: the shipped tables; a :linear
+  // axis may bring the generated table the reference builds for it (tables[d], n_pre[d] >= 10 000 rows, Julia memory
+  // order n_pre x 2 eqs column-major = itp.kernel_pre[d]; constructor.jl:117-118), transposed here to row-major
+  struct Slot { int kernel, d, rows; const double *src; };
   std::vector<Slot> slots;
-  auto slot_of = [&](int kernel, int d) {
+  auto slot_of = [&](int kernel, int d, int rows, const double *src) {
     for (size_t i = 0; i < slots.size(); ++i)
-      if (slots[i].kernel == kernel && slots[i].d == d) return (int)i;
-    slots.push_back({kernel, d});
+      if (slots[i].kernel == kernel && slots[i].d == d && slots[i].rows == rows) return (int)i;
+    slots.push_back({kernel, d, rows, src});
     return (int)slots.size() - 1;
   };
   for (int d = 0; d < nd; ++d) {
-    p.tab_slot_k[d] = slot_of(h->kernel[d], h->deriv[d]);
+    const bool gen = tables && n_pre && tables[d] && desc->subgrid[d] == CIB200_SG_LINEAR;
+    if (gen && n_pre[d] < 2) {
+      set_error("cib200_itp_create_tables: n_pre[%d] = %d", d, n_pre[d]);
+      cib200_itp_destroy(h);
+      return CIB200_EINVAL;
+    }
+    p.npre[d] = gen ? n_pre[d] : CIB_TAB_ROWS;
+    p.tab_slot_k[d] = slot_of(h->kernel[d], h->deriv[d], p.npre[d], gen ? tables[d] : nullptr);
     // linear axes read K only: their "derivative" table aliases K (its terms carry zero factors)
-    p.tab_slot_d[d] = desc->subgrid[d] == CIB200_SG_LINEAR ? p.tab_slot_k[d] : slot_of(h->kernel[d], h->deriv[d] + 1);
+    p.tab_slot_d[d] = desc->subgrid[d] == CIB200_SG_LINEAR ? p.tab_slot_k[d]
+                                                           : slot_of(h->kernel[d], h->deriv[d] + 1, CIB_TAB_ROWS, nullptr);
   }
+  for (int d = nd; d < 3; ++d) p.npre[d] = CIB_TAB_ROWS;
   p.prerange_pos = (nd == 2 && !desc->perdim && desc->subgrid[0] == CIB200_SG_LINEAR && desc->subgrid[1] == CIB200_SG_LINEAR) ? 1 : 0;
   for (int d = 0; d < 3; ++d) {
     p.subgrid[d] = d < nd ? desc->subgrid[d] : 0;
-    p.tab_slot_e[d] = (d < nd && desc->subgrid[d] == CIB200_SG_QUINTIC) ? slot_of(h->kernel[d], h->deriv[d] + 2) : -1;
+    p.tab_slot_e[d] = (d < nd && desc->subgrid[d] == CIB200_SG_QUINTIC) ? slot_of(h->kernel[d], h->deriv[d] + 2, CIB_TAB_ROWS, nullptr) : -1;
   }
   p.n_tab_slots = (int)slots.size();
   size_t tab_doubles = 0;
-  for (auto &s : slots) tab_doubles += (size_t)CIB_TAB_ROWS * 2 * kernel_eqs(s.kernel);
+  for (auto &s : slots) tab_doubles += (size_t)s.rows * 2 * kernel_eqs(s.kernel);
   CIB_CREATE_CUDA(cudaMalloc(&h->d_tables, sizeof(double) * tab_doubles));
   size_t off = 0;
   for (size_t i = 0; i < slots.size(); ++i) {
     const int e = kernel_eqs(slots[i].kernel);
-    const size_t nelem = (size_t)CIB_TAB_ROWS * 2 * e;
-    CIB_CREATE_CUDA(cudaMemcpy(h->d_tables + off, host_table(slots[i].kernel, slots[i].d), sizeof(double) * nelem, cudaMemcpyHostToDevice));
+    const size_t nelem = (size_t)slots[i].rows * 2 * e;
+    if (slots[i].src) {
+      std::vector<double> rm(nelem);
+      for (int r = 0; r < slots[i].rows; ++r)
+        for (int c = 0; c < 2 * e; ++c) rm[(size_t)r * 2 * e + c] = slots[i].src[(size_t)c * slots[i].rows + r];
+      CIB_CREATE_CUDA(cudaMemcpy(h->d_tables + off, rm.data(), sizeof(double) * nelem, cudaMemcpyHostToDevice));
+    } else {
+      CIB_CREATE_CUDA(cudaMemcpy(h->d_tables + off, host_table(slots[i].kernel, slots[i].d), sizeof(double) * nelem, cudaMemcpyHostToDevice));
+    }
     p.tab_slot_eqs[i] = e;
+    p.tab_slot_rows[i] = slots[i].rows;
     p.tab_slot_ptr[i] = h->d_tables + off;
     off += nelem;
   }

@@ -869,6 +869,8 @@ bool binned_supported(const cib200_itp *h) {
   const ItpParams &p = h->p;
   if (p.ndim != 3 || h->dtype != CIB200_F64) return false;
   if (p.eqs[0] != p.eqs[1] || p.eqs[1] != p.eqs[2]) return false;
+  for (int d = 0; d < 3; ++d)
+    if (p.npre[d] != CIB_N_PRE) return false;  // generated tables of :linear axes: records / staging assume 101 rows
   if (p.eqs[0] < 5) return false;  // a-series stencils (4^3 .. 8^3) stay on the gather kernel
   if ((p.s1 & 1) || (p.s2 & 1)) return false;  // TMA global strides must be multiples of 16 bytes
   const int T = BRICK_SIDE + 1 - 2 * p.eqs[0];

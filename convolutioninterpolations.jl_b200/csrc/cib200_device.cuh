@@ -15,7 +15,7 @@ struct AxisPos {
 };
 
 __device__ __forceinline__ bool locate_from_knot(double x, double knot0, double h, int eqs, int nk,
-                                                 const double *__restrict__ knots, AxisPos &p) {
+                                                 const double *__restrict__ knots, AxisPos &p, int npre = CIB_N_PRE) {
   double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x, knot0), h), 1.0);
   bool ok = fabs(i_float) < 9.0e18;  // floor(Int, .) throws InexactError otherwise (NaN / Inf)
   long long i = ok ? (long long)floor(i_float) : (long long)eqs;
@@ -23,11 +23,11 @@ __device__ __forceinline__ bool locate_from_knot(double x, double knot0, double 
   i = i > nk - eqs ? nk - eqs : i;
   double knot_i = knots[i - 1];  // the STORED knot, not knot0 + (i-1) h
   double x_diff_right = __dsub_rn(1.0, __ddiv_rn(__dsub_rn(x, knot_i), h));
-  double cidx = __dadd_rn(__dmul_rn(x_diff_right, (double)(CIB_N_PRE - 1)), 1.0);
+  double cidx = __dadd_rn(__dmul_rn(x_diff_right, (double)(npre - 1)), 1.0);
   ok = ok && (fabs(cidx) < 9.0e18);
   int idx = ok ? (int)floor(cidx) : 1;
   idx = idx < 1 ? 1 : idx;
-  idx = idx > CIB_N_PRE - 1 ? CIB_N_PRE - 1 : idx;
+  idx = idx > npre - 1 ? npre - 1 : idx;
   p.base = (int)(i - eqs);
   p.row = idx - 1;
   p.t = __dsub_rn(cidx, (double)idx);
@@ -37,7 +37,7 @@ __device__ __forceinline__ bool locate_from_knot(double x, double knot0, double 
 // (linear, linear) on the single-kernel 2-D path (eager_2d.jl:93-107): the table row comes from
 // floor(diff_right (n_pre - 1)) + 1 and t from the stored pre_range values, pre_range[r] = Float64((r-1)//(n_pre-1))
 __device__ __forceinline__ bool locate_prerange(double x, double knot0, double h, int eqs, int nk,
-                                                const double *__restrict__ knots, AxisPos &p) {
+                                                const double *__restrict__ knots, AxisPos &p, int npre = CIB_N_PRE) {
   double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x, knot0), h), 1.0);
   bool ok = fabs(i_float) < 9.0e18;
   long long i = ok ? (long long)floor(i_float) : (long long)eqs;
@@ -45,12 +45,12 @@ __device__ __forceinline__ bool locate_prerange(double x, double knot0, double h
   i = i > nk - eqs ? nk - eqs : i;
   const double knot_i = knots[i - 1];
   const double diff_right = __dsub_rn(1.0, __ddiv_rn(__dsub_rn(x, knot_i), h));
-  const double f = __dmul_rn(diff_right, (double)(CIB_N_PRE - 1));
+  const double f = __dmul_rn(diff_right, (double)(npre - 1));
   ok = ok && (fabs(f) < 9.0e18);
   int idx = ok ? (int)floor(f) + 1 : 1;
   idx = idx < 1 ? 1 : idx;
-  idx = idx > CIB_N_PRE - 1 ? CIB_N_PRE - 1 : idx;
-  const double r0 = __ddiv_rn((double)(idx - 1), (double)(CIB_N_PRE - 1)), r1 = __ddiv_rn((double)idx, (double)(CIB_N_PRE - 1));
+  idx = idx > npre - 1 ? npre - 1 : idx;
+  const double r0 = __ddiv_rn((double)(idx - 1), (double)(npre - 1)), r1 = __ddiv_rn((double)idx, (double)(npre - 1));
   p.base = (int)(i - eqs);
   p.row = idx - 1;
   p.t = __ddiv_rn(__dsub_rn(diff_right, r0), __dsub_rn(r1, r0));
@@ -59,8 +59,8 @@ __device__ __forceinline__ bool locate_prerange(double x, double knot0, double h
 
 // position of x on axis d in the variant the interpolant's evaluator uses
 __device__ __forceinline__ bool locate_axis(const ItpParams &p, int d, double x, AxisPos &pos) {
-  if (p.prerange_pos) return locate_prerange(x, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pos);
-  return locate_from_knot(x, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pos);
+  if (p.prerange_pos) return locate_prerange(x, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pos, p.npre[d]);
+  return locate_from_knot(x, p.knot0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pos, p.npre[d]);
 }
 
 // resample variant: the cell's left knot is COMPUTED (convolution_resample.jl:322-326)
@@ -143,21 +143,27 @@ __device__ __forceinline__ double blended_weight_quintic(const Hermite &b, const
   return blended_weight(b, tk, td, row, col, w) + (b.h20 * e0[0] + b.h21 * e0[w]);
 }
 
-// copy the distinct tables of an interpolant into shared memory; returns nothing, fills ptr arrays
+// copy the distinct 101-row tables of an interpolant into shared memory and fill the per-axis pointers; the generated
+// tables of :linear axes (>= 10 000 rows, constructor.jl:117-118) are too large to stage and are read from global
+// memory (they are L2-resident: 0.8 - 1.4 MB)
 __device__ __forceinline__ void stage_tables(const ItpParams &p, double *smem, const double *tk[3],
                                              const double *td[3]) {
-  int off[9];
+  const double *at[9];
   int o = 0;
   for (int s = 0; s < p.n_tab_slots; ++s) {
-    off[s] = o;
-    int nelem = CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
     const double *src = p.tab_slot_ptr[s];
+    if (p.tab_slot_rows[s] != CIB_TAB_ROWS) {
+      at[s] = src;
+      continue;
+    }
+    at[s] = smem + o;
+    int nelem = CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
     for (int i = threadIdx.x; i < nelem; i += blockDim.x) smem[o + i] = src[i];
     o += nelem;
   }
   for (int d = 0; d < p.ndim; ++d) {
-    tk[d] = smem + off[p.tab_slot_k[d]];
-    td[d] = smem + off[p.tab_slot_d[d]];
+    tk[d] = at[p.tab_slot_k[d]];
+    td[d] = at[p.tab_slot_d[d]];
   }
 }
 
@@ -165,13 +171,15 @@ __device__ __forceinline__ void stage_tables(const ItpParams &p, double *smem, c
 __device__ __forceinline__ const double *staged_e_table(const ItpParams &p, const double *smem, int d) {
   if (p.tab_slot_e[d] < 0) return nullptr;
   int o = 0;
-  for (int s = 0; s < p.tab_slot_e[d]; ++s) o += CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
+  for (int s = 0; s < p.tab_slot_e[d]; ++s)
+    if (p.tab_slot_rows[s] == CIB_TAB_ROWS) o += CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
   return smem + o;
 }
 
 __host__ __device__ inline int tables_smem_doubles(const ItpParams &p) {
   int o = 0;
-  for (int s = 0; s < p.n_tab_slots; ++s) o += CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
+  for (int s = 0; s < p.n_tab_slots; ++s)
+    if (p.tab_slot_rows[s] == CIB_TAB_ROWS) o += CIB_TAB_ROWS * 2 * p.tab_slot_eqs[s];
   return o;
 }
 

@@ -22,6 +22,7 @@
 #include <limits>
 
 #include <algorithm>
+#include <vector>
 
 #include "cib200_device.cuh"
 
@@ -37,7 +38,8 @@ struct NdParams {
   int nk[MAXND], eqs[MAXND];
   long long stride[MAXND];       // element strides of the padded grid (column-major)
   const double *knots[MAXND];    // device, extended knots
-  const double *tab[MAXND];      // device, K^(deriv_d) of axis d, 101 x 2 eqs_d
+  const double *tab[MAXND];      // device, K^(deriv_d) of axis d, npre[d] x 2 eqs_d
+  int npre[MAXND];               // 101 (shipped) or the generated length of the :linear axes (>= 10 000 in the reference)
   double h[MAXND], lo[MAXND], hi[MAXND], knot0[MAXND];
   double scale, eps_line;
 };
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(128) eval_nd_kernel(const NdParams p, const Nd
   const int ax = lane < nd ? lane : 0;
   const double lo = p.lo[ax], hi = p.hi[ax], hh = p.h[ax], k0 = p.knot0[ax];
   const int eq = p.eqs[ax], nk = p.nk[ax];
+  const int npre = p.perdim ? p.npre[ax] : p.npre[0];  // eager_nd.jl reads itp.pre_range[1] on every axis
   const double *__restrict__ kn = p.knots[ax];
   const long long sax = p.stride[ax];
   const unsigned axmask = nd >= 32 ? 0xffffffffu : ((1u << nd) - 1u);
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(128) eval_nd_kernel(const NdParams p, const Nd
       for (int task = 0; task < ntask; ++task) {
         const double xe = task == 0 ? cl : __dsub_rn(cl, __ddiv_rn(__dmul_rn(p.eps_line, dx), dist));
         AxisPos pos;
-        const bool ok = p.perdim ? locate_from_knot(xe, k0, hh, eq, nk, kn, pos) : locate_prerange(xe, k0, hh, eq, nk, kn, pos);
+        const bool ok = p.perdim ? locate_from_knot(xe, k0, hh, eq, nk, kn, pos, npre) : locate_prerange(xe, k0, hh, eq, nk, kn, pos, npre);
         if ((__ballot_sync(0xffffffffu, !ok) & axmask) != 0u) {
           err = 2;
           break;
@@ -304,9 +307,25 @@ static int nd_eval_common(cib200_itpnd *h, NdCoords c, long long nq, void *out, 
 
 extern "C" {
 
+static int32_t itpnd_create_impl(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
+                                 const double *const *knots, const double *h, const int32_t *kernel, const int32_t *deriv,
+                                 int32_t extrap, int32_t perdim, const double *const *tables, const int32_t *n_pre,
+                                 cib200_itpnd **handle);
 int32_t cib200_itpnd_create(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
                             const double *const *knots, const double *h, const int32_t *kernel, const int32_t *deriv,
                             int32_t extrap, int32_t perdim, cib200_itpnd **handle) {
+  return itpnd_create_impl(ndim, dtype, coef_shape, coefs, knots, h, kernel, deriv, extrap, perdim, nullptr, nullptr, handle);
+}
+int32_t cib200_itpnd_create_tables(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
+                                   const double *const *knots, const double *h, const int32_t *kernel,
+                                   const int32_t *deriv, int32_t extrap, int32_t perdim, const double *const *tables,
+                                   const int32_t *n_pre, cib200_itpnd **handle) {
+  return itpnd_create_impl(ndim, dtype, coef_shape, coefs, knots, h, kernel, deriv, extrap, perdim, tables, n_pre, handle);
+}
+static int32_t itpnd_create_impl(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
+                                 const double *const *knots, const double *h, const int32_t *kernel, const int32_t *deriv,
+                                 int32_t extrap, int32_t perdim, const double *const *tables, const int32_t *n_pre,
+                                 cib200_itpnd **handle) {
   if (!coef_shape || !coefs || !knots || !h || !kernel || !deriv || !handle) {
     set_error("cib200_itpnd_create: null argument");
     return CIB200_EINVAL;
@@ -381,9 +400,20 @@ int32_t cib200_itpnd_create(int32_t ndim, int32_t dtype, const int64_t *coef_sha
   for (int d = 0; d < ndim && e == cudaSuccess; ++d) {
     e = cudaMalloc((void **)&hd->d_knots[d], sizeof(double) * (size_t)coef_shape[d]);
     if (e == cudaSuccess) e = cudaMemcpy(hd->d_knots[d], knots[d], sizeof(double) * (size_t)coef_shape[d], cudaMemcpyHostToDevice);
-    const size_t tb = sizeof(double) * CIB_TAB_ROWS * 2 * (size_t)p.eqs[d];
+    // generated table of the axis (Julia memory order n_pre x 2 eqs, column-major = itp.kernel_pre[d]) or the shipped one
+    const bool gen = tables && n_pre && tables[d] && n_pre[d] >= 2;
+    p.npre[d] = gen ? n_pre[d] : CIB_TAB_ROWS;
+    const size_t nel = (size_t)p.npre[d] * 2 * (size_t)p.eqs[d], tb = sizeof(double) * nel;
     if (e == cudaSuccess) e = cudaMalloc((void **)&hd->d_tabs[d], tb);
-    if (e == cudaSuccess) e = cudaMemcpy(hd->d_tabs[d], host_table(kernel[d], deriv[d]), tb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && gen) {
+      std::vector<double> rm(nel);
+      const int w = 2 * p.eqs[d];
+      for (int r = 0; r < p.npre[d]; ++r)
+        for (int cc = 0; cc < w; ++cc) rm[(size_t)r * w + cc] = tables[d][(size_t)cc * p.npre[d] + r];
+      e = cudaMemcpy(hd->d_tabs[d], rm.data(), tb, cudaMemcpyHostToDevice);
+    } else if (e == cudaSuccess) {
+      e = cudaMemcpy(hd->d_tabs[d], host_table(kernel[d], deriv[d]), tb, cudaMemcpyHostToDevice);
+    }
     p.knots[d] = hd->d_knots[d];
     p.tab[d] = hd->d_tabs[d];
   }

@@ -53,6 +53,8 @@ struct ItpParams {
   int subgrid[3];          // cib200_subgrid: 0 cubic, 1 quintic (1-D / 2-D only), 2 linear
   int prerange_pos;        // 1: eager_2d.jl (linear, linear) position arithmetic (row / t from the stored pre_range)
   int n_tab_slots;
+  int npre[3];             // rows of axis d's K table: 101 (shipped), or the generated length of a :linear axis
+  int tab_slot_rows[9];    // rows of each distinct table (tables with more than 101 rows stay in global memory)
   int tab_slot_eqs[9];     // eqs of each distinct table
   const double *tab_slot_ptr[9];
   double h[3];

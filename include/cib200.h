@@ -123,6 +123,14 @@ int32_t cib200_extend_knots(const double *knots, int64_t n, int32_t n_extra, dou
 /* uploads coefficient grid, knots and tables once (replaces nothing: called by the glue right after
  * _build_fast_uniform_convolution, fast_convolution_interpolation_constructor.jl:99-174). */
 int32_t cib200_itp_create(const cib200_itp_desc *desc, cib200_itp **handle);
+/* The same for an interpolant with :linear-subgrid axes as the reference builds them: for such an axis the constructor
+ * raises the table length to max(precompute, 10_000) rows (fast_convolution_interpolation_constructor.jl:117-118) and
+ * generates K^(deriv) from exact rationals (precompute_kernel_and_range.jl:40-157).  tables[d]: itp.kernel_pre[d] of a
+ * :linear axis (n_pre[d] x 2 eqs doubles in Julia memory order, i.e. column-major; host memory, copied), NULL for the
+ * other axes and for :linear axes that should read the 101-row shipped table.  Large tables stay in global memory and
+ * the tile-binned strategies are not used for such interpolants. */
+int32_t cib200_itp_create_tables(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                                 cib200_itp **handle);
 int32_t cib200_itp_destroy(cib200_itp *handle);
 /* copies the handle's ghost-padded grid to host memory (fills itp.coefs when the grid was built on the device) */
 int32_t cib200_itp_get_coefs(cib200_itp *handle, void *coefs_out);
@@ -163,6 +171,11 @@ typedef struct cib200_itpnd cib200_itpnd; /* opaque */
 int32_t cib200_itpnd_create(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
                             const double *const *knots, const double *h, const int32_t *kernel,
                             const int32_t *deriv, int32_t extrap, int32_t perdim, cib200_itpnd **handle);
+/* with the generated tables of the (all :linear) axes, as cib200_itp_create_tables; perdim = 0 reads tables[0] on every axis */
+int32_t cib200_itpnd_create_tables(int32_t ndim, int32_t dtype, const int64_t *coef_shape, const void *coefs,
+                                   const double *const *knots, const double *h, const int32_t *kernel,
+                                   const int32_t *deriv, int32_t extrap, int32_t perdim, const double *const *tables,
+                                   const int32_t *n_pre, cib200_itpnd **handle);
 int32_t cib200_itpnd_destroy(cib200_itpnd *handle);
 /* same contracts as cib200_itp_eval / cib200_itp_eval_grid */
 int32_t cib200_itpnd_eval(cib200_itpnd *handle, int64_t nq, const void *const *x, void *out,

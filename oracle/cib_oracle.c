@@ -347,18 +347,18 @@ typedef struct {
 
 /* eager_3d.jl:115-137 (same lines in eager_1d.jl:60-71, eager_2d.jl:138-156, perdim_2d.jl:17-49).
  * returns 0 ok, 1 if floor(Int, .) would throw InexactError (NaN / Inf) */
-static inline int locate(double x, const double *knots, int64_t nk, double h, int eqs, axis_pos *p) {
+static inline int locate(double x, const double *knots, int64_t nk, double h, int eqs, int n_pre, axis_pos *p) {
   double i_float = (x - knots[0]) / h + 1.0;
   if (!(fabs(i_float) < 9.0e18)) return 1;
   int64_t i = (int64_t)floor(i_float);
   if (i < eqs) i = eqs;
   if (i > nk - eqs) i = nk - eqs;
   double x_diff_right = 1.0 - (x - knots[i - 1]) / h;
-  double cidx = x_diff_right * (double)(N_PRE - 1) + 1.0;
+  double cidx = x_diff_right * (double)(n_pre - 1) + 1.0;
   if (!(fabs(cidx) < 9.0e18)) return 1;
   int64_t idx = (int64_t)floor(cidx);
   if (idx < 1) idx = 1;
-  if (idx > N_PRE - 1) idx = N_PRE - 1;
+  if (idx > n_pre - 1) idx = n_pre - 1;
   p->i = i;
   p->idx = idx;
   p->t = cidx - (double)idx;
@@ -368,7 +368,7 @@ static inline int locate(double x, const double *knots, int64_t nk, double h, in
 /* the position variant of eager_2d.jl:93-107 ((linear, linear) on the single-kernel path; eager_nd.jl:97-115 uses the
  * same): table row from floor(diff_right * (n_pre - 1)) + 1 and t from the stored pre_range values,
  * pre_range[r] = Float64((r-1)//(n_pre-1)) (pre_range.jl) */
-static inline int locate_prerange(double x, const double *knots, int64_t nk, double h, int eqs, axis_pos *p) {
+static inline int locate_prerange(double x, const double *knots, int64_t nk, double h, int eqs, int n_pre, axis_pos *p) {
   double i_float = (x - knots[0]) / h + 1.0;
   if (!(fabs(i_float) < 9.0e18)) return 1;
   int64_t i = (int64_t)floor(i_float);
@@ -376,12 +376,12 @@ static inline int locate_prerange(double x, const double *knots, int64_t nk, dou
   if (i > nk - eqs) i = nk - eqs;
   double diff_left = (x - knots[i - 1]) / h;
   double diff_right = 1.0 - diff_left;
-  double f = diff_right * (double)(N_PRE - 1);
+  double f = diff_right * (double)(n_pre - 1);
   if (!(fabs(f) < 9.0e18)) return 1;
   int64_t idx = (int64_t)floor(f) + 1;
   if (idx < 1) idx = 1;
-  if (idx > N_PRE - 1) idx = N_PRE - 1;
-  double r0 = (double)(idx - 1) / (double)(N_PRE - 1), r1 = (double)idx / (double)(N_PRE - 1);
+  if (idx > n_pre - 1) idx = n_pre - 1;
+  double r0 = (double)(idx - 1) / (double)(n_pre - 1), r1 = (double)idx / (double)(n_pre - 1);
   p->i = i;
   p->idx = idx;
   p->t = (diff_right - r0) / (r1 - r0);
@@ -393,6 +393,7 @@ typedef struct {
   const double *kd[3];
   const double *ke[3]; /* K^(d+2): quintic subgrid only */
   int eqs[3];
+  int n_pre[3];        /* rows of kp[d]: 101, or the generated length of a :linear axis */
 } itp_tabs;
 
 #define TAB(T, row1, col1, eqs) ((T)[((row1)-1) * 2 * (eqs) + ((col1)-1)])
@@ -404,8 +405,8 @@ static int itp_core(const orc_itp *it, const itp_tabs *tb, const double *x, doub
   axis_pos p[3];
   const int prerange = it->ndim == 2 && !it->perdim && it->subgrid[0] == ORC_SG_LINEAR && it->subgrid[1] == ORC_SG_LINEAR;
   for (int d = 0; d < it->ndim; ++d)
-    if (prerange ? locate_prerange(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d])
-                 : locate(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], &p[d]))
+    if (prerange ? locate_prerange(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], tb->n_pre[d], &p[d])
+                 : locate(x[d], it->knots[d], it->cshape[d], it->h[d], tb->eqs[d], tb->n_pre[d], &p[d]))
       return ORC_ENAN;
 
   if (it->ndim == 1 && it->subgrid[0] == ORC_SG_LINEAR) { /* eager_1d.jl:73-90 */
@@ -694,6 +695,11 @@ int orc_itp_eval(const orc_itp *it, int64_t nq, const double *const *x, double *
   for (int d = 0; d < it->ndim; ++d) {
     tb.eqs[d] = orc_eqs(it->kernel[d]);
     tb.kp[d] = orc_table(it->kernel[d], it->deriv[d]);
+    tb.n_pre[d] = N_PRE;
+    if (it->subgrid[d] == ORC_SG_LINEAR && it->tab[d] && it->n_pre[d] >= 2) { /* generated table of a :linear axis */
+      tb.kp[d] = it->tab[d];
+      tb.n_pre[d] = it->n_pre[d];
+    }
     tb.kd[d] = orc_table(it->kernel[d], it->deriv[d] + 1);
     tb.ke[d] = it->subgrid[d] == ORC_SG_QUINTIC ? orc_table(it->kernel[d], it->deriv[d] + 2) : NULL;
     if (tb.eqs[d] < 0 || !tb.kp[d] || (!tb.kd[d] && it->subgrid[d] != ORC_SG_LINEAR)) return ORC_EARG;
@@ -724,6 +730,7 @@ int orc_itp_eval(const orc_itp *it, int64_t nq, const double *const *x, double *
 typedef struct {
   const double *kp[ORC_MAXND];
   int eqs[ORC_MAXND];
+  int n_pre[ORC_MAXND];
 } nd_tabs;
 
 /* the un-wrapped N-D functor: eager_nd.jl:97-140 (HigherOrderKernel: pre_range positions, itp.eqs[1] and
@@ -733,8 +740,10 @@ static int itp_core_nd(const orc_itp_nd *it, const nd_tabs *tb, const double *x,
   axis_pos p[ORC_MAXND];
   for (int d = 0; d < N; ++d) {
     const int eqs = it->perdim ? tb->eqs[d] : tb->eqs[0];
-    int bad = it->perdim ? locate(x[d], it->knots[d], it->cshape[d], it->h[d], eqs, &p[d])
-                         : locate_prerange(x[d], it->knots[d], it->cshape[d], it->h[d], eqs, &p[d]);
+    /* eager_nd.jl reads itp.pre_range[1] / itp.kernel_pre[1] on every axis */
+    const int npre = it->perdim ? tb->n_pre[d] : tb->n_pre[0];
+    int bad = it->perdim ? locate(x[d], it->knots[d], it->cshape[d], it->h[d], eqs, npre, &p[d])
+                         : locate_prerange(x[d], it->knots[d], it->cshape[d], it->h[d], eqs, npre, &p[d]);
     if (bad) return ORC_ENAN;
   }
   int64_t stride[ORC_MAXND];
@@ -826,6 +835,11 @@ int orc_itp_eval_nd(const orc_itp_nd *it, int64_t nq, const double *const *x, do
   for (int d = 0; d < it->ndim; ++d) {
     tb.eqs[d] = orc_eqs(it->kernel[d]);
     tb.kp[d] = orc_table(it->kernel[d], it->deriv[d]);
+    tb.n_pre[d] = N_PRE;
+    if (it->tab[d] && it->n_pre[d] >= 2) {
+      tb.kp[d] = it->tab[d];
+      tb.n_pre[d] = it->n_pre[d];
+    }
     if (tb.eqs[d] < 0 || !tb.kp[d]) return ORC_EARG;
     if (!it->perdim && (it->kernel[d] != it->kernel[0] || it->deriv[d] != it->deriv[0])) return ORC_EARG;
   }

@@ -49,13 +49,14 @@ class _Itp(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("cshape", C.c_int64 * 3), ("coefs", C.c_void_p),
                 ("knots", C.c_void_p * 3), ("h", C.c_double * 3), ("kernel", C.c_int32 * 3),
                 ("deriv", C.c_int32 * 3), ("extrap", C.c_int32), ("perdim", C.c_int32),
-                ("subgrid", C.c_int32 * 3)]
+                ("subgrid", C.c_int32 * 3), ("tab", C.c_void_p * 3), ("n_pre", C.c_int32 * 3)]
 
 
 class _ItpNd(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("cshape", C.c_int64 * 8), ("coefs", C.c_void_p),
                 ("knots", C.c_void_p * 8), ("h", C.c_double * 8), ("kernel", C.c_int32 * 8),
-                ("deriv", C.c_int32 * 8), ("extrap", C.c_int32), ("perdim", C.c_int32)]
+                ("deriv", C.c_int32 * 8), ("extrap", C.c_int32), ("perdim", C.c_int32),
+                ("tab", C.c_void_p * 8), ("n_pre", C.c_int32 * 8)]
 
 
 def lib():
@@ -106,6 +107,47 @@ def table_i1(kernel):
     p = lib().orc_table_i1(KERNEL_IDS[kernel])
     e = KERNEL_EQS[kernel]
     return np.ctypeslib.as_array(p, shape=(101, 2 * e)).copy()
+
+
+LINEAR_ROWS = 10_000  # precompute_actual of a :linear axis: max(precompute, 10_000), constructor.jl:117-118
+_GENERATED = {}
+
+
+def generated_table(kernel, d, n_pre=LINEAR_ROWS):
+    """precompute_kernel(F, degree, derivative, eqs, precompute, pre_range_exact), precompute_kernel_and_range.jl:150-157:
+    kernel_pre[r, c] = F(K^(d)((r-1)//(n_pre-1) - eqs + c - 1)) in exact rational arithmetic.  Every entry is the ratio of
+    two integers (sum of a_k/b_k * (m/Q)^k over the piece's coefficients, brought to the denominator lcm(b) * Q^n),
+    rounded once by Python's correctly rounded int / int.  Returns an (n_pre, 2 eqs) C-ordered array (cached)."""
+    key = (kernel, d, n_pre)
+    if key in _GENERATED:
+        return _GENERATED[key]
+    import json
+    from fractions import Fraction
+    info = json.load(open(os.path.join(_HERE, "kernel_polys.json")))[kernel]
+    eqs, Q = info["eqs"], n_pre - 1
+    pieces = []
+    for piece in info["pieces"]:
+        c = [Fraction(x) for x in piece]
+        dc = [c[k] * math.factorial(k) / math.factorial(k - d) for k in range(d, len(c))] or [Fraction(0)]
+        lcm = 1
+        for x in dc:
+            lcm = lcm * x.denominator // math.gcd(lcm, x.denominator)
+        pieces.append(([int(x * lcm) for x in dc], lcm))
+    t = np.zeros((n_pre, 2 * eqs))
+    for col in range(2 * eqs):
+        for r in range(n_pre):
+            m = r + (col - eqs) * Q  # s = m / Q
+            M = abs(m)
+            if M >= eqs * Q:
+                continue
+            A, lcm = pieces[M // Q]
+            n = len(A) - 1
+            num = sum(a * M ** k * Q ** (n - k) for k, a in enumerate(A))
+            if d % 2 == 1 and m < 0:
+                num = -num
+            t[r, col] = num / (lcm * Q ** n)
+    _GENERATED[key] = t
+    return t
 
 
 def ghost_matrix(which, kernel, rows):
@@ -223,7 +265,7 @@ class Interpolant:
     fast_convolution_interpolation_constructor.jl:99-174)."""
 
     def __init__(self, knots, values, kernel="b5", extrap="throw", bc="detect", derivative=0,
-                 subgrid="cubic"):
+                 subgrid="cubic", linear_rows=LINEAR_ROWS):
         values = np.asarray(values, dtype=np.float64)
         nd = values.ndim
         if nd < 1 or nd > 8:
@@ -268,6 +310,15 @@ class Interpolant:
             it.deriv[d] = self.derivs[d]
             if nd <= 3:
                 it.subgrid[d] = SUBGRID_IDS[self.subgrid[d]]
+        # :linear axes read the generated >= 10 000-row table (constructor.jl:117-118); linear_rows=101 keeps the shipped
+        # one (what the reference would compute from a 101-row table; only used to cross-check the two)
+        self._tabs = []
+        for d in range(nd):
+            if self.subgrid[d] == "linear" and linear_rows != 101:
+                t = generated_table(self.kernels[d], self.derivs[d], linear_rows)
+                self._tabs.append(t)
+                it.tab[d] = t.ctypes.data
+                it.n_pre[d] = linear_rows
         it.coefs = self.coefs.ctypes.data
         it.extrap = EXTRAP_IDS[extrap]
         it.perdim = int(self.perdim)

@@ -174,11 +174,23 @@ def test_linear_subgrid_and_top_derivatives(ci, oracle, kernel):
     assert g.itp.subgrid == ("linear",) * 3 and g.itp.perdim
     _compare(ci, oracle, k3, v3, tuple(q3), kernel=kernel, subgrid="linear", extrap="line")
     _compare(ci, oracle, k3, v3, tuple(q3), kernel=kernel, subgrid=("cubic", "quintic", "cubic"), extrap="flat")
-    if kernel == "b5":  # the binned strategies on an all-linear 3-D interpolant
+    # the reference's :linear axes read generated 10 000-row tables (constructor.jl:117-118): both sides did above; on the
+    # 101-row shipped tables the same interpolant is ~1e-4 away (and both sides agree on that variant too)
+    g101 = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", extrap="line", linear_rows=101)
+    o101 = oracle.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", extrap="line", linear_rows=101)
+    r101 = o101.eval(*q3)
+    assert rel_err(g101.eval(*q3), r101, _scale(o101) * _line_amplification(o101, tuple(q3))).max() <= TOL64
+    r10k = oracle.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", extrap="line").eval(*q3)
+    inside = ((q3 >= 0) & (q3 <= 1)).all(axis=0)
+    assert 1e-9 < np.abs(r101 - r10k)[inside].max() / np.abs(r10k)[inside].max() < 1e-2
+    assert g101.itp.linear_rows == 101 and g.itp.linear_rows == 10_000
+    if kernel == "b5":  # the binned strategies on an all-linear 3-D interpolant (101-row tables only: records pack the row)
         qb = rng.uniform(0, 1, (3, 300_007))
-        gg = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="gather")
-        gb = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned")
+        gg = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="gather", linear_rows=101)
+        gb = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned", linear_rows=101)
         assert rel_err(gb.eval(*qb), gg.eval(*qb), np.abs(v3).max()).max() <= 1e-14
+        with pytest.raises(ci.UnsupportedModeError):
+            ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned")
 
 
 @pytest.mark.parametrize("kernel", ["b5", "b7", "b13"])

@@ -237,6 +237,8 @@ def main():
         open(p, "w").write(text)
     os.makedirs(os.path.join(ROOT, "oracle"), exist_ok=True)
     json.dump(polys_json, open(os.path.join(ROOT, "oracle/kernel_polys.json"), "w"), indent=1)
+    # the product's own copy: the host mirror regenerates the >= 10 000-row tables of :linear axes from it (tables.py)
+    json.dump(polys_json, open(os.path.join(ROOT, "convolutioninterpolations.jl_b200/kernel_polys.json"), "w"), indent=1)
     os.makedirs(os.path.join(ROOT, "tests/golden"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "tests/golden/shipped_tables.npz"), **golden)
     json.dump(read_ghost_matrices(), open(os.path.join(ROOT, "tests/golden/ghost_matrices.json"), "w"), indent=1)
