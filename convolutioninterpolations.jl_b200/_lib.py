@@ -27,7 +27,7 @@ SYMBOLS = [
     "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
     "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itp_eval_multi", "cib200_device_count",
     "cib200_set_device", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
-    "cib200_itp_create_tables", "cib200_itpnd_create_tables",
+    "cib200_itp_create_tables", "cib200_itpnd_create_tables", "cib200_resample_tables",
     "cib200_itg_create", "cib200_itg_destroy", "cib200_itg_eval", "cib200_itg_eval_grid", "cib200_itg_get",
 ]
 
@@ -105,6 +105,8 @@ def lib():
     L.cib200_itp_scratch_bytes.argtypes = [vp, i64]
     L.cib200_resample.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, i32, vp]
     L.cib200_resample_sg.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, i32, vp]
+    L.cib200_resample_tables.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp,
+                                         C.POINTER(vp), C.POINTER(i32), i32, vp]
     L.cib200_smooth.argtypes = [i32, i32, vp, vp, vp, vp, dbl, i32, vp]
     L.cib200_smooth_halfwidth.restype = i32
     L.cib200_smooth_halfwidth.argtypes = [dbl]

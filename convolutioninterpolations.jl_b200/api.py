@@ -602,7 +602,7 @@ _UNSET = object()
 
 
 def convolution_resample(knots_in, knots_out, values, precompute=_UNSET, kernel=_UNSET, derivative=_UNSET,
-                         bc=_UNSET, subgrid=_UNSET, dtype=None):
+                         bc=_UNSET, subgrid=_UNSET, dtype=None, linear_rows=None):
     """convolution_resample(knots_in, knots_out, values; precompute, kernel, derivative, bc, subgrid)
     convolution_resample.jl:65-238 (front-ends) -> :240-386 (internal, replaced by cib200_resample).
 
@@ -636,8 +636,18 @@ def convolution_resample(knots_in, knots_out, values, precompute=_UNSET, kernel=
     if kwless and nd > 10:
         raise TypeError("no method matching convolution_resample for N > 10 without keyword arguments")
     _require_accelerated(kernels, derivs, sgs_valid, nd, "convolution_resample")
-    if not kwless:
-        _warn_linear_rows(sgs_valid, kernels, "convolution_resample")  # :228-229 precompute_actual >= 10 000
+    # kw method: precompute_actual = max(precompute, 10_000) rows for :linear axes (:228-229), generated from exact
+    # rationals; the kw-less wrappers pass 101 straight through.  linear_rows=101 keeps the shipped tables (not the
+    # reference's result, ~1e-6 .. 1e-4 relative away)
+    from . import tables as _tables
+    rows = _tables.LINEAR_ROWS if linear_rows is None else int(linear_rows)
+    gen = [None] * nd
+    if not kwless and rows != 101:
+        for d in range(nd):
+            if sgs_valid[d] == "linear" and kernels[d] not in ("a0", "a1"):
+                gen[d] = np.asfortranarray(_tables.generated_table(kernels[d], int(derivs[d]), rows))
+    elif not kwless:
+        _warn_linear_rows(sgs_valid, kernels, "convolution_resample")
     did, memkind, in_ptr, make_out, stream, keep = _sweep_io(values, dtype)
     ndt = _np_dtype(did)
     # T.(knots): :183-188
@@ -657,8 +667,10 @@ def convolution_resample(knots_in, knots_out, values, precompute=_UNSET, kernel=
     bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
     br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
     sg = (C.c_int32 * nd)(*[SUBGRID_IDS[x] for x in sgs_valid])
-    check(lib().cib200_resample_sg(nd, did, n_in, n_out, in_ptr, out_ptr, kinp, koutp, kid, dv, bl, br, sg, memkind,
-                                   stream))
+    tp = (C.c_void_p * nd)(*[None if t is None else t.ctypes.data for t in gen])
+    npre = (C.c_int32 * nd)(*[0 if t is None else t.shape[0] for t in gen])
+    check(lib().cib200_resample_tables(nd, did, n_in, n_out, in_ptr, out_ptr, kinp, koutp, kid, dv, bl, br, sg, tp, npre,
+                                       memkind, stream))
     del keep
     return view()
 

@@ -986,6 +986,15 @@ int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, con
                            void *out, const double *const *knots_in, const double *const *knots_out,
                            const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
                            const int32_t *bc_right, const int32_t *subgrid, int32_t memkind, void *stream) {
+  return cib200_resample_tables(ndim, dtype, n_in, n_out, values, out, knots_in, knots_out, kernel, deriv, bc_left,
+                                bc_right, subgrid, nullptr, nullptr, memkind, stream);
+}
+
+int32_t cib200_resample_tables(int32_t ndim, int32_t dtype, const int64_t *n_in, const int64_t *n_out, const void *values,
+                               void *out, const double *const *knots_in, const double *const *knots_out,
+                               const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                               const int32_t *bc_right, const int32_t *subgrid, const double *const *tables,
+                               const int32_t *n_pre, int32_t memkind, void *stream) {
   if (ndim < 1 || ndim > CIB200_MAX_SWEEP_DIM || !n_in || !n_out || !values || !out || !knots_in || !knots_out ||
       !kernel || !deriv || !bc_left || !bc_right) {
     set_error("cib200_resample: bad arguments");
@@ -1038,7 +1047,9 @@ int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, con
   bool owned;
   int rc = sweep_io(ndim, dtype, tin, tout, values, out, memkind, st, &d_in, &d_out, &owned);
   if (rc) return rc;
-  rc = sweep_resample(ndim, dtype, nin, nout, d_in, d_out, knots_in, knots_out, k, dv, bl, br, sgv, st);
+  int rows[CIB200_MAX_SWEEP_DIM];
+  for (int d = 0; d < ndim; ++d) rows[d] = (tables && n_pre && tables[d]) ? n_pre[d] : 0;
+  rc = sweep_resample(ndim, dtype, nin, nout, d_in, d_out, knots_in, knots_out, k, dv, bl, br, sgv, tables, rows, st);
   if (owned) {
     if (!rc) {
       cudaError_t e = cudaMemcpyAsync(out, d_out, esize(dtype) * (size_t)tout, cudaMemcpyDeviceToHost, st);

@@ -65,7 +65,7 @@ __device__ __forceinline__ bool locate_axis(const ItpParams &p, int d, double x,
 
 // resample variant: the cell's left knot is COMPUTED (convolution_resample.jl:322-326)
 __device__ __forceinline__ void locate_computed(double x, double x_expanded_1, double h, int eqs,
-                                                long long n_coef, AxisPos &p) {
+                                                long long n_coef, AxisPos &p, int npre = CIB_N_PRE) {
   double i_float = __dadd_rn(__ddiv_rn(__dsub_rn(x, x_expanded_1), h), 1.0);
   bool ok = fabs(i_float) < 9.0e18;
   long long i = ok ? (long long)floor(i_float) : (long long)eqs;
@@ -74,10 +74,10 @@ __device__ __forceinline__ void locate_computed(double x, double x_expanded_1, d
   double knot_i = __dadd_rn(x_expanded_1, __dmul_rn((double)(i - 1), h));
   double x_diff_left = __ddiv_rn(__dsub_rn(x, knot_i), h);
   double x_diff_right = __dsub_rn(1.0, x_diff_left);
-  double cidx = __dadd_rn(__dmul_rn(x_diff_right, (double)(CIB_N_PRE - 1)), 1.0);
+  double cidx = __dadd_rn(__dmul_rn(x_diff_right, (double)(npre - 1)), 1.0);
   int idx = (fabs(cidx) < 9.0e18) ? (int)floor(cidx) : 1;
   idx = idx < 1 ? 1 : idx;
-  idx = idx > CIB_N_PRE - 1 ? CIB_N_PRE - 1 : idx;
+  idx = idx > npre - 1 ? npre - 1 : idx;
   p.base = (int)(i - eqs);
   p.row = idx - 1;
   p.t = __dsub_rn(cidx, (double)idx);

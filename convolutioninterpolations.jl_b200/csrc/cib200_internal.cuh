@@ -131,7 +131,7 @@ void binned_destroy(cib200_itp *h);
 int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *n_out, const void *d_in,
                    void *d_out, const double *const *knots_in, const double *const *knots_out,
                    const int *kernel, const int *deriv, const int *bcl, const int *bcr, const int *subgrid,
-                   cudaStream_t st);
+                   const double *const *gen_tables, const int *gen_rows, cudaStream_t st);
 int sweep_build_coefs(int ndim, int dtype, const long long *n, const void *d_values, const double *h, const int *kernel,
                       const int *bcl, const int *bcr, void *d_coefs, cudaStream_t st);
 int sweep_smooth(int ndim, int dtype, const long long *n, const void *d_in, void *d_out, const double *h,

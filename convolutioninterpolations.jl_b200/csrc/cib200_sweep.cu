@@ -59,7 +59,8 @@ struct SweepParams {
 __global__ void resample_weights_kernel(const double *__restrict__ knots_out, long long n_out, double x_expanded_1,
                                         double h, int eqs, long long n_coef, const double *__restrict__ tk,
                                         const double *__restrict__ td, const double *__restrict__ te, int linear,
-                                        double *__restrict__ W, double *__restrict__ Wk, int *__restrict__ base) {
+                                        int npre, double *__restrict__ W, double *__restrict__ Wk,
+                                        int *__restrict__ base) {
   // one thread per (output knot, tap): the position arithmetic is recomputed by the 2 eqs threads of a knot (a
   // thread per knot made this launch a 7 us dependent chain in front of every pass)
   const int w = 2 * eqs;
@@ -68,7 +69,7 @@ __global__ void resample_weights_kernel(const double *__restrict__ knots_out, lo
   const long long k = idx / w;
   const int l = (int)(idx - k * w);
   AxisPos p;
-  locate_computed(knots_out[k], x_expanded_1, h, eqs, n_coef, p);
+  locate_computed(knots_out[k], x_expanded_1, h, eqs, n_coef, p, npre);
   if (l == 0) base[k] = p.base;
   // te != nullptr: quintic subgrid (:333-349); linear (:363-373): td aliases tk, its terms carry zero factors
   const Hermite hb = te ? hermite_basis_quintic(p.t) : (linear ? linear_basis(p.t) : hermite_basis(p.t));
@@ -1445,7 +1446,8 @@ struct TempBufs {
 template <typename T>
 static int resample_t(int ndim, const long long *n_in, const long long *n_out, const T *d_in, T *d_out,
                       const double *const *knots_in, const double *const *knots_out, const int *kernel,
-                      const int *deriv, const int *bcl, const int *bcr, const int *subgrid, cudaStream_t st) {
+                      const int *deriv, const int *bcl, const int *bcr, const int *subgrid,
+                      const double *const *gen_tables, const int *gen_rows, cudaStream_t st) {
   TempBufs tmp;
   tmp.st = st;
   long long shape[CIB200_MAX_SWEEP_DIM];
@@ -1464,8 +1466,23 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     double *d_ko, *d_W, *d_Wk;
     int *d_base;
     const int linear = subgrid[d] == CIB200_SG_LINEAR;
-    if ((rc = device_table(kernel[d], deriv[d], &d_tk))) return rc;
-    if ((rc = device_table(kernel[d], deriv[d] + (linear ? 0 : 1), &d_td))) return rc;
+    int npre = CIB_N_PRE;
+    if (linear && gen_tables && gen_rows && gen_tables[d] && gen_rows[d] >= 2) {
+      // generated table of a :linear axis (convolution_resample.jl:228-229: max(precompute, 10_000) rows), caller's
+      // column-major n_pre x 2 eqs image transposed to row-major; pageable source: the copy is staged before returning
+      npre = gen_rows[d];
+      std::vector<double> rm((size_t)npre * taps);
+      for (int r = 0; r < npre; ++r)
+        for (int cc = 0; cc < taps; ++cc) rm[(size_t)r * taps + cc] = gen_tables[d][(size_t)cc * npre + r];
+      double *d_gen;
+      if ((rc = tmp.alloc((void **)&d_gen, sizeof(double) * rm.size()))) return rc;
+      CIB_CUDA(cudaMemcpyAsync(d_gen, rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice, st));
+      CIB_CUDA(cudaStreamSynchronize(st));
+      d_tk = d_td = d_gen;
+    } else {
+      if ((rc = device_table(kernel[d], deriv[d], &d_tk))) return rc;
+      if ((rc = device_table(kernel[d], deriv[d] + (linear ? 0 : 1), &d_td))) return rc;
+    }
     if (subgrid[d] == CIB200_SG_QUINTIC && (rc = device_table(kernel[d], deriv[d] + 2, &d_te))) return rc;
     if ((rc = tmp.alloc((void **)&d_ko, sizeof(double) * (size_t)nout))) return rc;
     if ((rc = tmp.alloc((void **)&d_W, sizeof(double) * (size_t)nout * taps))) return rc;
@@ -1473,7 +1490,7 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
     if ((rc = tmp.alloc((void **)&d_base, sizeof(int) * (size_t)nout))) return rc;
     CIB_CUDA(cudaMemcpyAsync(d_ko, knots_out[d], sizeof(double) * (size_t)nout, cudaMemcpyHostToDevice, st));
     resample_weights_kernel<<<(unsigned)((nout * taps + 127) / 128), 128, 0, st>>>(d_ko, nout, x_expanded_1, h, eqs, n_coef,
-                                                                           d_tk, d_td, d_te, linear, d_W, d_Wk, d_base);
+                                                                           d_tk, d_td, d_te, linear, npre, d_W, d_Wk, d_base);
     CIB_LAUNCHED();
     CIB_CUDA(cudaGetLastError());
 
@@ -1607,10 +1624,11 @@ int sweep_build_coefs(int ndim, int dtype, const long long *n, const void *d_val
 
 int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *n_out, const void *d_in, void *d_out,
                    const double *const *knots_in, const double *const *knots_out, const int *kernel, const int *deriv,
-                   const int *bcl, const int *bcr, const int *subgrid, cudaStream_t st) {
+                   const int *bcl, const int *bcr, const int *subgrid, const double *const *gen_tables,
+                   const int *gen_rows, cudaStream_t st) {
   if (dtype == CIB200_F32)
-    return resample_t<float>(ndim, n_in, n_out, (const float *)d_in, (float *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, subgrid, st);
-  return resample_t<double>(ndim, n_in, n_out, (const double *)d_in, (double *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, subgrid, st);
+    return resample_t<float>(ndim, n_in, n_out, (const float *)d_in, (float *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, subgrid, gen_tables, gen_rows, st);
+  return resample_t<double>(ndim, n_in, n_out, (const double *)d_in, (double *)d_out, knots_in, knots_out, kernel, deriv, bcl, bcr, subgrid, gen_tables, gen_rows, st);
 }
 
 // convolution_kernels/convolution_kernel_gaussian.jl:23-31

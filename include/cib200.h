@@ -233,6 +233,15 @@ int32_t cib200_resample_sg(int32_t ndim, int32_t dtype, const int64_t *n_in, con
                            const int32_t *bc_left, const int32_t *bc_right, const int32_t *subgrid,
                            int32_t memkind, void *stream);
 
+/* the same with the generated tables of :linear axes: the kw method raises their length to max(precompute, 10_000)
+ * rows (convolution_resample.jl:228-229).  tables[d]: kernel_pre of a :linear axis (n_pre[d] x 2 eqs doubles, Julia
+ * memory order, host), NULL for the other axes; tables == NULL: every axis on the 101-row shipped tables */
+int32_t cib200_resample_tables(int32_t ndim, int32_t dtype, const int64_t *n_in, const int64_t *n_out,
+                               const void *values, void *out, const double *const *knots_in,
+                               const double *const *knots_out, const int32_t *kernel, const int32_t *deriv,
+                               const int32_t *bc_left, const int32_t *bc_right, const int32_t *subgrid,
+                               const double *const *tables, const int32_t *n_pre, int32_t memkind, void *stream);
+
 /* replaces convolution_smooth (convolution/convolution_gaussian_smoothing.jl:45-126).
  * h[d] = knots[d][2] - knots[d][1]. Fails with CIB200_EINVAL when the half-width E >= n[d] (:50-56). */
 int32_t cib200_smooth(int32_t ndim, int32_t dtype, const int64_t *n, const void *values, void *out,

@@ -863,6 +863,11 @@ int orc_itp_eval_nd(const orc_itp_nd *it, int64_t nq, const double *const *x, do
   return bad_rc;
 }
 
+int orc_resample_tables(int ndim, const int64_t *n_in, const int64_t *n_out, const double *values,
+                        double *out, const double *const *knots_in, const double *const *knots_out,
+                        const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                        const int32_t *bc_right, const int32_t *subgrid, const double *const *tab,
+                        const int32_t *n_pre_axis);
 /* convolution/convolution_resample.jl:240-386, cubic subgrid branch :350-361 */
 int orc_resample(int ndim, const int64_t *n_in, const int64_t *n_out, const double *values,
                  double *out, const double *const *knots_in, const double *const *knots_out,
@@ -876,6 +881,17 @@ int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const d
                     double *out, const double *const *knots_in, const double *const *knots_out,
                     const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
                     const int32_t *bc_right, const int32_t *subgrid) {
+  return orc_resample_tables(ndim, n_in, n_out, values, out, knots_in, knots_out, kernel, deriv, bc_left, bc_right,
+                             subgrid, NULL, NULL);
+}
+
+/* tab[d] / n_pre[d]: the generated table of a :linear axis (precompute_actual = max(precompute, 10_000),
+ * convolution_resample.jl:228-229), row-major; NULL = the 101-row shipped table */
+int orc_resample_tables(int ndim, const int64_t *n_in, const int64_t *n_out, const double *values,
+                        double *out, const double *const *knots_in, const double *const *knots_out,
+                        const int32_t *kernel, const int32_t *deriv, const int32_t *bc_left,
+                        const int32_t *bc_right, const int32_t *subgrid, const double *const *tab,
+                        const int32_t *n_pre_axis) {
   if (ndim < 1 || ndim > ORC_MAXDIM) return ORC_EARG;
   int64_t cur_shape[ORC_MAXDIM];
   int64_t tot = 1;
@@ -890,6 +906,11 @@ int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const d
     const int quintic = subgrid[d] == ORC_SG_QUINTIC;
     const double *kd2_pre = quintic ? orc_table(kernel[d], deriv[d] + 2) : NULL;
     const int linear = subgrid[d] == ORC_SG_LINEAR;
+    int n_pre = N_PRE;
+    if (linear && tab && n_pre_axis && tab[d] && n_pre_axis[d] >= 2) {
+      kernel_pre = tab[d];
+      n_pre = n_pre_axis[d];
+    }
     if (eqs_d < 0 || !kernel_pre || (!kd1_pre && !linear) || (quintic && !kd2_pre)) { free(current); return ORC_EARG; }
     const int64_t nin = cur_shape[d], nout = n_out[d];
     const double h_d = knots_in[d][1] - knots_in[d][0];
@@ -924,10 +945,10 @@ int orc_resample_sg(int ndim, const int64_t *n_in, const int64_t *n_out, const d
             double knot_i = x_expanded_1 + (double)(i - 1) * h_d;
             double x_diff_left = (xq - knot_i) / h_d;
             double x_diff_right = 1.0 - x_diff_left;
-            double continuous_idx = x_diff_right * (double)(N_PRE - 1) + 1.0;
+            double continuous_idx = x_diff_right * (double)(n_pre - 1) + 1.0;
             int64_t idx = (int64_t)floor(continuous_idx);
             if (idx < 1) idx = 1;
-            if (idx > N_PRE - 1) idx = N_PRE - 1;
+            if (idx > n_pre - 1) idx = n_pre - 1;
             double t = continuous_idx - (double)idx;
             double sum_f0 = 0, sum_f1 = 0, sum_d0 = 0, sum_d1 = 0, sum_dd0 = 0, sum_dd1 = 0;
             for (int l = -(eqs_d - 1); l <= eqs_d; ++l) {

@@ -73,6 +73,8 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_resample.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 4
         L.orc_resample_sg.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 5
+        L.orc_resample_tables.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)] * 2 + [C.c_void_p] * 5 + \
+            [C.POINTER(C.c_void_p), C.c_void_p]
         L.orc_smooth.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.orc_smooth_halfwidth.argtypes = [C.c_double]
         L.orc_ghost_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -468,7 +470,7 @@ _UNSET = object()
 
 
 def convolution_resample(knots_in, knots_out, values, kernel=_UNSET, derivative=_UNSET, bc=_UNSET,
-                         subgrid=_UNSET):
+                         subgrid=_UNSET, linear_rows=LINEAR_ROWS):
     """convolution_resample.jl:65-172 (kw-less wrappers: no _build_subgrids) / :174-238 (kw method) + :240-386."""
     kwless = all(a is _UNSET for a in (kernel, derivative, bc, subgrid))
     kernel = "b13" if kernel is _UNSET else kernel
@@ -497,7 +499,13 @@ def convolution_resample(knots_in, knots_out, values, kernel=_UNSET, derivative=
     bl = (C.c_int32 * nd)(*[BC_IDS[b[0]] for b in bcs])
     br = (C.c_int32 * nd)(*[BC_IDS[b[1]] for b in bcs])
     sg = (C.c_int32 * nd)(*[SUBGRID_IDS[x] for x in sgs])
-    rc = lib().orc_resample_sg(nd, n_in, n_out, v.ctypes.data, out.ctypes.data, kinp, koutp, kid, dv, bl, br, sg)
+    # kw method: precompute_actual = max(precompute, 10_000) for :linear axes (:228-229); the kw-less wrappers pass 101
+    tabs = [generated_table(kernels[d], derivs[d], linear_rows) if (sgs[d] == "linear" and not kwless and linear_rows != 101)
+            else None for d in range(nd)]
+    tp = (C.c_void_p * nd)(*[None if t is None else t.ctypes.data for t in tabs])
+    npre = (C.c_int32 * nd)(*[0 if t is None else t.shape[0] for t in tabs])
+    rc = lib().orc_resample_tables(nd, n_in, n_out, v.ctypes.data, out.ctypes.data, kinp, koutp, kid, dv, bl, br, sg,
+                                   tp, npre)
     if rc:
         raise OracleError(f"orc_resample rc={rc}")
     return out
