@@ -163,10 +163,10 @@ def _build_subgrids(kernels, derivs, subgrids):
 
 
 class LinearSubgridTableWarning(UserWarning):
-    """A :linear-subgrid axis is evaluated on the 101-row shipped table; the reference generates >= 10 000 rows for such
-    axes (precompute_actual = max(precompute, 10_000): fast_convolution_interpolation_constructor.jl:117-118,
-    convolution_resample.jl:228-229), so results agree with it only up to the table-resolution term
-    h_pre^2 / 8 * max|K''| ~ 1e-5 relative (DESIGN.md 1, row f)."""
+    """linear_rows=101 was requested: a :linear-subgrid axis is evaluated on the 101-row shipped table, whereas the
+    reference generates >= 10 000 rows for such axes (precompute_actual = max(precompute, 10_000):
+    fast_convolution_interpolation_constructor.jl:117-118, convolution_resample.jl:228-229) - the default here too.  The
+    101-row result is ~1e-4 relative away from the reference's (DESIGN.md 1, row f)."""
 
 
 def _warn_linear_rows(subgrids, kernels, what):

@@ -54,9 +54,9 @@ typedef enum { CIB200_BC_DETECT = 0, CIB200_BC_POLY = 1, CIB200_BC_LINEAR = 2, C
 typedef enum { CIB200_THROW = 0, CIB200_FLAT = 1, CIB200_LINE = 2 } cib200_extrap;
 /* subgrid = how the 101-row tables are interpolated between rows: cubic Hermite (K, K'), quintic Hermite (K, K', K'')
  * - cubic_hermite_interpolation.jl:15-28, quintic_hermite_interpolation.jl:16-37 - or linearly (K only: the path of
- * top derivatives and of every non-all-cubic 3-D interpolant) on the 101-row shipped tables.  NOTE: the reference's
- * constructors generate >= 10 000 rows for :linear axes (fast_convolution_interpolation_constructor.jl:117-118), so a glue
- * must only forward interpolants whose pre_range has 101 entries (julia/CIB200Glue.jl does); see DESIGN.md 1, row f */
+ * top derivatives and of every non-all-cubic 3-D interpolant).  The reference's constructors generate >= 10 000 table rows
+ * for :linear axes (fast_convolution_interpolation_constructor.jl:117-118): pass them through the *_create_tables /
+ * cib200_resample_tables entry points; without them a :linear axis reads the 101-row shipped table (1e-4 relative away) */
 typedef enum { CIB200_SG_CUBIC = 0, CIB200_SG_QUINTIC = 1, CIB200_SG_LINEAR = 2 } cib200_subgrid;
 
 /* evaluation strategies of cib200_itp_eval (3-D only; 1-D/2-D always use the direct kernel) */

@@ -67,8 +67,10 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     end
     itp.derivative_order isa DerivativeOrder || return false
     dv = derivative_tuple(itp)
-    all(d -> length(itp.pre_range[d]) == 101, 1:N) || return false   # precompute = 101: the shipped tables
     sg = effective_subgrids(subgrid_tuple(itp), N)
+    # cubic / quintic axes read the shipped 101-row tables; :linear axes carry generated tables of >= 10 000 rows
+    # (constructor.jl:117-118) which are handed to the library as they are (cib200_itp_create_tables)
+    all(d -> sg[d] === :linear || length(itp.pre_range[d]) == 101, 1:N) || return false
     all(s -> haskey(SUBGRID_ID, s), sg) || return false
     # tables a subgrid needs: K^(d) (:linear), + K^(d+1) (:cubic), + K^(d+2) (:quintic)
     need(d) = dv[d] + (sg[d] === :linear ? 0 : sg[d] === :cubic ? 1 : 2)
@@ -84,6 +86,14 @@ end
 effective_subgrids(sg, N) = (N == 3 && any(!=(:cubic), sg)) ? ntuple(_ -> :linear, 3) : sg
 subgrid_tuple(itp) = typeof(itp.subgrid).parameters[1]               # Val{SG}
 derivative_tuple(itp) = typeof(itp.derivative_order).parameters[1]   # DerivativeOrder{DO} (struct_constructors.jl:182)
+
+# itp.kernel_pre[d] of the :linear axes (n_pre x 2 eqs, column-major: passed as it lies in memory), C_NULL elsewhere
+function linear_tables(itp::FastConvolutionInterpolation{T,N}, sg) where {T,N}
+    tabs64 = [sg[d] === :linear ? Matrix{Float64}(itp.kernel_pre[d]) : Matrix{Float64}(undef, 0, 0) for d in 1:N]
+    tptr = [sg[d] === :linear ? pointer(tabs64[d]) : Ptr{Float64}(0) for d in 1:N]
+    npre = Int32[sg[d] === :linear ? size(tabs64[d], 1) : 0 for d in 1:N]
+    return tabs64, tptr, npre
+end
 
 # ---- handle cache: one upload per interpolant, freed by a finalizer --------------------------------
 mutable struct Handle
@@ -115,11 +125,12 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
                 hh = Float64[itp.h...]
                 kid = Int32[KERNEL_ID[ks[d]] for d in 1:N]
                 dvv = Int32[dv[d] for d in 1:N]
-                GC.@preserve itp knots64 cshape kptr hh kid dvv check(ccall((:cib200_itpnd_create, LIB), Int32,
+                tabs64, tptr, npre = linear_tables(itp, ntuple(_ -> :linear, N))
+                GC.@preserve itp knots64 cshape kptr hh kid dvv tabs64 tptr npre check(ccall((:cib200_itpnd_create_tables, LIB), Int32,
                     (Int32, Int32, Ptr{Int64}, Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32},
-                     Int32, Int32, Ref{Ptr{Cvoid}}),
+                     Int32, Int32, Ptr{Ptr{Float64}}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
                     N, T === Float32 ? 1 : 0, cshape, pointer(itp.coefs), kptr, hh, kid, dvv, extrap_id(etp.et),
-                    Int32(itp.kernel_sym isa HigherOrderMixedKernel), out))
+                    Int32(itp.kernel_sym isa HigherOrderMixedKernel), tptr, npre, out))
                 h = Handle(out[])
                 finalizer(x -> ccall((:cib200_itpnd_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
                 return h
@@ -146,13 +157,14 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
                                pad3(ntuple(d -> Int32(dv[d]), N), Int32(0)), extrap_id(etp.et),
                                Int32(itp.kernel_sym isa HigherOrderMixedKernel),
                                pad3(ntuple(d -> Int32(SUBGRID_ID[effective_subgrids(subgrid_tuple(itp), N)[d]]), N), Int32(0))))
+            tabs64, tptr, npre = linear_tables(itp, effective_subgrids(subgrid_tuple(itp), N))
             devs = devices()
             ptrs = Ptr{Cvoid}[]
             for dev in (isempty(devs) ? Int32[-1] : devs)
                 dev >= 0 && check(ccall((:cib200_set_device, LIB), Int32, (Int32,), dev))
                 out = Ref{Ptr{Cvoid}}(C_NULL)
-                GC.@preserve itp knots64 check(ccall((:cib200_itp_create, LIB), Int32,
-                                                     (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
+                GC.@preserve itp knots64 tabs64 tptr npre check(ccall((:cib200_itp_create_tables, LIB), Int32,
+                    (Ref{ItpDesc}, Ptr{Ptr{Float64}}, Ptr{Int32}, Ref{Ptr{Cvoid}}), desc, tptr, npre, out))
                 push!(ptrs, out[])
             end
             h = Handle(ptrs[1], ptrs)
@@ -223,13 +235,14 @@ end
 # ---- convolution_resample_internal (convolution_resample.jl:240-386) ---------------------------------
 function resample_accelerated(values::AbstractArray{T,N}, kernels, derivatives, subgrids, precompute) where {T,N}
     (T === Float64 || T === Float32) && N <= 8 && all(k -> haskey(KERNEL_ID, k), kernels) &&
-        all(s -> haskey(SUBGRID_ID, s), subgrids) && all(==(101), precompute) &&
+        all(s -> haskey(SUBGRID_ID, s), subgrids) &&
+        all(d -> subgrids[d] === :linear || precompute[d] == 101, 1:N) &&   # :linear axes: generated tables, passed below
         all(d -> derivatives[d] >= 0 && derivatives[d] + (subgrids[d] === :linear ? 0 : subgrids[d] === :cubic ? 1 : 2) <=
                  MAX_TABLE[kernels[d]], 1:N)
 end
 
 function cib200_resample(knots_in::NTuple{N}, knots_out::NTuple{N}, values::Array{T,N},
-                         kernels, derivatives, bcs, subgrids) where {T,N}
+                         kernels, derivatives, bcs, subgrids, precompute) where {T,N}
     kin = ntuple(d -> Vector{Float64}(knots_in[d]), N)
     kout = ntuple(d -> Vector{Float64}(knots_out[d]), N)
     out = Array{T,N}(undef, ntuple(d -> length(kout[d]), N))
@@ -238,15 +251,22 @@ function cib200_resample(knots_in::NTuple{N}, knots_out::NTuple{N}, values::Arra
     kid = Int32[KERNEL_ID[k] for k in kernels]; dv = Int32[derivatives...]
     bl = Int32[BC_ID[b[1]] for b in bcs]; br = Int32[BC_ID[b[2]] for b in bcs]
     sg = Int32[SUBGRID_ID[s] for s in subgrids]
-    GC.@preserve kin kout values out check(ccall((:cib200_resample_sg, LIB), Int32,
+    # :linear axes: the table convolution_resample_internal itself would fetch (:279-280; precompute[d] >= 10 000 from
+    # the kw method, 101 from the kw-less wrappers), column-major as it lies in memory
+    tabs = [subgrids[d] === :linear ?
+            Matrix{Float64}(get_precomputed_kernel_and_range(kernels[d], precompute[d], T, derivatives[d], :linear)[2]) :
+            Matrix{Float64}(undef, 0, 0) for d in 1:N]
+    tptr = [subgrids[d] === :linear ? pointer(tabs[d]) : Ptr{Float64}(0) for d in 1:N]
+    npre = Int32[subgrids[d] === :linear ? size(tabs[d], 1) : 0 for d in 1:N]
+    GC.@preserve kin kout values out tabs tptr npre check(ccall((:cib200_resample_tables, LIB), Int32,
         (Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}},
-         Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Cvoid}),
-        N, T === Float32 ? 1 : 0, n_in, n_out, values, out, pin, pout, kid, dv, bl, br, sg, 0, C_NULL))
+         Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Float64}}, Ptr{Int32}, Int32, Ptr{Cvoid}),
+        N, T === Float32 ? 1 : 0, n_in, n_out, values, out, pin, pout, kid, dv, bl, br, sg, tptr, npre, 0, C_NULL))
     return out
 end
 # in convolution_resample_internal, first line:
 #   resample_accelerated(values, kernels, derivatives, subgrids, precompute) &&
-#       return CIB200Glue.cib200_resample(knots_in, knots_out, values, kernels, derivatives, bcs, subgrids)
+#       return CIB200Glue.cib200_resample(knots_in, knots_out, values, kernels, derivatives, bcs, subgrids, precompute)
 
 # ---- convolution_smooth (convolution_gaussian_smoothing.jl:45-126) -----------------------------------
 function cib200_smooth(knots::NTuple{N,AbstractVector}, values::Array{T,N}, B::Float64) where {T,N}

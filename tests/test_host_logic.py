@@ -190,3 +190,23 @@ def test_linear_subgrid_axes_warn_about_the_table_length(ci):
         warnings.simplefilter("error")
         api._warn_linear_rows(("cubic", "quintic"), ("b5", "b5"), "test")
         api._warn_linear_rows(("linear",), ("a1",), "test")  # a0 / a1 keep their two-row tables
+
+
+def test_generated_tables_of_linear_axes(ci, oracle, golden_dir):
+    """tables.generated_table = precompute_kernel (precompute_kernel_and_range.jl:150-157) in exact integer arithmetic: 101
+    rows reproduce the shipped literals bit for bit, 10 000 rows equal the oracle's independent restatement, and a row of
+    the long table that coincides with a shipped sample point carries the same bits"""
+    from convitp_b200 import tables as T
+    g = np.load(os.path.join(golden_dir, "shipped_tables.npz"))
+    for k, d in (("b5", 0), ("b5", 3), ("b9", 2), ("b13", 6), ("a4", 0), ("a7", 1)):
+        name = f"KERNEL_PRE_{k}_d{d}" if f"KERNEL_PRE_{k}_d{d}" in g.files else f"KERNEL_D1_PRE_{k}_d{d - 1}"
+        t = T.generated_table(k, d, 101)
+        lit = g[name]
+        assert ((t.view(np.uint64) == lit.view(np.uint64)) | ((t == 0) & (lit == 0))).all(), (k, d)
+    for k, d in (("b5", 3), ("a4", 1)):
+        t = T.generated_table(k, d)
+        assert t.shape == (10_000, 2 * T._polys()[k]["eqs"])
+        assert np.array_equal(t, oracle.generated_table(k, d))
+        short = T.generated_table(k, d, 101)
+        assert np.array_equal(t[0], short[0]) and np.array_equal(t[-1], short[-1])      # s = c - eqs, c + 1 - eqs
+        assert np.array_equal(t[1111 * 9], T.generated_table(k, d, 12)[1 * 11])  # 9999/9999 ... (r-1)/(n-1) = 1: last row again
