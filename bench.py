@@ -204,6 +204,16 @@ def secondary_sweeps(peak):
                                       "roofline_frac": 4 * 16 * n ** 4 / (ms * 1e-3) / 1e9 / peak,
                                       "model": "4 passes x 16 B per grid point (40^4 is L2-resident)",
                                       "fp64_floor_ms": fp64_floor_ms, "fp64_frac": fp64_floor_ms / ms}
+    # antiderivative interpolant (derivative = -1 on every axis): 3-D :b5 on 256^3, 10^7 random queries
+    x = np.linspace(0, 1, 256)
+    itg = ci.convolution_interpolation((x, x, x), rng.random((256,) * 3), kernel="b5", derivative=-1, bc="poly",
+                                       coefs_on="device")
+    q = [torch.rand(10_000_000, dtype=torch.float64, device="cuda") for _ in range(3)]
+    ms = best_ms(lambda: itg.eval(*q))
+    out["antiderivative_3d_b5_256^3"] = {"value": 1e7 / (ms * 1e-3), "unit": "evals/s", "ms": ms,
+                                         "roofline_frac": 1e7 * (32 + 8 * 1331) / (ms * 1e-3) / 1e9 / peak,
+                                         "model": "gather model: 24 + 8 B + (10^3 + 3 x 10^2 + 3 x 10 + 1) coefficients x 8 B "
+                                                  "= 10.7 kB per evaluation (measured DRAM: 30.6 kB, DESIGN.md 5.3)"}
     return out
 
 
