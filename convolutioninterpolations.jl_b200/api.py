@@ -201,9 +201,9 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
             # generated 10 000-row tables (_build_subgrids + constructor.jl:117-118): reference path.
             if what != "convolution_interpolation":
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what} does not support antiderivatives")
-            if dv != -1 or any(x != -1 for x in derivs) or ndim > 3:
-                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative={tuple(derivs)}: only the antiderivative "
-                                           "on every axis (1-3 dimensions) is on the accelerated path")
+            if dv != -1 or ndim > 3:
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative={tuple(derivs)}: antiderivatives are "
+                                           "accelerated in 1-3 dimensions (N >= 4 resolves to :linear K~ tables)")
             if sg not in ("cubic", "quintic"):
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivative with the :{sg} subgrid needs "
                                            "generated tables")
@@ -279,12 +279,12 @@ class FastConvolutionInterpolation:
         from . import tables as _tables
         self.linear_rows = _tables.LINEAR_ROWS if linear_rows is None else int(linear_rows)
         self._gen_tables = [None] * nd
-        if not self._itg and self.linear_rows != 101:
+        if self.linear_rows != 101:
             for d in range(nd):
-                if self.subgrid[d] == "linear":
+                if self.subgrid[d] == "linear" and self.derivative[d] >= 0:
                     self._gen_tables[d] = np.asfortranarray(
                         _tables.generated_table(self.kernel[d], int(self.derivative[d]), self.linear_rows))
-        elif not self._itg:
+        else:
             _warn_linear_rows(self.subgrid, self.kernel, "convolution_interpolation")
         if self._itg and self.dtype_id != _lib.F64:
             raise UnsupportedModeError(_lib.EUNSUPPORTED, "the antiderivative path is Float64 only")
@@ -368,13 +368,16 @@ class FastConvolutionInterpolation:
             if devices is not None and len(devices) > 1:
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, "devices=[...] is not available for antiderivatives")
             handle = C.c_void_p()
-            check(L.cib200_itg_create(C.byref(desc), C.byref(handle)))
+            tp = (C.c_void_p * 3)(*[None if t is None else t.ctypes.data for t in self._gen_tables] + [None] * (3 - nd))
+            npre = (C.c_int32 * 3)(*[0 if t is None else t.shape[0] for t in self._gen_tables] + [0] * (3 - nd))
+            check(L.cib200_itg_create_tables(C.byref(desc), tp, npre, C.byref(handle)))
             self._handle = handle
             self._handles = [handle]
             self.devices = None
             self.eval_mode = "integral"
             # itp.anchor (constructor.jl:139): the result is zero at the first interior knot of each axis
-            self.anchor = tuple(float(k[e - 1]) for k, e in zip(self.knots, self.eqs))
+            self.anchor = tuple(float(k[e - 1]) if dv == -1 else 0.0
+                                for k, e, dv in zip(self.knots, self.eqs, self.derivative))
             return
         # one handle per device (the grid is replicated, query batches are split by cib200_itp_eval_multi);
         # devices=None: the current device only

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <limits>
 #include <mutex>
+#include <vector>
 
 #include "cib200_evalcore.cuh"
 
@@ -39,7 +40,23 @@ struct ItgParams {
   double h[3], lo[3], hi[3], knot0[3], anchor[3];
   double eps_line;
   int extrap;
+  // mixed interpolants (FastMixedIntegralOrder, convolution_fast_mixed_{1_integral_dim,2_integral_dims}.jl): the
+  // non-integral axes carry the usual stencil weights on the :linear subgrid, (1 - t) K[row] + t K[row + 1] on the
+  // generated table lin[d] (nlin[d] rows, global memory), and have no tails
+  int is_int[3];
+  int mixed;
+  int nlin[3];
+  const double *lin[3];
+  const double *knots[3];
+  double scale;  // mixed: prod (h_d | (-1/h_d)^DO_d), accumulated from 1.0 in axis order
 };
+
+// window weight jj of a non-integral axis (mixed_1_integral_dim.jl:92-105): linear blend of two table rows
+__device__ __forceinline__ double itg_linear_weight(const ItgParams &p, int d, const AxisPos &pos, int jj) {
+  const int w = 2 * p.eqs[d];
+  const double *kr = p.lin[d] + (long long)pos.row * w + jj;
+  return __dadd_rn(__dmul_rn(__dsub_rn(1.0, pos.t), __ldg(kr)), __dmul_rn(pos.t, __ldg(kr + w)));
+}
 
 // K~ at the signed distance sj (in cells) of a coefficient: eval_subgrid_helpers.jl:24-31; the same arithmetic gives
 // left_values with sj = eqs - j (_compute_left_values, constructor.jl:418-445)
@@ -191,10 +208,16 @@ __device__ __forceinline__ double itg_point(const ItgParams &p, const double *x,
     i = i > p.nk[d] - e ? p.nk[d] - e : i;
     base[d] = i - e;  // 0-based index of the first window coefficient (Julia j = i - eqs + 1)
     l[d] = i - e;     // Julia l = i - eqs (1-based), valid when >= 1
-    lok[d] = l[d] >= 1;
-    for (int jj = 0; jj < 2 * e; ++jj) {
-      const long long j = i - e + 1 + jj;
-      W[(d * p.wmax + jj) * bs] = __dsub_rn(itg_kt(p, d, j, x[d]), __ldg(p.lv[d] + (j - 1)));
+    lok[d] = l[d] >= 1 && p.is_int[d];  // tails exist along the integral axes only
+    if (p.is_int[d]) {
+      for (int jj = 0; jj < 2 * e; ++jj) {
+        const long long j = i - e + 1 + jj;
+        W[(d * p.wmax + jj) * bs] = __dsub_rn(itg_kt(p, d, j, x[d]), __ldg(p.lv[d] + (j - 1)));
+      }
+    } else {
+      AxisPos pos;
+      ok = locate_from_knot(x[d], p.knot0[d], p.h[d], e, p.nk[d], p.knots[d], pos, p.nlin[d]) && ok;
+      for (int jj = 0; jj < 2 * e; ++jj) W[(d * p.wmax + jj) * bs] = itg_linear_weight(p, d, pos, jj);
     }
   }
   double total = 0.0;
@@ -232,6 +255,7 @@ __device__ __forceinline__ double itg_point(const ItgParams &p, const double *x,
     }
     total += acc2;
   }
+  if (p.mixed) return __dmul_rn(total, p.scale);
   double r = __dmul_rn(total, p.h[0]);
   if (NDIM > 1) r = __dmul_rn(r, p.h[1]);
   if (NDIM > 2) r = __dmul_rn(r, p.h[2]);
@@ -310,6 +334,7 @@ __device__ __forceinline__ double itg_warp_point(const ItgParams &p, const ItgDe
   const double x[3] = {x0, x1, x2};
   int base[3];
   bool lok[3];
+  AxisPos pos[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const int e = p.eqs[d];
@@ -320,7 +345,11 @@ __device__ __forceinline__ double itg_warp_point(const ItgParams &p, const ItgDe
     i = i < e ? e : i;
     i = i > p.nk[d] - e ? p.nk[d] - e : i;
     base[d] = (int)i - e;  // 0-based first window coefficient; Julia's l = i - eqs is the same number (valid if >= 1)
-    lok[d] = base[d] >= 1;
+    lok[d] = base[d] >= 1 && p.is_int[d];
+    pos[d].base = base[d];
+    pos[d].row = 0;
+    pos[d].t = 0.0;
+    if (!p.is_int[d]) ok = locate_from_knot(x[d], p.knot0[d], p.h[d], e, p.nk[d], p.knots[d], pos[d], p.nlin[d]) && ok;
   }
   __syncwarp();
   const int ONE = 3 * p.wmax;
@@ -328,7 +357,10 @@ __device__ __forceinline__ double itg_warp_point(const ItgParams &p, const ItgDe
     const int d = idx / p.wmax, jj = idx - d * p.wmax;
     if (jj < 2 * p.eqs[d]) {
       const int j = (d == 0 ? base[0] : (d == 1 ? base[1] : base[2])) + 1 + jj;
-      W[idx] = __dsub_rn(itg_kt(p, d, j, d == 0 ? x0 : (d == 1 ? x1 : x2)), __ldg(p.lv[d] + (j - 1)));
+      if (p.is_int[d])
+        W[idx] = __dsub_rn(itg_kt(p, d, j, d == 0 ? x0 : (d == 1 ? x1 : x2)), __ldg(p.lv[d] + (j - 1)));
+      else
+        W[idx] = itg_linear_weight(p, d, d == 0 ? pos[0] : (d == 1 ? pos[1] : pos[2]), jj);
     }
   }
   __syncwarp();
@@ -366,6 +398,7 @@ __device__ __forceinline__ double itg_warp_point(const ItgParams &p, const ItgDe
     }
   }
   const double total = warp_sum(acc);
+  if (p.mixed) return __dmul_rn(total, p.scale);
   return __dmul_rn(__dmul_rn(__dmul_rn(total, p.h[0]), p.h[1]), p.h[2]);
 }
 
@@ -464,6 +497,8 @@ struct cib200_itg {
   double *d_tail[8];
   double *d_tabs[3][3];
   double *d_lv[3];
+  double *d_lin[3];    // mixed: generated :linear tables of the non-integral axes
+  double *d_knots[3];  // mixed: extended knots of the non-integral axes
   EvalStatus *d_status;
   cudaStream_t stream;
   std::mutex *mu;
@@ -592,6 +627,8 @@ int32_t cib200_itg_destroy(cib200_itg *h) {
     for (int k = 0; k < 3; ++k)
       if (h->d_tabs[d][k]) cudaFree(h->d_tabs[d][k]);
     if (h->d_lv[d]) cudaFree(h->d_lv[d]);
+    if (h->d_lin[d]) cudaFree(h->d_lin[d]);
+    if (h->d_knots[d]) cudaFree(h->d_knots[d]);
   }
   if (h->d_status) cudaFree(h->d_status);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -600,7 +637,17 @@ int32_t cib200_itg_destroy(cib200_itg *h) {
   return CIB200_OK;
 }
 
+static int32_t itg_create_impl(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                               cib200_itg **handle);
 int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
+  return itg_create_impl(desc, nullptr, nullptr, handle);
+}
+int32_t cib200_itg_create_tables(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                                 cib200_itg **handle) {
+  return itg_create_impl(desc, tables, n_pre, handle);
+}
+static int32_t itg_create_impl(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                               cib200_itg **handle) {
   if (!desc || !handle || !desc->coefs) {
     set_error("cib200_itg_create: null argument");
     return CIB200_EINVAL;
@@ -625,12 +672,14 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
       return CIB200_EUNSUPPORTED;
     }
     if (desc->deriv[d] != -1) {
-      set_error("cib200_itg_create: axis %d has derivative %d; mixed integral / interpolation axes resolve to the :linear "
-                "subgrid on generated tables (_build_subgrids) and stay on the reference path", d, desc->deriv[d]);
-      return CIB200_EUNSUPPORTED;
-    }
-    if (desc->subgrid[d] != CIB200_SG_CUBIC && desc->subgrid[d] != CIB200_SG_QUINTIC) {
-      set_error("cib200_itg_create: subgrid %d on axis %d needs generated tables", desc->subgrid[d], d);
+      // mixed interpolant: the axis is on the :linear subgrid (_build_subgrids, constructor.jl:474-491)
+      if (desc->deriv[d] < 0 || desc->subgrid[d] != CIB200_SG_LINEAR || !host_table(desc->kernel[d], desc->deriv[d])) {
+        set_error("cib200_itg_create: axis %d: derivative %d with subgrid %d is not a :linear axis of a mixed interpolant",
+                  d, desc->deriv[d], desc->subgrid[d]);
+        return CIB200_EUNSUPPORTED;
+      }
+    } else if (desc->subgrid[d] != CIB200_SG_CUBIC && desc->subgrid[d] != CIB200_SG_QUINTIC) {
+      set_error("cib200_itg_create: subgrid %d on integral axis %d needs generated tables", desc->subgrid[d], d);
       return CIB200_EUNSUPPORTED;
     }
     if (desc->coef_shape[d] < 2 * e || !desc->knots[d] || !(desc->h[d] > 0)) {
@@ -667,6 +716,21 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
     hmin = d == 0 ? desc->h[d] : std::min(hmin, desc->h[d]);
     p.wmax = std::max(p.wmax, 2 * e);
   }
+  int n_int = 0;
+  p.scale = 1.0;
+  for (int d = 0; d < nd; ++d) {
+    p.is_int[d] = desc->deriv[d] == -1;
+    n_int += p.is_int[d];
+    // mixed_1_integral_dim.jl:121-128: scale = one(T); scale *= h_d | (-1/h_d)^DO_d
+    p.scale *= p.is_int[d] ? desc->h[d] : jl_pow_int(-1.0 / desc->h[d], desc->deriv[d]);
+  }
+  p.mixed = n_int < nd;
+  if (n_int == 0) {
+    set_error("cib200_itg_create: no integral axis (use cib200_itp_create)");
+    delete h->mu;
+    delete h;
+    return CIB200_EINVAL;
+  }
   for (int d = nd; d < 3; ++d) {
     p.stride[d] = tot;
     p.nk[d] = 1;
@@ -684,6 +748,25 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
   if (e != cudaSuccess) return fail(e);
   p.A[0] = h->d_coefs;
   for (int d = 0; d < nd; ++d) {
+    if (!p.is_int[d]) {
+      // :linear axis of a mixed interpolant: generated table (caller's column-major n_pre x 2 eqs image) or the shipped
+      // K^(deriv); extended knots for the stored-knot position arithmetic
+      const bool gen = tables && n_pre && tables[d] && n_pre[d] >= 2;
+      p.nlin[d] = gen ? n_pre[d] : CIB_TAB_ROWS;
+      const int w = 2 * p.eqs[d];
+      std::vector<double> rm((size_t)p.nlin[d] * w);
+      const double *shipped = host_table(desc->kernel[d], desc->deriv[d]);
+      for (int r = 0; r < p.nlin[d]; ++r)
+        for (int c = 0; c < w; ++c) rm[(size_t)r * w + c] = gen ? tables[d][(size_t)c * p.nlin[d] + r] : shipped[(size_t)r * w + c];
+      e = cudaMalloc((void **)&h->d_lin[d], sizeof(double) * rm.size());
+      if (e == cudaSuccess) e = cudaMemcpy(h->d_lin[d], rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_knots[d], sizeof(double) * (size_t)p.nk[d]);
+      if (e == cudaSuccess) e = cudaMemcpy(h->d_knots[d], desc->knots[d], sizeof(double) * (size_t)p.nk[d], cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return fail(e);
+      p.lin[d] = h->d_lin[d];
+      p.knots[d] = h->d_knots[d];
+      continue;
+    }
     const size_t tb = sizeof(double) * CIB_TAB_ROWS * 2 * (size_t)p.eqs[d];
     const double *src[3] = {host_table_i1(desc->kernel[d]), host_table(desc->kernel[d], 0), host_table(desc->kernel[d], 1)};
     for (int k = 0; k < 3; ++k) {
@@ -710,6 +793,7 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
     cudaEventRecord(ev0, h->stream);
   }
   for (int d = 0; d < nd; ++d) {
+    if (!p.is_int[d]) continue;
     itg_left_values_kernel<<<(p.nk[d] + 127) / 128, 128, 0, h->stream>>>(p, d, h->d_lv[d]);
     CIB_LAUNCHED();
   }
@@ -721,6 +805,10 @@ int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle) {
     if (cudaDeviceGetLimit(&have, cudaLimitStackSize) == cudaSuccess && have < need) cudaDeviceSetLimit(cudaLimitStackSize, need);
   }
   for (int mask = 1; mask < (1 << nd); ++mask) {
+    bool on_int_axes = true;  // tails exist along the integral axes only (int_dims, constructor.jl:198, 235)
+    for (int d = 0; d < nd; ++d)
+      if ((mask >> d & 1) && !p.is_int[d]) on_int_axes = false;
+    if (!on_int_axes) continue;
     e = cudaMalloc((void **)&h->d_tail[mask], sizeof(double) * (size_t)tot);
     if (e != cudaSuccess) return fail(e);
     int first = 1;
@@ -805,7 +893,7 @@ int32_t cib200_itg_get(cib200_itg *h, int32_t what, int32_t index, void *out) {
   if (what == 0 && index >= 0 && index < h->p.ndim) {
     src = h->d_lv[index];
     bytes = sizeof(double) * (size_t)h->p.nk[index];
-  } else if (what == 1 && index >= 1 && index < (1 << h->p.ndim)) {
+  } else if (what == 1 && index >= 1 && index < (1 << h->p.ndim) && h->d_tail[index]) {
     src = h->d_tail[index];
     bytes = sizeof(double) * (size_t)h->ntot;
   } else {

@@ -192,9 +192,17 @@ int32_t cib200_itpnd_eval_grid(cib200_itpnd *handle, const int64_t *n, const voi
  * subgrid cubic or quintic (tables K~ = KERNEL_PRE_<k>_i1, K, K'); coefs may be host or device memory.  The prefix-sum
  * arrays are built on the device; the reference's suffix-sum arrays are identically zero wherever its evaluators read
  * them and are not materialised (cib200_integral.cu).  Results are anchored to zero at the first interior knot of each
- * axis (itp.anchor).  Mixed integral / non-integral axes and N >= 4 need generated tables: CIB200_EUNSUPPORTED. */
+ * axis (itp.anchor).  N >= 4 (every axis :linear on generated K~ tables): CIB200_EUNSUPPORTED. */
 typedef struct cib200_itg cib200_itg; /* opaque */
 int32_t cib200_itg_create(const cib200_itp_desc *desc, cib200_itg **handle);
+/* MIXED interpolants (FastMixedIntegralOrder; convolution_fast_mixed_1_integral_dim.jl:11-131,
+ * convolution_fast_mixed_2_integral_dims.jl): deriv[d] = -1 on one or two axes, >= 0 on the others, N <= 3.  The
+ * non-integral axes are on the :linear subgrid (_build_subgrids, constructor.jl:474-491: desc.subgrid[d] = LINEAR) and
+ * read generated tables: tables[d] = itp.kernel_pre[d] (n_pre[d] x 2 eqs doubles, Julia memory order, host), NULL on
+ * the integral axes (NULL on a :linear axis: the 101-row shipped K^(deriv), not what the reference builds).
+ * tables == NULL with every deriv[d] = -1 is cib200_itg_create. */
+int32_t cib200_itg_create_tables(const cib200_itp_desc *desc, const double *const *tables, const int32_t *n_pre,
+                                 cib200_itg **handle);
 int32_t cib200_itg_destroy(cib200_itg *handle);
 /* same contracts as cib200_itp_eval / cib200_itp_eval_grid */
 int32_t cib200_itg_eval(cib200_itg *handle, int64_t nq, const void *const *x, void *out, int32_t memkind,

@@ -1077,6 +1077,9 @@ const double *orc_table_i1(int kernel) {
   }
 }
 
+int orc_itg_create_mixed(int ndim, const int64_t *cshape, const double *coefs, const double *const *knots,
+                         const double *h, const int32_t *kernel, const int32_t *subgrid, const int32_t *deriv,
+                         const double *const *tab, const int32_t *n_pre, int extrap, orc_itg **out);
 struct orc_itg {
   int ndim, extrap;
   int64_t cshape[3], cstride[3], ntot;
@@ -1086,6 +1089,11 @@ struct orc_itg {
   int eqs[3], subgrid[3];
   const double *kp[3], *kd[3], *ke[3];
   double *lv[3];
+  /* mixed interpolants (FastMixedIntegralOrder): deriv[d] = -1 on the integral axes, >= 0 elsewhere; the other axes read
+   * the generated :linear table lin[d] (n_lin[d] rows, row-major) of K^(deriv[d]) */
+  int deriv[3], n_int;
+  double *lin[3];
+  int n_lin[3];
   /* tails, indexed by a base-3 code over the axes: digit 0 = free (local stencil), 1 = left (prefix), 2 = right
    * (suffix); code = s0 + 3 s1 + 9 s2.  1-D: tail1_left = [1], tail1_right = [2].  2-D: tail1_left[1] = [1],
    * tail1_right[1] = [2], tail1_left[2] = [3], tail1_right[2] = [6], tail2_ll = [4], tail2_rl = [5], tail2_lr = [7],
@@ -1205,15 +1213,30 @@ static double *weighted(const orc_itg *g, const int *side) {
 void orc_itg_destroy(orc_itg *g) {
   if (!g) return;
   free(g->coefs);
-  for (int d = 0; d < 3; ++d) { free(g->knots[d]); free(g->lv[d]); }
+  for (int d = 0; d < 3; ++d) { free(g->knots[d]); free(g->lv[d]); free(g->lin[d]); }
   for (int c = 0; c < 27; ++c) free(g->tail[c]);
   free(g);
 }
 
 int orc_itg_create(int ndim, const int64_t *cshape, const double *coefs, const double *const *knots, const double *h,
                    const int32_t *kernel, const int32_t *subgrid, int extrap, orc_itg **out) {
+  const int32_t dv[3] = {-1, -1, -1};
+  return orc_itg_create_mixed(ndim, cshape, coefs, knots, h, kernel, subgrid, dv, NULL, NULL, extrap, out);
+}
+
+/* deriv[d] = -1: integral axis (subgrid cubic / quintic on the shipped K~ tables); deriv[d] >= 0: interpolation /
+ * derivative axis on the :linear subgrid (_build_subgrids, constructor.jl:474-491) reading tab[d] (n_pre[d] rows,
+ * row-major; NULL = the 101-row shipped K^(deriv)) */
+int orc_itg_create_mixed(int ndim, const int64_t *cshape, const double *coefs, const double *const *knots,
+                         const double *h, const int32_t *kernel, const int32_t *subgrid, const int32_t *deriv,
+                         const double *const *tab, const int32_t *n_pre, int extrap, orc_itg **out) {
   if (ndim < 1 || ndim > 3) return ORC_EARG;
   orc_itg *g = (orc_itg *)calloc(1, sizeof(orc_itg));
+  for (int d = 0; d < ndim; ++d) {
+    g->deriv[d] = deriv[d];
+    g->n_int += deriv[d] == -1;
+  }
+  if (g->n_int == 0) { free(g); return ORC_EARG; }
   g->ndim = ndim;
   g->extrap = extrap;
   g->ntot = 1;
@@ -1227,8 +1250,15 @@ int orc_itg_create(int ndim, const int64_t *cshape, const double *coefs, const d
     g->kp[d] = orc_table_i1(kernel[d]);
     g->kd[d] = orc_table(kernel[d], 0);
     g->ke[d] = orc_table(kernel[d], 1);
-    if (g->eqs[d] < 0 || !g->kp[d] || !g->kd[d] || (subgrid[d] == ORC_SG_QUINTIC && !g->ke[d]) ||
-        subgrid[d] == ORC_SG_LINEAR /* needs the generated 10 000-row tables */) {
+    if (deriv[d] >= 0) { /* :linear axis of a mixed interpolant */
+      const double *src = (tab && n_pre && tab[d] && n_pre[d] >= 2) ? tab[d] : orc_table(kernel[d], deriv[d]);
+      g->n_lin[d] = (tab && n_pre && tab[d] && n_pre[d] >= 2) ? n_pre[d] : N_PRE;
+      if (g->eqs[d] < 0 || !src) { orc_itg_destroy(g); return ORC_EARG; }
+      const size_t nel = (size_t)g->n_lin[d] * 2 * (size_t)g->eqs[d];
+      g->lin[d] = (double *)malloc(sizeof(double) * nel);
+      memcpy(g->lin[d], src, sizeof(double) * nel);
+    } else if (g->eqs[d] < 0 || !g->kp[d] || !g->kd[d] || (subgrid[d] == ORC_SG_QUINTIC && !g->ke[d]) ||
+               subgrid[d] == ORC_SG_LINEAR /* integral axes: shipped K~ tables only */) {
       orc_itg_destroy(g);
       return ORC_EARG;
     }
@@ -1238,7 +1268,8 @@ int orc_itg_create(int ndim, const int64_t *cshape, const double *coefs, const d
   }
   g->coefs = (double *)malloc(sizeof(double) * (size_t)g->ntot);
   memcpy(g->coefs, coefs, sizeof(double) * (size_t)g->ntot);
-  for (int d = 0; d < ndim; ++d) compute_left_values(g, d, g->lv[d]);
+  for (int d = 0; d < ndim; ++d)
+    if (g->deriv[d] == -1) compute_left_values(g, d, g->lv[d]);
 
   /* scan recipes: {axis (0-based), reverse} in the order the reference applies them */
   typedef struct { int n; int ax[3]; int rev[3]; } recipe;
@@ -1246,6 +1277,10 @@ int orc_itg_create(int ndim, const int64_t *cshape, const double *coefs, const d
   for (int code = 1; code < ncode; ++code) {
     int side[3] = {code % 3, (code / 3) % 3, (code / 9) % 3};
     int nz = (side[0] != 0) + (side[1] != 0) + (side[2] != 0);
+    int on_int_axes = 1; /* tails exist along the integral axes only (int_dims, constructor.jl:198, 235) */
+    for (int d = 0; d < ndim; ++d)
+      if (side[d] && g->deriv[d] != -1) on_int_axes = 0;
+    if (!on_int_axes) continue;
     recipe r = {0, {0, 0, 0}, {0, 0, 0}};
     if (nz == 1) { /* tail1_left / tail1_right (:207-222), tail3_face_* (:330-331) */
       for (int d = 0; d < 3; ++d)
@@ -1283,8 +1318,10 @@ int orc_itg_create(int ndim, const int64_t *cshape, const double *coefs, const d
 }
 
 /* the un-wrapped functors: convolution_fast_integration_1d.jl:17-38, _2d.jl:18-80, _3d.jl:4-100 */
+static int itg_core_mixed(const orc_itg *g, const double *x, double *res);
 static int itg_core(const orc_itg *g, const double *x, double *res) {
   const int N = g->ndim;
+  if (g->n_int < N) return itg_core_mixed(g, x, res);
   int64_t i[3] = {1, 1, 1}, l[3], r[3];
   int l_ok[3], r_ok[3];
   for (int d = 0; d < N; ++d) {
@@ -1396,6 +1433,108 @@ static int itg_core(const orc_itg *g, const double *x, double *res) {
 #undef A3
 }
 
+/* FastMixedIntegralOrder functors, N <= 3: convolution_fast_mixed_1_integral_dim.jl:11-131 (one integral axis),
+ * convolution_fast_mixed_2_integral_dims.jl (two): Iterators.product over the stencils of the non-integral axes (first
+ * axis fastest) with the :linear kernel product, inside it the K~ centre loop(s) and the tail lookups of the integral
+ * axes; scale = prod(h_d over integral axes, (-1/h_d)^DO_d elsewhere), accumulated from one(T) in axis order */
+static int itg_core_mixed(const orc_itg *g, const double *x, double *res) {
+  const int N = g->ndim;
+  int64_t i[3] = {1, 1, 1}, l[3] = {0, 0, 0}, r[3] = {0, 0, 0}, idx_sg[3] = {0, 0, 0};
+  int l_ok[3] = {0, 0, 0}, r_ok[3] = {0, 0, 0}, id[2] = {-1, -1}, nid = 0;
+  double t_sg[3] = {0, 0, 0};
+  for (int d = 0; d < N; ++d) {
+    double i_float = (x[d] - g->knots[d][0]) / g->h[d] + 1.0;
+    if (!(fabs(i_float) < 9.0e18)) return ORC_ENAN;
+    int64_t v = (int64_t)floor(i_float);
+    if (v < g->eqs[d]) v = g->eqs[d];
+    if (v > g->cshape[d] - g->eqs[d]) v = g->cshape[d] - g->eqs[d];
+    i[d] = v;
+    l[d] = v - g->eqs[d];
+    r[d] = v + g->eqs[d] + 1;
+    l_ok[d] = l[d] >= 1;
+    r_ok[d] = r[d] <= g->cshape[d];
+    if (g->deriv[d] == -1) {
+      id[nid++] = d;
+    } else {
+      double diff_right = 1.0 - (x[d] - g->knots[d][v - 1]) / g->h[d];
+      double cidx = diff_right * (double)(g->n_lin[d] - 1) + 1.0;
+      if (!(fabs(cidx) < 9.0e18)) return ORC_ENAN;
+      int64_t k = (int64_t)floor(cidx);
+      if (k < 1) k = 1;
+      if (k > g->n_lin[d] - 1) k = g->n_lin[d] - 1;
+      idx_sg[d] = k;
+      t_sg[d] = cidx - (double)k;
+    }
+  }
+#define LVW(d, j) (eval_sg_kt(g, d, j, x[d]) - g->lv[d][(j)-1])
+#define AT(code, a) (g->tail[code][((a)[0] - 1) + ((a)[1] - 1) * g->cstride[1] + ((a)[2] - 1) * g->cstride[2]])
+  static const int P3[3] = {1, 3, 9};
+  double result = 0.0;
+  int64_t lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1}, c[3];
+  for (int d = 0; d < N; ++d)
+    if (g->deriv[d] != -1) { lo[d] = i[d] - g->eqs[d] + 1; hi[d] = i[d] + g->eqs[d]; }
+  for (c[2] = lo[2]; c[2] <= hi[2]; ++c[2])
+    for (c[1] = lo[1]; c[1] <= hi[1]; ++c[1])
+      for (c[0] = lo[0]; c[0] <= hi[0]; ++c[0]) {
+        double kt_prod = 1.0;
+        for (int d = 0; d < N; ++d) {
+          if (g->deriv[d] == -1) continue;
+          int64_t col = c[d] - i[d] + g->eqs[d];
+          double k0 = TAB(g->lin[d], idx_sg[d], col, g->eqs[d]), k1 = TAB(g->lin[d], idx_sg[d] + 1, col, g->eqs[d]);
+          kt_prod *= (1.0 - t_sg[d]) * k0 + t_sg[d] * k1;
+        }
+        int64_t a[3] = {c[0], c[1], c[2]};
+        if (nid == 1) {
+          const int D = id[0];
+          for (int64_t j = i[D] - g->eqs[D] + 1; j <= i[D] + g->eqs[D]; ++j) {
+            double lv = LVW(D, j);
+            a[D] = j;
+            result += g->coefs[(a[0] - 1) + (a[1] - 1) * g->cstride[1] + (a[2] - 1) * g->cstride[2]] * lv * kt_prod;
+          }
+          double tl = 0.0, tr = 0.0;
+          if (l_ok[D]) { a[D] = l[D]; tl = AT(1 * P3[D], a); }
+          if (r_ok[D]) { a[D] = r[D]; tr = AT(2 * P3[D], a); }
+          result += (tl + tr) * kt_prod;
+        } else {
+          const int D1 = id[0], D2 = id[1];
+          for (int64_t j2 = i[D2] - g->eqs[D2] + 1; j2 <= i[D2] + g->eqs[D2]; ++j2) {
+            double lv2 = LVW(D2, j2);
+            a[D2] = j2;
+            for (int64_t j1 = i[D1] - g->eqs[D1] + 1; j1 <= i[D1] + g->eqs[D1]; ++j1) {
+              double lv1 = LVW(D1, j1);
+              a[D1] = j1;
+              result += g->coefs[(a[0] - 1) + (a[1] - 1) * g->cstride[1] + (a[2] - 1) * g->cstride[2]] * lv1 * lv2 * kt_prod;
+            }
+            double tl1 = 0.0, tr1 = 0.0;
+            if (l_ok[D1]) { a[D1] = l[D1]; tl1 = AT(1 * P3[D1], a); }
+            if (r_ok[D1]) { a[D1] = r[D1]; tr1 = AT(2 * P3[D1], a); }
+            result += (tl1 + tr1) * lv2 * kt_prod;
+          }
+          for (int64_t j1 = i[D1] - g->eqs[D1] + 1; j1 <= i[D1] + g->eqs[D1]; ++j1) {
+            double lv1 = LVW(D1, j1);
+            a[D1] = j1;
+            double tl2 = 0.0, tr2 = 0.0;
+            if (l_ok[D2]) { a[D2] = l[D2]; tl2 = AT(1 * P3[D2], a); }
+            if (r_ok[D2]) { a[D2] = r[D2]; tr2 = AT(2 * P3[D2], a); }
+            result += (tl2 + tr2) * lv1 * kt_prod;
+          }
+          double c_ll = 0.0, c_rl = 0.0, c_lr = 0.0, c_rr = 0.0;
+          if (l_ok[D1] && l_ok[D2]) { a[D1] = l[D1]; a[D2] = l[D2]; c_ll = AT(1 * P3[D1] + 1 * P3[D2], a); }
+          if (r_ok[D1] && l_ok[D2]) { a[D1] = r[D1]; a[D2] = l[D2]; c_rl = AT(2 * P3[D1] + 1 * P3[D2], a); }
+          if (l_ok[D1] && r_ok[D2]) { a[D1] = l[D1]; a[D2] = r[D2]; c_lr = AT(1 * P3[D1] + 2 * P3[D2], a); }
+          if (r_ok[D1] && r_ok[D2]) { a[D1] = r[D1]; a[D2] = r[D2]; c_rr = AT(2 * P3[D1] + 2 * P3[D2], a); }
+          result += (c_ll + c_rl + c_lr + c_rr) * kt_prod;
+        }
+      }
+  double scale = 1.0;
+  for (int d = 0; d < N; ++d)
+    scale *= g->deriv[d] == -1 ? g->h[d] : jl_pow_int(-1.0 / g->h[d], g->deriv[d]);
+  *res = result * scale;
+  return ORC_OK;
+#undef LVW
+#undef AT
+}
+
 /* extrapolation_operator.jl:31-63 + extrapolate_point.jl:41-160 around the integral functor */
 static int itg_etp_point(const orc_itg *g, const double *x, double *res) {
   const int N = g->ndim;
@@ -1459,6 +1598,7 @@ double orc_itg_right_tail_maxabs(const orc_itg *g) {
   for (int code = 1; code < ncode; ++code) {
     int side[3] = {code % 3, (code / 3) % 3, (code / 9) % 3};
     if (side[0] != 2 && side[1] != 2 && side[2] != 2) continue;
+    if (!g->tail[code]) continue;
     for (int64_t o = 0; o < g->ntot; ++o) {
       int ok = 1;
       for (int d = 0; d < g->ndim; ++d) {

@@ -82,6 +82,9 @@ def lib():
         L.orc_table_i1.argtypes = [C.c_int]
         L.orc_itg_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.orc_itg_create_mixed.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
+                                           C.POINTER(C.c_void_p)]
         L.orc_itg_eval.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_int64)]
         L.orc_itg_destroy.argtypes = [C.c_void_p]
         L.orc_itg_right_tail_maxabs.restype = C.c_double
@@ -369,7 +372,8 @@ class IntegralInterpolant:
     99-174, tails :176-364; evaluators convolution_fast_integration_{1d,2d,3d}.jl).  Result anchored to zero at the first
     interior knot of each axis (`anchor`, constructor.jl:139)."""
 
-    def __init__(self, knots, values, kernel="b5", extrap="throw", bc="detect", subgrid="cubic"):
+    def __init__(self, knots, values, kernel="b5", extrap="throw", bc="detect", subgrid="cubic", derivative=-1,
+                 linear_rows=LINEAR_ROWS):
         values = np.asarray(values, dtype=np.float64)
         nd = values.ndim
         if nd < 1 or nd > 3:
@@ -377,7 +381,7 @@ class IntegralInterpolant:
         self.ndim = nd
         self.knots_in = _knots_tuple(knots, nd)
         self.kernels = _ntuple(kernel, nd, str)
-        self.derivs = (-1,) * nd
+        self.derivs = _ntuple(derivative, nd, int)  # -1: integral axis; >= 0: :linear axis of a mixed interpolant
         bcs = _norm_bc(bc, nd)
         fixed = []
         for d in range(nd):  # :poly -> :linear downgrade, convolution_interpolation_function.jl:135-143
@@ -386,23 +390,34 @@ class IntegralInterpolant:
                 b = ("linear", "linear") if b == ("poly", "poly") else (("linear", b[1]) if b[0] == "poly" else (b[0], "linear"))
             fixed.append(b)
         self.bc = tuple(fixed)
-        self.subgrid = build_subgrids_integral(self.kernels, _ntuple(subgrid, nd, str), nd)
-        for k, sg in zip(self.kernels, self.subgrid):
-            if sg == "linear" or (sg == "quintic" and MAX_TABLE_DERIVATIVE[k] < 1):
+        sg_int = build_subgrids_integral(self.kernels, _ntuple(subgrid, nd, str), nd)
+        # non-integral axes of a mixed interpolant resolve to :linear (has_integral_dim, constructor.jl:474-491)
+        self.subgrid = tuple(sg_int[d] if self.derivs[d] == -1 else "linear" for d in range(nd))
+        for k, sg, dv in zip(self.kernels, self.subgrid, self.derivs):
+            if dv == -1 and (sg == "linear" or (sg == "quintic" and MAX_TABLE_DERIVATIVE[k] < 1)):
                 raise OracleError(f"antiderivative: subgrid {self.subgrid} needs generated tables")
+            if dv < -1 or dv > MAX_TABLE_DERIVATIVE[k]:
+                raise OracleError(f"K^({dv}) of :{k} does not exist")
         self.eqs = tuple(KERNEL_EQS[k] for k in self.kernels)
         self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)
         self.coefs = create_coefs(values, self.h, self.kernels, self.bc)
         self.knots = tuple(extend_vector(k, e - 1) for k, e in zip(self.knots_in, self.eqs))
-        self.anchor = tuple(float(k[e - 1]) for k, e in zip(self.knots, self.eqs))
+        # anchor = knots_new[d][eqs[d]] on the integral axes, zero(T) elsewhere (constructor.jl:139)
+        self.anchor = tuple(float(k[e - 1]) if dv == -1 else 0.0 for k, e, dv in zip(self.knots, self.eqs, self.derivs))
         self.extrap = extrap
         cs = (C.c_int64 * nd)(*self.coefs.shape)
         kp = (C.c_void_p * nd)(*[k.ctypes.data for k in self.knots])
         hh = (C.c_double * nd)(*self.h)
         kid = (C.c_int32 * nd)(*[KERNEL_IDS[k] for k in self.kernels])
         sg = (C.c_int32 * nd)(*[SUBGRID_IDS[x] for x in self.subgrid])
+        dvs = (C.c_int32 * nd)(*self.derivs)
+        self._tabs = [generated_table(self.kernels[d], self.derivs[d], linear_rows)
+                      if (self.derivs[d] >= 0 and linear_rows != 101) else None for d in range(nd)]
+        tp = (C.c_void_p * nd)(*[None if t is None else t.ctypes.data for t in self._tabs])
+        npre = (C.c_int32 * nd)(*[0 if t is None else t.shape[0] for t in self._tabs])
         h = C.c_void_p()
-        rc = lib().orc_itg_create(nd, cs, self.coefs.ctypes.data, kp, hh, kid, sg, EXTRAP_IDS[extrap], C.byref(h))
+        rc = lib().orc_itg_create_mixed(nd, cs, self.coefs.ctypes.data, kp, hh, kid, sg, dvs, tp, npre,
+                                        EXTRAP_IDS[extrap], C.byref(h))
         if rc:
             raise OracleError(f"orc_itg_create rc={rc}")
         self._h = h
@@ -457,11 +472,7 @@ def convolution_interpolation(knots, values, **kw):
     nd = np.ndim(values)
     dvs = (dv,) * nd if isinstance(dv, int) else tuple(dv) * (nd if len(tuple(dv)) == 1 else 1)
     if any(d == -1 for d in dvs):
-        if not all(d == -1 for d in dvs):
-            # mixed integral / interpolation axes resolve every non-integral axis to the :linear subgrid on generated
-            # 10 000-row tables (_build_subgrids, constructor.jl:474-491): outside the shipped-table path
-            raise OracleError("mixed antiderivative / interpolation axes need generated tables")
-        kw = {k: v for k, v in kw.items() if k != "derivative"}
+        # pure (FastIntegralOrder) or mixed (FastMixedIntegralOrder: the other axes on :linear, generated tables)
         return IntegralInterpolant(knots, values, **kw)
     return Interpolant(knots, values, **kw)
 

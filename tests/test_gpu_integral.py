@@ -126,7 +126,7 @@ def test_errors_and_unsupported_modes(ci):
     with pytest.raises(ci.InexactError):
         g.eval(np.array([0.5, np.nan]))
     v2 = np.outer(x, x)
-    for kw in (dict(derivative=(-1, 0)), dict(derivative=(1, -1)), dict(derivative=-1, dtype=np.float32)):
+    for kw in (dict(derivative=(-1, 4)), dict(derivative=-1, dtype=np.float32), dict(derivative=(-1, 0), dtype=np.float32)):
         with pytest.raises(ci.UnsupportedModeError):
             ci.convolution_interpolation((x, x), v2, kernel="b5", **kw)
     with pytest.raises(ci.UnsupportedModeError):
@@ -151,3 +151,58 @@ def test_large_3d_grid_prefix_sums_and_linearity(ci):
     assert np.abs(ab - (2.0 * a - 3.0 * b)).max() <= 1e-12
     c = ci.convolution_interpolation((x, x, x), np.full((n, n, n), 1.75), kernel="b5", derivative=-1, bc="poly").eval(*q)
     assert np.abs(c - 1.75 * q[0] * q[1] * q[2]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("derivative,kw", [((-1, 0), dict(kernel="b5")), ((0, -1), dict(kernel="a4")),
+                                          ((-1, 1), dict(kernel=("b7", "b5"), subgrid="quintic")),
+                                          ((2, -1), dict(kernel="b5", bc="poly"))])
+@pytest.mark.parametrize("extrap", ["throw", "flat", "line"])
+def test_mixed_2d(ci, oracle, derivative, kw, extrap):
+    """FastMixedIntegralOrder (convolution_fast_mixed_1_integral_dim.jl): one integral axis, the other on the :linear
+    subgrid with the generated 10 000-row table"""
+    rng = np.random.default_rng(711)
+    shape = (53, 44)
+    k = (np.linspace(0, 2 * np.pi, shape[0]), np.linspace(-1, 1, shape[1]))
+    v = _field(shape, rng)
+    pad = 0.0 if extrap == "throw" else 0.15
+    q = np.stack([rng.uniform(kk[0] - pad, kk[-1] + pad, 40_003) for kk in k])
+    o = oracle.convolution_interpolation(k, v, derivative=derivative, extrap=extrap, **kw)
+    g = ci.convolution_interpolation(k, v, derivative=derivative, extrap=extrap, **kw)
+    ref, got = o.eval(*q), g.eval(*q)
+    S = np.abs(o.coefs).max()
+    for kk, h, dv in zip(o.knots_in, o.h, derivative):
+        S *= (kk[-1] - kk[0]) if dv == -1 else (1.0 / h) ** dv
+    amp = _line_amplification(o, tuple(q)) if extrap == "line" else 1.0
+    assert rel_err(got, ref, S * amp).max() <= TOL64
+    assert g.itp.subgrid == o.subgrid and g.itp.anchor == o.anchor and "linear" in g.itp.subgrid
+
+
+@pytest.mark.parametrize("derivative,kw", [((-1, 0, 0), dict(kernel="b5")), ((0, -1, -1), dict(kernel="b5", bc="poly")),
+                                          ((-1, 1, -1), dict(kernel=("a4", "b5", "b7"))), ((0, 0, -1), dict(kernel="a4"))])
+def test_mixed_3d(ci, oracle, derivative, kw):
+    """one (mixed_1_integral_dim.jl) and two (mixed_2_integral_dims.jl) integral axes in 3-D"""
+    rng = np.random.default_rng(712)
+    shape = (27, 31, 25)
+    k = tuple(np.linspace(0, 1 + 0.3 * i, s) for i, s in enumerate(shape))
+    v = _field(shape, rng)
+    for extrap, pad in (("throw", 0.0), ("line", 0.04)):
+        q = np.stack([rng.uniform(kk[0] - pad, kk[-1] + pad, 20_001) for kk in k])
+        o = oracle.convolution_interpolation(k, v, derivative=derivative, extrap=extrap, **kw)
+        g = ci.convolution_interpolation(k, v, derivative=derivative, extrap=extrap, **kw)
+        S = np.abs(o.coefs).max()
+        for kk, h, dv in zip(o.knots_in, o.h, derivative):
+            S *= (kk[-1] - kk[0]) if dv == -1 else (1.0 / h) ** dv
+        amp = _line_amplification(o, tuple(q)) if extrap == "line" else 1.0
+        assert rel_err(g.eval(*q), o.eval(*q), S * amp).max() <= TOL64
+
+
+def test_mixed_analytic(ci):
+    """d/dy of the x-antiderivative of sin x cos y = (-cos x + cos a) (-sin y), on the device path"""
+    errs = []
+    for n in (16, 32, 64):
+        x = np.linspace(0.0, 2 * np.pi, n)
+        itp = ci.convolution_interpolation((x, x), np.sin(x)[:, None] * np.cos(x)[None, :], kernel="b5",
+                                           derivative=(-1, 1), bc="poly")
+        q = np.random.default_rng(6).uniform(0.5, 5.7, (2, 1000))
+        errs.append(np.abs(itp.eval(*q) - (-np.cos(q[0]) + np.cos(itp.itp.anchor[0])) * (-np.sin(q[1]))).max())
+    assert errs[0] / errs[1] > 8 and errs[1] / errs[2] > 8 and errs[2] < 1e-7

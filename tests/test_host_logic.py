@@ -111,8 +111,8 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
         ci.convolution_interpolation(x, v, kernel="a1")           # a0 / a1: :linear subgrid only
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, kernel="a4", derivative=2)  # K'' of the a-series does not exist
-    with pytest.raises(U):  # mixed integral / interpolation axes resolve to :linear on generated tables
-        ci.convolution_interpolation((x, x), np.zeros((30, 30)), derivative=(-1, 0))
+    with pytest.raises(U):  # mixed integral / derivative axes: K^(4) of :b5 does not exist
+        ci.convolution_interpolation((x, x), np.zeros((30, 30)), derivative=(-1, 4))
     with pytest.raises(U):  # the antiderivative path is Float64 only
         ci.convolution_interpolation(x, v, derivative=-1, dtype=np.float32)
     with pytest.raises(U):  # N >= 4 integral directions: :linear subgrid

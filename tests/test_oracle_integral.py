@@ -59,8 +59,35 @@ def test_a_series_integral_directions_resolve_to_the_cubic_subgrid(oracle):
     a = oracle.convolution_interpolation(x, x ** 2, kernel="a4", derivative=-1, subgrid="quintic")
     b = oracle.convolution_interpolation(x, x ** 2, kernel="b5", derivative=-1, subgrid="quintic")
     assert a.subgrid == ("cubic",) and b.subgrid == ("quintic",)
-    with pytest.raises(oracle.OracleError):
-        oracle.convolution_interpolation((x, x), np.outer(x, x), kernel="b5", derivative=(-1, 0))
+    m = oracle.convolution_interpolation((x, x), np.outer(x, x), kernel="b5", derivative=(-1, 0), subgrid="quintic")
+    assert m.subgrid == ("quintic", "linear") and m.anchor == (0.0, 0.0)  # the other axis resolves to :linear
+
+
+@pytest.mark.parametrize("kernel", ["b5", "a4"])
+def test_mixed_integral_interpolation_axes(oracle, kernel):
+    """FastMixedIntegralOrder: x-antiderivative / y-derivative of sin x cos y and the two-integral-axes 3-D case converge"""
+    rng = np.random.default_rng(8)
+    for dv, exact in (((-1, 0), lambda q, a: (-np.cos(q[0]) + np.cos(a[0])) * np.cos(q[1])),
+                      ((0, -1), lambda q, a: np.sin(q[0]) * (np.sin(q[1]) - np.sin(a[1]))),
+                      ((-1, 1), lambda q, a: (-np.cos(q[0]) + np.cos(a[0])) * (-np.sin(q[1])))):
+        errs = []
+        for n in (16, 32, 64):
+            x = np.linspace(0, 2 * np.pi, n)
+            itp = oracle.convolution_interpolation((x, x), np.sin(x)[:, None] * np.cos(x)[None, :], kernel=kernel,
+                                                   derivative=dv, bc="poly")
+            q = rng.uniform(0.5, 5.7, (2, 300))
+            errs.append(np.abs(itp.eval(*q) - exact(q, itp.anchor)).max())
+            assert itp.right_tail_maxabs() == 0.0
+        assert errs[0] / errs[1] > MIN_RATIO and errs[1] / errs[2] > MIN_RATIO
+    errs = []
+    for n in (12, 24, 48):
+        x = np.linspace(0, 2 * np.pi, n)
+        v = np.sin(x)[:, None, None] * np.cos(x)[None, :, None] * np.sin(x)[None, None, :]
+        itp = oracle.convolution_interpolation((x, x, x), v, kernel=kernel, derivative=(0, -1, -1), bc="poly")
+        q = rng.uniform(0.6, 5.6, (3, 200))
+        a = itp.anchor
+        errs.append(np.abs(itp.eval(*q) - np.sin(q[0]) * (np.sin(q[1]) - np.sin(a[1])) * (-np.cos(q[2]) + np.cos(a[2]))).max())
+    assert errs[0] / errs[1] > MIN_RATIO and errs[1] / errs[2] > MIN_RATIO
 
 
 @pytest.mark.parametrize("shape,kernel", [((300,), "b5"), ((23, 19), ("b5", "a4")), ((14, 12, 13), ("a4", "b5", "b7"))])
