@@ -49,8 +49,12 @@ kernel_symbols(::HigherOrderKernel{KS}) where {KS} = KS        # struct_construc
 kernel_symbols(::HigherOrderMixedKernel{KS}) where {KS} = KS
 kernel_symbols(_) = nothing
 
-# antiderivative on EVERY axis (FastIntegralOrder, convolution_fast_integration_{1d,2d,3d}.jl): cib200_itg_*
-is_integral(itp::FastConvolutionInterpolation) = itp.derivative_order isa FastIntegralOrder
+# antiderivative on every axis (FastIntegralOrder, convolution_fast_integration_{1d,2d,3d}.jl) or on some of them
+# (FastMixedIntegralOrder{DO}, convolution_fast_mixed_{1_integral_dim,2_integral_dims}.jl): cib200_itg_*
+is_integral(itp::FastConvolutionInterpolation) =
+    itp.derivative_order isa FastIntegralOrder || itp.derivative_order isa FastMixedIntegralOrder
+integral_derivs(itp::FastConvolutionInterpolation{T,N}) where {T,N} =
+    itp.derivative_order isa FastIntegralOrder ? ntuple(_ -> -1, N) : typeof(itp.derivative_order).parameters[1]
 
 function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     (T === Float64 || T === Float32) || return false
@@ -62,8 +66,11 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     if is_integral(itp)
         # shipped K~ / K / K' tables only: Float64, N <= 3, cubic or quintic subgrid on every axis (mixed integral /
         # interpolation axes and N >= 4 resolve to :linear on generated tables, _build_subgrids)
-        return T === Float64 && N <= 3 && all(d -> length(itp.pre_range[d]) == 101, 1:N) &&
-               all(s -> s === :cubic || s === :quintic, subgrid_tuple(itp))
+        dvi = integral_derivs(itp)
+        sgi = subgrid_tuple(itp)
+        return T === Float64 && N <= 3 &&
+               all(d -> dvi[d] == -1 ? (length(itp.pre_range[d]) == 101 && (sgi[d] === :cubic || sgi[d] === :quintic)) :
+                                       (sgi[d] === :linear && 0 <= dvi[d] <= MAX_TABLE[ks[d]]), 1:N)
     end
     itp.derivative_order isa DerivativeOrder || return false
     dv = derivative_tuple(itp)
@@ -138,14 +145,17 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
             if is_integral(itp)
                 # the library builds left_values and the prefix-sum tails itself (constructor.jl:176-364, :414-448) from
                 # itp.coefs; itp.tail* of the Julia struct are not read
+                dvi = integral_derivs(itp)
                 desc = Ref(ItpDesc(Int32(N), Int32(0), pad3(Int64.(size(itp.coefs)), Int64(1)), pointer(itp.coefs),
                                    pad3(ntuple(d -> pointer(knots64[d]), N), Ptr{Float64}(0)),
                                    pad3(Float64.(itp.h), 1.0), pad3(ntuple(d -> Int32(KERNEL_ID[ks[d]]), N), Int32(0)),
-                                   pad3(ntuple(_ -> Int32(-1), N), Int32(0)), extrap_id(etp.et), Int32(0),
+                                   pad3(ntuple(d -> Int32(dvi[d]), N), Int32(0)), extrap_id(etp.et), Int32(0),
                                    pad3(ntuple(d -> Int32(SUBGRID_ID[subgrid_tuple(itp)[d]]), N), Int32(0))))
+                # the :linear (non-integral) axes of a mixed interpolant bring their generated tables
+                tabs64, tptr, npre = linear_tables(itp, ntuple(d -> dvi[d] == -1 ? :integral : :linear, N))
                 out = Ref{Ptr{Cvoid}}(C_NULL)
-                GC.@preserve itp knots64 check(ccall((:cib200_itg_create, LIB), Int32,
-                                                     (Ref{ItpDesc}, Ref{Ptr{Cvoid}}), desc, out))
+                GC.@preserve itp knots64 tabs64 tptr npre check(ccall((:cib200_itg_create_tables, LIB), Int32,
+                    (Ref{ItpDesc}, Ptr{Ptr{Float64}}, Ptr{Int32}, Ref{Ptr{Cvoid}}), desc, tptr, npre, out))
                 h = Handle(out[])
                 finalizer(x -> ccall((:cib200_itg_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
                 return h
