@@ -214,10 +214,17 @@ __global__ void bin_offsets_kernel(BinGeom g, int nblk, unsigned *__restrict__ h
 }
 
 __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGeom g, Coords c, long long nq,
-                                                              const unsigned *__restrict__ hist, Record *__restrict__ rec, int dbg) {
+                                                              unsigned *hist, Record *__restrict__ rec, int dbg) {
   extern __shared__ unsigned sh[];
-  const unsigned *src = hist + (size_t)blockIdx.x * g.nbin;
-  for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = src[i];
+  // dbg == 3: ONE write cursor per tile shared by all CTAs (row 0 of hist = tile starts, global atomics) instead of a
+  // private cursor per (CTA, tile): 32 k open 128-byte lines (4 MB) instead of 148 x 32 k (600 MB), so a line collects
+  // its four records in L2 before it is written back.  The order of the records inside a tile then varies from run to
+  // run; the value returned for a query does not depend on it.
+  const bool shared_cursors = dbg == 3;
+  if (!shared_cursors) {
+    const unsigned *src = hist + (size_t)blockIdx.x * g.nbin;
+    for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = src[i];
+  }
   __syncthreads();
   const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   long long per = (nq + gridDim.x - 1) / gridDim.x;
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
       if (q < q1) {
         unsigned lc;
         const int bin_ = classify(p, g, x[u], k0, lc);
-        const unsigned slot = dbg == 2 ? (unsigned)q : atomicAdd(&sh[bin_], 1u);
+        const unsigned slot = dbg == 2 ? (unsigned)q : (shared_cursors ? atomicAdd(hist + bin_, 1u) : atomicAdd(&sh[bin_], 1u));
         if (dbg == 1 && slot != 0xffffffffu) continue;
         // one 32-byte sector per query, written with two 16-byte stores; the spare word carries the cell inside the tile
         st_record(rec + slot, x[u][0], x[u][1], x[u][2], __hiloint2double((int)lc, (int)(unsigned)q));
@@ -1029,11 +1036,13 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   CIB_LAUNCHED();
   bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
-  bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, getenv("CIB200_DBG_SCATTER") ? atoi(getenv("CIB200_DBG_SCATTER")) : 0);
+  static const int scatter_mode = getenv("CIB200_DBG_SCATTER") ? atoi(getenv("CIB200_DBG_SCATTER"))
+                                  : (getenv("CIB200_SCATTER_SHARED") && getenv("CIB200_SCATTER_SHARED")[0] == '1' ? 3 : 0);
+  bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, scatter_mode);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 1, st);
-  if (getenv("CIB200_DBG_SCATTER") && atoi(getenv("CIB200_DBG_SCATTER")) != 0) {  // timing experiments only: no evaluation
+  if (scatter_mode == 1 || scatter_mode == 2) {  // timing experiments only: no evaluation
     for (int i = 2; i < 5; ++i) prof_mark(h, i, st);
     return CIB200_OK;
   }
