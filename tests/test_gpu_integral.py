@@ -206,3 +206,18 @@ def test_mixed_analytic(ci):
         q = np.random.default_rng(6).uniform(0.5, 5.7, (2, 1000))
         errs.append(np.abs(itp.eval(*q) - (-np.cos(q[0]) + np.cos(itp.itp.anchor[0])) * (-np.sin(q[1]))).max())
     assert errs[0] / errs[1] > 8 and errs[1] / errs[2] > 8 and errs[2] < 1e-7
+
+
+def test_1d_long_grid_pairwise_recursion(ci, oracle):
+    """n = 200 001: Base's accumulate_pairwise! recurses 11 levels (blocks of < 128); the device restates it in one thread
+    with a raised stack limit - bit-for-bit the same association as the oracle's restatement"""
+    rng = np.random.default_rng(706)
+    n = 200_001
+    x = np.linspace(0.0, 50.0, n)
+    v = np.sin(x) + 0.5 + 0.01 * rng.uniform(-1, 1, n)
+    q = rng.uniform(0.0, 50.0, 100_000)
+    _, _, g, o = _compare(ci, oracle, x, v, (q,), kernel="b5", bc="poly")
+    t, tr = g.itp.tail(1), o.tail(1)
+    assert np.abs(t - tr).max() <= 4e-16 * np.abs(tr).max()
+    exact = -np.cos(q) + np.cos(0.0) + 0.5 * q
+    assert np.abs(g.eval(q) - exact).max() < 5e-3  # the integrated noise is a random walk of ~1e-3
