@@ -196,9 +196,10 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
             raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: kernel :{k} (axis {d + 1}) is not on the "
                                        f"accelerated path ({ACCELERATED_KERNELS})")
         if dv < 0:
-            # FastIntegralOrder (convolution_fast_integration_{1d,2d,3d}.jl): every axis an integral direction, shipped
-            # K~ / K / K' tables.  Mixed integral / interpolation axes and N >= 4 resolve to the :linear subgrid on
-            # generated 10 000-row tables (_build_subgrids + constructor.jl:117-118): reference path.
+            # integral direction: FastIntegralOrder (every axis, convolution_fast_integration_{1d,2d,3d}.jl) or
+            # FastMixedIntegralOrder (some axes, convolution_fast_mixed_*.jl) on the shipped K~ / K / K' tables; the other
+            # axes of a mixed interpolant are ordinary :linear axes (checked below).  N >= 4 resolves the integral
+            # directions to :linear K~ tables and has no tails: reference path.
             if what != "convolution_interpolation":
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what} does not support antiderivatives")
             if dv != -1 or ndim > 3:
@@ -364,7 +365,8 @@ class FastConvolutionInterpolation:
         desc.extrap = EXTRAP_IDS[_extrap]
         desc.perdim = int(self.perdim)
         if self._itg:
-            # antiderivative on every axis: prefix-sum tails built on the device (constructor.jl:176-364)
+            # antiderivative on all or some axes: prefix-sum tails along the integral axes, built on the device
+            # (constructor.jl:176-364)
             if devices is not None and len(devices) > 1:
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, "devices=[...] is not available for antiderivatives")
             handle = C.c_void_p()

@@ -183,7 +183,8 @@ int32_t cib200_itpnd_eval(cib200_itpnd *handle, int64_t nq, const void *const *x
 int32_t cib200_itpnd_eval_grid(cib200_itpnd *handle, const int64_t *n, const void *const *x, void *out,
                                int32_t memkind, void *stream, int64_t *first_bad);
 
-/* ---- antiderivatives: derivative = -1 on EVERY axis, 1..3 dimensions --------------
+/* ---- antiderivatives: derivative = -1 on every axis (or on some: cib200_itg_create_tables), 1..3 dimensions
+ *       ---------------------------------------------------------------------------
  * itp.(xs...) / itp(xs, ys, zs) for the FastIntegralOrder functors
  *   convolution_fast_interpolation/convolution_fast_integration_1d.jl:17-38, _2d.jl:18-80, _3d.jl:4-100
  *   (+ eval_sg_kt, eval_subgrid_helpers.jl:22-32) behind extrapolation_operator.jl:31-99 / extrapolate_point.jl:41-160.
