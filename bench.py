@@ -258,6 +258,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One rank per GPU: run on (and first-touch the pinned host buffers from) the CPUs of the NUMA node the GPU hangs
+    off, so that the host-buffer leg of several ranks does not funnel through one socket's memory.  Best effort: any
+    failure leaves the default affinity.  Returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -274,6 +303,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for this path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -424,6 +454,7 @@ def main():
                            "queries_per_gpu_per_step": nq, "grid": args.grid, "kernel": "b5", "derivative": 0,
                            "bc": "poly", "extrap": "throw", "eval_mode": itp.itp.eval_mode,
                            "parallelism": f"query-sharded x{world}, coefficient grid replicated, no collective",
+                           "numa_node_of_rank0": numa,
                            "l2": "inputs (32 B/query x nq) and the 1.1 GB grid exceed the 126 MB L2; no flush needed",
                            "grid_build_s": build_s, "grid_build_device_ms": build_dev_ms},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
