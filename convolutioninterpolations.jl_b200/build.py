@@ -1,4 +1,7 @@
-"""Builds libcib200.so (sm_100a) in-tree with nvcc.  Usage: python build.py [--force]"""
+"""Builds libcib200.so (sm_100a) in-tree with nvcc.  Usage: python build.py [--force] [-v] [--experiments]
+
+--experiments adds -DCIB200_EXPERIMENTS: only such a build reads the CIB200_* tuning variables from the environment
+(cib200_internal.cuh tune_env); the default build ignores the environment."""
 import os
 import subprocess
 import sys
@@ -21,7 +24,7 @@ def _deps():
     return out
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, experiments=False):
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in _deps()):
         return SO
     objs = []
@@ -30,7 +33,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC, *FLAGS, *(["-DCIB200_EXPERIMENTS"] if experiments else []), "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -51,4 +54,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--experiments" in sys.argv, verbose="-v" in sys.argv,
+                experiments="--experiments" in sys.argv))

@@ -326,15 +326,27 @@ static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq
   if (mode == CIB200_EVAL_AUTO) {
     // large point lists: bin by coefficient brick (HBM traffic ~130 B/query instead of ~18 kB for random
     // queries); small batches cannot amortise one brick load per tile and go straight to the gather kernel
-    const bool big = nq >= (1LL << 22) && nq < 0xffffffffLL;
+    const bool big = nq >= (1LL << 22);
     mode = (big && !c.grid && binned_supported(h)) ? CIB200_EVAL_BINNED : CIB200_EVAL_GATHER;
   }
   if (mode == CIB200_EVAL_BINNED) {
     if (!binned_supported(h) || c.grid) {
-      set_error("cib200_itp_eval: BINNED strategy needs a 3-D f64 b5 interpolant and a point list");
+      set_error("cib200_itp_eval: BINNED strategy needs a 3-D interpolant with one kernel on all axes and a point list");
       return CIB200_EUNSUPPORTED;
     }
-    return launch_eval_binned(h, c, out, nq, st);
+    // records carry a 32-bit query index: batches of 2^32 queries or more are walked in 2^31-query slices on the
+    // same stream (the slices share the handle's scratch, so they run back to back anyway)
+    const long long slice = 1LL << 31;
+    const size_t es = esize(h->dtype);
+    for (long long q0 = 0; q0 < nq; q0 += slice) {
+      Coords cs = c;
+      for (int d = 0; d < 3; ++d)
+        if (c.x[d]) cs.x[d] = (const char *)c.x[d] + es * (size_t)q0;
+      cs.qoff = c.qoff + q0;
+      const int rc = launch_eval_binned(h, cs, (char *)out + es * (size_t)q0, std::min(slice, nq - q0), st);
+      if (rc) return rc;
+    }
+    return CIB200_OK;
   }
   for (int i = 0; i < 3; ++i) prof_mark(h, i, st);
   const int rc = launch_eval(h, c, out, nq, st);
@@ -538,7 +550,7 @@ static int32_t itp_create_impl(const cib200_itp_desc *desc, const double *const 
   if (rc) return rc;
   // The stencil gather touches 80-byte rows at arbitrary offsets; a smaller L2->DRAM fetch granularity
   // avoids dragging in the rest of a 64/128-byte block for every partially used sector (a hint).
-  if (const char *fg = getenv("CIB200_L2_FETCH")) {
+  if (const char *fg = tune_env("CIB200_L2_FETCH")) {
     size_t g = (size_t)atoi(fg);
     if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
   }
@@ -732,9 +744,26 @@ static int32_t eval_common(cib200_itp *h, const Coords &c_in, long long nq, void
   CIB_CUDA(cudaGetDevice(&dev));
   if (dev != h->device) CIB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (memkind == CIB200_DEVICE && h->busy_valid) CIB_CUDA(cudaStreamWaitEvent(st, h->ev_busy, 0));
+  if (h->busy_valid) {
+    // an earlier DEVICE call may still be running on the caller's stream: it shares the status words and the binning
+    // scratch with this call, whatever stream this one uses (a HOST call runs on the handle's own three streams)
+    if (memkind == CIB200_DEVICE) {
+      CIB_CUDA(cudaStreamWaitEvent(st, h->ev_busy, 0));
+    } else if (h->streams[0]) {
+      for (int i = 0; i < 3; ++i) CIB_CUDA(cudaStreamWaitEvent(h->streams[i], h->ev_busy, 0));
+    } else {
+      CIB_CUDA(cudaEventSynchronize(h->ev_busy));  // the streams do not exist yet (first HOST call)
+    }
+  }
   const int32_t rc = eval_common_locked(h, c_in, nq, out, memkind, stream, first_bad, who);
   if (memkind == CIB200_DEVICE && nq > 0 && cudaEventRecord(h->ev_busy, st) == cudaSuccess) h->busy_valid = 1;
+  if (memkind == CIB200_HOST) {
+    // a HOST call returns only after its streams drained (also on the error paths: no copy into or out of the caller's
+    // buffers may still be in flight when the call returns)
+    if (rc != CIB200_OK && h->streams[0])
+      for (int i = 0; i < 3; ++i) cudaStreamSynchronize(h->streams[i]);
+    h->busy_valid = 0;
+  }
   if (dev != h->device) cudaSetDevice(dev);
   return rc;
 }
@@ -791,7 +820,7 @@ static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long n
   // chunks overlap.  Measured on B200 (512^3 b5, pinned buffers): 10^9 queries 1.99e9 evals/s with 2^26 (1.66e9 with
   // 2^24); geometric ramp-up / ramp-down schedules were tried and lost to uniform chunks (small chunks bin poorly).
   int chunk_log2 = nq >= (1LL << 28) ? 26 : (nq >= (1LL << 27) ? 25 : 24);
-  if (const char *e = getenv("CIB200_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(30, atoi(e)));
+  if (const char *e = tune_env("CIB200_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(30, atoi(e)));
   std::vector<long long> sizes;
   for (long long rem = nq; rem > 0;) {
     const long long m = std::min(rem, 1LL << chunk_log2);

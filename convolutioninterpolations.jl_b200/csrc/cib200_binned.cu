@@ -245,8 +245,7 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
       if (q < q1) {
         unsigned lc;
         const int bin_ = classify(p, g, x[u], k0, lc);
-        const unsigned slot = dbg == 2 ? (unsigned)q : (shared_cursors ? atomicAdd(hist + bin_, 1u) : atomicAdd(&sh[bin_], 1u));
-        if (dbg == 1 && slot != 0xffffffffu) continue;
+        const unsigned slot = shared_cursors ? atomicAdd(hist + bin_, 1u) : atomicAdd(&sh[bin_], 1u);
         // one 32-byte sector per query, written with two 16-byte stores; the spare word carries the cell inside the tile
         st_record(rec + slot, x[u][0], x[u][1], x[u][2], __hiloint2double((int)lc, (int)(unsigned)q));
       }
@@ -925,7 +924,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
     set_error("binned strategy: shared memory budget exceeded");
     return CIB200_EUNSUPPORTED;
   }
-  const char *no_tma = getenv("CIB200_BINNED_NO_TMA");
+  const char *no_tma = tune_env("CIB200_BINNED_NO_TMA");
   const int use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   if constexpr (E == 5) {
    if (cellsort) {
@@ -1036,23 +1035,18 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   CIB_LAUNCHED();
   bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
-  static const int scatter_mode = getenv("CIB200_DBG_SCATTER") ? atoi(getenv("CIB200_DBG_SCATTER"))
-                                  : (getenv("CIB200_SCATTER_SHARED") && getenv("CIB200_SCATTER_SHARED")[0] == '1' ? 3 : 0);
+  static const int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
   bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, scatter_mode);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 1, st);
-  if (scatter_mode == 1 || scatter_mode == 2) {  // timing experiments only: no evaluation
-    for (int i = 2; i < 5; ++i) prof_mark(h, i, st);
-    return CIB200_OK;
-  }
   // cell-sorted variant: pays one more streaming pass over the records (64 B/query) to keep each cell's stencil in
   // registers across the queries that share it - worth it from about one query per two cells upwards (measured)
   double ncell = 1.0;
   for (int d = 0; d < 3; ++d) ncell *= (double)(p.nk[d] - 2 * p.eqs[d] + 1);
   // (b5 only: a lane's share of a wider stencil, KM x W coefficients, does not fit in registers)
   bool cellsort = p.eqs[0] == 5 && (double)nq >= 0.5 * ncell && g.T * g.T * g.T <= CELLS_MAX;
-  if (const char *e = getenv("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
+  if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   switch (p.eqs[0]) {
     case 5: return launch_pass_cd<5>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
     case 6: return launch_pass_cd<6>(h, bs, sc, (double *)out, c.qoff, cellsort, st);

@@ -517,7 +517,7 @@ static int itg_launch(cib200_itg *h, const Coords &c, void *out, long long nq, c
       itg_eval_kernel<2><<<grid, bs, smem, st>>>(h->p, c, (double *)out, nq, h->d_status);
       break;
     default: {
-      static const bool thread_kernel = getenv("CIB200_ITG_THREAD3D") != nullptr;  // the v0 kernel, kept for comparison
+      static const bool thread_kernel = tune_env("CIB200_ITG_THREAD3D") != nullptr;  // the v0 kernel, kept for comparison
       if (thread_kernel || h->ntot >= (1LL << 31)) {  // the warp kernel indexes with 32-bit offsets
         if (smem > 48 * 1024) e = cudaFuncSetAttribute(itg_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) itg_eval_kernel<3><<<grid, bs, smem, st>>>(h->p, c, (double *)out, nq, h->d_status);
@@ -785,7 +785,7 @@ static int32_t itg_create_impl(const cib200_itp_desc *desc, const double *const 
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) return fail(e);
   // left_values, then the prefix arrays: scans over the axes of the mask in ascending order (constructor.jl:207-343)
-  const bool stats = getenv("CIB200_ITG_STATS") != nullptr;
+  const bool stats = tune_env("CIB200_ITG_STATS") != nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (stats) {
     cudaEventCreate(&ev0);

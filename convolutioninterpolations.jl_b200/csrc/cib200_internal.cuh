@@ -29,6 +29,16 @@ extern std::atomic<long long> g_launches;
 
 #define CIB_LAUNCHED() (cib::g_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Tuning / experiment switches read from the environment exist only in builds made with -DCIB200_EXPERIMENTS
+// (python build.py --experiments).  The shipped library ignores the environment: no variable can change which
+// kernel runs, or skip work.
+#ifdef CIB200_EXPERIMENTS
+#include <stdlib.h>
+inline const char *tune_env(const char *name) { return getenv(name); }
+#else
+inline const char *tune_env(const char *) { return nullptr; }
+#endif
+
 // ---- kernel registry ------------------------------------------------------------------------
 int kernel_eqs(int kernel);              // degree_to_equations.jl:13-25
 int kernel_poly_nodes(int kernel);       // interior points of the polynomial ghost extrapolation (4 / 6 / 8)

@@ -1208,7 +1208,7 @@ static int launch_taps(const SweepParams &sp, const GhostMats &gm, const T *in, 
 }
 
 static int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
+  const char *e = tune_env(name);
   return (e && e[0]) ? atoi(e) : dflt;
 }
 

@@ -19,7 +19,7 @@
 #include <omp.h>
 #endif
 
-#include "oracle_tables.inc"
+#include "cib200_tables.inc" /* generated reference constants, one copy in the tree (see Makefile) */
 
 #define N_PRE 101
 

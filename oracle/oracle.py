@@ -20,6 +20,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# generated reference constants (tools/gen_tables.py): one copy in the tree, shared with the library's build
+_PKG = os.path.join(os.path.dirname(_HERE), "convolutioninterpolations.jl_b200")
+_TABLES_INC = os.path.join(_PKG, "csrc", "cib200_tables.inc")
+_POLYS_JSON = os.path.join(_PKG, "kernel_polys.json")
 _LIB = None
 
 KERNEL_IDS = {"b5": 0, "b7": 1, "b9": 2, "b11": 3, "b13": 4, "a3": 5, "a4": 6, "a5": 7, "a7": 8}
@@ -39,7 +43,7 @@ class OracleError(RuntimeError):
 
 def build(force=False):
     so = os.path.join(_HERE, "libcib_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("cib_oracle.c", "cib_oracle.h", "oracle_tables.inc")]
+    srcs = [os.path.join(_HERE, f) for f in ("cib_oracle.c", "cib_oracle.h")] + [_TABLES_INC]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "libcib_oracle.so"], check=True, capture_output=True)
     return so
@@ -128,7 +132,7 @@ def generated_table(kernel, d, n_pre=LINEAR_ROWS):
         return _GENERATED[key]
     import json
     from fractions import Fraction
-    info = json.load(open(os.path.join(_HERE, "kernel_polys.json")))[kernel]
+    info = json.load(open(_POLYS_JSON))[kernel]
     eqs, Q = info["eqs"], n_pre - 1
     pieces = []
     for piece in info["pieces"]:

@@ -48,7 +48,7 @@ def test_d1_companion_is_next_derivative_table(golden_dir):
                                            ("a5", 0, (0, 33, 100)), ("a7", 0, (2, 51, 99))])
 def test_rational_polynomials_regenerate_tables(kernel, d, rows, golden_dir):
     root = os.path.dirname(os.path.dirname(golden_dir))
-    polys = json.load(open(os.path.join(root, "oracle", "kernel_polys.json")))[kernel]
+    polys = json.load(open(os.path.join(root, "convolutioninterpolations.jl_b200", "kernel_polys.json")))[kernel]
     eqs = polys["eqs"]
     pieces = [[Fraction(c) for c in p] for p in polys["pieces"]]
     lit = _golden_tables(golden_dir)[f"KERNEL_PRE_{kernel}_d{d}"]

@@ -20,11 +20,9 @@ What it does
      (src/precomputed_kernels/kernel_b*.jl) and asserts BIT equality
      (this is the known-answer test that pins table layout + kernel maths),
   4. writes
-       oracle/kernel_polys.json                  exact rationals (oracle input)
        tests/golden/shipped_tables.npz           the shipped literals (golden KAT)
        tests/golden/ghost_matrices.json          the integer ghost matrices (golden KAT)
        convolutioninterpolations.jl_b200/csrc/cib200_tables.inc   C hex-float arrays
-       oracle/oracle_tables.inc                  same data for the C oracle
 
 Nothing here is imported at run time by the product, the tests or the bench.
 """
@@ -230,14 +228,11 @@ def main():
             index_rows.append((kernel, eqs, d, cname))
     inc.append("")
     text = "\n".join(inc) + "\n"
-    for rel in ("convolutioninterpolations.jl_b200/csrc/cib200_tables.inc",
-                "oracle/oracle_tables.inc"):
-        p = os.path.join(ROOT, rel)
-        os.makedirs(os.path.dirname(p), exist_ok=True)
-        open(p, "w").write(text)
-    os.makedirs(os.path.join(ROOT, "oracle"), exist_ok=True)
-    json.dump(polys_json, open(os.path.join(ROOT, "oracle/kernel_polys.json"), "w"), indent=1)
-    # the product's own copy: the host mirror regenerates the >= 10 000-row tables of :linear axes from it (tables.py)
+    # ONE copy of each generated artefact: the library compiles the .inc, the oracle's Makefile includes the same
+    # file, and the host mirror (tables.py) and the oracle both read the one kernel_polys.json
+    p = os.path.join(ROOT, "convolutioninterpolations.jl_b200/csrc/cib200_tables.inc")
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    open(p, "w").write(text)
     json.dump(polys_json, open(os.path.join(ROOT, "convolutioninterpolations.jl_b200/kernel_polys.json"), "w"), indent=1)
     os.makedirs(os.path.join(ROOT, "tests/golden"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "tests/golden/shipped_tables.npz"), **golden)
