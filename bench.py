@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     ap.add_argument("--no-secondary", action="store_true", help="skip the resample / smooth side measurements")
     return ap.parse_args()
 
@@ -133,6 +134,20 @@ def ncu_traffic_per_eval():
         return json.load(open(p))
     except Exception:
         return None
+
+
+def julia_probe():
+    """Is the real reference runnable on this box?  (It never was: the image has no Julia.)  When it is, the parity
+    recipe is tools/julia_cases.py write -> julia tools/julia_dump.jl -> tools/julia_cases.py check --gpu."""
+    import shutil
+    exe = shutil.which("julia")
+    if not exe:
+        return {"available": False, "recipe": "tools/julia_cases.py + tools/julia_dump.jl"}
+    try:
+        ver = subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=60).stdout.strip()
+    except Exception as e:  # noqa: BLE001
+        ver = f"probe failed: {e}"
+    return {"available": True, "version": ver, "recipe": "tools/julia_cases.py + tools/julia_dump.jl"}
 
 
 def cpu_baseline(seconds, grid_n=96, threads=None):
@@ -390,8 +405,55 @@ def main():
     dev_max = float((chk - out[sub]).abs().max())
     assert dev_max <= 1e-13 * vmax, f"subsample re-evaluation differs from the timed result by {dev_max}"
 
+    # ---- parity of the TIMED result with the CPU oracle (the checker, never the thing measured): a strided
+    # subsample of >= 2^20 of the step's results on the same 512^3 grid, oracle built independently from the values
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import oracle as O
+        O.set_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        knots_p, vals_p = make_grid(args.grid)
+        oitp = O.convolution_interpolation(knots_p, vals_p, kernel="b5", bc="poly")
+        del vals_p
+        stride = max(1, nq // (1 << 20))
+        psub = slice(0, nq, stride)
+        qh = [x[psub].cpu().numpy() for x in xs]
+        ref = oitp.eval(*qh)
+        got = out[psub].cpu().numpy()
+        S = float(np.abs(oitp.coefs).max())
+        perr = np.abs(got - ref) / np.maximum(np.abs(ref), S)
+        parity = {"max_rel_err": float(perr.max()), "n": int(len(ref)), "tol": 1e-12, "against": "oracle (port)",
+                  "what": f"every {stride}-th result of the last timed step vs oracle/cib_oracle.c on the same "
+                          f"{args.grid}^3 grid; relative to max(|ref|, max|coefs|)",
+                  "seconds": time.perf_counter() - t0}
+        assert parity["max_rel_err"] <= 1e-12, f"timed result differs from the oracle: {parity}"
+        del oitp, qh, ref, got
+
+    # ---- strong scaling: the literal BASELINE config 5 - 10^9 queries IN TOTAL, split over the ranks ----------
+    strong = None
+    if world > 1:
+        nqs = nq // world
+        xs_s = [x[:nqs] for x in xs]
+        out_s = out[:nqs]
+        for _ in range(2):
+            itp.eval(*xs_s, out=out_s)
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        evs[0].record()
+        for _ in range(args.steps):
+            itp.eval(*xs_s, out=out_s)
+        evs[1].record()
+        barrier()
+        ms_s = ci.sharding.max_over_ranks_ms(evs[0].elapsed_time(evs[1]), world, dev)
+        strong = {"value": world * nqs * args.steps / (ms_s * 1e-3), "unit": UNIT, "queries_total_per_step": world * nqs,
+                  "queries_per_gpu_per_step": nqs, "ms_per_step": ms_s / args.steps,
+                  "queries_per_cell_per_gpu": nqs / float(args.grid - 1) ** 3,
+                  "note": "fixed total work split over the ranks (scaling=strong); the per-GPU batch is sparser "
+                          "(fewer queries per cell), which costs the register-resident cell runs some reuse"}
+
     # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region -----------------------
     e2e = None
+    e2e_pageable = None
     if not args.no_e2e:
         if args.e2e_nq > 0:
             nqe = int(min(args.e2e_nq, nq))
@@ -422,6 +484,29 @@ def main():
                "h2d_bytes_per_step": 3 * 8 * nqe, "d2h_bytes_per_step": 8 * nqe, "queries_per_step": nqe,
                "note": "cib200_itp_eval with pinned host buffers: 2^26-query chunks, H2D / kernels / D2H on three streams over a 3-buffer ring"}
         del hx, hout
+        # the same call with PAGEABLE buffers (plain numpy arrays: what a caller that never pins hands over); bounded
+        # to 2.5e8 queries (8 GB) per step
+        if rank == 0 or world > 1:
+            nqp = int(min(nqe, 2.5e8))
+            px = [np.empty(nqp) for _ in range(3)]
+            for i in range(3):
+                px[i][:] = xs[i][:nqp].cpu().numpy()
+            pout = np.empty(nqp)
+            itp.eval(*px, out=pout)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(1, min(args.steps, 2))):
+                itp.eval(*px, out=pout)
+            torch.cuda.synchronize()
+            dtp = (time.perf_counter() - t0) / max(1, min(args.steps, 2))
+            ttp = torch.tensor([dtp], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ttp, op=dist.ReduceOp.MAX)
+            assert float(np.abs(pout - out[:nqp].cpu().numpy()).max()) <= 1e-13 * vmax
+            e2e_pageable = {"value": world * nqp / float(ttp.item()), "unit": UNIT, "queries_per_step": nqp,
+                            "h2d_bytes_per_step": 3 * 8 * nqp, "d2h_bytes_per_step": 8 * nqp,
+                            "note": "cib200_itp_eval with pageable host buffers (numpy arrays, nothing registered)"}
+            del px, pout
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -457,7 +542,8 @@ def main():
                            "numa_node_of_rank0": numa,
                            "l2": "inputs (32 B/query x nq) and the 1.1 GB grid exceed the 126 MB L2; no flush needed",
                            "grid_build_s": build_s, "grid_build_device_ms": build_dev_ms},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pageable": e2e_pageable, "parity": parity,
+                "strong_scaling": strong, "julia": julia_probe(), "gpu_launches": launches, "clocks": clocks,
                 "step_ms": step_ms, "secondary": None if (args.no_secondary or world > 1) else secondary_sweeps(peak)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,14 +1,18 @@
 # CIB200Glue.jl - the thin `ccall` glue a maintainer adds to ConvolutionInterpolations.jl to route the
-# uniform-grid hot path to libcib200.so (C-ABI: include/cib200.h).  NOT executable in this repository's
-# build container (Julia is not installed there); kept in sync with the header by hand and exercised through
-# the identical ctypes binding in convolutioninterpolations.jl_b200/_lib.py.
+# uniform-grid hot path to libcib200.so (C-ABI: include/cib200.h).  UNTESTED: Julia is not installed in this
+# repository's build container, so this file has never been executed.  What is checked mechanically
+# (tests/test_glue_consistency.py): every `ccall` names an exported symbol of include/cib200.h and passes the
+# prototype's argument count and C types, the ItpDesc mirror has the fields of cib200_itp_desc in order, and every
+# reference name used below is imported and exists in /root/reference/src.  The same ABI is exercised end to end by
+# the ctypes binding in convolutioninterpolations.jl_b200/_lib.py.
 #
 # Nothing of the public API changes: the methods below are added on the reference's own types.
 #   include("CIB200Glue.jl") at the end of src/ConvolutionInterpolations.jl, `using .CIB200Glue`.
 module CIB200Glue
 
 using ..ConvolutionInterpolations: ConvolutionExtrapolation, FastConvolutionInterpolation,
-    HigherOrderKernel, HigherOrderMixedKernel, Throw, Flat, Line, DerivativeOrder
+    HigherOrderKernel, HigherOrderMixedKernel, Throw, Flat, Line, DerivativeOrder,
+    FastIntegralOrder, FastMixedIntegralOrder, get_precomputed_kernel_and_range
 
 const LIB = get(ENV, "CIB200_LIB", "libcib200.so")
 const KERNEL_ID = Dict(:b5 => 0, :b7 => 1, :b9 => 2, :b11 => 3, :b13 => 4, :a3 => 5, :a4 => 6, :a5 => 7, :a7 => 8)
@@ -110,8 +114,27 @@ end
 Handle(p::Ptr{Cvoid}) = Handle(p, Ptr{Cvoid}[p])
 # GPUs to use from this process: ENV["CIB200_DEVICES"] = "0,1,2,3" (default: the current device only)
 devices() = haskey(ENV, "CIB200_DEVICES") ? parse.(Int32, split(ENV["CIB200_DEVICES"], ",")) : Int32[]
-const HANDLES = WeakKeyDict{Any,Handle}()
+# ConvolutionExtrapolation and FastConvolutionInterpolation are immutable structs (no finalizers, no WeakKeyDict keys):
+# the cache is keyed on the identity of the one mutable object an interpolant owns for its whole life, its coefficient
+# array, plus the extrapolation mode; a finalizer on that array drops the entry and frees the device memory.
+const HANDLES = Dict{Tuple{UInt,Int32},Handle}()
 const HANDLES_LOCK = ReentrantLock()
+function release_handles(coefs)
+    # finalizers must not block: if the lock is busy, try again at the next collection (Julia manual, "finalizer")
+    if trylock(HANDLES_LOCK)
+        try
+            id = objectid(coefs)
+            for key in [k for k in keys(HANDLES) if k[1] == id]
+                finalize(pop!(HANDLES, key))
+            end
+        finally
+            unlock(HANDLES_LOCK)
+        end
+    else
+        finalizer(release_handles, coefs)
+    end
+    return nothing
+end
 
 extrap_id(::Throw) = Int32(0)
 extrap_id(::Flat) = Int32(1)
@@ -119,7 +142,9 @@ extrap_id(::Line) = Int32(2)
 
 function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
     lock(HANDLES_LOCK) do
-        get!(HANDLES, etp) do
+        key = (objectid(etp.itp.coefs), extrap_id(etp.et))
+        fresh = !any(k -> k[1] == key[1], keys(HANDLES))
+        hd = get!(HANDLES, key) do
             itp = etp.itp
             ks = kernel_symbols(itp.kernel_sym)
             dv = derivative_tuple(itp)
@@ -181,7 +206,26 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
             finalizer(x -> foreach(p -> ccall((:cib200_itp_destroy, LIB), Int32, (Ptr{Cvoid},), p), x.replicas), h)
             h
         end
+        fresh && finalizer(release_handles, etp.itp.coefs)
+        hd
     end
+end
+
+# ---- query / result buffers -------------------------------------------------------------------------
+# A coordinate vector that already is a dense Vector{T} is passed as it lies in memory (no copy); anything else
+# (ranges, views, other element types) is materialised once.  The library moves pageable host memory through its own
+# pinned staging ring (cib200_itp_eval, memkind HOST), so nothing has to be page-locked for a one-off call.  Buffers
+# that are re-used across many calls can be page-locked once with `pin!` (cib200_host_register: the copies then run
+# straight from the caller's memory at PCIe rate); `unpin!` before the array is resized or dropped.
+as_dense(::Type{T}, x::Vector{T}) where {T} = x
+as_dense(::Type{T}, x::AbstractVector) where {T} = Vector{T}(x)
+function pin!(x::Array)
+    GC.@preserve x check(ccall((:cib200_host_register, LIB), Int32, (Ptr{Cvoid}, Csize_t), x, sizeof(x)))
+    return x
+end
+function unpin!(x::Array)
+    GC.@preserve x check(ccall((:cib200_host_unregister, LIB), Int32, (Ptr{Cvoid},), x))
+    return x
 end
 
 # ---- itp.(xs...) : replaces the per-element loop over extrapolation_operator.jl:31-63 ---------------
@@ -189,7 +233,7 @@ function Base.Broadcast.broadcasted(etp::ConvolutionExtrapolation{T,N}, xs::Vara
     accelerated(etp.itp) || return Base.Broadcast.broadcasted(Base.Broadcast.DefaultArrayStyle{1}(), etp, xs...)
     nq = length(xs[1])
     all(x -> length(x) == nq, xs) || throw(DimensionMismatch("coordinate vectors must have equal length"))
-    xq = ntuple(d -> Vector{T}(xs[d]), N)
+    xq = ntuple(d -> as_dense(T, xs[d]), N)
     out = Vector{T}(undef, nq)
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
     bad = Ref{Int64}(-1)
@@ -220,7 +264,7 @@ end
 # ---- itp(xs, ys, zs) with vectors: Cartesian product, extrapolation_operator.jl:66-99 ----------------
 function (etp::ConvolutionExtrapolation{T,N})(xs::Vararg{AbstractVector{<:Real},N}) where {T,N}
     accelerated(etp.itp) || return invoke(etp, Tuple{Vararg{AbstractArray,N}}, xs...)
-    xq = ntuple(d -> Vector{T}(xs[d]), N)
+    xq = ntuple(d -> as_dense(T, xs[d]), N)
     n = Int64[length(x) for x in xq]
     out = zeros(T, n...)
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]

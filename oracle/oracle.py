@@ -552,3 +552,92 @@ def convolution_smooth(knots, values, B):
 def theta(B, terms):
     q = math.exp(-B)
     return 1.0 + sum(2 * q ** (n * n) for n in range(1, terms + 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# SECOND oracle: the reference's DIRECT evaluators.  They share nothing with the fast path but
+# the ghost-padded coefficient grid: no tables, no Hermite blending - every stencil weight is the kernel polynomial
+# itself, evaluated at the query by Horner's rule.  The reference asserts fast ~ direct to 1e-6
+# (test/test_constructors.jl:4-49); the table + cubic-Hermite scheme is good to ~1e-9, which is what pins the fast
+# restatement (and the CUDA path) against an independent statement of the same interpolant.
+# ---------------------------------------------------------------------------------------------
+_POLY_CACHE = {}
+
+
+def kernel_poly_coefs(kernel, d):
+    """Float64 coefficient vectors of K^(d) per piece, as the reference stores them: the exact rational
+    k (k-1) ... (k-d+1) c_k (convolution_kernel_b5.jl:9-60: `b5_coefs_d1 = [0//1*c0, 1//1*c1, ...]`), converted once by
+    T(coef[i]) inside horner (horner.jl:44-52).  The d leading (zero) coefficients are kept: Horner skips them."""
+    key = (kernel, d)
+    if key not in _POLY_CACHE:
+        import json
+        from fractions import Fraction
+        info = json.load(open(_POLYS_JSON))[kernel]
+        out = []
+        for piece in info["pieces"]:
+            c = [Fraction(x) for x in piece]
+            dc = [c[k] * (math.factorial(k) // math.factorial(k - d)) if k >= d else Fraction(0) for k in range(len(c))]
+            out.append(np.array([float(x) for x in dc]))
+        _POLY_CACHE[key] = (info["eqs"], out)
+    return _POLY_CACHE[key]
+
+
+def kernel_value(kernel, d, s):
+    """(::ConvolutionKernel{kernel, DO})(s), e.g. convolution_kernel_b5.jl:62-92: piece by floor(|s|), Horner from the
+    highest coefficient down to index 1 + DO (horner.jl:48-50), times sign(s) for odd DO, zero for |s| >= eqs."""
+    eqs, pieces = kernel_poly_coefs(kernel, d)
+    s = np.asarray(s, dtype=np.float64)
+    sa = np.abs(s)
+    out = np.zeros_like(sa)
+    piece = np.floor(sa).astype(np.int64)
+    for p, coef in enumerate(pieces):
+        m = piece == p
+        if not m.any():
+            continue
+        x = sa[m]
+        r = np.full_like(x, coef[-1])
+        for i in range(len(coef) - 2, d - 1, -1):
+            r = r * x + coef[i]
+        out[m] = r
+    if d % 2 == 1:
+        out = out * np.sign(s)
+    return out
+
+
+def direct_eval(itp, *xs):
+    """The direct evaluators convolution_kernel_interpolation_eager_{1d,2d,3d}.jl (3-D: :1-29) on the ghost-padded grid
+    of `itp` (an Interpolant): result = sum_{l,m,n} coefs[i+l, j+m, k+n] K1(s1) K2(s2) K3(s3), s_d = (x_d - knots_d[.]) / h_d,
+    times prod_d 1 / h_d^DO_d.  In-domain queries only (the extrapolation wrapper is the fast path's, not restated here)."""
+    nd = itp.ndim
+    assert 1 <= nd <= 3 and len(xs) == nd
+    xs = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in xs]
+    nq = xs[0].size
+    idx, wts = [], []
+    for d in range(nd):
+        k, h, e = itp.knots[d], itp.h[d], itp.eqs[d]
+        i_float = (xs[d] - k[0]) / h + 1.0
+        i = np.clip(np.floor(i_float).astype(np.int64), e, len(k) - e)  # 1-based
+        taps = np.arange(-(e - 1), e + 1)
+        pos = (i[:, None] - 1) + taps[None, :]  # 0-based indices of the 2 eqs taps
+        s = (xs[d][:, None] - k[pos]) / h
+        idx.append(pos)
+        wts.append(kernel_value(itp.kernels[d], itp.derivs[d], s))
+    c = itp.coefs
+    res = np.zeros(nq)
+    if nd == 1:
+        for l in range(wts[0].shape[1]):
+            res += c[idx[0][:, l]] * wts[0][:, l]
+    elif nd == 2:
+        for l in range(wts[0].shape[1]):
+            for m in range(wts[1].shape[1]):
+                res += c[idx[0][:, l], idx[1][:, m]] * wts[0][:, l] * wts[1][:, m]
+    else:
+        for l in range(wts[0].shape[1]):
+            for m in range(wts[1].shape[1]):
+                wlm = wts[0][:, l] * wts[1][:, m]
+                for n in range(wts[2].shape[1]):
+                    res += c[idx[0][:, l], idx[1][:, m], idx[2][:, n]] * wlm * wts[2][:, n]
+    scale = 1.0
+    for d in range(nd):
+        scale *= 1.0 / itp.h[d] ** itp.derivs[d]
+    return res * scale

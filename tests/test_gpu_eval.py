@@ -6,6 +6,8 @@ results of sin-product fixtures cross zero.  For Line
 reference formula f_b + (f_b - f_in)/eps * dist amplifies ANY rounding difference by dist/eps, so S is scaled
 by (1 + 2 dist/eps) for those queries; the amplification is a property of the formula, not of either side.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -65,11 +67,13 @@ def test_c1_1d_b5_n1000_1e6_queries(ci, oracle):
 
 
 def test_c2_2d_b5_derivative_line_extrapolation(ci, oracle):
-    """BASELINE config 2 (200^2, derivative=(1,0) -> per-dim path, Line extrapolation), 10^6 of the 10^7 queries."""
+    """BASELINE config 2 at FULL size (200^2, derivative=(1,0) -> per-dim path, Line extrapolation, all 10^7 queries
+    against the oracle)."""
     rng = np.random.default_rng(0xC1B200 + 2)
     x = np.linspace(0, 2 * np.pi, 200)
     v = np.sin(x)[:, None] * np.cos(x)[None, :] + 0.05 * rng.uniform(-1, 1, (200, 200))
-    q = rng.uniform(-0.1 * 2 * np.pi, 1.1 * 2 * np.pi, (2, 1_000_000))
+    oracle.set_threads(os.cpu_count() or 1)
+    q = rng.uniform(-0.1 * 2 * np.pi, 1.1 * 2 * np.pi, (2, 10_000_000))
     got, ref, g, o = _compare(ci, oracle, (x, x), v, (q[0], q[1]), kernel="b5", derivative=(1, 0), extrap="line")
     assert o.perdim and g.itp.perdim
     outside = (q < 0).any(axis=0) | (q > 2 * np.pi).any(axis=0)
@@ -88,6 +92,67 @@ def test_c5_small_3d_b5(ci, oracle, extrap):
     lo, hi = (0.0, 1.0) if extrap == "throw" else (-0.08, 1.08)
     q = rng.uniform(lo, hi, (3, 100_003))  # ragged: not a multiple of the 32-query warp tile
     _compare(ci, oracle, knots, v, tuple(q), kernel="b5", extrap=extrap)
+
+
+def test_c5_full_grid_512_cube_2e26_queries_against_the_oracle(ci, oracle):
+    """BASELINE config 5 on its REAL grid: 512^3 :b5, 2^26 uniformly random queries through AUTO (tile binning + cell
+    sort + register-resident stencils: 32 768 tiles, u32 record offsets, 16 384-record work items), device-resident;
+    a strided subsample of 2^20 results against the oracle on the same grid, and every result finite.  A second batch
+    of 2^22 + 5 queries takes the binned kernel without the cell sort (below 0.5 query per cell)."""
+    import torch
+    rng = np.random.default_rng(0xC1B200 + 5)
+    n = 512
+    g = np.linspace(0.0, 1.0, n)
+    a = np.sin(2 * np.pi * g) + 0.5 * np.cos(6 * np.pi * g + 0.3)
+    b = np.cos(2 * np.pi * g) + 0.3 * np.sin(10 * np.pi * g)
+    c = np.sin(4 * np.pi * g + 1.0)
+    v = np.empty((n, n, n), order="F")
+    for k in range(n):
+        v[:, :, k] = a[:, None] * b[None, :] * c[k] + 0.01 * rng.uniform(-1, 1, (n, n))
+    oracle.set_threads(os.cpu_count() or 1)
+    o = oracle.convolution_interpolation((g, g, g), v, kernel="b5", bc="poly")
+    itp = ci.convolution_interpolation((g, g, g), v, kernel="b5", bc="poly")
+    assert np.array_equal(itp.itp.coefs, o.coefs) or np.abs(itp.itp.coefs - o.coefs).max() <= 1e-13 * np.abs(o.coefs).max()
+    S = _scale(o)
+    for nq, stride in ((1 << 26, 64), ((1 << 22) + 5, 4)):
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(nq)
+        xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in range(3)]
+        out = itp.eval(*xs)
+        assert bool(torch.isfinite(out).all())
+        sub = slice(0, nq, stride)
+        q = [x[sub].cpu().numpy() for x in xs]
+        ref = o.eval(*q)
+        err = rel_err(out[sub].cpu().numpy(), ref, S)
+        assert err.max() <= TOL64, (nq, err.max(), int(err.argmax()))
+        assert len(ref) >= 1 << 20
+        del xs, out
+
+
+@pytest.mark.parametrize("kernel,deriv", [("b5", 0), ("b5", (1, 0, 2)), ("b7", (0, 3, 1)), ("b13", 0), ("b13", (1, 0, 0)), ("a4", 0)])
+def test_cuda_path_agrees_with_the_direct_evaluator(ci, oracle, kernel, deriv):
+    """Second, independent oracle: the reference's DIRECT evaluators (kernel polynomials by Horner, no tables;
+    oracle.direct_eval, convolution_kernel_interpolation_eager_3d.jl:1-29).  The reference asserts fast ~ direct to 1e-6
+    (test/test_constructors.jl:21,45); the CUDA library is held to the same bound against the direct statement."""
+    rng = np.random.default_rng(7)
+    g = np.linspace(0.0, 2 * np.pi, 24)
+    v = np.sin(g)[:, None, None] * np.cos(g)[None, :, None] * np.sin(g + 0.3)[None, None, :]
+    q = rng.uniform(0.0, 2 * np.pi, (3, 4000))
+    o = oracle.Interpolant((g, g, g), v, kernel=kernel, derivative=deriv, bc="detect")
+    got = ci.convolution_interpolation((g, g, g), v, kernel=kernel, derivative=deriv, bc="detect").eval(*q)
+    direct = oracle.direct_eval(o, *q)
+    assert np.abs(got - direct).max() <= 1e-6 * _scale(o)
+    # 1-D and 2-D, every kernel of the reference's test loop (test_constructors.jl:9)
+    x = np.linspace(0.0, 2 * np.pi, 30)
+    q1 = rng.uniform(0.0, 2 * np.pi, 3000)
+    o1 = oracle.Interpolant((x,), np.sin(x), kernel=kernel)
+    g1 = ci.convolution_interpolation(x, np.sin(x), kernel=kernel).eval(q1)
+    assert np.abs(g1 - oracle.direct_eval(o1, q1)).max() <= 1e-6
+    v2 = np.sin(x)[:, None] * np.cos(x)[None, :]
+    o2 = oracle.Interpolant((x, x), v2, kernel=kernel)
+    q2 = rng.uniform(0.0, 2 * np.pi, (2, 3000))
+    g2 = ci.convolution_interpolation((x, x), v2, kernel=kernel).eval(*q2)
+    assert np.abs(g2 - oracle.direct_eval(o2, *q2)).max() <= 1e-6
 
 
 @pytest.mark.parametrize("kernel,deriv,bc", [("b13", (1, 0, 0), "detect"), ("b13", 0, "poly"), ("b7", (0, 2, 1), "linear"),
