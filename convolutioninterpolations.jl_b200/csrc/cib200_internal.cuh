@@ -144,6 +144,9 @@ int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *
                    const double *const *gen_tables, const int *gen_rows, cudaStream_t st);
 int sweep_build_coefs(int ndim, int dtype, const long long *n, const void *d_values, const double *h, const int *kernel,
                       const int *bcl, const int *bcr, void *d_coefs, cudaStream_t st);
+// persistent TMA-fed FIR pass of convolution_smooth (cib200_smooth.cu); -1: the pass does not qualify
+int smooth_pipe_pass(const double *in, double *out, long long inner, long long n, long long outer, int E,
+                     const double *kw, cudaStream_t st);
 int sweep_smooth(int ndim, int dtype, const long long *n, const void *d_in, void *d_out, const double *h,
                  double B, cudaStream_t st);
 }  // namespace cib

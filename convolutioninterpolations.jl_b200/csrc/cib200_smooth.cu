@@ -1,0 +1,424 @@
+// cib200_smooth.cu - convolution_smooth, Float64, as a chain of persistent TMA-fed FIR passes.
+//
+// Replaces the per-line loop of convolution_smooth (convolution/convolution_gaussian_smoothing.jl:70-124) and the
+// ghost fill it calls (fill_ghost_points_gaussian!, convolution_coefs/create_convolutional_coefs.jl:443-494) for the
+// shapes BASELINE config 4 names; every other case stays on sweep_pipe_kernel / sweep_kernel (cib200_sweep.cu).
+//
+// One pass = one axis; the array is viewed as [inner][n][outer].  What bounds a pass is the FP64 pipe (2E+1 DFMAs per
+// point: E = 24 for B = 0.05), so the design removes every FP64 instruction and every stall that is not one of those:
+//
+//  * zero padding instead of ghost rows.  The reference extends a line by E ghosts per side (an affine extrapolation
+//    a + b (1 - k) of the mean-centred line, least-squares fit over its first / last points) and convolves the
+//    extended line.  A ghost's contribution to output i is linear in (a, b):  out[i] += a S0[i] + b S1[i] with
+//    S0[i] = sum_k kw[.], S1[i] = sum_k kw[.] (1 - k) over the ghosts output i can see - two host-computed tables of
+//    E - 1 entries (the reference's slot quirk, SURVEY.md 3.5, is in the tables: ghost k sits k + 1 slots outside, the
+//    slot next to the line stays 0).  The FIR then runs over the line padded with ZEROS, which the TMA unit produces for
+//    free (box coordinates start at -E, out-of-bounds elements are zero-filled): no ring clearing, no ghost stores,
+//    and every window row that lies outside the line is skipped as a whole (19 % of the DFMAs at n = 64, 31 % at 40).
+//  * a "stats" stage (lane = line) computes the line mean and the two fits: n + 64 FP64 instructions per line instead
+//    of ~540 for mean (twice) + fit + 46 ghost evaluations.
+//  * consumers pull (tile, block of 8 outputs) items from a shared counter, so clipped boundary blocks and interior
+//    blocks balance by themselves; taps are literal offsets into the kernel-parameter bank (DFMA R, R, c[0][imm], R).
+//  * axis >= 1: one 3-D TMA box {BI, n + 2E + 7, 32 / BI} per tile, lane = (inner index, outer index); BI = 8 keeps
+//    all 32 lanes busy when `inner` is 40.  axis 0: one 2-D box of 32 lines, line-major with pitch P = 2 (mod 4); a
+//    lane = line reads its window two elements at a time (LDS.128: 8 lanes x 16 bytes per wavefront, and P / 2 odd
+//    puts the 8 lanes into 8 distinct 16-byte banks: conflict-free without padding tricks; a TMA box can only start
+//    on a 16-byte boundary, so odd column shifts are not available).  Results go back through a per-warp transposing
+//    stage so that global stores are full 32-byte sectors.
+//  * passes are chained with programmatic dependent launch: the next pass's prologue overlaps this pass's tail.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "cib200_pipe.cuh"
+
+namespace cib {
+using namespace pipe;
+
+struct SmoothPipeParams {
+  long long inner, outer, ntiles;
+  int n, nblk;
+  int H;            // axis >= 1: rows of a tile buffer; axis 0: pitch P of a line
+  int tiles_inner;  // axis >= 1: tiles along `inner`
+  int nb, nstats, ncons;
+  int nfit;
+  double nf, sx, denom;
+  double kw[64];          // normalised Gaussian taps, l = -E..E
+  double s0[32], s1[32];  // ghost tables, index = distance of the output from the boundary (0..E-2)
+};
+
+static constexpr int SP_R = 8;  // outputs per block
+
+
+template <int TAPS, int ROW>
+__device__ __forceinline__ void fir_block8(const double *__restrict__ p, int clo, int chi, const SmoothPipeParams &sp,
+                                           double (&acc)[SP_R]) {
+  constexpr int W = TAPS + SP_R - 1, NCH = (W + 7) / 8;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c >= clo && c < chi) {  // warp-uniform: chunks of 8 window rows that lie inside the line
+      double x[8];
+      if (ROW == 1) {  // axis 0: the window is contiguous and 16-byte aligned (W is even)
+#pragma unroll
+        for (int i = 0; i < 8; i += 2)
+          if (8 * c + i < W) {
+            const double2 v = *(const double2 *)(p + 8 * c + i);
+            x[i] = v.x;
+            x[i + 1] = v.y;
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (8 * c + i < W) x[i] = p[(8 * c + i) * ROW];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = 8 * c + i;
+        if (j < W) {
+#pragma unroll
+          for (int r = 0; r < SP_R; ++r) {
+            const int l = j - r;
+            if (l >= 0 && l < TAPS) acc[r] = fma(x[i], sp.kw[l], acc[r]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// mean of a line in the association of line_mean (cib200_sweep.cu): 8 interleaved partial sums, pairwise combine
+template <int ROW>
+__device__ __forceinline__ double line_mean_rows(const double *__restrict__ x0, int n) {
+  double s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.0;
+  int j = 0;
+  for (; j + 8 <= n; j += 8) {
+    double v[8];
+    if (ROW == 1) {  // axis 0: 16-byte loads (x0 is 16-byte aligned: E and the pitch are even)
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const double2 t = *(const double2 *)(x0 + j + i);
+        v[i] = t.x;
+        v[i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = x0[(j + i) * ROW];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = __dadd_rn(s[i], v[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (j + i < n) s[i] = __dadd_rn(s[i], x0[(j + i) * ROW]);
+  const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
+                               __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
+  return __ddiv_rn(sum, (double)n);
+}
+
+// least-squares line through the first nfit mean-centred points counted from one end (fill_ghost_points_gaussian!,
+// create_convolutional_coefs.jl:455-478): x_k = k = 1..nfit, returns the centred intercept a and the slope b
+template <int ROW>
+__device__ __forceinline__ double2 fit_side(const double *__restrict__ q, int step_sign, double mean, const SmoothPipeParams &sp) {
+  double sy = 0.0, sxy = 0.0, xk = 1.0;
+  for (int k = 0; k < sp.nfit; ++k) {
+    const double yk = __dsub_rn(q[step_sign * k * ROW], mean);
+    sy = __dadd_rn(sy, yk);
+    sxy = __dadd_rn(sxy, __dmul_rn(xk, yk));
+    xk += 1.0;
+  }
+  const double b = __ddiv_rn(__dsub_rn(__dmul_rn(sp.nf, sxy), __dmul_rn(sp.sx, sy)), sp.denom);
+  const double a = __ddiv_rn(__dsub_rn(sy, __dmul_rn(b, sp.sx)), sp.nf);
+  return make_double2(a, b);
+}
+
+// BI: lanes along `inner` in a tile of an axis >= 1 pass (32 or 8); BI = 0: axis 0
+template <int TAPS, int BI>
+__global__ void __launch_bounds__(640, 1)
+    smooth_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SmoothPipeParams sp,
+                       double *__restrict__ out) {
+  constexpr int E = (TAPS - 1) / 2;
+  constexpr bool AXIS0 = BI == 0;
+  constexpr int ROW = AXIS0 ? 1 : BI;
+  constexpr int BO = AXIS0 ? 1 : 32 / (BI > 0 ? BI : 32);
+  constexpr int W = TAPS + SP_R - 1;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int NB = sp.nb, n = sp.n, nblk = sp.nblk;
+  const int TILE = 32 * sp.H;  // doubles
+  double *tiles = (double *)smem_raw;
+  double *lpar = tiles + (size_t)NB * TILE;  // [NB][32][4]: aL bL aR bR of every line of the tile
+  double *stab = lpar + NB * 128;            // s0[32] s1[32]
+  double *stage = stab + 64;                 // axis 0: [ncons][32 * 9] transposing store stage
+  unsigned long long *bars = (unsigned long long *)(stage + (AXIS0 ? sp.ncons * 288 : 0));
+  unsigned long long *loaded = bars, *ready = bars + NB, *empty = bars + 2 * NB;
+  unsigned *counter = (unsigned *)(bars + 3 * NB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 64) stab[tid] = tid < 32 ? sp.s0[tid] : sp.s1[tid - 32];
+  if (tid == 0) {
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(loaded + b, 1);
+      mbar_init(ready + b, 1);
+      mbar_init(empty + b, (unsigned)nblk);
+    }
+    *counter = 0;
+    mbar_init_fence();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  const long long tstep = gridDim.x;
+  const unsigned my_tiles = blockIdx.x < sp.ntiles ? (unsigned)((sp.ntiles - blockIdx.x + tstep - 1) / tstep) : 0u;
+
+  // position of this lane's line in a tile buffer and in the array
+  int lbase;             // doubles from the start of the tile buffer to this line's row -E (axis 0: column -E)
+  long long gline_i = 0, gline_o = 0;
+  if (AXIS0) {
+    lbase = lane * sp.H;
+    gline_o = lane;  // + 32 t
+  } else {
+    const int i = lane % (BI > 0 ? BI : 32), oo = lane / (BI > 0 ? BI : 32);
+    lbase = oo * sp.H * ROW + i;
+    gline_i = i;   // + tile_i BI
+    gline_o = oo;  // + tile_o BO
+  }
+
+  if (warp == 0) {
+    // ------------------------------- producer: one elected lane feeds the ring with TMA boxes -----------------
+    if (lane == 0) {
+      pdl_wait();  // the input of this pass is the output of the previous launch
+      for (unsigned seq = 0; seq < my_tiles; ++seq) {
+        const int b = seq % NB;
+        const unsigned rev = seq / NB;
+        const long long t = blockIdx.x + (long long)seq * tstep;
+        if (rev > 0) mbar_wait(empty + b, (rev - 1) & 1u, 1000 + (int)seq);
+        fence_async_proxy();
+        mbar_expect_tx(loaded + b, (unsigned)(TILE * 8));
+        double *dst = tiles + (size_t)b * TILE;
+        if (AXIS0) {
+          tma_load_2d(dst, &tmap, -E, (int)(t * 32), loaded + b);
+        } else {
+          const int tile_i = (int)(t % sp.tiles_inner), tile_o = (int)(t / sp.tiles_inner);
+          tma_load_3d(dst, &tmap, tile_i * ROW, -E, tile_o * BO, loaded + b);
+        }
+      }
+    }
+  } else if (warp <= sp.nstats) {
+    // ------------------------------- stats: line mean + the two boundary fits (lane = line) -------------------
+    for (unsigned seq = warp - 1; seq < my_tiles; seq += sp.nstats) {
+      const int b = seq % NB;
+      const unsigned rev = seq / NB;
+      mbar_wait(loaded + b, rev & 1u, 2000 + (int)seq);
+      const double *x0 = tiles + (size_t)b * TILE + lbase + E * ROW;  // element 0 of the line
+      const double mean = line_mean_rows<ROW>(x0, n);
+      const double2 L = fit_side<ROW>(x0, 1, mean, sp);
+      const double2 Rr = fit_side<ROW>(x0 + (n - 1) * ROW, -1, mean, sp);
+      double2 *lp = (double2 *)(lpar + b * 128 + lane * 4);
+      lp[0] = L;
+      lp[1] = Rr;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready + b);
+    }
+  } else if (warp - 1 - sp.nstats < sp.ncons) {
+    // ------------------------------- consumers: (tile, block of 8 outputs) items from a shared counter ---------
+    const int cw = warp - 1 - sp.nstats;
+    double *mystage = stage + cw * 288;
+    for (;;) {
+      unsigned item = 0;
+      if (lane == 0) item = atomicAdd(counter, 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      const unsigned seq = item / (unsigned)nblk;
+      if (seq >= my_tiles) break;
+      const int kb = (int)(item - seq * (unsigned)nblk);
+      const int b = seq % NB;
+      const unsigned rev = seq / NB;
+      const long long t = blockIdx.x + (long long)seq * tstep;
+      const int k0 = kb * SP_R;
+      // window row j <-> input index k0 - E + j; rows outside [0, n) are zero padding
+      const int jlo = E - k0 > 0 ? E - k0 : 0;
+      const int jhi = n + E - k0 < W ? n + E - k0 : W;
+      const int clo = jlo >> 3, chi = (jhi + 7) >> 3;
+      mbar_wait(ready + b, rev & 1u, 3000 + (int)seq);
+      const double *p = tiles + (size_t)b * TILE + lbase + k0 * ROW;
+      double acc[SP_R];
+#pragma unroll
+      for (int r = 0; r < SP_R; ++r) acc[r] = 0.0;
+      fir_block8<TAPS, ROW>(p, clo, chi, sp, acc);
+      if (k0 < E - 1) {  // outputs that see left ghosts
+        const double2 ab = *(const double2 *)(lpar + b * 128 + lane * 4);
+#pragma unroll
+        for (int r = 0; r < SP_R; ++r) {
+          const int k = k0 + r;
+          if (k < E - 1) acc[r] = fma(ab.y, stab[32 + k], fma(ab.x, stab[k], acc[r]));
+        }
+      }
+      if (k0 + SP_R - 1 > n - E) {  // outputs that see right ghosts: distance n - 1 - k < E - 1
+        const double2 ab = *(const double2 *)(lpar + b * 128 + lane * 4 + 2);
+#pragma unroll
+        for (int r = 0; r < SP_R; ++r) {
+          const int d = n - 1 - (k0 + r);
+          if (d >= 0 && d < E - 1) acc[r] = fma(ab.y, stab[32 + d], fma(ab.x, stab[d], acc[r]));
+        }
+      }
+      if (AXIS0) {
+        // transposing stage: lane = line writes its 8 outputs, then lane = (line % 4, output) stores whole sectors
+#pragma unroll
+        for (int r = 0; r < SP_R; ++r) mystage[lane * 9 + r] = acc[r];
+        __syncwarp();
+        const int r = lane & 7, l4 = lane >> 3;
+        const long long line0 = t * 32;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int tl2 = it * 4 + l4;
+          const double v = mystage[tl2 * 9 + r];
+          if (line0 + tl2 < sp.outer && k0 + r < n) out[(line0 + tl2) * n + k0 + r] = v;
+        }
+      } else {
+        const int tile_i = (int)(t % sp.tiles_inner), tile_o = (int)(t / sp.tiles_inner);
+        const long long gi = (long long)tile_i * ROW + gline_i, go = (long long)tile_o * BO + gline_o;
+        if (gi < sp.inner && go < sp.outer) {
+          double *op = out + gi + sp.inner * ((long long)k0 + (long long)n * go);
+#pragma unroll
+          for (int r = 0; r < SP_R; ++r)
+            if (k0 + r < n) op[(long long)r * sp.inner] = acc[r];
+        }
+      }
+      __syncwarp();  // every lane is done with the tile (and with the stage) before the slot is handed back
+      if (lane == 0) mbar_arrive(empty + b);
+    }
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+static int pipe_smem_budget() {
+  int dev = 0, v = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return v > 0 ? v : 48 * 1024;
+}
+
+template <int TAPS, int BI>
+static int launch_smooth_pass(const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads, size_t smem,
+                              cudaStream_t st) {
+  auto k = smooth_pipe_kernel<TAPS, BI>;
+  CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)std::min<long long>(sp.ntiles, (long long)sm_count()));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (tune_env("CIB200_NO_PDL")) cfg.numAttrs = 0;
+  CIB_CUDA(cudaLaunchKernelEx(&cfg, k, tmap, sp, out));
+  CIB_LAUNCHED();
+  return CIB200_OK;
+}
+
+template <int TAPS>
+static int launch_smooth_bi(int bi, const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads, size_t smem,
+                            cudaStream_t st) {
+  if (bi == 0) return launch_smooth_pass<TAPS, 0>(tmap, sp, out, threads, smem, st);
+  if (bi == 8) return launch_smooth_pass<TAPS, 8>(tmap, sp, out, threads, smem, st);
+  return launch_smooth_pass<TAPS, 32>(tmap, sp, out, threads, smem, st);
+}
+
+// One pass of convolution_smooth along the axis that splits the array into [inner][n][outer].  Returns -1 when the
+// pass does not qualify (the caller falls back to the generic sweep kernels), a cib200 status otherwise.
+int smooth_pipe_pass(const double *in, double *out, long long inner, long long n_ll, long long outer, int E,
+                     const double *kw, cudaStream_t st) {
+  const int taps = 2 * E + 1;
+  if (taps != 13 && taps != 17 && taps != 25 && taps != 35 && taps != 49) return -1;
+  if (n_ll <= E || n_ll + 2 * E + SP_R > 250) return -1;  // TMA box extents are at most 256 elements
+  if (((uintptr_t)in & 15) || !tma_encode_tiled_fn()) return -1;
+  const int n = (int)n_ll;
+  const bool axis0 = inner == 1;
+  if (const char *e = tune_env("CIB200_SMOOTH_NEW")) {  // 1: axis 0 only, 2: axis >= 1 only
+    if ((e[0] == '1' && !axis0) || (e[0] == '2' && axis0)) return -1;
+  }
+  SmoothPipeParams sp;
+  memset(&sp, 0, sizeof sp);
+  sp.inner = inner;
+  sp.outer = outer;
+  sp.n = n;
+  sp.nblk = (n + SP_R - 1) / SP_R;
+  int bi = 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  const int rows = n + 2 * E + SP_R - 1;  // -E .. n + E + 6: every window row a block can touch
+  if (axis0) {
+    if ((n & 1) || (E & 1)) return -1;  // line stride and box start (-E elements) must be multiples of 16 bytes
+    int P = rows;
+    while ((P & 3) != 2) ++P;  // P / 2 odd: the 8 lanes of an LDS.128 wavefront fall into 8 distinct 16-byte banks
+    if (P > 256 || outer >= (1LL << 31)) return -1;
+    sp.H = P;
+    sp.ntiles = (outer + 31) / 32;
+    cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)outer};
+    cuuint64_t gstr[1] = {(cuuint64_t)n * 8};
+    cuuint32_t box[2] = {(cuuint32_t)P, 32};
+    if (pipe::encode_f64(&tmap, 2, in, gdim, gstr, box)) return -1;
+  } else {
+    if ((inner & 1) || inner >= (1LL << 31) || outer >= (1LL << 31)) return -1;
+    bi = (inner % 32 == 0) ? 32 : ((inner % 8 == 0 && inner < 256) ? 8 : 32);
+    int H = rows;
+    if (bi < 32 && !(H & 1)) ++H;  // odd: the 32 / BI outer slabs of a tile start in different banks
+    if (H > 256) return -1;
+    sp.H = H;
+    sp.tiles_inner = (int)((inner + bi - 1) / bi);
+    const int bo = 32 / bi;
+    sp.ntiles = (long long)sp.tiles_inner * ((outer + bo - 1) / bo);
+    cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)n, (cuuint64_t)outer};
+    cuuint64_t gstr[2] = {(cuuint64_t)inner * 8, (cuuint64_t)inner * (cuuint64_t)n * 8};
+    cuuint32_t box[3] = {(cuuint32_t)bi, (cuuint32_t)H, (cuuint32_t)bo};
+    if (pipe::encode_f64(&tmap, 3, in, gdim, gstr, box)) return -1;
+  }
+  if (sp.ntiles >= (1LL << 31) / 32) return -1;
+  // roles: 1 producer warp, stats warps, consumer warps
+  sp.nstats = 2;
+  sp.ncons = 16;
+  if (const char *e = tune_env("CIB200_SMOOTH_NSTATS")) sp.nstats = std::max(1, std::min(4, atoi(e)));
+  if (const char *e = tune_env("CIB200_SMOOTH_NCONS")) sp.ncons = std::max(1, std::min(17 - sp.nstats + 2, atoi(e)));
+  const int threads = 32 * (1 + sp.nstats + sp.ncons);
+  if (threads > 640) return -1;
+  const size_t tile_bytes = (size_t)32 * sp.H * 8;
+  const size_t fixed = 64 * 8 + (axis0 ? (size_t)sp.ncons * 288 * 8 : 0) + 8 * 3 * 8 + 16 + 1024 /* alignment slack */;
+  const size_t per_slot = tile_bytes + 128 * 8;
+  const size_t budget = (size_t)pipe_smem_budget();
+  if (fixed + 3 * per_slot > budget) return -1;
+  sp.nb = (int)std::min<size_t>(8, (budget - fixed) / per_slot);
+  if (const char *e = tune_env("CIB200_SMOOTH_NB")) sp.nb = std::max(2, std::min(sp.nb, atoi(e)));
+  // least-squares constants (create_convolutional_coefs.jl:455-470): sums of small integers, exact
+  sp.nfit = std::min(std::max(E / 3, 6), n);
+  sp.nf = (double)sp.nfit;
+  sp.sx = sp.nf * (sp.nf + 1.0) * 0.5;
+  const double sxx = sp.nf * (sp.nf + 1.0) * (2.0 * sp.nf + 1.0) / 6.0;
+  sp.denom = sp.nf * sxx - sp.sx * sp.sx;
+  for (int l = 0; l < taps; ++l) sp.kw[l] = kw[l];
+  // ghost k = 1..E-1 sits k + 1 slots outside the line and holds a + b (1 - k); output at distance i from the boundary
+  // sees the ghosts with k + 1 + i <= E
+  for (int i = 0; i + 1 < E && i < 32; ++i) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = 1; k + 1 + i <= E; ++k) {
+      const double w = kw[E - (k + 1 + i)];
+      a0 += w;
+      a1 += w * (double)(1 - k);
+    }
+    sp.s0[i] = a0;
+    sp.s1[i] = a1;
+  }
+  const size_t smem = fixed + (size_t)sp.nb * per_slot;
+  switch (taps) {
+    case 13: return launch_smooth_bi<13>(bi, tmap, sp, out, threads, smem, st);
+    case 17: return launch_smooth_bi<17>(bi, tmap, sp, out, threads, smem, st);
+    case 25: return launch_smooth_bi<25>(bi, tmap, sp, out, threads, smem, st);
+    case 35: return launch_smooth_bi<35>(bi, tmap, sp, out, threads, smem, st);
+    default: return launch_smooth_bi<49>(bi, tmap, sp, out, threads, smem, st);
+  }
+}
+
+}  // namespace cib

@@ -1678,6 +1678,14 @@ static int smooth_t(int ndim, const long long *n, const T *d_in, T *d_out, const
     if (taps <= 64)
       for (int l = 0; l < taps; ++l) sp.kwc[l] = kw[(size_t)l];
     T *next = (d == ndim - 1) ? d_out : scratch[d & 1];
+    if (sizeof(T) == sizeof(double) && tune_env("CIB200_SMOOTH_OLD") == nullptr) {
+      rc = smooth_pipe_pass((const double *)cur, (double *)next, sp.inner, sp.n_in, sp.outer, E, kw.data(), st);
+      if (rc > 0) return rc;
+      if (rc == 0) {
+        cur = next;
+        continue;
+      }
+    }
     if ((rc = launch_pass<T, true>(sp, gm, cur, next, sp.inner == 1, st))) return rc;
     cur = next;
   }
