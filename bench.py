@@ -178,6 +178,17 @@ def cpu_baseline(seconds, grid_n=96, threads=None):
                       f"evaluator (eager_3d.jl:181-305) in C with OpenMP, {dt:.1f} s"}
 
 
+
+def julia_order(a):
+    """CUDA tensor indexed like `a` whose MEMORY is column-major (axis 0 contiguous) - how a Julia array lies in memory.
+    The host mirror hands such a tensor to the library as it is; a C-ordered tensor would first be transposed by a
+    torch copy kernel inside the timed region (0.1 ms for 64^4)."""
+    import numpy as np
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    return t.permute(*reversed(range(t.dim())))
+
+
 def secondary_sweeps(peak):
     """BASELINE.json's metric also names `resample output pts/s`: configs 3 and 4 (the separable sweeps), device-resident,
     CUDA events, best of 10 after 3 warm-ups, against the separable-sweep byte model of SURVEY.md 8d.  Side numbers:
@@ -202,7 +213,7 @@ def secondary_sweeps(peak):
     out = {}
     kin = tuple(np.linspace(0, 2 * np.pi, 128) for _ in range(3))
     kout = tuple(np.linspace(0, 2 * np.pi, 256) for _ in range(3))
-    v = torch.from_numpy(rng.random((128, 128, 128))).cuda()
+    v = julia_order(rng.random((128, 128, 128)))
     ms = best_ms(lambda: ci.convolution_resample(kin, kout, v, kernel="b13"))
     nbytes = 8 * ((128 ** 3 + 256 * 128 ** 2) + (256 * 128 ** 2 + 256 ** 2 * 128) + (256 ** 2 * 128 + 256 ** 3))
     out["resample_b13_128_to_256"] = {"value": 256 ** 3 / (ms * 1e-3), "unit": "output pts/s", "ms": ms,
@@ -210,7 +221,7 @@ def secondary_sweeps(peak):
                                       "model": "sum over the 3 passes of bytes read + written = 352.3 MB"}
     for n in (40, 64):
         ks = tuple(np.linspace(0, 2 * np.pi, n) for _ in range(4))
-        v4 = torch.from_numpy(rng.random((n,) * 4)).cuda()
+        v4 = julia_order(rng.random((n,) * 4))
         ms = best_ms(lambda: ci.convolution_smooth(ks, v4, 0.05))
         # the smooth passes are FP64-bound before they are HBM-bound: 49 DFMA per point and pass against 64 FP64
         # lanes per clock and SM (tools/micro) = 148 x 64 x 1.965e9 DFMA/s

@@ -39,26 +39,34 @@ using namespace pipe;
 
 struct SmoothPipeParams {
   long long inner, outer, ntiles;
+  long long line_o_stride;  // axis >= 1: inner * n (elements between consecutive `outer` slabs)
   int n, nblk;
   int H;            // axis >= 1: rows of a tile buffer; axis 0: pitch P of a line
   int tiles_inner;  // axis >= 1: tiles along `inner`
   int nb, nstats, ncons;
-  int nfit;
-  double nf, sx, denom;
+  unsigned magic_nblk, magic_nb, magic_ti;  // floor(2^32 / d) + 1: exact division of the small counters below by d
+  double nf, sx, inv_denom, inv_nf, inv_n;
   double kw[64];          // normalised Gaussian taps, l = -E..E
   double s0[32], s1[32];  // ghost tables, index = distance of the output from the boundary (0..E-2)
 };
 
-static constexpr int SP_R = 8;  // outputs per block
+// per-tile header written by the stats warp: where the tile's outputs go (consumers stay in 32-bit arithmetic)
+struct TileHdr {
+  long long obase;  // element offset of (first line of the tile, output 0)
+  int vi, vo;       // valid lines along inner / outer (axis 0: vo = valid lines)
+};
 
+__device__ __forceinline__ unsigned div_magic(unsigned x, unsigned magic) { return __umulhi(x, magic); }
 
-template <int TAPS, int ROW>
-__device__ __forceinline__ void fir_block8(const double *__restrict__ p, int clo, int chi, const SmoothPipeParams &sp,
-                                           double (&acc)[SP_R]) {
-  constexpr int W = TAPS + SP_R - 1, NCH = (W + 7) / 8;
+// R consecutive outputs of one line from a window of TAPS + R - 1 input rows; chunks of 8 rows outside [clo, chi) lie in
+// the zero padding and are skipped (warp-uniform); taps are literal offsets into the kernel-parameter bank
+template <int TAPS, int ROW, int R>
+__device__ __forceinline__ void fir_block(const double *__restrict__ p, int clo, int chi, const SmoothPipeParams &sp,
+                                          double (&acc)[R]) {
+  constexpr int W = TAPS + R - 1, NCH = (W + 7) / 8;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    if (c >= clo && c < chi) {  // warp-uniform: chunks of 8 window rows that lie inside the line
+    if (c >= clo && c < chi) {
       double x[8];
       if (ROW == 1) {  // axis 0: the window is contiguous and 16-byte aligned (W is even)
 #pragma unroll
@@ -78,7 +86,7 @@ __device__ __forceinline__ void fir_block8(const double *__restrict__ p, int clo
         const int j = 8 * c + i;
         if (j < W) {
 #pragma unroll
-          for (int r = 0; r < SP_R; ++r) {
+          for (int r = 0; r < R; ++r) {
             const int l = j - r;
             if (l >= 0 && l < TAPS) acc[r] = fma(x[i], sp.kw[l], acc[r]);
           }
@@ -88,7 +96,7 @@ __device__ __forceinline__ void fir_block8(const double *__restrict__ p, int clo
   }
 }
 
-// mean of a line in the association of line_mean (cib200_sweep.cu): 8 interleaved partial sums, pairwise combine
+// sum of a line in the association of line_mean (cib200_sweep.cu): 8 interleaved partial sums, pairwise combine
 template <int ROW>
 __device__ __forceinline__ double line_mean_rows(const double *__restrict__ x0, int n) {
   double s[8];
@@ -116,43 +124,58 @@ __device__ __forceinline__ double line_mean_rows(const double *__restrict__ x0, 
     if (j + i < n) s[i] = __dadd_rn(s[i], x0[(j + i) * ROW]);
   const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
                                __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
-  return __ddiv_rn(sum, (double)n);
+  return sum;
 }
 
-// least-squares line through the first nfit mean-centred points counted from one end (fill_ghost_points_gaussian!,
-// create_convolutional_coefs.jl:455-478): x_k = k = 1..nfit, returns the centred intercept a and the slope b
-template <int ROW>
-__device__ __forceinline__ double2 fit_side(const double *__restrict__ q, int step_sign, double mean, const SmoothPipeParams &sp) {
-  double sy = 0.0, sxy = 0.0, xk = 1.0;
-  for (int k = 0; k < sp.nfit; ++k) {
-    const double yk = __dsub_rn(q[step_sign * k * ROW], mean);
-    sy = __dadd_rn(sy, yk);
-    sxy = __dadd_rn(sxy, __dmul_rn(xk, yk));
-    xk += 1.0;
+// least-squares lines through the first NFIT mean-centred points counted from either end (fill_ghost_points_gaussian!,
+// create_convolutional_coefs.jl:455-478): x_k = k = 1..NFIT; returns (a, b) = centred intercept and slope, left and
+// right.  Both fits are unrolled together (four independent accumulation chains), and the three divisions of the
+// reference (mean = sum / n, b = ... / denom, a = ... / n_fit) are multiplications by host-computed reciprocals: one
+// more rounding each (<= 1e-16 relative), off the tile's critical path by ~400 cycles of dependent DDIV sequences.
+template <int ROW, int NFIT>
+__device__ __forceinline__ void fit_both(const double *__restrict__ x0, int n, double mean, const SmoothPipeParams &sp,
+                                         double2 &L, double2 &Rr) {
+  double yl[NFIT], yr[NFIT];
+#pragma unroll
+  for (int k = 0; k < NFIT; ++k) {
+    yl[k] = __dsub_rn(x0[k * ROW], mean);
+    yr[k] = __dsub_rn(x0[(n - 1 - k) * ROW], mean);
   }
-  const double b = __ddiv_rn(__dsub_rn(__dmul_rn(sp.nf, sxy), __dmul_rn(sp.sx, sy)), sp.denom);
-  const double a = __ddiv_rn(__dsub_rn(sy, __dmul_rn(b, sp.sx)), sp.nf);
-  return make_double2(a, b);
+  double syl = 0.0, sxyl = 0.0, syr = 0.0, sxyr = 0.0;
+#pragma unroll
+  for (int k = 0; k < NFIT; ++k) {
+    syl = __dadd_rn(syl, yl[k]);
+    sxyl = __dadd_rn(sxyl, __dmul_rn((double)(k + 1), yl[k]));
+    syr = __dadd_rn(syr, yr[k]);
+    sxyr = __dadd_rn(sxyr, __dmul_rn((double)(k + 1), yr[k]));
+  }
+  const double bl = __dmul_rn(__dsub_rn(__dmul_rn(sp.nf, sxyl), __dmul_rn(sp.sx, syl)), sp.inv_denom);
+  const double br = __dmul_rn(__dsub_rn(__dmul_rn(sp.nf, sxyr), __dmul_rn(sp.sx, syr)), sp.inv_denom);
+  L = make_double2(__dmul_rn(__dsub_rn(syl, __dmul_rn(bl, sp.sx)), sp.inv_nf), bl);
+  Rr = make_double2(__dmul_rn(__dsub_rn(syr, __dmul_rn(br, sp.sx)), sp.inv_nf), br);
 }
 
-// BI: lanes along `inner` in a tile of an axis >= 1 pass (32 or 8); BI = 0: axis 0
-template <int TAPS, int BI>
+// BI: lanes along `inner` in a tile of an axis >= 1 pass (32 or 8); BI = 0: axis 0.  R: outputs per work item.
+template <int TAPS, int BI, int R>
 __global__ void __launch_bounds__(640, 1)
     smooth_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SmoothPipeParams sp,
                        double *__restrict__ out) {
   constexpr int E = (TAPS - 1) / 2;
   constexpr bool AXIS0 = BI == 0;
   constexpr int ROW = AXIS0 ? 1 : BI;
-  constexpr int BO = AXIS0 ? 1 : 32 / (BI > 0 ? BI : 32);
-  constexpr int W = TAPS + SP_R - 1;
+  constexpr int BIX = BI > 0 ? BI : 32;
+  constexpr int BO = AXIS0 ? 1 : 32 / BIX;
+  constexpr int W = TAPS + R - 1;
+  constexpr int SPITCH = R + 1;  // transposing stage of axis 0
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NB = sp.nb, n = sp.n, nblk = sp.nblk;
   const int TILE = 32 * sp.H;  // doubles
   double *tiles = (double *)smem_raw;
   double *lpar = tiles + (size_t)NB * TILE;  // [NB][32][4]: aL bL aR bR of every line of the tile
   double *stab = lpar + NB * 128;            // s0[32] s1[32]
-  double *stage = stab + 64;                 // axis 0: [ncons][32 * 9] transposing store stage
-  unsigned long long *bars = (unsigned long long *)(stage + (AXIS0 ? sp.ncons * 288 : 0));
+  TileHdr *hdr = (TileHdr *)(stab + 64);     // [NB]
+  double *stage = (double *)(hdr + NB);      // axis 0: [ncons][32 * SPITCH] transposing store stage
+  unsigned long long *bars = (unsigned long long *)(stage + (AXIS0 ? sp.ncons * 32 * SPITCH : 0));
   unsigned long long *loaded = bars, *ready = bars + NB, *empty = bars + 2 * NB;
   unsigned *counter = (unsigned *)(bars + 3 * NB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -168,30 +191,21 @@ __global__ void __launch_bounds__(640, 1)
   }
   __syncthreads();
   pdl_launch_dependents();
-  const long long tstep = gridDim.x;
-  const unsigned my_tiles = blockIdx.x < sp.ntiles ? (unsigned)((sp.ntiles - blockIdx.x + tstep - 1) / tstep) : 0u;
+  const unsigned tstep = gridDim.x;
+  const unsigned ntiles = (unsigned)sp.ntiles;
+  const unsigned my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + tstep - 1) / tstep : 0u;
 
-  // position of this lane's line in a tile buffer and in the array
-  int lbase;             // doubles from the start of the tile buffer to this line's row -E (axis 0: column -E)
-  long long gline_i = 0, gline_o = 0;
-  if (AXIS0) {
-    lbase = lane * sp.H;
-    gline_o = lane;  // + 32 t
-  } else {
-    const int i = lane % (BI > 0 ? BI : 32), oo = lane / (BI > 0 ? BI : 32);
-    lbase = oo * sp.H * ROW + i;
-    gline_i = i;   // + tile_i BI
-    gline_o = oo;  // + tile_o BO
-  }
+  // this lane's line: offset of its row -E (axis 0: column -E) in a tile buffer, and of its outputs from the tile's
+  const int li = AXIS0 ? 0 : lane % BIX, lo = AXIS0 ? lane : lane / BIX;
+  const int lbase = AXIS0 ? lane * sp.H : lo * sp.H * ROW + li;
 
   if (warp == 0) {
     // ------------------------------- producer: one elected lane feeds the ring with TMA boxes -----------------
     if (lane == 0) {
       pdl_wait();  // the input of this pass is the output of the previous launch
+      unsigned b = 0, rev = 0;
       for (unsigned seq = 0; seq < my_tiles; ++seq) {
-        const int b = seq % NB;
-        const unsigned rev = seq / NB;
-        const long long t = blockIdx.x + (long long)seq * tstep;
+        const unsigned t = blockIdx.x + seq * tstep;
         if (rev > 0) mbar_wait(empty + b, (rev - 1) & 1u, 1000 + (int)seq);
         fence_async_proxy();
         mbar_expect_tx(loaded + b, (unsigned)(TILE * 8));
@@ -199,21 +213,42 @@ __global__ void __launch_bounds__(640, 1)
         if (AXIS0) {
           tma_load_2d(dst, &tmap, -E, (int)(t * 32), loaded + b);
         } else {
-          const int tile_i = (int)(t % sp.tiles_inner), tile_o = (int)(t / sp.tiles_inner);
-          tma_load_3d(dst, &tmap, tile_i * ROW, -E, tile_o * BO, loaded + b);
+          const unsigned tile_o = div_magic(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
+          tma_load_3d(dst, &tmap, (int)tile_i * ROW, -E, (int)tile_o * BO, loaded + b);
+        }
+        if (++b == (unsigned)NB) {
+          b = 0;
+          ++rev;
         }
       }
     }
   } else if (warp <= sp.nstats) {
     // ------------------------------- stats: line mean + the two boundary fits (lane = line) -------------------
     for (unsigned seq = warp - 1; seq < my_tiles; seq += sp.nstats) {
-      const int b = seq % NB;
-      const unsigned rev = seq / NB;
-      mbar_wait(loaded + b, rev & 1u, 2000 + (int)seq);
+      const unsigned rev = div_magic(seq, sp.magic_nb), b = seq - rev * NB;
+      const unsigned t = blockIdx.x + seq * tstep;
+      mbar_wait(loaded + b, rev & 1u, 2000 + (int)seq);  // also: the slot's previous tile has been consumed
+      if (lane == 0) {
+        TileHdr h;
+        if (AXIS0) {
+          h.obase = (long long)t * 32 * n;
+          const long long rem = sp.outer - (long long)t * 32;
+          h.vi = 1;
+          h.vo = rem < 32 ? (int)rem : 32;
+        } else {
+          const unsigned tile_o = div_magic(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
+          h.obase = (long long)tile_i * ROW + sp.line_o_stride * ((long long)tile_o * BO);
+          const long long ri = sp.inner - (long long)tile_i * ROW, ro = sp.outer - (long long)tile_o * BO;
+          h.vi = ri < BIX ? (int)ri : BIX;
+          h.vo = ro < BO ? (int)ro : BO;
+        }
+        hdr[b] = h;
+      }
       const double *x0 = tiles + (size_t)b * TILE + lbase + E * ROW;  // element 0 of the line
-      const double mean = line_mean_rows<ROW>(x0, n);
-      const double2 L = fit_side<ROW>(x0, 1, mean, sp);
-      const double2 Rr = fit_side<ROW>(x0 + (n - 1) * ROW, -1, mean, sp);
+      const double mean = __dmul_rn(line_mean_rows<ROW>(x0, n), sp.inv_n);
+      constexpr int NFIT = E / 3 > 6 ? E / 3 : 6;  // n_fit = max(E / 3, 6) (the host checks n >= NFIT)
+      double2 L, Rr;
+      fit_both<ROW, NFIT>(x0, n, mean, sp, L, Rr);
       double2 *lp = (double2 *)(lpar + b * 128 + lane * 4);
       lp[0] = L;
       lp[1] = Rr;
@@ -221,67 +256,73 @@ __global__ void __launch_bounds__(640, 1)
       if (lane == 0) mbar_arrive(ready + b);
     }
   } else if (warp - 1 - sp.nstats < sp.ncons) {
-    // ------------------------------- consumers: (tile, block of 8 outputs) items from a shared counter ---------
+    // ------------------------------- consumers: (tile, block of R outputs) items from a shared counter ---------
     const int cw = warp - 1 - sp.nstats;
-    double *mystage = stage + cw * 288;
+    double *mystage = stage + cw * 32 * SPITCH;
+    // per-lane output offset from the tile's base (axis >= 1) / transposed store roles (axis 0)
+    const long long lane_off = AXIS0 ? 0 : (long long)li + sp.line_o_stride * lo;
+    const int sr = lane % R, sl = lane / R;  // axis 0: this lane stores output sr of lines sl, sl + 32 / R, ...
     for (;;) {
       unsigned item = 0;
       if (lane == 0) item = atomicAdd(counter, 1u);
       item = __shfl_sync(0xffffffffu, item, 0);
-      const unsigned seq = item / (unsigned)nblk;
+      const unsigned seq = div_magic(item, sp.magic_nblk);
       if (seq >= my_tiles) break;
-      const int kb = (int)(item - seq * (unsigned)nblk);
-      const int b = seq % NB;
-      const unsigned rev = seq / NB;
-      const long long t = blockIdx.x + (long long)seq * tstep;
-      const int k0 = kb * SP_R;
+      const int k0 = (int)(item - seq * (unsigned)nblk) * R;
+      const unsigned rev = div_magic(seq, sp.magic_nb), b = seq - rev * NB;
       // window row j <-> input index k0 - E + j; rows outside [0, n) are zero padding
       const int jlo = E - k0 > 0 ? E - k0 : 0;
       const int jhi = n + E - k0 < W ? n + E - k0 : W;
       const int clo = jlo >> 3, chi = (jhi + 7) >> 3;
       mbar_wait(ready + b, rev & 1u, 3000 + (int)seq);
       const double *p = tiles + (size_t)b * TILE + lbase + k0 * ROW;
-      double acc[SP_R];
+      double acc[R];
 #pragma unroll
-      for (int r = 0; r < SP_R; ++r) acc[r] = 0.0;
-      fir_block8<TAPS, ROW>(p, clo, chi, sp, acc);
+      for (int r = 0; r < R; ++r) acc[r] = 0.0;
+      fir_block<TAPS, ROW, R>(p, clo, chi, sp, acc);
       if (k0 < E - 1) {  // outputs that see left ghosts
         const double2 ab = *(const double2 *)(lpar + b * 128 + lane * 4);
 #pragma unroll
-        for (int r = 0; r < SP_R; ++r) {
-          const int k = k0 + r;
-          if (k < E - 1) acc[r] = fma(ab.y, stab[32 + k], fma(ab.x, stab[k], acc[r]));
-        }
+        for (int r = 0; r < R; ++r)
+          if (k0 + r < E - 1) acc[r] = fma(ab.y, stab[32 + k0 + r], fma(ab.x, stab[k0 + r], acc[r]));
       }
-      if (k0 + SP_R - 1 > n - E) {  // outputs that see right ghosts: distance n - 1 - k < E - 1
+      if (k0 + R - 1 > n - E) {  // outputs that see right ghosts: distance n - 1 - k < E - 1
         const double2 ab = *(const double2 *)(lpar + b * 128 + lane * 4 + 2);
 #pragma unroll
-        for (int r = 0; r < SP_R; ++r) {
+        for (int r = 0; r < R; ++r) {
           const int d = n - 1 - (k0 + r);
           if (d >= 0 && d < E - 1) acc[r] = fma(ab.y, stab[32 + d], fma(ab.x, stab[d], acc[r]));
         }
       }
+      const TileHdr h = hdr[b];
       if (AXIS0) {
-        // transposing stage: lane = line writes its 8 outputs, then lane = (line % 4, output) stores whole sectors
+        // transposing stage: lane = line writes its R outputs, then lane = (line % (32 / R), output) stores whole
+        // sectors: R consecutive doubles per line
 #pragma unroll
-        for (int r = 0; r < SP_R; ++r) mystage[lane * 9 + r] = acc[r];
+        for (int r = 0; r < R; ++r) mystage[lane * SPITCH + r] = acc[r];
         __syncwarp();
-        const int r = lane & 7, l4 = lane >> 3;
-        const long long line0 = t * 32;
+        double *op = out + h.obase + (long long)sl * n + k0 + sr;
+        const bool kok = k0 + sr < n;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int tl2 = it * 4 + l4;
-          const double v = mystage[tl2 * 9 + r];
-          if (line0 + tl2 < sp.outer && k0 + r < n) out[(line0 + tl2) * n + k0 + r] = v;
+        for (int it = 0; it < R; ++it) {
+          const int tl2 = it * (32 / R) + sl;
+          const double v = mystage[tl2 * SPITCH + sr];
+          if (kok && tl2 < h.vo) op[(long long)it * (32 / R) * n] = v;
         }
-      } else {
-        const int tile_i = (int)(t % sp.tiles_inner), tile_o = (int)(t / sp.tiles_inner);
-        const long long gi = (long long)tile_i * ROW + gline_i, go = (long long)tile_o * BO + gline_o;
-        if (gi < sp.inner && go < sp.outer) {
-          double *op = out + gi + sp.inner * ((long long)k0 + (long long)n * go);
+      } else if (li < h.vi && lo < h.vo) {
+        double *op = out + h.obase + lane_off + (long long)k0 * sp.inner;
+        if (k0 + R <= n) {
 #pragma unroll
-          for (int r = 0; r < SP_R; ++r)
-            if (k0 + r < n) op[(long long)r * sp.inner] = acc[r];
+          for (int r = 0; r < R; ++r) {
+            *op = acc[r];
+            op += sp.inner;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (k0 + r < n) *op = acc[r];
+            op += sp.inner;
+          }
         }
       }
       __syncwarp();  // every lane is done with the tile (and with the stage) before the slot is handed back
@@ -292,17 +333,32 @@ __global__ void __launch_bounds__(640, 1)
 
 // ---- host ----------------------------------------------------------------------------------------------------------
 static int pipe_smem_budget() {
-  int dev = 0, v = 0;
+  static int cached[64];
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  return v > 0 ? v : 48 * 1024;
+  int &v = cached[dev & 63];
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (v <= 0) v = 48 * 1024;
+  }
+  return v;
 }
 
-template <int TAPS, int BI>
+template <int TAPS, int BI, int R>
 static int launch_smooth_pass(const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads, size_t smem,
                               cudaStream_t st) {
-  auto k = smooth_pipe_kernel<TAPS, BI>;
-  CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto k = smooth_pipe_kernel<TAPS, BI, R>;
+  {
+    // the attribute is per (function, device): set it once to the device's limit instead of before every launch
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+      CIB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem_budget()));
+      done.fetch_or(bit, std::memory_order_release);
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)std::min<long long>(sp.ntiles, (long long)sm_count()));
@@ -321,11 +377,12 @@ static int launch_smooth_pass(const CUtensorMap &tmap, const SmoothPipeParams &s
 }
 
 template <int TAPS>
-static int launch_smooth_bi(int bi, const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads, size_t smem,
-                            cudaStream_t st) {
-  if (bi == 0) return launch_smooth_pass<TAPS, 0>(tmap, sp, out, threads, smem, st);
-  if (bi == 8) return launch_smooth_pass<TAPS, 8>(tmap, sp, out, threads, smem, st);
-  return launch_smooth_pass<TAPS, 32>(tmap, sp, out, threads, smem, st);
+static int launch_smooth_bi(int bi, int R, const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads,
+                            size_t smem, cudaStream_t st) {
+  (void)R;  // R = 16 was measured (64^4: 0.279 vs 0.272 ms, 40^4: 0.077 vs 0.069 ms) and is not instantiated
+  if (bi == 0) return launch_smooth_pass<TAPS, 0, 8>(tmap, sp, out, threads, smem, st);
+  if (bi == 8) return launch_smooth_pass<TAPS, 8, 8>(tmap, sp, out, threads, smem, st);
+  return launch_smooth_pass<TAPS, 32, 8>(tmap, sp, out, threads, smem, st);
 }
 
 // One pass of convolution_smooth along the axis that splits the array into [inner][n][outer].  Returns -1 when the
@@ -334,7 +391,7 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
                      const double *kw, cudaStream_t st) {
   const int taps = 2 * E + 1;
   if (taps != 13 && taps != 17 && taps != 25 && taps != 35 && taps != 49) return -1;
-  if (n_ll <= E || n_ll + 2 * E + SP_R > 250) return -1;  // TMA box extents are at most 256 elements
+  if (n_ll <= E || n_ll + 2 * E + 16 > 250) return -1;  // TMA box extents are at most 256 elements
   if (((uintptr_t)in & 15) || !tma_encode_tiled_fn()) return -1;
   const int n = (int)n_ll;
   const bool axis0 = inner == 1;
@@ -346,11 +403,14 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
   sp.inner = inner;
   sp.outer = outer;
   sp.n = n;
-  sp.nblk = (n + SP_R - 1) / SP_R;
+  // outputs per work item
+  const int R = 8;
+  sp.nblk = (n + R - 1) / R;
+  sp.line_o_stride = inner * n_ll;
   int bi = 0;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof tmap);
-  const int rows = n + 2 * E + SP_R - 1;  // -E .. n + E + 6: every window row a block can touch
+  const int rows = sp.nblk * R + 2 * E;  // -E .. nblk R + E - 1: every window row a block can touch
   if (axis0) {
     if ((n & 1) || (E & 1)) return -1;  // line stride and box start (-E elements) must be multiples of 16 bytes
     int P = rows;
@@ -377,27 +437,35 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
     cuuint32_t box[3] = {(cuuint32_t)bi, (cuuint32_t)H, (cuuint32_t)bo};
     if (pipe::encode_f64(&tmap, 3, in, gdim, gstr, box)) return -1;
   }
-  if (sp.ntiles >= (1LL << 31) / 32) return -1;
+  if (sp.ntiles * (long long)std::max(sp.nblk, 32) >= (1LL << 26)) return -1;  // 32-bit tile / item counters with exact magic division
   // roles: 1 producer warp, stats warps, consumer warps
-  sp.nstats = 2;
+  sp.nstats = 2;  // a tile's stats are a ~600-cycle dependent chain, its FIR ~1 300 cycles of the FP64 pipe
   sp.ncons = 16;
   if (const char *e = tune_env("CIB200_SMOOTH_NSTATS")) sp.nstats = std::max(1, std::min(4, atoi(e)));
   if (const char *e = tune_env("CIB200_SMOOTH_NCONS")) sp.ncons = std::max(1, std::min(17 - sp.nstats + 2, atoi(e)));
   const int threads = 32 * (1 + sp.nstats + sp.ncons);
   if (threads > 640) return -1;
   const size_t tile_bytes = (size_t)32 * sp.H * 8;
-  const size_t fixed = 64 * 8 + (axis0 ? (size_t)sp.ncons * 288 * 8 : 0) + 8 * 3 * 8 + 16 + 1024 /* alignment slack */;
+  const size_t fixed = 64 * 8 + 8 * sizeof(TileHdr) + (axis0 ? (size_t)sp.ncons * 32 * (R + 1) * 8 : 0) + 8 * 3 * 8 + 16 +
+                       1024 /* alignment slack */;
   const size_t per_slot = tile_bytes + 128 * 8;
   const size_t budget = (size_t)pipe_smem_budget();
   if (fixed + 3 * per_slot > budget) return -1;
   sp.nb = (int)std::min<size_t>(8, (budget - fixed) / per_slot);
   if (const char *e = tune_env("CIB200_SMOOTH_NB")) sp.nb = std::max(2, std::min(sp.nb, atoi(e)));
+  auto magic = [](unsigned d) { return (unsigned)((1ULL << 32) / d) + 1u; };  // exact for dividends below 2^32 / d
+  sp.magic_nblk = magic((unsigned)sp.nblk);
+  sp.magic_nb = magic((unsigned)sp.nb);
+  sp.magic_ti = magic((unsigned)std::max(1, sp.tiles_inner));
   // least-squares constants (create_convolutional_coefs.jl:455-470): sums of small integers, exact
-  sp.nfit = std::min(std::max(E / 3, 6), n);
-  sp.nf = (double)sp.nfit;
+  const int nfit = std::max(E / 3, 6);
+  if (n < nfit) return -1;
+  sp.nf = (double)nfit;
   sp.sx = sp.nf * (sp.nf + 1.0) * 0.5;
   const double sxx = sp.nf * (sp.nf + 1.0) * (2.0 * sp.nf + 1.0) / 6.0;
-  sp.denom = sp.nf * sxx - sp.sx * sp.sx;
+  sp.inv_denom = 1.0 / (sp.nf * sxx - sp.sx * sp.sx);
+  sp.inv_nf = 1.0 / sp.nf;
+  sp.inv_n = 1.0 / (double)n;
   for (int l = 0; l < taps; ++l) sp.kw[l] = kw[l];
   // ghost k = 1..E-1 sits k + 1 slots outside the line and holds a + b (1 - k); output at distance i from the boundary
   // sees the ghosts with k + 1 + i <= E
@@ -413,11 +481,11 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
   }
   const size_t smem = fixed + (size_t)sp.nb * per_slot;
   switch (taps) {
-    case 13: return launch_smooth_bi<13>(bi, tmap, sp, out, threads, smem, st);
-    case 17: return launch_smooth_bi<17>(bi, tmap, sp, out, threads, smem, st);
-    case 25: return launch_smooth_bi<25>(bi, tmap, sp, out, threads, smem, st);
-    case 35: return launch_smooth_bi<35>(bi, tmap, sp, out, threads, smem, st);
-    default: return launch_smooth_bi<49>(bi, tmap, sp, out, threads, smem, st);
+    case 13: return launch_smooth_bi<13>(bi, R, tmap, sp, out, threads, smem, st);
+    case 17: return launch_smooth_bi<17>(bi, R, tmap, sp, out, threads, smem, st);
+    case 25: return launch_smooth_bi<25>(bi, R, tmap, sp, out, threads, smem, st);
+    case 35: return launch_smooth_bi<35>(bi, R, tmap, sp, out, threads, smem, st);
+    default: return launch_smooth_bi<49>(bi, R, tmap, sp, out, threads, smem, st);
   }
 }
 

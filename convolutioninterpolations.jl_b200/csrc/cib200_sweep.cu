@@ -1648,11 +1648,8 @@ static int smooth_t(int ndim, const long long *n, const T *d_in, T *d_out, const
   std::vector<double> kw((size_t)taps);
   const double norm = theta(B, E);
   for (int l = -E; l <= E; ++l) kw[(size_t)(l + E)] = exp(-B * ((double)l * (double)l)) / norm;  // :59-63
-  double *d_kw;
+  double *d_kw = nullptr;  // only the generic sweep kernels read the taps from memory: uploaded on first need
   int rc;
-  if ((rc = tmp.alloc((void **)&d_kw, sizeof(double) * (size_t)taps))) return rc;
-  CIB_CUDA(cudaMemcpyAsync(d_kw, kw.data(), sizeof(double) * (size_t)taps, cudaMemcpyHostToDevice, st));
-  // (pageable source: the runtime stages the copy before returning, so kw may go out of scope)
   long long tot = 1;
   for (int d = 0; d < ndim; ++d) tot *= n[d];
   T *scratch[2] = {nullptr, nullptr};
@@ -1686,6 +1683,12 @@ static int smooth_t(int ndim, const long long *n, const T *d_in, T *d_out, const
         continue;
       }
     }
+    if (!d_kw) {
+      if ((rc = tmp.alloc((void **)&d_kw, sizeof(double) * (size_t)taps))) return rc;
+      // (pageable source: the runtime stages the copy before returning, so kw may go out of scope)
+      CIB_CUDA(cudaMemcpyAsync(d_kw, kw.data(), sizeof(double) * (size_t)taps, cudaMemcpyHostToDevice, st));
+    }
+    sp.W = d_kw;
     if ((rc = launch_pass<T, true>(sp, gm, cur, next, sp.inner == 1, st))) return rc;
     cur = next;
   }
