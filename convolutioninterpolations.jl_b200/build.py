@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcib200.so")
-SOURCES = ["cib200_api.cu", "cib200_eval.cu", "cib200_sweep.cu", "cib200_binned.cu", "cib200_evalnd.cu", "cib200_integral.cu", "cib200_smooth.cu"]
+SOURCES = ["cib200_api.cu", "cib200_eval.cu", "cib200_sweep.cu", "cib200_binned.cu", "cib200_evalnd.cu", "cib200_integral.cu", "cib200_smooth.cu", "cib200_resample.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "--fmad=true",

@@ -144,6 +144,11 @@ int sweep_resample(int ndim, int dtype, const long long *n_in, const long long *
                    const double *const *gen_tables, const int *gen_rows, cudaStream_t st);
 int sweep_build_coefs(int ndim, int dtype, const long long *n, const void *d_values, const double *h, const int *kernel,
                       const int *bcl, const int *bcr, void *d_coefs, cudaStream_t st);
+// persistent TMA-fed passes of convolution_resample (cib200_resample.cu); -1: the call does not qualify
+int resample_pipe_all(int ndim, const long long *n_in, const long long *n_out, const double *d_in, double *d_out,
+                      const double *const *knots_in, const double *const *knots_out, const int *kernel, const int *eqs_a,
+                      const double *const *tk, const double *const *td, const double *const *te, const int *linear,
+                      const int *npre, const double *scale, const int *bcl, const int *bcr, cudaStream_t st);
 // persistent TMA-fed FIR pass of convolution_smooth (cib200_smooth.cu); -1: the pass does not qualify
 int smooth_pipe_pass(const double *in, double *out, long long inner, long long n, long long outer, int E,
                      const double *kw, cudaStream_t st);

@@ -41,6 +41,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         : "memory");
   } while (!done);
 }
+// x / d for the small counters of the pipelines: magic = floor(2^32 / d) + 1 (exact for x < 2^32 / d), 0 for d = 1
+__device__ __forceinline__ unsigned div_u(unsigned x, unsigned magic) { return magic ? __umulhi(x, magic) : x; }
+inline unsigned div_magic_for(unsigned d) { return d <= 1 ? 0u : (unsigned)((1ULL << 32) / d) + 1u; }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar) {

@@ -32,6 +32,7 @@
 
 #include <algorithm>
 
+#include "cib200_ghost.cuh"
 #include "cib200_pipe.cuh"
 
 namespace cib {
@@ -55,8 +56,6 @@ struct TileHdr {
   long long obase;  // element offset of (first line of the tile, output 0)
   int vi, vo;       // valid lines along inner / outer (axis 0: vo = valid lines)
 };
-
-__device__ __forceinline__ unsigned div_magic(unsigned x, unsigned magic) { return __umulhi(x, magic); }
 
 // R consecutive outputs of one line from a window of TAPS + R - 1 input rows; chunks of 8 rows outside [clo, chi) lie in
 // the zero padding and are skipped (warp-uniform); taps are literal offsets into the kernel-parameter bank
@@ -94,37 +93,6 @@ __device__ __forceinline__ void fir_block(const double *__restrict__ p, int clo,
       }
     }
   }
-}
-
-// sum of a line in the association of line_mean (cib200_sweep.cu): 8 interleaved partial sums, pairwise combine
-template <int ROW>
-__device__ __forceinline__ double line_mean_rows(const double *__restrict__ x0, int n) {
-  double s[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = 0.0;
-  int j = 0;
-  for (; j + 8 <= n; j += 8) {
-    double v[8];
-    if (ROW == 1) {  // axis 0: 16-byte loads (x0 is 16-byte aligned: E and the pitch are even)
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        const double2 t = *(const double2 *)(x0 + j + i);
-        v[i] = t.x;
-        v[i + 1] = t.y;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = x0[(j + i) * ROW];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = __dadd_rn(s[i], v[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (j + i < n) s[i] = __dadd_rn(s[i], x0[(j + i) * ROW]);
-  const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
-                               __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
-  return sum;
 }
 
 // least-squares lines through the first NFIT mean-centred points counted from either end (fill_ghost_points_gaussian!,
@@ -213,7 +181,7 @@ __global__ void __launch_bounds__(640, 1)
         if (AXIS0) {
           tma_load_2d(dst, &tmap, -E, (int)(t * 32), loaded + b);
         } else {
-          const unsigned tile_o = div_magic(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
+          const unsigned tile_o = div_u(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
           tma_load_3d(dst, &tmap, (int)tile_i * ROW, -E, (int)tile_o * BO, loaded + b);
         }
         if (++b == (unsigned)NB) {
@@ -225,7 +193,7 @@ __global__ void __launch_bounds__(640, 1)
   } else if (warp <= sp.nstats) {
     // ------------------------------- stats: line mean + the two boundary fits (lane = line) -------------------
     for (unsigned seq = warp - 1; seq < my_tiles; seq += sp.nstats) {
-      const unsigned rev = div_magic(seq, sp.magic_nb), b = seq - rev * NB;
+      const unsigned rev = div_u(seq, sp.magic_nb), b = seq - rev * NB;
       const unsigned t = blockIdx.x + seq * tstep;
       mbar_wait(loaded + b, rev & 1u, 2000 + (int)seq);  // also: the slot's previous tile has been consumed
       if (lane == 0) {
@@ -236,7 +204,7 @@ __global__ void __launch_bounds__(640, 1)
           h.vi = 1;
           h.vo = rem < 32 ? (int)rem : 32;
         } else {
-          const unsigned tile_o = div_magic(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
+          const unsigned tile_o = div_u(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
           h.obase = (long long)tile_i * ROW + sp.line_o_stride * ((long long)tile_o * BO);
           const long long ri = sp.inner - (long long)tile_i * ROW, ro = sp.outer - (long long)tile_o * BO;
           h.vi = ri < BIX ? (int)ri : BIX;
@@ -245,7 +213,7 @@ __global__ void __launch_bounds__(640, 1)
         hdr[b] = h;
       }
       const double *x0 = tiles + (size_t)b * TILE + lbase + E * ROW;  // element 0 of the line
-      const double mean = __dmul_rn(line_mean_rows<ROW>(x0, n), sp.inv_n);
+      const double mean = __dmul_rn(line_sum_rows<ROW>(x0, n), sp.inv_n);
       constexpr int NFIT = E / 3 > 6 ? E / 3 : 6;  // n_fit = max(E / 3, 6) (the host checks n >= NFIT)
       double2 L, Rr;
       fit_both<ROW, NFIT>(x0, n, mean, sp, L, Rr);
@@ -266,10 +234,10 @@ __global__ void __launch_bounds__(640, 1)
       unsigned item = 0;
       if (lane == 0) item = atomicAdd(counter, 1u);
       item = __shfl_sync(0xffffffffu, item, 0);
-      const unsigned seq = div_magic(item, sp.magic_nblk);
+      const unsigned seq = div_u(item, sp.magic_nblk);
       if (seq >= my_tiles) break;
       const int k0 = (int)(item - seq * (unsigned)nblk) * R;
-      const unsigned rev = div_magic(seq, sp.magic_nb), b = seq - rev * NB;
+      const unsigned rev = div_u(seq, sp.magic_nb), b = seq - rev * NB;
       // window row j <-> input index k0 - E + j; rows outside [0, n) are zero padding
       const int jlo = E - k0 > 0 ? E - k0 : 0;
       const int jhi = n + E - k0 < W ? n + E - k0 : W;
@@ -453,7 +421,7 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
   if (fixed + 3 * per_slot > budget) return -1;
   sp.nb = (int)std::min<size_t>(8, (budget - fixed) / per_slot);
   if (const char *e = tune_env("CIB200_SMOOTH_NB")) sp.nb = std::max(2, std::min(sp.nb, atoi(e)));
-  auto magic = [](unsigned d) { return (unsigned)((1ULL << 32) / d) + 1u; };  // exact for dividends below 2^32 / d
+  auto magic = [](unsigned d) { return pipe::div_magic_for(d); };
   sp.magic_nblk = magic((unsigned)sp.nblk);
   sp.magic_nb = magic((unsigned)sp.nb);
   sp.magic_ti = magic((unsigned)std::max(1, sp.tiles_inner));

@@ -27,15 +27,9 @@
 #include <vector>
 
 #include "cib200_device.cuh"
+#include "cib200_ghost.cuh"
 
 namespace cib {
-
-struct GhostMats {
-  double poly[9][8];  // rows 0..eqs-2 used; columns 0..m-1
-  double lin[9][2];
-  double quad[9][3];
-  int poly_nodes;
-};
 
 struct SweepParams {
   long long inner, n_in, n_out, outer;
@@ -76,124 +70,6 @@ __global__ void resample_weights_kernel(const double *__restrict__ knots_out, lo
   const double v = te ? blended_weight_quintic(hb, tk, td, te, p.row, l, w) : blended_weight(hb, tk, td, p.row, l, w);
   W[(long long)l * n_out + k] = v;
   Wk[k * w + l] = v;
-}
-
-// ---- ghost fill of one line held in shared memory ----------------------------------------------
-// bl = buf + ti; line(j) = bl[(pad + j) * pitch], j = 0..n-1.  Everything below is lane-private (lane = line),
-// fully unrolled with compile-time node counts so that no array is indexed dynamically (no local memory), and
-// plain mul/add via __d*_rn so that the :detect branch decisions and the ghost values do not depend on fma
-// contraction.
-// The reference computes sum(slice)/n with Julia's `sum` (create_convolutional_coefs.jl:242,312): a @simd loop whose
-// lanes are partial sums in an unspecified (vector-width dependent) association.  Here: 8 interleaved partial sums
-// combined pairwise - the dependent chain is n/8 additions instead of n, and the result is within a few ulp of any
-// other association (the oracle's sequential loop included).
-__device__ __forceinline__ double line_mean(const double *bl, int pad, int pitch, int n) {
-  double s[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = 0.0;
-  const double *p = bl + pad * pitch;
-  int j = 0;
-  for (; j + 8 <= n; j += 8) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = __dadd_rn(s[i], p[(j + i) * pitch]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (j + i < n) s[i] = __dadd_rn(s[i], p[(j + i) * pitch]);
-  const double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
-                               __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
-  return __ddiv_rn(sum, (double)n);
-}
-
-// NS = polynomial node count of the kernel (6 for b5, 8 otherwise), EQS-1 ghosts per side
-// core on registers: y[0..7] = centred boundary values (y[0] = the boundary point itself, then inward; 0 past the line),
-// gh[j-1] = ghost j = 1..EQS-1 counted outward
-template <int NS, int EQS>
-__device__ __forceinline__ void ghost_poly_core(const double (&y)[8], int n, double mean, double h, int bc, bool right,
-                                                const GhostMats &gm, double (&gh)[EQS > 1 ? EQS - 1 : 1]) {
-  bool use_poly = false;
-  if (n >= NS && (bc == CIB200_BC_DETECT || bc == CIB200_BC_POLY)) {
-    if (bc == CIB200_BC_POLY) {
-      use_poly = true;
-    } else {
-      // natural-order window p[0..NS-1]: left p[i] = y[i]; right p[i] = y[NS-1-i]
-      double d1[NS - 1], d2[NS - 2];
-      double mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-      for (int d = 0; d < NS - 1; ++d) {
-        const double a = right ? y[NS - 2 - d] : y[d + 1];
-        const double b = right ? y[NS - 1 - d] : y[d];
-        d1[d] = __dsub_rn(a, b);
-        mn = fmin(mn, d1[d]);
-        mx = fmax(mx, d1[d]);
-      }
-      const bool periodic = __ddiv_rn(__dmul_rn(mn, mx), __dmul_rn(h, h)) < -1.0 / 10;
-      mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-      for (int d = 0; d < NS - 2; ++d) {
-        d2[d] = __dsub_rn(d1[d + 1], d1[d]);
-        mn = fmin(mn, d2[d]);
-        mx = fmax(mx, d2[d]);
-      }
-      const bool high_curv = __ddiv_rn(fabs(__dsub_rn(mx, mn)), h) > 1.0 / 2;
-      bool high_d3 = false;
-      if (NS > 4) {
-        mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-        for (int d = 0; d < NS - 3; ++d) {
-          const double v = __dsub_rn(d2[d + 1], d2[d]);
-          mn = fmin(mn, v);
-          mx = fmax(mx, v);
-        }
-        high_d3 = __ddiv_rn(fabs(__dsub_rn(mx, mn)), h) > 1.0 / 2;
-      }
-      use_poly = !periodic && !high_curv && !high_d3;
-    }
-  }
-  if (use_poly) {
-#pragma unroll
-    for (int j = 1; j <= EQS - 1; ++j) {
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < NS; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.poly[j - 1][k], y[k]));
-      gh[j - 1] = __dadd_rn(mean, acc);
-    }
-  } else if (bc == CIB200_BC_QUADRATIC) {
-#pragma unroll
-    for (int j = 1; j <= EQS - 1; ++j) {
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.quad[j - 1][k], y[k]));
-      gh[j - 1] = __dadd_rn(mean, acc);
-    }
-  } else {
-#pragma unroll
-    for (int j = 1; j <= EQS - 1; ++j) {
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) acc = __dadd_rn(acc, __dmul_rn(gm.lin[j - 1][k], y[k]));
-      gh[j - 1] = __dadd_rn(mean, acc);
-    }
-  }
-}
-
-// the same on a line held in shared memory: bl = buf + ti, line(j) = bl[(pad + j) * pitch]
-template <int NS, int EQS>
-__device__ __forceinline__ void ghost_poly_side(double *bl, int pad, int pitch, int n, double mean, double h, int bc,
-                                                bool right, const GhostMats &gm) {
-  double y[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int j = right ? (n - 1 - k) : k;
-    y[k] = k < n ? __dsub_rn(bl[(pad + j) * pitch], mean) : 0.0;
-  }
-  double gh[EQS > 1 ? EQS - 1 : 1];
-  ghost_poly_core<NS, EQS>(y, n, mean, h, bc, right, gm, gh);
-  const int row0 = right ? (pad + n) : (pad - 1);  // slot of ghost j = 1
-  const int step = right ? pitch : -pitch;
-  double *g = bl + row0 * pitch;
-#pragma unroll
-  for (int j = 1; j <= EQS - 1; ++j) g[(j - 1) * step] = gh[j - 1];
 }
 
 // ---- device-side constructor ghost fill: create_convolutional_coefs on the GPU ------------------------------------
@@ -1138,6 +1014,14 @@ static void lagrange_rows(int m, int rows, double *out, int ld) {
     }
 }
 
+void ghost_mats_for(int kernel, int eqs, GhostMats *gm) {
+  memset(gm, 0, sizeof *gm);
+  gm->poly_nodes = kernel_poly_nodes(kernel);
+  lagrange_rows(gm->poly_nodes, eqs - 1, &gm->poly[0][0], 8);
+  lagrange_rows(2, eqs - 1, &gm->lin[0][0], 2);
+  lagrange_rows(3, eqs - 1, &gm->quad[0][0], 3);
+}
+
 static double pow_int(double x, int n) {  // same restatement as cib200_eval.cu (Julia pow_body)
   if (n == 0) return 1.0;
   if (n == 1) return x;
@@ -1454,6 +1338,29 @@ static int resample_t(int ndim, const long long *n_in, const long long *n_out, c
   for (int d = 0; d < ndim; ++d) shape[d] = n_in[d];
   const T *cur = d_in;
   int rc;
+  if (sizeof(T) == sizeof(double)) {
+    // Float64 on the shipped 101-row tables: the persistent TMA-fed passes of cib200_resample.cu when every axis qualifies
+    const double *tk[CIB200_MAX_SWEEP_DIM], *td[CIB200_MAX_SWEEP_DIM], *te[CIB200_MAX_SWEEP_DIM];
+    int lin[CIB200_MAX_SWEEP_DIM], npre_a[CIB200_MAX_SWEEP_DIM], eqs_a[CIB200_MAX_SWEEP_DIM];
+    double sc[CIB200_MAX_SWEEP_DIM];
+    bool ok = true;
+    for (int d = 0; d < ndim && ok; ++d) {
+      eqs_a[d] = kernel_eqs(kernel[d]);
+      lin[d] = subgrid[d] == CIB200_SG_LINEAR;
+      npre_a[d] = CIB_N_PRE;
+      te[d] = nullptr;
+      if (lin[d] && gen_tables && gen_rows && gen_tables[d] && gen_rows[d] >= 2) ok = false;  // generated tables: generic path
+      if (ok && device_table(kernel[d], deriv[d], &tk[d])) ok = false;
+      if (ok && device_table(kernel[d], deriv[d] + (lin[d] ? 0 : 1), &td[d])) ok = false;
+      if (ok && subgrid[d] == CIB200_SG_QUINTIC && device_table(kernel[d], deriv[d] + 2, &te[d])) ok = false;
+      sc[d] = pow_int(-1.0 / (knots_in[d][1] - knots_in[d][0]), deriv[d]);  // :379
+    }
+    if (ok) {
+      rc = resample_pipe_all(ndim, n_in, n_out, (const double *)d_in, (double *)d_out, knots_in, knots_out, kernel, eqs_a, tk,
+                             td, te, lin, npre_a, sc, bcl, bcr, st);
+      if (rc >= 0) return rc;
+    }
+  }
   for (int d = 0; d < ndim; ++d) {
     const int eqs = kernel_eqs(kernel[d]);
     const int taps = 2 * eqs;
