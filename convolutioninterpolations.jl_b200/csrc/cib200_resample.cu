@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256) resample_blocks_kernel(const double *__re
                                                               double h, int eqs, long long n_coef,
                                                               const double *__restrict__ tk, const double *__restrict__ td,
                                                               const double *__restrict__ te, int linear, int npre, int shift,
-                                                              int winmax, double *__restrict__ Wd, int2 *__restrict__ binfo) {
+                                                              int even, int winmax, double *__restrict__ Wd,
+                                                              int2 *__restrict__ binfo) {
   __shared__ AxisPos pos[RS_R];
   __shared__ int s_a, s_win;
   const int b = blockIdx.x, k0 = b * RS_R, tid = threadIdx.x;
@@ -82,9 +83,10 @@ __global__ void __launch_bounds__(256) resample_blocks_kernel(const double *__re
       lo = min(lo, pos[r].base);
       hi = max(hi, pos[r].base);
     }
-    const int a = (lo + shift) & ~1;
+    // axis 0 reads the window two rows per 16-byte load: even origin, even length
+    const int a = even ? ((lo + shift) & ~1) : lo + shift;
     int win = hi + shift + taps - a;
-    win = (win + 1) & ~1;
+    if (even) win = (win + 1) & ~1;
     s_a = a;
     s_win = win;
     binfo[b] = make_int2(a, win <= winmax ? win : -1);  // -1: host bound violated, the pass kernel traps
@@ -121,7 +123,7 @@ static int host_base(double x, double x1, double h, int eqs, long long n_coef) {
 // bound by shared-memory bandwidth (measured: 124 k of 159 k cycles on the 256 x 256 x 128 -> 256^3 pass); two lines per
 // thread share the weights, 12 wavefronts for 16 DFMAs.
 template <int EQS, int BI, int RL>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __maxnreg__(RL == 2 ? 128 : 96)
     resample_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ResamplePipeParams sp,
                          const __grid_constant__ GhostMats gm, double *__restrict__ out) {
   constexpr bool AXIS0 = BI == 0;
@@ -489,26 +491,33 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
       lo = std::min(lo, base);
       hi = std::max(hi, base);
     }
-    const int a = (lo + shift) & ~1;
-    winmax = std::max(winmax, ((hi + shift + 2 * eqs - a) + 1) & ~1);
+    const int a = axis0 ? ((lo + shift) & ~1) : lo + shift;
+    const int win = hi + shift + 2 * eqs - a;
+    winmax = std::max(winmax, axis0 ? ((win + 1) & ~1) : win);
   }
-  winmax += 2;
+  // (the device recomputes the windows with the same IEEE operations; a longer one would make the pass trap, not drop taps)
   sp.winmax = winmax;
-  // roles: producer, ghost teams (2 warps each), consumers
-  sp.nteams = 2;
-  sp.ncons = 13;  // 18 warps: 112 registers per thread (the two-line consumer needs ~100)
-  if (const char *e = tune_env("CIB200_RS_NTEAMS")) sp.nteams = std::max(1, std::min(3, atoi(e)));
-  if (const char *e = tune_env("CIB200_RS_NCONS")) sp.ncons = std::max(1, std::min(17 - 2 * sp.nteams, atoi(e)));
-  ps.threads = 32 * (1 + 2 * sp.nteams + sp.ncons);
+  // roles: producer, ghost teams (2 warps each), consumers.  Two lines per consumer thread (ring slots of two tiles:
+  // the 8 broadcast weight loads of a window row then feed 16 DFMAs) when two such slots fit and every SM gets at least
+  // one of them (measured on BASELINE config 3: 0.144 ms against 0.161 ms with one line per thread everywhere); else one
+  // line per thread and a deeper ring.
   const size_t tile_bytes = (size_t)32 * sp.H * 8;
   const size_t wd_bytes = (size_t)sp.nblk * winmax * RS_R * 8 + (size_t)((sp.nblk + 1) & ~1) * 8;
-  const size_t fixed = wd_bytes + 16 * sizeof(RsTileHdr) + (axis0 ? (size_t)sp.ncons * 32 * (RS_R + 1) * 8 : 0) + 8 * 3 * 8 + 16 +
-                       1024 /* alignment slack */;
   const size_t budget = (size_t)rs_smem_budget();
+  auto fixed_for = [&](int ncons) {
+    return wd_bytes + 16 * sizeof(RsTileHdr) + (axis0 ? (size_t)ncons * 32 * (RS_R + 1) * 8 : 0) + 8 * 3 * 8 + 16 +
+           1024 /* alignment slack */;
+  };
+  sp.nteams = 2;
+  if (const char *e = tune_env("CIB200_RS_NTEAMS")) sp.nteams = std::max(1, std::min(3, atoi(e)));
+  ps.rl = (fixed_for(11) + 4 * tile_bytes <= budget && sp.ntiles >= 2 * (long long)sm_count()) ? 2 : 1;
+  if (const char *e = tune_env("CIB200_RS_RL")) ps.rl = (atoi(e) == 2 && fixed_for(11) + 4 * tile_bytes <= budget) ? 2 : 1;
+  // 128 registers x 16 warps (two lines per thread) or 96 x 20 warps
+  sp.ncons = (ps.rl == 2 ? 15 : 19) - 2 * sp.nteams;
+  if (const char *e = tune_env("CIB200_RS_NCONS")) sp.ncons = std::max(1, std::min(sp.ncons, atoi(e)));
+  ps.threads = 32 * (1 + 2 * sp.nteams + sp.ncons);
+  const size_t fixed = fixed_for(sp.ncons);
   if (fixed + 3 * tile_bytes > budget) return false;
-  // two lines per consumer thread (ring slots of two tiles) whenever two such slots fit; else one line, >= 3 slots
-  ps.rl = (fixed + 4 * tile_bytes <= budget && sp.ntiles >= 2 * (long long)sm_count()) ? 2 : 1;
-  if (const char *e = tune_env("CIB200_RS_RL")) ps.rl = (atoi(e) == 2 && fixed + 4 * tile_bytes <= budget) ? 2 : 1;
   sp.nb = (int)std::min<size_t>(8, (budget - fixed) / (tile_bytes * ps.rl));
   if (const char *e = tune_env("CIB200_RS_NB")) sp.nb = std::max(2, std::min(sp.nb, atoi(e)));
   ps.smem = fixed + (size_t)sp.nb * tile_bytes * ps.rl;
@@ -590,7 +599,7 @@ int resample_pipe_all(int ndim, const long long *n_in, const long long *n_out, c
     const double h = sp.h;
     const double x1 = knots_in[d][0] - (double)(ps.eqs - 1) * h;
     resample_blocks_kernel<<<sp.nblk, 256, 0, st>>>(d_ko, sp.n_out, x1, h, ps.eqs, (long long)sp.n_in + 2 * sp.pad, tk[d], td[d],
-                                                    te[d], linear[d], npre[d], sp.padx - sp.pad, sp.winmax, d_wd, d_bi);
+                                                    te[d], linear[d], npre[d], sp.padx - sp.pad, ps.bi == 0 ? 1 : 0, sp.winmax, d_wd, d_bi);
     CIB_LAUNCHED();
     sp.Wd = d_wd;
     sp.binfo = d_bi;
