@@ -431,11 +431,13 @@ def main():
         qh = [x[psub].cpu().numpy() for x in xs]
         ref = oitp.eval(*qh)
         got = out[psub].cpu().numpy()
-        S = float(np.abs(oitp.coefs).max())
+        # relative to the magnitude of the FIELD (max |values|), not of the ghost-padded grid: the polynomial ghosts of a
+        # noisy field grow by orders of magnitude towards the corners and would make any error look small
+        S = vmax
         perr = np.abs(got - ref) / np.maximum(np.abs(ref), S)
         parity = {"max_rel_err": float(perr.max()), "n": int(len(ref)), "tol": 1e-12, "against": "oracle (port)",
                   "what": f"every {stride}-th result of the last timed step vs oracle/cib_oracle.c on the same "
-                          f"{args.grid}^3 grid; relative to max(|ref|, max|coefs|)",
+                          f"{args.grid}^3 grid; relative to max(|ref|, max|values|)",
                   "seconds": time.perf_counter() - t0}
         assert parity["max_rel_err"] <= 1e-12, f"timed result differs from the oracle: {parity}"
         del oitp, qh, ref, got

@@ -312,6 +312,47 @@ static int ensure_stage(cib200_itp *h, size_t bytes) {
   return CIB200_OK;
 }
 
+static int ensure_host_stage(cib200_itp *h, size_t bytes) {
+  if (h->h_stage_bytes >= bytes) return CIB200_OK;
+  for (int i = 0; i < cib200_itp::NSTAGE; ++i) {
+    if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
+    h->h_stage[i] = nullptr;
+  }
+  h->h_stage_bytes = 0;
+  for (int i = 0; i < cib200_itp::NSTAGE; ++i) CIB_CUDA(cudaHostAlloc(&h->h_stage[i], bytes, cudaHostAllocDefault));
+  h->h_stage_bytes = bytes;
+  return CIB200_OK;
+}
+
+// is this host pointer pageable (neither cudaHostAlloc'ed nor cudaHostRegister'ed)?
+static bool is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy split over a few host threads (one thread moves ~10 GB/s; a PCIe 5 x16 link wants ~50)
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nt = std::min<size_t>(std::min<unsigned>(8u, hw), bytes >> 22);  // >= 4 MB per thread
+  if (nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t o = t * per;
+    if (o >= bytes) break;
+    const size_t m = std::min(per, bytes - o);
+    pool.emplace_back([=]() { memcpy((char *)dst + o, (const char *)src + o, m); });
+  }
+  for (auto &t : pool) t.join();
+}
+
 int prof_mark(cib200_itp *h, int i, cudaStream_t st) {
   if (!h->profiling) return CIB200_OK;
   if (!h->prof_ev[0])
@@ -678,6 +719,7 @@ int32_t cib200_itp_destroy(cib200_itp *h) {
   if (h->d_status) cudaFree(h->d_status);
   for (int i = 0; i < cib200_itp::NSTAGE; ++i) {
     if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+    if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
@@ -819,7 +861,16 @@ static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long n
   // 512^3 grid; the pipeline is then H2D-bound, 24 B/query over PCIe), smaller for small batches so that at least four
   // chunks overlap.  Measured on B200 (512^3 b5, pinned buffers): 10^9 queries 1.99e9 evals/s with 2^26 (1.66e9 with
   // 2^24); geometric ramp-up / ramp-down schedules were tried and lost to uniform chunks (small chunks bin poorly).
+  // Pageable caller buffers (what a caller that never pins hands over): cudaMemcpyAsync from pageable memory is staged
+  // by the runtime through one small internal buffer, synchronously (measured: 0.30e9 evals/s against 1.9e9 with pinned
+  // buffers).  Instead the coordinates are packed into the handle's own pinned ring by a few host threads while the
+  // device works on the previous chunk, and results are unpacked from it the same way.
+  bool stage_in = false;
+  for (int d = 0; d < nd; ++d) stage_in = stage_in || is_pageable(c_in.x[d]);
+  const bool stage_out = is_pageable(out);
+  const bool staged = stage_in || stage_out;
   int chunk_log2 = nq >= (1LL << 28) ? 26 : (nq >= (1LL << 27) ? 25 : 24);
+  if (staged) chunk_log2 = std::min(chunk_log2, 24);  // 3 x 2^24 x 32 B = 1.5 GB of pinned memory at most
   if (const char *e = tune_env("CIB200_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(30, atoi(e)));
   std::vector<long long> sizes;
   for (long long rem = nq; rem > 0;) {
@@ -831,21 +882,41 @@ static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long n
   for (long long m : sizes) chunk = std::max(chunk, m);
   // per buffer: nd coordinate chunks + 1 result chunk
   if ((rc = ensure_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
+  if (staged && (rc = ensure_host_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
   s_in = h->streams[0];
   s_comp = h->streams[1];
   s_out = h->streams[2];
   if ((rc = reset_status(h, s_comp))) return rc;
   constexpr int NS = cib200_itp::NSTAGE;
   long long q0 = 0;
+  long long slot_q0[NS] = {0}, slot_m[NS] = {0};
+  auto unpack = [&](int b) -> int {  // results of the chunk that last used slot b: pinned ring -> caller's array
+    CIB_CUDA(cudaEventSynchronize(h->ev_out[b]));
+    par_memcpy((char *)out + es * (size_t)slot_q0[b], (const char *)h->h_stage[b] + es * (size_t)chunk * nd, es * (size_t)slot_m[b]);
+    return CIB200_OK;
+  };
   for (size_t ichunk = 0; ichunk < sizes.size(); ++ichunk) {
     const int b = (int)(ichunk % NS);
     const long long m = sizes[ichunk];
     char *base = (char *)h->d_stage[b];
     Coords c = c_in;
-    if (ichunk >= (size_t)NS) CIB_CUDA(cudaStreamWaitEvent(s_in, h->ev_out[b], 0));  // buffer b drained by its last D2H
+    if (ichunk >= (size_t)NS) {
+      CIB_CUDA(cudaStreamWaitEvent(s_in, h->ev_out[b], 0));  // device buffer b drained by its last D2H
+      if (stage_out) {
+        if ((rc = unpack(b))) return rc;
+      } else if (stage_in) {
+        CIB_CUDA(cudaEventSynchronize(h->ev_in[b]));  // the pinned slot's last H2D has left it
+      }
+    }
     for (int d = 0; d < nd; ++d) {
       char *dst = base + es * (size_t)chunk * d;
-      CIB_CUDA(cudaMemcpyAsync(dst, (const char *)c_in.x[d] + es * (size_t)q0, es * (size_t)m, cudaMemcpyHostToDevice, s_in));
+      const char *src = (const char *)c_in.x[d] + es * (size_t)q0;
+      if (stage_in) {
+        char *hp = (char *)h->h_stage[b] + es * (size_t)chunk * d;
+        par_memcpy(hp, src, es * (size_t)m);
+        src = hp;
+      }
+      CIB_CUDA(cudaMemcpyAsync(dst, src, es * (size_t)m, cudaMemcpyHostToDevice, s_in));
       c.x[d] = dst;
     }
     CIB_CUDA(cudaEventRecord(h->ev_in[b], s_in));
@@ -855,9 +926,17 @@ static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long n
     if ((rc = eval_dispatch(h, c, dout, m, s_comp))) return rc;
     CIB_CUDA(cudaEventRecord(h->ev_comp[b], s_comp));
     CIB_CUDA(cudaStreamWaitEvent(s_out, h->ev_comp[b], 0));
-    CIB_CUDA(cudaMemcpyAsync((char *)out + es * (size_t)q0, dout, es * (size_t)m, cudaMemcpyDeviceToHost, s_out));
+    void *hdst = stage_out ? (void *)((char *)h->h_stage[b] + es * (size_t)chunk * nd) : (void *)((char *)out + es * (size_t)q0);
+    CIB_CUDA(cudaMemcpyAsync(hdst, dout, es * (size_t)m, cudaMemcpyDeviceToHost, s_out));
     CIB_CUDA(cudaEventRecord(h->ev_out[b], s_out));
+    slot_q0[b] = q0;
+    slot_m[b] = m;
     q0 += m;
+  }
+  if (stage_out) {  // the last chunks, oldest first
+    const size_t nch = sizes.size();
+    for (size_t ichunk = nch > (size_t)NS ? nch - NS : 0; ichunk < nch; ++ichunk)
+      if ((rc = unpack((int)(ichunk % NS)))) return rc;
   }
   CIB_CUDA(cudaStreamSynchronize(s_out));
   int code;

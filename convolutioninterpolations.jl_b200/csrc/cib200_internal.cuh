@@ -109,6 +109,10 @@ struct cib200_itp {
   static constexpr int NSTAGE = 3;
   void *d_stage[NSTAGE];
   size_t stage_bytes;
+  // pinned twin of the ring for PAGEABLE caller buffers (lazily allocated): the caller's arrays are packed into /
+  // unpacked from it by a few host threads while the device works on the previous chunk
+  void *h_stage[NSTAGE];
+  size_t h_stage_bytes;
   cudaStream_t streams[3];          // 0: H2D, 1: compute, 2: D2H
   cudaEvent_t ev_in[NSTAGE], ev_comp[NSTAGE], ev_out[NSTAGE];
   // scratch for the binned strategy (lazily allocated, grows)
