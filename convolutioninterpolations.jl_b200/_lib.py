@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcib200.so")
+# (CIB200_SO_NAME: load an A/B build of the library, development only - see build.py)
+SO_PATH = os.path.join(_HERE, os.environ.get("CIB200_SO_NAME", "libcib200.so"))
 
 OK, EOOB, ENAN, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(7)
 F64, F32 = 0, 1

@@ -12,7 +12,10 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcib200.so")
 SOURCES = ["cib200_api.cu", "cib200_eval.cu", "cib200_sweep.cu", "cib200_binned.cu", "cib200_evalnd.cu", "cib200_integral.cu", "cib200_smooth.cu", "cib200_resample.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+# CIB200_EXTRA_NVCC_FLAGS / CIB200_SO_NAME: A/B builds of kernel variants during development (tools/ab_build.sh)
+SO = os.path.join(HERE, os.environ.get("CIB200_SO_NAME", "libcib200.so"))
+FLAGS = [*os.environ.get("CIB200_EXTRA_NVCC_FLAGS", "").split(),
+         "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "--fmad=true",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

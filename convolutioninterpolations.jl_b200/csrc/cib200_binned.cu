@@ -883,6 +883,14 @@ bool binned_supported(const cib200_itp *h) {
   if (T < 4) return false;
   long long nt = 1;
   for (int d = 0; d < 3; ++d) nt *= (p.nk[d] - 2 * p.eqs[d] + 1 + T - 1) / T;
+  // the evaluation kernels stage the brick, the interpolant's distinct tables and per-warp scratch (>= 4 warps): an
+  // interpolant whose tables do not fit (e.g. :b13 with three different derivative orders: six 14.5 kB tables) stays
+  // on the gather kernel instead of failing at launch time
+  int dev = 0, max_smem = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t need = (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + 4 * (size_t)(32 * 3 * 4 + 64 + 256)) + 32 + 8 * 96;
+  if (need > (size_t)max_smem) return false;
   return nt + 1 <= MAX_BINS && encode_fn() != nullptr;
 }
 

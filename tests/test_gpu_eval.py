@@ -129,6 +129,28 @@ def test_c5_full_grid_512_cube_2e26_queries_against_the_oracle(ci, oracle):
         del xs, out
 
 
+def test_auto_mode_falls_back_when_the_tables_do_not_fit_next_to_the_brick(ci, oracle):
+    """:b13 with three different derivative orders stages six distinct 14.5 kB tables: brick + tables + scratch exceed
+    the shared memory of an SM, so a batch above the AUTO threshold (2^22 queries) must take the gather kernel
+    instead of failing at launch time (the same interpolant works for small batches)."""
+    import torch
+    rng = np.random.default_rng(5)
+    g = np.linspace(0.0, 1.0, 28)
+    v = _field((28, 28, 28), rng, noise=0.01)
+    kw = dict(kernel="b13", derivative=(0, 2, 4), bc="detect")
+    o = oracle.convolution_interpolation((g, g, g), v, **kw)
+    itp = ci.convolution_interpolation((g, g, g), v, **kw)
+    nq = (1 << 22) + 3
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in range(3)]
+    out = itp.eval(*xs)
+    sub = slice(0, nq, 97)
+    ref = o.eval(*[x[sub].cpu().numpy() for x in xs])
+    err = rel_err(out[sub].cpu().numpy(), ref, _scale(o))
+    assert err.max() <= TOL64, err.max()
+
+
 @pytest.mark.parametrize("kernel,deriv", [("b5", 0), ("b5", (1, 0, 2)), ("b7", (0, 3, 1)), ("b13", 0), ("b13", (1, 0, 0)), ("a4", 0)])
 def test_cuda_path_agrees_with_the_direct_evaluator(ci, oracle, kernel, deriv):
     """Second, independent oracle: the reference's DIRECT evaluators (kernel polynomials by Horner, no tables;
