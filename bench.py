@@ -197,17 +197,17 @@ def secondary_sweeps(peak):
     import torch
     import convitp_b200 as ci
 
-    def best_ms(fn):
-        for _ in range(3):
+    def best_ms(fn, reps=10):
+        for _ in range(3 if reps >= 10 else 1):
             fn()
         torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         ev[0].record()
-        for i in range(10):
+        for i in range(reps):
             fn()
             ev[i + 1].record()
         torch.cuda.synchronize()
-        return min(ev[i].elapsed_time(ev[i + 1]) for i in range(10))
+        return min(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
 
     rng = np.random.default_rng(SEED)
     out = {}
@@ -230,6 +230,30 @@ def secondary_sweeps(peak):
                                       "roofline_frac": 4 * 16 * n ** 4 / (ms * 1e-3) / 1e9 / peak,
                                       "model": "4 passes x 16 B per grid point (40^4 is L2-resident)",
                                       "fp64_floor_ms": fp64_floor_ms, "fp64_frac": fp64_floor_ms / ms}
+    # north_star names :b5 / :b13: the same 512^3 evaluation with :b13 (18^3 stencil: binned kernel, 25^3 brick per 8^3
+    # cells), and with :b5 in the opt-in Float32 mode; 2.5e8 device-resident queries each
+    n5 = 512
+    g5, v5 = make_grid(n5)
+    nq5 = 250_000_000
+    q5 = [torch.rand(nq5, dtype=torch.float64, device="cuda") for _ in range(3)]
+    o5 = torch.empty(nq5, dtype=torch.float64, device="cuda")
+    it13 = ci.convolution_interpolation(g5, v5, kernel="b13", bc="poly", coefs_on="device")
+    ms = best_ms(lambda: it13.eval(*q5, out=o5), reps=3)
+    out["b13_3d_512"] = {"value": nq5 / (ms * 1e-3), "unit": "evals/s", "ms": ms, "queries": nq5,
+                         "roofline_frac": nq5 * (32 + 8 * 18 ** 3) / (ms * 1e-3) / 1e9 / peak,
+                         "model": "gather model: 24 + 8 B + 18^3 x 8 B = 46.7 kB per evaluation"}
+    del it13, o5
+    g32 = tuple(np.asarray(k, dtype=np.float32) for k in g5)
+    it32 = ci.convolution_interpolation(g32, v5.astype(np.float32), kernel="b5", bc="poly")
+    del v5
+    q32 = [x.to(torch.float32) for x in q5]
+    del q5
+    o32 = torch.empty(nq5, dtype=torch.float32, device="cuda")
+    ms = best_ms(lambda: it32.eval(*q32, out=o32), reps=3)
+    out["b5_3d_512_float32"] = {"value": nq5 / (ms * 1e-3), "unit": "evals/s", "ms": ms, "queries": nq5,
+                                "roofline_frac": nq5 * (16 + 4 * 1000) / (ms * 1e-3) / 1e9 / peak,
+                                "model": "gather model in Float32: 12 + 4 B + 10^3 x 4 B = 4 016 B per evaluation"}
+    del it32, q32, o32
     # antiderivative interpolant (derivative = -1 on every axis): 3-D :b5 on 256^3, 10^7 random queries
     x = np.linspace(0, 1, 256)
     itg = ci.convolution_interpolation((x, x, x), rng.random((256,) * 3), kernel="b5", derivative=-1, bc="poly",
@@ -542,7 +566,15 @@ def main():
                              "registers: `traffic` is the measured DRAM bytes of the same kernel, and the kernel's own bound "
                              "is shared-memory bandwidth (DESIGN.md 5)",
                     "peak_source": peak_src, "traffic_source": tr.get("source"),
-                    "dram_bytes_per_eval_measured": tr.get("dram_bytes_per_eval")}
+                    "dram_bytes_per_eval_measured": tr.get("dram_bytes_per_eval"),
+                    # what bounds the kernel (the gather-model frac above does not say): measured DRAM bytes over the
+                    # live kernel time against the HBM peak, and the ncu figures of the same launch shape
+                    "dram_frac": (tr.get("dram_bytes_per_eval") and
+                                  tr["dram_bytes_per_eval"] * nq / (kernel_ms * 1e-3) / 1e9 / peak),
+                    "fp64_frac": tr.get("fp64_pipe_active_pct") and tr["fp64_pipe_active_pct"] / 100.0,
+                    "smem_wavefronts_per_eval": tr.get("smem_wavefronts_per_eval"),
+                    "smem_frac": tr.get("l1tex_throughput_pct") and tr["l1tex_throughput_pct"] / 100.0,
+                    "bound_by": "shared-memory bandwidth (l1tex), then the FP64 pipe; DRAM is at dram_frac" if cellrun else None}
         cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,

@@ -29,6 +29,7 @@ SYMBOLS = [
     "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itp_eval_multi", "cib200_device_count",
     "cib200_set_device", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
     "cib200_itp_create_tables", "cib200_itpnd_create_tables", "cib200_resample_tables",
+    "cib200_itgnd_create", "cib200_itgnd_destroy", "cib200_itgnd_eval", "cib200_itgnd_eval_grid",
     "cib200_itg_create", "cib200_itg_create_tables", "cib200_itg_destroy", "cib200_itg_eval", "cib200_itg_eval_grid", "cib200_itg_get",
 ]
 
@@ -95,6 +96,10 @@ def lib():
     L.cib200_itpnd_destroy.argtypes = [vp]
     L.cib200_itpnd_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
     L.cib200_itpnd_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itgnd_create.argtypes = [i32, vp, vp, C.POINTER(vp), vp, vp, vp, i32, C.POINTER(vp), vp, vp, C.POINTER(vp)]
+    L.cib200_itgnd_destroy.argtypes = [vp]
+    L.cib200_itgnd_eval.argtypes = [vp, i64, C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
+    L.cib200_itgnd_eval_grid.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), vp, i32, vp, C.POINTER(i64)]
     L.cib200_itg_create.argtypes = [C.POINTER(ItpDesc), C.POINTER(vp)]
     L.cib200_itg_create_tables.argtypes = [C.POINTER(ItpDesc), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
     L.cib200_itg_destroy.argtypes = [vp]

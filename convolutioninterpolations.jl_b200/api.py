@@ -202,9 +202,21 @@ def _require_accelerated(kernels, derivs, subgrids, ndim, what, perdim=True):
             # directions to :linear K~ tables and has no tails: reference path.
             if what != "convolution_interpolation":
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what} does not support antiderivatives")
-            if dv != -1 or ndim > 3:
-                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative={tuple(derivs)}: antiderivatives are "
-                                           "accelerated in 1-3 dimensions (N >= 4 resolves to :linear K~ tables)")
+            if dv != -1:
+                raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative={tuple(derivs)} is not a valid order")
+            if ndim > 3:
+                # N >= 4: every axis on the :linear subgrid with generated tables, three functors
+                # (convolution_fast_integration_nd.jl, convolution_fast_mixed_3_integral_dims.jl,
+                # convolution_fast_mixed_N_integral_dims.jl): cib200_itgnd_*.  One or two integral axes in N >= 4
+                # dimensions (the N-D instances of convolution_fast_mixed_{1_integral_dim,2_integral_dims}.jl) stay on
+                # the reference path.
+                n_int = sum(1 for x in derivs if x == -1)
+                if n_int < 3:
+                    raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: derivative={tuple(derivs)}: {n_int} integral "
+                                               f"axes in {ndim} dimensions are not on the accelerated path (3 or more are)")
+                if sg != "linear":
+                    raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: N >= 4 antiderivatives use the :linear subgrid")
+                continue
             if sg not in ("cubic", "quintic"):
                 raise UnsupportedModeError(_lib.EUNSUPPORTED, f"{what}: antiderivative with the :{sg} subgrid needs "
                                            "generated tables")
@@ -330,6 +342,34 @@ class FastConvolutionInterpolation:
             self.knots.append(ext)
         self.knots = tuple(self.knots)
         # ---- upload ----
+        if nd >= 4 and self._itg:
+            # antiderivative / mixed interpolants in N >= 4 dimensions: convolution_fast_integration_nd.jl (every axis
+            # integral: its loops stop at domain_size[d]), convolution_fast_mixed_3_integral_dims.jl,
+            # convolution_fast_mixed_N_integral_dims.jl - cib200_itgnd_*
+            self._nd = True
+            self._itgnd = True
+            rows = self.linear_rows
+            tabs = [np.asfortranarray(_tables.generated_table(self.kernel[d], int(self.derivative[d]), rows))
+                    if rows != 101 else None for d in range(nd)]
+            self._gen_tables = tabs
+            cs = (C.c_int64 * nd)(*cshape)
+            kp = (C.c_void_p * nd)(*[k.ctypes.data for k in self.knots])
+            dv = (C.c_int32 * nd)(*[int(d) for d in self.derivative])
+            tp = (C.c_void_p * nd)(*[None if t is None else t.ctypes.data for t in tabs])
+            npre = (C.c_int32 * nd)(*[0 if t is None else t.shape[0] for t in tabs])
+            all_int = all(d == -1 for d in self.derivative)
+            ext = (C.c_int64 * nd)(*(v.shape if all_int else cshape))
+            handle = C.c_void_p()
+            if coefs_on == "device":
+                coefs_ptr = self.coefs.ctypes.data
+            check(L.cib200_itgnd_create(nd, cs, coefs_ptr, kp, hh, kid, dv, EXTRAP_IDS[_extrap], tp, npre, ext,
+                                        C.byref(handle)))
+            self._handle = handle
+            self._handles = [handle]
+            self.devices = None
+            self.eval_mode = "integral-nd"
+            self.anchor = tuple(float(k[e - 1]) if d == -1 else 0.0 for k, e, d in zip(self.knots, self.eqs, self.derivative))
+            return
         if nd >= 4:
             # HigherDimension evaluators (eager_nd.jl:97-140 / perdim_nd.jl:4-36): every axis on the :linear subgrid
             self._nd = True
@@ -430,7 +470,7 @@ class FastConvolutionInterpolation:
 
     def _entry(self, name):
         """the C-ABI entry point of this interpolant's family: cib200_itp_* / cib200_itpnd_* / cib200_itg_*"""
-        fam = "itg" if getattr(self, "_itg", False) else ("itpnd" if self._nd else "itp")
+        fam = "itgnd" if getattr(self, "_itgnd", False) else ("itg" if getattr(self, "_itg", False) else ("itpnd" if self._nd else "itp"))
         return getattr(lib(), f"cib200_{fam}_{name}")
 
     def set_eval_mode(self, mode):

@@ -36,6 +36,16 @@ namespace cib {
 static constexpr int BRICK_SIDE = 25;        // T + 2E - 1
 static constexpr int BRICK_PITCH = 26;       // inner TMA box extent: 26 * 8 B is a multiple of 16 B
 static constexpr int BRICK_DOUBLES = BRICK_PITCH * BRICK_SIDE * BRICK_SIDE;
+// Float32 mode (coefficients / queries / results in float, arithmetic in double): the brick is staged as floats
+// (inner extent 28: 28 * 4 B is a multiple of 16 B) and converted when a lane loads its stencil share
+template <typename T>
+struct BrickGeom {
+  static constexpr int PITCH = sizeof(T) == 8 ? 26 : 28;
+  static constexpr int PLANE = PITCH * BRICK_SIDE;
+  static constexpr int ELEMS = PLANE * BRICK_SIDE;
+  static constexpr int BYTES = (ELEMS * (int)sizeof(T) + 15) & ~15;
+  static constexpr int DOUBLES = BYTES / 8;  // where the staged tables start, in doubles from the brick
+};
 static constexpr int CHUNK_QUERIES = 16384;  // queries per work item
 static constexpr int BIN_U = 4;              // queries per thread and iteration in the binning passes
 static constexpr int MAX_BINS = 49152;       // u32 histogram must fit one CTA's shared memory (192 KB)
@@ -113,6 +123,7 @@ __device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, co
   return (t[2] * g.nt[1] + t[1]) * g.nt[0] + t[0];
 }
 
+template <typename T>
 __global__ void __launch_bounds__(1024, 1) bin_count_kernel(ItpParams p, BinGeom g, Coords c, long long nq,
                                                             unsigned *__restrict__ hist) {
   extern __shared__ unsigned sh[];
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(1024, 1) bin_count_kernel(ItpParams p, BinGeom
     for (int u = 0; u < BIN_U; ++u) {
       const long long q = qb + (long long)u * blockDim.x;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? ((const double *)c.x[d])[q] : 0.0;
+      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? (double)((const T *)c.x[d])[q] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < BIN_U; ++u) {
@@ -213,6 +224,7 @@ __global__ void bin_offsets_kernel(BinGeom g, int nblk, unsigned *__restrict__ h
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGeom g, Coords c, long long nq,
                                                               unsigned *hist, Record *__restrict__ rec, int dbg) {
   extern __shared__ unsigned sh[];
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
     for (int u = 0; u < BIN_U; ++u) {
       const long long q = qb + (long long)u * blockDim.x;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? ((const double *)c.x[d])[q] : 0.0;
+      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? (double)((const T *)c.x[d])[q] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < BIN_U; ++u) {
@@ -390,18 +402,19 @@ struct BinnedWarpSmem {
 // so one LDS instruction (immediate offset, no index arithmetic) feeds one DFMA, and the per-query weights a
 // lane needs are 1 + KM + W values.  The 32 lane partials of 8 consecutive queries are combined with a
 // reduce-scatter butterfly (9 shuffle steps per 8 queries instead of 40).
-template <int E>
+template <int E, typename TC>
 __global__ void __launch_bounds__(512, 1)
     eval_binned_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
                        const Record *__restrict__ rec, const WorkItem *__restrict__ items,
-                       unsigned *__restrict__ n_items, double *__restrict__ out, int use_tma) {
+                       unsigned *__restrict__ n_items, TC *__restrict__ out, int use_tma) {
   using WS = BinnedWarpSmem<E>;
+  using BG = BrickGeom<TC>;
   constexpr int W = 2 * E, G = 32 / W, ACTIVE = W * G, KM = (W + G - 1) / G;
-  constexpr int PITCH = BRICK_PITCH, PLANE = BRICK_PITCH * BRICK_SIDE;
+  constexpr int PITCH = BG::PITCH, PLANE = BG::PLANE;
   constexpr int WAXH = WS::WAX / 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *brick = (double *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][BRICK_PITCH], axis 0 contiguous
-  double *tab = brick + BRICK_DOUBLES;
+  TC *brick = (TC *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][PITCH], axis 0 contiguous
+  double *tab = (double *)smem_raw + BG::DOUBLES;
   const double *tk[3];
   const double *td[3];
   stage_tables(p, tab, tk, td);
@@ -443,18 +456,18 @@ __global__ void __launch_bounds__(512, 1)
     if (use_tma) {
       if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old brick before the async write
-        mbar_expect_tx(bar, BRICK_DOUBLES * 8);
+        mbar_expect_tx(bar, BG::ELEMS * (int)sizeof(TC));
         tma_load_3d(brick, &tmap, org[0], org[1], org[2], bar);
       }
       mbar_wait(bar, parity);
       parity ^= 1;
     } else {
       // plain cooperative copy (driver without cuTensorMapEncodeTiled): same brick image, zero outside
-      const double *__restrict__ cg = (const double *)p.coefs;
-      for (int e = threadIdx.x; e < BRICK_DOUBLES; e += blockDim.x) {
-        const int bx = e % BRICK_PITCH, by = (e / BRICK_PITCH) % BRICK_SIDE, bz = e / (BRICK_PITCH * BRICK_SIDE);
+      const TC *__restrict__ cg = (const TC *)p.coefs;
+      for (int e = threadIdx.x; e < BG::ELEMS; e += blockDim.x) {
+        const int bx = e % PITCH, by = (e / PITCH) % BRICK_SIDE, bz = e / PLANE;
         const int gx = org[0] + bx, gy = org[1] + by, gz = org[2] + bz;
-        brick[e] = (gx < p.nk[0] && gy < p.nk[1] && gz < p.nk[2]) ? __ldg(cg + gx + (long long)gy * p.s1 + (long long)gz * p.s2) : 0.0;
+        brick[e] = (gx < p.nk[0] && gy < p.nk[1] && gz < p.nk[2]) ? __ldg(cg + gx + (long long)gy * p.s1 + (long long)gz * p.s2) : (TC)0;
       }
       __syncthreads();
     }
@@ -517,12 +530,12 @@ __global__ void __launch_bounds__(512, 1)
             double wy[KM];
 #pragma unroll
             for (int k = 0; k < KM; ++k) wy[k] = ((G - 1) + k * G < W || kval[k]) ? wq[W + gle + k * G] : 0.0;
-            const double *base = brick + m.x + lane_off;
+            const TC *base = brick + m.x + lane_off;
             // sum_k wy[k] sum_n c[k][n] wz[n], even / odd n in separate chains - the association of
             // eval_cellrun_kernel, so that both kernels return the same bits for the same query
-            auto coef = [&](int k, int n) {
-              if ((G - 1) + k * G < W) return base[k * G * PITCH + n * PLANE];  // compile-time: every lane group has this tap
-              return kval[k] ? base[k * G * PITCH + n * PLANE] : 0.0;          // last, partially populated tap
+            auto coef = [&](int k, int n) -> double {
+              if ((G - 1) + k * G < W) return (double)base[k * G * PITCH + n * PLANE];  // compile-time: every lane group has this tap
+              return kval[k] ? (double)base[k * G * PITCH + n * PLANE] : 0.0;          // last, partially populated tap
             };
             double be[KM], bo[KM];
             {
@@ -577,7 +590,7 @@ __global__ void __launch_bounds__(512, 1)
         s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
         if ((lane >> 3) == (j0 >> 3)) res = s1;
       }
-      if (have) out[idx] = apply_scale<3>(res, sc);
+      if (have) out[idx] = (TC)apply_scale<3>(res, sc);
     }
   }
 }
@@ -597,29 +610,31 @@ struct CellrunWarpSmem {
   static constexpr int DOUBLES = HB + MISC + WQ;
 };
 
-template <int E>
+template <int E, typename TC>
 __global__ void __launch_bounds__(384, 1)
     eval_cellrun_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
                         const Record *__restrict__ rec, const WorkItem *__restrict__ items,
-                        unsigned *__restrict__ n_items, double *__restrict__ out, int use_tma) {
+                        unsigned *__restrict__ n_items, TC *__restrict__ out, int use_tma) {
   using WS = CellrunWarpSmem<E>;
+  using BG = BrickGeom<TC>;
   constexpr int W = 2 * E, G = 32 / W, ACTIVE = W * G, KM = (W + G - 1) / G;
   static_assert(3 * W <= 32, "one lane per (axis, tap) pair");
-  constexpr int PITCH = BRICK_PITCH, PLANE = BRICK_PITCH * BRICK_SIDE;
+  constexpr int PITCH = BG::PITCH, PLANE = BG::PLANE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *brick = (double *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][BRICK_PITCH], axis 0 contiguous
-  double *tab = brick + BRICK_DOUBLES;
+  TC *brick = (TC *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][PITCH], axis 0 contiguous
+  double *smd = (double *)smem_raw;  // the same memory in doubles: tables and per-warp scratch follow the brick
+  double *tab = smd + BG::DOUBLES;
   const double *tk[3];
   const double *td[3];
   stage_tables(p, tab, tk, td);
   const int nwarps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wbase = BRICK_DOUBLES + ((tables_smem_doubles(p) + 1) & ~1);  // doubles from the start of shared memory
-  double *wsm = brick + wbase + warp * WS::DOUBLES;
+  const int wbase = BG::DOUBLES + ((tables_smem_doubles(p) + 1) & ~1);  // doubles from the start of shared memory
+  double *wsm = smd + wbase + warp * WS::DOUBLES;
   double *hbs = wsm;                        // [32][3][4]
   int *misc = (int *)(wsm + WS::HB);        // [32][4]
   double *wq = wsm + WS::HB + WS::MISC;     // [8][32]
-  unsigned long long *bar = (unsigned long long *)(brick + wbase + nwarps * WS::DOUBLES);
+  unsigned long long *bar = (unsigned long long *)(smd + wbase + nwarps * WS::DOUBLES);
   unsigned *slot = (unsigned *)(bar + 1);  // [2]
   double *kt = (double *)(bar + 2);         // [3][32]: the stored knots the tile's queries can select
   if (threadIdx.x == 0) {
@@ -638,8 +653,8 @@ __global__ void __launch_bounds__(384, 1)
   // weight role of this lane: axis wa, tap wcol; table offsets relative to `brick` keep the loads in the shared window
   const bool wrole = lane < 3 * W;
   const int wa = wrole ? lane / W : 2, wcol = wrole ? lane - wa * W : 0;
-  const int tko = (int)((wa == 0 ? tk[0] : (wa == 1 ? tk[1] : tk[2])) - brick) + wcol;
-  const int tdo = (int)((wa == 0 ? td[0] : (wa == 1 ? td[1] : td[2])) - brick) + wcol;
+  const int tko = (int)((wa == 0 ? tk[0] : (wa == 1 ? tk[1] : tk[2])) - smd) + wcol;
+  const int tdo = (int)((wa == 0 ? td[0] : (wa == 1 ? td[1] : td[2])) - smd) + wcol;
   const unsigned total_items = n_items[0];
   unsigned parity = 0;
   double creg[KM][W];  // this lane's share of the current cell's stencil: c[l, gle + k G, n]
@@ -663,18 +678,18 @@ __global__ void __launch_bounds__(384, 1)
     if (use_tma) {
       if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, BRICK_DOUBLES * 8);
+        mbar_expect_tx(bar, BG::ELEMS * (int)sizeof(TC));
         tma_load_3d(brick, &tmap, org[0], org[1], org[2], bar);
       }
       mbar_wait(bar, parity);
       parity ^= 1;
       __syncthreads();  // kt
     } else {
-      const double *__restrict__ cg = (const double *)p.coefs;
-      for (int e = threadIdx.x; e < BRICK_DOUBLES; e += blockDim.x) {
-        const int bx = e % BRICK_PITCH, by = (e / BRICK_PITCH) % BRICK_SIDE, bz = e / (BRICK_PITCH * BRICK_SIDE);
+      const TC *__restrict__ cg = (const TC *)p.coefs;
+      for (int e = threadIdx.x; e < BG::ELEMS; e += blockDim.x) {
+        const int bx = e % PITCH, by = (e / PITCH) % BRICK_SIDE, bz = e / PLANE;
         const int gx = org[0] + bx, gy = org[1] + by, gz = org[2] + bz;
-        brick[e] = (gx < p.nk[0] && gy < p.nk[1] && gz < p.nk[2]) ? __ldg(cg + gx + (long long)gy * p.s1 + (long long)gz * p.s2) : 0.0;
+        brick[e] = (gx < p.nk[0] && gy < p.nk[1] && gz < p.nk[2]) ? __ldg(cg + gx + (long long)gy * p.s1 + (long long)gz * p.s2) : (TC)0;
       }
       __syncthreads();
     }
@@ -730,7 +745,7 @@ __global__ void __launch_bounds__(384, 1)
               const double2 *hp = (const double2 *)(hbs + (j * 3 + wa) * 4);
               h0[u] = hp[0];
               h1[u] = hp[1];
-              const double *kp = brick + tko + rw, *dp = brick + tdo + rw;
+              const double *kp = smd + tko + rw, *dp = smd + tdo + rw;
               ka[u] = kp[0];
               kb[u] = kp[W];
               da[u] = dp[0];
@@ -751,13 +766,13 @@ __global__ void __launch_bounds__(384, 1)
             const int mx = misc[j * 4];
             if (mx != cur) {  // warp-uniform: first query of a run - fetch the cell's stencil into registers
               cur = mx;
-              const double *base = brick + mx + lane_off;
+              const TC *base = brick + mx + lane_off;
 #pragma unroll
               for (int n = 0; n < W; ++n)
 #pragma unroll
                 for (int k = 0; k < KM; ++k) {
-                  if ((G - 1) + k * G < W) creg[k][n] = base[k * G * PITCH + n * PLANE];
-                  else creg[k][n] = kval[k] ? base[k * G * PITCH + n * PLANE] : 0.0;
+                  if ((G - 1) + k * G < W) creg[k][n] = (double)base[k * G * PITCH + n * PLANE];
+                  else creg[k][n] = kval[k] ? (double)base[k * G * PITCH + n * PLANE] : 0.0;
                 }
             }
             const double *wj = wq + jj * 32;
@@ -819,15 +834,15 @@ __global__ void __launch_bounds__(384, 1)
         s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
         if ((lane >> 3) == (j0 >> 3)) res = s1;
       }
-      if (have) out[idx] = apply_scale<3>(res, sc);
+      if (have) out[idx] = (TC)apply_scale<3>(res, sc);
     }
   }
 }
 
 // spill bin: queries outside the domain (Flat / Line / Throw) or with NaN / Inf coordinates
-template <int E>
+template <int E, typename TC>
 __global__ void __launch_bounds__(256) eval_spill_kernel(ItpParams p, BinGeom g, Scale sc, const Record *__restrict__ rec,
-                                                         const unsigned *__restrict__ tile_start, double *__restrict__ out,
+                                                         const unsigned *__restrict__ tile_start, TC *__restrict__ out,
                                                          EvalStatus *status, long long qoff) {
   extern __shared__ double smem[];
   const double *tk[3];
@@ -842,13 +857,13 @@ __global__ void __launch_bounds__(256) eval_spill_kernel(ItpParams p, BinGeom g,
     Plan pl = make_plan<3>(p, x, pa, pb);
     double v = CUDART_NAN;
     if (pl.ntask >= 1) {
-      double fb = apply_scale<3>(core_thread<double, 3, E>(p, tk, td, pa), sc);
+      double fb = apply_scale<3>(core_thread<TC, 3, E>(p, tk, td, pa), sc);
       v = fb;
-      if (pl.ntask == 2) v = finish_line(fb, apply_scale<3>(core_thread<double, 3, E>(p, tk, td, pb), sc), p.eps_line, pl.dist);
+      if (pl.ntask == 2) v = finish_line(fb, apply_scale<3>(core_thread<TC, 3, E>(p, tk, td, pb), sc), p.eps_line, pl.dist);
     } else {
       report(status, pl.err, (long long)rc.idx + qoff);
     }
-    out[rc.idx] = v;
+    out[rc.idx] = (TC)v;
   }
 }
 
@@ -873,12 +888,13 @@ void *tma_encode_tiled_fn() {
 
 bool binned_supported(const cib200_itp *h) {
   const ItpParams &p = h->p;
-  if (p.ndim != 3 || h->dtype != CIB200_F64) return false;
+  if (p.ndim != 3) return false;
+  const size_t es = h->dtype == CIB200_F32 ? 4 : 8;
   if (p.eqs[0] != p.eqs[1] || p.eqs[1] != p.eqs[2]) return false;
   for (int d = 0; d < 3; ++d)
     if (p.npre[d] != CIB_N_PRE) return false;  // generated tables of :linear axes: records / staging assume 101 rows
   if (p.eqs[0] < 5) return false;  // a-series stencils (4^3 .. 8^3) stay on the gather kernel
-  if ((p.s1 & 1) || (p.s2 & 1)) return false;  // TMA global strides must be multiples of 16 bytes
+  if (((size_t)p.s1 * es) % 16 || ((size_t)p.s2 * es) % 16) return false;  // TMA global strides: multiples of 16 bytes
   const int T = BRICK_SIDE + 1 - 2 * p.eqs[0];
   if (T < 4) return false;
   long long nt = 1;
@@ -889,7 +905,7 @@ bool binned_supported(const cib200_itp *h) {
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t need = (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + 4 * (size_t)(32 * 3 * 4 + 64 + 256)) + 32 + 8 * 96;
+  const size_t need = (size_t)(es == 4 ? BrickGeom<float>::BYTES : BrickGeom<double>::BYTES) + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + 4 * (size_t)(32 * 3 * 4 + 64 + 256)) + 32 + 8 * 96;
   if (need > (size_t)max_smem) return false;
   return nt + 1 <= MAX_BINS && encode_fn() != nullptr;
 }
@@ -914,15 +930,15 @@ void binned_destroy(cib200_itp *h) {
   h->bin_state = nullptr;
 }
 
-template <int E>
-static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *out, long long qoff, bool cellsort,
+template <int E, typename TC>
+static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, long long qoff, bool cellsort,
                           cudaStream_t st) {
   const ItpParams &p = h->p;
   using WS = BinnedWarpSmem<E>;
   int nwarps = cellsort ? 12 : 16;
   const size_t per_warp = cellsort ? (size_t)CellrunWarpSmem<5>::DOUBLES : (size_t)WS::DOUBLES;
   auto smem_for = [&](int nw) {
-    return (size_t)BRICK_DOUBLES * 8 + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nw * per_warp) + 32 + 8 * 96;
+    return (size_t)BrickGeom<TC>::BYTES + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nw * per_warp) + 32 + 8 * 96;
   };
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
@@ -939,7 +955,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
     bin_cellsort_kernel<<<bs->nblk, 1024, 0, st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
-    auto kern = eval_cellrun_kernel<E>;
+    auto kern = eval_cellrun_kernel<E, TC>;
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec2, bs->items, bs->n_items, out,
                                                           use_tma);
@@ -947,7 +963,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
   }
   if (!(E == 5 && cellsort)) {
     prof_mark(h, 2, st);
-    auto kern = eval_binned_kernel<E>;
+    auto kern = eval_binned_kernel<E, TC>;
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec, bs->items, bs->n_items, out,
                                                           use_tma);
@@ -955,7 +971,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, double *
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 3, st);
-  auto spill = eval_spill_kernel<E>;
+  auto spill = eval_spill_kernel<E, TC>;
   const size_t tsm = 8 * (size_t)tables_smem_doubles(p);
   if (tsm > 48 * 1024) CIB_CUDA(cudaFuncSetAttribute(spill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
   spill<<<bs->nblk, 256, tsm, st>>>(p, bs->g, sc, bs->rec, bs->tile_start, out, h->d_status, qoff);
@@ -986,10 +1002,12 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     g.nbin = g.ntiles + 1;
     bs->nblk = sm_count();
     cuuint64_t gdim[3] = {(cuuint64_t)p.nk[0], (cuuint64_t)p.nk[1], (cuuint64_t)p.nk[2]};
-    cuuint64_t gstr[2] = {(cuuint64_t)p.s1 * 8, (cuuint64_t)p.s2 * 8};
-    cuuint32_t box[3] = {BRICK_PITCH, BRICK_SIDE, BRICK_SIDE};
+    const bool f32 = h->dtype == CIB200_F32;
+    const cuuint64_t esz = f32 ? 4 : 8;
+    cuuint64_t gstr[2] = {(cuuint64_t)p.s1 * esz, (cuuint64_t)p.s2 * esz};
+    cuuint32_t box[3] = {(cuuint32_t)(f32 ? BrickGeom<float>::PITCH : BrickGeom<double>::PITCH), BRICK_SIDE, BRICK_SIDE};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode_fn()(&bs->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(p.coefs), gdim, gstr, box,
+    CUresult r = encode_fn()(&bs->tmap, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(p.coefs), gdim, gstr, box,
                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1032,10 +1050,13 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   for (int d = 0; d < 3; ++d) sc.s[d] = jl_pow_int(-1.0 / p.h[d], h->deriv[d]);
   sc.perdim2d = 0;
   const size_t hsm = 4 * (size_t)g.nbin;
-  CIB_CUDA(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-  CIB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+  const bool f32 = h->dtype == CIB200_F32;
+  auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
+  auto kscatter = f32 ? bin_scatter_kernel<float> : bin_scatter_kernel<double>;
+  CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+  CIB_CUDA(cudaFuncSetAttribute(kscatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   prof_mark(h, 0, st);
-  bin_count_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist);
+  kcount<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist);
   CIB_LAUNCHED();
   bin_totals_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
@@ -1044,7 +1065,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
   static const int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
-  bin_scatter_kernel<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, scatter_mode);
+  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, scatter_mode);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 1, st);
@@ -1056,11 +1077,16 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   bool cellsort = p.eqs[0] == 5 && (double)nq >= 0.5 * ncell && g.T * g.T * g.T <= CELLS_MAX;
   if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   switch (p.eqs[0]) {
-    case 5: return launch_pass_cd<5>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 6: return launch_pass_cd<6>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 7: return launch_pass_cd<7>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 8: return launch_pass_cd<8>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 9: return launch_pass_cd<9>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 5: return f32 ? launch_pass_cd<5, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<5, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 6: return f32 ? launch_pass_cd<6, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<6, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 7: return f32 ? launch_pass_cd<7, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<7, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 8: return f32 ? launch_pass_cd<8, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<8, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 9: return f32 ? launch_pass_cd<9, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<9, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
   }
   set_error("binned strategy: unsupported kernel");
   return CIB200_EUNSUPPORTED;

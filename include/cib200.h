@@ -216,6 +216,31 @@ int32_t cib200_itg_eval_grid(cib200_itg *handle, const int64_t *n, const void *c
  * tail3_edge_ll[1..3], 7 = tail3_corner_lll */
 int32_t cib200_itg_get(cib200_itg *handle, int32_t what, int32_t index, void *out);
 
+/* ---- antiderivative / mixed interpolants in N >= 4 dimensions (the remainder) --------------
+ * itp.(xs...) / itp(xs...) for
+ *   convolution_fast_interpolation/convolution_fast_integration_nd.jl:1-28          derivative = -1 on every axis
+ *   convolution_fast_interpolation/convolution_fast_mixed_3_integral_dims.jl:8-225  exactly three integral axes
+ *   convolution_fast_interpolation/convolution_fast_mixed_N_integral_dims.jl:15-82  four or more integral axes, mixed
+ * behind extrapolation_operator.jl:31-99.  Float64; every axis is on the :linear subgrid (_build_subgrids,
+ * fast_convolution_interpolation_constructor.jl:456-494): tables[d] = itp.kernel_pre[d] (n_pre[d] x 2 eqs doubles, Julia
+ * memory order, host; NULL: the 101-row shipped K~ / K^(deriv)), deriv[d] = -1 marks the integral axes.
+ * sum_extent[d]: how many leading (padded) entries of an integral axis the functor visits - itp.domain_size[d] for the
+ * every-axis-integral functor, whose loops run over 1:domain_size[d] (convolution_fast_integration_nd.jl:20), size(coefs, d)
+ * for the other two (NULL: size(coefs, d) everywhere).  left_values are recomputed by the library
+ * (_compute_left_values, constructor.jl:414-448); the tail arrays of the three-axis functor are not needed: the kernel
+ * evaluates the sum they accelerate directly (one CTA per query, O(grid) work - what the other two functors do anyway). */
+typedef struct cib200_itgnd cib200_itgnd; /* opaque */
+int32_t cib200_itgnd_create(int32_t ndim, const int64_t *coef_shape, const double *coefs, const double *const *knots,
+                            const double *h, const int32_t *kernel, const int32_t *deriv, int32_t extrap,
+                            const double *const *tables, const int32_t *n_pre, const int64_t *sum_extent,
+                            cib200_itgnd **handle);
+int32_t cib200_itgnd_destroy(cib200_itgnd *handle);
+/* same contracts as cib200_itp_eval / cib200_itp_eval_grid */
+int32_t cib200_itgnd_eval(cib200_itgnd *handle, int64_t nq, const void *const *x, void *out, int32_t memkind,
+                          void *stream, int64_t *first_bad);
+int32_t cib200_itgnd_eval_grid(cib200_itgnd *handle, const int64_t *n, const void *const *x, void *out,
+                               int32_t memkind, void *stream, int64_t *first_bad);
+
 /* Measurement hook (bench.py's roofline): with profiling enabled the library brackets the passes of every evaluation
  * with CUDA events on the launching stream; cib200_itp_last_pass_ms then returns, for the most recent call, the
  * device time in ms of {binning passes, cell sort, evaluation kernel, spill kernel} (gather strategy: {0, 0, kernel, 0}).

@@ -641,3 +641,327 @@ def direct_eval(itp, *xs):
     for d in range(nd):
         scale *= 1.0 / itp.h[d] ** itp.derivs[d]
     return res * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# Antiderivative / mixed interpolants in N >= 4 dimensions (the remainder):
+#   convolution_fast_integration_nd.jl:1-28          every axis integral (HigherDimension, no tails)
+#   convolution_fast_mixed_3_integral_dims.jl:1-232  exactly three integral axes (27-region tail decomposition)
+#   convolution_fast_mixed_N_integral_dims.jl:15-82  any other count of integral axes >= 4 (brute force over the grid)
+# restated in numpy / plain Python loops (small cases only; test infrastructure).  For N >= 4 every axis is on the
+# :linear subgrid (_build_subgrids, constructor.jl:456-494) and reads generated tables of >= 10 000 rows.
+# ---------------------------------------------------------------------------------------------
+_GENERATED_I1 = {}
+
+
+def generated_table_i1(kernel, n_pre=LINEAR_ROWS):
+    """kernel_pre of an integral axis on the :linear subgrid: K~((r-1)//(n_pre-1) - eqs + c - 1) = int_0^s K(u) du in exact
+    rational arithmetic, rounded once (precompute_kernel_and_range.jl:150-157 with the _i1 polynomials,
+    convolution_kernel_b5.jl:52-58); odd in s, +-1/2 outside the support."""
+    key = (kernel, n_pre)
+    if key in _GENERATED_I1:
+        return _GENERATED_I1[key]
+    import json
+    from fractions import Fraction
+    info = json.load(open(_POLYS_JSON))[kernel]
+    eqs, Q = info["eqs"], n_pre - 1
+    pieces, below = [], Fraction(0)
+    for p, piece in enumerate(info["pieces"]):
+        c = [Fraction(x) for x in piece]
+        a = [Fraction(0)] + [c[k] / (k + 1) for k in range(len(c))]
+        val = lambda s, a=a: sum(ak * s ** k for k, ak in enumerate(a))
+        a[0] = below - val(Fraction(p))
+        below += val(Fraction(p + 1)) - val(Fraction(p))
+        lcm = 1
+        for x in a:
+            lcm = lcm * x.denominator // math.gcd(lcm, x.denominator)
+        pieces.append(([int(x * lcm) for x in a], lcm))
+    t = np.zeros((n_pre, 2 * eqs))
+    for col in range(2 * eqs):
+        for r in range(n_pre):
+            m = r + (col - eqs) * Q
+            M = abs(m)
+            if M >= eqs * Q:
+                t[r, col] = 0.5 if m > 0 else -0.5
+                continue
+            A, lcm = pieces[M // Q]
+            n = len(A) - 1
+            num = sum(a * M ** k * Q ** (n - k) for k, a in enumerate(A))
+            t[r, col] = (num if m >= 0 else -num) / (lcm * Q ** n)
+    _GENERATED_I1[key] = t
+    return t
+
+
+def _suffix_sum(a, axis):
+    """_suffix_sum, constructor.jl:450-454"""
+    return np.flip(np.cumsum(np.flip(a, axis=axis), axis=axis), axis=axis)
+
+
+class IntegralInterpolantND:
+    """convolution_interpolation(knots, values; kernel, derivative) with derivative[d] = -1 on some or all axes, N >= 4
+    (also constructible for N < 4 to cross-check the functors against each other).  Every axis on the :linear subgrid."""
+
+    def __init__(self, knots, values, kernel="b5", derivative=-1, bc="detect", extrap="throw", linear_rows=LINEAR_ROWS,
+                 functor=None):
+        values = np.asarray(values, dtype=np.float64)
+        nd = values.ndim
+        self.ndim = nd
+        self.knots_in = _knots_tuple(knots, nd)
+        self.kernels = _ntuple(kernel, nd, str)
+        self.derivs = _ntuple(derivative, nd, int)
+        bcs = _norm_bc(bc, nd)
+        fixed = []
+        for d in range(nd):
+            b = bcs[d]
+            if "poly" in b and values.shape[d] < MIN_POLY_BC_POINTS[self.kernels[d]]:
+                b = ("linear", "linear") if b == ("poly", "poly") else (("linear", b[1]) if b[0] == "poly" else (b[0], "linear"))
+            fixed.append(b)
+        self.eqs = tuple(KERNEL_EQS[k] for k in self.kernels)
+        self.h = tuple(float(k[1] - k[0]) for k in self.knots_in)
+        self.coefs = create_coefs(values, self.h, self.kernels, tuple(fixed))
+        self.knots = tuple(extend_vector(k, e - 1) for k, e in zip(self.knots_in, self.eqs))
+        self.domain_size = values.shape
+        self.extrap = extrap
+        self.tables = tuple(generated_table_i1(k, linear_rows) if dv == -1 else generated_table(k, dv, linear_rows)
+                            for k, dv in zip(self.kernels, self.derivs))
+        self.n_pre = linear_rows
+        self.int_dims = [d for d in range(nd) if self.derivs[d] == -1]
+        ni = len(self.int_dims)
+        # functor selection: integral_dimension = Val(n_integral) for <= 3, HigherDimension otherwise (constructor.jl:150)
+        self.functor = functor or ("nd" if ni == nd else ("mixed3" if ni == 3 else "mixedN"))
+        self.left_values = tuple(self._left_values(d) if self.derivs[d] == -1 else np.zeros(1) for d in range(nd))
+        if self.functor == "mixed3":
+            self._build_tails3()
+
+    # _compute_left_values, constructor.jl:414-448 (linear subgrid branch)
+    def _left_values(self, d):
+        eqs, n = self.eqs[d], self.coefs.shape[d]
+        tab, npre = self.tables[d], self.n_pre
+        lv = np.zeros(n)
+        for j in range(1, n + 1):
+            sj = float(eqs - j)
+            if abs(sj) >= eqs:
+                lv[j - 1] = 0.5 * np.sign(sj)
+                continue
+            col_float = eqs + sj
+            col = min(max(int(math.floor(col_float)) + 1, 1), 2 * eqs)
+            cidx = (col_float - (col - 1)) * (npre - 1) + 1.0
+            idx = min(max(int(math.floor(cidx)), 1), npre - 1)
+            t = cidx - idx
+            lv[j - 1] = (1.0 - t) * tab[idx - 1, col - 1] + t * tab[idx, col - 1]
+        return lv
+
+    # K~ lookup of an integral axis: eval_sg_kt (eval_subgrid_helpers.jl:22-32), linear subgrid
+    def _kt(self, d, j, x):
+        eqs, h = self.eqs[d], self.h[d]
+        xjd = self.knots[d][eqs - 1] + (j - eqs) * h
+        sj = (x - xjd) / h
+        if abs(sj) >= eqs:
+            return 0.5 * np.sign(sj)
+        col_float = eqs + sj
+        col = min(max(int(math.floor(col_float)) + 1, 1), 2 * eqs)
+        t = (col_float - (col - 1)) * (self.n_pre - 1) + 1.0
+        idx = min(max(int(math.floor(t)), 1), self.n_pre - 1)
+        t -= idx
+        tab = self.tables[d]
+        return (1.0 - t) * tab[idx - 1, col - 1] + t * tab[idx, col - 1]
+
+    # K^(DO) lookup of a derivative axis at padded index j (mixed_N :52-68); None outside the stencil
+    def _kd(self, d, j, x):
+        eqs, h, k = self.eqs[d], self.h[d], self.knots[d]
+        pos = min(max(int(math.floor((x - k[0]) / h + 1.0)), eqs), len(k) - eqs)
+        col = j - pos + eqs
+        if col < 1 or col > 2 * eqs:
+            return None
+        diff_right = 1.0 - (x - k[pos - 1]) / h
+        cidx = diff_right * (self.n_pre - 1) + 1.0
+        i = min(max(int(math.floor(cidx)), 1), self.n_pre - 1)
+        t = cidx - i
+        tab = self.tables[d]
+        return (1.0 - t) * tab[i - 1, col - 1] + t * tab[i, col - 1]
+
+    def _scale(self):
+        s = 1.0
+        for d in range(self.ndim):
+            s *= self.h[d] if self.derivs[d] == -1 else (-1.0 / self.h[d]) ** self.derivs[d]
+        return s
+
+    def _eval_nd(self, x):
+        """convolution_fast_integration_nd.jl:16-28: the loops run over 1:domain_size[d] - the INTERIOR extents - while
+        coefs and left_values are indexed in padded numbering: the last 2 (eqs - 1) padded entries of every axis are
+        never visited (restated literally)."""
+        nd = self.ndim
+        w = [np.array([self._kt(d, j, x[d]) - self.left_values[d][j - 1] for j in range(1, self.domain_size[d] + 1)])
+             for d in range(nd)]
+        sub = self.coefs[tuple(slice(0, n) for n in self.domain_size)]
+        acc = sub
+        for d in range(nd - 1, -1, -1):
+            acc = np.tensordot(acc, w[d], axes=([d], [0]))
+        return float(acc) * float(np.prod(self.h))
+
+    def _eval_mixed_n(self, x):
+        """convolution_fast_mixed_N_integral_dims.jl:24-82: brute force over the whole padded grid"""
+        nd = self.ndim
+        w = []
+        for d in range(nd):
+            n = self.coefs.shape[d]
+            if self.derivs[d] == -1:
+                w.append(np.array([self._kt(d, j, x[d]) - self.left_values[d][j - 1] for j in range(1, n + 1)]))
+            else:
+                w.append(np.array([self._kd(d, j, x[d]) or 0.0 for j in range(1, n + 1)]))
+        acc = self.coefs
+        for d in range(nd - 1, -1, -1):
+            acc = np.tensordot(acc, w[d], axes=([d], [0]))
+        return float(acc) * self._scale()
+
+    def _build_tails3(self):
+        """_build_tails_dispatch(..., ::Val{3}), constructor.jl:277-334: the arrays the functor reads"""
+        c = self.coefs
+        nd = self.ndim
+        d1, d2, d3 = self.int_dims
+        shp = lambda d: tuple(c.shape[d] if i == d else 1 for i in range(nd))
+        lv = {d: self.left_values[d].reshape(shp(d)) for d in (d1, d2, d3)}
+        wl = {d: 0.5 - lv[d] for d in lv}
+        wr = {d: -0.5 - lv[d] for d in lv}
+        cs, ss = (lambda a, d: np.cumsum(a, axis=d)), _suffix_sum
+        self.tail1_left = {d: cs(c * wl[d], d) for d in lv}
+        self.tail1_right = {d: ss(c * wr[d], d) for d in lv}
+        # tail3_edge_xx[k]: free in int_dim k, saturated in the other two (1-based k = 1, 2, 3 as in the reference)
+        self.edge_ll = {1: cs(cs(c * wl[d2] * wl[d3], d2), d3), 2: cs(cs(c * wl[d1] * wl[d3], d1), d3), 3: cs(cs(c * wl[d1] * wl[d2], d1), d2)}
+        self.edge_rl = {1: ss(cs(c * wr[d2] * wl[d3], d3), d2), 2: ss(cs(c * wr[d1] * wl[d3], d3), d1), 3: ss(cs(c * wr[d1] * wl[d2], d2), d1)}
+        self.edge_lr = {1: cs(ss(c * wl[d2] * wr[d3], d3), d2), 2: cs(ss(c * wl[d1] * wr[d3], d3), d1), 3: cs(ss(c * wl[d1] * wr[d2], d2), d1)}
+        self.edge_rr = {1: ss(ss(c * wr[d2] * wr[d3], d3), d2), 2: ss(ss(c * wr[d1] * wr[d3], d3), d1), 3: ss(ss(c * wr[d1] * wr[d2], d2), d1)}
+        self.corner = {
+            "lll": cs(cs(cs(c * wl[d1] * wl[d2] * wl[d3], d1), d2), d3),
+            "rll": ss(cs(cs(c * wr[d1] * wl[d2] * wl[d3], d2), d3), d1),
+            "lrl": cs(ss(cs(c * wl[d1] * wr[d2] * wl[d3], d3), d2), d1),
+            "llr": cs(cs(ss(c * wl[d1] * wl[d2] * wr[d3], d3), d1), d2),
+            "rrl": ss(ss(cs(c * wr[d1] * wr[d2] * wl[d3], d3), d2), d1),
+            "rlr": ss(cs(ss(c * wr[d1] * wl[d2] * wr[d3], d2), d1), d3),
+            "lrr": cs(ss(ss(c * wl[d1] * wr[d2] * wr[d3], d3), d2), d1),
+            "rrr": ss(ss(ss(c * wr[d1] * wr[d2] * wr[d3], d3), d2), d1),
+        }
+
+    def _eval_mixed3(self, x):
+        """convolution_fast_mixed_3_integral_dims.jl:8-225 (1-based indices kept; arrays indexed with -1)"""
+        import itertools
+        nd, c = self.ndim, self.coefs
+        d1, d2, d3 = self.int_dims
+        isint = [d in (d1, d2, d3) for d in range(nd)]
+        i = [min(max(int(math.floor((x[d] - self.knots[d][0]) / self.h[d] + 1.0)), self.eqs[d]), c.shape[d] - self.eqs[d])
+             for d in range(nd)]
+        l = [i[d] - self.eqs[d] for d in range(nd)]
+        r = [i[d] + self.eqs[d] + 1 for d in range(nd)]
+        l_ok = [l[d] >= 1 for d in range(nd)]
+        r_ok = [r[d] <= c.shape[d] for d in range(nd)]
+        rng = lambda d: range(i[d] - self.eqs[d] + 1, i[d] + self.eqs[d] + 1)
+        lvw = lambda d, j: self._kt(d, j, x[d]) - self.left_values[d][j - 1]
+        at = lambda arr, idx: arr[tuple(k - 1 for k in idx)]
+
+        def setidx(idx, **kw):
+            idx = list(idx)
+            for d, v in kw.items():
+                idx[int(d[1:])] = v
+            return idx
+
+        result = 0.0
+        deriv_ranges = [range(1, 2) if isint[d] else rng(d) for d in range(nd)]
+        for idx_d in itertools.product(*deriv_ranges):
+            kt_prod, skip = 1.0, False
+            for d in range(nd):
+                if isint[d]:
+                    continue
+                kv = self._kd(d, idx_d[d], x[d])
+                if kv is None:
+                    skip = True
+                    break
+                kt_prod *= kv
+            if skip:
+                continue
+            S = lambda idx, **kw: setidx(idx, **{f"d{k}": v for k, v in kw.items()})
+            for j3 in rng(d3):
+                lv3 = lvw(d3, j3)
+                idx3 = S(idx_d, **{str(d3): j3})
+                for j2 in rng(d2):
+                    lv2 = lvw(d2, j2)
+                    lv23 = lv2 * lv3
+                    idx23 = S(idx3, **{str(d2): j2})
+                    for j1 in rng(d1):
+                        lv1 = lvw(d1, j1)
+                        result += at(c, S(idx23, **{str(d1): j1})) * lv1 * lv23 * kt_prod
+                    tl1 = at(self.tail1_left[d1], S(idx23, **{str(d1): l[d1]})) if l_ok[d1] else 0.0
+                    tr1 = at(self.tail1_right[d1], S(idx23, **{str(d1): r[d1]})) if r_ok[d1] else 0.0
+                    result += (tl1 + tr1) * lv23 * kt_prod
+                for j1 in rng(d1):
+                    lv1 = lvw(d1, j1)
+                    idx13 = S(idx3, **{str(d1): j1})
+                    tl2 = at(self.tail1_left[d2], S(idx13, **{str(d2): l[d2]})) if l_ok[d2] else 0.0
+                    tr2 = at(self.tail1_right[d2], S(idx13, **{str(d2): r[d2]})) if r_ok[d2] else 0.0
+                    result += (tl2 + tr2) * lv1 * lv3 * kt_prod
+                for (a1, ok1, a2, ok2, arr) in ((l, l_ok, l, l_ok, self.edge_ll[3]), (r, r_ok, l, l_ok, self.edge_rl[3]),
+                                                (l, l_ok, r, r_ok, self.edge_lr[3]), (r, r_ok, r, r_ok, self.edge_rr[3])):
+                    v = at(arr, S(idx3, **{str(d1): a1[d1], str(d2): a2[d2]})) if (ok1[d1] and ok2[d2]) else 0.0
+                    result += v * lv3 * kt_prod
+            for j2 in rng(d2):
+                lv2 = lvw(d2, j2)
+                for j1 in rng(d1):
+                    lv1 = lvw(d1, j1)
+                    idx12 = S(idx_d, **{str(d1): j1, str(d2): j2})
+                    tl3 = at(self.tail1_left[d3], S(idx12, **{str(d3): l[d3]})) if l_ok[d3] else 0.0
+                    tr3 = at(self.tail1_right[d3], S(idx12, **{str(d3): r[d3]})) if r_ok[d3] else 0.0
+                    result += (tl3 + tr3) * lv1 * lv2 * kt_prod
+            for j2 in rng(d2):
+                lv2 = lvw(d2, j2)
+                idx2 = S(idx_d, **{str(d2): j2})
+                for (a1, ok1, a3, ok3, arr) in ((l, l_ok, l, l_ok, self.edge_ll[2]), (r, r_ok, l, l_ok, self.edge_rl[2]),
+                                                (l, l_ok, r, r_ok, self.edge_lr[2]), (r, r_ok, r, r_ok, self.edge_rr[2])):
+                    v = at(arr, S(idx2, **{str(d1): a1[d1], str(d3): a3[d3]})) if (ok1[d1] and ok3[d3]) else 0.0
+                    result += v * lv2 * kt_prod
+            for j1 in rng(d1):
+                lv1 = lvw(d1, j1)
+                idx1 = S(idx_d, **{str(d1): j1})
+                for (a2, ok2, a3, ok3, arr) in ((l, l_ok, l, l_ok, self.edge_ll[1]), (r, r_ok, l, l_ok, self.edge_rl[1]),
+                                                (l, l_ok, r, r_ok, self.edge_lr[1]), (r, r_ok, r, r_ok, self.edge_rr[1])):
+                    v = at(arr, S(idx1, **{str(d2): a2[d2], str(d3): a3[d3]})) if (ok2[d2] and ok3[d3]) else 0.0
+                    result += v * lv1 * kt_prod
+            for name, arr in self.corner.items():
+                sel = [(l, l_ok) if ch == "l" else (r, r_ok) for ch in name]
+                if sel[0][1][d1] and sel[1][1][d2] and sel[2][1][d3]:
+                    result += at(arr, S(idx_d, **{str(d1): sel[0][0][d1], str(d2): sel[1][0][d2], str(d3): sel[2][0][d3]})) * kt_prod
+        return result * self._scale()
+
+    def _core(self, x):
+        return {"nd": self._eval_nd, "mixed3": self._eval_mixed3, "mixedN": self._eval_mixed_n}[self.functor](x)
+
+    def eval_points(self, *xs):
+        """the extrapolation wrapper (extrapolation_operator.jl:31-63, extrapolate_point.jl:98-160) around the functor"""
+        xs = [np.asarray(x, dtype=np.float64).ravel() for x in xs]
+        lo = np.array([k[e - 1] for k, e in zip(self.knots, self.eqs)])
+        hi = np.array([k[-e] for k, e in zip(self.knots, self.eqs)])
+        hmin = min(self.h)
+        out = np.empty(xs[0].size)
+        for q in range(xs[0].size):
+            x = np.array([a[q] for a in xs])
+            if np.all((x >= lo) & (x <= hi)):
+                out[q] = self._core(x)
+                continue
+            if self.extrap == "throw":
+                raise OracleError(f"query {q} outside the domain with extrap=throw")
+            xc = np.clip(x, lo, hi)
+            if self.extrap == "flat":
+                out[q] = self._core(xc)
+                continue
+            dx = x - xc
+            d2 = 0.0
+            for v in dx:
+                d2 += v * v
+            if d2 < 2.220446049250313e-16:
+                out[q] = self._core(xc)
+                continue
+            eps, dist = hmin / 100.0, math.sqrt(d2)
+            fb = self._core(xc)
+            fi = self._core(xc - eps * dx / dist)
+            out[q] = fb + (fb - fi) / eps * dist
+        return out
+
+    eval = eval_points

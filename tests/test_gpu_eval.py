@@ -423,6 +423,37 @@ def test_float32_opt_in_mode(ci, oracle):
     assert rel_err(g1.eval(q1), o1.eval(q1.astype(np.float64)), _scale(o1)).max() <= TOL32
 
 
+@pytest.mark.parametrize("kernel,nq", [("b5", (1 << 22) + 77), ("b5", 40_000_003), ("b13", (1 << 22) + 5)])
+def test_float32_mode_on_the_binned_strategies(ci, oracle, kernel, nq):
+    """Float32 interpolants take the tile-binned strategies too (the brick is staged as floats by a FLOAT32 tensor map,
+    records and arithmetic stay double): a batch above the AUTO threshold - and, for :b5 at >= 0.5 query per cell, the
+    cell-sorted kernel - against the Float64 oracle (1e-5) and against the same interpolant's gather kernel."""
+    import torch
+    rng = np.random.default_rng(23)
+    shape = (56, 64, 48)  # padded extents multiples of 4: Float32 TMA strides are multiples of 16 bytes
+    knots = tuple((np.arange(n) / 64).astype(np.float32) for n in shape)
+    v = _field(shape, rng, noise=0.01).astype(np.float32)
+    extrap = "flat" if kernel == "b13" else "throw"
+    itp = ci.convolution_interpolation(knots, v, kernel=kernel, bc="poly", extrap=extrap)
+    assert itp.itp.dtype == np.float32
+    o = oracle.convolution_interpolation(tuple(k.astype(np.float64) for k in knots), v.astype(np.float64), kernel=kernel,
+                                         bc="poly", extrap=extrap)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(nq)
+    hi = [float(k[-1]) for k in knots]
+    xs = [(torch.rand(nq, dtype=torch.float32, device="cuda", generator=gen) * (1.04 if extrap == "flat" else 1.0) * h
+           - (0.02 * h if extrap == "flat" else 0.0)).clamp(None if extrap == "flat" else 0.0, None if extrap == "flat" else h)
+          for h in hi]
+    out = itp.eval(*xs)
+    assert out.dtype == torch.float32 and bool(torch.isfinite(out).all())
+    sub = slice(0, nq, max(1, nq // 200_000))
+    q = [x[sub].cpu().numpy() for x in xs]
+    ref = o.eval(*[a.astype(np.float64) for a in q])
+    assert rel_err(out[sub].cpu().numpy(), ref, _scale(o)).max() <= TOL32
+    small = itp.eval(*[x[sub].contiguous() for x in xs])  # below the threshold: gather kernel
+    assert float((small - out[sub]).abs().max()) <= 1e-6 * _scale(o)
+
+
 @pytest.mark.parametrize("kernel,shape", [("b5", (64, 60, 56)), ("b13", (40, 44, 36)), ("b7", (50, 30, 34))])
 def test_binned_strategy_equals_gather_strategy(ci, oracle, kernel, shape):
     """The binned strategy (tile binning + TMA-staged bricks) uses the same positions and the same per-axis
