@@ -67,9 +67,16 @@ function accelerated(itp::FastConvolutionInterpolation{T,N}) where {T,N}
     ks === nothing && return false
     all(k -> haskey(KERNEL_ID, k), ks) || return false
     itp.lazy === Val{false}() || return false
+    if is_integral(itp) && N >= 4
+        # N >= 4: every axis :linear on generated tables; three or more integral axes (convolution_fast_integration_nd.jl,
+        # convolution_fast_mixed_3_integral_dims.jl, convolution_fast_mixed_N_integral_dims.jl): cib200_itgnd_*
+        dvi = integral_derivs(itp)
+        return T === Float64 && count(==(-1), dvi) >= 3 && all(==(:linear), subgrid_tuple(itp)) &&
+               all(d -> dvi[d] == -1 || 0 <= dvi[d] <= MAX_TABLE[ks[d]], 1:N)
+    end
     if is_integral(itp)
         # shipped K~ / K / K' tables only: Float64, N <= 3, cubic or quintic subgrid on every axis (mixed integral /
-        # interpolation axes and N >= 4 resolve to :linear on generated tables, _build_subgrids)
+        # interpolation axes resolve to :linear on generated tables, _build_subgrids)
         dvi = integral_derivs(itp)
         sgi = subgrid_tuple(itp)
         return T === Float64 && N <= 3 &&
@@ -149,6 +156,27 @@ function handle(etp::ConvolutionExtrapolation{T,N}) where {T,N}
             ks = kernel_symbols(itp.kernel_sym)
             dv = derivative_tuple(itp)
             knots64 = ntuple(d -> Vector{Float64}(itp.knots[d]), N)
+            if N >= 4 && is_integral(itp)
+                # antiderivative / mixed interpolants in N >= 4 dimensions: cib200_itgnd_*.  left_values and tails of the
+                # Julia struct are not read; the every-axis-integral functor visits 1:domain_size[d] only
+                dvi = integral_derivs(itp)
+                out = Ref{Ptr{Cvoid}}(C_NULL)
+                cshape = Int64[size(itp.coefs)...]
+                kptr = [pointer(knots64[d]) for d in 1:N]
+                hh = Float64[itp.h...]
+                kid = Int32[KERNEL_ID[ks[d]] for d in 1:N]
+                dvv = Int32[dvi[d] for d in 1:N]
+                tabs64, tptr, npre = linear_tables(itp, ntuple(_ -> :linear, N))
+                ext = Int64[(itp.derivative_order isa FastIntegralOrder ? itp.domain_size[d] : size(itp.coefs, d)) for d in 1:N]
+                coefs64 = Array{Float64,N}(itp.coefs)
+                GC.@preserve coefs64 knots64 cshape kptr hh kid dvv tabs64 tptr npre ext check(ccall((:cib200_itgnd_create, LIB), Int32,
+                    (Int32, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Int32,
+                     Ptr{Ptr{Float64}}, Ptr{Int32}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                    N, cshape, coefs64, kptr, hh, kid, dvv, extrap_id(etp.et), tptr, npre, ext, out))
+                h = Handle(out[])
+                finalizer(x -> ccall((:cib200_itgnd_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+                return h
+            end
             if N >= 4
                 # HigherDimension evaluators (eager_nd.jl:97-140 / perdim_nd.jl:4-36): cib200_itpnd_*
                 out = Ref{Ptr{Cvoid}}(C_NULL)
@@ -245,6 +273,12 @@ function Base.Broadcast.broadcasted(etp::ConvolutionExtrapolation{T,N}, xs::Vara
         return out
     end
     hp = hd.ptr
+    if is_integral(etp.itp) && N >= 4
+        GC.@preserve xq out ptrs check(ccall((:cib200_itgnd_eval, LIB), Int32,
+            (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+            hp, nq, ptrs, out, 0, C_NULL, bad))
+        return out
+    end
     if is_integral(etp.itp)
         GC.@preserve xq out ptrs check(ccall((:cib200_itg_eval, LIB), Int32,
             (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
@@ -270,6 +304,12 @@ function (etp::ConvolutionExtrapolation{T,N})(xs::Vararg{AbstractVector{<:Real},
     ptrs = [Ptr{Cvoid}(pointer(xq[d])) for d in 1:N]
     bad = Ref{Int64}(-1)
     hp = handle(etp).ptr
+    if is_integral(etp.itp) && N >= 4
+        GC.@preserve xq out ptrs check(ccall((:cib200_itgnd_eval_grid, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),
+            hp, n, ptrs, out, 0, C_NULL, bad))
+        return out
+    end
     if is_integral(etp.itp)
         GC.@preserve xq out ptrs check(ccall((:cib200_itg_eval_grid, LIB), Int32,
             (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{Int64}),

@@ -56,6 +56,8 @@ JULIA_OF_C = {
     "cib200_itp *": {"Ptr{Cvoid}"},
     "cib200_itpnd *": {"Ptr{Cvoid}"},
     "cib200_itg *": {"Ptr{Cvoid}"},
+    "cib200_itgnd *": {"Ptr{Cvoid}"},
+    "cib200_itgnd * *": {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"},
     "cib200_itp * *": {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"},
     "cib200_itpnd * *": {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"},
     "cib200_itg * *": {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"},
