@@ -116,7 +116,7 @@ def test_unsupported_modes_are_rejected_not_approximated(ci):
     with pytest.raises(U):  # the antiderivative path is Float64 only
         ci.convolution_interpolation(x, v, derivative=-1, dtype=np.float32)
     with pytest.raises(U):  # N >= 4 integral directions: :linear subgrid
-        ci.convolution_interpolation((x[:12],) * 4, np.zeros((12,) * 4), derivative=-1)
+        ci.convolution_interpolation((x[:12],) * 4, np.zeros((12,) * 4), derivative=(-1, 0, 0, -1))  # < 3 integral axes in 4-D
     with pytest.raises(U):
         ci.convolution_interpolation(x, v, derivative=4)          # K^(4) of :b5 does not exist in the tables
     with pytest.raises(U):
