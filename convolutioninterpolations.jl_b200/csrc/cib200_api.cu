@@ -367,8 +367,12 @@ static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq
   if (mode == CIB200_EVAL_AUTO) {
     // large point lists: bin by coefficient brick (HBM traffic ~130 B/query instead of ~18 kB for random
     // queries); small batches cannot amortise one brick load per tile and go straight to the gather kernel
-    const bool big = nq >= (1LL << 22);
-    mode = (big && !c.grid && binned_supported(h)) ? CIB200_EVAL_BINNED : CIB200_EVAL_GATHER;
+    // measured crossover (tools/sweep_threshold.py, :b5): the binned pipeline pays one brick load per occupied tile and
+    // five small launches, the gather kernel 18 kB of DRAM traffic per query - binned wins from ~100 queries per tile
+    // (512^3: 2^21.5 queries, 2.8x at 2^22; 128^3: 2^17, 2.5x at 2^20)
+    bool big = false;
+    if (nq >= (1LL << 17) && !c.grid && binned_supported(h)) big = nq >= 96 * binned_tile_count(h);
+    mode = big ? CIB200_EVAL_BINNED : CIB200_EVAL_GATHER;
   }
   if (mode == CIB200_EVAL_BINNED) {
     if (!binned_supported(h) || c.grid) {

@@ -910,6 +910,14 @@ bool binned_supported(const cib200_itp *h) {
   return nt + 1 <= MAX_BINS && encode_fn() != nullptr;
 }
 
+long long binned_tile_count(const cib200_itp *h) {
+  const ItpParams &p = h->p;
+  const int T = BRICK_SIDE + 1 - 2 * p.eqs[0];
+  long long nt = 1;
+  for (int d = 0; d < 3; ++d) nt *= (p.nk[d] - 2 * p.eqs[d] + 1 + T - 1) / T;
+  return nt;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 long long binned_scratch_bytes(const cib200_itp *h, long long nq) {

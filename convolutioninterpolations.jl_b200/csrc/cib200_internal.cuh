@@ -139,6 +139,7 @@ int launch_eval(const cib200_itp *h, const Coords &c, void *out, long long nq, c
 // binned strategy (cib200_binned.cu)
 bool binned_supported(const cib200_itp *h);
 long long binned_scratch_bytes(const cib200_itp *h, long long nq);
+long long binned_tile_count(const cib200_itp *h);
 int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, cudaStream_t st);
 void binned_destroy(cib200_itp *h);
 // sweeps (cib200_sweep.cu)
