@@ -243,10 +243,11 @@ def secondary_sweeps(peak):
                          "roofline_frac": nq5 * (32 + 8 * 18 ** 3) / (ms * 1e-3) / 1e9 / peak,
                          "model": "gather model: 24 + 8 B + 18^3 x 8 B = 46.7 kB per evaluation"}
     del it13, o5
-    g32 = tuple(np.asarray(k, dtype=np.float32) for k in g5)
+    # dyadic knots: a 512-point Float32 linspace does not pass the reference's uniformity test (spacing jitter 3.6e-5)
+    g32 = tuple((np.arange(n5) / n5).astype(np.float32) for _ in range(3))
     it32 = ci.convolution_interpolation(g32, v5.astype(np.float32), kernel="b5", bc="poly")
     del v5
-    q32 = [x.to(torch.float32) for x in q5]
+    q32 = [(x * ((n5 - 1) / n5)).to(torch.float32) for x in q5]
     del q5
     o32 = torch.empty(nq5, dtype=torch.float32, device="cuda")
     ms = best_ms(lambda: it32.eval(*q32, out=o32), reps=3)

@@ -49,6 +49,9 @@ struct BrickGeom {
 static constexpr int CHUNK_QUERIES = 16384;  // queries per work item
 static constexpr int BIN_U = 4;              // queries per thread and iteration in the binning passes
 static constexpr int MAX_BINS = 49152;       // u32 histogram must fit one CTA's shared memory (192 KB)
+// more tiles than that (:b13 on 512^3: 8^3-cell tiles, 262 144 of them): ONE histogram / ONE write cursor per tile in
+// global memory, shared by all CTAs (L2 atomics) instead of private ones per CTA in shared memory
+static constexpr int MAX_BINS_GLOBAL = 1 << 21;
 
 struct BinGeom {
   int T;
@@ -125,9 +128,10 @@ __device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, co
 
 template <typename T>
 __global__ void __launch_bounds__(1024, 1) bin_count_kernel(ItpParams p, BinGeom g, Coords c, long long nq,
-                                                            unsigned *__restrict__ hist) {
+                                                            unsigned *__restrict__ hist, int global_hist) {
   extern __shared__ unsigned sh[];
-  for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = 0;
+  if (!global_hist)
+    for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   long long per = (nq + gridDim.x - 1) / gridDim.x;
@@ -147,9 +151,14 @@ __global__ void __launch_bounds__(1024, 1) bin_count_kernel(ItpParams p, BinGeom
     for (int u = 0; u < BIN_U; ++u) {
       const long long q = qb + (long long)u * blockDim.x;
       unsigned lc;
-      if (q < q1) atomicAdd(&sh[classify(p, g, x[u], k0, lc)], 1u);
+      if (q < q1) {
+        const int bin_ = classify(p, g, x[u], k0, lc);
+        if (global_hist) atomicAdd(hist + bin_, 1u);
+        else atomicAdd(&sh[bin_], 1u);
+      }
     }
   }
+  if (global_hist) return;
   __syncthreads();
   unsigned *dst = hist + (size_t)blockIdx.x * g.nbin;
   for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) dst[i] = sh[i];
@@ -893,7 +902,7 @@ bool binned_supported(const cib200_itp *h) {
   if (p.eqs[0] != p.eqs[1] || p.eqs[1] != p.eqs[2]) return false;
   for (int d = 0; d < 3; ++d)
     if (p.npre[d] != CIB_N_PRE) return false;  // generated tables of :linear axes: records / staging assume 101 rows
-  if (p.eqs[0] < 5) return false;  // a-series stencils (4^3 .. 8^3) stay on the gather kernel
+  if (p.eqs[0] < 2) return false;
   if (((size_t)p.s1 * es) % 16 || ((size_t)p.s2 * es) % 16) return false;  // TMA global strides: multiples of 16 bytes
   const int T = BRICK_SIDE + 1 - 2 * p.eqs[0];
   if (T < 4) return false;
@@ -907,7 +916,7 @@ bool binned_supported(const cib200_itp *h) {
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t need = (size_t)(es == 4 ? BrickGeom<float>::BYTES : BrickGeom<double>::BYTES) + 8 * ((size_t)((tables_smem_doubles(p) + 1) & ~1) + 4 * (size_t)(32 * 3 * 4 + 64 + 256)) + 32 + 8 * 96;
   if (need > (size_t)max_smem) return false;
-  return nt + 1 <= MAX_BINS && encode_fn() != nullptr;
+  return nt + 1 <= MAX_BINS_GLOBAL && encode_fn() != nullptr;
 }
 
 long long binned_tile_count(const cib200_itp *h) {
@@ -926,7 +935,7 @@ long long binned_scratch_bytes(const cib200_itp *h, long long nq) {
   const int T = BRICK_SIDE + 1 - 2 * p.eqs[0];
   long long nt = 1;
   for (int d = 0; d < 3; ++d) nt *= (p.nk[d] - 2 * p.eqs[d] + 1 + T - 1) / T;
-  const size_t nbin = (size_t)nt + 1, nblk = (size_t)sm_count();
+  const size_t nbin = (size_t)nt + 1, nblk = nbin > (size_t)MAX_BINS ? 1 : (size_t)sm_count();
   size_t b = 2 * align_up(sizeof(Record) * (size_t)nq, 256);
   b += align_up(4 * nblk * nbin, 256) + align_up(4 * (nbin + 1), 256);
   b += align_up(sizeof(WorkItem) * ((size_t)nt + (size_t)nq / CHUNK_QUERIES + 1), 256) + 256;
@@ -1046,7 +1055,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     bs->rec2 = (Record *)base;
     base += align_up(sizeof(Record) * (size_t)nq, 256);
     bs->hist = (unsigned *)base;
-    base += align_up(4 * (size_t)bs->nblk * g.nbin, 256);
+    base += align_up(4 * (size_t)(g.nbin > MAX_BINS ? 1 : bs->nblk) * g.nbin, 256);
     bs->tile_start = (unsigned *)base;
     base += align_up(4 * ((size_t)g.nbin + 1), 256);
     bs->items = (WorkItem *)base;
@@ -1057,23 +1066,26 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   Scale sc;
   for (int d = 0; d < 3; ++d) sc.s[d] = jl_pow_int(-1.0 / p.h[d], h->deriv[d]);
   sc.perdim2d = 0;
-  const size_t hsm = 4 * (size_t)g.nbin;
+  const bool global_hist = g.nbin > MAX_BINS;
+  const int hrows = global_hist ? 1 : bs->nblk;
+  const size_t hsm = global_hist ? 0 : 4 * (size_t)g.nbin;
+  if (global_hist) CIB_CUDA(cudaMemsetAsync(bs->hist, 0, 4 * (size_t)g.nbin, st));
   const bool f32 = h->dtype == CIB200_F32;
   auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
   auto kscatter = f32 ? bin_scatter_kernel<float> : bin_scatter_kernel<double>;
   CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   CIB_CUDA(cudaFuncSetAttribute(kscatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   prof_mark(h, 0, st);
-  kcount<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist);
+  kcount<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, global_hist ? 1 : 0);
   CIB_LAUNCHED();
-  bin_totals_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
+  bin_totals_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
   bin_scan_kernel<<<1, 1024, 0, st>>>(g, bs->tile_start, bs->items, bs->n_items);
   CIB_LAUNCHED();
-  bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, bs->nblk, bs->hist, bs->tile_start);
+  bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
   static const int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
-  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, scatter_mode);
+  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, global_hist ? 3 : scatter_mode);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 1, st);
@@ -1085,6 +1097,13 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   bool cellsort = p.eqs[0] == 5 && (double)nq >= 0.5 * ncell && g.T * g.T * g.T <= CELLS_MAX;
   if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   switch (p.eqs[0]) {
+    // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
+    case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<2, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 3: return f32 ? launch_pass_cd<3, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<3, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 4: return f32 ? launch_pass_cd<4, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
+                   : launch_pass_cd<4, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
     case 5: return f32 ? launch_pass_cd<5, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
                    : launch_pass_cd<5, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
     case 6: return f32 ? launch_pass_cd<6, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)

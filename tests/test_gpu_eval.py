@@ -455,7 +455,8 @@ def test_float32_mode_on_the_binned_strategies(ci, oracle, kernel, nq):
     assert float((small - out[sub]).abs().max()) <= 1e-6 * _scale(o)
 
 
-@pytest.mark.parametrize("kernel,shape", [("b5", (64, 60, 56)), ("b13", (40, 44, 36)), ("b7", (50, 30, 34))])
+@pytest.mark.parametrize("kernel,shape", [("b5", (64, 60, 56)), ("b13", (40, 44, 36)), ("b7", (50, 30, 34)),
+                                          ("a3", (50, 44, 60)), ("a4", (64, 60, 56)), ("a7", (40, 52, 36))])
 def test_binned_strategy_equals_gather_strategy(ci, oracle, kernel, shape):
     """The binned strategy (tile binning + TMA-staged bricks) uses the same positions and the same per-axis
     weights as the direct gather kernel; only the association of the (2E)^3-term sum differs (lanes own
@@ -486,6 +487,28 @@ def test_binned_strategy_equals_gather_strategy(ci, oracle, kernel, shape):
     qi[2, 777] = np.nan
     with pytest.raises(ci.InexactError, match="query 777 "):
         gb.eval(*qi)
+
+
+def test_binned_strategy_with_more_tiles_than_a_shared_memory_histogram_holds(ci, oracle):
+    """:b13 tiles are 8^3 cells: a 300^3 grid has 54 872 of them, more than the 49 152 bins of the per-CTA shared-memory
+    histograms - the binning passes then keep one histogram / one write cursor per tile in global memory"""
+    import torch
+    rng = np.random.default_rng(77)
+    n = 300
+    g = np.linspace(0.0, 1.0, n)
+    a, b, c = np.sin(2 * np.pi * g), np.cos(3 * np.pi * g), np.sin(np.pi * g + 0.5)
+    v = a[:, None, None] * b[None, :, None] * c[None, None, :] + 0.01 * rng.uniform(-1, 1, (n, n, n))
+    itp = ci.convolution_interpolation((g, g, g), v, kernel="b13", bc="poly", eval_mode="binned")
+    o = oracle.convolution_interpolation((g, g, g), v, kernel="b13", bc="poly")
+    nq = 3_000_017
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in range(3)]
+    out = itp.eval(*xs)
+    assert bool(torch.isfinite(out).all())
+    sub = slice(0, nq, 151)
+    ref = o.eval(*[x[sub].cpu().numpy() for x in xs])
+    assert rel_err(out[sub].cpu().numpy(), ref, _scale(o)).max() <= TOL64
 
 
 def test_binned_device_resident_and_auto_mode(ci):
