@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(512, 1)
         int4 m;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+          locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d], p.npre[d]);
           const Hermite hb = p.subgrid[d] == CIB200_SG_LINEAR ? linear_basis(pa[d].t) : hermite_basis(pa[d].t);
           double2 *dst = (double2 *)(hbs + (lane * 3 + d) * 4);
           dst[0] = make_double2(hb.h00, hb.h01);
@@ -900,8 +900,9 @@ bool binned_supported(const cib200_itp *h) {
   if (p.ndim != 3) return false;
   const size_t es = h->dtype == CIB200_F32 ? 4 : 8;
   if (p.eqs[0] != p.eqs[1] || p.eqs[1] != p.eqs[2]) return false;
-  for (int d = 0; d < 3; ++d)
-    if (p.npre[d] != CIB_N_PRE) return false;  // generated tables of :linear axes: records / staging assume 101 rows
+  // (generated >= 10 000-row tables of :linear axes stay in global memory - L2-resident - and are read from there by the
+  // weight lanes of eval_binned_kernel; only the cell-sorted kernel needs every table in shared memory)
+  if (p.prerange_pos) return false;
   if (p.eqs[0] < 2) return false;
   if (((size_t)p.s1 * es) % 16 || ((size_t)p.s2 * es) % 16) return false;  // TMA global strides: multiples of 16 bytes
   const int T = BRICK_SIDE + 1 - 2 * p.eqs[0];
@@ -1096,6 +1097,8 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   // (b5 only: a lane's share of a wider stencil, KM x W coefficients, does not fit in registers)
   bool cellsort = p.eqs[0] == 5 && (double)nq >= 0.5 * ncell && g.T * g.T * g.T <= CELLS_MAX;
   if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
+  for (int d = 0; d < 3; ++d)
+    if (p.npre[d] != CIB_N_PRE) cellsort = false;  // the cell-run kernel addresses its tables inside shared memory
   switch (p.eqs[0]) {
     // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
     case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)

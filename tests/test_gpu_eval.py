@@ -271,13 +271,15 @@ def test_linear_subgrid_and_top_derivatives(ci, oracle, kernel):
     inside = ((q3 >= 0) & (q3 <= 1)).all(axis=0)
     assert 1e-9 < np.abs(r101 - r10k)[inside].max() / np.abs(r10k)[inside].max() < 1e-2
     assert g101.itp.linear_rows == 101 and g.itp.linear_rows == 10_000
-    if kernel == "b5":  # the binned strategies on an all-linear 3-D interpolant (101-row tables only: records pack the row)
+    if kernel == "b5":  # the binned strategies on an all-linear 3-D interpolant
         qb = rng.uniform(0, 1, (3, 300_007))
         gg = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="gather", linear_rows=101)
         gb = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned", linear_rows=101)
         assert rel_err(gb.eval(*qb), gg.eval(*qb), np.abs(v3).max()).max() <= 1e-14
-        with pytest.raises(ci.UnsupportedModeError):
-            ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned")
+        # generated 10 000-row tables: read from global memory by the binned kernel (round 2)
+        gb10k = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="binned")
+        gg10k = ci.convolution_interpolation(k3, v3, kernel=kernel, subgrid="linear", eval_mode="gather")
+        assert rel_err(gb10k.eval(*qb), gg10k.eval(*qb), np.abs(v3).max()).max() <= 1e-14
 
 
 @pytest.mark.parametrize("kernel", ["b5", "b7", "b13"])
@@ -509,6 +511,29 @@ def test_binned_strategy_with_more_tiles_than_a_shared_memory_histogram_holds(ci
     sub = slice(0, nq, 151)
     ref = o.eval(*[x[sub].cpu().numpy() for x in xs])
     assert rel_err(out[sub].cpu().numpy(), ref, _scale(o)).max() <= TOL64
+
+
+@pytest.mark.parametrize("kw", [dict(kernel="b5", derivative=(3, 0, 1)), dict(kernel="b7", subgrid=("cubic", "linear", "cubic")),
+                                dict(kernel="b13", derivative=(6, 0, 0)), dict(kernel="a4", derivative=(1, 0, 0))])
+def test_linear_subgrid_interpolants_on_the_binned_strategy(ci, oracle, kw):
+    """top derivatives / non-all-cubic 3-D interpolants resolve to the :linear subgrid on generated 10 000-row tables
+    (constructor.jl:117-118): the binned kernel reads those tables from global memory; same results as the gather
+    kernel and as the oracle"""
+    rng = np.random.default_rng(41)
+    shape = (44, 40, 36)
+    knots = tuple(np.linspace(0, 1, n) for n in shape)
+    v = _field(shape, rng, noise=0.01)
+    q = rng.uniform(-0.02, 1.02, (3, 200_003))
+    gb = ci.convolution_interpolation(knots, v, extrap="flat", eval_mode="binned", **kw)
+    gg = ci.convolution_interpolation(knots, v, extrap="flat", eval_mode="gather", **kw)
+    assert gb.itp.subgrid == ("linear",) * 3
+    o = oracle.convolution_interpolation(knots, v, extrap="flat", **kw)
+    rb, rg = gb.eval(*q), gg.eval(*q)
+    S = _scale(o)
+    # (top-derivative tables have entries of magnitude 1e3..1e5 with alternating signs: the two strategies associate the
+    # stencil sum differently, the common bound is the parity tolerance)
+    assert rel_err(rb, rg, S).max() <= TOL64
+    assert rel_err(rb, o.eval(*q), S).max() <= TOL64
 
 
 def test_binned_device_resident_and_auto_mode(ci):
