@@ -29,70 +29,9 @@
 
 #include <algorithm>
 
-#include "cib200_evalcore.cuh"
+#include "cib200_binned.cuh"
 
 namespace cib {
-
-static constexpr int BRICK_SIDE = 25;        // T + 2E - 1
-static constexpr int BRICK_PITCH = 26;       // inner TMA box extent: 26 * 8 B is a multiple of 16 B
-static constexpr int BRICK_DOUBLES = BRICK_PITCH * BRICK_SIDE * BRICK_SIDE;
-// Float32 mode (coefficients / queries / results in float, arithmetic in double): the brick is staged as floats
-// (inner extent 28: 28 * 4 B is a multiple of 16 B) and converted when a lane loads its stencil share
-template <typename T>
-struct BrickGeom {
-  static constexpr int PITCH = sizeof(T) == 8 ? 26 : 28;
-  static constexpr int PLANE = PITCH * BRICK_SIDE;
-  static constexpr int ELEMS = PLANE * BRICK_SIDE;
-  static constexpr int BYTES = (ELEMS * (int)sizeof(T) + 15) & ~15;
-  static constexpr int DOUBLES = BYTES / 8;  // where the staged tables start, in doubles from the brick
-};
-static constexpr int CHUNK_QUERIES = 16384;  // queries per work item
-static constexpr int BIN_U = 4;              // queries per thread and iteration in the binning passes
-static constexpr int MAX_BINS = 49152;       // u32 histogram must fit one CTA's shared memory (192 KB)
-// more tiles than that (:b13 on 512^3: 8^3-cell tiles, 262 144 of them): ONE histogram / ONE write cursor per tile in
-// global memory, shared by all CTAs (L2 atomics) instead of private ones per CTA in shared memory
-static constexpr int MAX_BINS_GLOBAL = 1 << 21;
-
-struct BinGeom {
-  int T;
-  int nt[3];
-  int ntiles;  // spill bin = ntiles
-  int nbin;    // ntiles + 1
-};
-
-struct __align__(32) Record {
-  double x, y, z;
-  unsigned idx;
-  unsigned pad;
-};
-
-struct WorkItem {
-  unsigned bin, start, count;
-};
-
-// A record is one 32-byte sector: moved with ONE 256-bit access (sm_100: LDG/STG.E.ENL2.256).  Two 16-byte stores
-// to a scattered sector reach L2 as two partial-sector writes, which is what limited the scatter pass.
-__device__ __forceinline__ void st_record(Record *dst, double a, double b, double c, double d) {
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-__device__ __forceinline__ void ld_record(const Record *src, double2 &a, double2 &b) {
-  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(src));
-}
-
-struct BinState {
-  BinGeom g;
-  CUtensorMap tmap;
-  int nblk;           // CTAs of passes A / B (= SM count)
-  size_t cap_q;       // queries the scratch can hold
-  // scratch layout (device)
-  Record *rec;
-  Record *rec2;       // records sorted by (tile, cell) - cell-sorted variant only
-  unsigned *hist;     // [nblk][nbin] counts -> write cursors
-  unsigned *tile_start;  // [nbin + 1]
-  WorkItem *items;
-  unsigned *n_items;  // [0] = number of items, [1] = work counter
-  size_t max_items;
-};
 
 // ---- classification -----------------------------------------------------------------------------
 __device__ __forceinline__ int first_coef(double x, double knot0, double h, int eqs, int nk, bool &ok) {
@@ -277,19 +216,28 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
 // ---- pass B2: counting sort of every tile's records by cell ---------------------------------------
 // One CTA per tile at a time (persistent CTAs pull tiles from a counter): histogram of the 12-bit cell ids carried
 // by the records in shared memory, exclusive scan, then the records are re-read (L2) and written to their slot in
-// the second record array.  Afterwards the queries of a cell are consecutive, so the evaluation kernel can keep the
-// cell's (2E)^3 coefficients in registers for the whole run.
-static constexpr int CELLS_MAX = 4096;  // T^3 with T = 16 (E = 5); smaller for wider kernels
+// the second record array.  Afterwards the queries of a cell are consecutive.
+//
+// SLOTS (lane-per-query evaluation, two queries of one cell per lane): the pass also emits the tile's SLOT LIST - one
+// u32 per pair of consecutive records of the same cell, (record offset inside the tile) * 2 + (the pair is complete) -
+// at slots[tile_start[tile] ...], and the tile's slot count.  A cell with n records gets ceil(n / 2) slots, so a lane
+// of the evaluation kernel never meets two different cells.
+static size_t cellsort_smem_bytes(bool slots) { return 4 * (size_t)(slots ? 3 * CELLS_MAX + 1 : CELLS_MAX); }
 
+template <bool SLOTS>
 __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const Record *__restrict__ rec,
                                                                Record *__restrict__ rec2,
                                                                const unsigned *__restrict__ tile_start,
-                                                               unsigned *__restrict__ counter) {
-  __shared__ unsigned hist[CELLS_MAX];
-  __shared__ unsigned wsum[32];
+                                                               unsigned *__restrict__ counter,
+                                                               unsigned *__restrict__ slots,
+                                                               unsigned *__restrict__ tile_nslots) {
+  extern __shared__ unsigned cs_sh[];           // cellsort_smem_bytes(SLOTS)
+  unsigned *hist = cs_sh;                         // [CELLS_MAX] counts, then write cursors
+  unsigned *cstart = cs_sh + CELLS_MAX;           // [CELLS_MAX + 1] first record of each cell, relative to the tile (SLOTS)
+  unsigned *sstart = cs_sh + 2 * CELLS_MAX + 1;   // [CELLS_MAX] first slot of each cell, relative to the tile (SLOTS)
+  __shared__ unsigned wsum[32], wsum2[32];
   __shared__ unsigned s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ncell = g.T * g.T * g.T;
   for (;;) {
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
     __syncthreads();
@@ -310,37 +258,58 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
         if (cell[u] >= 0) atomicAdd(&hist[cell[u]], 1u);
     }
     __syncthreads();
-    // exclusive scan of hist[0..4095]: 4 consecutive bins per thread, warp scan, scan of the 32 warp totals
-    unsigned v[4], tsum = 0;
+    // exclusive scans over hist[0..4095] (records) and over ceil(hist / 2) (slots): 4 consecutive bins per thread,
+    // warp scan, scan of the 32 warp totals
+    unsigned v[4], tsum = 0, tsum2 = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       v[i] = hist[tid * 4 + i];
       tsum += v[i];
+      tsum2 += (v[i] + 1) >> 1;
     }
-    unsigned inc = tsum;
+    unsigned inc = tsum, inc2 = tsum2;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += y;
+      const unsigned y2 = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) {
+        inc += y;
+        inc2 += y2;
+      }
     }
-    if (lane == 31) wsum[warp] = inc;
+    if (lane == 31) {
+      wsum[warp] = inc;
+      wsum2[warp] = inc2;
+    }
     __syncthreads();
     if (warp == 0) {
-      unsigned w = wsum[lane], winc = w;
+      unsigned w = wsum[lane], winc = w, w2 = wsum2[lane], winc2 = w2;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned y = __shfl_up_sync(0xffffffffu, winc, o);
-        if (lane >= o) winc += y;
+        const unsigned y2 = __shfl_up_sync(0xffffffffu, winc2, o);
+        if (lane >= o) {
+          winc += y;
+          winc2 += y2;
+        }
       }
       wsum[lane] = winc - w;
+      wsum2[lane] = winc2 - w2;
+      if (SLOTS && lane == 31) tile_nslots[tile] = winc2;
     }
     __syncthreads();
-    unsigned run = r0 + wsum[warp] + inc - tsum;
+    unsigned run = wsum[warp] + inc - tsum, run2 = wsum2[warp] + inc2 - tsum2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      hist[tid * 4 + i] = run;
+      hist[tid * 4 + i] = r0 + run;
+      if (SLOTS) {
+        cstart[tid * 4 + i] = run;
+        sstart[tid * 4 + i] = run2;
+      }
       run += v[i];
+      run2 += (v[i] + 1) >> 1;
     }
+    if (SLOTS && tid == 1023) cstart[CELLS_MAX] = run;
     __syncthreads();
     for (unsigned rb = r0 + tid; rb < r1; rb += 4 * 1024) {
       double2 a[4], b[4];
@@ -353,46 +322,18 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
         if (r < r1) {
-          const unsigned slot = atomicAdd(&hist[__double2hiint(b[u].y)], 1u);
-          st_record(rec2 + slot, a[u].x, a[u].y, b[u].x, b[u].y);
+          const int cell = __double2hiint(b[u].y);
+          const unsigned pos = atomicAdd(&hist[cell], 1u);
+          st_record(rec2 + pos, a[u].x, a[u].y, b[u].x, b[u].y);
+          if (SLOTS) {
+            const unsigned rel = pos - r0, rank = rel - cstart[cell];
+            if (!(rank & 1u)) slots[r0 + sstart[cell] + (rank >> 1)] = (rel << 1) | (rel + 1 < cstart[cell + 1] ? 1u : 0u);
+          }
         }
       }
     }
     __syncthreads();  // hist / s_tile are reused by the next tile
   }
-  (void)ncell;
-}
-
-// ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG, SYNCS) -----------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  unsigned done;
-  unsigned spins = 0;
-  do {
-    if (++spins > (1u << 24)) __trap();  // a lost TMA must not hang the device
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, int x, int y, int z, unsigned long long *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(dst)),
-      "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-      : "memory");
 }
 
 // per-warp shared-memory scratch of eval_binned_kernel (doubles)
@@ -940,6 +881,7 @@ long long binned_scratch_bytes(const cib200_itp *h, long long nq) {
   size_t b = 2 * align_up(sizeof(Record) * (size_t)nq, 256);
   b += align_up(4 * nblk * nbin, 256) + align_up(4 * (nbin + 1), 256);
   b += align_up(sizeof(WorkItem) * ((size_t)nt + (size_t)nq / CHUNK_QUERIES + 1), 256) + 256;
+  b += align_up(4 * (size_t)nq, 256) + align_up(4 * nbin, 256);  // slot list + slots per tile (lane-per-query kernel)
   return (long long)b;
 }
 
@@ -949,9 +891,28 @@ void binned_destroy(cib200_itp *h) {
 }
 
 template <int E, typename TC>
-static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, long long qoff, bool cellsort,
+static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, long long qoff, bool cellsort, int lq,
                           cudaStream_t st) {
   const ItpParams &p = h->p;
+  if (lq) {
+    // lane-per-query kernel on (tile, cell)-sorted records (lq = 2: two queries of a cell per lane, slot list)
+    static bool attr_set = false;
+    if (!attr_set) {
+      CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)cellsort_smem_bytes(true)));
+      attr_set = true;
+    }
+    if (lq == 2)
+      bin_cellsort_kernel<true><<<bs->nblk, 1024, cellsort_smem_bytes(true), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
+                                                                                  bs->n_items + 2, bs->slots, bs->tile_nslots);
+    else
+      bin_cellsort_kernel<false><<<bs->nblk, 1024, cellsort_smem_bytes(false), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
+                                                                                    bs->n_items + 2, nullptr, nullptr);
+    CIB_LAUNCHED();
+    prof_mark(h, 2, st);
+    const int rc = launch_eval_lanequery(h, bs, sc, out, lq, st);
+    if (rc != CIB200_OK) return rc;
+  }
   using WS = BinnedWarpSmem<E>;
   int nwarps = cellsort ? 12 : 16;
   const size_t per_warp = cellsort ? (size_t)CellrunWarpSmem<5>::DOUBLES : (size_t)WS::DOUBLES;
@@ -969,8 +930,8 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
   const char *no_tma = tune_env("CIB200_BINNED_NO_TMA");
   const int use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   if constexpr (E == 5) {
-   if (cellsort) {
-    bin_cellsort_kernel<<<bs->nblk, 1024, 0, st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2);
+   if (cellsort && !lq) {
+    bin_cellsort_kernel<false><<<bs->nblk, 1024, cellsort_smem_bytes(false), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     auto kern = eval_cellrun_kernel<E, TC>;
@@ -979,14 +940,14 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
                                                           use_tma);
    }
   }
-  if (!(E == 5 && cellsort)) {
+  if (!(E == 5 && cellsort) && !lq) {
     prof_mark(h, 2, st);
     auto kern = eval_binned_kernel<E, TC>;
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec, bs->items, bs->n_items, out,
                                                           use_tma);
   }
-  CIB_LAUNCHED();
+  if (!lq) CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 3, st);
   auto spill = eval_spill_kernel<E, TC>;
@@ -1062,6 +1023,10 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     bs->items = (WorkItem *)base;
     base += align_up(sizeof(WorkItem) * ((size_t)g.ntiles + (size_t)nq / CHUNK_QUERIES + 1), 256);
     bs->n_items = (unsigned *)base;
+    base += 256;
+    bs->slots = (unsigned *)base;
+    base += align_up(4 * (size_t)nq, 256);
+    bs->tile_nslots = (unsigned *)base;
   }
   const BinGeom &g = bs->g;
   Scale sc;
@@ -1099,24 +1064,29 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   for (int d = 0; d < 3; ++d)
     if (p.npre[d] != CIB_N_PRE) cellsort = false;  // the cell-run kernel addresses its tables inside shared memory
+  // lane-per-query kernel (cib200_lanequery.cu): Float64 :b5-width stencils on cell-sorted records; two queries per lane
+  // from two queries per cell upwards
+  int lq = 0;
+  if (cellsort && !f32 && nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024) lq = (double)nq >= 2.0 * ncell ? 2 : 1;
+  if (const char *e = tune_env("CIB200_LANEQUERY")) lq = cellsort && !f32 ? atoi(e) : 0;
   switch (p.eqs[0]) {
     // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
-    case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<2, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 3: return f32 ? launch_pass_cd<3, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<3, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 4: return f32 ? launch_pass_cd<4, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<4, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 5: return f32 ? launch_pass_cd<5, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<5, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 6: return f32 ? launch_pass_cd<6, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<6, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 7: return f32 ? launch_pass_cd<7, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<7, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 8: return f32 ? launch_pass_cd<8, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<8, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
-    case 9: return f32 ? launch_pass_cd<9, float>(h, bs, sc, (float *)out, c.qoff, cellsort, st)
-                   : launch_pass_cd<9, double>(h, bs, sc, (double *)out, c.qoff, cellsort, st);
+    case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<2, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 3: return f32 ? launch_pass_cd<3, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<3, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 4: return f32 ? launch_pass_cd<4, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<4, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 5: return f32 ? launch_pass_cd<5, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<5, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 6: return f32 ? launch_pass_cd<6, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<6, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 7: return f32 ? launch_pass_cd<7, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<7, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 8: return f32 ? launch_pass_cd<8, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<8, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
+    case 9: return f32 ? launch_pass_cd<9, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+                   : launch_pass_cd<9, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
   }
   set_error("binned strategy: unsupported kernel");
   return CIB200_EUNSUPPORTED;
