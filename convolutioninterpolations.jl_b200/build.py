@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcib200.so")
-SOURCES = ["cib200_api.cu", "cib200_eval.cu", "cib200_sweep.cu", "cib200_binned.cu", "cib200_evalnd.cu", "cib200_integral.cu", "cib200_smooth.cu", "cib200_resample.cu", "cib200_integral_nd.cu", "cib200_lanequery.cu"]
+SOURCES = ["cib200_api.cu", "cib200_eval.cu", "cib200_sweep.cu", "cib200_binned.cu", "cib200_evalnd.cu", "cib200_integral.cu", "cib200_smooth.cu", "cib200_resample.cu", "cib200_integral_nd.cu", "cib200_lanequery.cu", "cib200_cellmma.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # CIB200_EXTRA_NVCC_FLAGS / CIB200_SO_NAME: A/B builds of kernel variants during development (tools/ab_build.sh)
 SO = os.path.join(HERE, os.environ.get("CIB200_SO_NAME", "libcib200.so"))

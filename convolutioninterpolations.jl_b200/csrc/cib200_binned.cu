@@ -218,13 +218,16 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
 // by the records in shared memory, exclusive scan, then the records are re-read (L2) and written to their slot in
 // the second record array.  Afterwards the queries of a cell are consecutive.
 //
-// SLOTS (lane-per-query evaluation, two queries of one cell per lane): the pass also emits the tile's SLOT LIST - one
+// MODE 1 (lane-per-query evaluation, two queries of one cell per lane): the pass also emits the tile's SLOT LIST - one
 // u32 per pair of consecutive records of the same cell, (record offset inside the tile) * 2 + (the pair is complete) -
 // at slots[tile_start[tile] ...], and the tile's slot count.  A cell with n records gets ceil(n / 2) slots, so a lane
 // of the evaluation kernel never meets two different cells.
-static size_t cellsort_smem_bytes(bool slots) { return 4 * (size_t)(slots ? 3 * CELLS_MAX + 1 : CELLS_MAX); }
+// MODE 2 (tensor-core evaluation, cib200_cellmma.cu): the GROUP LIST - one uint2 {record offset inside the tile, count}
+// per run of up to 8 consecutive records of an aligned PAIR of cells along axis 0 (cells 2p, 2p + 1 of a row: their
+// stencils share an 11-wide window), at ((uint2 *)slots)[tile_start[tile] ...], and the tile's group count.
+static size_t cellsort_smem_bytes(int mode) { return 4 * (size_t)(mode ? 3 * CELLS_MAX + 1 : CELLS_MAX); }
 
-template <bool SLOTS>
+template <int MODE>
 __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const Record *__restrict__ rec,
                                                                Record *__restrict__ rec2,
                                                                const unsigned *__restrict__ tile_start,
@@ -233,8 +236,8 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
                                                                unsigned *__restrict__ tile_nslots) {
   extern __shared__ unsigned cs_sh[];           // cellsort_smem_bytes(SLOTS)
   unsigned *hist = cs_sh;                         // [CELLS_MAX] counts, then write cursors
-  unsigned *cstart = cs_sh + CELLS_MAX;           // [CELLS_MAX + 1] first record of each cell, relative to the tile (SLOTS)
-  unsigned *sstart = cs_sh + 2 * CELLS_MAX + 1;   // [CELLS_MAX] first slot of each cell, relative to the tile (SLOTS)
+  unsigned *cstart = cs_sh + CELLS_MAX;           // [CELLS_MAX + 1] first record of each cell, relative to the tile (MODE > 0)
+  unsigned *sstart = cs_sh + 2 * CELLS_MAX + 1;   // first slot of each cell (MODE 1) / first group of each cell pair (MODE 2)
   __shared__ unsigned wsum[32], wsum2[32];
   __shared__ unsigned s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -265,8 +268,9 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
     for (int i = 0; i < 4; ++i) {
       v[i] = hist[tid * 4 + i];
       tsum += v[i];
-      tsum2 += (v[i] + 1) >> 1;
+      if (MODE == 1) tsum2 += (v[i] + 1) >> 1;
     }
+    if (MODE == 2) tsum2 = ((v[0] + v[1] + 7) >> 3) + ((v[2] + v[3] + 7) >> 3);
     unsigned inc = tsum, inc2 = tsum2;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -295,21 +299,25 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
       }
       wsum[lane] = winc - w;
       wsum2[lane] = winc2 - w2;
-      if (SLOTS && lane == 31) tile_nslots[tile] = winc2;
+      if (MODE && lane == 31) tile_nslots[tile] = winc2;
     }
     __syncthreads();
     unsigned run = wsum[warp] + inc - tsum, run2 = wsum2[warp] + inc2 - tsum2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       hist[tid * 4 + i] = r0 + run;
-      if (SLOTS) {
-        cstart[tid * 4 + i] = run;
+      if (MODE) cstart[tid * 4 + i] = run;
+      if (MODE == 1) {
         sstart[tid * 4 + i] = run2;
+        run2 += (v[i] + 1) >> 1;
+      }
+      if (MODE == 2 && !(i & 1)) {
+        sstart[tid * 2 + (i >> 1)] = run2;
+        run2 += (v[i] + v[i + 1] + 7) >> 3;
       }
       run += v[i];
-      run2 += (v[i] + 1) >> 1;
     }
-    if (SLOTS && tid == 1023) cstart[CELLS_MAX] = run;
+    if (MODE && tid == 1023) cstart[CELLS_MAX] = run;
     __syncthreads();
     for (unsigned rb = r0 + tid; rb < r1; rb += 4 * 1024) {
       double2 a[4], b[4];
@@ -325,9 +333,15 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
           const int cell = __double2hiint(b[u].y);
           const unsigned pos = atomicAdd(&hist[cell], 1u);
           st_record(rec2 + pos, a[u].x, a[u].y, b[u].x, b[u].y);
-          if (SLOTS) {
+          if (MODE == 1) {
             const unsigned rel = pos - r0, rank = rel - cstart[cell];
             if (!(rank & 1u)) slots[r0 + sstart[cell] + (rank >> 1)] = (rel << 1) | (rel + 1 < cstart[cell + 1] ? 1u : 0u);
+          }
+          if (MODE == 2) {
+            const int c0 = cell & ~1;
+            const unsigned rel = pos - r0, rank = rel - cstart[c0];
+            if (!(rank & 7u))
+              ((uint2 *)slots)[r0 + sstart[cell >> 1] + (rank >> 3)] = make_uint2(rel, min(8u, cstart[c0 + 2] - cstart[c0] - rank));
           }
         }
       }
@@ -881,7 +895,7 @@ long long binned_scratch_bytes(const cib200_itp *h, long long nq) {
   size_t b = 2 * align_up(sizeof(Record) * (size_t)nq, 256);
   b += align_up(4 * nblk * nbin, 256) + align_up(4 * (nbin + 1), 256);
   b += align_up(sizeof(WorkItem) * ((size_t)nt + (size_t)nq / CHUNK_QUERIES + 1), 256) + 256;
-  b += align_up(4 * (size_t)nq, 256) + align_up(4 * nbin, 256);  // slot list + slots per tile (lane-per-query kernel)
+  b += align_up(8 * (size_t)nq, 256) + align_up(4 * nbin, 256);  // slot / group list + slots per tile (cell-sorted kernels)
   return (long long)b;
 }
 
@@ -898,19 +912,24 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
     // lane-per-query kernel on (tile, cell)-sorted records (lq = 2: two queries of a cell per lane, slot list)
     static bool attr_set = false;
     if (!attr_set) {
-      CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)cellsort_smem_bytes(true)));
+      CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(1)));
+      CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(2)));
       attr_set = true;
     }
-    if (lq == 2)
-      bin_cellsort_kernel<true><<<bs->nblk, 1024, cellsort_smem_bytes(true), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                                  bs->n_items + 2, bs->slots, bs->tile_nslots);
+    if (lq == 3)  // tensor-core kernel: group list
+      bin_cellsort_kernel<2><<<bs->nblk, 1024, cellsort_smem_bytes(2), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
+                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots);
+    else if (lq == 2)
+      bin_cellsort_kernel<1><<<bs->nblk, 1024, cellsort_smem_bytes(1), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
+                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots);
     else
-      bin_cellsort_kernel<false><<<bs->nblk, 1024, cellsort_smem_bytes(false), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                                    bs->n_items + 2, nullptr, nullptr);
+      bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
+                                                                            bs->n_items + 2, nullptr, nullptr);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
-    const int rc = launch_eval_lanequery(h, bs, sc, out, lq, st);
+    int rc;
+    if constexpr (sizeof(TC) == 8) rc = lq == 3 ? launch_eval_cellmma(h, bs, sc, out, st) : launch_eval_lanequery(h, bs, sc, out, lq, st);
+    else rc = CIB200_EUNSUPPORTED;
     if (rc != CIB200_OK) return rc;
   }
   using WS = BinnedWarpSmem<E>;
@@ -931,7 +950,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
   const int use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   if constexpr (E == 5) {
    if (cellsort && !lq) {
-    bin_cellsort_kernel<false><<<bs->nblk, 1024, cellsort_smem_bytes(false), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr);
+    bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     auto kern = eval_cellrun_kernel<E, TC>;
@@ -994,6 +1013,12 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
       set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
       return CIB200_ECUDA;
     }
+    if (!f32) {  // brick rows of 28 doubles: the B-fragment loads of the tensor-core kernel are conflict-free at that pitch
+      cuuint32_t box28[3] = {CELLMMA_PITCH, BRICK_SIDE, BRICK_SIDE};
+      bs->tmap28_valid = encode_fn()(&bs->tmap28, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(p.coefs), gdim, gstr, box28, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
     h->bin_state = bs;
   }
   // scratch
@@ -1025,7 +1050,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     bs->n_items = (unsigned *)base;
     base += 256;
     bs->slots = (unsigned *)base;
-    base += align_up(4 * (size_t)nq, 256);
+    base += align_up(8 * (size_t)nq, 256);
     bs->tile_nslots = (unsigned *)base;
   }
   const BinGeom &g = bs->g;
@@ -1069,6 +1094,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   int lq = 0;
   if (cellsort && !f32 && nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024) lq = (double)nq >= 2.0 * ncell ? 2 : 1;
   if (const char *e = tune_env("CIB200_LANEQUERY")) lq = cellsort && !f32 ? atoi(e) : 0;
+  if (lq == 3 && !(bs->tmap28_valid && cellmma_smem_bytes(p) <= 227 * 1024)) lq = 0;
   switch (p.eqs[0]) {
     // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
     case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)

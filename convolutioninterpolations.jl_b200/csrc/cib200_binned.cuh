@@ -26,6 +26,7 @@ static constexpr int MAX_BINS = 49152;       // u32 histogram must fit one CTA's
 // more tiles than that (:b13 on 512^3: 8^3-cell tiles, 262 144 of them): ONE histogram / ONE write cursor per tile in
 // global memory, shared by all CTAs (L2 atomics) instead of private ones per CTA in shared memory
 static constexpr int MAX_BINS_GLOBAL = 1 << 21;
+static constexpr int CELLMMA_PITCH = 28;       // brick row pitch of the tensor-core kernel (doubles)
 static constexpr int CELLS_MAX = 4096;        // cells of a tile the cell sort handles: T^3 with T = 16 (E = 5)
 
 struct BinGeom {
@@ -67,14 +68,21 @@ struct BinState {
   WorkItem *items;
   unsigned *n_items;  // [0] = number of items, [1] = work counter
   size_t max_items;
-  unsigned *slots;        // [nq] slot list of the lane-per-query kernel (pairs of records of one cell), per tile
-  unsigned *tile_nslots;  // [nbin] slots of each tile
+  unsigned *slots;        // [nq] slot list (u32) of the lane-per-query kernel / group list (uint2) of the tensor-core kernel
+  unsigned *tile_nslots;  // [nbin] slots / groups of each tile
+  CUtensorMap tmap28;     // the same coefficient array with brick rows of 28 elements (tensor-core kernel, Float64)
+  int tmap28_valid;
 };
 
 // lane-per-query evaluation kernel (cib200_lanequery.cu): records sorted by (tile, cell) in bs->rec2; qpl = 2 also needs
 // the slot list of bin_cellsort_kernel<true>
 size_t lanequery_smem_bytes(const ItpParams &p, bool f32);
 int launch_eval_lanequery(cib200_itp *h, BinState *bs, const Scale &sc, void *out, int qpl, cudaStream_t st);
+// tensor-core evaluation kernel (cib200_cellmma.cu): records sorted by (tile, cell) + the group list of bin_cellsort_kernel<2>
+size_t cellmma_smem_bytes(const ItpParams &p);
+int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st);
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG, SYNCS) -----------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -37,8 +37,6 @@ __device__ __forceinline__ void lq_axis_weights(const double *__restrict__ kr, c
   }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <int E, int QPL, int NT, bool ZLAZY, typename TC>
 __global__ void __launch_bounds__(NT, 1)
     eval_lanequery_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,

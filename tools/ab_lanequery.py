@@ -25,8 +25,7 @@ xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in
 out = torch.empty(nq, dtype=torch.float64, device="cuda")
 itp.itp.set_profiling(True)
 ref = None
-cases = [("cellrun", "0", "0"), ("lq2 256thr", "2", "0"), ("lq2 384thr zlazy", "2", "1"), ("lq2 256thr zlazy", "2", "2"),
-         ("lq1 384thr", "1", "0"), ("lq1 384thr zlazy", "1", "1"), ("lq1 512thr zlazy", "1", "2")]
+cases = [("cellrun", "0", "0"), ("lq2 256thr", "2", "0"), ("mma 384thr breg", "3", "0"), ("mma 384thr", "3", "1"), ("mma 512thr", "3", "2"), ("mma 512thr breg", "3", "3")]
 only = os.environ.get("AB_CASES")  # comma-separated case names
 reps = int(os.environ.get("AB_REPS", "3"))
 for name, lq, var in cases:
@@ -34,6 +33,7 @@ for name, lq, var in cases:
         continue
     os.environ["CIB200_LANEQUERY"] = lq
     os.environ["CIB200_LQ_VARIANT"] = var
+    os.environ["CIB200_MMA_VARIANT"] = var
     best = None
     for _ in range(reps):
         itp.eval(*xs, out=out)
@@ -52,16 +52,17 @@ for name, lq, var in cases:
 if os.environ.get("AB_SPARSE"):
     # sparse batches: eval_binned_kernel (no cell sort) against cell sort + lane-per-query kernel, one query per lane
     print("sparse batches on the same grid: whole call (binning + cell sort + evaluation), ms")
-    for lg in (18, 20, 22, 24, 26, 28):
+    for lg in (18, 20, 22, 24, 26, 27, 28, 29):
         m = 1 << lg
         if m > nq:
             break
         q = [x[:m] for x in xs]
         row = []
-        for cs, lq in (("0", "0"), ("1", "0"), ("1", "1"), ("1", "2")):
+        for cs, lq in (("0", "0"), ("1", "0"), ("1", "2"), ("1", "3")):
             os.environ["CIB200_BINNED_CELLSORT"] = cs
             os.environ["CIB200_LANEQUERY"] = lq
             os.environ["CIB200_LQ_VARIANT"] = "0"
+            os.environ["CIB200_MMA_VARIANT"] = "0"
             best = 1e30
             for _ in range(3):
                 itp.eval(*q, out=out[:m])
@@ -69,4 +70,4 @@ if os.environ.get("AB_SPARSE"):
                 ms = itp.itp.last_pass_ms()
                 best = min(best, sum(ms.values()))
             row.append(best)
-        print(f"2^{lg}: eval_binned {row[0]:8.3f}   cellsort+cellrun {row[1]:8.3f}   cellsort+lq1 {row[2]:8.3f}   cellsort+lq2 {row[3]:8.3f}", flush=True)
+        print(f"2^{lg}: eval_binned {row[0]:8.3f}   cellsort+cellrun {row[1]:8.3f}   cellsort+lq2 {row[2]:8.3f}   cellsort+mma {row[3]:8.3f}", flush=True)
