@@ -18,6 +18,7 @@ BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
 SUBGRID_IDS = {"cubic": 0, "quintic": 1, "linear": 2}
 EVAL_MODES = {"auto": 0, "gather": 1, "binned": 2}
+STRATEGIES = {0: "none", 1: "gather", 2: "binned", 3: "cellrun", 4: "lanequery", 5: "cellmma"}  # cib200_strategy
 
 # every symbol include/cib200.h declares (tests assert the library exports all of them)
 SYMBOLS = [
@@ -25,7 +26,7 @@ SYMBOLS = [
     "cib200_build_coefs", "cib200_extend_knots", "cib200_itp_create", "cib200_itp_destroy",
     "cib200_itp_set_eval_mode", "cib200_itp_eval", "cib200_itp_eval_grid", "cib200_itp_scratch_bytes",
     "cib200_resample", "cib200_resample_sg", "cib200_smooth", "cib200_smooth_halfwidth", "cib200_host_register",
-    "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms",
+    "cib200_host_unregister", "cib200_itp_set_profiling", "cib200_itp_last_pass_ms", "cib200_itp_last_strategy",
     "cib200_build_coefs_device", "cib200_itp_get_coefs", "cib200_itp_eval_multi", "cib200_device_count",
     "cib200_set_device", "cib200_itpnd_create", "cib200_itpnd_destroy", "cib200_itpnd_eval", "cib200_itpnd_eval_grid",
     "cib200_itp_create_tables", "cib200_itpnd_create_tables", "cib200_resample_tables",
@@ -108,6 +109,7 @@ def lib():
     L.cib200_itg_get.argtypes = [vp, i32, i32, vp]
     L.cib200_itp_set_profiling.argtypes = [vp, i32]
     L.cib200_itp_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.cib200_itp_last_strategy.argtypes = [vp]
     L.cib200_itp_scratch_bytes.restype = i64
     L.cib200_itp_scratch_bytes.argtypes = [vp, i64]
     L.cib200_resample.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, i32, vp]

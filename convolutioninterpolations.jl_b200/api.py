@@ -492,6 +492,11 @@ class FastConvolutionInterpolation:
         check(lib().cib200_itp_last_pass_ms(self._handle, ms))
         return dict(zip(("binning", "cellsort", "eval_kernel", "spill"), (float(v) for v in ms)))
 
+    def last_strategy(self):
+        """Which evaluation kernel the most recent 3-D call ran: gather | binned | cellrun | lanequery | cellmma
+        (cib200_itp_last_strategy; measurement / test hook)."""
+        return _lib.STRATEGIES[int(lib().cib200_itp_last_strategy(self._handle))]
+
     def close(self):
         hs = getattr(self, "_handles", None) or ([self._handle] if getattr(self, "_handle", None) else [])
         self._handle, self._handles = None, []

@@ -396,6 +396,7 @@ static int eval_dispatch(cib200_itp *h, const Coords &c, void *out, long long nq
     return CIB200_OK;
   }
   for (int i = 0; i < 3; ++i) prof_mark(h, i, st);
+  h->last_strategy = CIB200_STRATEGY_GATHER;
   const int rc = launch_eval(h, c, out, nq, st);
   prof_mark(h, 3, st);
   prof_mark(h, 4, st);
@@ -773,6 +774,8 @@ int32_t cib200_itp_last_pass_ms(cib200_itp *h, float *ms) {
   for (int i = 0; i < 4; ++i) CIB_CUDA(cudaEventElapsedTime(&ms[i], h->prof_ev[i], h->prof_ev[i + 1]));
   return CIB200_OK;
 }
+
+int32_t cib200_itp_last_strategy(cib200_itp *h) { return h ? h->last_strategy : 0; }
 
 int64_t cib200_itp_scratch_bytes(cib200_itp *h, int64_t nq) {
   if (!h) return 0;

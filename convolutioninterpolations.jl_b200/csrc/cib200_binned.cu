@@ -1089,12 +1089,18 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   for (int d = 0; d < 3; ++d)
     if (p.npre[d] != CIB_N_PRE) cellsort = false;  // the cell-run kernel addresses its tables inside shared memory
-  // lane-per-query kernel (cib200_lanequery.cu): Float64 :b5-width stencils on cell-sorted records; two queries per lane
-  // from two queries per cell upwards
+  // cell-sorted strategies for Float64 :b5-width stencils (every table staged in shared memory):
+  //   >= 2.5 queries per cell: the tensor-core kernel (cib200_cellmma.cu; measured crossover with eval_cellrun_kernel on
+  //                            512^3: 2^28 queries = 2 per cell 93 vs 91 ms, 2^29 143 vs 162 ms, 10^9 228 vs 286 ms)
+  //   >= 0.5 query per cell:   eval_cellrun_kernel
+  // the lane-per-query kernel (cib200_lanequery.cu: 195 ms per 10^9 where the tensor-core kernel takes 166) is kept for
+  // experiments builds (CIB200_LANEQUERY=1|2)
   int lq = 0;
-  if (cellsort && !f32 && nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024) lq = (double)nq >= 2.0 * ncell ? 2 : 1;
+  if (cellsort && !f32 && (double)nq >= 2.5 * ncell && bs->tmap28_valid && cellmma_smem_bytes(p) <= 227 * 1024) lq = 3;
   if (const char *e = tune_env("CIB200_LANEQUERY")) lq = cellsort && !f32 ? atoi(e) : 0;
   if (lq == 3 && !(bs->tmap28_valid && cellmma_smem_bytes(p) <= 227 * 1024)) lq = 0;
+  if ((lq == 1 || lq == 2) && !(nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024)) lq = 0;
+  h->last_strategy = lq == 3 ? CIB200_STRATEGY_CELLMMA : (lq ? CIB200_STRATEGY_LANEQUERY : (cellsort ? CIB200_STRATEGY_CELLRUN : CIB200_STRATEGY_BINNED));
   switch (p.eqs[0]) {
     // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
     case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)

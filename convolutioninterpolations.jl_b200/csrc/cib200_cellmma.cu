@@ -350,13 +350,13 @@ static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, double *out,
 }
 
 int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st) {
-  int variant = 0;
+  int variant = 2;  // 16 warps, B fragments straight from the brick: measured best (tools/ab_lanequery.py)
   if (const char *e = tune_env("CIB200_MMA_VARIANT")) variant = atoi(e);
   switch (variant) {
     case 1: return launch_mma<384, false>(h, bs, sc, (double *)out, st);
-    case 2: return launch_mma<512, false>(h, bs, sc, (double *)out, st);
     case 3: return launch_mma<512, true>(h, bs, sc, (double *)out, st);
-    default: return launch_mma<384, true>(h, bs, sc, (double *)out, st);
+    case 0: return launch_mma<384, true>(h, bs, sc, (double *)out, st);
+    default: return launch_mma<512, false>(h, bs, sc, (double *)out, st);
   }
 }
 

@@ -127,6 +127,7 @@ struct cib200_itp {
   int profiling;
   cudaEvent_t prof_ev[5];  // before binning | after scatter | after cell sort | after evaluation | after spill
   int prof_valid;
+  int last_strategy;  // cib200_strategy of the most recent evaluation
 };
 
 namespace cib {

@@ -247,6 +247,17 @@ int32_t cib200_itgnd_eval_grid(cib200_itgnd *handle, const int64_t *n, const voi
  * No counterpart in the reference. */
 int32_t cib200_itp_set_profiling(cib200_itp *handle, int32_t enable);
 int32_t cib200_itp_last_pass_ms(cib200_itp *handle, float *ms4);
+/* which evaluation kernel the most recent 3-D point-evaluation call on this handle ran (cib200_strategy below;
+ * host-buffer calls: the strategy of the last chunk).  Measurement / test hook, no counterpart in the reference. */
+typedef enum {
+  CIB200_STRATEGY_NONE = 0,
+  CIB200_STRATEGY_GATHER = 1,    /* eval_thread_kernel / eval_warp3d_kernel straight from global memory             */
+  CIB200_STRATEGY_BINNED = 2,    /* tile binning + eval_binned_kernel (TMA-staged bricks)                            */
+  CIB200_STRATEGY_CELLRUN = 3,   /* + cell sort, eval_cellrun_kernel (register-resident stencils)                    */
+  CIB200_STRATEGY_LANEQUERY = 4, /* + cell sort, eval_lanequery_kernel (experiments builds only)                     */
+  CIB200_STRATEGY_CELLMMA = 5    /* + cell sort with group list, eval_cellmma_kernel (FP64 tensor cores, DMMA)       */
+} cib200_strategy;
+int32_t cib200_itp_last_strategy(cib200_itp *handle);
 
 /* bytes of device scratch the BINNED strategy needs for nq queries (0 for the other modes) */
 int64_t cib200_itp_scratch_bytes(cib200_itp *handle, int64_t nq);

@@ -95,10 +95,11 @@ def test_c5_small_3d_b5(ci, oracle, extrap):
 
 
 def test_c5_full_grid_512_cube_2e26_queries_against_the_oracle(ci, oracle):
-    """BASELINE config 5 on its REAL grid: 512^3 :b5, 2^26 uniformly random queries through AUTO (tile binning + cell
-    sort + register-resident stencils: 32 768 tiles, u32 record offsets, 16 384-record work items), device-resident;
-    a strided subsample of 2^20 results against the oracle on the same grid, and every result finite.  A second batch
-    of 2^22 + 5 queries takes the binned kernel without the cell sort (below 0.5 query per cell)."""
+    """BASELINE config 5 on its REAL grid: 512^3 :b5 through AUTO, device-resident, three densities: 4 10^8 + 9 uniformly
+    random queries (3 per cell: tile binning + cell sort with group list + the tensor-core kernel; 32 768 tiles, u32 record
+    offsets, ragged groups), 2^26 (cell sort + register-resident stencils) and 2^22 + 5 (binned kernel without the cell
+    sort, below 0.5 query per cell); a strided subsample of >= 2^20 results against the oracle on the same grid, and
+    every result finite."""
     import torch
     rng = np.random.default_rng(0xC1B200 + 5)
     n = 512
@@ -114,11 +115,12 @@ def test_c5_full_grid_512_cube_2e26_queries_against_the_oracle(ci, oracle):
     itp = ci.convolution_interpolation((g, g, g), v, kernel="b5", bc="poly")
     assert np.array_equal(itp.itp.coefs, o.coefs) or np.abs(itp.itp.coefs - o.coefs).max() <= 1e-13 * np.abs(o.coefs).max()
     S = _scale(o)
-    for nq, stride in ((1 << 26, 64), ((1 << 22) + 5, 4)):
+    for nq, stride, strategy in ((400_000_009, 256, "cellmma"), (1 << 26, 64, "cellrun"), ((1 << 22) + 5, 4, "binned")):
         gen = torch.Generator(device="cuda")
         gen.manual_seed(nq)
         xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in range(3)]
         out = itp.eval(*xs)
+        assert itp.itp.last_strategy() == strategy
         assert bool(torch.isfinite(out).all())
         sub = slice(0, nq, stride)
         q = [x[sub].cpu().numpy() for x in xs]
@@ -536,6 +538,54 @@ def test_linear_subgrid_interpolants_on_the_binned_strategy(ci, oracle, kw):
     assert rel_err(rb, o.eval(*q), S).max() <= TOL64
 
 
+@pytest.mark.parametrize("kw,strategy", [(dict(kernel="b5"), "cellmma"), (dict(kernel="b5", derivative=(1, 1, 1), bc="detect"), "cellmma"),
+                                         (dict(kernel="b5", subgrid="linear", linear_rows=101), "cellmma"),
+                                         (dict(kernel="b5", derivative=(1, 0, 2)), "cellrun"),
+                                         (dict(kernel="b5", derivative=(0, 1, 0)), "cellrun")])
+def test_tensor_core_strategy_against_the_oracle(ci, oracle, kw, strategy):
+    """Dense batches of a Float64 :b5-width interpolant (>= 2.5 queries per cell) take eval_cellmma_kernel: the axis-0
+    contraction of up to 8 queries of an aligned cell pair as FP64 tensor-core products (DMMA), weights from the staged
+    cubic-in-t tables.  Same results as the gather kernel (a few ulp: another association) and as the oracle, for plain
+    evaluation, a derivative, the linear subgrid, queries outside the domain (spill bin), ragged cell-pair groups
+    (1 .. 8 queries) and adversarially clustered batches; a query's bits do not depend on the batch it arrives in.
+    Interpolants with more than one distinct (K, K') table pair (mixed derivative orders) do not fit their staged tables
+    next to the brick and stay on eval_cellrun_kernel."""
+    import warnings
+    import torch
+    rng = np.random.default_rng(57)
+    shape = (54, 47, 41)  # 53 cells along axis 0: the last cell pair of a row is half empty (padded extent even: TMA strides)
+    knots = tuple(np.linspace(0, 1, n) for n in shape)
+    v = _field(shape, rng, noise=0.02)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gb = ci.convolution_interpolation(knots, v, extrap="flat", eval_mode="binned", **kw)
+        gg = ci.convolution_interpolation(knots, v, extrap="flat", eval_mode="gather", **kw)
+    o = oracle.convolution_interpolation(knots, v, extrap="flat", **{k: w for k, w in kw.items() if k != "linear_rows"}) \
+        if "linear_rows" not in kw else None
+    S = np.abs(v).max() if o is None else _scale(o)
+    nq = 600_011  # ~6 per cell
+    q = rng.uniform(-0.01, 1.01, (3, nq))
+    q[:, :50_000] = (0.37 + 0.02 * rng.random((3, 50_000)))            # a dense blob: many full groups per cell pair
+    q[:, 50_000:50_100] = np.array([[0.5], [0.25], [0.75]])            # 100 identical queries
+    rb, rg = gb.eval(*q), gg.eval(*q)
+    assert gb.itp.last_strategy() == strategy
+    assert np.isfinite(rb).all()
+    scale_g = S if o is not None else np.abs(rg).max()
+    assert rel_err(rb, rg, scale_g).max() <= 1e-13
+    if o is not None:
+        assert rel_err(rb, o.eval(*q), S).max() <= TOL64
+    assert np.all(rb[50_000:50_100] == rb[50_000])
+    # batch independence, bitwise: a permuted batch and a sub-batch that is still dense enough for the same kernel
+    perm = rng.permutation(nq)
+    rp = gb.eval(*q[:, perm])
+    assert np.array_equal(rp, rb[perm])
+    half = gb.eval(*np.ascontiguousarray(q[:, : nq // 2]))
+    assert gb.itp.last_strategy() == strategy and np.array_equal(half, rb[: nq // 2])
+    # device-resident tensors through the same path
+    tq = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in q]
+    assert np.array_equal(gb.eval(*tq).cpu().numpy(), rb)
+
+
 def test_binned_device_resident_and_auto_mode(ci):
     import torch
     rng = np.random.default_rng(32)
@@ -590,7 +640,11 @@ def test_host_buffer_pipeline_equals_device_resident(ci):
         g = ci.convolution_interpolation(k, v, bc="poly", eval_mode=mode)
         dev = g.eval(*tq).cpu().numpy()
         host = g.eval(*q)
-        assert np.array_equal(host, dev), mode
+        # (binned: the 2^24-query chunks take the tensor-core kernel like the device-resident call, the ragged last chunk
+        # of 12 345 queries the sparse kernel - another association of the stencil sum, a few ulp)
+        full = 3 * (1 << 24)
+        assert np.array_equal(host[:full], dev[:full]), mode
+        assert np.abs(host[full:] - dev[full:]).max() <= (0.0 if mode == "gather" else 1e-14 * np.abs(v).max()), mode
         g.itp.close()
 
 
