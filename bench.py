@@ -425,6 +425,7 @@ def main():
     barrier()
     launches = ci.launch_count() - launches0
     passes = itp.itp.last_pass_ms()  # the last timed step, measured live with CUDA events
+    strategy = itp.itp.last_strategy()  # the kernel the timed steps ran (cib200_itp_last_strategy)
     itp.itp.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
@@ -552,13 +553,13 @@ def main():
         kernel_ms = passes["eval_kernel"]  # the dominant kernel's own launch, CUDA events inside the library
         achieved = BYTES_PER_EVAL * nq / (kernel_ms * 1e-3) / 1e9
         traffic = ncu_traffic_per_eval()
-        binned = passes["binning"] > 0
-        cellrun = passes["cellsort"] > 0
-        tr = (traffic or {}).get("cellrun" if cellrun else ("binned" if binned else "gather"), {})
-        kname = ("eval_cellrun_kernel<5>" if cellrun else "eval_binned_kernel<5>") if binned else "eval_warp3d_kernel<double,5>"
+        cellrun = strategy in ("cellrun", "cellmma")
+        tr = (traffic or {}).get(strategy, {})
+        kname = {"cellmma": "eval_cellmma_kernel<512,false>", "cellrun": "eval_cellrun_kernel<5>", "binned": "eval_binned_kernel<5>",
+                 "lanequery": "eval_lanequery_kernel<5,2>"}.get(strategy, "eval_warp3d_kernel<double,5>")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": tr.get("dram_bytes_per_eval") and tr["dram_bytes_per_eval"] * nq,
-                    "kernel": kname, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_avg_ms,
+                    "kernel": kname, "strategy": strategy, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_avg_ms,
                     "passes_ms": passes,
                     "whole_step": {"achieved": BYTES_PER_EVAL * nq / (step_avg_ms * 1e-3) / 1e9,
                                    "frac": BYTES_PER_EVAL * nq / (step_avg_ms * 1e-3) / 1e9 / peak},
@@ -573,9 +574,12 @@ def main():
                     "dram_frac": (tr.get("dram_bytes_per_eval") and
                                   tr["dram_bytes_per_eval"] * nq / (kernel_ms * 1e-3) / 1e9 / peak),
                     "fp64_frac": tr.get("fp64_pipe_active_pct") and tr["fp64_pipe_active_pct"] / 100.0,
+                    "dmma_frac": tr.get("dmma_pipe_active_pct") and tr["dmma_pipe_active_pct"] / 100.0,
                     "smem_wavefronts_per_eval": tr.get("smem_wavefronts_per_eval"),
                     "smem_frac": tr.get("l1tex_throughput_pct") and tr["l1tex_throughput_pct"] / 100.0,
-                    "bound_by": "shared-memory bandwidth (l1tex), then the FP64 pipe; DRAM is at dram_frac" if cellrun else None}
+                    "bound_by": ("shared-memory return path (l1tex) and the FP64 pipe (DMMA + DFMA) together; DRAM is at dram_frac"
+                                 if strategy == "cellmma" else
+                                 "shared-memory bandwidth (l1tex), then the FP64 pipe; DRAM is at dram_frac" if cellrun else None)}
         cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
