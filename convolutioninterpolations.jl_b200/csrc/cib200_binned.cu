@@ -172,7 +172,11 @@ __global__ void bin_offsets_kernel(BinGeom g, int nblk, unsigned *__restrict__ h
   }
 }
 
-template <typename T>
+// POSREC (tensor-core evaluation kernel): the record of a query inside the domain carries its POSITIONS instead of its
+// coordinates - {t_0, t_1, t_2, index, (row_0 + 100 (row_1 + 100 row_2)) << 12 | cell in tile} - computed here once with
+// the reference's arithmetic (locate_from_knot), so the evaluation kernel starts from table rows and fractions without a
+// single division.  Records of the spill bin keep the coordinates.
+template <typename T, bool POSREC>
 __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGeom g, Coords c, long long nq,
                                                               unsigned *hist, Record *__restrict__ rec, int dbg) {
   extern __shared__ unsigned sh[];
@@ -206,7 +210,15 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
         unsigned lc;
         const int bin_ = classify(p, g, x[u], k0, lc);
         const unsigned slot = shared_cursors ? atomicAdd(hist + bin_, 1u) : atomicAdd(&sh[bin_], 1u);
-        // one 32-byte sector per query, written with two 16-byte stores; the spare word carries the cell inside the tile
+        if (POSREC && bin_ != g.ntiles) {
+          AxisPos pa[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) locate_from_knot(x[u][d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
+          const unsigned code = ((unsigned)(pa[0].row + 100 * (pa[1].row + 100 * pa[2].row)) << 12) | lc;
+          st_record(rec + slot, pa[0].t, pa[1].t, pa[2].t, __hiloint2double((int)code, (int)(unsigned)q));
+          continue;
+        }
+        // one 32-byte sector per query, written with one 32-byte store; the spare word carries the cell inside the tile
         st_record(rec + slot, x[u][0], x[u][1], x[u][2], __hiloint2double((int)lc, (int)(unsigned)q));
       }
     }
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
-        cell[u] = r < r1 ? __ldg((const int2 *)(rec + r) + 3).y : -1;  // {idx, cell}
+        cell[u] = r < r1 ? (__ldg((const int2 *)(rec + r) + 3).y & (CELLS_MAX - 1)) : -1;  // {idx, cell (+ table rows above bit 12)}
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
         if (r < r1) {
-          const int cell = __double2hiint(b[u].y);
+          const int cell = __double2hiint(b[u].y) & (CELLS_MAX - 1);
           const unsigned pos = atomicAdd(&hist[cell], 1u);
           st_record(rec2 + pos, a[u].x, a[u].y, b[u].x, b[u].y);
           if (MODE == 1) {
@@ -1057,29 +1069,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   Scale sc;
   for (int d = 0; d < 3; ++d) sc.s[d] = jl_pow_int(-1.0 / p.h[d], h->deriv[d]);
   sc.perdim2d = 0;
-  const bool global_hist = g.nbin > MAX_BINS;
-  const int hrows = global_hist ? 1 : bs->nblk;
-  const size_t hsm = global_hist ? 0 : 4 * (size_t)g.nbin;
-  if (global_hist) CIB_CUDA(cudaMemsetAsync(bs->hist, 0, 4 * (size_t)g.nbin, st));
   const bool f32 = h->dtype == CIB200_F32;
-  auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
-  auto kscatter = f32 ? bin_scatter_kernel<float> : bin_scatter_kernel<double>;
-  CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-  CIB_CUDA(cudaFuncSetAttribute(kscatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-  prof_mark(h, 0, st);
-  kcount<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, global_hist ? 1 : 0);
-  CIB_LAUNCHED();
-  bin_totals_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
-  CIB_LAUNCHED();
-  bin_scan_kernel<<<1, 1024, 0, st>>>(g, bs->tile_start, bs->items, bs->n_items);
-  CIB_LAUNCHED();
-  bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
-  CIB_LAUNCHED();
-  static const int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
-  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, global_hist ? 3 : scatter_mode);
-  CIB_LAUNCHED();
-  CIB_CUDA(cudaGetLastError());
-  prof_mark(h, 1, st);
   // cell-sorted variant: pays one more streaming pass over the records (64 B/query) to keep each cell's stencil in
   // registers across the queries that share it - worth it from about one query per two cells upwards (measured)
   double ncell = 1.0;
@@ -1101,6 +1091,29 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   if (lq == 3 && !(bs->tmap28_valid && cellmma_smem_bytes(p) <= 227 * 1024)) lq = 0;
   if ((lq == 1 || lq == 2) && !(nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024)) lq = 0;
   h->last_strategy = lq == 3 ? CIB200_STRATEGY_CELLMMA : (lq ? CIB200_STRATEGY_LANEQUERY : (cellsort ? CIB200_STRATEGY_CELLRUN : CIB200_STRATEGY_BINNED));
+  const bool global_hist = g.nbin > MAX_BINS;
+  const int hrows = global_hist ? 1 : bs->nblk;
+  const size_t hsm = global_hist ? 0 : 4 * (size_t)g.nbin;
+  if (global_hist) CIB_CUDA(cudaMemsetAsync(bs->hist, 0, 4 * (size_t)g.nbin, st));
+  auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
+  // (the tensor-core kernel reads position records: table rows and fractions computed once, in the scatter pass)
+  auto kscatter = f32 ? bin_scatter_kernel<float, false> : (lq == 3 ? bin_scatter_kernel<double, true> : bin_scatter_kernel<double, false>);
+  CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+  CIB_CUDA(cudaFuncSetAttribute(kscatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+  prof_mark(h, 0, st);
+  kcount<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, global_hist ? 1 : 0);
+  CIB_LAUNCHED();
+  bin_totals_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
+  CIB_LAUNCHED();
+  bin_scan_kernel<<<1, 1024, 0, st>>>(g, bs->tile_start, bs->items, bs->n_items);
+  CIB_LAUNCHED();
+  bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
+  CIB_LAUNCHED();
+  static const int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
+  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, global_hist ? 3 : scatter_mode);
+  CIB_LAUNCHED();
+  CIB_CUDA(cudaGetLastError());
+  prof_mark(h, 1, st);
   switch (p.eqs[0]) {
     // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
     case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)

@@ -117,14 +117,12 @@ __global__ void __launch_bounds__(NT, 1)
   double *wq = wsm + WS::TQ + WS::MISC;  // [8][WQS]
   unsigned long long *bar = (unsigned long long *)(smd + wbase + nwarps * WS::DOUBLES);
   unsigned *slot = (unsigned *)(bar + 1);  // [2]
-  double *kt = (double *)(bar + 2);        // [3][32]: the stored knots the tile's queries can select
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = lane; i < WS::WQ; i += 32) wq[i] = 0.0;  // the zero pads of WX / wz are never written again
   __syncthreads();
-  const double k0[3] = {p.knot0[0], p.knot0[1], p.knot0[2]};
   // weight role of this lane: quarter-warp = one (query, axis) pair per pass, lane = pair of taps (lanes 5..7 idle)
   const int wquarter = lane >> 3;
   const bool wrole = (lane & 7) < 5;
@@ -155,11 +153,6 @@ __global__ void __launch_bounds__(NT, 1)
     if (cnt == 0) continue;  // block-uniform
     const int tx = it.bin % g.nt[0], ty = (it.bin / g.nt[0]) % g.nt[1], tz = it.bin / (g.nt[0] * g.nt[1]);
     const int org[3] = {tx * g.T, ty * g.T, tz * g.T};
-    if (threadIdx.x < 96) {
-      const int d = threadIdx.x >> 5, r = threadIdx.x & 31;
-      const int o = d == 0 ? org[0] : (d == 1 ? org[1] : org[2]);
-      kt[threadIdx.x] = __ldg(p.knots[d] + min(o + r, p.nk[d] - 1));
-    }
     if (threadIdx.x == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(bar, MELEMS * 8);
@@ -167,7 +160,6 @@ __global__ void __launch_bounds__(NT, 1)
     }
     mbar_wait(bar, parity);
     parity ^= 1;
-    __syncthreads();  // kt
     // contiguous range of this warp, in batches of 4 groups (32 records: lane = (group, row))
     const unsigned per = ((cnt + nwarps - 1) / nwarps + 3u) & ~3u;
     const unsigned w0 = warp * per, w1 = min(cnt, w0 + per);
@@ -188,18 +180,18 @@ __global__ void __launch_bounds__(NT, 1)
       // ---- phase 1: one record per lane: positions into the warp's scratch ----------------------------------------
       __syncwarp();  // the previous batch is done with tq / misc
       if ((unsigned)prow < ge.y) {
+        // position record (bin_scatter_kernel<double, true>): {t_0, t_1, t_2, index, rows << 12 | cell in tile}
         double2 ra, rb;
         ld_record(rc + ge.x + prow, ra, rb);
-        const double x[3] = {ra.x, ra.y, rb.x};
-        AxisPos pa[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          locate_from_knot(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], kt + 32 * d - org[d], pa[d]);
-          tq[lane * 3 + d] = pa[d].t;
-        }
-        const int bx = pa[0].base - org[0];
-        const int m = bx + (pa[1].base - org[1]) * MP + (pa[2].base - org[2]) * MPL;
-        misc[lane] = make_int4(2 * m + (bx & 1), pa[0].row | (pa[1].row << 10) | (pa[2].row << 20), __double2loint(rb.y), 0);
+        tq[lane * 3 + 0] = ra.x;
+        tq[lane * 3 + 1] = ra.y;
+        tq[lane * 3 + 2] = rb.x;
+        const unsigned code = (unsigned)__double2hiint(rb.y);
+        const unsigned lc = code & 4095u, rcode = code >> 12;
+        const unsigned rz = rcode / 10000u, ry = (rcode - rz * 10000u) / 100u, rx = rcode - rz * 10000u - ry * 100u;
+        const int bx = lc & 15u;  // T = 16 cells per tile side (2E = 10)
+        const int m = bx + (int)((lc >> 4) & 15u) * MP + (int)(lc >> 8) * MPL;
+        misc[lane] = make_int4(2 * m + (bx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
       }
       if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
       __syncwarp();
