@@ -1086,9 +1086,22 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   // the lane-per-query kernel (cib200_lanequery.cu: 195 ms per 10^9 where the tensor-core kernel takes 166) is kept for
   // experiments builds (CIB200_LANEQUERY=1|2)
   int lq = 0;
-  if (cellsort && !f32 && (double)nq >= 2.5 * ncell && bs->tmap28_valid && cellmma_smem_bytes(p) <= 227 * 1024) lq = 3;
-  if (const char *e = tune_env("CIB200_LANEQUERY")) lq = cellsort && !f32 ? atoi(e) : 0;
-  if (lq == 3 && !(bs->tmap28_valid && cellmma_smem_bytes(p) <= 227 * 1024)) lq = 0;
+  {
+    // tensor-core kernel: any :b-series width (tile side 26 - 2E is even: aligned cell pairs), every table staged
+    bool mma_ok = !f32 && bs->tmap28_valid && g.T % 2 == 0 && g.T * g.T * g.T <= CELLS_MAX && p.eqs[0] >= 5;
+    for (int d = 0; d < 3; ++d)
+      if (p.npre[d] != CIB_N_PRE) mma_ok = false;
+    const int kind = mma_ok ? cellmma_kind(p) : 0;
+    // against eval_cellrun_kernel (:b5) the crossover is 2.5 queries per cell; wider kernels only have eval_binned_kernel
+    // as the alternative (:b13 on 512^3, 2.5 10^8 queries = 1.9 per cell: 678 ms against 262 ms)
+    const double dens = p.eqs[0] == 5 ? 2.5 : 1.0;
+    if (kind && (double)nq >= dens * ncell) lq = 3;
+    if (const char *e = tune_env("CIB200_LANEQUERY")) {
+      lq = atoi(e);
+      if (lq == 3 && !kind) lq = 0;
+      if ((lq == 1 || lq == 2) && !(cellsort && !f32)) lq = 0;
+    }
+  }
   if ((lq == 1 || lq == 2) && !(nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024)) lq = 0;
   h->last_strategy = lq == 3 ? CIB200_STRATEGY_CELLMMA : (lq ? CIB200_STRATEGY_LANEQUERY : (cellsort ? CIB200_STRATEGY_CELLRUN : CIB200_STRATEGY_BINNED));
   const bool global_hist = g.nbin > MAX_BINS;

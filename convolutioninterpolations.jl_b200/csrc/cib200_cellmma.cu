@@ -319,10 +319,299 @@ __global__ void __launch_bounds__(NT, 1)
   }
 }
 
+// ---- the same kernel for every :b-series width (2E = 10 .. 18) and for interpolants with several table pairs ---------------
+// Generalisation of eval_cellmma_kernel: E is a template parameter (tile side T = 26 - 2E, K = 2E + 1 padded to 4 KS,
+// (2E)^2 columns), the weights are blended from the staged K / K' tables (no cubic tables: they would not fit next to the
+// brick for wide kernels or several derivative orders), and the column tiles are processed in chunks of 13 so that the
+// accumulators stay at 26 registers whatever the width.  Column layout:
+//   regular tiles  (h, n), h < MH = 2E / 8:  column c -> (m = 8 h + c, n_z = n)
+//   leftover tiles u (the ML = 2E mod 8 remaining m):  column c -> (m = 8 MH + c / NPT, n_z = NPT u + c % NPT)
+template <int E>
+struct MmaGeom {
+  static constexpr int W = 2 * E, T = BRICK_SIDE + 1 - W;
+  static constexpr int KS = (W + 1 + 3) / 4;
+  static constexpr int MH = W / 8, ML = W % 8;
+  static constexpr int NPT = ML == 0 ? 1 : (ML <= 2 ? 4 : (ML <= 4 ? 2 : 1));
+  static constexpr int NREG = W * MH, NLEFT = ML ? (W + NPT - 1) / NPT : 0, NTILES = NREG + NLEFT;
+  static constexpr int WX_LEN = 4 * KS + 2;
+  static constexpr int WY_OFF = WX_LEN, WY_LEN = (ML && NPT == 1) ? 8 * (MH + 1) : W;
+  static constexpr int WZ_OFF = WY_OFF + WY_LEN, WZ_LEN = ML ? ((NPT * NLEFT + 1) & ~1) : W;
+  static constexpr int RAW = WX_LEN + WY_LEN + WZ_LEN;
+  static constexpr int WQS = RAW + ((4 - RAW % 16) + 16) % 16;  // = 4 mod 16 doubles: A-fragment loads of a half-warp hit distinct banks
+  static constexpr int WARP_DOUBLES = 32 * 3 + 32 * 2 + 8 * WQS;
+  static constexpr int CHUNK = 13;
+};
+
+template <int E, int NT>
+__global__ void __launch_bounds__(NT, 1)
+    eval_cellmma_gen_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
+                            const Record *__restrict__ rec, const uint2 *__restrict__ groups,
+                            const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
+                            const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, double *__restrict__ out) {
+  using G = MmaGeom<E>;
+  constexpr int W = G::W, T = G::T, KS = G::KS, MH = G::MH, NPT = G::NPT, WQS_ = G::WQS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *smd = (double *)smem_raw;
+  double *brick = smd;  // [BRICK_SIDE][BRICK_SIDE][MP], axis 0 contiguous
+  double *tab = smd + MELEMS;
+  const double *tk[3];
+  const double *td[3];
+  stage_tables(p, tab, tk, td);
+  constexpr int nwarps = NT >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wbase = MELEMS + ((tables_smem_doubles(p) + 1) & ~1);
+  double *wsm = smd + wbase + warp * G::WARP_DOUBLES;
+  double *tq = wsm;                  // [32][3]
+  int4 *misc = (int4 *)(wsm + 96);   // [32]
+  double *wq = wsm + 96 + 64;        // [8][WQS]
+  unsigned long long *bar = (unsigned long long *)(smd + wbase + nwarps * G::WARP_DOUBLES);
+  unsigned *slot = (unsigned *)(bar + 1);  // [2]
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = lane; i < 8 * WQS_; i += 32) wq[i] = 0.0;  // the zero pads are never written again
+  __syncthreads();
+  // weight role: LPC lanes per (query, axis) pair, lane = pair of taps; 32 / LPC pairs per pass
+  constexpr int LPC = W / 2 <= 8 ? 8 : 16, CPP = 32 / LPC;
+  const int wsub = lane / LPC;
+  const bool wrole = (lane % LPC) < W / 2;
+  const int wpp = wrole ? (lane % LPC) : W / 2 - 1;
+  const int tko0 = (int)(tk[0] - smd) + 2 * wpp, tko1 = (int)(tk[1] - smd) + 2 * wpp, tko2 = (int)(tk[2] - smd) + 2 * wpp;
+  const int tdo0 = (int)(td[0] - smd) + 2 * wpp, tdo1 = (int)(td[1] - smd) + 2 * wpp, tdo2 = (int)(td[2] - smd) + 2 * wpp;
+  const bool lin0 = p.subgrid[0] == CIB200_SG_LINEAR, lin1 = p.subgrid[1] == CIB200_SG_LINEAR, lin2 = p.subgrid[2] == CIB200_SG_LINEAR;
+  const int mq = lane >> 2, mr = lane & 3;
+  const int boff = mr + mq * MP;                                             // regular tiles
+  const int boff2 = mr + (8 * MH + mq / NPT) * MP + (mq % NPT) * MPL;        // leftover tiles
+  const bool lm_ok = 8 * MH + mq / NPT < W;                                  // leftover column has a real m
+  const unsigned total_items = n_items[0];
+  unsigned parity = 0;
+  for (unsigned iter = 0;; ++iter) {
+    if (threadIdx.x == 0) slot[iter & 1] = atomicAdd(&n_items[1], 1u);
+    __syncthreads();  // also: every warp is done with the previous brick
+    const unsigned item = slot[iter & 1];
+    if (item >= total_items) break;
+    const WorkItem it = items[item];
+    const unsigned r0 = tile_start[it.bin];
+    const unsigned ng = tile_ngroups[it.bin];
+    const unsigned first = min(it.start - r0, ng);
+    const unsigned cnt = min((unsigned)CHUNK_QUERIES, ng - first);
+    if (cnt == 0) continue;  // block-uniform
+    const int tx = it.bin % g.nt[0], ty = (it.bin / g.nt[0]) % g.nt[1], tz = it.bin / (g.nt[0] * g.nt[1]);
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, MELEMS * 8);
+      tma_load_3d(brick, &tmap, tx * T, ty * T, tz * T, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const unsigned per = ((cnt + nwarps - 1) / nwarps + 3u) & ~3u;
+    const unsigned w0 = warp * per, w1 = min(cnt, w0 + per);
+    const uint2 *gl = groups + r0 + first;
+    const Record *rc = rec + r0;
+    const int pg = lane >> 3, prow = lane & 7;
+    uint2 ge_n = make_uint2(0u, 0u);
+    if (w0 + pg < w1) ge_n = __ldg(gl + w0 + pg);
+    for (unsigned b0 = w0; b0 < w1; b0 += 4) {
+      const int ngb = (int)min(4u, w1 - b0);
+      const uint2 ge = ge_n;
+      ge_n = make_uint2(0u, 0u);
+      if (b0 + 4 + pg < w1) ge_n = __ldg(gl + b0 + 4 + pg);
+      __syncwarp();  // the previous batch is done with tq / misc
+      if ((unsigned)prow < ge.y) {
+        double2 ra, rb;
+        ld_record(rc + ge.x + prow, ra, rb);
+        tq[lane * 3 + 0] = ra.x;
+        tq[lane * 3 + 1] = ra.y;
+        tq[lane * 3 + 2] = rb.x;
+        const unsigned code = (unsigned)__double2hiint(rb.y);
+        const unsigned lc = code & 4095u, rcode = code >> 12;
+        const unsigned rz = rcode / 10000u, ry = (rcode - rz * 10000u) / 100u, rx = rcode - rz * 10000u - ry * 100u;
+        const unsigned cz = lc / (unsigned)(T * T), cy = (lc - cz * (unsigned)(T * T)) / (unsigned)T, cx = lc - cz * (unsigned)(T * T) - cy * (unsigned)T;
+        const int m = (int)cx + (int)cy * MP + (int)cz * MPL;
+        misc[lane] = make_int4(2 * m + (int)(cx & 1u), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
+      }
+      if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
+      __syncwarp();
+      for (int gi = 0; gi < ngb; ++gi) {
+        const int cntg = (int)__shfl_sync(0xffffffffu, ge.y, gi * 8);
+        const int sb = gi * 8;
+        // ---- weights: blended from the staged K / K' rows, CPP (query, axis) pairs per pass ------------------------------
+        const int ncombo = 3 * cntg;
+#pragma unroll 1
+        for (int c8 = 0; c8 < ncombo; c8 += 2 * CPP) {
+          double tt[2];
+          double2 ka[2], kb[2], da[2], db[2];
+          int dst[2];
+          bool li[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int ci = min(c8 + CPP * u + wsub, ncombo - 1);  // past the end: recompute the last pair, not stored
+            const int qq = (ci * 11) >> 5, ax = ci - 3 * qq;      // ci / 3, ci % 3 (ci < 24)
+            tt[u] = tq[(sb + qq) * 3 + ax];
+            const int row = ((misc[sb + qq].y >> (10 * ax)) & 1023) * W;
+            const double2 *kp = (const double2 *)(smd + (ax == 0 ? tko0 : (ax == 1 ? tko1 : tko2)) + row);
+            const double2 *dp = (const double2 *)(smd + (ax == 0 ? tdo0 : (ax == 1 ? tdo1 : tdo2)) + row);
+            ka[u] = kp[0];
+            kb[u] = kp[W / 2];
+            da[u] = dp[0];
+            db[u] = dp[W / 2];
+            li[u] = ax == 0 ? lin0 : (ax == 1 ? lin1 : lin2);
+            dst[u] = qq * WQS_ + (ax == 0 ? 2 : (ax == 1 ? G::WY_OFF : G::WZ_OFF)) + 2 * wpp;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const Hermite hb = li[u] ? linear_basis(tt[u]) : hermite_basis(tt[u]);
+            double2 wv;
+            wv.x = hb.h00 * ka[u].x + hb.h01 * kb[u].x + (hb.h10 * da[u].x + hb.h11 * db[u].x);
+            wv.y = hb.h00 * ka[u].y + hb.h01 * kb[u].y + (hb.h10 * da[u].y + hb.h11 * db[u].y);
+            if (wrole && c8 + CPP * u + wsub < ncombo) *(double2 *)(wq + dst[u]) = wv;
+          }
+        }
+        __syncwarp();
+        // ---- the axis-0 contraction on the tensor cores, 13 column tiles at a time ----------------------------------------
+        const int mf = misc[sb].x;
+        const int win = (mf >> 1) - (mf & 1);  // brick offset of the pair's first cell
+        const bool qv = mq < cntg;
+        const int4 mi = misc[sb + mq];
+        const double *wrow = wq + mq * WQS_;
+        double a[KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) a[s] = qv ? wrow[2 - (mi.x & 1) + 4 * s + mr] : 0.0;
+        double wz[W];
+#pragma unroll
+        for (int n = 0; n < W; n += 2) {
+          const double2 v = *(const double2 *)(wrow + G::WZ_OFF + n);
+          wz[n] = v.x;
+          wz[n + 1] = v.y;
+        }
+        double sreg[MH > 0 ? MH : 1][2], sl0 = 0.0, sl1 = 0.0;
+#pragma unroll
+        for (int h = 0; h < MH; ++h) sreg[h][0] = sreg[h][1] = 0.0;
+        const double *bb = brick + win + boff, *bc = brick + win + boff2;
+#pragma unroll
+        for (int c0 = 0; c0 < G::NTILES; c0 += G::CHUNK) {
+          constexpr int CH = G::CHUNK;
+          double acc[CH][2];
+#pragma unroll
+          for (int t = 0; t < CH; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+          for (int s = 0; s < KS; ++s) {
+            const bool kz = 4 * s + mr > W;  // K index beyond the (2E + 1)-wide window
+#pragma unroll
+            for (int t = 0; t < CH; ++t) {
+              const int ti = c0 + t;
+              if (ti < G::NREG) {
+                const int h = ti / W, n = ti - h * W;
+                dmma884(acc[t][0], acc[t][1], a[s], kz ? 0.0 : bb[8 * h * MP + n * MPL + 4 * s]);
+              } else if (ti < G::NTILES) {
+                const int u = ti - G::NREG;
+                const bool z = kz || !lm_ok || NPT * u + (mq % NPT) >= W;
+                dmma884(acc[t][0], acc[t][1], a[s], z ? 0.0 : bc[NPT * u * MPL + 4 * s]);
+              }
+            }
+          }
+          // partial epilogue of the chunk
+#pragma unroll
+          for (int t = 0; t < CH; ++t) {
+            const int ti = c0 + t;
+            if (ti < G::NREG) {
+              const int h = ti / W, n = ti - h * W;
+              sreg[h][0] = fma(acc[t][0], wz[n], sreg[h][0]);
+              sreg[h][1] = fma(acc[t][1], wz[n], sreg[h][1]);
+            } else if (ti < G::NTILES) {
+              const int u = ti - G::NREG;
+              if (NPT == 1) {  // columns (m = 8 MH + 2c, 2c + 1; n_z = u)
+                sl0 = fma(acc[t][0], wz[u], sl0);
+                sl1 = fma(acc[t][1], wz[u], sl1);
+              } else {  // columns (m = 8 MH + 2c / NPT; n_z = NPT u + (2c) % NPT, + 1)
+                const double2 v = *(const double2 *)(wrow + G::WZ_OFF + NPT * u + ((2 * mr) % NPT));
+                sl0 = fma(acc[t][0], v.x, sl0);
+                sl0 = fma(acc[t][1], v.y, sl0);
+              }
+            }
+          }
+        }
+        double e = 0.0;
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          const double2 wy = *(const double2 *)(wrow + G::WY_OFF + 8 * h + 2 * mr);
+          e += fma(sreg[h][0], wy.x, sreg[h][1] * wy.y);
+        }
+        if (G::ML) {
+          if (NPT == 1) {
+            const double2 wy = *(const double2 *)(wrow + G::WY_OFF + 8 * MH + 2 * mr);
+            e += fma(sl0, wy.x, sl1 * wy.y);
+          } else {
+            e += sl0 * wrow[G::WY_OFF + 8 * MH + (2 * mr) / NPT];
+          }
+        }
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        if (qv && mr == 0) out[(unsigned)mi.z] = apply_scale<3>(e, sc);
+        __syncwarp();  // wq is rewritten by the next group
+      }
+    }
+  }
+}
+
+template <int E>
+static size_t mma_gen_smem(const ItpParams &p, int nwarps) {
+  return 8 * ((size_t)MELEMS + (size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nwarps * MmaGeom<E>::WARP_DOUBLES + 2 + 96);
+}
+
+template <int E, int NT>
+static int launch_mma_gen(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
+  const ItpParams &p = h->p;
+  auto kern = eval_cellmma_gen_kernel<E, NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  kern<<<bs->nblk, NT, mma_gen_smem<E>(p, NT / 32), st>>>(bs->tmap28, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots, bs->tile_start,
+                                                         bs->tile_nslots, bs->items, bs->n_items, out);
+  CIB_LAUNCHED();
+  CIB_CUDA(cudaGetLastError());
+  return CIB200_OK;
+}
+
+// threads per CTA of the generic kernel: the most warps whose scratch fits next to the brick and the staged tables
+template <int E>
+static int mma_gen_threads(const ItpParams &p) {
+  for (int nt : {512, 384, 256})
+    if (mma_gen_smem<E>(p, nt / 32) <= 227 * 1024) return nt;
+  return 0;
+}
+template <int E>
+static int launch_mma_gen_e(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
+  switch (mma_gen_threads<E>(h->p)) {
+    case 512: return launch_mma_gen<E, 512>(h, bs, sc, out, st);
+    case 384: return launch_mma_gen<E, 384>(h, bs, sc, out, st);
+    case 256: return launch_mma_gen<E, 256>(h, bs, sc, out, st);
+  }
+  set_error("tensor-core strategy: shared memory budget exceeded");
+  return CIB200_EUNSUPPORTED;
+}
+
 static size_t mma_smem(const ItpParams &p, int nwarps) {
   return 8 * ((size_t)MELEMS + (size_t)mma_ptab_count(p) * PTAB_DOUBLES + (size_t)nwarps * MmaWarpSmem::DOUBLES + 2 + 96);
 }
 size_t cellmma_smem_bytes(const ItpParams &p) { return mma_smem(p, 16); }
+
+// 1: the tuned :b5 kernel (one table pair, cubic tables); 2: the generic kernel; 0: this interpolant does not fit
+int cellmma_kind(const ItpParams &p) {
+  const int E = p.eqs[0];
+  if (E == 5 && mma_ptab_count(p) == 1 && mma_smem(p, 16) <= 227 * 1024) return 1;
+  switch (E) {
+    case 5: return mma_gen_threads<5>(p) ? 2 : 0;
+    case 6: return mma_gen_threads<6>(p) ? 2 : 0;
+    case 7: return mma_gen_threads<7>(p) ? 2 : 0;
+    case 8: return mma_gen_threads<8>(p) ? 2 : 0;
+    case 9: return mma_gen_threads<9>(p) ? 2 : 0;
+  }
+  return 0;
+}
 
 template <int NT, bool BREG>
 static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
@@ -342,6 +631,17 @@ static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, double *out,
 }
 
 int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st) {
+  if (cellmma_kind(h->p) == 2 || tune_env("CIB200_MMA_GENERIC")) {
+    switch (h->p.eqs[0]) {
+      case 5: return launch_mma_gen_e<5>(h, bs, sc, (double *)out, st);
+      case 6: return launch_mma_gen_e<6>(h, bs, sc, (double *)out, st);
+      case 7: return launch_mma_gen_e<7>(h, bs, sc, (double *)out, st);
+      case 8: return launch_mma_gen_e<8>(h, bs, sc, (double *)out, st);
+      case 9: return launch_mma_gen_e<9>(h, bs, sc, (double *)out, st);
+    }
+    set_error("tensor-core strategy: unsupported kernel width");
+    return CIB200_EUNSUPPORTED;
+  }
   int variant = 2;  // 16 warps, B fragments straight from the brick: measured best (tools/ab_lanequery.py)
   if (const char *e = tune_env("CIB200_MMA_VARIANT")) variant = atoi(e);
   switch (variant) {

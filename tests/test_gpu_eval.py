@@ -540,16 +540,22 @@ def test_linear_subgrid_interpolants_on_the_binned_strategy(ci, oracle, kw):
 
 @pytest.mark.parametrize("kw,strategy", [(dict(kernel="b5"), "cellmma"), (dict(kernel="b5", derivative=(1, 1, 1), bc="detect"), "cellmma"),
                                          (dict(kernel="b5", subgrid="linear", linear_rows=101), "cellmma"),
-                                         (dict(kernel="b5", derivative=(1, 0, 2)), "cellrun"),
-                                         (dict(kernel="b5", derivative=(0, 1, 0)), "cellrun")])
+                                         (dict(kernel="b5", derivative=(1, 0, 2)), "cellmma"),
+                                         (dict(kernel="b5", derivative=(0, 1, 0)), "cellmma"),
+                                         (dict(kernel="b7"), "cellmma"), (dict(kernel="b9", derivative=(0, 0, 1)), "cellmma"),
+                                         (dict(kernel="b11", bc="detect"), "cellmma"), (dict(kernel="b13"), "cellmma"),
+                                         (dict(kernel="b13", derivative=(1, 1, 1)), "cellmma"),
+                                         (dict(kernel="b13", derivative=(2, 0, 1)), "binned"),  # six 14.5-kB tables do not fit next to the brick
+                                         (dict(kernel="a4"), "binned")])
 def test_tensor_core_strategy_against_the_oracle(ci, oracle, kw, strategy):
     """Dense batches of a Float64 :b5-width interpolant (>= 2.5 queries per cell) take eval_cellmma_kernel: the axis-0
     contraction of up to 8 queries of an aligned cell pair as FP64 tensor-core products (DMMA), weights from the staged
     cubic-in-t tables.  Same results as the gather kernel (a few ulp: another association) and as the oracle, for plain
     evaluation, a derivative, the linear subgrid, queries outside the domain (spill bin), ragged cell-pair groups
     (1 .. 8 queries) and adversarially clustered batches; a query's bits do not depend on the batch it arrives in.
-    Interpolants with more than one distinct (K, K') table pair (mixed derivative orders) do not fit their staged tables
-    next to the brick and stay on eval_cellrun_kernel."""
+    Interpolants with more than one distinct (K, K') table pair (mixed derivative orders) and the wider kernels (:b7 .. :b13:
+    12^3 .. 18^3 stencils, column tiles in chunks of 13) take the generic variant of the kernel (weights blended from the
+    staged K / K' tables); the a-series stays on eval_binned_kernel."""
     import warnings
     import torch
     rng = np.random.default_rng(57)
