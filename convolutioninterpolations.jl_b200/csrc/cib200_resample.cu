@@ -37,11 +37,17 @@ namespace cib {
 using namespace pipe;
 
 static constexpr int RS_R = 8;  // output knots per work item
+static constexpr int RS_MMA_PITCH = 36;  // doubles between two rows of a tile for the tensor-core consumer (axis >= 1)
+
+__device__ __forceinline__ void mma_f64_884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 struct ResamplePipeParams {
   long long inner, outer, ntiles;
   long long out_o_stride;  // axis >= 1: inner * n_out
   int n_in, n_out, nblk;
+  int nitem, bpi;   // work items per tile slot, blocks per item (tensor-core consumer: several blocks per item)
   int H;            // axis >= 1: rows of a tile buffer; axis 0: pitch P of a line
   int tiles_inner;
   int nb, nteams, ncons;
@@ -49,7 +55,7 @@ struct ResamplePipeParams {
   int padx;         // physical left margin of a line in the tile (axis 0: pad rounded up to even)
   int winmax;       // rows per block in the dense weight table
   int bcl, bcr;
-  unsigned magic_nblk, magic_nb, magic_ti, magic_teams;
+  unsigned magic_nblk, magic_nb, magic_ti, magic_teams, magic_nitem;
   double h, scale;
   const double *Wd;  // [nblk][winmax][8]
   const int2 *binfo;  // per block: first physical window row, window rows
@@ -122,19 +128,25 @@ static int host_base(double x, double x1, double h, int eqs, long long n_coef) {
 // (2 shared-memory wavefronts each): with one line per thread a row costs 2 + 8 wavefronts for 8 DFMAs and the pass is
 // bound by shared-memory bandwidth (measured: 124 k of 159 k cycles on the 256 x 256 x 128 -> 256^3 pass); two lines per
 // thread share the weights, 12 wavefronts for 16 DFMAs.
-template <int EQS, int BI, int RL>
+// MMA: the consumers contract a block on the FP64 tensor cores instead (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): rows of the
+// product = the block's 8 output knots, K = the window rows, columns = 8 lines; the dense block table IS the A operand
+// and a lane loads ONE double per operand and 8 FMAs, where the DFMA consumer needs a weight broadcast per FMA pair -
+// 60 shared-memory wavefronts per (block, 32 lines) instead of 220.  Tile rows get a pitch of 36 doubles (axis >= 1) /
+// lines a pitch = 4 mod 16 (axis 0) so that the four K rows x eight lines of a B fragment hit distinct banks.
+template <int EQS, int BI, int RL, bool MMA>
 __global__ void __maxnreg__(RL == 2 ? 128 : 96)
     resample_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ResamplePipeParams sp,
                          const __grid_constant__ GhostMats gm, double *__restrict__ out) {
   constexpr bool AXIS0 = BI == 0;
-  constexpr int ROW = AXIS0 ? 1 : BI;
   constexpr int BIX = BI > 0 ? BI : 32;
+  constexpr int ROW = AXIS0 ? 1 : (MMA ? RS_MMA_PITCH : BI);  // doubles between two rows of a tile
+  static_assert(!MMA || (RL == 1 && BI != 8), "tensor-core consumer: one tile per slot, 32 lines along inner or axis 0");
   constexpr int BO = AXIS0 ? 1 : 32 / BIX;
   constexpr int NS = EQS < 5 ? 4 : (EQS == 5 ? 6 : 8);
   constexpr int SPITCH = RS_R + 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NB = sp.nb, nblk = sp.nblk, n = sp.n_in;
-  const int TILE = 32 * sp.H;  // doubles
+  const int TILE = (AXIS0 ? 32 : (MMA ? RS_MMA_PITCH : 32)) * sp.H;  // doubles
   const int SLOT = RL * TILE;
   double *tiles = (double *)smem_raw;
   double *wd = tiles + (size_t)NB * SLOT;                       // [nblk][winmax][8]
@@ -149,7 +161,7 @@ __global__ void __maxnreg__(RL == 2 ? 128 : 96)
     for (int b = 0; b < NB; ++b) {
       mbar_init(loaded + b, 1);
       mbar_init(ready + b, 2);  // the two side warps of a ghost team
-      mbar_init(empty + b, (unsigned)nblk);
+      mbar_init(empty + b, (unsigned)sp.nitem);
     }
     *counter = 0;
     mbar_init_fence();
@@ -190,7 +202,7 @@ __global__ void __maxnreg__(RL == 2 ? 128 : 96)
             tma_load_2d(dst, &tmap, -sp.padx, (int)(t * 32), loaded + b);
           } else {
             const unsigned tile_o = div_u(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
-            tma_load_3d(dst, &tmap, (int)tile_i * ROW, -sp.padx, (int)tile_o * BO, loaded + b);
+            tma_load_3d(dst, &tmap, (int)tile_i * BIX, -sp.padx, (int)tile_o * BO, loaded + b);
           }
         }
         if (++b == (unsigned)NB) {
@@ -219,8 +231,8 @@ __global__ void __maxnreg__(RL == 2 ? 128 : 96)
             hd.vo = rem < 32 ? (int)rem : 32;
           } else {
             const unsigned tile_o = div_u(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
-            hd.obase = (long long)tile_i * ROW + sp.out_o_stride * ((long long)tile_o * BO);
-            const long long ri = sp.inner - (long long)tile_i * ROW, ro = sp.outer - (long long)tile_o * BO;
+            hd.obase = (long long)tile_i * BIX + sp.out_o_stride * ((long long)tile_o * BO);
+            const long long ri = sp.inner - (long long)tile_i * BIX, ro = sp.outer - (long long)tile_o * BO;
             hd.vi = ri < BIX ? (int)ri : BIX;
             hd.vo = ro < BO ? (int)ro : BO;
           }
@@ -248,15 +260,63 @@ __global__ void __maxnreg__(RL == 2 ? 128 : 96)
       unsigned item = 0;
       if (lane == 0) item = atomicAdd(counter, 1u);
       item = __shfl_sync(0xffffffffu, item, 0);
-      const unsigned seq = div_u(item, sp.magic_nblk);
+      const unsigned seq = div_u(item, sp.magic_nitem);
       if (seq >= my_slots) break;
-      const int blk = (int)(item - seq * (unsigned)nblk);
-      const int k0 = blk * RS_R;
       const unsigned rev = div_u(seq, sp.magic_nb), b = seq - rev * NB;
+      const int blk_first = (int)(item - seq * (unsigned)sp.nitem) * sp.bpi;
+      mbar_wait(ready + b, rev & 1u, 3000 + (int)seq);
+      if (MMA) {
+       const RsTileHdr hd = hdr[b * RL];
+       for (int blk = blk_first; blk < min(blk_first + sp.bpi, nblk); ++blk) {
+        const int k0 = blk * RS_R;
+        const int2 bw = binfo[blk];
+        if (bw.y < 0) __trap();  // a block window longer than the host's bound: never silently drop taps
+        // rows = the 8 knots of the block, K = window rows (4 per step), columns = 8 lines; 4 column groups per tile
+        const int mq = lane >> 2, mr = lane & 3;
+        const double *wblk = wd + (size_t)blk * sp.winmax * RS_R + mq;           // A[knot mq][row j] = wblk[j * 8]
+        const double *xb = tiles + (size_t)b * SLOT + (AXIS0 ? mq * sp.H + bw.x : bw.x * ROW + mq);  // B[row j][line mq]
+        constexpr int XJ = AXIS0 ? 1 : ROW;              // stride of a window row
+        const int XG = AXIS0 ? 8 * sp.H : 8;             // stride of a column group (8 lines)
+        double ac[4][2];
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) ac[cg][0] = ac[cg][1] = 0.0;
+#pragma unroll 2
+        for (int j0 = 0; j0 < bw.y; j0 += 4) {
+          const int j = j0 + mr;
+          const bool jv = j < bw.y;  // (rows past the window may lie outside the tile buffer: never read them)
+          const double a = jv ? wblk[j * RS_R] : 0.0;
+          double xv[4];
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) xv[cg] = jv ? xb[j * XJ + cg * XG] : 0.0;
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) mma_f64_884(ac[cg][0], ac[cg][1], a, xv[cg]);
+        }
+        if (k0 + mq < nout) {
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            const int line = 8 * cg + 2 * mr;
+            const double v0 = __dmul_rn(ac[cg][0], sp.scale), v1 = __dmul_rn(ac[cg][1], sp.scale);  // (-1/h)^derivative, :379
+            if (AXIS0) {
+              double *op = out + hd.obase + (long long)line * nout + k0 + mq;
+              if (line < hd.vo) op[0] = v0;
+              if (line + 1 < hd.vo) op[nout] = v1;
+            } else if (hd.vo > 0) {
+              double *op = out + hd.obase + (long long)(k0 + mq) * sp.inner + line;
+              if (line + 1 < hd.vi) *(double2 *)op = make_double2(v0, v1);  // inner is even: 16-byte aligned
+              else if (line < hd.vi) op[0] = v0;
+            }
+          }
+        }
+       }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + b);
+        continue;
+      }
+      const int blk = blk_first;  // (bpi = 1)
+      const int k0 = blk * RS_R;
       const int2 bw = binfo[blk];
       if (bw.y < 0) __trap();  // a block window longer than the host's bound: never silently drop taps
       const double2 *w = (const double2 *)(wd + (size_t)blk * sp.winmax * RS_R);
-      mbar_wait(ready + b, rev & 1u, 3000 + (int)seq);
       const double *p = tiles + (size_t)b * SLOT + lbase + bw.x * ROW;
       double acc[RL][RS_R];
 #pragma unroll
@@ -365,14 +425,14 @@ struct RsPass {
   CUtensorMap tmap;
   ResamplePipeParams sp;
   GhostMats gm;
-  int eqs, bi, rl, threads;
+  int eqs, bi, rl, threads, mma;
   size_t smem;
   double *out;
 };
 
-template <int EQS, int BI, int RL>
+template <int EQS, int BI, int RL, bool MMA = false>
 static int launch_rs(const RsPass &ps, cudaStream_t st) {
-  auto k = resample_pipe_kernel<EQS, BI, RL>;
+  auto k = resample_pipe_kernel<EQS, BI, RL, MMA>;
   {
     static std::atomic<unsigned long long> done{0};
     int dev = 0;
@@ -401,6 +461,7 @@ static int launch_rs(const RsPass &ps, cudaStream_t st) {
 
 template <int EQS>
 static int launch_rs_bi(const RsPass &ps, cudaStream_t st) {
+  if (ps.mma) return ps.bi == 0 ? launch_rs<EQS, 0, 1, true>(ps, st) : launch_rs<EQS, 32, 1, true>(ps, st);
   if (ps.rl == 2) {
     if (ps.bi == 0) return launch_rs<EQS, 0, 2>(ps, st);
     if (ps.bi == 8) return launch_rs<EQS, 8, 2>(ps, st);
@@ -435,6 +496,8 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
   if (n_coef + 2 > 250 || n_in < 2 || n_out < 1 || n_out > 4096) return false;
   if (((uintptr_t)in & 15) || !tma_encode_tiled_fn()) return false;
   const bool axis0 = inner == 1;
+  // tensor-core consumer (DMMA): axis 0 and passes with 32 lines along `inner`
+  const bool mma = !(tune_env("CIB200_RS_MMA") && tune_env("CIB200_RS_MMA")[0] == '0') && (axis0 || inner % 32 == 0 || !(inner % 8 == 0 && inner < 256));
   ResamplePipeParams &sp = ps.sp;
   sp.inner = inner;
   sp.outer = outer;
@@ -454,7 +517,11 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
     if (n_in & 1) return false;  // global line stride must be a multiple of 16 bytes
     sp.padx = pad + (pad & 1);   // the box origin (-padx elements) must be a multiple of 16 bytes
     int P = (int)n_coef + (sp.padx - pad) + 1;
-    while ((P & 3) != 2) ++P;  // P / 2 odd: conflict-free 16-byte reads with lane = line
+    if (mma) {
+      while ((P & 15) != 4) ++P;  // line pitch = 4 mod 16 doubles: the B fragments (4 rows x 8 lines) hit distinct banks
+    } else {
+      while ((P & 3) != 2) ++P;  // P / 2 odd: conflict-free 16-byte reads with lane = line
+    }
     if (P > 256 || outer >= (1LL << 31)) return false;
     sp.H = P;
     sp.ntiles = (outer + 31) / 32;
@@ -469,6 +536,7 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
     ps.bi = (inner % 32 == 0) ? 32 : ((inner % 8 == 0 && inner < 256) ? 8 : 32);
     int H = (int)n_coef + 1;  // + 1: a block window is rounded up to an even number of rows
     if (ps.bi < 32 && !(H & 1)) ++H;
+    if (mma && ps.bi == 32) H = (H + 3) & ~3;  // 36-double rows: a tile is a multiple of 128 bytes (TMA destination alignment)
     if (H > 256) return false;
     sp.H = H;
     sp.tiles_inner = (int)((inner + ps.bi - 1) / ps.bi);
@@ -476,7 +544,7 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
     sp.ntiles = (long long)sp.tiles_inner * ((outer + bo - 1) / bo);
     cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)n_in, (cuuint64_t)outer};
     cuuint64_t gstr[2] = {(cuuint64_t)inner * 8, (cuuint64_t)inner * (cuuint64_t)n_in * 8};
-    cuuint32_t box[3] = {(cuuint32_t)ps.bi, (cuuint32_t)H, (cuuint32_t)bo};
+    cuuint32_t box[3] = {(cuuint32_t)(mma ? RS_MMA_PITCH : ps.bi), (cuuint32_t)H, (cuuint32_t)bo};
     if (pipe::encode_f64(&ps.tmap, 3, in, gdim, gstr, box)) return false;
   }
   if (sp.ntiles * (long long)std::max(sp.nblk, 32) >= (1LL << 26)) return false;
@@ -501,7 +569,8 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
   // the 8 broadcast weight loads of a window row then feed 16 DFMAs) when two such slots fit and every SM gets at least
   // one of them (measured on BASELINE config 3: 0.144 ms against 0.161 ms with one line per thread everywhere); else one
   // line per thread and a deeper ring.
-  const size_t tile_bytes = (size_t)32 * sp.H * 8;
+  ps.mma = (mma && (axis0 || ps.bi == 32)) ? 1 : 0;
+  const size_t tile_bytes = (size_t)((ps.mma && !axis0) ? RS_MMA_PITCH : 32) * sp.H * 8;
   const size_t wd_bytes = (size_t)sp.nblk * winmax * RS_R * 8 + (size_t)((sp.nblk + 1) & ~1) * 8;
   const size_t budget = (size_t)rs_smem_budget();
   auto fixed_for = [&](int ncons) {
@@ -512,6 +581,7 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
   if (const char *e = tune_env("CIB200_RS_NTEAMS")) sp.nteams = std::max(1, std::min(3, atoi(e)));
   ps.rl = (fixed_for(11) + 4 * tile_bytes <= budget && sp.ntiles >= 2 * (long long)sm_count()) ? 2 : 1;
   if (const char *e = tune_env("CIB200_RS_RL")) ps.rl = (atoi(e) == 2 && fixed_for(11) + 4 * tile_bytes <= budget) ? 2 : 1;
+  if (ps.mma) ps.rl = 1;
   // 128 registers x 16 warps (two lines per thread) or 96 x 20 warps
   sp.ncons = (ps.rl == 2 ? 15 : 19) - 2 * sp.nteams;
   if (const char *e = tune_env("CIB200_RS_NCONS")) sp.ncons = std::max(1, std::min(sp.ncons, atoi(e)));
@@ -522,7 +592,11 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
   if (const char *e = tune_env("CIB200_RS_NB")) sp.nb = std::max(2, std::min(sp.nb, atoi(e)));
   ps.smem = fixed + (size_t)sp.nb * tile_bytes * ps.rl;
   auto magic = [](unsigned d) { return pipe::div_magic_for(d); };
+  sp.bpi = ps.mma ? 2 : 1;
+  if (const char *e = tune_env("CIB200_RS_BPI")) sp.bpi = ps.mma ? std::max(1, std::min(8, atoi(e))) : 1;
+  sp.nitem = (sp.nblk + sp.bpi - 1) / sp.bpi;
   sp.magic_nblk = magic((unsigned)sp.nblk);
+  sp.magic_nitem = magic((unsigned)sp.nitem);
   sp.magic_nb = magic((unsigned)sp.nb);
   sp.magic_ti = magic((unsigned)std::max(1, sp.tiles_inner));
   sp.magic_teams = magic((unsigned)sp.nteams);
