@@ -123,21 +123,32 @@ __device__ __forceinline__ void fit_both(const double *__restrict__ x0, int n, d
   Rr = make_double2(__dmul_rn(__dsub_rn(syr, __dmul_rn(br, sp.sx)), sp.inv_nf), br);
 }
 
+static constexpr int SM_MMA_PITCH = 36;  // doubles between two rows of a tile for the tensor-core consumer (axis >= 1)
+
+__device__ __forceinline__ void sm_mma_f64_884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // BI: lanes along `inner` in a tile of an axis >= 1 pass (32 or 8); BI = 0: axis 0.  R: outputs per work item.
-template <int TAPS, int BI, int R>
+// MMA: the FIR of a block runs on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): rows = the block's 8
+// outputs, K = the TAPS + 7 window rows, columns = 8 lines.  The A operand is the Toeplitz band of the taps - the same for
+// every block, so a lane keeps its (TAPS + 10) / 4 fragments in registers for the whole kernel - and the B fragments are
+// one conflict-free LDS.64 per DMMA (tile rows at a pitch of 36 doubles, axis 0: line pitch = 4 mod 16).
+template <int TAPS, int BI, int R, bool MMA>
 __global__ void __launch_bounds__(640, 1)
     smooth_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SmoothPipeParams sp,
                        double *__restrict__ out) {
   constexpr int E = (TAPS - 1) / 2;
   constexpr bool AXIS0 = BI == 0;
-  constexpr int ROW = AXIS0 ? 1 : BI;
   constexpr int BIX = BI > 0 ? BI : 32;
+  constexpr int ROW = AXIS0 ? 1 : (MMA ? SM_MMA_PITCH : BI);  // doubles between two rows of a tile
+  static_assert(!MMA || (R == 8 && BI != 8), "tensor-core consumer: blocks of 8 outputs, 32 lines along inner or axis 0");
   constexpr int BO = AXIS0 ? 1 : 32 / BIX;
   constexpr int W = TAPS + R - 1;
   constexpr int SPITCH = R + 1;  // transposing stage of axis 0
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NB = sp.nb, n = sp.n, nblk = sp.nblk;
-  const int TILE = 32 * sp.H;  // doubles
+  const int TILE = ((MMA && !AXIS0) ? SM_MMA_PITCH : 32) * sp.H;  // doubles
   double *tiles = (double *)smem_raw;
   double *lpar = tiles + (size_t)NB * TILE;  // [NB][32][4]: aL bL aR bR of every line of the tile
   double *stab = lpar + NB * 128;            // s0[32] s1[32]
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(640, 1)
           tma_load_2d(dst, &tmap, -E, (int)(t * 32), loaded + b);
         } else {
           const unsigned tile_o = div_u(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
-          tma_load_3d(dst, &tmap, (int)tile_i * ROW, -E, (int)tile_o * BO, loaded + b);
+          tma_load_3d(dst, &tmap, (int)tile_i * BIX, -E, (int)tile_o * BO, loaded + b);
         }
         if (++b == (unsigned)NB) {
           b = 0;
@@ -205,8 +216,8 @@ __global__ void __launch_bounds__(640, 1)
           h.vo = rem < 32 ? (int)rem : 32;
         } else {
           const unsigned tile_o = div_u(t, sp.magic_ti), tile_i = t - tile_o * sp.tiles_inner;
-          h.obase = (long long)tile_i * ROW + sp.line_o_stride * ((long long)tile_o * BO);
-          const long long ri = sp.inner - (long long)tile_i * ROW, ro = sp.outer - (long long)tile_o * BO;
+          h.obase = (long long)tile_i * BIX + sp.line_o_stride * ((long long)tile_o * BO);
+          const long long ri = sp.inner - (long long)tile_i * BIX, ro = sp.outer - (long long)tile_o * BO;
           h.vi = ri < BIX ? (int)ri : BIX;
           h.vo = ro < BO ? (int)ro : BO;
         }
@@ -230,6 +241,15 @@ __global__ void __launch_bounds__(640, 1)
     // per-lane output offset from the tile's base (axis >= 1) / transposed store roles (axis 0)
     const long long lane_off = AXIS0 ? 0 : (long long)li + sp.line_o_stride * lo;
     const int sr = lane % R, sl = lane / R;  // axis 0: this lane stores output sr of lines sl, sl + 32 / R, ...
+    // tensor-core consumer: this lane's fragments of the Toeplitz band, A[output mq][window row j] = kw[j - mq]
+    double afr[MMA ? (W + 3) / 4 : 1];
+    if (MMA) {
+#pragma unroll
+      for (int s = 0; s < (W + 3) / 4; ++s) {
+        const int l = 4 * s + (lane & 3) - (lane >> 2);
+        afr[s] = (l >= 0 && l < TAPS) ? sp.kw[l] : 0.0;
+      }
+    }
     for (;;) {
       unsigned item = 0;
       if (lane == 0) item = atomicAdd(counter, 1u);
@@ -243,6 +263,68 @@ __global__ void __launch_bounds__(640, 1)
       const int jhi = n + E - k0 < W ? n + E - k0 : W;
       const int clo = jlo >> 3, chi = (jhi + 7) >> 3;
       mbar_wait(ready + b, rev & 1u, 3000 + (int)seq);
+      if (MMA) {
+        constexpr int KS = (W + 3) / 4;
+        const int mq = lane >> 2, mr = lane & 3;
+        const double *xb = tiles + (size_t)b * TILE + (AXIS0 ? mq * sp.H + k0 + mr : (k0 + mr) * ROW + mq);  // B[row 4 s + mr][line mq]
+        constexpr int XS = AXIS0 ? 4 : 4 * ROW;      // stride of a K step (4 window rows)
+        const int XG = AXIS0 ? 8 * sp.H : 8;         // stride of a column group (8 lines)
+        const int slo = jlo >> 2, shi = (jhi + 3) >> 2;  // K steps outside [slo, shi) lie in the zero padding
+        double ac[4][2];
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) ac[cg][0] = ac[cg][1] = 0.0;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          if (s >= slo && s < shi) {  // warp-uniform
+            double xv[4];
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) xv[cg] = xb[s * XS + cg * XG];
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) sm_mma_f64_884(ac[cg][0], ac[cg][1], afr[s], xv[cg]);
+          }
+        }
+        const int ko = k0 + mq;  // this lane's output
+        if (ko < E - 1) {  // sees left ghosts
+          const double t0 = stab[ko], t1 = stab[32 + ko];
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            const double *lp = lpar + b * 128 + (8 * cg + 2 * mr) * 4;
+            const double2 a0 = *(const double2 *)lp, a1 = *(const double2 *)(lp + 4);
+            ac[cg][0] = fma(a0.y, t1, fma(a0.x, t0, ac[cg][0]));
+            ac[cg][1] = fma(a1.y, t1, fma(a1.x, t0, ac[cg][1]));
+          }
+        }
+        const int dr = n - 1 - ko;
+        if (dr >= 0 && dr < E - 1) {  // sees right ghosts
+          const double t0 = stab[dr], t1 = stab[32 + dr];
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            const double *lp = lpar + b * 128 + (8 * cg + 2 * mr) * 4 + 2;
+            const double2 a0 = *(const double2 *)lp, a1 = *(const double2 *)(lp + 4);
+            ac[cg][0] = fma(a0.y, t1, fma(a0.x, t0, ac[cg][0]));
+            ac[cg][1] = fma(a1.y, t1, fma(a1.x, t0, ac[cg][1]));
+          }
+        }
+        const TileHdr h = hdr[b];
+        if (ko < n) {
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            const int line = 8 * cg + 2 * mr;
+            if (AXIS0) {
+              double *op = out + h.obase + (long long)line * n + ko;
+              if (line < h.vo) op[0] = ac[cg][0];
+              if (line + 1 < h.vo) op[n] = ac[cg][1];
+            } else if (h.vo > 0) {
+              double *op = out + h.obase + (long long)ko * sp.inner + line;
+              if (line + 1 < h.vi) *(double2 *)op = make_double2(ac[cg][0], ac[cg][1]);  // inner is even: 16-byte aligned
+              else if (line < h.vi) op[0] = ac[cg][0];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + b);
+        continue;
+      }
       const double *p = tiles + (size_t)b * TILE + lbase + k0 * ROW;
       double acc[R];
 #pragma unroll
@@ -312,10 +394,10 @@ static int pipe_smem_budget() {
   return v;
 }
 
-template <int TAPS, int BI, int R>
+template <int TAPS, int BI, int R, bool MMA = false>
 static int launch_smooth_pass(const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads, size_t smem,
                               cudaStream_t st) {
-  auto k = smooth_pipe_kernel<TAPS, BI, R>;
+  auto k = smooth_pipe_kernel<TAPS, BI, R, MMA>;
   {
     // the attribute is per (function, device): set it once to the device's limit instead of before every launch
     static std::atomic<unsigned long long> done{0};
@@ -345,8 +427,10 @@ static int launch_smooth_pass(const CUtensorMap &tmap, const SmoothPipeParams &s
 }
 
 template <int TAPS>
-static int launch_smooth_bi(int bi, int R, const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads,
+static int launch_smooth_bi(int bi, int R, bool mma, const CUtensorMap &tmap, const SmoothPipeParams &sp, double *out, int threads,
                             size_t smem, cudaStream_t st) {
+  if (mma) return bi == 0 ? launch_smooth_pass<TAPS, 0, 8, true>(tmap, sp, out, threads, smem, st)
+                          : launch_smooth_pass<TAPS, 32, 8, true>(tmap, sp, out, threads, smem, st);
   (void)R;  // R = 16 was measured (64^4: 0.279 vs 0.272 ms, 40^4: 0.077 vs 0.069 ms) and is not instantiated
   if (bi == 0) return launch_smooth_pass<TAPS, 0, 8>(tmap, sp, out, threads, smem, st);
   if (bi == 8) return launch_smooth_pass<TAPS, 8, 8>(tmap, sp, out, threads, smem, st);
@@ -378,11 +462,20 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
   int bi = 0;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof tmap);
-  const int rows = sp.nblk * R + 2 * E;  // -E .. nblk R + E - 1: every window row a block can touch
+  const int rows = sp.nblk * R + 2 * E + 3;  // -E .. nblk R + E - 1: every window row a block can touch (+ the K-step padding)
+  // tensor-core consumer (DMMA): measured SLOWER than the DFMA consumer here (64^4: 0.320 against 0.259 ms, 40^4: 0.066
+  // against 0.061 ms) - the FIR pass is bound by the FP64 pipe itself, and the Toeplitz band pads 49 taps to 56 K rows
+  // while the DFMA loop touches real taps only - so it is off unless an experiments build asks for it (CIB200_SMOOTH_MMA=1)
+  bool mma = (tune_env("CIB200_SMOOTH_MMA") && tune_env("CIB200_SMOOTH_MMA")[0] == '1') &&
+             (axis0 || inner % 32 == 0 || !(inner % 8 == 0 && inner < 256));
   if (axis0) {
     if ((n & 1) || (E & 1)) return -1;  // line stride and box start (-E elements) must be multiples of 16 bytes
     int P = rows;
-    while ((P & 3) != 2) ++P;  // P / 2 odd: the 8 lanes of an LDS.128 wavefront fall into 8 distinct 16-byte banks
+    if (mma) {
+      while ((P & 15) != 4) ++P;  // line pitch = 4 mod 16 doubles: the B fragments (4 rows x 8 lines) hit distinct banks
+    } else {
+      while ((P & 3) != 2) ++P;  // P / 2 odd: the 8 lanes of an LDS.128 wavefront fall into 8 distinct 16-byte banks
+    }
     if (P > 256 || outer >= (1LL << 31)) return -1;
     sp.H = P;
     sp.ntiles = (outer + 31) / 32;
@@ -395,6 +488,8 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
     bi = (inner % 32 == 0) ? 32 : ((inner % 8 == 0 && inner < 256) ? 8 : 32);
     int H = rows;
     if (bi < 32 && !(H & 1)) ++H;  // odd: the 32 / BI outer slabs of a tile start in different banks
+    if (bi != 32) mma = false;
+    if (mma) H = (H + 3) & ~3;     // 36-double rows: a tile is a multiple of 128 bytes (TMA destination alignment)
     if (H > 256) return -1;
     sp.H = H;
     sp.tiles_inner = (int)((inner + bi - 1) / bi);
@@ -402,7 +497,7 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
     sp.ntiles = (long long)sp.tiles_inner * ((outer + bo - 1) / bo);
     cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)n, (cuuint64_t)outer};
     cuuint64_t gstr[2] = {(cuuint64_t)inner * 8, (cuuint64_t)inner * (cuuint64_t)n * 8};
-    cuuint32_t box[3] = {(cuuint32_t)bi, (cuuint32_t)H, (cuuint32_t)bo};
+    cuuint32_t box[3] = {(cuuint32_t)(mma ? SM_MMA_PITCH : bi), (cuuint32_t)H, (cuuint32_t)bo};
     if (pipe::encode_f64(&tmap, 3, in, gdim, gstr, box)) return -1;
   }
   if (sp.ntiles * (long long)std::max(sp.nblk, 32) >= (1LL << 26)) return -1;  // 32-bit tile / item counters with exact magic division
@@ -413,7 +508,7 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
   if (const char *e = tune_env("CIB200_SMOOTH_NCONS")) sp.ncons = std::max(1, std::min(17 - sp.nstats + 2, atoi(e)));
   const int threads = 32 * (1 + sp.nstats + sp.ncons);
   if (threads > 640) return -1;
-  const size_t tile_bytes = (size_t)32 * sp.H * 8;
+  const size_t tile_bytes = (size_t)((mma && !axis0) ? SM_MMA_PITCH : 32) * sp.H * 8;
   const size_t fixed = 64 * 8 + 8 * sizeof(TileHdr) + (axis0 ? (size_t)sp.ncons * 32 * (R + 1) * 8 : 0) + 8 * 3 * 8 + 16 +
                        1024 /* alignment slack */;
   const size_t per_slot = tile_bytes + 128 * 8;
@@ -449,11 +544,11 @@ int smooth_pipe_pass(const double *in, double *out, long long inner, long long n
   }
   const size_t smem = fixed + (size_t)sp.nb * per_slot;
   switch (taps) {
-    case 13: return launch_smooth_bi<13>(bi, R, tmap, sp, out, threads, smem, st);
-    case 17: return launch_smooth_bi<17>(bi, R, tmap, sp, out, threads, smem, st);
-    case 25: return launch_smooth_bi<25>(bi, R, tmap, sp, out, threads, smem, st);
-    case 35: return launch_smooth_bi<35>(bi, R, tmap, sp, out, threads, smem, st);
-    default: return launch_smooth_bi<49>(bi, R, tmap, sp, out, threads, smem, st);
+    case 13: return launch_smooth_bi<13>(bi, R, mma, tmap, sp, out, threads, smem, st);
+    case 17: return launch_smooth_bi<17>(bi, R, mma, tmap, sp, out, threads, smem, st);
+    case 25: return launch_smooth_bi<25>(bi, R, mma, tmap, sp, out, threads, smem, st);
+    case 35: return launch_smooth_bi<35>(bi, R, mma, tmap, sp, out, threads, smem, st);
+    default: return launch_smooth_bi<49>(bi, R, mma, tmap, sp, out, threads, smem, st);
   }
 }
 
