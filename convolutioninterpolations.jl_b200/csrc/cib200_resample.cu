@@ -28,6 +28,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "cib200_ghost.cuh"
@@ -603,6 +604,100 @@ static bool plan_pass(RsPass &ps, const double *in, double *out, long long inner
   return true;
 }
 
+// ---- cache of the per-pass block tables ---------------------------------------------------------------------------
+// The dense block tables of a pass depend on the output knots and the kernel only - not on the data - and building them
+// costs an upload of the knots and one small launch per axis (3 x 4 us of the 0.12 ms of BASELINE config 3).  A repeated
+// resample onto the same knots (the usual case: every time step, every field) finds them here.  Entries are keyed on every
+// input of resample_blocks_kernel (the table pointers are the library's own device copies of the shipped tables) and on
+// the knot values themselves; an event orders a first use on another stream after the build.
+struct BlockTabEntry {
+  int dev, n_out, eqs, linear, npre, shift, even, winmax;
+  long long n_coef;
+  double x1, h;
+  const double *tk, *td, *te;
+  std::vector<double> knots;
+  double *wd;
+  int2 *bi;
+  cudaEvent_t ready;
+  cudaStream_t stream;
+  unsigned long long stamp;
+};
+static std::mutex g_bt_mu;
+static std::vector<BlockTabEntry> g_bt;
+static unsigned long long g_bt_clock = 0;
+static constexpr size_t BT_MAX_ENTRIES = 48;
+
+// returns 0 and the device tables, or -1 (the caller builds them into stream-ordered scratch as before)
+static int block_tables_cached(const double *knots_out, int n_out, double x1, double h, int eqs, long long n_coef, const double *tk,
+                               const double *td, const double *te, int linear, int npre, int shift, int even, int winmax,
+                               cudaStream_t st, const double **wd_out, const int2 **bi_out) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) return -1;
+  const bool capturing = cap != cudaStreamCaptureStatusNone;  // a hit is fine under capture; a miss would need cudaMalloc
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> guard(g_bt_mu);
+  for (BlockTabEntry &e : g_bt) {
+    if (e.dev == dev && e.n_out == n_out && e.eqs == eqs && e.linear == linear && e.npre == npre && e.shift == shift &&
+        e.even == even && e.winmax == winmax && e.n_coef == n_coef && e.x1 == x1 && e.h == h && e.tk == tk && e.td == td &&
+        e.te == te && memcmp(e.knots.data(), knots_out, sizeof(double) * (size_t)n_out) == 0) {
+      e.stamp = ++g_bt_clock;
+      if (st != e.stream && cudaEventQuery(e.ready) != cudaSuccess) {  // built on another stream and not finished yet
+        if (capturing || cudaStreamWaitEvent(st, e.ready, 0) != cudaSuccess) return -1;
+      }
+      *wd_out = e.wd;
+      *bi_out = e.bi;
+      return 0;
+    }
+  }
+  if (capturing) return -1;
+  if (g_bt.size() >= BT_MAX_ENTRIES) {  // evict the least recently used entry
+    size_t lru = 0;
+    for (size_t i = 1; i < g_bt.size(); ++i)
+      if (g_bt[i].stamp < g_bt[lru].stamp) lru = i;
+    cudaEventSynchronize(g_bt[lru].ready);
+    cudaDeviceSynchronize();  // (rare) nothing in flight may still read the tables
+    cudaFree(g_bt[lru].wd);
+    cudaFree(g_bt[lru].bi);
+    cudaEventDestroy(g_bt[lru].ready);
+    g_bt.erase(g_bt.begin() + (long)lru);
+  }
+  BlockTabEntry e;
+  e.dev = dev; e.n_out = n_out; e.eqs = eqs; e.linear = linear; e.npre = npre; e.shift = shift; e.even = even; e.winmax = winmax;
+  e.n_coef = n_coef; e.x1 = x1; e.h = h; e.tk = tk; e.td = td; e.te = te;
+  e.knots.assign(knots_out, knots_out + n_out);
+  e.wd = nullptr; e.bi = nullptr; e.stream = st; e.stamp = ++g_bt_clock;
+  const int nblk = (n_out + RS_R - 1) / RS_R;
+  double *d_ko = nullptr;
+  if (cudaMalloc((void **)&e.wd, sizeof(double) * (size_t)nblk * winmax * RS_R) != cudaSuccess ||
+      cudaMalloc((void **)&e.bi, sizeof(int2) * (size_t)nblk) != cudaSuccess ||
+      cudaMallocAsync((void **)&d_ko, sizeof(double) * (size_t)n_out, st) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    if (e.wd) cudaFree(e.wd);
+    if (e.bi) cudaFree(e.bi);
+    if (d_ko) cudaFreeAsync(d_ko, st);
+    return -1;
+  }
+  // (e.knots is the library's own copy: the asynchronous upload may outlive the caller's array)
+  if (cudaMemcpyAsync(d_ko, e.knots.data(), sizeof(double) * (size_t)n_out, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    cudaFree(e.wd);
+    cudaFree(e.bi);
+    cudaFreeAsync(d_ko, st);
+    cudaEventDestroy(e.ready);
+    return -1;
+  }
+  resample_blocks_kernel<<<nblk, 256, 0, st>>>(d_ko, n_out, x1, h, eqs, n_coef, tk, td, te, linear, npre, shift, even, winmax, e.wd, e.bi);
+  CIB_LAUNCHED();
+  cudaEventRecord(e.ready, st);
+  cudaFreeAsync(d_ko, st);
+  *wd_out = e.wd;
+  *bi_out = e.bi;
+  g_bt.push_back(std::move(e));
+  // the vector may have reallocated: the upload reads the moved-from buffer's storage, which std::vector's move keeps alive
+  return 0;
+}
+
 // The whole call: -1 when any axis does not qualify (the caller then runs the generic path for the whole call).
 // tk / td / te[d]: device tables K^(d), K^(d+1) (K again for a linear axis), K^(d+2) (quintic axes, else nullptr).
 int resample_pipe_all(int ndim, const long long *n_in, const long long *n_out, const double *d_in, double *d_out,
@@ -657,6 +752,19 @@ int resample_pipe_all(int ndim, const long long *n_in, const long long *n_out, c
   for (int d = 0; d < ndim; ++d) {
     RsPass &ps = passes[(size_t)d];
     ResamplePipeParams &sp = ps.sp;
+    const double h = sp.h;
+    const double x1 = knots_in[d][0] - (double)(ps.eqs - 1) * h;
+    {
+      const double *c_wd = nullptr;
+      const int2 *c_bi = nullptr;
+      if (!tune_env("CIB200_RS_NO_TABLE_CACHE") &&
+          block_tables_cached(knots_out[d], sp.n_out, x1, h, ps.eqs, (long long)sp.n_in + 2 * sp.pad, tk[d], td[d], te[d], linear[d],
+                              npre[d], sp.padx - sp.pad, ps.bi == 0 ? 1 : 0, sp.winmax, st, &c_wd, &c_bi) == 0) {
+        sp.Wd = c_wd;
+        sp.binfo = c_bi;
+        continue;
+      }
+    }
     double *d_ko = nullptr, *d_wd = nullptr;
     int2 *d_bi = nullptr;
     if (!dalloc((void **)&d_ko, sizeof(double) * (size_t)sp.n_out) ||
@@ -670,8 +778,6 @@ int resample_pipe_all(int ndim, const long long *n_in, const long long *n_out, c
       set_error("resample: knot upload failed");
       return CIB200_ECUDA;
     }
-    const double h = sp.h;
-    const double x1 = knots_in[d][0] - (double)(ps.eqs - 1) * h;
     resample_blocks_kernel<<<sp.nblk, 256, 0, st>>>(d_ko, sp.n_out, x1, h, ps.eqs, (long long)sp.n_in + 2 * sp.pad, tk[d], td[d],
                                                     te[d], linear[d], npre[d], sp.padx - sp.pad, ps.bi == 0 ? 1 : 0, sp.winmax, d_wd, d_bi);
     CIB_LAUNCHED();

@@ -32,9 +32,9 @@ def best(reps=30):
     return ts[0], ts[len(ts) // 2]
 
 
-for env in ({"CIB200_RS_MMA": "0"}, {"CIB200_RS_BPI": "1"}, {}, {"CIB200_RS_BPI": "4"}, {"CIB200_RS_BPI": "4", "CIB200_RS_NTEAMS": "3"},
-            {"CIB200_RS_BPI": "4", "CIB200_RS_NTEAMS": "1"}, {"CIB200_RS_BPI": "4", "CIB200_RS_NCONS": "11"}):
-    for k in ("CIB200_RS_MMA", "CIB200_RS_NTEAMS", "CIB200_RS_NB", "CIB200_RS_NCONS", "CIB200_NO_PDL", "CIB200_RS_BPI"):
+for env in ({"CIB200_RS_MMA": "0", "CIB200_RS_NO_TABLE_CACHE": "1"}, {"CIB200_RS_NO_TABLE_CACHE": "1"}, {}, {"CIB200_RS_NO_TABLE_CACHE": "1"}, {},
+            {"CIB200_NO_PDL": "1"}, {"CIB200_RS_NCONS": "11"}):
+    for k in ("CIB200_RS_MMA", "CIB200_RS_NTEAMS", "CIB200_RS_NB", "CIB200_RS_NCONS", "CIB200_NO_PDL", "CIB200_RS_BPI", "CIB200_RS_NO_TABLE_CACHE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     b, m = best()
