@@ -197,7 +197,7 @@ def secondary_sweeps(peak):
     import torch
     import convitp_b200 as ci
 
-    def best_ms(fn, reps=10):
+    def best_ms(fn, reps=30):
         for _ in range(3 if reps >= 10 else 1):
             fn()
         torch.cuda.synchronize()

@@ -30,7 +30,7 @@ def julia_order(a):
     return t.permute(*reversed(range(t.dim())))
 
 
-def timeit(fn, warmup=3, iters=10):
+def timeit(fn, warmup=3, iters=30):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
