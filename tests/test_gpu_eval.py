@@ -592,6 +592,21 @@ def test_tensor_core_strategy_against_the_oracle(ci, oracle, kw, strategy):
     assert np.array_equal(gb.eval(*tq).cpu().numpy(), rb)
 
 
+def test_last_strategy_reports_the_kernel_of_the_last_call(ci):
+    """cib200_itp_last_strategy: AUTO on a 128^3 :b5 grid takes the gather kernel for a small batch, the binned kernel for
+    a sparse large one, the cell-run kernel from 0.5 query per cell and the tensor-core kernel from 2.5."""
+    import torch
+    rng = np.random.default_rng(12)
+    n = 128
+    k = tuple(np.linspace(0, 1, n) for _ in range(3))
+    itp = ci.convolution_interpolation(k, _field((n, n, n), rng), bc="poly")
+    ncell = (n - 1) ** 3
+    for nq, want in ((10_000, "gather"), (int(0.2 * ncell), "binned"), (int(1.0 * ncell), "cellrun"), (int(3.0 * ncell), "cellmma")):
+        q = [torch.rand(nq, dtype=torch.float64, device="cuda") for _ in range(3)]
+        itp.eval(*q)
+        assert itp.itp.last_strategy() == want, (nq, want, itp.itp.last_strategy())
+
+
 def test_binned_device_resident_and_auto_mode(ci):
     import torch
     rng = np.random.default_rng(32)

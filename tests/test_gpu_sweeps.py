@@ -191,3 +191,32 @@ def test_output_slab_decomposition_is_bit_identical(ci):
         ks, _ = ci.sharding.output_slab(kout, 4, r)
         parts.append(ci.convolution_resample(kin, ks, v, kernel="b13", derivative=(1, 0, 0)))
     assert np.array_equal(np.concatenate(parts, axis=2), full)
+
+
+def test_resample_block_table_cache_and_tensor_core_consumer_shapes(ci, oracle):
+    """The dense block tables of a pass are cached across calls, keyed on the output knots and the kernel
+    (cib200_resample.cu, block_tables_cached): a repeated call returns the same bits, a call onto other knots (same
+    lengths, shifted values) must not see the first call's tables, and more distinct knot sets than the cache holds
+    (48 entries, LRU eviction) still match the oracle.  Shapes: tiles with fewer than 32 valid lines, output lengths that
+    are not a multiple of the 8-knot blocks, a window bound that changes with the knots (tensor-core consumer, K steps)."""
+    rng = np.random.default_rng(91)
+    kin = (np.linspace(0.0, 1.0, 37), np.linspace(-1.0, 2.0, 50), np.linspace(0.0, 3.0, 44))
+    v = _sin_field((37, 50, 44), rng, 0.02)
+    kout = (np.linspace(0.0, 1.0, 61), np.linspace(-1.0, 2.0, 83), np.linspace(0.0, 3.0, 70))
+    a, _ = _check_resample(ci, oracle, kin, kout, v, kernel="b5")
+    b = ci.convolution_resample(kin, kout, v, kernel="b5")
+    assert np.array_equal(a, b)
+    kout2 = (np.linspace(0.02, 0.97, 61), np.linspace(-0.9, 1.8, 83), np.linspace(0.1, 2.9, 70))
+    c, _ = _check_resample(ci, oracle, kin, kout2, v, kernel="b5")
+    assert not np.array_equal(a, c)
+    _check_resample(ci, oracle, kin, kout, v, kernel="b5", derivative=(0, 1, 0))  # another table pair, same knots
+    x = np.linspace(0.0, 1.0, 40)
+    v2 = _sin_field((40, 36), rng, 0.02)
+    for i in range(60):  # more knot sets than cache entries
+        ko = (np.linspace(0.001 * i, 1.0 - 0.0007 * i, 57 + (i % 3)), np.linspace(0.0, 1.0, 36)[: 36] * 1.0)
+        got = ci.convolution_resample((x, np.linspace(0.0, 1.0, 36)), ko, v2, kernel="b7")
+        if i % 10 == 0 or i == 59:
+            ref = oracle.convolution_resample((x, np.linspace(0.0, 1.0, 36)), ko, v2, kernel="b7")
+            assert rel_err(got, ref, np.abs(v2).max()).max() <= TOL64
+    again = ci.convolution_resample(kin, kout, v, kernel="b5")  # evicted in between: rebuilt, same bits
+    assert np.array_equal(a, again)
