@@ -586,7 +586,8 @@ struct CellrunWarpSmem {
   static constexpr int DOUBLES = HB + MISC + WQ;
 };
 
-template <int E, typename TC>
+// POSREC: the records carry positions (bin_scatter_kernel<double, true>): fractions and table rows instead of coordinates
+template <int E, typename TC, bool POSREC>
 __global__ void __launch_bounds__(384, 1)
     eval_cellrun_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
                         const Record *__restrict__ rec, const WorkItem *__restrict__ items,
@@ -684,7 +685,28 @@ __global__ void __launch_bounds__(384, 1)
       const double2 ra = ra_n, rb = rb_n;
       if (b0 + 32 + lane < w1) ld_record(rec + it.start + b0 + 32 + lane, ra_n, rb_n);
       __syncwarp();  // the previous batch is done with hbs / misc
-      if (have) {
+      if (have && POSREC) {
+        const double t[3] = {ra.x, ra.y, rb.x};
+        idx = (unsigned)__double2loint(rb.y);
+        const unsigned code = (unsigned)__double2hiint(rb.y);
+        const unsigned lc = code & 4095u, rcode = code >> 12;
+        const unsigned rz = rcode / 10000u, ry = (rcode - rz * 10000u) / 100u, rx = rcode - rz * 10000u - ry * 100u;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const Hermite hb = p.subgrid[d] == CIB200_SG_LINEAR ? linear_basis(t[d]) : hermite_basis(t[d]);
+          double2 *dst = (double2 *)(hbs + (lane * 3 + d) * 4);
+          dst[0] = make_double2(hb.h00, hb.h01);
+          dst[1] = make_double2(hb.h10, hb.h11);
+        }
+        const unsigned T = (unsigned)g.T, cz = lc / (T * T), cy = (lc - cz * T * T) / T, cx = lc - cz * T * T - cy * T;
+        int4 m;
+        m.x = (int)cx + (int)cy * PITCH + (int)cz * PLANE;
+        m.y = (int)rx * W;
+        m.z = (int)ry * W;
+        m.w = (int)rz * W;
+        ((int4 *)misc)[lane] = m;
+      }
+      if (have && !POSREC) {
         const double x[3] = {ra.x, ra.y, rb.x};
         idx = (unsigned)__double2loint(rb.y);
         AxisPos pa[3];
@@ -965,7 +987,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
     bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
-    auto kern = eval_cellrun_kernel<E, TC>;
+    auto kern = eval_cellrun_kernel<E, TC, sizeof(TC) == 8>;  // Float64: position records (launch_eval_binned picks the matching scatter)
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec2, bs->items, bs->n_items, out,
                                                           use_tma);
@@ -1109,8 +1131,9 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   const size_t hsm = global_hist ? 0 : 4 * (size_t)g.nbin;
   if (global_hist) CIB_CUDA(cudaMemsetAsync(bs->hist, 0, 4 * (size_t)g.nbin, st));
   auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
-  // (the tensor-core kernel reads position records: table rows and fractions computed once, in the scatter pass)
-  auto kscatter = f32 ? bin_scatter_kernel<float, false> : (lq == 3 ? bin_scatter_kernel<double, true> : bin_scatter_kernel<double, false>);
+  // (the tensor-core and the cell-run kernel read position records: table rows and fractions computed once, in the scatter pass)
+  auto kscatter = f32 ? bin_scatter_kernel<float, false>
+                      : ((lq == 3 || (cellsort && lq == 0)) ? bin_scatter_kernel<double, true> : bin_scatter_kernel<double, false>);
   CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   CIB_CUDA(cudaFuncSetAttribute(kscatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   prof_mark(h, 0, st);
