@@ -963,7 +963,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
     prof_mark(h, 2, st);
     int rc;
     if constexpr (sizeof(TC) == 8) rc = lq == 3 ? launch_eval_cellmma(h, bs, sc, out, st) : launch_eval_lanequery(h, bs, sc, out, lq, st);
-    else rc = CIB200_EUNSUPPORTED;
+    else rc = lq == 3 ? launch_eval_cellmma(h, bs, sc, out, st) : CIB200_EUNSUPPORTED;
     if (rc != CIB200_OK) return rc;
   }
   using WS = BinnedWarpSmem<E>;
@@ -987,7 +987,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
     bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
-    auto kern = eval_cellrun_kernel<E, TC, sizeof(TC) == 8>;  // Float64: position records (launch_eval_binned picks the matching scatter)
+    auto kern = eval_cellrun_kernel<E, TC, true>;  // position records (launch_eval_binned picks the matching scatter)
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(nwarps)));
     kern<<<bs->nblk, nwarps * 32, smem_for(nwarps), st>>>(bs->tmap, p, bs->g, sc, bs->rec2, bs->items, bs->n_items, out,
                                                           use_tma);
@@ -1110,10 +1110,10 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   int lq = 0;
   {
     // tensor-core kernel: any :b-series width (tile side 26 - 2E is even: aligned cell pairs), every table staged
-    bool mma_ok = !f32 && bs->tmap28_valid && g.T % 2 == 0 && g.T * g.T * g.T <= CELLS_MAX && p.eqs[0] >= 5;
+    bool mma_ok = (f32 || bs->tmap28_valid) && g.T % 2 == 0 && g.T * g.T * g.T <= CELLS_MAX && p.eqs[0] >= 5;
     for (int d = 0; d < 3; ++d)
       if (p.npre[d] != CIB_N_PRE) mma_ok = false;
-    const int kind = mma_ok ? cellmma_kind(p) : 0;
+    const int kind = mma_ok ? cellmma_kind(p, f32) : 0;
     // against eval_cellrun_kernel (:b5) the crossover is 2.5 queries per cell; wider kernels only have eval_binned_kernel
     // as the alternative (:b13 on 512^3, 2.5 10^8 queries = 1.9 per cell: 678 ms against 262 ms)
     const double dens = p.eqs[0] == 5 ? 2.5 : 1.0;
@@ -1122,6 +1122,7 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
       lq = atoi(e);
       if (lq == 3 && !kind) lq = 0;
       if ((lq == 1 || lq == 2) && !(cellsort && !f32)) lq = 0;
+      if (f32 && lq != 3) lq = 0;
     }
   }
   if ((lq == 1 || lq == 2) && !(nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024)) lq = 0;
@@ -1132,8 +1133,9 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   if (global_hist) CIB_CUDA(cudaMemsetAsync(bs->hist, 0, 4 * (size_t)g.nbin, st));
   auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
   // (the tensor-core and the cell-run kernel read position records: table rows and fractions computed once, in the scatter pass)
-  auto kscatter = f32 ? bin_scatter_kernel<float, false>
-                      : ((lq == 3 || (cellsort && lq == 0)) ? bin_scatter_kernel<double, true> : bin_scatter_kernel<double, false>);
+  const bool posrec = lq == 3 || (cellsort && lq == 0);
+  auto kscatter = f32 ? (posrec ? bin_scatter_kernel<float, true> : bin_scatter_kernel<float, false>)
+                      : (posrec ? bin_scatter_kernel<double, true> : bin_scatter_kernel<double, false>);
   CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   CIB_CUDA(cudaFuncSetAttribute(kscatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
   prof_mark(h, 0, st);
@@ -1152,21 +1154,21 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   prof_mark(h, 1, st);
   switch (p.eqs[0]) {
     // a-series (:a3 eqs 2, :a4 / :a5 eqs 3, :a7 eqs 4): the same binned kernel on 4^3 .. 8^3 stencils
-    case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 2: return f32 ? launch_pass_cd<2, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<2, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 3: return f32 ? launch_pass_cd<3, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 3: return f32 ? launch_pass_cd<3, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<3, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 4: return f32 ? launch_pass_cd<4, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 4: return f32 ? launch_pass_cd<4, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<4, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 5: return f32 ? launch_pass_cd<5, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 5: return f32 ? launch_pass_cd<5, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<5, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 6: return f32 ? launch_pass_cd<6, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 6: return f32 ? launch_pass_cd<6, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<6, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 7: return f32 ? launch_pass_cd<7, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 7: return f32 ? launch_pass_cd<7, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<7, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 8: return f32 ? launch_pass_cd<8, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 8: return f32 ? launch_pass_cd<8, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<8, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
-    case 9: return f32 ? launch_pass_cd<9, float>(h, bs, sc, (float *)out, c.qoff, cellsort, 0, st)
+    case 9: return f32 ? launch_pass_cd<9, float>(h, bs, sc, (float *)out, c.qoff, cellsort, lq, st)
                    : launch_pass_cd<9, double>(h, bs, sc, (double *)out, c.qoff, cellsort, lq, st);
   }
   set_error("binned strategy: unsupported kernel");

@@ -80,7 +80,7 @@ size_t lanequery_smem_bytes(const ItpParams &p, bool f32);
 int launch_eval_lanequery(cib200_itp *h, BinState *bs, const Scale &sc, void *out, int qpl, cudaStream_t st);
 // tensor-core evaluation kernel (cib200_cellmma.cu): records sorted by (tile, cell) + the group list of bin_cellsort_kernel<2>
 size_t cellmma_smem_bytes(const ItpParams &p);
-int cellmma_kind(const ItpParams &p);  // 0: not supported, 1: tuned :b5 kernel, 2: generic kernel (any :b width, several table pairs)
+int cellmma_kind(const ItpParams &p, bool f32 = false);  // 0: not supported, 1: tuned :b5 kernel, 2: generic kernel (any :b width, several table pairs)
 int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st);
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

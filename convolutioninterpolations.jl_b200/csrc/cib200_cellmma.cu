@@ -96,21 +96,24 @@ __device__ __forceinline__ void stage_poly_tables(const ItpParams &p, double *pt
   }
 }
 
-template <int NT, bool BREG>
+// TC = float: the opt-in Float32 mode - the brick is staged as floats (same 28-element rows: the B-fragment loads stay
+// conflict-free) and converted when a fragment is loaded; positions, weights and accumulation are Float64 as everywhere
+template <int NT, bool BREG, typename TC>
 __global__ void __launch_bounds__(NT, 1)
     eval_cellmma_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
                         const Record *__restrict__ rec, const uint2 *__restrict__ groups,
                         const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
-                        const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, double *__restrict__ out) {
+                        const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, TC *__restrict__ out) {
   using WS = MmaWarpSmem;
+  constexpr int BRICKD = MELEMS * (int)sizeof(TC) / 8;  // doubles the brick occupies
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *smd = (double *)smem_raw;
-  double *brick = smd;  // [BRICK_SIDE][BRICK_SIDE][MP], axis 0 contiguous
-  double *ptab = smd + MELEMS;
+  TC *brick = (TC *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][MP], axis 0 contiguous
+  double *ptab = smd + BRICKD;
   stage_poly_tables(p, ptab, NT);
   constexpr int nwarps = NT >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wbase = MELEMS + mma_ptab_count(p) * PTAB_DOUBLES;
+  const int wbase = BRICKD + mma_ptab_count(p) * PTAB_DOUBLES;
   double *wsm = smd + wbase + warp * WS::DOUBLES;
   double *tq = wsm;                      // [32][3]
   int4 *misc = (int4 *)(wsm + WS::TQ);   // [32]
@@ -127,9 +130,9 @@ __global__ void __launch_bounds__(NT, 1)
   const int wquarter = lane >> 3;
   const bool wrole = (lane & 7) < 5;
   const int wpp = wrole ? (lane & 7) : 4;
-  const int wtab0 = MELEMS + mma_ptab_index(p, 0) * PTAB_DOUBLES + 2 * wpp;  // from smd
-  const int wtab1 = MELEMS + mma_ptab_index(p, 1) * PTAB_DOUBLES + 2 * wpp;
-  const int wtab2 = MELEMS + mma_ptab_index(p, 2) * PTAB_DOUBLES + 2 * wpp;
+  const int wtab0 = BRICKD + mma_ptab_index(p, 0) * PTAB_DOUBLES + 2 * wpp;  // from smd
+  const int wtab1 = BRICKD + mma_ptab_index(p, 1) * PTAB_DOUBLES + 2 * wpp;
+  const int wtab2 = BRICKD + mma_ptab_index(p, 2) * PTAB_DOUBLES + 2 * wpp;
   // MMA roles: A row / accumulator row q, K index / column pair r
   const int mq = lane >> 2, mr = lane & 3;
   // B-fragment offsets of this lane inside the window: tiles 0..9 and tiles 10..12
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(NT, 1)
     const int org[3] = {tx * g.T, ty * g.T, tz * g.T};
     if (threadIdx.x == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, MELEMS * 8);
+      mbar_expect_tx(bar, MELEMS * (int)sizeof(TC));
       tma_load_3d(brick, &tmap, org[0], org[1], org[2], bar);
     }
     mbar_wait(bar, parity);
@@ -236,19 +239,19 @@ __global__ void __launch_bounds__(NT, 1)
         const int win = (mf >> 1) - (mf & 1);  // brick offset of the pair's first cell
         if (BREG && win != curwin) {  // warp-uniform: a new cell pair - fetch its B fragments
           curwin = win;
-          const double *bb = brick + win + boff, *bc = brick + win + boff2;
+          const TC *bb = brick + win + boff, *bc = brick + win + boff2;
 #pragma unroll
           for (int t = 0; t < 10; ++t) {
-            breg[t * 3 + 0] = bb[t * MPL];
-            breg[t * 3 + 1] = bb[t * MPL + 4];
-            breg[t * 3 + 2] = bk3 ? 0.0 : bb[t * MPL + 8];
+            breg[t * 3 + 0] = (double)bb[t * MPL];
+            breg[t * 3 + 1] = (double)bb[t * MPL + 4];
+            breg[t * 3 + 2] = bk3 ? 0.0 : (double)bb[t * MPL + 8];
           }
 #pragma unroll
           for (int u = 0; u < 3; ++u) {
             const bool z = u == 2 && bt12;
-            breg[(10 + u) * 3 + 0] = z ? 0.0 : bc[4 * u * MPL];
-            breg[(10 + u) * 3 + 1] = z ? 0.0 : bc[4 * u * MPL + 4];
-            breg[(10 + u) * 3 + 2] = (z || bk3) ? 0.0 : bc[4 * u * MPL + 8];
+            breg[(10 + u) * 3 + 0] = z ? 0.0 : (double)bc[4 * u * MPL];
+            breg[(10 + u) * 3 + 1] = z ? 0.0 : (double)bc[4 * u * MPL + 4];
+            breg[(10 + u) * 3 + 2] = (z || bk3) ? 0.0 : (double)bc[4 * u * MPL + 8];
           }
         }
         const bool qv = mq < cntg;
@@ -269,14 +272,14 @@ __global__ void __launch_bounds__(NT, 1)
 #pragma unroll
             for (int t = 0; t < 13; ++t) dmma884(acc[t][0], acc[t][1], a[s], breg[t * 3 + s]);
         } else {  // B fragments straight from the brick, one LDS.64 per DMMA
-          const double *bb = brick + win + boff, *bc = brick + win + boff2;
+          const TC *bb = brick + win + boff, *bc = brick + win + boff2;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
 #pragma unroll
-            for (int t = 0; t < 10; ++t) dmma884(acc[t][0], acc[t][1], a[s], (s == 2 && bk3) ? 0.0 : bb[t * MPL + 4 * s]);
+            for (int t = 0; t < 10; ++t) dmma884(acc[t][0], acc[t][1], a[s], (s == 2 && bk3) ? 0.0 : (double)bb[t * MPL + 4 * s]);
 #pragma unroll
             for (int u = 0; u < 3; ++u)
-              dmma884(acc[10 + u][0], acc[10 + u][1], a[s], ((u == 2 && bt12) || (s == 2 && bk3)) ? 0.0 : bc[4 * u * MPL + 4 * s]);
+              dmma884(acc[10 + u][0], acc[10 + u][1], a[s], ((u == 2 && bt12) || (s == 2 && bk3)) ? 0.0 : (double)bc[4 * u * MPL + 4 * s]);
           }
         }
         // ---- epilogue: the other two contractions on the accumulator fragments, quad reduction -----------------------
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(NT, 1)
         double e = fma(s0, wy01.x, s1 * wy01.y) + v * wy89;
         e += __shfl_xor_sync(0xffffffffu, e, 1);
         e += __shfl_xor_sync(0xffffffffu, e, 2);
-        if (qv && mr == 0) out[(unsigned)mi.z] = apply_scale<3>(e, sc);
+        if (qv && mr == 0) out[(unsigned)mi.z] = (TC)apply_scale<3>(e, sc);
         __syncwarp();  // wq is rewritten by the next group
       }
     }
@@ -594,14 +597,15 @@ static int launch_mma_gen_e(cib200_itp *h, BinState *bs, const Scale &sc, double
   return CIB200_EUNSUPPORTED;
 }
 
-static size_t mma_smem(const ItpParams &p, int nwarps) {
-  return 8 * ((size_t)MELEMS + (size_t)mma_ptab_count(p) * PTAB_DOUBLES + (size_t)nwarps * MmaWarpSmem::DOUBLES + 2 + 96);
+static size_t mma_smem(const ItpParams &p, int nwarps, size_t esize = 8) {
+  return esize * (size_t)MELEMS + 8 * ((size_t)mma_ptab_count(p) * PTAB_DOUBLES + (size_t)nwarps * MmaWarpSmem::DOUBLES + 2 + 96);
 }
 size_t cellmma_smem_bytes(const ItpParams &p) { return mma_smem(p, 16); }
 
 // 1: the tuned :b5 kernel (one table pair, cubic tables); 2: the generic kernel; 0: this interpolant does not fit
-int cellmma_kind(const ItpParams &p) {
+int cellmma_kind(const ItpParams &p, bool f32) {
   const int E = p.eqs[0];
+  if (f32) return (E == 5 && mma_ptab_count(p) == 1) ? 1 : 0;  // Float32: the tuned :b5 kernel only
   if (E == 5 && mma_ptab_count(p) == 1 && mma_smem(p, 16) <= 227 * 1024) return 1;
   switch (E) {
     case 5: return mma_gen_threads<5>(p) ? 2 : 0;
@@ -613,24 +617,26 @@ int cellmma_kind(const ItpParams &p) {
   return 0;
 }
 
-template <int NT, bool BREG>
-static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
+template <int NT, bool BREG, typename TC = double>
+static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cudaStream_t st) {
   const ItpParams &p = h->p;
-  const size_t smem = mma_smem(p, NT / 32);
-  auto kern = eval_cellmma_kernel<NT, BREG>;
+  const size_t smem = mma_smem(p, NT / 32, sizeof(TC));
+  auto kern = eval_cellmma_kernel<NT, BREG, TC>;
   static bool attr_set = false;
   if (!attr_set) {
     CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  kern<<<bs->nblk, NT, smem, st>>>(bs->tmap28, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots, bs->tile_start, bs->tile_nslots,
-                                   bs->items, bs->n_items, out);
+  // (Float32: the handle's own tensor map already stages rows of 28 floats)
+  kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots,
+                                   bs->tile_start, bs->tile_nslots, bs->items, bs->n_items, out);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   return CIB200_OK;
 }
 
 int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st) {
+  if (h->dtype == CIB200_F32) return launch_mma<512, false, float>(h, bs, sc, (float *)out, st);
   if (cellmma_kind(h->p) == 2 || tune_env("CIB200_MMA_GENERIC")) {
     switch (h->p.eqs[0]) {
       case 5: return launch_mma_gen_e<5>(h, bs, sc, (double *)out, st);

@@ -427,11 +427,13 @@ def test_float32_opt_in_mode(ci, oracle):
     assert rel_err(g1.eval(q1), o1.eval(q1.astype(np.float64)), _scale(o1)).max() <= TOL32
 
 
-@pytest.mark.parametrize("kernel,nq", [("b5", (1 << 22) + 77), ("b5", 40_000_003), ("b13", (1 << 22) + 5)])
-def test_float32_mode_on_the_binned_strategies(ci, oracle, kernel, nq):
+@pytest.mark.parametrize("kernel,nq,strategy", [("b5", 200_003, "cellrun"), ("b5", (1 << 22) + 77, "cellmma"), ("b5", 40_000_003, "cellmma"),
+                                                ("b13", (1 << 22) + 5, "binned")])
+def test_float32_mode_on_the_binned_strategies(ci, oracle, kernel, nq, strategy):
     """Float32 interpolants take the tile-binned strategies too (the brick is staged as floats by a FLOAT32 tensor map,
-    records and arithmetic stay double): a batch above the AUTO threshold - and, for :b5 at >= 0.5 query per cell, the
-    cell-sorted kernel - against the Float64 oracle (1e-5) and against the same interpolant's gather kernel."""
+    records and arithmetic stay double): a batch above the AUTO threshold - for :b5 the cell-run kernel from 0.5 query per
+    cell and the tensor-core kernel (float brick converted when a B fragment is loaded) from 2.5 - against the Float64
+    oracle (1e-5) and against the same interpolant's gather kernel."""
     import torch
     rng = np.random.default_rng(23)
     shape = (56, 64, 48)  # padded extents multiples of 4: Float32 TMA strides are multiples of 16 bytes
@@ -450,6 +452,7 @@ def test_float32_mode_on_the_binned_strategies(ci, oracle, kernel, nq):
     else:
         xs = [(torch.rand(nq, dtype=torch.float32, device="cuda", generator=gen) * h).clamp(0.0, h) for h in hi]
     out = itp.eval(*xs)
+    assert itp.itp.last_strategy() == strategy
     assert out.dtype == torch.float32 and bool(torch.isfinite(out).all())
     sub = slice(0, nq, max(1, nq // 200_000))
     q = [x[sub].cpu().numpy() for x in xs]
