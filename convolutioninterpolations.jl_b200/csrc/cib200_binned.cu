@@ -184,7 +184,15 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
   // private cursor per (CTA, tile): 32 k open 128-byte lines (4 MB) instead of 148 x 32 k (600 MB), so a line collects
   // its four records in L2 before it is written back.  The order of the records inside a tile then varies from run to
   // run; the value returned for a query does not depend on it.
-  const bool shared_cursors = dbg == 3;
+  const bool shared_cursors = (dbg & 3) == 3;
+  // dbg & 4 (experiment): L2 eviction hints - coordinates are streamed (evict_first), records are written evict_last so
+  // that a 128-byte line of four records stays in L2 until it is complete
+  const bool hints = dbg & 4;
+  unsigned long long pol_first = 0, pol_last = 0;
+  if (hints) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+  }
   if (!shared_cursors) {
     const unsigned *src = hist + (size_t)blockIdx.x * g.nbin;
     for (int i = threadIdx.x; i < g.nbin; i += blockDim.x) sh[i] = src[i];
@@ -201,7 +209,15 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
     for (int u = 0; u < BIN_U; ++u) {
       const long long q = qb + (long long)u * blockDim.x;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) x[u][d] = q < q1 ? (double)((const T *)c.x[d])[q] : 0.0;
+      for (int d = 0; d < 3; ++d) {
+        if (hints && sizeof(T) == 8) {
+          double v = 0.0;
+          if (q < q1) asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"((const double *)c.x[d] + q), "l"(pol_first));
+          x[u][d] = v;
+        } else {
+          x[u][d] = q < q1 ? (double)((const T *)c.x[d])[q] : 0.0;
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < BIN_U; ++u) {
@@ -215,7 +231,12 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
 #pragma unroll
           for (int d = 0; d < 3; ++d) locate_from_knot(x[u][d], k0[d], p.h[d], p.eqs[d], p.nk[d], p.knots[d], pa[d]);
           const unsigned code = ((unsigned)(pa[0].row + 100 * (pa[1].row + 100 * pa[2].row)) << 12) | lc;
-          st_record(rec + slot, pa[0].t, pa[1].t, pa[2].t, __hiloint2double((int)code, (int)(unsigned)q));
+          if (hints)
+            asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(rec + slot), "d"(pa[0].t), "d"(pa[1].t), "d"(pa[2].t),
+                         "d"(__hiloint2double((int)code, (int)(unsigned)q)), "l"(pol_last)
+                         : "memory");
+          else
+            st_record(rec + slot, pa[0].t, pa[1].t, pa[2].t, __hiloint2double((int)code, (int)(unsigned)q));
           continue;
         }
         // one 32-byte sector per query, written with one 32-byte store; the spare word carries the cell inside the tile
@@ -1147,8 +1168,9 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   CIB_LAUNCHED();
   bin_offsets_kernel<<<(g.nbin + 255) / 256, 256, 0, st>>>(g, hrows, bs->hist, bs->tile_start);
   CIB_LAUNCHED();
-  static const int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
-  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, global_hist ? 3 : scatter_mode);
+  int scatter_mode = (tune_env("CIB200_SCATTER_SHARED") && tune_env("CIB200_SCATTER_SHARED")[0] == '1') ? 3 : 0;
+  if (tune_env("CIB200_SCATTER_HINTS") && tune_env("CIB200_SCATTER_HINTS")[0] == '1') scatter_mode |= 4;
+  kscatter<<<bs->nblk, 1024, hsm, st>>>(p, g, c, nq, bs->hist, bs->rec, global_hist ? (3 | (scatter_mode & 4)) : scatter_mode);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   prof_mark(h, 1, st);
