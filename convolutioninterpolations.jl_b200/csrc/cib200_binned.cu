@@ -266,7 +266,14 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
                                                                const unsigned *__restrict__ tile_start,
                                                                unsigned *__restrict__ counter,
                                                                unsigned *__restrict__ slots,
-                                                               unsigned *__restrict__ tile_nslots) {
+                                                               unsigned *__restrict__ tile_nslots, int l2hint) {
+  // l2hint (experiment): the histogram loop reads the records' cell words with an evict_last policy, the scatter loop
+  // re-reads the records evict_first - the tile's second read should then hit L2
+  unsigned long long pol_first = 0, pol_last = 0;
+  if (l2hint) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+  }
   extern __shared__ unsigned cs_sh[];           // cellsort_smem_bytes(SLOTS)
   unsigned *hist = cs_sh;                         // [CELLS_MAX] counts, then write cursors
   unsigned *cstart = cs_sh + CELLS_MAX;           // [CELLS_MAX + 1] first record of each cell, relative to the tile (MODE > 0)
@@ -287,7 +294,14 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
-        cell[u] = r < r1 ? (__ldg((const int2 *)(rec + r) + 3).y & (CELLS_MAX - 1)) : -1;  // {idx, cell (+ table rows above bit 12)}
+        // {idx, cell (+ table rows above bit 12)}; hint: the sector is read again by the scatter loop below - keep it in L2
+        int cw = -1;
+        if (r < r1) {
+          if (l2hint) asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(cw) : "l"((const int *)(rec + r) + 7), "l"(pol_last));
+          else cw = __ldg((const int2 *)(rec + r) + 3).y;
+          cw &= CELLS_MAX - 1;
+        }
+        cell[u] = cw;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
@@ -357,7 +371,12 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned r = rb + u * 1024;
-        if (r < r1) ld_record(rec + r, a[u], b[u]);
+        if (r < r1) {
+          if (l2hint)
+            asm volatile("ld.global.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=d"(a[u].x), "=d"(a[u].y), "=d"(b[u].x), "=d"(b[u].y) : "l"(rec + r), "l"(pol_first));
+          else ld_record(rec + r, a[u], b[u]);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -963,23 +982,20 @@ template <int E, typename TC>
 static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, long long qoff, bool cellsort, int lq,
                           cudaStream_t st) {
   const ItpParams &p = h->p;
+  const int cs_hint = (tune_env("CIB200_CELLSORT_L2HINT") && tune_env("CIB200_CELLSORT_L2HINT")[0] == '1') ? 1 : 0;
   if (lq) {
     // lane-per-query kernel on (tile, cell)-sorted records (lq = 2: two queries of a cell per lane, slot list)
-    static bool attr_set = false;
-    if (!attr_set) {
-      CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(1)));
-      CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(2)));
-      attr_set = true;
-    }
+    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(1)));
+    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(2)));
     if (lq == 3)  // tensor-core kernel: group list
       bin_cellsort_kernel<2><<<bs->nblk, 1024, cellsort_smem_bytes(2), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots);
+                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
     else if (lq == 2)
       bin_cellsort_kernel<1><<<bs->nblk, 1024, cellsort_smem_bytes(1), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots);
+                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
     else
       bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, nullptr, nullptr);
+                                                                            bs->n_items + 2, nullptr, nullptr, cs_hint);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     int rc;
@@ -1005,7 +1021,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
   const int use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   if constexpr (E == 5) {
    if (cellsort && !lq) {
-    bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr);
+    bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr, cs_hint);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     auto kern = eval_cellrun_kernel<E, TC, true>;  // position records (launch_eval_binned picks the matching scatter)

@@ -567,11 +567,8 @@ template <int E, int NT>
 static int launch_mma_gen(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
   const ItpParams &p = h->p;
   auto kern = eval_cellmma_gen_kernel<E, NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  // (the attribute is per function AND device: set on every launch, a host-side call of about a microsecond)
+  CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   kern<<<bs->nblk, NT, mma_gen_smem<E>(p, NT / 32), st>>>(bs->tmap28, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots, bs->tile_start,
                                                          bs->tile_nslots, bs->items, bs->n_items, out);
   CIB_LAUNCHED();
@@ -622,11 +619,8 @@ static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cud
   const ItpParams &p = h->p;
   const size_t smem = mma_smem(p, NT / 32, sizeof(TC));
   auto kern = eval_cellmma_kernel<NT, BREG, TC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  // (the attribute is per function AND device: set on every launch, a host-side call of about a microsecond)
+  CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // (Float32: the handle's own tensor map already stages rows of 28 floats)
   kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots,
                                    bs->tile_start, bs->tile_nslots, bs->items, bs->n_items, out);

@@ -214,11 +214,8 @@ static int launch_lq(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cuda
   const ItpParams &p = h->p;
   const size_t smem = lanequery_smem_bytes(p, sizeof(TC) == 4);
   auto kern = eval_lanequery_kernel<E, QPL, NT, ZLAZY, TC>;
-  static bool attr_set = false;  // (one device per process: the attribute is per function and device)
-  if (!attr_set) {
-    CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  // (the attribute is per function AND device: set on every launch, a host-side call of about a microsecond)
+  CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   kern<<<bs->nblk, NT, smem, st>>>(bs->tmap, p, bs->g, sc, bs->rec2, bs->slots, bs->tile_start, bs->tile_nslots, bs->items,
                                    bs->n_items, out, 1);
   CIB_LAUNCHED();
