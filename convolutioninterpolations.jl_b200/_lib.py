@@ -18,7 +18,7 @@ BC_IDS = {"detect": 0, "poly": 1, "linear": 2, "quadratic": 3}
 EXTRAP_IDS = {"throw": 0, "flat": 1, "line": 2}
 SUBGRID_IDS = {"cubic": 0, "quintic": 1, "linear": 2}
 EVAL_MODES = {"auto": 0, "gather": 1, "binned": 2}
-STRATEGIES = {0: "none", 1: "gather", 2: "binned", 3: "cellrun", 4: "lanequery", 5: "cellmma"}  # cib200_strategy
+STRATEGIES = {0: "none", 1: "gather", 2: "binned", 3: "cellrun", 4: "lanequery", 5: "cellmma", 6: "cellmma_block"}  # cib200_strategy
 
 # every symbol include/cib200.h declares (tests assert the library exports all of them)
 SYMBOLS = [

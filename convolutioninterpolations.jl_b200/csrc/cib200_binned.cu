@@ -43,7 +43,7 @@ __device__ __forceinline__ int first_coef(double x, double knot0, double h, int 
   return (int)(i - eqs);
 }
 
-// bin of a query; lcell = its cell inside the tile, (cz T + cy) T + cx (0 for the spill bin)
+// bin of a query; lcell = its cell inside the tile, block-major (lcell_encode; 0 for the spill bin)
 __device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, const double *x, const double *k0,
                                         unsigned &lcell) {
   lcell = 0;
@@ -61,7 +61,7 @@ __device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, co
     c[d] = fc - t[d] * g.T;
   }
   if (!ok) return g.ntiles;
-  lcell = (unsigned)((c[2] * g.T + c[1]) * g.T + c[0]);
+  lcell = lcell_encode(c[0], c[1], c[2], g.T);
   return (t[2] * g.nt[1] + t[1]) * g.nt[0] + t[0];
 }
 
@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
 // MODE 2 (tensor-core evaluation, cib200_cellmma.cu): the GROUP LIST - one uint2 {record offset inside the tile, count}
 // per run of up to 8 consecutive records of an aligned PAIR of cells along axis 0 (cells 2p, 2p + 1 of a row: their
 // stencils share an 11-wide window), at ((uint2 *)slots)[tile_start[tile] ...], and the tile's group count.
+// MODE 3: the same with the 2 x 2 x 2 BLOCKS of the block-major cell numbering (lcell >> 3) instead of pairs - sparse
+// batches fill the 8 rows of a tensor-core product from eight cells.
 static size_t cellsort_smem_bytes(int mode) { return 4 * (size_t)(mode ? 3 * CELLS_MAX + 1 : CELLS_MAX); }
 
 template <int MODE>
@@ -318,6 +320,10 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
       if (MODE == 1) tsum2 += (v[i] + 1) >> 1;
     }
     if (MODE == 2) tsum2 = ((v[0] + v[1] + 7) >> 3) + ((v[2] + v[3] + 7) >> 3);
+    if (MODE == 3) {  // a block = the 4 cells of this thread and of its neighbour: the even lane owns it
+      const unsigned other = __shfl_xor_sync(0xffffffffu, tsum, 1);
+      tsum2 = (lane & 1) ? 0u : (tsum + other + 7) >> 3;
+    }
     unsigned inc = tsum, inc2 = tsum2;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
         sstart[tid * 2 + (i >> 1)] = run2;
         run2 += (v[i] + v[i + 1] + 7) >> 3;
       }
+      if (MODE == 3 && i == 0 && !(lane & 1)) sstart[tid >> 1] = run2;
       run += v[i];
     }
     if (MODE && tid == 1023) cstart[CELLS_MAX] = run;
@@ -389,11 +396,12 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
             const unsigned rel = pos - r0, rank = rel - cstart[cell];
             if (!(rank & 1u)) slots[r0 + sstart[cell] + (rank >> 1)] = (rel << 1) | (rel + 1 < cstart[cell + 1] ? 1u : 0u);
           }
-          if (MODE == 2) {
-            const int c0 = cell & ~1;
+          if (MODE >= 2) {
+            constexpr int BLK = MODE == 2 ? 2 : 8, BSH = MODE == 2 ? 1 : 3;
+            const int c0 = cell & ~(BLK - 1);
             const unsigned rel = pos - r0, rank = rel - cstart[c0];
             if (!(rank & 7u))
-              ((uint2 *)slots)[r0 + sstart[cell >> 1] + (rank >> 3)] = make_uint2(rel, min(8u, cstart[c0 + 2] - cstart[c0] - rank));
+              ((uint2 *)slots)[r0 + sstart[cell >> BSH] + (rank >> 3)] = make_uint2(rel, min(8u, cstart[c0 + BLK] - cstart[c0] - rank));
           }
         }
       }
@@ -738,9 +746,10 @@ __global__ void __launch_bounds__(384, 1)
           dst[0] = make_double2(hb.h00, hb.h01);
           dst[1] = make_double2(hb.h10, hb.h11);
         }
-        const unsigned T = (unsigned)g.T, cz = lc / (T * T), cy = (lc - cz * T * T) / T, cx = lc - cz * T * T - cy * T;
+        int cx, cy, cz;
+        lcell_decode(lc, (unsigned)g.T, cx, cy, cz);
         int4 m;
-        m.x = (int)cx + (int)cy * PITCH + (int)cz * PLANE;
+        m.x = cx + cy * PITCH + cz * PLANE;
         m.y = (int)rx * W;
         m.z = (int)ry * W;
         m.w = (int)rz * W;
@@ -987,7 +996,11 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
     // lane-per-query kernel on (tile, cell)-sorted records (lq = 2: two queries of a cell per lane, slot list)
     CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(1)));
     CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(2)));
-    if (lq == 3)  // tensor-core kernel: group list
+    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(3)));
+    if (lq == 4)  // tensor-core kernel on 2 x 2 x 2 cell blocks: group list per block
+      bin_cellsort_kernel<3><<<bs->nblk, 1024, cellsort_smem_bytes(3), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
+                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
+    else if (lq == 3)  // tensor-core kernel: group list
       bin_cellsort_kernel<2><<<bs->nblk, 1024, cellsort_smem_bytes(2), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
                                                                             bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
     else if (lq == 2)
@@ -999,8 +1012,10 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     int rc;
-    if constexpr (sizeof(TC) == 8) rc = lq == 3 ? launch_eval_cellmma(h, bs, sc, out, st) : launch_eval_lanequery(h, bs, sc, out, lq, st);
-    else rc = lq == 3 ? launch_eval_cellmma(h, bs, sc, out, st) : CIB200_EUNSUPPORTED;
+    if (lq == 4) rc = launch_eval_celloct(h, bs, sc, out, st);
+    else if (lq == 3) rc = launch_eval_cellmma(h, bs, sc, out, st);
+    else if constexpr (sizeof(TC) == 8) rc = launch_eval_lanequery(h, bs, sc, out, lq, st);
+    else rc = CIB200_EUNSUPPORTED;
     if (rc != CIB200_OK) return rc;
   }
   using WS = BinnedWarpSmem<E>;
@@ -1158,19 +1173,20 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     if (const char *e = tune_env("CIB200_LANEQUERY")) {
       lq = atoi(e);
       if (lq == 3 && !kind) lq = 0;
+      if (lq == 4 && kind != 1) lq = 0;
       if ((lq == 1 || lq == 2) && !(cellsort && !f32)) lq = 0;
-      if (f32 && lq != 3) lq = 0;
+      if (f32 && lq != 3 && lq != 4) lq = 0;
     }
   }
   if ((lq == 1 || lq == 2) && !(nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024)) lq = 0;
-  h->last_strategy = lq == 3 ? CIB200_STRATEGY_CELLMMA : (lq ? CIB200_STRATEGY_LANEQUERY : (cellsort ? CIB200_STRATEGY_CELLRUN : CIB200_STRATEGY_BINNED));
+  h->last_strategy = lq == 4 ? CIB200_STRATEGY_CELLMMA_BLOCK : lq == 3 ? CIB200_STRATEGY_CELLMMA : (lq ? CIB200_STRATEGY_LANEQUERY : (cellsort ? CIB200_STRATEGY_CELLRUN : CIB200_STRATEGY_BINNED));
   const bool global_hist = g.nbin > MAX_BINS;
   const int hrows = global_hist ? 1 : bs->nblk;
   const size_t hsm = global_hist ? 0 : 4 * (size_t)g.nbin;
   if (global_hist) CIB_CUDA(cudaMemsetAsync(bs->hist, 0, 4 * (size_t)g.nbin, st));
   auto kcount = f32 ? bin_count_kernel<float> : bin_count_kernel<double>;
   // (the tensor-core and the cell-run kernel read position records: table rows and fractions computed once, in the scatter pass)
-  const bool posrec = lq == 3 || (cellsort && lq == 0);
+  const bool posrec = lq == 3 || lq == 4 || (cellsort && lq == 0);
   auto kscatter = f32 ? (posrec ? bin_scatter_kernel<float, true> : bin_scatter_kernel<float, false>)
                       : (posrec ? bin_scatter_kernel<double, true> : bin_scatter_kernel<double, false>);
   CIB_CUDA(cudaFuncSetAttribute(kcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));

@@ -82,6 +82,23 @@ int launch_eval_lanequery(cib200_itp *h, BinState *bs, const Scale &sc, void *ou
 size_t cellmma_smem_bytes(const ItpParams &p);
 int cellmma_kind(const ItpParams &p, bool f32 = false);  // 0: not supported, 1: tuned :b5 kernel, 2: generic kernel (any :b width, several table pairs)
 int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st);
+int launch_eval_celloct(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st);  // 2 x 2 x 2 cell blocks (:b5, one table pair)
+
+// Cell of a query inside its tile.  Cells are numbered BLOCK-MAJOR: the tile (even side T) is cut into 2 x 2 x 2 blocks,
+// lcell = block * 8 + (cz & 1) * 4 + (cy & 1) * 2 + (cx & 1), blocks in x-fastest order.  After the cell sort the records of
+// an aligned cell pair along axis 0 (lcell >> 1) and of a whole block (lcell >> 3) are contiguous: the tensor-core kernels
+// take the rows of one product from such a pair / block.
+__device__ __forceinline__ unsigned lcell_encode(int cx, int cy, int cz, int T) {
+  const int hb = T >> 1;
+  return (unsigned)(((((cz >> 1) * hb + (cy >> 1)) * hb + (cx >> 1)) << 3) | ((cz & 1) << 2) | ((cy & 1) << 1) | (cx & 1));
+}
+__device__ __forceinline__ void lcell_decode(unsigned lc, unsigned T, int &cx, int &cy, int &cz) {
+  const unsigned hb = T >> 1, blk = lc >> 3;
+  const unsigned bz = blk / (hb * hb), by = (blk - bz * hb * hb) / hb, bx = blk - bz * hb * hb - by * hb;
+  cx = (int)(2 * bx + (lc & 1u));
+  cy = (int)(2 * by + ((lc >> 1) & 1u));
+  cz = (int)(2 * bz + ((lc >> 2) & 1u));
+}
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

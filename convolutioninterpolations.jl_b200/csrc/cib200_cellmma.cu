@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(NT, 1)
         const unsigned code = (unsigned)__double2hiint(rb.y);
         const unsigned lc = code & 4095u, rcode = code >> 12;
         const unsigned rz = rcode / 10000u, ry = (rcode - rz * 10000u) / 100u, rx = rcode - rz * 10000u - ry * 100u;
-        const int bx = lc & 15u;  // T = 16 cells per tile side (2E = 10)
-        const int m = bx + (int)((lc >> 4) & 15u) * MP + (int)(lc >> 8) * MPL;
+        int bx, by, bz;
+        lcell_decode(lc, 16u, bx, by, bz);  // T = 16 cells per tile side (2E = 10)
+        const int m = bx + by * MP + bz * MPL;
         misc[lane] = make_int4(2 * m + (bx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
       }
       if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
@@ -322,6 +323,215 @@ __global__ void __launch_bounds__(NT, 1)
   }
 }
 
+// ---- sparse batches: rows of a product from a 2 x 2 x 2 BLOCK of cells ----------------------------------------------------
+// Below ~4 queries per cell an aligned cell pair no longer fills the 8 rows of a DMMA product.  The eight cells of a block
+// of the block-major numbering share an 11 x 11 x 11 window of the brick, so the rows of one product can come from all of
+// them: K = the 11 axis-0 rows (3 steps, as before), columns = (m', n') in 0..10 x 0..10 - 121 columns in 17 tiles, 51
+// DMMAs per group, two chunks of accumulators.  A query's own stencil starts at (dx, dy, dz) in {0, 1}^3 inside the window:
+// the axis-0 shift is in its A fragments (as in the pair kernel), the other two in which weight multiplies which column in
+// the epilogue (a column outside the query's 10 x 10 range gets weight zero).  Column layout:
+//   tile t = 0..10  :  column c -> (m' = c, n' = t)
+//   tile 11 + u     :  column c -> (m' = 8 + (c & 3), n' = 2 u + (c >> 2)),  u = 0..5  (m' = 11 and n' = 11: zero)
+template <int NT, typename TC>
+__global__ void __launch_bounds__(NT, 1)
+    eval_celloct_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
+                        const Record *__restrict__ rec, const uint2 *__restrict__ groups,
+                        const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
+                        const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, TC *__restrict__ out) {
+  using WS = MmaWarpSmem;
+  constexpr int BRICKD = MELEMS * (int)sizeof(TC) / 8;  // doubles the brick occupies
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *smd = (double *)smem_raw;
+  TC *brick = (TC *)smem_raw;  // [BRICK_SIDE][BRICK_SIDE][MP], axis 0 contiguous
+  double *ptab = smd + BRICKD;
+  stage_poly_tables(p, ptab, NT);
+  constexpr int nwarps = NT >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wbase = BRICKD + mma_ptab_count(p) * PTAB_DOUBLES;
+  double *wsm = smd + wbase + warp * WS::DOUBLES;
+  double *tq = wsm;                      // [32][3]
+  int4 *misc = (int4 *)(wsm + WS::TQ);   // [32]
+  double *wq = wsm + WS::TQ + WS::MISC;  // [8][WQS]
+  unsigned long long *bar = (unsigned long long *)(smd + wbase + nwarps * WS::DOUBLES);
+  unsigned *slot = (unsigned *)(bar + 1);  // [2]
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = lane; i < WS::WQ; i += 32) wq[i] = 0.0;  // the zero pads of WX / wz are never written again
+  __syncthreads();
+  // weight role of this lane: quarter-warp = one (query, axis) pair per pass, lane = pair of taps (lanes 5..7 idle)
+  const int wquarter = lane >> 3;
+  const bool wrole = (lane & 7) < 5;
+  const int wpp = wrole ? (lane & 7) : 4;
+  const int wtab0 = BRICKD + mma_ptab_index(p, 0) * PTAB_DOUBLES + 2 * wpp;  // from smd
+  const int wtab1 = BRICKD + mma_ptab_index(p, 1) * PTAB_DOUBLES + 2 * wpp;
+  const int wtab2 = BRICKD + mma_ptab_index(p, 2) * PTAB_DOUBLES + 2 * wpp;
+  // MMA roles: A row / accumulator row q, K index / column pair r
+  const int mq = lane >> 2, mr = lane & 3;
+  // B-fragment offsets of this lane inside the window: tiles 0..9 and tiles 10..12
+  const int boff = mr + mq * MP;
+  const int boff2 = mr + (8 + (mq & 3)) * MP + (mq >> 2) * MPL;
+  const bool bk3 = mr == 3;   // K index 11 (step 2): outside the 11-wide window
+  const bool bm11 = (mq & 3) == 3;  // leftover tiles: the column slot of m' = 11
+  const unsigned total_items = n_items[0];
+  unsigned parity = 0;
+  for (unsigned iter = 0;; ++iter) {
+    if (threadIdx.x == 0) slot[iter & 1] = atomicAdd(&n_items[1], 1u);
+    __syncthreads();  // also: every warp is done with the previous brick
+    const unsigned item = slot[iter & 1];
+    if (item >= total_items) break;
+    const WorkItem it = items[item];
+    // item j of a tile covers the tile's groups [j CHUNK, (j + 1) CHUNK): a tile has at most as many groups as records
+    const unsigned r0 = tile_start[it.bin];
+    const unsigned ng = tile_ngroups[it.bin];
+    const unsigned first = min(it.start - r0, ng);
+    const unsigned cnt = min((unsigned)CHUNK_QUERIES, ng - first);
+    if (cnt == 0) continue;  // block-uniform
+    const int tx = it.bin % g.nt[0], ty = (it.bin / g.nt[0]) % g.nt[1], tz = it.bin / (g.nt[0] * g.nt[1]);
+    const int org[3] = {tx * g.T, ty * g.T, tz * g.T};
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, MELEMS * (int)sizeof(TC));
+      tma_load_3d(brick, &tmap, org[0], org[1], org[2], bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    // contiguous range of this warp, in batches of 4 groups (32 records: lane = (group, row))
+    const unsigned per = ((cnt + nwarps - 1) / nwarps + 3u) & ~3u;
+    const unsigned w0 = warp * per, w1 = min(cnt, w0 + per);
+    const uint2 *gl = groups + r0 + first;
+    const Record *rc = rec + r0;
+    const int pg = lane >> 3, prow = lane & 7;
+    uint2 ge_n = make_uint2(0u, 0u);
+    if (w0 + pg < w1) ge_n = __ldg(gl + w0 + pg);
+    for (unsigned b0 = w0; b0 < w1; b0 += 4) {
+      const int ngb = (int)min(4u, w1 - b0);
+      const uint2 ge = ge_n;
+      ge_n = make_uint2(0u, 0u);
+      if (b0 + 4 + pg < w1) ge_n = __ldg(gl + b0 + 4 + pg);
+      // ---- phase 1: one record per lane: positions into the warp's scratch ----------------------------------------
+      __syncwarp();  // the previous batch is done with tq / misc
+      if ((unsigned)prow < ge.y) {
+        // position record (bin_scatter_kernel<double, true>): {t_0, t_1, t_2, index, rows << 12 | cell in tile}
+        double2 ra, rb;
+        ld_record(rc + ge.x + prow, ra, rb);
+        tq[lane * 3 + 0] = ra.x;
+        tq[lane * 3 + 1] = ra.y;
+        tq[lane * 3 + 2] = rb.x;
+        const unsigned code = (unsigned)__double2hiint(rb.y);
+        const unsigned lc = code & 4095u, rcode = code >> 12;
+        const unsigned rz = rcode / 10000u, ry = (rcode - rz * 10000u) / 100u, rx = rcode - rz * 10000u - ry * 100u;
+        int bx, by, bz;
+        lcell_decode(lc, 16u, bx, by, bz);  // T = 16 cells per tile side (2E = 10)
+        const int m = bx + by * MP + bz * MPL;
+        misc[lane] = make_int4(m - (bx & 1) - (by & 1) * MP - (bz & 1) * MPL, (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), (int)(lc & 7u));
+      }
+      if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
+      __syncwarp();
+      for (int gi = 0; gi < ngb; ++gi) {
+        const int cntg = (int)__shfl_sync(0xffffffffu, ge.y, gi * 8);
+        const int sb = gi * 8;  // first scratch slot of the group
+        // ---- weights of the group's queries, two queries per pass: Horner on the staged cubics ----------------------
+        // one (query, axis) pair per QUARTER-warp and pass, lane = pair of taps (5 of 8 lanes): the four 16-byte loads of
+        // a quarter read one contiguous 80-byte run of a table row each - conflict-free whatever rows the other quarters
+        // need.  All loads of two passes are issued before their first store (the compiler cannot prove that the wq
+        // stores do not alias the scratch it reads, and would serialise the passes).
+        const int ncombo = 3 * cntg;
+#pragma unroll 1
+        for (int c8 = 0; c8 < ncombo; c8 += 8) {
+          double tt[2];
+          double2 c0[2], c1[2], c2[2], c3[2];
+          int dst[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int ci = min(c8 + 4 * u + wquarter, ncombo - 1);  // past the end: recompute the last pair, not stored
+            const int qq = (ci * 11) >> 5, ax = ci - 3 * qq;        // ci / 3, ci % 3 (ci < 24)
+            tt[u] = tq[(sb + qq) * 3 + ax];
+            const int row = (misc[sb + qq].y >> (10 * ax)) & 1023;
+            const double2 *pr = (const double2 *)(smd + (ax == 0 ? wtab0 : (ax == 1 ? wtab1 : wtab2)) + row * PTAB_ROW);
+            c0[u] = pr[0];
+            c1[u] = pr[5];
+            c2[u] = pr[10];
+            c3[u] = pr[15];
+            dst[u] = qq * WQS + (ax == 0 ? 2 : (ax == 1 ? 14 : 24)) + 2 * wpp;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            double2 wv;
+            wv.x = fma(tt[u], fma(tt[u], fma(tt[u], c3[u].x, c2[u].x), c1[u].x), c0[u].x);
+            wv.y = fma(tt[u], fma(tt[u], fma(tt[u], c3[u].y, c2[u].y), c1[u].y), c0[u].y);
+            if (wrole && c8 + 4 * u + wquarter < ncombo) *(double2 *)(wq + dst[u]) = wv;
+          }
+        }
+        __syncwarp();
+        // ---- the axis-0 contraction on the tensor cores ------------------------------------------------------------
+        const int win = misc[sb].x;  // brick offset of the block's first cell (the same for every record of the group)
+        const bool qv = mq < cntg;
+        const int4 mi = misc[sb + mq];
+        const int dx = mi.w & 1, dy = (mi.w >> 1) & 1, dz = (mi.w >> 2) & 1;
+        const double *wrow = wq + mq * WQS;
+        double a[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) a[s] = qv ? wrow[2 - dx + 4 * s + mr] : 0.0;
+        const TC *bb = brick + win + boff, *bc = brick + win + boff2;
+        // weights of this lane's columns: m' = 2 mr, 2 mr + 1 (regular tiles) and m' = 8 + 2 (mr & 1), + 1 (leftover tiles)
+        auto wyv = [&](int mp) { const unsigned l = (unsigned)(mp - dy); return l < 10u ? wrow[14 + l] : 0.0; };
+        auto wzv = [&](int np) { const unsigned l = (unsigned)(np - dz); return l < 10u ? wrow[24 + l] : 0.0; };
+        const double wyA = wyv(2 * mr), wyB = wyv(2 * mr + 1);
+        const double wyC = wyv(8 + 2 * (mr & 1)), wyD = wyv(9 + 2 * (mr & 1));
+        double s0 = 0.0, s1 = 0.0, v0 = 0.0, v1 = 0.0;
+        {  // chunk 1: regular tiles n' = 0..8
+          double acc[9][2];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) dmma884(acc[t][0], acc[t][1], a[s], (s == 2 && bk3) ? 0.0 : (double)bb[t * MPL + 4 * s]);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const double wz = wzv(t);
+            s0 = fma(acc[t][0], wz, s0);
+            s1 = fma(acc[t][1], wz, s1);
+          }
+        }
+        {  // chunk 2: regular tiles n' = 9, 10 and the six leftover tiles
+          double acc[8][2];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const bool kz = s == 2 && bk3;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) dmma884(acc[t][0], acc[t][1], a[s], kz ? 0.0 : (double)bb[(9 + t) * MPL + 4 * s]);
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+              dmma884(acc[2 + u][0], acc[2 + u][1], a[s], (kz || bm11 || (u == 5 && (mq >> 2))) ? 0.0 : (double)bc[2 * u * MPL + 4 * s]);
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const double wz = wzv(9 + t);
+            s0 = fma(acc[t][0], wz, s0);
+            s1 = fma(acc[t][1], wz, s1);
+          }
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {  // columns 2 mr, 2 mr + 1 of tile 11 + u: m' = 8 + 2 (mr & 1), + 1; n' = 2 u + (mr >> 1)
+            const double wz = wzv(2 * u + (mr >> 1));
+            v0 = fma(acc[2 + u][0], wz, v0);
+            v1 = fma(acc[2 + u][1], wz, v1);
+          }
+        }
+        double e = fma(s0, wyA, s1 * wyB) + fma(v0, wyC, v1 * wyD);
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        if (qv && mr == 0) out[(unsigned)mi.z] = (TC)apply_scale<3>(e, sc);
+        __syncwarp();  // wq is rewritten by the next group
+      }
+    }
+  }
+}
+
 // ---- the same kernel for every :b-series width (2E = 10 .. 18) and for interpolants with several table pairs ---------------
 // Generalisation of eval_cellmma_kernel: E is a template parameter (tile side T = 26 - 2E, K = 2E + 1 padded to 4 KS,
 // (2E)^2 columns), the weights are blended from the staged K / K' tables (no cubic tables: they would not fit next to the
@@ -430,9 +640,10 @@ __global__ void __launch_bounds__(NT, 1)
         const unsigned code = (unsigned)__double2hiint(rb.y);
         const unsigned lc = code & 4095u, rcode = code >> 12;
         const unsigned rz = rcode / 10000u, ry = (rcode - rz * 10000u) / 100u, rx = rcode - rz * 10000u - ry * 100u;
-        const unsigned cz = lc / (unsigned)(T * T), cy = (lc - cz * (unsigned)(T * T)) / (unsigned)T, cx = lc - cz * (unsigned)(T * T) - cy * (unsigned)T;
-        const int m = (int)cx + (int)cy * MP + (int)cz * MPL;
-        misc[lane] = make_int4(2 * m + (int)(cx & 1u), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
+        int cx, cy, cz;
+        lcell_decode(lc, (unsigned)T, cx, cy, cz);
+        const int m = cx + cy * MP + cz * MPL;
+        misc[lane] = make_int4(2 * m + (cx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
       }
       if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
       __syncwarp();
@@ -627,6 +838,25 @@ static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cud
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
   return CIB200_OK;
+}
+
+template <int NT, typename TC>
+static int launch_oct(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cudaStream_t st) {
+  const ItpParams &p = h->p;
+  const size_t smem = mma_smem(p, NT / 32, sizeof(TC));
+  auto kern = eval_celloct_kernel<NT, TC>;
+  CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots,
+                                   bs->tile_start, bs->tile_nslots, bs->items, bs->n_items, out);
+  CIB_LAUNCHED();
+  CIB_CUDA(cudaGetLastError());
+  return CIB200_OK;
+}
+
+// block variant (sparse batches): records sorted by (tile, block-major cell) + the group list of bin_cellsort_kernel<3>
+int launch_eval_celloct(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st) {
+  if (h->dtype == CIB200_F32) return launch_oct<512, float>(h, bs, sc, (float *)out, st);
+  return launch_oct<512, double>(h, bs, sc, (double *)out, st);
 }
 
 int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st) {

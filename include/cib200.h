@@ -255,7 +255,8 @@ typedef enum {
   CIB200_STRATEGY_BINNED = 2,    /* tile binning + eval_binned_kernel (TMA-staged bricks)                            */
   CIB200_STRATEGY_CELLRUN = 3,   /* + cell sort, eval_cellrun_kernel (register-resident stencils)                    */
   CIB200_STRATEGY_LANEQUERY = 4, /* + cell sort, eval_lanequery_kernel (experiments builds only)                     */
-  CIB200_STRATEGY_CELLMMA = 5    /* + cell sort with group list, eval_cellmma_kernel (FP64 tensor cores, DMMA)       */
+  CIB200_STRATEGY_CELLMMA = 5,   /* + cell sort with group list, eval_cellmma_kernel (FP64 tensor cores, DMMA)       */
+  CIB200_STRATEGY_CELLMMA_BLOCK = 6 /* the same with rows from 2 x 2 x 2 cell blocks, eval_celloct_kernel (sparser batches) */
 } cib200_strategy;
 int32_t cib200_itp_last_strategy(cib200_itp *handle);
 

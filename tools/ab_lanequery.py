@@ -25,7 +25,7 @@ xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in
 out = torch.empty(nq, dtype=torch.float64, device="cuda")
 itp.itp.set_profiling(True)
 ref = None
-cases = [("cellrun", "0", "0"), ("lq2 256thr", "2", "0"), ("mma 384thr breg", "3", "0"), ("mma 384thr", "3", "1"), ("mma 512thr", "3", "2"), ("mma 512thr breg", "3", "3")]
+cases = [("cellrun", "0", "0"), ("lq2 256thr", "2", "0"), ("mma 384thr breg", "3", "0"), ("mma 384thr", "3", "1"), ("mma 512thr", "3", "2"), ("mma 512thr breg", "3", "3"), ("mma blocks", "4", "0")]
 only = os.environ.get("AB_CASES")  # comma-separated case names
 reps = int(os.environ.get("AB_REPS", "3"))
 for name, lq, var in cases:
@@ -58,7 +58,8 @@ if os.environ.get("AB_SPARSE"):
             break
         q = [x[:m] for x in xs]
         row = []
-        for cs, lq in (("0", "0"), ("1", "0"), ("1", "2"), ("1", "3")):
+        ref_s = None
+        for cs, lq in (("0", "0"), ("1", "0"), ("1", "4"), ("1", "3")):
             os.environ["CIB200_BINNED_CELLSORT"] = cs
             os.environ["CIB200_LANEQUERY"] = lq
             os.environ["CIB200_LQ_VARIANT"] = "0"
@@ -69,5 +70,10 @@ if os.environ.get("AB_SPARSE"):
                 torch.cuda.synchronize()
                 ms = itp.itp.last_pass_ms()
                 best = min(best, sum(ms.values()))
+            if ref_s is None:
+                ref_s = out[:m].clone()
+            else:
+                row_err = float((out[:m] - ref_s).abs().max()) / vmax
+                assert row_err < 1e-13, (lg, cs, lq, row_err)
             row.append(best)
-        print(f"2^{lg}: eval_binned {row[0]:8.3f}   cellsort+cellrun {row[1]:8.3f}   cellsort+lq2 {row[2]:8.3f}   cellsort+mma {row[3]:8.3f}", flush=True)
+        print(f"2^{lg}: eval_binned {row[0]:8.3f}   cellsort+cellrun {row[1]:8.3f}   cellsort+mma(blocks) {row[2]:8.3f}   cellsort+mma(pairs) {row[3]:8.3f}", flush=True)
