@@ -1153,10 +1153,9 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
   if (const char *e = tune_env("CIB200_BINNED_CELLSORT")) cellsort = (e[0] == '1') && p.eqs[0] == 5 && g.T * g.T * g.T <= CELLS_MAX;
   for (int d = 0; d < 3; ++d)
     if (p.npre[d] != CIB_N_PRE) cellsort = false;  // the cell-run kernel addresses its tables inside shared memory
-  // cell-sorted strategies for Float64 :b5-width stencils (every table staged in shared memory):
-  //   >= 2.5 queries per cell: the tensor-core kernel (cib200_cellmma.cu; measured crossover with eval_cellrun_kernel on
-  //                            512^3: 2^28 queries = 2 per cell 93 vs 91 ms, 2^29 143 vs 162 ms, 10^9 228 vs 286 ms)
-  //   >= 0.5 query per cell:   eval_cellrun_kernel
+  // cell-sorted strategies for :b5-width stencils (every table staged in shared memory):
+  //   the tensor-core kernels (cib200_cellmma.cu), see below
+  //   >= 0.5 query per cell and no tensor-core kernel for this interpolant: eval_cellrun_kernel
   // the lane-per-query kernel (cib200_lanequery.cu: 195 ms per 10^9 where the tensor-core kernel takes 166) is kept for
   // experiments builds (CIB200_LANEQUERY=1|2)
   int lq = 0;
@@ -1170,6 +1169,10 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     // as the alternative (:b13 on 512^3, 2.5 10^8 queries = 1.9 per cell: 678 ms against 262 ms)
     const double dens = p.eqs[0] == 5 ? 2.5 : 1.0;
     if (kind && (double)nq >= dens * ncell) lq = 3;
+    // the tuned :b5 kernels (one table pair; Float64 and Float32): rows of a product from an aligned cell PAIR from 4.5
+    // queries per cell, from a 2 x 2 x 2 cell BLOCK from 0.4 (measured on 512^3, whole call: 2^26 queries 25.6 ms against
+    // 29.8 for the cell-run kernel, 2^28 67 against 90, 2^29 127 against 140 for pairs; 7 10^8: pairs 156 against 164)
+    if (kind == 1) lq = (double)nq >= 4.5 * ncell ? 3 : ((double)nq >= 0.4 * ncell ? 4 : 0);
     if (const char *e = tune_env("CIB200_LANEQUERY")) {
       lq = atoi(e);
       if (lq == 3 && !kind) lq = 0;
