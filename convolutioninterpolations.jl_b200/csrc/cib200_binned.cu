@@ -1169,10 +1169,11 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     // as the alternative (:b13 on 512^3, 2.5 10^8 queries = 1.9 per cell: 678 ms against 262 ms)
     const double dens = p.eqs[0] == 5 ? 2.5 : 1.0;
     if (kind && (double)nq >= dens * ncell) lq = 3;
-    // the tuned :b5 kernels (one table pair; Float64 and Float32): rows of a product from an aligned cell PAIR from 4.5
-    // queries per cell, from a 2 x 2 x 2 cell BLOCK from 0.4 (measured on 512^3, whole call: 2^26 queries 25.6 ms against
-    // 29.8 for the cell-run kernel, 2^28 67 against 90, 2^29 127 against 140 for pairs; 7 10^8: pairs 156 against 164)
-    if (kind == 1) lq = (double)nq >= 4.5 * ncell ? 3 : ((double)nq >= 0.4 * ncell ? 4 : 0);
+    // the tuned :b5 kernels (one table pair; Float64 and Float32): rows of a product from an aligned cell PAIR from 3
+    // queries per cell, from a 2 x 2 x 2 cell BLOCK from 0.4 (measured on 512^3, whole call, tools/ab_pairs_vs_blocks.py:
+    // 2 per cell pairs 77.1 / blocks 67.0 ms, 3 per cell 96.5 / 96.0, 4 per cell 122.6 / 126.2; against the cell-run kernel:
+    // 2^26 queries 25.6 against 29.8 ms, 2^28 67 against 90)
+    if (kind == 1) lq = (double)nq >= 3.0 * ncell ? 3 : ((double)nq >= 0.4 * ncell ? 4 : 0);
     if (const char *e = tune_env("CIB200_LANEQUERY")) {
       lq = atoi(e);
       if (lq == 3 && !kind) lq = 0;

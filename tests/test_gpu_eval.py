@@ -95,8 +95,8 @@ def test_c5_small_3d_b5(ci, oracle, extrap):
 
 
 def test_c5_full_grid_512_cube_2e26_queries_against_the_oracle(ci, oracle):
-    """BASELINE config 5 on its REAL grid: 512^3 :b5 through AUTO, device-resident, three densities: 6.2 10^8 + 9 uniformly
-    random queries (4.6 per cell: tile binning + cell sort with group list + the tensor-core kernel on cell pairs; 32 768
+    """BASELINE config 5 on its REAL grid: 512^3 :b5 through AUTO, device-resident, three densities: 4.2 10^8 + 9 uniformly
+    random queries (3.1 per cell: tile binning + cell sort with group list + the tensor-core kernel on cell pairs; 32 768
     tiles, u32 record offsets, ragged groups), 2^26 (0.5 per cell: the tensor-core kernel on 2 x 2 x 2 cell blocks) and
     2^22 + 5 (binned kernel without the cell sort); a strided subsample of >= 2^20 results against the oracle on the same
     grid, and every result finite."""
@@ -115,7 +115,7 @@ def test_c5_full_grid_512_cube_2e26_queries_against_the_oracle(ci, oracle):
     itp = ci.convolution_interpolation((g, g, g), v, kernel="b5", bc="poly")
     assert np.array_equal(itp.itp.coefs, o.coefs) or np.abs(itp.itp.coefs - o.coefs).max() <= 1e-13 * np.abs(o.coefs).max()
     S = _scale(o)
-    for nq, stride, strategy in ((620_000_009, 512, "cellmma"), (1 << 26, 64, "cellmma_block"), ((1 << 22) + 5, 4, "binned")):
+    for nq, stride, strategy in ((420_000_009, 256, "cellmma"), (1 << 26, 64, "cellmma_block"), ((1 << 22) + 5, 4, "binned")):
         gen = torch.Generator(device="cuda")
         gen.manual_seed(nq)
         xs = [torch.rand(nq, dtype=torch.float64, device="cuda", generator=gen) for _ in range(3)]
@@ -432,7 +432,7 @@ def test_float32_opt_in_mode(ci, oracle):
 def test_float32_mode_on_the_binned_strategies(ci, oracle, kernel, nq, strategy):
     """Float32 interpolants take the tile-binned strategies too (the brick is staged as floats by a FLOAT32 tensor map,
     records and arithmetic stay double): a batch above the AUTO threshold - for :b5 the tensor-core kernels (float brick
-    converted when a B fragment is loaded; cell blocks from 0.4 query per cell, cell pairs from 4.5) - against the Float64
+    converted when a B fragment is loaded; cell blocks from 0.4 query per cell, cell pairs from 3) - against the Float64
     oracle (1e-5) and against the same interpolant's gather kernel."""
     import torch
     rng = np.random.default_rng(23)
@@ -589,18 +589,17 @@ def test_tensor_core_strategy_against_the_oracle(ci, oracle, kw, strategy):
     rp = gb.eval(*q[:, perm])
     assert np.array_equal(rp, rb[perm])
     half = gb.eval(*np.ascontiguousarray(q[:, : nq // 2]))
+    assert gb.itp.last_strategy() == strategy and np.array_equal(half, rb[: nq // 2])
     if kw in (dict(kernel="b5"), dict(kernel="b5", derivative=(1, 1, 1), bc="detect"), dict(kernel="b5", subgrid="linear", linear_rows=101)):
-        # 3 queries per cell: the tuned :b5 kernel switches to rows from 2 x 2 x 2 cell blocks (another association: a few ulp)
+        # 2 queries per cell and fewer: the tuned :b5 kernel takes the rows of a product from 2 x 2 x 2 cell blocks (another
+        # association: a few ulp); its bits do not depend on the batch either
+        third = gb.eval(*np.ascontiguousarray(q[:, : nq // 3]))
         assert gb.itp.last_strategy() == "cellmma_block"
-        assert rel_err(half, rb[: nq // 2], scale_g).max() <= 1e-13
-        third = gb.eval(*np.ascontiguousarray(q[:, nq // 2: nq // 2 + nq // 3]))  # the block kernel: batch-independent bits
-        assert gb.itp.last_strategy() == "cellmma_block"
-        both = gb.eval(*np.ascontiguousarray(q[:, nq // 2:]))
-        assert np.array_equal(third, both[: nq // 3])
+        assert rel_err(third, rb[: nq // 3], scale_g).max() <= 1e-13
         if o is not None:
-            assert rel_err(half, o.eval(*q[:, : nq // 2]), S).max() <= TOL64
-    else:
-        assert gb.itp.last_strategy() == strategy and np.array_equal(half, rb[: nq // 2])
+            assert rel_err(third, o.eval(*q[:, : nq // 3]), S).max() <= TOL64
+        fifth = gb.eval(*np.ascontiguousarray(q[:, : nq // 5]))
+        assert gb.itp.last_strategy() == "cellmma_block" and np.array_equal(fifth, third[: nq // 5])
     # device-resident tensors through the same path
     tq = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in q]
     assert np.array_equal(gb.eval(*tq).cpu().numpy(), rb)
@@ -630,15 +629,15 @@ def test_cell_run_kernel_for_interpolants_with_several_table_pairs(ci, oracle, d
 
 def test_last_strategy_reports_the_kernel_of_the_last_call(ci):
     """cib200_itp_last_strategy: AUTO on a 128^3 :b5 grid takes the gather kernel for a small batch, the binned kernel for
-    a sparse large one, the tensor-core kernel on 2 x 2 x 2 cell blocks from 0.4 query per cell and on cell pairs from 4.5."""
+    a sparse large one, the tensor-core kernel on 2 x 2 x 2 cell blocks from 0.4 query per cell and on cell pairs from 3."""
     import torch
     rng = np.random.default_rng(12)
     n = 128
     k = tuple(np.linspace(0, 1, n) for _ in range(3))
     itp = ci.convolution_interpolation(k, _field((n, n, n), rng), bc="poly")
     ncell = (n - 1) ** 3
-    for nq, want in ((10_000, "gather"), (int(0.2 * ncell), "binned"), (int(1.0 * ncell), "cellmma_block"), (int(3.0 * ncell), "cellmma_block"),
-                     (int(5.0 * ncell), "cellmma")):
+    for nq, want in ((10_000, "gather"), (int(0.2 * ncell), "binned"), (int(1.0 * ncell), "cellmma_block"), (int(2.5 * ncell), "cellmma_block"),
+                     (int(4.0 * ncell), "cellmma")):
         q = [torch.rand(nq, dtype=torch.float64, device="cuda") for _ in range(3)]
         itp.eval(*q)
         assert itp.itp.last_strategy() == want, (nq, want, itp.itp.last_strategy())
