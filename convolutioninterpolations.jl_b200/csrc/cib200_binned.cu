@@ -1165,21 +1165,22 @@ int launch_eval_binned(cib200_itp *h, const Coords &c, void *out, long long nq, 
     for (int d = 0; d < 3; ++d)
       if (p.npre[d] != CIB_N_PRE) mma_ok = false;
     const int kind = mma_ok ? cellmma_kind(p, f32) : 0;
-    // against eval_cellrun_kernel (:b5) the crossover is 2.5 queries per cell; wider kernels only have eval_binned_kernel
-    // as the alternative (:b13 on 512^3, 2.5 10^8 queries = 1.9 per cell: 678 ms against 262 ms)
-    const double dens = p.eqs[0] == 5 ? 2.5 : 1.0;
-    if (kind && (double)nq >= dens * ncell) lq = 3;
-    // the tuned :b5 kernels (one table pair; Float64 and Float32): rows of a product from an aligned cell PAIR from 3
-    // queries per cell, from a 2 x 2 x 2 cell BLOCK from 0.4 (measured on 512^3, whole call, tools/ab_pairs_vs_blocks.py:
-    // 2 per cell pairs 77.1 / blocks 67.0 ms, 3 per cell 96.5 / 96.0, 4 per cell 122.6 / 126.2; against the cell-run kernel:
-    // 2^26 queries 25.6 against 29.8 ms, 2^28 67 against 90)
-    if (kind == 1) lq = (double)nq >= 3.0 * ncell ? 3 : ((double)nq >= 0.4 * ncell ? 4 : 0);
+    // Rows of a product from a 2 x 2 x 2 cell BLOCK from 0.4 query per cell, from an aligned cell PAIR where that is
+    // faster: the window of a block is 2E + 1 wide in both column indices ((2E + 1)^2 / (2E)^2 more DMMAs per group: 21 %
+    // for :b5, 11 % for :b13) but eight cells fill its 8 rows.  Measured on 512^3, whole call (tools/ab_pairs_vs_blocks.py,
+    // tools/ab_cellmma_gen.py): :b5 2 per cell pairs 77.1 / blocks 67.0 ms, 3 per cell 96.5 / 96.0, 4 per cell 122.6 / 126.2;
+    // :b7 1.1 per cell 104 / 73, 3.7 per cell 189 / 198; :b9 1.9 per cell 168 / 121; :b11 237 / 175; :b13 0.9 per cell
+    // 253 / 148 (binned kernel 345), 1.9: 319 / 248, 3.7: 472 / 449, 7.5: 831 / 824.  Against the cell-run kernel (:b5):
+    // 2^26 queries 25.6 against 29.8 ms, 2^28 67 against 90.
+    const double pairs_from = p.eqs[0] <= 6 ? 3.0 : (p.eqs[0] == 7 ? 5.0 : 1e300);
+    if (kind) lq = (double)nq >= pairs_from * ncell ? 3 : ((double)nq >= 0.4 * ncell ? 4 : 0);
     if (const char *e = tune_env("CIB200_LANEQUERY")) {
       lq = atoi(e);
       if (lq == 3 && !kind) lq = 0;
-      if (lq == 4 && kind != 1) lq = 0;
+      if (lq == 4 && !kind) lq = 0;
       if ((lq == 1 || lq == 2) && !(cellsort && !f32)) lq = 0;
       if (f32 && lq != 3 && lq != 4) lq = 0;
+      if (f32 && kind != 1) lq = 0;
     }
   }
   if ((lq == 1 || lq == 2) && !(nq < 0x7fffffffLL && lanequery_smem_bytes(p, false) <= 227 * 1024)) lq = 0;

@@ -539,13 +539,17 @@ __global__ void __launch_bounds__(NT, 1)
 // accumulators stay at 26 registers whatever the width.  Column layout:
 //   regular tiles  (h, n), h < MH = 2E / 8:  column c -> (m = 8 h + c, n_z = n)
 //   leftover tiles u (the ML = 2E mod 8 remaining m):  column c -> (m = 8 MH + c / NPT, n_z = NPT u + c % NPT)
-template <int E>
+// BLK: rows of a product from a 2 x 2 x 2 block of cells instead of an aligned pair (sparser batches): the window of the
+// brick is 2E + 1 wide along every axis, so the columns are (m', n') in [0, 2E + 1)^2 and a query's own 2E x 2E range starts at
+// (dy, dz) in {0, 1}^2 - its weights for columns outside that range are zero
+template <int E, bool BLK = false>
 struct MmaGeom {
   static constexpr int W = 2 * E, T = BRICK_SIDE + 1 - W;
+  static constexpr int WC = BLK ? W + 1 : W;  // extent of the column indices m, n
   static constexpr int KS = (W + 1 + 3) / 4;
-  static constexpr int MH = W / 8, ML = W % 8;
-  static constexpr int NPT = ML == 0 ? 1 : (ML <= 2 ? 4 : (ML <= 4 ? 2 : 1));
-  static constexpr int NREG = W * MH, NLEFT = ML ? (W + NPT - 1) / NPT : 0, NTILES = NREG + NLEFT;
+  static constexpr int MH = WC / 8, ML = WC % 8;
+  static constexpr int NPT = ML == 0 ? 1 : (ML <= 1 ? 8 : (ML <= 2 ? 4 : (ML <= 4 ? 2 : 1)));
+  static constexpr int NREG = WC * MH, NLEFT = ML ? (WC + NPT - 1) / NPT : 0, NTILES = NREG + NLEFT;
   static constexpr int WX_LEN = 4 * KS + 2;
   static constexpr int WY_OFF = WX_LEN, WY_LEN = (ML && NPT == 1) ? 8 * (MH + 1) : W;
   static constexpr int WZ_OFF = WY_OFF + WY_LEN, WZ_LEN = ML ? ((NPT * NLEFT + 1) & ~1) : W;
@@ -555,14 +559,14 @@ struct MmaGeom {
   static constexpr int CHUNK = 13;
 };
 
-template <int E, int NT>
+template <int E, int NT, bool BLK>
 __global__ void __launch_bounds__(NT, 1)
     eval_cellmma_gen_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
                             const Record *__restrict__ rec, const uint2 *__restrict__ groups,
                             const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
                             const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, double *__restrict__ out) {
-  using G = MmaGeom<E>;
-  constexpr int W = G::W, T = G::T, KS = G::KS, MH = G::MH, NPT = G::NPT, WQS_ = G::WQS;
+  using G = MmaGeom<E, BLK>;
+  constexpr int W = G::W, WC = G::WC, T = G::T, KS = G::KS, MH = G::MH, NPT = G::NPT, WQS_ = G::WQS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *smd = (double *)smem_raw;
   double *brick = smd;  // [BRICK_SIDE][BRICK_SIDE][MP], axis 0 contiguous
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(NT, 1)
   const int mq = lane >> 2, mr = lane & 3;
   const int boff = mr + mq * MP;                                             // regular tiles
   const int boff2 = mr + (8 * MH + mq / NPT) * MP + (mq % NPT) * MPL;        // leftover tiles
-  const bool lm_ok = 8 * MH + mq / NPT < W;                                  // leftover column has a real m
+  const bool lm_ok = 8 * MH + mq / NPT < WC;                                 // leftover column has a real m
   const unsigned total_items = n_items[0];
   unsigned parity = 0;
   for (unsigned iter = 0;; ++iter) {
@@ -643,7 +647,8 @@ __global__ void __launch_bounds__(NT, 1)
         int cx, cy, cz;
         lcell_decode(lc, (unsigned)T, cx, cy, cz);
         const int m = cx + cy * MP + cz * MPL;
-        misc[lane] = make_int4(2 * m + (cx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
+        misc[lane] = BLK ? make_int4(m - (cx & 1) - (cy & 1) * MP - (cz & 1) * MPL, (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), (int)(lc & 7u))
+                         : make_int4(2 * m + (cx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
       }
       if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
       __syncwarp();
@@ -685,19 +690,30 @@ __global__ void __launch_bounds__(NT, 1)
         __syncwarp();
         // ---- the axis-0 contraction on the tensor cores, 13 column tiles at a time ----------------------------------------
         const int mf = misc[sb].x;
-        const int win = (mf >> 1) - (mf & 1);  // brick offset of the pair's first cell
+        const int win = BLK ? mf : (mf >> 1) - (mf & 1);  // brick offset of the pair's / block's first cell
         const bool qv = mq < cntg;
         const int4 mi = misc[sb + mq];
+        const int dx = BLK ? (mi.w & 1) : (mi.x & 1), dy = BLK ? ((mi.w >> 1) & 1) : 0, dz = BLK ? ((mi.w >> 2) & 1) : 0;
         const double *wrow = wq + mq * WQS_;
+        // weight of column index m' / n' for this lane's query: its own range starts at dy / dz inside the window
+        auto wyv = [&](int mp) { const unsigned l = (unsigned)(mp - dy); return l < (unsigned)W ? wrow[G::WY_OFF + l] : 0.0; };
         double a[KS];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) a[s] = qv ? wrow[2 - (mi.x & 1) + 4 * s + mr] : 0.0;
-        double wz[W];
+        for (int s = 0; s < KS; ++s) a[s] = qv ? wrow[2 - dx + 4 * s + mr] : 0.0;
+        double wz[WC];
+        if (BLK) {
 #pragma unroll
-        for (int n = 0; n < W; n += 2) {
-          const double2 v = *(const double2 *)(wrow + G::WZ_OFF + n);
-          wz[n] = v.x;
-          wz[n + 1] = v.y;
+          for (int n = 0; n < WC; ++n) {
+            const unsigned l = (unsigned)(n - dz);
+            wz[n] = l < (unsigned)W ? wrow[G::WZ_OFF + l] : 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int n = 0; n + 1 < WC; n += 2) {
+            const double2 v = *(const double2 *)(wrow + G::WZ_OFF + n);
+            wz[n] = v.x;
+            wz[n + 1] = v.y;
+          }
         }
         double sreg[MH > 0 ? MH : 1][2], sl0 = 0.0, sl1 = 0.0;
 #pragma unroll
@@ -716,11 +732,11 @@ __global__ void __launch_bounds__(NT, 1)
             for (int t = 0; t < CH; ++t) {
               const int ti = c0 + t;
               if (ti < G::NREG) {
-                const int h = ti / W, n = ti - h * W;
+                const int h = ti / WC, n = ti - h * WC;
                 dmma884(acc[t][0], acc[t][1], a[s], kz ? 0.0 : bb[8 * h * MP + n * MPL + 4 * s]);
               } else if (ti < G::NTILES) {
                 const int u = ti - G::NREG;
-                const bool z = kz || !lm_ok || NPT * u + (mq % NPT) >= W;
+                const bool z = kz || !lm_ok || NPT * u + (mq % NPT) >= WC;
                 dmma884(acc[t][0], acc[t][1], a[s], z ? 0.0 : bc[NPT * u * MPL + 4 * s]);
               }
             }
@@ -730,7 +746,7 @@ __global__ void __launch_bounds__(NT, 1)
           for (int t = 0; t < CH; ++t) {
             const int ti = c0 + t;
             if (ti < G::NREG) {
-              const int h = ti / W, n = ti - h * W;
+              const int h = ti / WC, n = ti - h * WC;
               sreg[h][0] = fma(acc[t][0], wz[n], sreg[h][0]);
               sreg[h][1] = fma(acc[t][1], wz[n], sreg[h][1]);
             } else if (ti < G::NTILES) {
@@ -738,6 +754,11 @@ __global__ void __launch_bounds__(NT, 1)
               if (NPT == 1) {  // columns (m = 8 MH + 2c, 2c + 1; n_z = u)
                 sl0 = fma(acc[t][0], wz[u], sl0);
                 sl1 = fma(acc[t][1], wz[u], sl1);
+              } else if (BLK) {  // columns (m = 8 MH + 2c / NPT; n_z = NPT u + (2c) % NPT, + 1): dynamic n_z, predicated
+                const int n0 = NPT * u + ((2 * mr) % NPT);
+                const unsigned l0 = (unsigned)(n0 - dz), l1 = (unsigned)(n0 + 1 - dz);
+                sl0 = fma(acc[t][0], l0 < (unsigned)W ? wrow[G::WZ_OFF + l0] : 0.0, sl0);
+                sl0 = fma(acc[t][1], l1 < (unsigned)W ? wrow[G::WZ_OFF + l1] : 0.0, sl0);
               } else {  // columns (m = 8 MH + 2c / NPT; n_z = NPT u + (2c) % NPT, + 1)
                 const double2 v = *(const double2 *)(wrow + G::WZ_OFF + NPT * u + ((2 * mr) % NPT));
                 sl0 = fma(acc[t][0], v.x, sl0);
@@ -749,11 +770,18 @@ __global__ void __launch_bounds__(NT, 1)
         double e = 0.0;
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
-          const double2 wy = *(const double2 *)(wrow + G::WY_OFF + 8 * h + 2 * mr);
-          e += fma(sreg[h][0], wy.x, sreg[h][1] * wy.y);
+          if (BLK) {
+            e += fma(sreg[h][0], wyv(8 * h + 2 * mr), sreg[h][1] * wyv(8 * h + 2 * mr + 1));
+          } else {
+            const double2 wy = *(const double2 *)(wrow + G::WY_OFF + 8 * h + 2 * mr);
+            e += fma(sreg[h][0], wy.x, sreg[h][1] * wy.y);
+          }
         }
         if (G::ML) {
-          if (NPT == 1) {
+          if (BLK) {
+            if (NPT == 1) e += fma(sl0, wyv(8 * MH + 2 * mr), sl1 * wyv(8 * MH + 2 * mr + 1));
+            else e += sl0 * wyv(8 * MH + (2 * mr) / NPT);
+          } else if (NPT == 1) {
             const double2 wy = *(const double2 *)(wrow + G::WY_OFF + 8 * MH + 2 * mr);
             e += fma(sl0, wy.x, sl1 * wy.y);
           } else {
@@ -771,13 +799,14 @@ __global__ void __launch_bounds__(NT, 1)
 
 template <int E>
 static size_t mma_gen_smem(const ItpParams &p, int nwarps) {
-  return 8 * ((size_t)MELEMS + (size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nwarps * MmaGeom<E>::WARP_DOUBLES + 2 + 96);
+  constexpr int wd = MmaGeom<E, false>::WARP_DOUBLES > MmaGeom<E, true>::WARP_DOUBLES ? MmaGeom<E, false>::WARP_DOUBLES : MmaGeom<E, true>::WARP_DOUBLES;
+  return 8 * ((size_t)MELEMS + (size_t)((tables_smem_doubles(p) + 1) & ~1) + (size_t)nwarps * wd + 2 + 96);
 }
 
-template <int E, int NT>
+template <int E, int NT, bool BLK>
 static int launch_mma_gen(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
   const ItpParams &p = h->p;
-  auto kern = eval_cellmma_gen_kernel<E, NT>;
+  auto kern = eval_cellmma_gen_kernel<E, NT, BLK>;
   // (the attribute is per function AND device: set on every launch, a host-side call of about a microsecond)
   CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   kern<<<bs->nblk, NT, mma_gen_smem<E>(p, NT / 32), st>>>(bs->tmap28, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots, bs->tile_start,
@@ -794,12 +823,12 @@ static int mma_gen_threads(const ItpParams &p) {
     if (mma_gen_smem<E>(p, nt / 32) <= 227 * 1024) return nt;
   return 0;
 }
-template <int E>
+template <int E, bool BLK>
 static int launch_mma_gen_e(cib200_itp *h, BinState *bs, const Scale &sc, double *out, cudaStream_t st) {
   switch (mma_gen_threads<E>(h->p)) {
-    case 512: return launch_mma_gen<E, 512>(h, bs, sc, out, st);
-    case 384: return launch_mma_gen<E, 384>(h, bs, sc, out, st);
-    case 256: return launch_mma_gen<E, 256>(h, bs, sc, out, st);
+    case 512: return launch_mma_gen<E, 512, BLK>(h, bs, sc, out, st);
+    case 384: return launch_mma_gen<E, 384, BLK>(h, bs, sc, out, st);
+    case 256: return launch_mma_gen<E, 256, BLK>(h, bs, sc, out, st);
   }
   set_error("tensor-core strategy: shared memory budget exceeded");
   return CIB200_EUNSUPPORTED;
@@ -855,6 +884,17 @@ static int launch_oct(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cud
 
 // block variant (sparse batches): records sorted by (tile, block-major cell) + the group list of bin_cellsort_kernel<3>
 int launch_eval_celloct(cib200_itp *h, BinState *bs, const Scale &sc, void *out, cudaStream_t st) {
+  if (cellmma_kind(h->p, h->dtype == CIB200_F32) == 2) {  // generic kernel (any :b width, several table pairs), Float64
+    switch (h->p.eqs[0]) {
+      case 5: return launch_mma_gen_e<5, true>(h, bs, sc, (double *)out, st);
+      case 6: return launch_mma_gen_e<6, true>(h, bs, sc, (double *)out, st);
+      case 7: return launch_mma_gen_e<7, true>(h, bs, sc, (double *)out, st);
+      case 8: return launch_mma_gen_e<8, true>(h, bs, sc, (double *)out, st);
+      case 9: return launch_mma_gen_e<9, true>(h, bs, sc, (double *)out, st);
+    }
+    set_error("tensor-core strategy: unsupported kernel width");
+    return CIB200_EUNSUPPORTED;
+  }
   if (h->dtype == CIB200_F32) return launch_oct<512, float>(h, bs, sc, (float *)out, st);
   return launch_oct<512, double>(h, bs, sc, (double *)out, st);
 }
@@ -863,11 +903,11 @@ int launch_eval_cellmma(cib200_itp *h, BinState *bs, const Scale &sc, void *out,
   if (h->dtype == CIB200_F32) return launch_mma<512, false, float>(h, bs, sc, (float *)out, st);
   if (cellmma_kind(h->p) == 2 || tune_env("CIB200_MMA_GENERIC")) {
     switch (h->p.eqs[0]) {
-      case 5: return launch_mma_gen_e<5>(h, bs, sc, (double *)out, st);
-      case 6: return launch_mma_gen_e<6>(h, bs, sc, (double *)out, st);
-      case 7: return launch_mma_gen_e<7>(h, bs, sc, (double *)out, st);
-      case 8: return launch_mma_gen_e<8>(h, bs, sc, (double *)out, st);
-      case 9: return launch_mma_gen_e<9>(h, bs, sc, (double *)out, st);
+      case 5: return launch_mma_gen_e<5, false>(h, bs, sc, (double *)out, st);
+      case 6: return launch_mma_gen_e<6, false>(h, bs, sc, (double *)out, st);
+      case 7: return launch_mma_gen_e<7, false>(h, bs, sc, (double *)out, st);
+      case 8: return launch_mma_gen_e<8, false>(h, bs, sc, (double *)out, st);
+      case 9: return launch_mma_gen_e<9, false>(h, bs, sc, (double *)out, st);
     }
     set_error("tensor-core strategy: unsupported kernel width");
     return CIB200_EUNSUPPORTED;

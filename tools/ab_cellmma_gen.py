@@ -36,15 +36,20 @@ def run(itp, nq, env):
     return best
 
 
-for kw, nq in ((dict(kernel="b5"), NQ), (dict(kernel="b5", derivative=(1, 0, 0)), NQ), (dict(kernel="b7"), 500_000_000),
-               (dict(kernel="b13"), 250_000_000), (dict(kernel="b13"), 1_000_000_000)):
+for kw, nq in ((dict(kernel="b5", derivative=(1, 0, 0)), NQ), (dict(kernel="b5", derivative=(1, 0, 0)), 250_000_000), (dict(kernel="b7"), 500_000_000),
+               (dict(kernel="b7"), 150_000_000), (dict(kernel="b9"), 250_000_000), (dict(kernel="b11"), 250_000_000),
+               (dict(kernel="b13"), 125_000_000), (dict(kernel="b13"), 250_000_000), (dict(kernel="b13"), 500_000_000), (dict(kernel="b13"), 1_000_000_000)):
     itp = ci.convolution_interpolation(knots, vals, bc="poly", eval_mode="binned", **kw)
     itp.itp.set_profiling(True)
     auto = run(itp, nq, {})
     ref = out[:1 << 20].clone()
     alt = run(itp, nq, {"CIB200_LANEQUERY": "0"})
     d = float((out[:1 << 20] - ref).abs().max() / ref.abs().max())
-    line = f"{kw} nq {nq:.1e}: default {auto[2]} {auto[0]:8.2f} ms (kernel {auto[1]:8.2f})   without the tensor-core kernel {alt[2]} {alt[0]:8.2f} ms (kernel {alt[1]:8.2f})  max rel diff {d:.1e}"
+    prs = run(itp, nq, {"CIB200_LANEQUERY": "3"})
+    blk = run(itp, nq, {"CIB200_LANEQUERY": "4"})
+    d2 = float((out[:1 << 20] - ref).abs().max() / ref.abs().max())
+    line = (f"{kw} nq {nq:.1e}: default {auto[2]} {auto[0]:8.2f} ms (kernel {auto[1]:8.2f})   without the tensor-core kernel {alt[2]} {alt[0]:8.2f} ms "
+            f"(kernel {alt[1]:8.2f})  max rel diff {d:.1e}   pairs {prs[0]:8.2f}   blocks {blk[2]} {blk[0]:8.2f} (diff {d2:.1e})")
     if kw == dict(kernel="b5"):
         g = run(itp, nq, {"CIB200_MMA_GENERIC": "1"})
         line += f"   generic kernel forced: {g[0]:8.2f} ms (kernel {g[1]:8.2f})"
