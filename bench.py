@@ -553,9 +553,9 @@ def main():
         kernel_ms = passes["eval_kernel"]  # the dominant kernel's own launch, CUDA events inside the library
         achieved = BYTES_PER_EVAL * nq / (kernel_ms * 1e-3) / 1e9
         traffic = ncu_traffic_per_eval()
-        cellrun = strategy in ("cellrun", "cellmma")
+        cellrun = strategy in ("cellrun", "cellmma", "cellmma_block")
         tr = (traffic or {}).get(strategy, {})
-        kname = {"cellmma": "eval_cellmma_kernel<512,false>", "cellrun": "eval_cellrun_kernel<5>", "binned": "eval_binned_kernel<5>",
+        kname = {"cellmma": "eval_cellmma_kernel<512,false>", "cellmma_block": "eval_celloct_kernel<512>", "cellrun": "eval_cellrun_kernel<5>", "binned": "eval_binned_kernel<5>",
                  "lanequery": "eval_lanequery_kernel<5,2>"}.get(strategy, "eval_warp3d_kernel<double,5>")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": tr.get("dram_bytes_per_eval") and tr["dram_bytes_per_eval"] * nq,
@@ -578,7 +578,7 @@ def main():
                     "smem_wavefronts_per_eval": tr.get("smem_wavefronts_per_eval"),
                     "smem_frac": tr.get("l1tex_throughput_pct") and tr["l1tex_throughput_pct"] / 100.0,
                     "bound_by": ("shared-memory return path (l1tex) and the FP64 pipe (DMMA + DFMA) together; DRAM is at dram_frac"
-                                 if strategy == "cellmma" else
+                                 if strategy in ("cellmma", "cellmma_block") else
                                  "shared-memory bandwidth (l1tex), then the FP64 pipe; DRAM is at dram_frac" if cellrun else None)}
         cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
