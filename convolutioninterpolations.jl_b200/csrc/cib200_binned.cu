@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(1024, 1) bin_scatter_kernel(ItpParams p, BinGe
 // stencils share an 11-wide window), at ((uint2 *)slots)[tile_start[tile] ...], and the tile's group count.
 // MODE 3: the same with the 2 x 2 x 2 BLOCKS of the block-major cell numbering (lcell >> 3) instead of pairs - sparse
 // batches fill the 8 rows of a tensor-core product from eight cells.
-static size_t cellsort_smem_bytes(int mode) { return 4 * (size_t)(mode ? 3 * CELLS_MAX + 1 : CELLS_MAX); }
+static constexpr int CELLSORT_NIDS = 65536;  // cell ids kept in shared memory in the permutation mode (128 KB)
+static size_t cellsort_smem_bytes(int mode, bool perm = false) {
+  return 4 * (size_t)(mode ? 3 * CELLS_MAX + 2 : CELLS_MAX) + (perm ? 2 * (size_t)CELLSORT_NIDS : 0);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const Record *__restrict__ rec,
@@ -268,7 +271,13 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
                                                                const unsigned *__restrict__ tile_start,
                                                                unsigned *__restrict__ counter,
                                                                unsigned *__restrict__ slots,
-                                                               unsigned *__restrict__ tile_nslots, int l2hint) {
+                                                               unsigned *__restrict__ tile_nslots, int l2hint,
+                                                               unsigned *__restrict__ perm, int nids) {
+  // perm != nullptr (tensor-core kernels): the records are NOT moved - the pass writes the permutation
+  // perm[sorted position] = record offset inside the tile (4 bytes per record instead of 32 read + 32 written) and the
+  // evaluation kernel gathers the 32-byte records of a group through it (whole sectors, inside the tile's 1-MB region).
+  // The cell ids of up to `nids` records of the tile stay in shared memory between the two loops (u16), so a record's
+  // sector is read once.
   // l2hint (experiment): the histogram loop reads the records' cell words with an evict_last policy, the scatter loop
   // re-reads the records evict_first - the tile's second read should then hit L2
   unsigned long long pol_first = 0, pol_last = 0;
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
   unsigned *hist = cs_sh;                         // [CELLS_MAX] counts, then write cursors
   unsigned *cstart = cs_sh + CELLS_MAX;           // [CELLS_MAX + 1] first record of each cell, relative to the tile (MODE > 0)
   unsigned *sstart = cs_sh + 2 * CELLS_MAX + 1;   // first slot of each cell (MODE 1) / first group of each cell pair (MODE 2)
+  unsigned short *ids = (unsigned short *)(cs_sh + 3 * CELLS_MAX + 2);  // [nids] cell ids of the tile's records (perm mode)
   __shared__ unsigned wsum[32], wsum2[32];
   __shared__ unsigned s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -302,6 +312,7 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
           if (l2hint) asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(cw) : "l"((const int *)(rec + r) + 7), "l"(pol_last));
           else cw = __ldg((const int2 *)(rec + r) + 3).y;
           cw &= CELLS_MAX - 1;
+          if (perm && r - r0 < (unsigned)nids) ids[r - r0] = (unsigned short)cw;
         }
         cell[u] = cw;
       }
@@ -373,6 +384,21 @@ __global__ void __launch_bounds__(1024, 1) bin_cellsort_kernel(BinGeom g, const 
     }
     if (MODE && tid == 1023) cstart[CELLS_MAX] = run;
     __syncthreads();
+    if (perm) {
+      for (unsigned r = r0 + tid; r < r1; r += 1024) {
+        const unsigned rel_in = r - r0;
+        const int cell = rel_in < (unsigned)nids ? (int)ids[rel_in] : (__ldg((const int2 *)(rec + r) + 3).y & (CELLS_MAX - 1));
+        const unsigned pos = atomicAdd(&hist[cell], 1u);
+        perm[pos] = rel_in;
+        if (MODE >= 2) {
+          constexpr int BLK = MODE == 2 ? 2 : 8, BSH = MODE == 2 ? 1 : 3;
+          const int c0 = cell & ~(BLK - 1);
+          const unsigned rel = pos - r0, rank = rel - cstart[c0];
+          if (!(rank & 7u))
+            ((uint2 *)slots)[r0 + sstart[cell >> BSH] + (rank >> 3)] = make_uint2(rel, min(8u, cstart[c0 + BLK] - cstart[c0] - rank));
+        }
+      }
+    } else
     for (unsigned rb = r0 + tid; rb < r1; rb += 4 * 1024) {
       double2 a[4], b[4];
 #pragma unroll
@@ -995,20 +1021,24 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
   if (lq) {
     // lane-per-query kernel on (tile, cell)-sorted records (lq = 2: two queries of a cell per lane, slot list)
     CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(1)));
-    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(2)));
-    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(3)));
+    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(2, true)));
+    CIB_CUDA(cudaFuncSetAttribute(bin_cellsort_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cellsort_smem_bytes(3, true)));
+    // (tensor-core kernels: the cell sort writes a permutation into the second record array's memory, records stay put)
+    const bool use_perm = !(tune_env("CIB200_CELLSORT_PERM") && tune_env("CIB200_CELLSORT_PERM")[0] == '0');
+    unsigned *permp = (use_perm && lq >= 3) ? (unsigned *)bs->rec2 : nullptr;
+    bs->perm = permp;
     if (lq == 4)  // tensor-core kernel on 2 x 2 x 2 cell blocks: group list per block
-      bin_cellsort_kernel<3><<<bs->nblk, 1024, cellsort_smem_bytes(3), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
+      bin_cellsort_kernel<3><<<bs->nblk, 1024, cellsort_smem_bytes(3, use_perm), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2,
+                                                                                      bs->slots, bs->tile_nslots, cs_hint, permp, CELLSORT_NIDS);
     else if (lq == 3)  // tensor-core kernel: group list
-      bin_cellsort_kernel<2><<<bs->nblk, 1024, cellsort_smem_bytes(2), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
+      bin_cellsort_kernel<2><<<bs->nblk, 1024, cellsort_smem_bytes(2, use_perm), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2,
+                                                                                      bs->slots, bs->tile_nslots, cs_hint, permp, CELLSORT_NIDS);
     else if (lq == 2)
       bin_cellsort_kernel<1><<<bs->nblk, 1024, cellsort_smem_bytes(1), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint);
+                                                                            bs->n_items + 2, bs->slots, bs->tile_nslots, cs_hint, nullptr, 0);
     else
       bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start,
-                                                                            bs->n_items + 2, nullptr, nullptr, cs_hint);
+                                                                            bs->n_items + 2, nullptr, nullptr, cs_hint, nullptr, 0);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     int rc;
@@ -1036,7 +1066,7 @@ static int launch_pass_cd(cib200_itp *h, BinState *bs, const Scale &sc, TC *out,
   const int use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   if constexpr (E == 5) {
    if (cellsort && !lq) {
-    bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr, cs_hint);
+    bin_cellsort_kernel<0><<<bs->nblk, 1024, cellsort_smem_bytes(0), st>>>(bs->g, bs->rec, bs->rec2, bs->tile_start, bs->n_items + 2, nullptr, nullptr, cs_hint, nullptr, 0);
     CIB_LAUNCHED();
     prof_mark(h, 2, st);
     auto kern = eval_cellrun_kernel<E, TC, true>;  // position records (launch_eval_binned picks the matching scatter)

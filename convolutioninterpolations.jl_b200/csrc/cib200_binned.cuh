@@ -70,6 +70,7 @@ struct BinState {
   size_t max_items;
   unsigned *slots;        // [nq] slot list (u32) of the lane-per-query kernel / group list (uint2) of the tensor-core kernel
   unsigned *tile_nslots;  // [nbin] slots / groups of each tile
+  unsigned *perm;         // tensor-core kernels: sorted position -> record offset in the tile (nullptr: records were moved to rec2)
   CUtensorMap tmap28;     // the same coefficient array with brick rows of 28 elements (tensor-core kernel, Float64)
   int tmap28_valid;
 };

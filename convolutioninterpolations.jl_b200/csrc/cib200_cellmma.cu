@@ -101,7 +101,7 @@ __device__ __forceinline__ void stage_poly_tables(const ItpParams &p, double *pt
 template <int NT, bool BREG, typename TC>
 __global__ void __launch_bounds__(NT, 1)
     eval_cellmma_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
-                        const Record *__restrict__ rec, const uint2 *__restrict__ groups,
+                        const Record *__restrict__ rec, const unsigned *__restrict__ perm, const uint2 *__restrict__ groups,
                         const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
                         const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, TC *__restrict__ out) {
   using WS = MmaWarpSmem;
@@ -169,8 +169,13 @@ __global__ void __launch_bounds__(NT, 1)
     const uint2 *gl = groups + r0 + first;
     const Record *rc = rec + r0;
     const int pg = lane >> 3, prow = lane & 7;
-    uint2 ge_n = make_uint2(0u, 0u);
+    // group entries are fetched two batches ahead, the permutation entry of a record one batch ahead, and the record itself
+    // is pulled into L2 while the previous batch is being evaluated: three dependent loads, none of them waited for
+    uint2 ge_n = make_uint2(0u, 0u), ge_nn = make_uint2(0u, 0u);
     if (w0 + pg < w1) ge_n = __ldg(gl + w0 + pg);
+    if (w0 + 4 + pg < w1) ge_nn = __ldg(gl + w0 + 4 + pg);
+    unsigned pv_n = 0;
+    if (perm && (unsigned)prow < ge_n.y) pv_n = __ldg(perm + r0 + ge_n.x + prow);
     int curwin = -1;
     double breg[39];
 #pragma unroll
@@ -178,14 +183,19 @@ __global__ void __launch_bounds__(NT, 1)
     for (unsigned b0 = w0; b0 < w1; b0 += 4) {
       const int ngb = (int)min(4u, w1 - b0);
       const uint2 ge = ge_n;
-      ge_n = make_uint2(0u, 0u);
-      if (b0 + 4 + pg < w1) ge_n = __ldg(gl + b0 + 4 + pg);
+      const unsigned pv = pv_n;
+      ge_n = ge_nn;
+      ge_nn = make_uint2(0u, 0u);
+      if (b0 + 8 + pg < w1) ge_nn = __ldg(gl + b0 + 8 + pg);
+      pv_n = 0;
+      if (perm && (unsigned)prow < ge_n.y) pv_n = __ldg(perm + r0 + ge_n.x + prow);
       // ---- phase 1: one record per lane: positions into the warp's scratch ----------------------------------------
       __syncwarp();  // the previous batch is done with tq / misc
       if ((unsigned)prow < ge.y) {
         // position record (bin_scatter_kernel<double, true>): {t_0, t_1, t_2, index, rows << 12 | cell in tile}
         double2 ra, rb;
-        ld_record(rc + ge.x + prow, ra, rb);
+        // (perm: the cell sort left the records where the scatter pass put them and wrote the sorted order as indices)
+        ld_record(rc + (perm ? pv : ge.x + prow), ra, rb);
         tq[lane * 3 + 0] = ra.x;
         tq[lane * 3 + 1] = ra.y;
         tq[lane * 3 + 2] = rb.x;
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(NT, 1)
         const int m = bx + by * MP + bz * MPL;
         misc[lane] = make_int4(2 * m + (bx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
       }
-      if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
+      if (!perm && ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
       __syncwarp();
       for (int gi = 0; gi < ngb; ++gi) {
         const int cntg = (int)__shfl_sync(0xffffffffu, ge.y, gi * 8);
@@ -319,6 +329,7 @@ __global__ void __launch_bounds__(NT, 1)
         if (qv && mr == 0) out[(unsigned)mi.z] = (TC)apply_scale<3>(e, sc);
         __syncwarp();  // wq is rewritten by the next group
       }
+      if (perm && (unsigned)prow < ge_n.y) prefetch_l2(rc + pv_n);  // the next batch's record (its index arrived long ago)
     }
   }
 }
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(NT, 1)
 template <int NT, typename TC>
 __global__ void __launch_bounds__(NT, 1)
     eval_celloct_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
-                        const Record *__restrict__ rec, const uint2 *__restrict__ groups,
+                        const Record *__restrict__ rec, const unsigned *__restrict__ perm, const uint2 *__restrict__ groups,
                         const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
                         const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, TC *__restrict__ out) {
   using WS = MmaWarpSmem;
@@ -403,19 +414,29 @@ __global__ void __launch_bounds__(NT, 1)
     const uint2 *gl = groups + r0 + first;
     const Record *rc = rec + r0;
     const int pg = lane >> 3, prow = lane & 7;
-    uint2 ge_n = make_uint2(0u, 0u);
+    // group entries are fetched two batches ahead, the permutation entry of a record one batch ahead, and the record itself
+    // is pulled into L2 while the previous batch is being evaluated: three dependent loads, none of them waited for
+    uint2 ge_n = make_uint2(0u, 0u), ge_nn = make_uint2(0u, 0u);
     if (w0 + pg < w1) ge_n = __ldg(gl + w0 + pg);
+    if (w0 + 4 + pg < w1) ge_nn = __ldg(gl + w0 + 4 + pg);
+    unsigned pv_n = 0;
+    if (perm && (unsigned)prow < ge_n.y) pv_n = __ldg(perm + r0 + ge_n.x + prow);
     for (unsigned b0 = w0; b0 < w1; b0 += 4) {
       const int ngb = (int)min(4u, w1 - b0);
       const uint2 ge = ge_n;
-      ge_n = make_uint2(0u, 0u);
-      if (b0 + 4 + pg < w1) ge_n = __ldg(gl + b0 + 4 + pg);
+      const unsigned pv = pv_n;
+      ge_n = ge_nn;
+      ge_nn = make_uint2(0u, 0u);
+      if (b0 + 8 + pg < w1) ge_nn = __ldg(gl + b0 + 8 + pg);
+      pv_n = 0;
+      if (perm && (unsigned)prow < ge_n.y) pv_n = __ldg(perm + r0 + ge_n.x + prow);
       // ---- phase 1: one record per lane: positions into the warp's scratch ----------------------------------------
       __syncwarp();  // the previous batch is done with tq / misc
       if ((unsigned)prow < ge.y) {
         // position record (bin_scatter_kernel<double, true>): {t_0, t_1, t_2, index, rows << 12 | cell in tile}
         double2 ra, rb;
-        ld_record(rc + ge.x + prow, ra, rb);
+        // (perm: the cell sort left the records where the scatter pass put them and wrote the sorted order as indices)
+        ld_record(rc + (perm ? pv : ge.x + prow), ra, rb);
         tq[lane * 3 + 0] = ra.x;
         tq[lane * 3 + 1] = ra.y;
         tq[lane * 3 + 2] = rb.x;
@@ -427,7 +448,7 @@ __global__ void __launch_bounds__(NT, 1)
         const int m = bx + by * MP + bz * MPL;
         misc[lane] = make_int4(m - (bx & 1) - (by & 1) * MP - (bz & 1) * MPL, (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), (int)(lc & 7u));
       }
-      if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
+      if (!perm && ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
       __syncwarp();
       for (int gi = 0; gi < ngb; ++gi) {
         const int cntg = (int)__shfl_sync(0xffffffffu, ge.y, gi * 8);
@@ -528,6 +549,7 @@ __global__ void __launch_bounds__(NT, 1)
         if (qv && mr == 0) out[(unsigned)mi.z] = (TC)apply_scale<3>(e, sc);
         __syncwarp();  // wq is rewritten by the next group
       }
+      if (perm && (unsigned)prow < ge_n.y) prefetch_l2(rc + pv_n);  // the next batch's record (its index arrived long ago)
     }
   }
 }
@@ -562,7 +584,7 @@ struct MmaGeom {
 template <int E, int NT, bool BLK>
 __global__ void __launch_bounds__(NT, 1)
     eval_cellmma_gen_kernel(const __grid_constant__ CUtensorMap tmap, ItpParams p, BinGeom g, Scale sc,
-                            const Record *__restrict__ rec, const uint2 *__restrict__ groups,
+                            const Record *__restrict__ rec, const unsigned *__restrict__ perm, const uint2 *__restrict__ groups,
                             const unsigned *__restrict__ tile_start, const unsigned *__restrict__ tile_ngroups,
                             const WorkItem *__restrict__ items, unsigned *__restrict__ n_items, double *__restrict__ out) {
   using G = MmaGeom<E, BLK>;
@@ -627,17 +649,27 @@ __global__ void __launch_bounds__(NT, 1)
     const uint2 *gl = groups + r0 + first;
     const Record *rc = rec + r0;
     const int pg = lane >> 3, prow = lane & 7;
-    uint2 ge_n = make_uint2(0u, 0u);
+    // group entries are fetched two batches ahead, the permutation entry of a record one batch ahead, and the record itself
+    // is pulled into L2 while the previous batch is being evaluated: three dependent loads, none of them waited for
+    uint2 ge_n = make_uint2(0u, 0u), ge_nn = make_uint2(0u, 0u);
     if (w0 + pg < w1) ge_n = __ldg(gl + w0 + pg);
+    if (w0 + 4 + pg < w1) ge_nn = __ldg(gl + w0 + 4 + pg);
+    unsigned pv_n = 0;
+    if (perm && (unsigned)prow < ge_n.y) pv_n = __ldg(perm + r0 + ge_n.x + prow);
     for (unsigned b0 = w0; b0 < w1; b0 += 4) {
       const int ngb = (int)min(4u, w1 - b0);
       const uint2 ge = ge_n;
-      ge_n = make_uint2(0u, 0u);
-      if (b0 + 4 + pg < w1) ge_n = __ldg(gl + b0 + 4 + pg);
+      const unsigned pv = pv_n;
+      ge_n = ge_nn;
+      ge_nn = make_uint2(0u, 0u);
+      if (b0 + 8 + pg < w1) ge_nn = __ldg(gl + b0 + 8 + pg);
+      pv_n = 0;
+      if (perm && (unsigned)prow < ge_n.y) pv_n = __ldg(perm + r0 + ge_n.x + prow);
       __syncwarp();  // the previous batch is done with tq / misc
       if ((unsigned)prow < ge.y) {
         double2 ra, rb;
-        ld_record(rc + ge.x + prow, ra, rb);
+        // (perm: the cell sort left the records where the scatter pass put them and wrote the sorted order as indices)
+        ld_record(rc + (perm ? pv : ge.x + prow), ra, rb);
         tq[lane * 3 + 0] = ra.x;
         tq[lane * 3 + 1] = ra.y;
         tq[lane * 3 + 2] = rb.x;
@@ -650,7 +682,7 @@ __global__ void __launch_bounds__(NT, 1)
         misc[lane] = BLK ? make_int4(m - (cx & 1) - (cy & 1) * MP - (cz & 1) * MPL, (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), (int)(lc & 7u))
                          : make_int4(2 * m + (cx & 1), (int)(rx | (ry << 10) | (rz << 20)), __double2loint(rb.y), 0);
       }
-      if (ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
+      if (!perm && ge_n.y) prefetch_l2(rc + ge_n.x + min((unsigned)prow, ge_n.y - 1));
       __syncwarp();
       for (int gi = 0; gi < ngb; ++gi) {
         const int cntg = (int)__shfl_sync(0xffffffffu, ge.y, gi * 8);
@@ -793,6 +825,7 @@ __global__ void __launch_bounds__(NT, 1)
         if (qv && mr == 0) out[(unsigned)mi.z] = apply_scale<3>(e, sc);
         __syncwarp();  // wq is rewritten by the next group
       }
+      if (perm && (unsigned)prow < ge_n.y) prefetch_l2(rc + pv_n);  // the next batch's record (its index arrived long ago)
     }
   }
 }
@@ -809,7 +842,7 @@ static int launch_mma_gen(cib200_itp *h, BinState *bs, const Scale &sc, double *
   auto kern = eval_cellmma_gen_kernel<E, NT, BLK>;
   // (the attribute is per function AND device: set on every launch, a host-side call of about a microsecond)
   CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  kern<<<bs->nblk, NT, mma_gen_smem<E>(p, NT / 32), st>>>(bs->tmap28, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots, bs->tile_start,
+  kern<<<bs->nblk, NT, mma_gen_smem<E>(p, NT / 32), st>>>(bs->tmap28, p, bs->g, sc, bs->perm ? bs->rec : bs->rec2, bs->perm, (const uint2 *)bs->slots, bs->tile_start,
                                                          bs->tile_nslots, bs->items, bs->n_items, out);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
@@ -862,7 +895,7 @@ static int launch_mma(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cud
   // (the attribute is per function AND device: set on every launch, a host-side call of about a microsecond)
   CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // (Float32: the handle's own tensor map already stages rows of 28 floats)
-  kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots,
+  kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->perm ? bs->rec : bs->rec2, bs->perm, (const uint2 *)bs->slots,
                                    bs->tile_start, bs->tile_nslots, bs->items, bs->n_items, out);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());
@@ -875,7 +908,7 @@ static int launch_oct(cib200_itp *h, BinState *bs, const Scale &sc, TC *out, cud
   const size_t smem = mma_smem(p, NT / 32, sizeof(TC));
   auto kern = eval_celloct_kernel<NT, TC>;
   CIB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->rec2, (const uint2 *)bs->slots,
+  kern<<<bs->nblk, NT, smem, st>>>(sizeof(TC) == 8 ? bs->tmap28 : bs->tmap, p, bs->g, sc, bs->perm ? bs->rec : bs->rec2, bs->perm, (const uint2 *)bs->slots,
                                    bs->tile_start, bs->tile_nslots, bs->items, bs->n_items, out);
   CIB_LAUNCHED();
   CIB_CUDA(cudaGetLastError());

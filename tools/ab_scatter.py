@@ -21,8 +21,8 @@ out = torch.empty(nq, dtype=torch.float64, device="cuda")
 itp.itp.set_profiling(True)
 ref = None
 for env in ({}, {"CIB200_SCATTER_SHARED": "1"}, {"CIB200_SCATTER_HINTS": "1"}, {"CIB200_SCATTER_SHARED": "1", "CIB200_SCATTER_HINTS": "1"},
-            {"CIB200_CELLSORT_L2HINT": "1"}, {}):
-    for k in ("CIB200_SCATTER_SHARED", "CIB200_SCATTER_HINTS", "CIB200_CELLSORT_L2HINT"):
+            {"CIB200_CELLSORT_L2HINT": "1"}, {"CIB200_CELLSORT_PERM": "0"}, {}):
+    for k in ("CIB200_SCATTER_SHARED", "CIB200_SCATTER_HINTS", "CIB200_CELLSORT_L2HINT", "CIB200_CELLSORT_PERM"):
         os.environ.pop(k, None)
     os.environ.update(env)
     best = None
