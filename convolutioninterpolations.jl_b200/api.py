@@ -519,7 +519,12 @@ class ConvolutionExtrapolation:
         self.et = et
 
     # -- itp.(xs, ys, zs): element-wise over equally shaped coordinate arrays --------------------
-    def eval(self, *xs, out=None):
+    def eval(self, *xs, out=None, check_finite=False):
+        """itp.(xs...).  numpy arrays (host buffers): synchronous, a NaN / Inf coordinate raises InexactError and - with
+        extrap=Throw - a query outside the domain DomainError, as the reference does.  CUDA torch tensors: the call is
+        stream-ordered and returns without a host synchronisation; with extrap=Throw the status is fetched (and raised) as
+        for host buffers, with Flat / Line a NaN / Inf coordinate yields NaN in the result unless `check_finite=True` asks the
+        library to fetch the status word (one synchronisation) and raise like the host path."""
         itp = self.itp
         if len(xs) != itp.ndim:
             raise ValueError(f"expected {itp.ndim} coordinate arrays, got {len(xs)}")
@@ -538,7 +543,8 @@ class ConvolutionExtrapolation:
             if out is None:
                 out = torch.empty(shape, dtype=tdt, device=xs[0].device)
             ptrs = (C.c_void_p * itp.ndim)(*[x.data_ptr() for x in xs])
-            check(itp._entry("eval")(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE, _stream_ptr(xs[0]), None))
+            check(itp._entry("eval")(itp._handle, nq, ptrs, C.c_void_p(out.data_ptr()), _lib.DEVICE, _stream_ptr(xs[0]),
+                                     C.byref(bad) if check_finite else None))
             return out
         ndt = _np_dtype(itp.dtype_id)
         xs = np.broadcast_arrays(*[np.asarray(x, dtype=ndt) for x in xs])

@@ -631,6 +631,21 @@ def test_interpolants_with_several_table_pairs_at_one_query_per_cell(ci, oracle,
     assert rel_err(out.cpu().numpy(), ref, _scale(o)).max() <= (TOL64 if dtype == np.float64 else TOL32)
 
 
+def test_device_tensors_check_finite_option(ci):
+    """CUDA tensors with extrap=Flat: a NaN coordinate yields NaN without a host synchronisation, and raises InexactError
+    like the host-buffer path when the caller asks for the status word (check_finite=True)."""
+    import torch
+    rng = np.random.default_rng(3)
+    k = tuple(np.linspace(0, 1, 24) for _ in range(3))
+    itp = ci.convolution_interpolation(k, _field((24, 24, 24), rng), extrap="flat")
+    q = [torch.rand(5000, dtype=torch.float64, device="cuda") for _ in range(3)]
+    q[1][1234] = float("nan")
+    out = itp.eval(*q)
+    assert bool(torch.isnan(out[1234])) and int(torch.isnan(out).sum()) == 1
+    with pytest.raises(ci.InexactError, match="query 1234 "):
+        itp.eval(*q, check_finite=True)
+
+
 def test_last_strategy_reports_the_kernel_of_the_last_call(ci):
     """cib200_itp_last_strategy: AUTO on a 128^3 :b5 grid takes the gather kernel for a small batch, the binned kernel for
     a sparse large one, the tensor-core kernel on 2 x 2 x 2 cell blocks from 0.4 query per cell and on cell pairs from 3."""
