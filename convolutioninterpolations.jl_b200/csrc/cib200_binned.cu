@@ -57,7 +57,7 @@ __device__ __forceinline__ int classify(const ItpParams &p, const BinGeom &g, co
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const int fc = first_coef(x[d], k0[d], p.h[d], p.eqs[d], p.nk[d], ok);
-    t[d] = fc / g.T;
+    t[d] = g.T == 16 ? fc >> 4 : (g.T == 8 ? fc >> 3 : fc / g.T);  // (:b5 / :b13 tiles: no integer division)
     c[d] = fc - t[d] * g.T;
   }
   if (!ok) return g.ntiles;
