@@ -11,8 +11,9 @@ import bench  # noqa: E402
 import convitp_b200 as ci  # noqa: E402
 
 nq = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
+kernel = sys.argv[2] if len(sys.argv) > 2 else "b5"
 knots, vals = bench.make_grid(512)
-itp = ci.convolution_interpolation(knots, vals, kernel="b5", bc="poly")
+itp = ci.convolution_interpolation(knots, vals, kernel=kernel, bc="poly")
 del vals
 gen = torch.Generator(device="cuda")
 gen.manual_seed(bench.SEED)
