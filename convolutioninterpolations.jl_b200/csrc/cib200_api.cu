@@ -879,19 +879,31 @@ static int32_t eval_common_locked(cib200_itp *h, const Coords &c_in, long long n
   const bool stage_out = is_pageable(out);
   const bool staged = stage_in || stage_out;
   int chunk_log2 = nq >= (1LL << 28) ? 26 : (nq >= (1LL << 27) ? 25 : 24);
-  if (staged) chunk_log2 = std::min(chunk_log2, 24);  // 3 x 2^24 x 32 B = 1.5 GB of pinned memory at most
+  // pageable buffers go through the handle's pinned ring: 2^24-query chunks (1.5 GB of pinned memory), 2^26 for batches of
+  // 2^27 queries and more (6.4 GB: the chunks are then dense enough for the cell-sorted kernels - measured on 512^3 b5,
+  // 5 10^8 queries: 1.10e9 -> 1.42e9 evals/s, tools/ab_pageable_chunk.py); falls back to 2^24 when that much cannot be pinned
+  if (staged) chunk_log2 = nq >= (1LL << 27) ? 26 : 24;
   if (const char *e = tune_env("CIB200_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(30, atoi(e)));
   std::vector<long long> sizes;
-  for (long long rem = nq; rem > 0;) {
-    const long long m = std::min(rem, 1LL << chunk_log2);
-    sizes.push_back(m);
-    rem -= m;
-  }
   long long chunk = 0;
-  for (long long m : sizes) chunk = std::max(chunk, m);
-  // per buffer: nd coordinate chunks + 1 result chunk
-  if ((rc = ensure_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
-  if (staged && (rc = ensure_host_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
+  for (;;) {
+    sizes.clear();
+    for (long long rem = nq; rem > 0;) {
+      const long long m = std::min(rem, 1LL << chunk_log2);
+      sizes.push_back(m);
+      rem -= m;
+    }
+    chunk = 0;
+    for (long long m : sizes) chunk = std::max(chunk, m);
+    // per buffer: nd coordinate chunks + 1 result chunk
+    if ((rc = ensure_stage(h, es * (size_t)chunk * (size_t)(nd + 1)))) return rc;
+    if (!staged) break;
+    rc = ensure_host_stage(h, es * (size_t)chunk * (size_t)(nd + 1));
+    if (rc == CIB200_OK) break;
+    if (chunk_log2 <= 24) return rc;
+    cudaGetLastError();
+    chunk_log2 = 24;
+  }
   s_in = h->streams[0];
   s_comp = h->streams[1];
   s_out = h->streams[2];
